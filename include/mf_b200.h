@@ -1,0 +1,165 @@
+/*
+ * mf_b200.h -- C ABI of libmf_b200.so: the B200-native (sm_100a) audio -> face-frame hot path
+ * that sits behind Caxson/mere-fusion's BaseReal / BaseASR plugin surface.
+ *
+ * Conventions:
+ *   - extern "C", plain pointers and sizes, no C++ / torch types;
+ *   - every function returns 0 on success or a negative MF_E_* code, never throws;
+ *     mf_last_error() gives the message for the last failure on that context;
+ *   - unless stated otherwise every data pointer is a DEVICE pointer owned by the caller
+ *     (e.g. torch tensor .data_ptr()); pointers documented "host" are host memory;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued asynchronously on it, with
+ *     no hidden synchronisation (mf_*_load are the exception: they synchronise once);
+ *   - the library owns only its context: weights, workspaces and per-session state (the ErNeRF
+ *     audio-feature EMA); one mf_ctx per (GPU, session); contexts are independent, a single
+ *     context is not thread-safe.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef MF_B200_H
+#define MF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MF_ABI_VERSION 1
+
+#define MF_OK 0
+#define MF_E_INVALID -1     /* bad argument / shape */
+#define MF_E_CUDA -2        /* a CUDA runtime call failed */
+#define MF_E_STATE -3       /* weights for this head not loaded */
+#define MF_E_UNSUPPORTED -4 /* configuration outside what the kernels implement */
+
+typedef struct mf_ctx mf_ctx;
+
+int mf_version(void);
+/* one context per (GPU, session).  Fails with MF_E_CUDA when no sm_100 device is present:
+ * there is no CPU fallback. */
+int mf_create(int device, mf_ctx **out);
+void mf_destroy(mf_ctx *ctx);
+const char *mf_last_error(const mf_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * ErNeRF, kernel level: drop-in equivalents of the reference's pybind functions, same argument
+ * order and meaning, at::Tensor replaced by device pointers.  Outputs are pre-allocated by the
+ * caller exactly as the reference's Python wrappers do.
+ * ------------------------------------------------------------------------------------------ */
+
+/* ernerf/raymarching/src/raymarching.h:7  near_far_from_aabb (kernel raymarching.cu:91-145) */
+int mf_near_far_from_aabb(mf_ctx *ctx, const float *rays_o, const float *rays_d, const float *aabb,
+                          uint32_t N, float min_near, float *nears, float *fars, void *stream);
+
+/* ernerf/raymarching/src/raymarching.h:19  march_rays (kernel raymarching.cu:827-929).
+ * xyzs/dirs/deltas must be zero-filled by the caller (raymarching/raymarching.py:383-385).
+ * noises may be NULL (= zeros, perturb=False). */
+int mf_march_rays(mf_ctx *ctx, uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive,
+                  const float *rays_t, const float *rays_o, const float *rays_d, float bound,
+                  float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *grid,
+                  const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                  const float *noises, void *stream);
+
+/* ernerf/raymarching/src/raymarching.h:37  composite_rays_triplane (kernel raymarching.cu:2141-2249).
+ * ambs_aud / ambs_eye / uncertainties and their *_sum outputs may be NULL (unused by the live
+ * path). */
+int mf_composite_rays_triplane(mf_ctx *ctx, uint32_t n_alive, uint32_t n_step, float T_thresh,
+                               int32_t *rays_alive, float *rays_t, const float *sigmas,
+                               const float *rgbs, const float *deltas, const float *ambs_aud,
+                               const float *ambs_eye, const float *uncertainties,
+                               float *weights_sum, float *depth, float *image, float *amb_aud_sum,
+                               float *amb_eye_sum, float *uncertainty_sum, void *stream);
+
+/* ernerf/gridencoder/src/gridencoder.h:12  grid_encode_forward, D = 2 (kernel gridencoder.cu:75-175).
+ * embeddings_is_half: 0 = fp32 table + fp32 outputs, 1 = fp16 table + fp16 outputs (the torso
+ * encoder under autocast).  outputs is [L, B, C] like the reference kernel's. */
+int mf_grid_encode_forward(mf_ctx *ctx, const float *inputs, const void *embeddings,
+                           const int32_t *offsets, void *outputs, uint32_t B, uint32_t D,
+                           uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                           int align_corners, int embeddings_is_half, void *stream);
+
+/* ernerf/shencoder/src/shencoder.h:9  sh_encode_forward, degree C = 4 (kernel shencoder.cu:27-68) */
+int mf_sh_encode_forward(mf_ctx *ctx, const float *inputs, float *outputs, uint32_t B, uint32_t D,
+                         uint32_t C, void *stream);
+
+/* ernerf/freqencoder/src/freqencoder.h:7  freq_encode_forward (kernel freqencoder.cu:30-58) */
+int mf_freq_encode_forward(mf_ctx *ctx, const float *inputs, uint32_t B, uint32_t D, uint32_t deg,
+                           uint32_t C, float *outputs, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ErNeRF, frame level: the fused render that replaces
+ *   NeRFReal.test_step -> Trainer.test_gui_with_data -> NeRFRenderer.run_cuda + run_torso
+ *   (nerfreal.py:70-127, ernerf/nerf_triplane/utils.py:1191-1223, renderer.py:158-352).
+ * ------------------------------------------------------------------------------------------ */
+
+#define MF_ERNERF_HEAD_LEVELS 12
+#define MF_ERNERF_TORSO_LEVELS 16
+
+/* host struct.  Mirrors what reaches run_cuda through **vars(opt) (utils.py:949-950). */
+typedef struct mf_ernerf_cfg {
+    float bound;                /* opt.bound (1) */
+    float min_near;             /* opt.min_near (0.05) */
+    float dt_gamma;             /* opt.dt_gamma (1/256) */
+    float T_thresh;             /* run_cuda default 1e-4 */
+    float density_thresh_torso; /* min(opt.density_thresh_torso, mean_density_torso), renderer.py:325 */
+    float torso_shrink;         /* opt.torso_shrink (0.8) */
+    uint32_t max_steps;         /* opt.max_steps (16) */
+    uint32_t cascade;           /* 1 + ceil(log2(bound)); only 1 is supported */
+    uint32_t grid_size;         /* 128 */
+    uint32_t smooth_lips;       /* opt.smooth_lips: EMA of the audio feature, renderer.py:190-194 */
+    float head_log2_scale;      /* S = log2(per_level_scale) of encoder_xy/yz/xz (grid.py:31) */
+    uint32_t head_base;         /* 64 */
+    int32_t head_offsets[MF_ERNERF_HEAD_LEVELS + 1];
+    float torso_log2_scale;
+    uint32_t torso_base;        /* 16 */
+    int32_t torso_offsets[MF_ERNERF_TORSO_LEVELS + 1];
+    uint32_t audio_in_dim;      /* 44 for the esperanto wav2vec2 head (network.py:104-111) */
+} mf_ernerf_cfg;
+
+/* `blob` is the DEVICE-resident packed checkpoint produced by
+ * mere_fusion_b200.ernerf_pack.pack_ernerf (so a torch.distributed-broadcast tensor can be
+ * handed over directly).  The blob must stay alive until mf_destroy. */
+int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, const mf_ernerf_cfg *cfg /*host*/);
+
+typedef struct mf_ernerf_frame {
+    const float *pose;       /* host, [4,4] row-major cam2world after nerf_matrix_to_ngp (provider.py:19-26) */
+    float fx, fy, cx, cy;    /* intrinsics (provider.py:263-270) */
+    int32_t H, W;            /* render size: rays are the H*W pixel centres (utils.py:255-341) */
+    const float *auds;       /* device, [8, audio_in_dim, 16] attention window (nerfasr.py:75-103) */
+    const float *enc_a;      /* device or NULL: [32] pre-encoded audio feature; skips encode_audio and
+                                the EMA state so frames can be rendered out of order */
+    float eye;               /* eye area (provider.py:240-253) */
+    const void *bg_color;    /* device or NULL: fp16 [H*W,3]; NULL = white (opt.bg_img default) */
+    const float *rays_o;     /* device or NULL: explicit rays [N,3] (then N = n_rays, and */
+    const float *rays_d;     /*   bg_coords [N,2] must be given too) instead of the pixel grid */
+    const float *bg_coords;
+    int32_t n_rays;
+    int32_t outH, outW;      /* output size: bilinear resize, utils.py:1212; ignored for explicit rays */
+    float *out_image_f32;    /* device or NULL: [outH,outW,3] fp32 in [0,1] (what test_gui_with_data returns) */
+} mf_ernerf_frame;
+
+/* optional observability for the parity tests (all device pointers, any may be NULL) */
+typedef struct mf_ernerf_debug {
+    float *nears, *fars;     /* [N] */
+    int32_t *round_info;     /* [17*4] per round: n_alive, n_step, samples emitted, 0 */
+    float *weights_sum;      /* [N] */
+    float *image_head;       /* [N,3] composited head before background */
+    float *enc_a;            /* [32] the (smoothed) audio feature used */
+    uint8_t *torso_mask;     /* [N] */
+} mf_ernerf_debug;
+
+/* out_rgb: device u8 [outH,outW,3] RGB = (image*255) truncated (nerfreal.py:110). */
+int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *frame /*host*/, uint8_t *out_rgb,
+                     const mf_ernerf_debug *dbg /*host, nullable*/, void *stream);
+/* forget the audio-feature EMA (a new session on a reused context) */
+int mf_ernerf_reset_state(mf_ctx *ctx);
+/* kernels launched by the last mf_ernerf_render on this context */
+int mf_ernerf_last_launches(const mf_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MF_B200_H */

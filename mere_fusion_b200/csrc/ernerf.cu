@@ -1,0 +1,1343 @@
+// ernerf.cu -- sm_100a ErNeRF frame renderer behind the C ABI of include/mf_b200.h.
+//
+// Replaces, per frame, the ~400 launches + <=16 host syncs of the reference's
+// NeRFRenderer.run_cuda / run_torso (ernerf/nerf_triplane/renderer.py:158-352) by
+//   k_setup         1 CTA   : AudioNet + AudioAttNet + EMA (network.py:9-66,222-237), the
+//                             per-frame torso constants, and the round counters
+//   k_head          persistent cooperative kernel, one grid barrier per march round:
+//                   ray generation (utils.py:255-341) -> near/far (raymarching.cu:91-145) ->
+//                   march (raymarching.cu:827-929) -> tri-plane hash-grid gather
+//                   (gridencoder.cu:75-175) -> SH (shencoder.cu:27-68) -> aud_ch_att / eye_att /
+//                   sigma / color MLPs (network.py:249-308) on warp-level tensor-core tiles ->
+//                   composite (raymarching.cu:2141-2249) -> warp-aggregated alive-ray compaction
+//                   (renderer.py:266), all in registers / shared memory
+//   k_torso_compose torso occupancy + deformation + tiled grid + MLPs (network.py:166-201,
+//                   renderer.py:294-352), background blend, clamp, optional fp32 / u8 output
+//   k_resize_u8     bilinear resize (utils.py:1212) + u8 (nerfreal.py:110) when sizes differ
+//
+// Round semantics are the reference's: round r marches every alive ray n_step =
+// clamp(N / n_alive, 1, 8) samples, and the loop ends when the summed n_step reaches max_steps;
+// the alive count is a global quantity, hence the grid barrier between rounds.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "ernerf_device.cuh"
+#include "ernerf_layout.h"
+
+namespace cg = cooperative_groups;
+using namespace ernerf;
+
+#define ER_MAX_ROUNDS 16
+#define ER_CTR_STRIDE 32 /* ints per counter row */
+// counters layout (ints): [0] n_alive[r], [1] tile ticket[r], [2] samples emitted[r], [3] n_step[r]
+
+struct HeadLevels { GridLevel lv[MF_ERNERF_HEAD_LEVELS]; };
+struct TorsoLevels { GridLevel lv[MF_ERNERF_TORSO_LEVELS]; };
+
+struct FrameGeom {
+    int N, H, W;
+    float R[9], T[3];
+    float inv_fx, inv_fy, cx, cy;
+    const float *rays_o, *rays_d, *bg_coords;  // nullable: explicit rays
+    float inv_Hm1, inv_Wm1;
+};
+
+struct ErnerfState {
+    mf_ernerf_cfg cfg;
+    // blob views
+    const float *planes = nullptr;
+    uint32_t plane_rows = 0;
+    const uint8_t *bitfield = nullptr;
+    const __half2 *torso_table = nullptr;
+    const float *torso_density = nullptr;
+    const __half *head_mlp = nullptr, *torso_mlp = nullptr, *audio = nullptr, *torso_const = nullptr;
+    const float *misc = nullptr;
+    HeadLevels hl;
+    TorsoLevels tl;
+    // persistent device state
+    float *state = nullptr;  // [0..31] enc_a (smoothed), [32] has_prev flag, [64..95] bias_def, [96..127] bias_tor
+    int *counters = nullptr; // [ER_MAX_ROUNDS+1][ER_CTR_STRIDE]
+    // per-N workspace
+    int capN = 0;
+    int *alive[2] = {nullptr, nullptr};
+    float *rays_t = nullptr, *fars = nullptr, *nears = nullptr, *weights_sum = nullptr, *image = nullptr;
+    float *final_f32 = nullptr;  // [N,3] when a resize follows
+    int head_grid = 0;
+    int last_launches = 0;
+    float misc_host[24] = {0};  // anchor_points[12], individual_codes[0], individual_codes_torso[0]
+};
+
+// =========================================================================================
+// load-time: level scales on the device (same exp2f as the reference kernel)
+// =========================================================================================
+__global__ void k_level_scales(float S, uint32_t H, int L, float *out) {
+    const uint32_t level = threadIdx.x;
+    if ((int)level < L) out[level] = exp2f(level * S) * H - 1.0f;
+}
+
+static void fill_levels(GridLevel *lv, int L, const float *scales, const int32_t *offsets, uint32_t gridtype) {
+    for (int l = 0; l < L; l++) {
+        GridLevel g;
+        g.scale = scales[l];
+        const uint32_t resolution = (uint32_t)std::ceil(scales[l]) + 1;
+        g.stride1 = resolution + 1;
+        g.offset = (uint32_t)offsets[l];
+        g.size = (uint32_t)(offsets[l + 1] - offsets[l]);
+        // get_grid_index (gridencoder.cu:54-72): d = 0 always contributes; d = 1 iff stride <= size
+        uint32_t stride = g.stride1;
+        uint32_t mode = 0;
+        if (stride <= g.size) {
+            mode |= 1u;
+            stride *= g.stride1;
+        }
+        if (gridtype == 0 && stride > g.size) mode |= 2u;
+        if ((g.size & (g.size - 1)) == 0) mode |= 4u;
+        g.mode = mode;
+        lv[l] = g;
+    }
+}
+
+// =========================================================================================
+// k_setup: audio encoder + per-frame constants
+// =========================================================================================
+struct SetupParams {
+    const float *auds;        // [8, A, 16] or null
+    const float *enc_a_in;    // [32] or null
+    const __half *audio;      // weights image
+    const __half *torso_const;
+    const float *misc;
+    float *state;
+    int *counters;
+    int A;
+    int N;
+    int smooth;
+    float wa[6];              // wrapped anchor (fp16-rounded), network.py:175-176
+    float *dbg_enc_a;
+};
+
+__device__ __forceinline__ float lrelu16(float v16) { return v16 > 0.f ? v16 : round_half(v16 * 0.02f); }
+
+// nn.Conv1d(k=3) under autocast on a [B, Cin, T] activation held in shared memory as fp16 values
+__device__ void conv1d_k3(const float *x, float *y, const __half *W, const __half *b, int B, int Cin, int T, int Cout,
+                          int stride) {
+    const int To = (T + 2 - 3) / stride + 1;
+    for (int o = threadIdx.x; o < B * Cout * To; o += blockDim.x) {
+        const int t = o % To, co = (o / To) % Cout, bb = o / (To * Cout);
+        float acc = 0.f;
+        for (int c = 0; c < Cin; c++) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int ti = t * stride + k - 1;
+                if (ti >= 0 && ti < T) acc = fmaf(__half2float(W[(co * Cin + c) * 3 + k]), x[(bb * Cin + c) * T + ti], acc);
+            }
+        }
+        y[(bb * Cout + co) * To + t] = lrelu16(round_half(acc + __half2float(b[co])));
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_setup(SetupParams p) {
+    __shared__ float bufA[8 * 64 * 16];  // activations (values already rounded to fp16)
+    __shared__ float bufB[8 * 32 * 8];
+    __shared__ float enc[8 * 32];
+    __shared__ float att[8];
+    __shared__ float anchor[42];
+    const int tid = threadIdx.x;
+
+    // counters: round 0 has all N rays alive (renderer.py:240-241)
+    for (int i = tid; i < (ER_MAX_ROUNDS + 1) * ER_CTR_STRIDE; i += blockDim.x) p.counters[i] = 0;
+    __syncthreads();
+    if (tid == 0) p.counters[0] = p.N;
+
+    // per-frame torso constants: enc_anchor = freq(wrapped_anchor, deg 3) (network.py:177), then the
+    // contribution of [enc_anchor(42) | ind_code_torso(8)] to the first layer of both torso MLPs
+    if (tid < 42) anchor[tid] = freq_elem(p.wa, 6, tid);
+    __syncthreads();
+    if (tid < 64) {
+        const int which = tid / 32, n = tid % 32;
+        const __half *Wc = p.torso_const + (which * 32 + n) * 50;
+        float acc = 0.f;
+        for (int k = 0; k < 42; k++) acc = fmaf(__half2float(Wc[k]), round_half(anchor[k]), acc);
+        for (int k = 0; k < 8; k++) acc = fmaf(__half2float(Wc[42 + k]), round_half(p.misc[16 + k]), acc);
+        p.state[64 + which * 32 + n] = acc;
+    }
+
+    if (p.enc_a_in) {  // pre-encoded feature: no EMA, no state update
+        if (tid < 32) {
+            p.state[tid] = p.enc_a_in[tid];
+            if (p.dbg_enc_a) p.dbg_enc_a[tid] = p.enc_a_in[tid];
+        }
+        return;
+    }
+
+    // ---- AudioNet (network.py:40-66): x[:, :, 0:16] -> 4x conv(k3,s2,p1)+LeakyReLU -> fc
+    const int A = p.A;
+    const __half *w = p.audio;
+    for (int i = tid; i < 8 * A * 16; i += blockDim.x) bufA[i] = round_half(p.auds[i]);
+    __syncthreads();
+    conv1d_k3(bufA, bufB, w, w + 32 * A * 3, 8, A, 16, 32, 2);  w += 32 * A * 3 + 32;
+    conv1d_k3(bufB, bufA, w, w + 32 * 32 * 3, 8, 32, 8, 32, 2);  w += 32 * 32 * 3 + 32;
+    conv1d_k3(bufA, bufB, w, w + 64 * 32 * 3, 8, 32, 4, 64, 2);  w += 64 * 32 * 3 + 64;
+    conv1d_k3(bufB, bufA, w, w + 64 * 64 * 3, 8, 64, 2, 64, 2);  w += 64 * 64 * 3 + 64;
+    // bufA: [8][64] ; fc1.0 64->64 + LeakyReLU
+    for (int o = tid; o < 8 * 64; o += blockDim.x) {
+        const int n = o % 64, bb = o / 64;
+        float acc = 0.f;
+        for (int k = 0; k < 64; k++) acc = fmaf(__half2float(w[n * 64 + k]), bufA[bb * 64 + k], acc);
+        bufB[o] = lrelu16(round_half(acc + __half2float(w[64 * 64 + n])));
+    }
+    __syncthreads();
+    w += 64 * 64 + 64;
+    for (int o = tid; o < 8 * 32; o += blockDim.x) {  // fc1.2 64->32
+        const int n = o % 32, bb = o / 32;
+        float acc = 0.f;
+        for (int k = 0; k < 64; k++) acc = fmaf(__half2float(w[n * 64 + k]), bufB[bb * 64 + k], acc);
+        enc[o] = round_half(acc + __half2float(w[32 * 64 + n]));
+    }
+    __syncthreads();
+    w += 32 * 64 + 32;
+    // ---- AudioAttNet (network.py:9-36): y = enc^T [1, 32, 8] -> 5x conv(k3,s1,p1)+LeakyReLU -> Linear(8,8) -> softmax
+    for (int i = tid; i < 32 * 8; i += blockDim.x) bufA[i] = enc[(i % 8) * 32 + i / 8];
+    __syncthreads();
+    conv1d_k3(bufA, bufB, w, w + 16 * 32 * 3, 1, 32, 8, 16, 1);  w += 16 * 32 * 3 + 16;
+    conv1d_k3(bufB, bufA, w, w + 8 * 16 * 3, 1, 16, 8, 8, 1);    w += 8 * 16 * 3 + 8;
+    conv1d_k3(bufA, bufB, w, w + 4 * 8 * 3, 1, 8, 8, 4, 1);      w += 4 * 8 * 3 + 4;
+    conv1d_k3(bufB, bufA, w, w + 2 * 4 * 3, 1, 4, 8, 2, 1);      w += 2 * 4 * 3 + 2;
+    conv1d_k3(bufA, bufB, w, w + 1 * 2 * 3, 1, 2, 8, 1, 1);      w += 1 * 2 * 3 + 1;
+    if (tid < 8) {
+        float acc = 0.f;
+        for (int k = 0; k < 8; k++) acc = fmaf(__half2float(w[tid * 8 + k]), bufB[k], acc);
+        att[tid] = round_half(acc + __half2float(w[64 + tid]));
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float mx = att[0];
+        for (int k = 1; k < 8; k++) mx = fmaxf(mx, att[k]);
+        float e[8], s = 0.f;
+        for (int k = 0; k < 8; k++) { e[k] = expf(att[k] - mx); s += e[k]; }
+        float out = 0.f;
+        for (int k = 0; k < 8; k++) out += (e[k] / s) * enc[k * 32 + tid];
+        // renderer.py:190-194
+        if (p.smooth) {
+            if (p.state[32] != 0.f) out = 0.35f * p.state[tid] + (1 - 0.35f) * out;
+        }
+        __syncwarp();
+        p.state[tid] = out;
+        if (tid == 0 && p.smooth) p.state[32] = 1.f;
+        if (p.dbg_enc_a) p.dbg_enc_a[tid] = out;
+    }
+}
+
+// =========================================================================================
+// warp-level MLP tiles (mma.sync m16n8k16, activations chained in registers)
+// =========================================================================================
+// one layer: c[NT] += a[KS] x W^T, W = smem [>=NT*8][WS] halfs.  B fragments via ldmatrix.
+template <int KS, int NT, int WS>
+__device__ __forceinline__ void mlp_layer(float (&c)[NT][4], const uint32_t (&a)[KS][4], const __half *W, int lane) {
+    // ldmatrix.x4 row address for this lane: row (lane & 7) of matrix q = lane >> 3, k offset 8q
+    const uint32_t base = smem_u32(W) + ((lane & 7) * WS + (lane >> 3) * 8) * 2;
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+#pragma unroll
+        for (int kk = 0; kk + 1 < KS; kk += 2) {
+            uint32_t b[4];
+            ldmatrix_x4(b, base + (nt * 8 * WS + kk * 16) * 2);
+            mma16816(c[nt], a[kk], b[0], b[1]);
+            mma16816(c[nt], a[kk + 1], b[2], b[3]);
+        }
+        if (KS & 1) {
+            uint32_t b0, b1;
+            ldmatrix_x2(b0, b1, base + (nt * 8 * WS + (KS - 1) * 16) * 2);
+            mma16816(c[nt], a[KS - 1], b0, b1);
+        }
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void zero_acc(float (&c)[NT][4]) {
+#pragma unroll
+    for (int i = 0; i < NT; i++) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+}
+
+// accumulators of NT n-tiles -> A fragments of NT/2 k-steps for the next layer (ReLU optional)
+template <int NT, bool RELU>
+__device__ __forceinline__ void acc_to_a(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
+#pragma unroll
+    for (int j = 0; j < NT / 2; j++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float v0 = c[2 * j + h][0], v1 = c[2 * j + h][1], v2 = c[2 * j + h][2], v3 = c[2 * j + h][3];
+            if (RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+            a[j][2 * h + 0] = pack_half2(v0, v1);
+            a[j][2 * h + 1] = pack_half2(v2, v3);
+        }
+    }
+}
+
+// load the A fragments of k-step `kk` of a 16-row tile stored row-major in shared memory
+__device__ __forceinline__ void load_a(uint32_t (&a)[4], const __half *tile, int row_stride, int kk, int lane) {
+    const int q = lane >> 3;
+    const int row = (lane & 7) + 8 * (q & 1), col = kk * 16 + 8 * (q >> 1);
+    ldmatrix_x4(a, smem_u32(tile + row * row_stride + col));
+}
+
+// =========================================================================================
+// k_head
+// =========================================================================================
+#define HEAD_THREADS 256
+#define HEAD_WARPS (HEAD_THREADS / 32)
+#define XS_STRIDE 56 /* enc_x tile row stride in halfs (48 + 8) */
+#define SH_STRIDE 24 /* SH tile row stride in halfs (16 + 8) */
+
+struct HeadParams {
+    FrameGeom g;
+    HeadLevels hl;
+    const float *planes;
+    uint32_t plane_rows;
+    const uint8_t *bitfield;
+    const __half *mlp_image;
+    const float *state;  // enc_a at [0..31]
+    float eye;
+    float bound, min_near, dt_gamma, T_thresh;
+    uint32_t max_steps, cascade, grid_size;
+    float aabb[6];
+    int *alive0, *alive1;
+    int *counters;
+    float *rays_t, *nears, *fars, *weights_sum, *image;
+};
+
+struct HeadSmem {
+    alignas(16) unsigned char mlp[ER_H_BYTES];
+    alignas(16) __half xs[HEAD_WARPS][32 * XS_STRIDE];
+    alignas(16) __half sh[HEAD_WARPS][32 * SH_STRIDE];
+    float enc_a[32];
+    alignas(8) uint64_t bar;
+};
+
+__device__ __forceinline__ void gen_ray(const FrameGeom &g, int idx, Ray &r) {
+    if (g.rays_o) {
+        r.ox = g.rays_o[idx * 3]; r.oy = g.rays_o[idx * 3 + 1]; r.oz = g.rays_o[idx * 3 + 2];
+        r.dx = g.rays_d[idx * 3]; r.dy = g.rays_d[idx * 3 + 1]; r.dz = g.rays_d[idx * 3 + 2];
+    } else {
+        // utils.py:274-277,318-328: i = col + 0.5, j = row + 0.5; (i - cx) / fx on CUDA is a multiply
+        // by the fp32 reciprocal; directions normalised, then @ R^T
+        const int row = idx / g.W, col = idx - row * g.W;
+        const float xs = ((float)col + 0.5f - g.cx) * g.inv_fx;
+        const float ys = ((float)row + 0.5f - g.cy) * g.inv_fy;
+        const float nrm = sqrtf(fmaf(ys, ys, xs * xs) + 1.0f);
+        const float d0 = xs / nrm, d1 = ys / nrm, d2 = 1.0f / nrm;
+        r.dx = fmaf(d2, g.R[2], fmaf(d1, g.R[1], d0 * g.R[0]));
+        r.dy = fmaf(d2, g.R[5], fmaf(d1, g.R[4], d0 * g.R[3]));
+        r.dz = fmaf(d2, g.R[8], fmaf(d1, g.R[7], d0 * g.R[6]));
+        r.ox = g.T[0]; r.oy = g.T[1]; r.oz = g.T[2];
+    }
+    r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+}
+
+// density + color for one 16-row tile (rows m*16..m*16+15 of the warp's 32-sample tile).
+// Returns in lane (t == 0): sigma logit of rows g / g+8; rgb in lanes t == 0 (r, g) and t == 1 (b).
+__device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, __half *xs, const __half *sh, int m, int lane,
+                                              float eye, float &sig_lo, float &sig_hi, float (&rgb)[4]) {
+    const __half *W = reinterpret_cast<const __half *>(sm.mlp);
+    const float *colbias = reinterpret_cast<const float *>(sm.mlp + ER_H_COLBIAS_BYTES);
+    const int g = lane >> 2, t = lane & 3;
+    __half *xt = xs + m * 16 * XS_STRIDE;
+
+    uint32_t ax[3][4];
+#pragma unroll
+    for (int kk = 0; kk < 3; kk++) load_a(ax[kk], xt, XS_STRIDE, kk, lane);
+
+    uint32_t aw[2][4];  // enc_w = enc_a * aud_ch_att  -> sigma_net K cols 48..79
+    {
+        float c1[8][4];
+        zero_acc(c1);
+        mlp_layer<3, 8, 56>(c1, ax, W + ER_H_AUD1, lane);
+        uint32_t ah[4][4];
+        acc_to_a<8, true>(c1, ah);
+        float c2[4][4];
+        zero_acc(c2);
+        mlp_layer<4, 4, 72>(c2, ah, W + ER_H_AUD2, lane);
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int col = (2 * j + h) * 8 + 2 * t;
+                const float e0 = sm.enc_a[col], e1 = sm.enc_a[col + 1];
+                aw[j][2 * h + 0] = pack_half2(e0 * round_half(c2[2 * j + h][0]), e1 * round_half(c2[2 * j + h][1]));
+                aw[j][2 * h + 1] = pack_half2(e0 * round_half(c2[2 * j + h][2]), e1 * round_half(c2[2 * j + h][3]));
+            }
+    }
+    {   // eye_att = sigmoid(MLP(36 -> 16 -> 1)); e = eye * eye_att -> column 36 of the enc_x block
+        float ce[2][4];
+        zero_acc(ce);
+        mlp_layer<3, 2, 56>(ce, ax, W + ER_H_EYE1, lane);
+        const __half *w2 = W + ER_H_EYE2;
+        float lo = 0.f, hi = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            const float w0 = __half2float(w2[nt * 8 + 2 * t]), w1 = __half2float(w2[nt * 8 + 2 * t + 1]);
+            lo = fmaf(round_half(fmaxf(ce[nt][0], 0.f)), w0, lo);
+            lo = fmaf(round_half(fmaxf(ce[nt][1], 0.f)), w1, lo);
+            hi = fmaf(round_half(fmaxf(ce[nt][2], 0.f)), w0, hi);
+            hi = fmaf(round_half(fmaxf(ce[nt][3], 0.f)), w1, hi);
+        }
+        lo += __shfl_xor_sync(0xffffffffu, lo, 1);
+        lo += __shfl_xor_sync(0xffffffffu, lo, 2);
+        hi += __shfl_xor_sync(0xffffffffu, hi, 1);
+        hi += __shfl_xor_sync(0xffffffffu, hi, 2);
+        if (t == 0) {
+            xt[g * XS_STRIDE + 36] = __float2half_rn(eye * sigmoid16(round_half(lo)));
+            xt[(g + 8) * XS_STRIDE + 36] = __float2half_rn(eye * sigmoid16(round_half(hi)));
+        }
+        __syncwarp();
+        load_a(ax[2], xt, XS_STRIDE, 2, lane);
+    }
+    uint32_t ag[4][4];  // geo_feat (fp16)
+    {
+        uint32_t a5[5][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            a5[0][i] = ax[0][i]; a5[1][i] = ax[1][i]; a5[2][i] = ax[2][i];
+            a5[3][i] = aw[0][i]; a5[4][i] = aw[1][i];
+        }
+        float c[8][4];
+        zero_acc(c);
+        mlp_layer<5, 8, 88>(c, a5, W + ER_H_SIG1, lane);
+        uint32_t ah[4][4];
+        acc_to_a<8, true>(c, ah);
+        zero_acc(c);
+        mlp_layer<4, 8, 72>(c, ah, W + ER_H_SIG2, lane);
+        acc_to_a<8, true>(c, ah);
+        zero_acc(c);
+        mlp_layer<4, 8, 72>(c, ah, W + ER_H_SIG3, lane);
+        acc_to_a<8, false>(c, ag);
+        float cs[1][4];
+        zero_acc(cs);
+        mlp_layer<4, 1, 72>(cs, ah, W + ER_H_SIG3 + 64 * 72, lane);
+        sig_lo = round_half(cs[0][0]);  // valid in lanes t == 0 (column 0 of the 9th n-tile)
+        sig_hi = round_half(cs[0][2]);
+    }
+    {   // color_net: [geo 64 | SH 16] -> 64 -> 3, individual code folded into the accumulator init
+        uint32_t a5[5][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { a5[0][i] = ag[0][i]; a5[1][i] = ag[1][i]; a5[2][i] = ag[2][i]; a5[3][i] = ag[3][i]; }
+        load_a(a5[4], sh + m * 16 * SH_STRIDE, SH_STRIDE, 0, lane);
+        float c[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            c[nt][0] = c[nt][2] = colbias[nt * 8 + 2 * t];
+            c[nt][1] = c[nt][3] = colbias[nt * 8 + 2 * t + 1];
+        }
+        mlp_layer<5, 8, 88>(c, a5, W + ER_H_COL1, lane);
+        uint32_t ah[4][4];
+        acc_to_a<8, true>(c, ah);
+        float cc[1][4];
+        zero_acc(cc);
+        mlp_layer<4, 1, 72>(cc, ah, W + ER_H_COL2, lane);
+#pragma unroll
+        for (int i = 0; i < 4; i++) rgb[i] = affine16(sigmoid16(round_half(cc[0][i])));
+    }
+}
+
+__global__ void __launch_bounds__(HEAD_THREADS, 2) k_head(const __grid_constant__ HeadParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    HeadSmem &sm = *reinterpret_cast<HeadSmem *>(smem_raw);
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // stage the MLP image with one bulk TMA copy
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&sm.bar, ER_H_BYTES);
+        bulk_g2s(sm.mlp, p.mlp_image, ER_H_BYTES, &sm.bar);
+    }
+    if (threadIdx.x < 32) sm.enc_a[threadIdx.x] = p.state[threadIdx.x];
+    mbar_wait(&sm.bar, 0);
+    __syncthreads();
+
+    const MarchParams mp = make_march_params(p.bound, p.dt_gamma, p.max_steps, p.cascade, p.grid_size, p.bitfield);
+    __half *xs = sm.xs[warp];
+    __half *sh = sm.sh[warp];
+    const int N = p.g.N;
+    volatile int *ctr = p.counters;
+
+    uint32_t step_total = 0;
+    for (int r = 0; r < ER_MAX_ROUNDS; r++) {
+        const int n_alive = ctr[r * ER_CTR_STRIDE + 0];
+        if (n_alive <= 0 || step_total >= p.max_steps) break;
+        const int n_step = max(min(N / n_alive, 8), 1);
+        const int n_tiles = (n_alive + 31) / 32;
+        const int *alive_in = (r & 1) ? p.alive1 : p.alive0;
+        int *alive_out = (r & 1) ? p.alive0 : p.alive1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[r * ER_CTR_STRIDE + 3] = n_step;
+
+        while (true) {
+            int tile = 0;
+            if (lane == 0) tile = atomicAdd(&p.counters[r * ER_CTR_STRIDE + 1], 1);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= n_tiles) break;
+
+            const int slot = tile * 32 + lane;
+            const bool valid = slot < n_alive;
+            int ray = 0;
+            Ray ry;
+            float t = 0.f, far = 0.f, ws = 0.f, cr = 0.f, cg_ = 0.f, cb = 0.f;
+            if (valid) {
+                ray = (r == 0) ? slot : alive_in[slot];
+                gen_ray(p.g, ray, ry);
+                if (r == 0) {
+                    float near;
+                    near_far_aabb(ry.ox, ry.oy, ry.oz, ry.dx, ry.dy, ry.dz, p.aabb, p.min_near, near, far);
+                    t = near;
+                    p.fars[ray] = far;
+                    if (p.nears) p.nears[ray] = near;
+                } else {
+                    t = p.rays_t[ray];
+                    far = p.fars[ray];
+                    ws = p.weights_sum[ray];
+                    cr = p.image[ray * 3]; cg_ = p.image[ray * 3 + 1]; cb = p.image[ray * 3 + 2];
+                }
+                float shv[16];
+                sh4(ry.dx, ry.dy, ry.dz, shv);
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    *reinterpret_cast<uint32_t *>(sh + lane * SH_STRIDE + 2 * i) = pack_half2(shv[2 * i], shv[2 * i + 1]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) *reinterpret_cast<uint32_t *>(sh + lane * SH_STRIDE + 2 * i) = 0u;
+            }
+            bool alive = valid;
+            int emitted = 0;
+
+            for (int s = 0; s < n_step; s++) {
+                float x = 0.f, y = 0.f, z = 0.f, dt = 0.f;
+                uint32_t vox;
+                bool has = false;
+                if (alive) {
+                    has = march_next(mp, ry, t, far, x, y, z, dt, vox);
+                    if (!has) alive = false;  // deltas[0] == 0 in the reference compositor: ray ends
+                }
+                const uint32_t hasmask = __ballot_sync(0xffffffffu, has);
+                if (hasmask == 0u) break;
+                emitted += __popc(hasmask);
+
+                // ---- tri-plane gather: 3 planes x 12 levels x 4 corners, fp32 (gridencoder.cu:75-175)
+                __half *row = xs + lane * XS_STRIDE;
+                if (has) {
+                    const float rb = 1.0f / (2.0f * p.bound);
+                    const float u[3] = {(x + p.bound) * rb, (y + p.bound) * rb, (z + p.bound) * rb};
+#pragma unroll
+                    for (int pl = 0; pl < 3; pl++) {
+                        const float a = (pl == 1) ? u[1] : u[0];
+                        const float b = (pl == 0) ? u[1] : u[2];
+                        const float *tab = p.planes + (size_t)pl * p.plane_rows;
+                        float f[12];
+#pragma unroll
+                        for (int l = 0; l < 12; l++) f[l] = grid_level_f32(tab, p.hl.lv[l], a, b);
+#pragma unroll
+                        for (int l = 0; l < 6; l++)
+                            *reinterpret_cast<uint32_t *>(row + pl * 12 + 2 * l) = pack_half2(f[2 * l], f[2 * l + 1]);
+                    }
+#pragma unroll
+                    for (int i = 18; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
+                }
+                __syncwarp();
+
+                // ---- MLPs on two 16-row tensor-core tiles; results routed back to lane == sample
+                float sigma_logit = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+                for (int m = 0; m < 2; m++) {
+                    if (((hasmask >> (16 * m)) & 0xffffu) == 0u) continue;
+                    float slo, shi, rgb[4];
+                    head_mlp_tile(sm, xs, sh, m, lane, p.eye, slo, shi, rgb);
+                    const int src0 = 4 * (lane & 7), src1 = src0 + 1;
+                    const float v_slo = __shfl_sync(0xffffffffu, slo, src0), v_shi = __shfl_sync(0xffffffffu, shi, src0);
+                    const float r_lo = __shfl_sync(0xffffffffu, rgb[0], src0), r_hi = __shfl_sync(0xffffffffu, rgb[2], src0);
+                    const float g_lo = __shfl_sync(0xffffffffu, rgb[1], src0), g_hi = __shfl_sync(0xffffffffu, rgb[3], src0);
+                    const float b_lo = __shfl_sync(0xffffffffu, rgb[0], src1), b_hi = __shfl_sync(0xffffffffu, rgb[2], src1);
+                    if ((lane >> 4) == m) {
+                        const bool hi = lane & 8;
+                        sigma_logit = hi ? v_shi : v_slo;
+                        c0 = hi ? r_hi : r_lo;
+                        c1 = hi ? g_hi : g_lo;
+                        c2 = hi ? b_hi : b_lo;
+                    }
+                }
+                __syncwarp();
+
+                // ---- composite (raymarching.cu:2189-2218)
+                if (has) {
+                    const float sigma = expf(sigma_logit);  // torch.exp runs in fp32 under autocast
+                    const float alpha = 1.0f - __expf(-sigma * dt);
+                    const float T = 1 - ws;
+                    const float weight = alpha * T;
+                    ws += weight;
+                    cr = fmaf(weight, c0, cr);
+                    cg_ = fmaf(weight, c1, cg_);
+                    cb = fmaf(weight, c2, cb);
+                    if (T < p.T_thresh) alive = false;
+                }
+            }
+
+            if (valid) {
+                p.weights_sum[ray] = ws;
+                p.image[ray * 3] = cr; p.image[ray * 3 + 1] = cg_; p.image[ray * 3 + 2] = cb;
+                if (alive) p.rays_t[ray] = t;
+            }
+            // ---- compaction (renderer.py:266), warp-aggregated
+            const uint32_t amask = __ballot_sync(0xffffffffu, alive);
+            if (amask) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&p.counters[(r + 1) * ER_CTR_STRIDE + 0], __popc(amask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (alive) alive_out[base + __popc(amask & ((1u << lane) - 1u))] = ray;
+            }
+            if (lane == 0 && emitted) atomicAdd(&p.counters[r * ER_CTR_STRIDE + 2], emitted);
+            __syncwarp();
+        }
+        step_total += n_step;
+        grid.sync();
+    }
+}
+
+// =========================================================================================
+// k_torso_compose
+// =========================================================================================
+#define TORSO_THREADS 256
+#define TORSO_WARPS (TORSO_THREADS / 32)
+#define TX_STRIDE 88 /* torso_net input tile: [feat 32 | freq 34 | pad] = 80 + 8 */
+
+struct TorsoParams {
+    FrameGeom g;
+    TorsoLevels tl;
+    const __half2 *table;
+    const float *density;   // [G*G]
+    const __half *mlp_image;
+    const float *state;     // bias_def at [64..95], bias_tor at [96..127]
+    const __half *bg_color; // [N,3] or null (white)
+    float thresh, shrink;
+    int G;
+    const float *weights_sum, *image;
+    float *out_f32;         // [N,3] or null
+    uint8_t *out_u8;        // [N,3] or null
+    uint8_t *dbg_mask;
+    float *dbg_image_head;
+};
+
+struct TorsoSmem {
+    alignas(16) __half mlp[ER_T_HALFS];
+    alignas(16) __half xt[TORSO_WARPS][32 * TX_STRIDE];
+    float bias[64];
+};
+
+// F.grid_sample(bilinear, zeros padding, align_corners=True) on a [G, G] image (renderer.py:326)
+__device__ __forceinline__ float grid_sample_ac(const float *img, int G, float x, float y) {
+    const float ix = ((x + 1.f) / 2) * (G - 1), iy = ((y + 1.f) / 2) * (G - 1);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    const float nw = ((fx + 1) - ix) * ((fy + 1) - iy), ne = (ix - fx) * ((fy + 1) - iy);
+    const float sw = ((fx + 1) - ix) * (iy - fy), se = (ix - fx) * (iy - fy);
+    auto at = [&](int yy, int xx) { return (xx >= 0 && xx < G && yy >= 0 && yy < G) ? __ldg(img + yy * G + xx) : 0.f; };
+    float out = 0.f;
+    out = fmaf(at(y0, x0), nw, out);
+    out = fmaf(at(y0, x1), ne, out);
+    out = fmaf(at(y1, x0), sw, out);
+    out = fmaf(at(y1, x1), se, out);
+    return out;
+}
+
+__global__ void __launch_bounds__(TORSO_THREADS) k_torso_compose(const __grid_constant__ TorsoParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TorsoSmem &sm = *reinterpret_cast<TorsoSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < ER_T_HALFS / 8; i += blockDim.x)
+        reinterpret_cast<uint4 *>(sm.mlp)[i] = __ldg(reinterpret_cast<const uint4 *>(p.mlp_image) + i);
+    if (threadIdx.x < 64) sm.bias[threadIdx.x] = p.state[64 + threadIdx.x];
+    __syncthreads();
+
+    const int N = p.g.N;
+    const int n_tiles = (N + 31) / 32;
+    __half *xt = sm.xt[warp];
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int tile = blockIdx.x * TORSO_WARPS + warp; tile < n_tiles; tile += gridDim.x * TORSO_WARPS) {
+        const int pix = tile * 32 + lane;
+        const bool valid = pix < N;
+        float c0 = 0.f, c1 = 0.f;  // bg_coords: c0 runs over image rows (utils.py:246-251)
+        if (valid) {
+            if (p.g.bg_coords) {
+                c0 = p.g.bg_coords[pix * 2];
+                c1 = p.g.bg_coords[pix * 2 + 1];
+            } else {
+                const int row = pix / p.g.W, col = pix - row * p.g.W;
+                c0 = ((float)row * p.g.inv_Hm1) * 2 - 1;
+                c1 = ((float)col * p.g.inv_Wm1) * 2 - 1;
+            }
+        }
+        const bool masked = valid && (grid_sample_ac(p.density, p.G, c0, c1) > p.thresh);
+        const uint32_t mmask = __ballot_sync(0xffffffffu, masked);
+        float alpha = 0.f, tc0 = 0.f, tc1 = 0.f, tc2 = 0.f;
+
+        if (mmask) {
+            // x * torso_shrink -> freq(deg 8) 34 values -> cols 32..65 of the tile (cols 66..79 zero)
+            const float xin[2] = {c0 * p.shrink, c1 * p.shrink};
+            __half *row = xt + lane * TX_STRIDE;
+#pragma unroll
+            for (int c = 0; c < 34; c += 2)
+                *reinterpret_cast<uint32_t *>(row + 32 + c) =
+                    masked ? pack_half2(freq_elem(xin, 2, c), freq_elem(xin, 2, c + 1)) : 0u;
+#pragma unroll
+            for (int c = 66; c < 80; c += 2) *reinterpret_cast<uint32_t *>(row + c) = 0u;
+            __syncwarp();
+
+            float dxy[2] = {0.f, 0.f};
+#pragma unroll 1
+            for (int m = 0; m < 2; m++) {
+                if (((mmask >> (16 * m)) & 0xffffu) == 0u) continue;
+                // torso_deform_net: [freq 34 (+ constants as bias)] -> 32 -> 32 -> 2
+                uint32_t a3[3][4];
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) load_a(a3[kk], xt + m * 16 * TX_STRIDE + 32, TX_STRIDE, kk, lane);
+                float c[4][4];
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    c[nt][0] = c[nt][2] = sm.bias[nt * 8 + 2 * t];
+                    c[nt][1] = c[nt][3] = sm.bias[nt * 8 + 2 * t + 1];
+                }
+                mlp_layer<3, 4, 56>(c, a3, sm.mlp + ER_T_DEF1, lane);
+                uint32_t ah[2][4];
+                acc_to_a<4, true>(c, ah);
+                zero_acc(c);
+                mlp_layer<2, 4, 40>(c, ah, sm.mlp + ER_T_DEF2, lane);
+                acc_to_a<4, true>(c, ah);
+                float cd[1][4];
+                zero_acc(cd);
+                mlp_layer<2, 1, 40>(cd, ah, sm.mlp + ER_T_DEF3, lane);
+                // dx (cols 0, 1) lives in lanes t == 0
+                const int src0 = 4 * (lane & 7);
+                const float d0lo = __shfl_sync(0xffffffffu, cd[0][0], src0), d1lo = __shfl_sync(0xffffffffu, cd[0][1], src0);
+                const float d0hi = __shfl_sync(0xffffffffu, cd[0][2], src0), d1hi = __shfl_sync(0xffffffffu, cd[0][3], src0);
+                if ((lane >> 4) == m) {
+                    dxy[0] = round_half((lane & 8) ? d0hi : d0lo);
+                    dxy[1] = round_half((lane & 8) ? d1hi : d1lo);
+                }
+            }
+            // x = clamp(x + dx, -1, 1); tiled grid on (x + 1) / 2 (network.py:188-190), fp16 table
+            if (masked) {
+                const float u = (clampf_(xin[0] + dxy[0], -1.f, 1.f) + 1.f) * 0.5f;
+                const float v = (clampf_(xin[1] + dxy[1], -1.f, 1.f) + 1.f) * 0.5f;
+#pragma unroll
+                for (int l = 0; l < MF_ERNERF_TORSO_LEVELS; l++) {
+                    float o0, o1;
+                    grid_level_f16x2(p.table, p.tl.lv[l], u, v, o0, o1);
+                    *reinterpret_cast<uint32_t *>(row + 2 * l) = pack_half2(o0, o1);
+                }
+            } else {
+#pragma unroll
+                for (int l = 0; l < 16; l++) *reinterpret_cast<uint32_t *>(row + 2 * l) = 0u;
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int m = 0; m < 2; m++) {
+                if (((mmask >> (16 * m)) & 0xffffu) == 0u) continue;
+                // torso_net: [feat 32 | freq 34 (+ constants as bias)] -> 32 -> 32 -> 4
+                uint32_t a5[5][4];
+#pragma unroll
+                for (int kk = 0; kk < 5; kk++) load_a(a5[kk], xt + m * 16 * TX_STRIDE, TX_STRIDE, kk, lane);
+                float c[4][4];
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    c[nt][0] = c[nt][2] = sm.bias[32 + nt * 8 + 2 * t];
+                    c[nt][1] = c[nt][3] = sm.bias[32 + nt * 8 + 2 * t + 1];
+                }
+                mlp_layer<5, 4, 88>(c, a5, sm.mlp + ER_T_TOR1, lane);
+                uint32_t ah[2][4];
+                acc_to_a<4, true>(c, ah);
+                zero_acc(c);
+                mlp_layer<2, 4, 40>(c, ah, sm.mlp + ER_T_TOR2, lane);
+                acc_to_a<4, true>(c, ah);
+                float co[1][4];
+                zero_acc(co);
+                mlp_layer<2, 1, 40>(co, ah, sm.mlp + ER_T_TOR3, lane);
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) o[i] = affine16(sigmoid16(round_half(co[0][i])));
+                // cols: 0 alpha, 1..3 color -> lanes t == 0 hold (alpha, r), t == 1 hold (g, b)
+                const int src0 = 4 * (lane & 7), src1 = src0 + 1;
+                const float a_lo = __shfl_sync(0xffffffffu, o[0], src0), a_hi = __shfl_sync(0xffffffffu, o[2], src0);
+                const float r_lo = __shfl_sync(0xffffffffu, o[1], src0), r_hi = __shfl_sync(0xffffffffu, o[3], src0);
+                const float g_lo = __shfl_sync(0xffffffffu, o[0], src1), g_hi = __shfl_sync(0xffffffffu, o[2], src1);
+                const float b_lo = __shfl_sync(0xffffffffu, o[1], src1), b_hi = __shfl_sync(0xffffffffu, o[3], src1);
+                if ((lane >> 4) == m && masked) {
+                    const bool hi = lane & 8;
+                    alpha = hi ? a_hi : a_lo;
+                    tc0 = hi ? r_hi : r_lo;
+                    tc1 = hi ? g_hi : g_lo;
+                    tc2 = hi ? b_hi : b_lo;
+                }
+            }
+            __syncwarp();
+        }
+
+        if (valid) {
+            // renderer.py:344 bg = torso_color * torso_alpha + bg * (1 - torso_alpha); :275-277 compose + clamp
+            float bg[3] = {1.f, 1.f, 1.f};
+            if (p.bg_color) {
+                bg[0] = __half2float(p.bg_color[pix * 3]);
+                bg[1] = __half2float(p.bg_color[pix * 3 + 1]);
+                bg[2] = __half2float(p.bg_color[pix * 3 + 2]);
+            }
+            const float tc[3] = {tc0, tc1, tc2};
+            const float ws = p.weights_sum[pix];
+            float out[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float b = tc[k] * alpha + bg[k] * (1 - alpha);
+                const float head = p.image[pix * 3 + k];
+                out[k] = fminf(fmaxf(head + (1 - ws) * b, 0.f), 1.f);
+                if (p.dbg_image_head) p.dbg_image_head[pix * 3 + k] = head;
+            }
+            if (p.out_f32) { p.out_f32[pix * 3] = out[0]; p.out_f32[pix * 3 + 1] = out[1]; p.out_f32[pix * 3 + 2] = out[2]; }
+            if (p.out_u8) {
+                p.out_u8[pix * 3] = (uint8_t)(out[0] * 255.f);
+                p.out_u8[pix * 3 + 1] = (uint8_t)(out[1] * 255.f);
+                p.out_u8[pix * 3 + 2] = (uint8_t)(out[2] * 255.f);
+            }
+            if (p.dbg_mask) p.dbg_mask[pix] = masked ? 1 : 0;
+        }
+    }
+}
+
+// F.interpolate(mode='bilinear', align_corners=False) (utils.py:1212) + (x*255).astype(uint8)
+__global__ void k_resize_u8(const float *__restrict__ in, int H, int W, int outH, int outW, float *out_f32,
+                            uint8_t *out_u8) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= outH * outW) return;
+    const int oy = idx / outW, ox = idx - oy * outW;
+    const float sy = fmaxf(((float)H / outH) * (oy + 0.5f) - 0.5f, 0.f);
+    const float sx = fmaxf(((float)W / outW) * (ox + 0.5f) - 0.5f, 0.f);
+    const int y0 = min((int)sy, H - 1), x0 = min((int)sx, W - 1);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - y0, lx = sx - x0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float v00 = in[(y0 * W + x0) * 3 + k], v01 = in[(y0 * W + x1) * 3 + k];
+        const float v10 = in[(y1 * W + x0) * 3 + k], v11 = in[(y1 * W + x1) * 3 + k];
+        const float v = (1 - ly) * ((1 - lx) * v00 + lx * v01) + ly * ((1 - lx) * v10 + lx * v11);
+        if (out_f32) out_f32[idx * 3 + k] = v;
+        if (out_u8) out_u8[idx * 3 + k] = (uint8_t)(v * 255.f);
+    }
+}
+
+// =========================================================================================
+// kernel-level drop-ins (same device functions as the fused path)
+// =========================================================================================
+__global__ void k_near_far(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                           const float *__restrict__ aabb, uint32_t N, float min_near, float *nears, float *fars) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    float ab[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) ab[i] = aabb[i];
+    near_far_aabb(rays_o[n * 3], rays_o[n * 3 + 1], rays_o[n * 3 + 2], rays_d[n * 3], rays_d[n * 3 + 1],
+                  rays_d[n * 3 + 2], ab, min_near, nears[n], fars[n]);
+}
+
+__global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int *__restrict__ rays_alive,
+                             const float *__restrict__ rays_t, const float *__restrict__ rays_o,
+                             const float *__restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                             uint32_t C, uint32_t H, const uint8_t *__restrict__ grid,
+                             const float *__restrict__ nears, const float *__restrict__ fars, float *xyzs,
+                             float *dirs, float *deltas, const float *__restrict__ noises) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    const float noise = noises ? noises[n] : 0.f;
+    Ray r;
+    r.ox = rays_o[index * 3]; r.oy = rays_o[index * 3 + 1]; r.oz = rays_o[index * 3 + 2];
+    r.dx = rays_d[index * 3]; r.dy = rays_d[index * 3 + 1]; r.dz = rays_d[index * 3 + 2];
+    r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+    const MarchParams mp = make_march_params(bound, dt_gamma, max_steps, C, H, grid);
+    xyzs += (size_t)n * n_step * 3;
+    dirs += (size_t)n * n_step * 3;
+    deltas += (size_t)n * n_step * 2;
+    float t = rays_t[index];
+    const float far = fars[index];
+    (void)nears;
+    t += clampf_(t * dt_gamma, mp.dt_min, mp.dt_max) * noise;
+    for (uint32_t step = 0; step < n_step; step++) {
+        float x, y, z, dt;
+        uint32_t vox;
+        if (!march_next(mp, r, t, far, x, y, z, dt, vox)) break;
+        xyzs[0] = x; xyzs[1] = y; xyzs[2] = z;
+        dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz;
+        deltas[0] = dt; deltas[1] = t;
+        xyzs += 3; dirs += 3; deltas += 2;
+    }
+}
+
+__global__ void k_composite_rays_triplane(uint32_t n_alive, uint32_t n_step, float T_thresh, int *rays_alive,
+                                          float *rays_t, const float *__restrict__ sigmas,
+                                          const float *__restrict__ rgbs, const float *__restrict__ deltas,
+                                          const float *__restrict__ ambs_aud, const float *__restrict__ ambs_eye,
+                                          const float *__restrict__ uncertainties, float *weights_sum, float *depth,
+                                          float *image, float *amb_aud_sum, float *amb_eye_sum,
+                                          float *uncertainty_sum) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    sigmas += (size_t)n * n_step; rgbs += (size_t)n * n_step * 3; deltas += (size_t)n * n_step * 2;
+    if (ambs_aud) ambs_aud += (size_t)n * n_step;
+    if (ambs_eye) ambs_eye += (size_t)n * n_step;
+    if (uncertainties) uncertainties += (size_t)n * n_step;
+    float t = rays_t[index];
+    float weight_sum = weights_sum[index], d = depth ? depth[index] : 0.f;
+    float r = image[index * 3], g = image[index * 3 + 1], b = image[index * 3 + 2];
+    float a_aud = amb_aud_sum ? amb_aud_sum[index] : 0.f, a_eye = amb_eye_sum ? amb_eye_sum[index] : 0.f;
+    float u = uncertainty_sum ? uncertainty_sum[index] : 0.f;
+    uint32_t step = 0;
+    while (step < n_step) {
+        if (deltas[0] == 0) break;
+        const float alpha = 1.0f - __expf(-sigmas[0] * deltas[0]);
+        const float T = 1 - weight_sum;
+        const float weight = alpha * T;
+        weight_sum += weight;
+        t = deltas[1];
+        d += weight * t;
+        r += weight * rgbs[0];
+        g += weight * rgbs[1];
+        b += weight * rgbs[2];
+        if (ambs_aud) a_aud += ambs_aud[0];
+        if (ambs_eye) a_eye += ambs_eye[0];
+        if (uncertainties) u += weight * uncertainties[0];
+        if (T < T_thresh) break;
+        sigmas++; rgbs += 3; deltas += 2; step++;
+        if (ambs_aud) ambs_aud++;
+        if (ambs_eye) ambs_eye++;
+        if (uncertainties) uncertainties++;
+    }
+    if (step < n_step) rays_alive[n] = -1;
+    else rays_t[index] = t;
+    weights_sum[index] = weight_sum;
+    if (depth) depth[index] = d;
+    image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+    if (amb_aud_sum) amb_aud_sum[index] = a_aud;
+    if (amb_eye_sum) amb_eye_sum[index] = a_eye;
+    if (uncertainty_sum) uncertainty_sum[index] = u;
+}
+
+struct GridLevelsAny { GridLevel lv[16]; };
+
+__global__ void k_grid_encode(const float *__restrict__ inputs, const void *__restrict__ table, GridLevelsAny lv,
+                              void *outputs, uint32_t B, uint32_t C, int is_half) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    const float u = inputs[b * 2], v = inputs[b * 2 + 1];
+    if (!is_half) {  // C == 1
+        reinterpret_cast<float *>(outputs)[(size_t)level * B + b] =
+            grid_level_f32(reinterpret_cast<const float *>(table), lv.lv[level], u, v);
+    } else {  // C == 2
+        float o0, o1;
+        grid_level_f16x2(reinterpret_cast<const __half2 *>(table), lv.lv[level], u, v, o0, o1);
+        reinterpret_cast<__half2 *>(outputs)[(size_t)level * B + b] = __floats2half2_rn(o0, o1);
+    }
+}
+
+__global__ void k_sh4(const float *__restrict__ inputs, float *outputs, uint32_t B) {
+    const uint32_t b = threadIdx.x + blockIdx.x * blockDim.x;
+    if (b >= B) return;
+    float o[16];
+    sh4(inputs[b * 3], inputs[b * 3 + 1], inputs[b * 3 + 2], o);
+#pragma unroll
+    for (int i = 0; i < 16; i++) outputs[(size_t)b * 16 + i] = o[i];
+}
+
+__global__ void k_freq(const float *__restrict__ inputs, uint32_t B, uint32_t D, uint32_t C, float *outputs) {
+    const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
+    if (t >= B * C) return;
+    const uint32_t b = t / C, c = t - b * C;
+    outputs[t] = freq_elem(inputs + (size_t)b * D, D, c);
+}
+
+// =========================================================================================
+// host side
+// =========================================================================================
+static int compute_scales(mf_ctx *ctx, float S, uint32_t H, int L, float *host_out) {
+    float *d = nullptr;
+    MF_CUDA(ctx, cudaMalloc(&d, 32 * sizeof(float)));
+    k_level_scales<<<1, 32>>>(S, H, L, d);
+    cudaError_t e = cudaMemcpy(host_out, d, L * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return mf_fail(ctx, MF_E_CUDA, "level scales: %s", cudaGetErrorString(e));
+    return MF_OK;
+}
+
+extern "C" int mf_ernerf_blob_layout(int32_t *out, int n) {
+    const int32_t v[] = {ER_H_AUD1, ER_H_AUD2, ER_H_EYE1, ER_H_SIG1, ER_H_SIG2, ER_H_SIG3, ER_H_COL1, ER_H_COL2,
+                         ER_H_EYE2, ER_H_HALFS, ER_H_COLBIAS_BYTES, ER_H_BYTES,
+                         ER_T_DEF1, ER_T_DEF2, ER_T_DEF3, ER_T_TOR1, ER_T_TOR2, ER_T_TOR3, ER_T_HALFS, ER_T_BYTES};
+    const int cnt = (int)(sizeof(v) / sizeof(v[0]));
+    for (int i = 0; i < cnt && i < n; i++) out[i] = v[i];
+    return cnt;
+}
+
+static void ernerf_free_ws(ErnerfState *s) {
+    cudaFree(s->alive[0]); cudaFree(s->alive[1]); cudaFree(s->rays_t); cudaFree(s->fars); cudaFree(s->nears);
+    cudaFree(s->weights_sum); cudaFree(s->image); cudaFree(s->final_f32);
+    s->alive[0] = s->alive[1] = nullptr;
+    s->rays_t = s->fars = s->nears = s->weights_sum = s->image = s->final_f32 = nullptr;
+    s->capN = 0;
+}
+
+void ernerf_destroy(mf_ctx *ctx) {
+    ErnerfState *s = ctx->ernerf;
+    if (!s) return;
+    ernerf_free_ws(s);
+    cudaFree(s->state);
+    cudaFree(s->counters);
+    delete s;
+    ctx->ernerf = nullptr;
+}
+
+extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, const mf_ernerf_cfg *cfg) {
+    if (!ctx) return MF_E_INVALID;
+    MF_REQUIRE(ctx, blob && cfg, "mf_ernerf_load: null blob/cfg");
+    MF_REQUIRE(ctx, cfg->cascade == 1, "mf_ernerf_load: only cascade == 1 (bound <= 1) is implemented");
+    MF_REQUIRE(ctx, cfg->audio_in_dim >= 1 && cfg->audio_in_dim <= 64, "mf_ernerf_load: audio_in_dim %u unsupported",
+               cfg->audio_in_dim);
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    ernerf_destroy(ctx);
+    // header
+    std::vector<unsigned char> head(sizeof(mf_blob_header) + MF_BLOB_MAX_ENTRIES * sizeof(mf_blob_entry));
+    const size_t hbytes = std::min(head.size(), nbytes);
+    MF_CUDA(ctx, cudaMemcpy(head.data(), blob, hbytes, cudaMemcpyDeviceToHost));
+    const mf_blob_header *h = reinterpret_cast<const mf_blob_header *>(head.data());
+    MF_REQUIRE(ctx, hbytes >= sizeof(mf_blob_header) && h->magic == MF_BLOB_MAGIC && h->kind == 1,
+               "mf_ernerf_load: not an ErNeRF blob");
+    MF_REQUIRE(ctx, h->n_entries <= MF_BLOB_MAX_ENTRIES, "mf_ernerf_load: too many entries");
+    const mf_blob_entry *ent = reinterpret_cast<const mf_blob_entry *>(head.data() + sizeof(mf_blob_header));
+    ErnerfState *s = new (std::nothrow) ErnerfState();
+    MF_REQUIRE(ctx, s, "mf_ernerf_load: out of host memory");
+    s->cfg = *cfg;
+    const unsigned char *base = reinterpret_cast<const unsigned char *>(blob);
+    size_t sz[16] = {0};
+    const void *ptr[16] = {nullptr};
+    for (uint32_t i = 0; i < h->n_entries; i++) {
+        if (ent[i].id < 16) {
+            if (ent[i].offset + ent[i].nbytes > nbytes) {
+                delete s;
+                return mf_fail(ctx, MF_E_INVALID, "mf_ernerf_load: entry %u out of range", ent[i].id);
+            }
+            ptr[ent[i].id] = base + ent[i].offset;
+            sz[ent[i].id] = ent[i].nbytes;
+        }
+    }
+    const uint32_t head_rows = (uint32_t)cfg->head_offsets[MF_ERNERF_HEAD_LEVELS];
+    const uint32_t torso_rows = (uint32_t)cfg->torso_offsets[MF_ERNERF_TORSO_LEVELS];
+    const size_t G = cfg->grid_size;
+    const size_t audio_halfs = (size_t)32 * cfg->audio_in_dim * 3 + 32 + 32 * 32 * 3 + 32 + 64 * 32 * 3 + 64 +
+                               64 * 64 * 3 + 64 + 64 * 64 + 64 + 32 * 64 + 32 + 16 * 32 * 3 + 16 + 8 * 16 * 3 + 8 +
+                               4 * 8 * 3 + 4 + 2 * 4 * 3 + 2 + 1 * 2 * 3 + 1 + 64 + 8;
+    bool ok = sz[ER_ID_HEAD_PLANES] == (size_t)3 * head_rows * 4 && sz[ER_ID_BITFIELD] == G * G * G / 8 &&
+              sz[ER_ID_TORSO_TABLE] == (size_t)torso_rows * 4 && sz[ER_ID_TORSO_DENSITY] == G * G * 4 &&
+              sz[ER_ID_HEAD_MLP] == ER_H_BYTES && sz[ER_ID_TORSO_MLP] == ER_T_BYTES &&
+              sz[ER_ID_AUDIO] == audio_halfs * 2 && sz[ER_ID_MISC] == 24 * 4 && sz[ER_ID_TORSO_CONST] == 2 * 32 * 50 * 2;
+    if (!ok) {
+        delete s;
+        return mf_fail(ctx, MF_E_INVALID, "mf_ernerf_load: blob entry sizes do not match cfg (strict loader)");
+    }
+    s->planes = (const float *)ptr[ER_ID_HEAD_PLANES];
+    s->plane_rows = head_rows;
+    s->bitfield = (const uint8_t *)ptr[ER_ID_BITFIELD];
+    s->torso_table = (const __half2 *)ptr[ER_ID_TORSO_TABLE];
+    s->torso_density = (const float *)ptr[ER_ID_TORSO_DENSITY];
+    s->head_mlp = (const __half *)ptr[ER_ID_HEAD_MLP];
+    s->torso_mlp = (const __half *)ptr[ER_ID_TORSO_MLP];
+    s->audio = (const __half *)ptr[ER_ID_AUDIO];
+    s->misc = (const float *)ptr[ER_ID_MISC];
+    s->torso_const = (const __half *)ptr[ER_ID_TORSO_CONST];
+    ctx->ernerf = s;
+    MF_CUDA(ctx, cudaMemcpy(s->misc_host, s->misc, sizeof(s->misc_host), cudaMemcpyDeviceToHost));
+
+    float sc[16];
+    int rc = compute_scales(ctx, cfg->head_log2_scale, cfg->head_base, MF_ERNERF_HEAD_LEVELS, sc);
+    if (rc) return rc;
+    fill_levels(s->hl.lv, MF_ERNERF_HEAD_LEVELS, sc, cfg->head_offsets, 0);
+    rc = compute_scales(ctx, cfg->torso_log2_scale, cfg->torso_base, MF_ERNERF_TORSO_LEVELS, sc);
+    if (rc) return rc;
+    fill_levels(s->tl.lv, MF_ERNERF_TORSO_LEVELS, sc, cfg->torso_offsets, 1);
+
+    MF_CUDA(ctx, cudaMalloc(&s->state, 128 * sizeof(float)));
+    MF_CUDA(ctx, cudaMemset(s->state, 0, 128 * sizeof(float)));
+    MF_CUDA(ctx, cudaMalloc(&s->counters, (ER_MAX_ROUNDS + 1) * ER_CTR_STRIDE * sizeof(int)));
+
+    MF_CUDA(ctx, cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
+    MF_CUDA(ctx, cudaFuncSetAttribute(k_torso_compose, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(TorsoSmem)));
+    int per_sm = 0;
+    MF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_head, HEAD_THREADS, sizeof(HeadSmem)));
+    MF_REQUIRE(ctx, per_sm >= 1, "k_head does not fit on an SM");
+    s->head_grid = per_sm * ctx->sm_count;
+    MF_CUDA(ctx, cudaDeviceSynchronize());
+    return MF_OK;
+}
+
+extern "C" int mf_ernerf_reset_state(mf_ctx *ctx) {
+    if (!ctx) return MF_E_INVALID;
+    if (!ctx->ernerf) return mf_fail(ctx, MF_E_STATE, "ErNeRF weights not loaded");
+    MF_CUDA(ctx, cudaMemset(ctx->ernerf->state, 0, 64 * sizeof(float)));
+    return MF_OK;
+}
+
+extern "C" int mf_ernerf_last_launches(const mf_ctx *ctx) { return (ctx && ctx->ernerf) ? ctx->ernerf->last_launches : 0; }
+
+static int ensure_ws(mf_ctx *ctx, ErnerfState *s, int N) {
+    if (N <= s->capN) return MF_OK;
+    ernerf_free_ws(s);
+    MF_CUDA(ctx, cudaMalloc(&s->alive[0], (size_t)N * 4));
+    MF_CUDA(ctx, cudaMalloc(&s->alive[1], (size_t)N * 4));
+    MF_CUDA(ctx, cudaMalloc(&s->rays_t, (size_t)N * 4));
+    MF_CUDA(ctx, cudaMalloc(&s->fars, (size_t)N * 4));
+    MF_CUDA(ctx, cudaMalloc(&s->nears, (size_t)N * 4));
+    MF_CUDA(ctx, cudaMalloc(&s->weights_sum, (size_t)N * 4));
+    MF_CUDA(ctx, cudaMalloc(&s->image, (size_t)N * 12));
+    MF_CUDA(ctx, cudaMalloc(&s->final_f32, (size_t)N * 12));
+    s->capN = N;
+    return MF_OK;
+}
+
+// inverse of a general 4x4 (Gauss-Jordan, partial pivoting) in double
+static bool inv4(const double *m, double *out) {
+    double a[4][8];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) { a[i][j] = m[i * 4 + j]; a[i][4 + j] = (i == j); }
+    for (int c = 0; c < 4; c++) {
+        int piv = c;
+        for (int r = c + 1; r < 4; r++) if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+        if (std::fabs(a[piv][c]) < 1e-300) return false;
+        if (piv != c) for (int j = 0; j < 8; j++) std::swap(a[piv][j], a[c][j]);
+        const double d = a[c][c];
+        for (int j = 0; j < 8; j++) a[c][j] /= d;
+        for (int r = 0; r < 4; r++) if (r != c) {
+            const double f = a[r][c];
+            for (int j = 0; j < 8; j++) a[r][j] -= f * a[c][j];
+        }
+    }
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out[i * 4 + j] = a[i][4 + j];
+    return true;
+}
+
+static inline float h16(float v) { return __half2float(__float2half_rn(v)); }
+
+extern "C" int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *f, uint8_t *out_rgb, const mf_ernerf_debug *dbg,
+                                void *stream_) {
+    if (!ctx) return MF_E_INVALID;
+    ErnerfState *s = ctx->ernerf;
+    if (!s) return mf_fail(ctx, MF_E_STATE, "mf_ernerf_render: ErNeRF weights not loaded");
+    MF_REQUIRE(ctx, f && f->pose, "mf_ernerf_render: null frame/pose");
+    MF_REQUIRE(ctx, f->auds || f->enc_a, "mf_ernerf_render: need auds or enc_a");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool explicit_rays = f->rays_o != nullptr;
+    if (explicit_rays)
+        MF_REQUIRE(ctx, f->rays_d && f->bg_coords && f->n_rays > 0, "explicit rays need rays_d, bg_coords, n_rays");
+    else
+        MF_REQUIRE(ctx, f->H > 1 && f->W > 1, "mf_ernerf_render: bad H/W");
+    const int N = explicit_rays ? f->n_rays : f->H * f->W;
+    const int outH = explicit_rays ? 1 : (f->outH > 0 ? f->outH : f->H);
+    const int outW = explicit_rays ? N : (f->outW > 0 ? f->outW : f->W);
+    const bool resize = !explicit_rays && (outH != f->H || outW != f->W);
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_ws(ctx, s, N);
+    if (rc) return rc;
+
+    FrameGeom g;
+    g.N = N; g.H = explicit_rays ? 1 : f->H; g.W = explicit_rays ? N : f->W;
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) g.R[i * 3 + j] = f->pose[i * 4 + j];
+        g.T[i] = f->pose[i * 4 + 3];
+    }
+    g.inv_fx = 1.0f / f->fx; g.inv_fy = 1.0f / f->fy; g.cx = f->cx; g.cy = f->cy;
+    g.rays_o = f->rays_o; g.rays_d = f->rays_d; g.bg_coords = f->bg_coords;
+    g.inv_Hm1 = explicit_rays ? 0.f : 1.0f / (float)(f->H - 1);
+    g.inv_Wm1 = explicit_rays ? 0.f : 1.0f / (float)(f->W - 1);
+
+    // wrapped anchor (network.py:175-176): anchor_points @ inverse(pose^T) runs as an fp16 matmul
+    // under autocast, the two divisions in fp16
+    SetupParams sp;
+    {
+        double pt[16], inv[16];
+        for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) pt[i * 4 + j] = f->pose[j * 4 + i];
+        MF_REQUIRE(ctx, inv4(pt, inv), "mf_ernerf_render: singular pose");
+        const float *ap = s->misc_host;  // anchor_points, cached at load time
+        for (int a = 0; a < 3; a++) {
+            float w[4];
+            for (int j = 0; j < 4; j++) {
+                float acc = 0.f;
+                for (int k = 0; k < 4; k++) acc += h16(ap[a * 4 + k]) * h16((float)inv[k * 4 + j]);
+                w[j] = h16(acc);
+            }
+            sp.wa[a * 2 + 0] = h16(h16(w[0] / w[3]) / w[2]);
+            sp.wa[a * 2 + 1] = h16(h16(w[1] / w[3]) / w[2]);
+        }
+    }
+    sp.auds = f->auds; sp.enc_a_in = f->enc_a; sp.audio = s->audio; sp.torso_const = s->torso_const;
+    sp.misc = s->misc; sp.state = s->state; sp.counters = s->counters; sp.A = (int)s->cfg.audio_in_dim;
+    sp.N = N; sp.smooth = (int)s->cfg.smooth_lips; sp.dbg_enc_a = dbg ? dbg->enc_a : nullptr;
+    int launches = 0;
+    k_setup<<<1, 256, 0, stream>>>(sp);
+    launches++;
+
+    HeadParams hp;
+    hp.g = g; hp.hl = s->hl; hp.planes = s->planes; hp.plane_rows = s->plane_rows; hp.bitfield = s->bitfield;
+    hp.mlp_image = s->head_mlp; hp.state = s->state; hp.eye = f->eye;
+    hp.bound = s->cfg.bound; hp.min_near = s->cfg.min_near; hp.dt_gamma = s->cfg.dt_gamma; hp.T_thresh = s->cfg.T_thresh;
+    hp.max_steps = s->cfg.max_steps; hp.cascade = s->cfg.cascade; hp.grid_size = s->cfg.grid_size;
+    const float b = s->cfg.bound;  // renderer.py:86
+    const float aabb[6] = {-b, -b / 2, -b, b, b / 2, b};
+    for (int i = 0; i < 6; i++) hp.aabb[i] = aabb[i];
+    hp.alive0 = s->alive[0]; hp.alive1 = s->alive[1]; hp.counters = s->counters;
+    hp.rays_t = s->rays_t; hp.nears = dbg && dbg->nears ? dbg->nears : nullptr;
+    hp.fars = s->fars; hp.weights_sum = s->weights_sum; hp.image = s->image;
+    {
+        void *args[] = {&hp};
+        const int grid = std::min(s->head_grid, std::max(1, (N + 31) / 32 / HEAD_WARPS + 1));
+        MF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_head, dim3(grid), dim3(HEAD_THREADS), args,
+                                                 sizeof(HeadSmem), stream));
+        launches++;
+    }
+
+    TorsoParams tp;
+    tp.g = g; tp.tl = s->tl; tp.table = s->torso_table; tp.density = s->torso_density; tp.mlp_image = s->torso_mlp;
+    tp.state = s->state; tp.bg_color = (const __half *)f->bg_color; tp.thresh = s->cfg.density_thresh_torso;
+    tp.shrink = s->cfg.torso_shrink; tp.G = (int)s->cfg.grid_size; tp.weights_sum = s->weights_sum; tp.image = s->image;
+    tp.out_f32 = resize ? s->final_f32 : f->out_image_f32;
+    tp.out_u8 = resize ? nullptr : out_rgb;
+    tp.dbg_mask = dbg ? dbg->torso_mask : nullptr;
+    tp.dbg_image_head = dbg ? dbg->image_head : nullptr;
+    {
+        const int n_tiles = (N + 31) / 32;
+        const int grid = std::max(1, std::min((n_tiles + TORSO_WARPS - 1) / TORSO_WARPS, ctx->sm_count * 4));
+        k_torso_compose<<<grid, TORSO_THREADS, sizeof(TorsoSmem), stream>>>(tp);
+        launches++;
+    }
+    if (resize) {
+        const int tot = outH * outW;
+        k_resize_u8<<<(tot + 255) / 256, 256, 0, stream>>>(s->final_f32, f->H, f->W, outH, outW, f->out_image_f32, out_rgb);
+        launches++;
+    }
+    if (dbg) {
+        if (dbg->fars) MF_CUDA(ctx, cudaMemcpyAsync(dbg->fars, s->fars, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
+        if (dbg->weights_sum)
+            MF_CUDA(ctx, cudaMemcpyAsync(dbg->weights_sum, s->weights_sum, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
+        if (dbg->round_info)
+            MF_CUDA(ctx, cudaMemcpy2DAsync(dbg->round_info, 4 * sizeof(int), s->counters, ER_CTR_STRIDE * sizeof(int),
+                                           4 * sizeof(int), ER_MAX_ROUNDS + 1, cudaMemcpyDeviceToDevice, stream));
+    }
+    MF_CUDA(ctx, cudaGetLastError());
+    s->last_launches = launches;
+    return MF_OK;
+}
+
+// ---- kernel-level entry points ---------------------------------------------------------
+extern "C" int mf_near_far_from_aabb(mf_ctx *ctx, const float *rays_o, const float *rays_d, const float *aabb,
+                                     uint32_t N, float min_near, float *nears, float *fars, void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    MF_REQUIRE(ctx, rays_o && rays_d && aabb && nears && fars, "mf_near_far_from_aabb: null pointer");
+    if (N == 0) return MF_OK;
+    k_near_far<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    MF_CUDA(ctx, cudaGetLastError());
+    return MF_OK;
+}
+
+extern "C" int mf_march_rays(mf_ctx *ctx, uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive,
+                             const float *rays_t, const float *rays_o, const float *rays_d, float bound,
+                             float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *grid,
+                             const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                             const float *noises, void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    MF_REQUIRE(ctx, rays_alive && rays_t && rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas,
+               "mf_march_rays: null pointer");
+    MF_REQUIRE(ctx, C >= 1 && H >= 1 && max_steps >= 1, "mf_march_rays: bad C/H/max_steps");
+    if (n_alive == 0 || n_step == 0) return MF_OK;
+    k_march_rays<<<(n_alive + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_alive, n_step, rays_alive, rays_t, rays_o,
+                                                                            rays_d, bound, dt_gamma, max_steps, C, H,
+                                                                            grid, nears, fars, xyzs, dirs, deltas, noises);
+    MF_CUDA(ctx, cudaGetLastError());
+    return MF_OK;
+}
+
+extern "C" int mf_composite_rays_triplane(mf_ctx *ctx, uint32_t n_alive, uint32_t n_step, float T_thresh,
+                                          int32_t *rays_alive, float *rays_t, const float *sigmas, const float *rgbs,
+                                          const float *deltas, const float *ambs_aud, const float *ambs_eye,
+                                          const float *uncertainties, float *weights_sum, float *depth, float *image,
+                                          float *amb_aud_sum, float *amb_eye_sum, float *uncertainty_sum,
+                                          void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    MF_REQUIRE(ctx, rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && image,
+               "mf_composite_rays_triplane: null pointer");
+    if (n_alive == 0) return MF_OK;
+    k_composite_rays_triplane<<<(n_alive + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, ambs_aud, ambs_eye, uncertainties,
+        weights_sum, depth, image, amb_aud_sum, amb_eye_sum, uncertainty_sum);
+    MF_CUDA(ctx, cudaGetLastError());
+    return MF_OK;
+}
+
+extern "C" int mf_grid_encode_forward(mf_ctx *ctx, const float *inputs, const void *embeddings,
+                                      const int32_t *offsets, void *outputs, uint32_t B, uint32_t D, uint32_t C,
+                                      uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                      int embeddings_is_half, void *stream_) {
+    if (!ctx) return MF_E_INVALID;
+    MF_REQUIRE(ctx, inputs && embeddings && offsets && outputs, "mf_grid_encode_forward: null pointer");
+    if (D != 2 || align_corners || L > 16 || L < 1 || !((C == 1 && !embeddings_is_half) || (C == 2 && embeddings_is_half)))
+        return mf_fail(ctx, MF_E_UNSUPPORTED,
+                       "mf_grid_encode_forward: only D=2, align_corners=False, (C=1,fp32) or (C=2,fp16) are on the hot path");
+    if (B == 0) return MF_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int32_t off[17];
+    MF_CUDA(ctx, cudaMemcpyAsync(off, offsets, (L + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    MF_CUDA(ctx, cudaStreamSynchronize(stream));
+    float sc[16];
+    int rc = compute_scales(ctx, S, H, (int)L, sc);
+    if (rc) return rc;
+    GridLevelsAny lv;
+    fill_levels(lv.lv, (int)L, sc, off, gridtype);
+    k_grid_encode<<<dim3((B + 255) / 256, L), 256, 0, stream>>>(inputs, embeddings, lv, outputs, B, C, embeddings_is_half);
+    MF_CUDA(ctx, cudaGetLastError());
+    return MF_OK;
+}
+
+extern "C" int mf_sh_encode_forward(mf_ctx *ctx, const float *inputs, float *outputs, uint32_t B, uint32_t D,
+                                    uint32_t C, void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    MF_REQUIRE(ctx, inputs && outputs, "mf_sh_encode_forward: null pointer");
+    if (D != 3 || C != 4) return mf_fail(ctx, MF_E_UNSUPPORTED, "mf_sh_encode_forward: only D=3, degree 4 is on the hot path");
+    if (B == 0) return MF_OK;
+    k_sh4<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(inputs, outputs, B);
+    MF_CUDA(ctx, cudaGetLastError());
+    return MF_OK;
+}
+
+extern "C" int mf_freq_encode_forward(mf_ctx *ctx, const float *inputs, uint32_t B, uint32_t D, uint32_t deg,
+                                      uint32_t C, float *outputs, void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    MF_REQUIRE(ctx, inputs && outputs, "mf_freq_encode_forward: null pointer");
+    MF_REQUIRE(ctx, C == D + D * deg * 2, "mf_freq_encode_forward: C != D + 2*D*deg");
+    if (B == 0) return MF_OK;
+    const uint32_t tot = B * C;
+    k_freq<<<(tot + 127) / 128, 128, 0, (cudaStream_t)stream>>>(inputs, B, D, C, outputs);
+    MF_CUDA(ctx, cudaGetLastError());
+    return MF_OK;
+}

@@ -1,0 +1,78 @@
+"""ErnerfRenderer: torch tensors in/out around mf_ernerf_render (include/mf_b200.h).
+
+Replaces Trainer.test_gui_with_data + NeRFRenderer.run_cuda/run_torso
+(ernerf/nerf_triplane/utils.py:1191-1223, renderer.py:158-352) for one session on one GPU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Context, MfErnerfDebug, MfErnerfFrame, check, lib
+from .ernerf_pack import pack_ernerf
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class ErnerfRenderer:
+    def __init__(self, state_dict=None, mean_density_torso=0.0, opt=None, device=0, blob=None, cfg=None):
+        """Either (state_dict, mean_density_torso) or a pre-packed (blob, cfg) -- e.g. a blob
+        broadcast from rank 0."""
+        self.device = torch.device("cuda", device)
+        self.ctx = Context(device)
+        if blob is None:
+            blob, cfg = pack_ernerf(state_dict, mean_density_torso, opt)
+        if isinstance(blob, np.ndarray):
+            blob = torch.from_numpy(blob)
+        self.blob = blob.to(self.device)          # must outlive the context
+        self.cfg = cfg
+        check(self.ctx.handle, lib().mf_ernerf_load(self.ctx.handle, _ptr(self.blob), self.blob.numel(),
+                                                     ctypes.byref(cfg)), "mf_ernerf_load")
+
+    def reset(self):
+        check(self.ctx.handle, lib().mf_ernerf_reset_state(self.ctx.handle), "mf_ernerf_reset_state")
+
+    @property
+    def last_launches(self):
+        return lib().mf_ernerf_last_launches(self.ctx.handle)
+
+    def render(self, pose, intrinsics, H, W, auds=None, eye=0.25, out=None, outH=None, outW=None, enc_a=None,
+               bg_color=None, rays_o=None, rays_d=None, bg_coords=None, out_f32=None, debug=False, stream=None):
+        """pose: 16 floats (host, row-major cam2world); auds: cuda fp32 [8, A, 16];
+        returns u8 cuda tensor [outH, outW, 3] RGB (and a dict of debug tensors when debug=True)."""
+        pose = np.ascontiguousarray(np.asarray(pose, np.float32).reshape(16))
+        fr = MfErnerfFrame()
+        fr.pose = pose.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        fr.fx, fr.fy, fr.cx, fr.cy = [float(v) for v in intrinsics]
+        fr.H, fr.W = int(H), int(W)
+        fr.auds = _ptr(auds)
+        fr.enc_a = _ptr(enc_a)
+        fr.eye = float(eye)
+        fr.bg_color = _ptr(bg_color)
+        explicit = rays_o is not None
+        fr.rays_o, fr.rays_d, fr.bg_coords = _ptr(rays_o), _ptr(rays_d), _ptr(bg_coords)
+        fr.n_rays = int(rays_o.shape[0]) if explicit else 0
+        oH, oW = (1, fr.n_rays) if explicit else (int(outH or H), int(outW or W))
+        fr.outH, fr.outW = oH, oW
+        if out is None:
+            out = torch.empty((oH, oW, 3), dtype=torch.uint8, device=self.device)
+        fr.out_image_f32 = _ptr(out_f32)
+        dbg = None
+        dbg_t = None
+        if debug:
+            N = fr.n_rays if explicit else H * W
+            f32 = dict(dtype=torch.float32, device=self.device)
+            dbg_t = dict(nears=torch.zeros(N, **f32), fars=torch.zeros(N, **f32),
+                         round_info=torch.zeros((17, 4), dtype=torch.int32, device=self.device),
+                         weights_sum=torch.zeros(N, **f32), image_head=torch.zeros((N, 3), **f32),
+                         enc_a=torch.zeros(32, **f32), torso_mask=torch.zeros(N, dtype=torch.uint8, device=self.device))
+            dbg = MfErnerfDebug(*[_ptr(dbg_t[k]) for k in ("nears", "fars", "round_info", "weights_sum",
+                                                           "image_head", "enc_a", "torso_mask")])
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        rc = lib().mf_ernerf_render(self.ctx.handle, ctypes.byref(fr), _ptr(out),
+                                    ctypes.byref(dbg) if dbg is not None else None, ctypes.c_void_p(s.cuda_stream))
+        check(self.ctx.handle, rc, "mf_ernerf_render")
+        return (out, dbg_t) if debug else out

@@ -1,0 +1,247 @@
+"""GPU parity: sm_100a ErNeRF kernels (through the C ABI) vs the CPU oracle, real checkpoint."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import ernerf_inputs, load_ernerf_fixture, psnr
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def env():
+    from mere_fusion_b200._lib import Context, lib
+    from mere_fusion_b200.ernerf import ErnerfRenderer
+    from oracle.ernerf_oracle import ErnerfOracle
+    sd, md = load_ernerf_fixture()
+    ren = ErnerfRenderer(sd, md, device=0)
+    orc = ErnerfOracle(sd, md)
+    return dict(sd=sd, md=md, ren=ren, orc=orc, lib=lib(), ctx=Context(0))
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _rays(H=96, frame=0):
+    from oracle import ernerf_oracle as O
+    pose, intr, auds, eye = ernerf_inputs(frame, H, H)
+    ro, rd = O.get_rays(pose, intr, H, H)
+    return pose, intr, auds, eye, ro, rd
+
+
+def test_near_far_bit_exact(env):
+    from oracle import ernerf_oracle as O
+    _, _, _, _, ro, rd = _rays()
+    aabb = np.array([-1, -0.5, -1, 1, 0.5, 1], np.float32)
+    n_ref, f_ref = O.near_far_from_aabb(ro, rd, aabb, 0.05)
+    N = ro.shape[0]
+    nears = torch.empty(N, device="cuda")
+    fars = torch.empty(N, device="cuda")
+    rc = env["lib"].mf_near_far_from_aabb(env["ctx"].handle, P(cu(ro)), P(cu(rd)), P(cu(aabb)), N, 0.05, P(nears), P(fars), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(nears.cpu().numpy(), n_ref)
+    assert np.array_equal(fars.cpu().numpy(), f_ref)
+    assert (n_ref < 1e30).sum() > 100      # the case is not degenerate
+
+
+@pytest.mark.parametrize("n_step", [1, 3, 8])
+def test_march_rays_bit_exact(env, n_step):
+    from oracle import ernerf_oracle as O
+    _, _, _, _, ro, rd = _rays()
+    aabb = np.array([-1, -0.5, -1, 1, 0.5, 1], np.float32)
+    nears, fars = O.near_far_from_aabb(ro, rd, aabb, 0.05)
+    N = ro.shape[0]
+    alive = np.arange(N, dtype=np.int32)[::2].copy()     # ragged subset
+    n_alive = alive.shape[0]
+    bit = np.ascontiguousarray(env["sd"]["density_bitfield"], np.uint8)
+    x_ref, d_ref, dl_ref = O.march_rays(n_alive, n_step, alive, nears.copy(), ro, rd, 1.0, bit, 1, 128, nears, fars,
+                                        128, 1 / 256, 16)
+    M = x_ref.shape[0]
+    xyzs = torch.zeros(M, 3, device="cuda")
+    dirs = torch.zeros(M, 3, device="cuda")
+    deltas = torch.zeros(M, 2, device="cuda")
+    rc = env["lib"].mf_march_rays(env["ctx"].handle, n_alive, n_step, P(cu(alive)), P(cu(nears)), P(cu(ro)), P(cu(rd)),
+                                  1.0, 1 / 256, 16, 1, 128, P(cu(bit)), P(cu(nears)), P(cu(fars)), P(xyzs), P(dirs),
+                                  P(deltas), None, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    # sample counts (which rows are non-zero) are integer outputs: exact
+    assert np.array_equal(deltas.cpu().numpy()[:, 0] != 0, dl_ref[:, 0] != 0)
+    assert (dl_ref[:, 0] != 0).sum() > 100
+    assert np.array_equal(xyzs.cpu().numpy(), x_ref)
+    assert np.array_equal(dirs.cpu().numpy(), d_ref)
+    assert np.array_equal(deltas.cpu().numpy(), dl_ref)
+
+
+def test_composite_matches_oracle(env):
+    from oracle import ernerf_oracle as O
+    rng = np.random.default_rng(5)
+    n_alive, n_step, N = 1000, 4, 3000
+    alive = rng.permutation(N)[:n_alive].astype(np.int32)
+    sig = np.exp(rng.standard_normal(n_alive * n_step) * 2 + 1).astype(np.float32)
+    rgb = rng.random((n_alive * n_step, 3)).astype(np.float32)
+    deltas = np.zeros((n_alive * n_step, 2), np.float32)
+    deltas[:, 0] = 0.027
+    deltas[:, 1] = rng.random(n_alive * n_step) + 1
+    deltas.reshape(n_alive, n_step, 2)[rng.random(n_alive) < 0.3, 2:, :] = 0   # rays that ran out of samples
+    ws = (rng.random(N) * 0.5).astype(np.float32)
+    depth = rng.random(N).astype(np.float32)
+    img = rng.random((N, 3)).astype(np.float32)
+    rt = rng.random(N).astype(np.float32)
+    a_ref, t_ref, ws_ref, d_ref, im_ref = alive.copy(), rt.copy(), ws.copy(), depth.copy(), img.copy()
+    O.composite_rays_triplane(n_alive, n_step, a_ref, t_ref, sig, rgb, deltas, ws_ref, d_ref, im_ref, 1e-4)
+    ga, gt, gws, gd, gim = cu(alive), cu(rt), cu(ws), cu(depth), cu(img)
+    rc = env["lib"].mf_composite_rays_triplane(env["ctx"].handle, n_alive, n_step, 1e-4, P(ga), P(gt), P(cu(sig)),
+                                               P(cu(rgb)), P(cu(deltas)), None, None, None, P(gws), P(gd), P(gim),
+                                               None, None, None, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(ga.cpu().numpy(), a_ref)            # alive mask: exact
+    assert np.array_equal(gt.cpu().numpy(), t_ref)
+    np.testing.assert_allclose(gws.cpu().numpy(), ws_ref, rtol=0, atol=2e-6)   # __expf vs expf
+    np.testing.assert_allclose(gim.cpu().numpy(), im_ref, rtol=0, atol=4e-6)
+    np.testing.assert_allclose(gd.cpu().numpy(), d_ref, rtol=0, atol=1e-5)
+
+
+def test_grid_encode_head_plane(env):
+    from oracle import ernerf_oracle as O
+    rng = np.random.default_rng(1)
+    B = 4099
+    x = rng.random((B, 2)).astype(np.float32)
+    x[:5] = [[0, 0], [1, 1], [0, 1], [0.5, 0.5], [1.0000001, 0.2]]     # corners + one out-of-range point
+    emb = env["sd"]["encoder_xy.embeddings"].astype(np.float32)
+    off = env["sd"]["encoder_xy.offsets"].astype(np.int32)
+    ref = O.grid_encode(x, emb, off, env["orc"].hs, 64, 0)
+    out = torch.empty(12, B, 1, device="cuda")
+    rc = env["lib"].mf_grid_encode_forward(env["ctx"].handle, P(cu(x)), P(cu(emb)), P(cu(off)), P(out), B, 2, 1, 12,
+                                           float(np.log2(env["orc"].hs)), 64, 0, 0, 0, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().transpose(1, 0, 2).reshape(B, 12)
+    assert np.array_equal(got, ref)                                   # fp32, same fma order: exact
+
+
+def test_grid_encode_torso_fp16(env):
+    from oracle import ernerf_oracle as O
+    rng = np.random.default_rng(2)
+    B = 3001
+    x = rng.random((B, 2)).astype(np.float32)
+    emb = env["sd"]["torso_encoder.embeddings"].astype(np.float16)
+    off = env["sd"]["torso_encoder.offsets"].astype(np.int32)
+    ref = O.grid_encode(x, emb, off, env["orc"].ts, 16, 1, half=True)
+    out = torch.empty(16, B, 2, device="cuda", dtype=torch.float16)
+    rc = env["lib"].mf_grid_encode_forward(env["ctx"].handle, P(cu(x)), P(cu(emb)), P(cu(off)), P(out), B, 2, 2, 16,
+                                           float(np.log2(env["orc"].ts)), 16, 1, 0, 1, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().transpose(1, 0, 2).reshape(B, 32)
+    assert np.array_equal(got, ref)
+
+
+def test_sh_and_freq(env):
+    from oracle import ernerf_oracle as O
+    rng = np.random.default_rng(3)
+    d = rng.standard_normal((1000, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    out = torch.empty(1000, 16, device="cuda")
+    assert env["lib"].mf_sh_encode_forward(env["ctx"].handle, P(cu(d)), P(out), 1000, 3, 4, None) == 0
+    np.testing.assert_allclose(out.cpu().numpy(), O.sh_encode4(d), rtol=0, atol=5e-7)
+    for D, deg in ((2, 8), (6, 3)):
+        x = (rng.random((777, D)).astype(np.float32) * 2 - 1)
+        C = D + D * deg * 2
+        o = torch.empty(777, C, device="cuda")
+        assert env["lib"].mf_freq_encode_forward(env["ctx"].handle, P(cu(x)), 777, D, deg, C, P(o), None) == 0
+        # __sinf (MUFU) vs sinf: absolute error grows with |arg| (<= 2^7 here)
+        np.testing.assert_allclose(o.cpu().numpy(), O.freq_encode(x, deg), rtol=0, atol=2e-4)
+
+
+def test_unsupported_and_errors(env):
+    L, ctx = env["lib"], env["ctx"]
+    assert L.mf_sh_encode_forward(ctx.handle, P(torch.zeros(3, device="cuda")), P(torch.zeros(16, device="cuda")), 1, 3, 6, None) == -4
+    assert L.mf_near_far_from_aabb(ctx.handle, None, None, None, 1, 0.05, None, None, None) == -1
+    assert b"null pointer" in L.mf_last_error(ctx.handle)
+    from mere_fusion_b200._lib import Context, MfErnerfFrame
+    c2 = Context(0)
+    assert L.mf_ernerf_render(c2.handle, ctypes.byref(MfErnerfFrame()), None, None, None) == -3   # not loaded
+
+
+@pytest.mark.parametrize("H,frame", [(64, 0), (128, 7)])
+def test_full_frame_vs_oracle(env, H, frame):
+    """rays generated in-kernel from the pose; RGB within fp16-MLP tolerance of the oracle."""
+    ren, orc = env["ren"], env["orc"]
+    pose, intr, auds, eye = ernerf_inputs(frame, H, H)
+    ren.reset()
+    orc.enc_a_prev = None
+    dbg_o = {}
+    img_ref, u8_ref = orc.render_frame(pose, intr, H, H, auds, eye, debug=dbg_o)
+    f32 = torch.empty(H, H, 3, device="cuda")
+    out, dbg = ren.render(pose, intr, H, H, cu(auds), eye, out_f32=f32, debug=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(dbg["enc_a"].cpu().numpy(), dbg_o["enc_a"][0], rtol=0, atol=2e-3)
+    # AABB hit mask is an integer-valued output: allow only rays_d ulp effects (none expected)
+    hit_o = dbg_o["nears"] < 1e30
+    hit_g = dbg["nears"].cpu().numpy() < 1e30
+    assert (hit_o != hit_g).sum() <= 2
+    ri = dbg["round_info"].cpu().numpy()
+    rounds = [(int(a), int(s)) for a, s, _, _ in zip(ri[:, 0], ri[:, 3], ri[:, 2], ri[:, 1]) if s > 0]
+    ref_rounds = [(a, s) for a, s, _ in dbg_o["rounds"]]
+    assert rounds[0] == ref_rounds[0]
+    assert len(rounds) == len(ref_rounds)
+    for (a, s), (ra, rs) in zip(rounds, ref_rounds):
+        assert s == rs and abs(a - ra) <= max(2, ra // 200)      # alive counts: SURVEY N4
+    assert np.array_equal(dbg["torso_mask"].cpu().numpy().astype(bool), dbg_o["torso_mask"]) or \
+        (dbg["torso_mask"].cpu().numpy().astype(bool) != dbg_o["torso_mask"]).sum() <= 2
+    p = psnr(f32.cpu().numpy(), img_ref)
+    assert p >= 40.0, f"PSNR {p:.2f} dB"                          # tolerance stated in SURVEY.md 7.3
+    d8 = np.abs(out.cpu().numpy().astype(int) - u8_ref.astype(int))
+    assert np.percentile(d8, 99) <= 2
+
+
+def test_explicit_rays_first_march_bit_exact(env):
+    """fed the same rays, nears/fars and the first-round sample count are bit-exact."""
+    from oracle import ernerf_oracle as O
+    ren, orc = env["ren"], env["orc"]
+    H = 80
+    pose, intr, auds, eye, ro, rd = _rays(H, 3)
+    sub = np.arange(0, H * H, 3)                       # "2048 rays"-style subset: 2134 rays
+    ro, rd = np.ascontiguousarray(ro[sub]), np.ascontiguousarray(rd[sub])
+    bgc = np.ascontiguousarray(O.get_bg_coords(H, H)[sub])
+    ren.reset()
+    orc.enc_a_prev = None
+    dbg_o = {}
+    img_ref = orc.run_cuda(ro, rd, auds, bgc, pose, eye, np.ones((len(sub), 3), np.float16), debug=dbg_o)
+    f32 = torch.empty(1, len(sub), 3, device="cuda")
+    out, dbg = ren.render(pose, intr, H, H, cu(auds), eye, rays_o=cu(ro), rays_d=cu(rd), bg_coords=cu(bgc),
+                          out_f32=f32, debug=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(dbg["nears"].cpu().numpy(), dbg_o["nears"])
+    assert np.array_equal(dbg["fars"].cpu().numpy(), dbg_o["fars"])
+    ri = dbg["round_info"].cpu().numpy()
+    assert (int(ri[0, 0]), int(ri[0, 3]), int(ri[0, 2])) == dbg_o["rounds"][0]
+    assert np.array_equal(dbg["torso_mask"].cpu().numpy().astype(bool), dbg_o["torso_mask"])
+    assert psnr(f32.cpu().numpy().reshape(-1, 3), img_ref) >= 40.0
+
+
+def test_ema_state_and_resize(env):
+    ren, orc = env["ren"], env["orc"]
+    H = 64
+    ren.reset()
+    orc.enc_a_prev = None
+    for frame in (0, 1, 2):
+        pose, intr, auds, eye = ernerf_inputs(frame, H, H)
+        dbg_o = {}
+        img_ref, u8_ref = orc.render_frame(pose, intr, H, H, auds, eye, outH=96, outW=80, debug=dbg_o)
+        f32 = torch.empty(96, 80, 3, device="cuda")
+        out, dbg = ren.render(pose, intr, H, H, cu(auds), eye, outH=96, outW=80, out_f32=f32, debug=True)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(dbg["enc_a"].cpu().numpy(), dbg_o["enc_a"][0], rtol=0, atol=2e-3)
+        assert out.shape == (96, 80, 3)
+        assert psnr(f32.cpu().numpy(), img_ref) >= 40.0
