@@ -81,6 +81,11 @@ int mf_grid_encode_forward(mf_ctx *ctx, const float *inputs, const void *embeddi
                            uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
                            int align_corners, int embeddings_is_half, void *stream);
 
+/* The per-level scale `exp2f(level * S) * H - 1.0f` (gridencoder.cu:124) as the device evaluates it
+ * (CUDA exp2f is approximate): scales_host is a HOST array of L floats.  Lets a CPU checker use
+ * the very constants the kernels use.  Synchronises. */
+int mf_grid_level_scales(mf_ctx *ctx, float S, uint32_t H, uint32_t L, float *scales_host);
+
 /* ernerf/shencoder/src/shencoder.h:9  sh_encode_forward, degree C = 4 (kernel shencoder.cu:27-68) */
 int mf_sh_encode_forward(mf_ctx *ctx, const float *inputs, float *outputs, uint32_t B, uint32_t D,
                          uint32_t C, void *stream);
@@ -156,6 +161,14 @@ int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *frame /*host*/, uint8_t
                      const mf_ernerf_debug *dbg /*host, nullable*/, void *stream);
 /* forget the audio-feature EMA (a new session on a reused context) */
 int mf_ernerf_reset_state(mf_ctx *ctx);
+/* offsets of the packed-blob MLP images (csrc/ernerf_layout.h) for the Python packer; returns the
+ * number of values defined and writes min(n, that) of them. */
+int mf_ernerf_blob_layout(int32_t *out, int n);
+/* measurement hooks (bench.py roofline): with profiling enabled every mf_ernerf_render records CUDA
+ * events around the dominant kernel (k_head) on the launching stream; mf_ernerf_last_head_ms waits
+ * for the last one and returns its duration and the number of samples it marched+shaded. */
+int mf_ernerf_profile(mf_ctx *ctx, int enable);
+int mf_ernerf_last_head_ms(mf_ctx *ctx, float *ms /*host*/, int64_t *samples /*host*/);
 /* kernels launched by the last mf_ernerf_render on this context */
 int mf_ernerf_last_launches(const mf_ctx *ctx);
 

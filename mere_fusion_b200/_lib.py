@@ -62,6 +62,8 @@ def lib():
                                        ctypes.POINTER(MfErnerfDebug), c_vp]
         L.mf_ernerf_reset_state.argtypes = [c_vp]
         L.mf_ernerf_last_launches.argtypes = [c_vp]
+        L.mf_ernerf_profile.argtypes = [c_vp, ctypes.c_int]
+        L.mf_ernerf_last_head_ms.argtypes = [c_vp, ctypes.POINTER(c_f), ctypes.POINTER(ctypes.c_int64)]
         L.mf_ernerf_blob_layout.argtypes = [ctypes.POINTER(c_i32), ctypes.c_int]
         L.mf_near_far_from_aabb.argtypes = [c_vp, c_vp, c_vp, c_vp, c_u32, c_f, c_vp, c_vp, c_vp]
         L.mf_march_rays.argtypes = [c_vp, c_u32, c_u32, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_u32, c_u32, c_u32,
@@ -69,6 +71,7 @@ def lib():
         L.mf_composite_rays_triplane.argtypes = [c_vp, c_u32, c_u32, c_f] + [c_vp] * 15
         L.mf_grid_encode_forward.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_u32, c_f,
                                              c_u32, c_u32, ctypes.c_int, ctypes.c_int, c_vp]
+        L.mf_grid_level_scales.argtypes = [c_vp, c_f, c_u32, c_u32, ctypes.POINTER(c_f)]
         L.mf_sh_encode_forward.argtypes = [c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_vp]
         L.mf_freq_encode_forward.argtypes = [c_vp, c_vp, c_u32, c_u32, c_u32, c_u32, c_vp, c_vp]
         _lib = L

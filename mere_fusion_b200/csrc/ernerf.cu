@@ -68,7 +68,9 @@ struct ErnerfState {
     float *final_f32 = nullptr;  // [N,3] when a resize follows
     int head_grid = 0;
     int last_launches = 0;
-    float misc_host[24] = {0};  // anchor_points[12], individual_codes[0], individual_codes_torso[0]
+    float misc_host[24] = {0};
+    bool profile = false;  // CUDA events around k_head on the launching stream (bench roofline)
+    cudaEvent_t ev_head[2] = {nullptr, nullptr};  // anchor_points[12], individual_codes[0], individual_codes_torso[0]
 };
 
 // =========================================================================================
@@ -1007,6 +1009,7 @@ void ernerf_destroy(mf_ctx *ctx) {
     ernerf_free_ws(s);
     cudaFree(s->state);
     cudaFree(s->counters);
+    if (s->ev_head[0]) { cudaEventDestroy(s->ev_head[0]); cudaEventDestroy(s->ev_head[1]); }
     delete s;
     ctx->ernerf = nullptr;
 }
@@ -1098,6 +1101,34 @@ extern "C" int mf_ernerf_reset_state(mf_ctx *ctx) {
     if (!ctx) return MF_E_INVALID;
     if (!ctx->ernerf) return mf_fail(ctx, MF_E_STATE, "ErNeRF weights not loaded");
     MF_CUDA(ctx, cudaMemset(ctx->ernerf->state, 0, 64 * sizeof(float)));
+    return MF_OK;
+}
+
+extern "C" int mf_ernerf_profile(mf_ctx *ctx, int enable) {
+    if (!ctx) return MF_E_INVALID;
+    ErnerfState *s = ctx->ernerf;
+    if (!s) return mf_fail(ctx, MF_E_STATE, "ErNeRF weights not loaded");
+    if (enable && !s->ev_head[0]) {
+        MF_CUDA(ctx, cudaEventCreate(&s->ev_head[0]));
+        MF_CUDA(ctx, cudaEventCreate(&s->ev_head[1]));
+    }
+    s->profile = enable != 0;
+    return MF_OK;
+}
+
+extern "C" int mf_ernerf_last_head_ms(mf_ctx *ctx, float *ms, int64_t *samples) {
+    if (!ctx) return MF_E_INVALID;
+    ErnerfState *s = ctx->ernerf;
+    if (!s || !s->ev_head[0]) return mf_fail(ctx, MF_E_STATE, "profiling not enabled");
+    MF_CUDA(ctx, cudaEventSynchronize(s->ev_head[1]));
+    if (ms) MF_CUDA(ctx, cudaEventElapsedTime(ms, s->ev_head[0], s->ev_head[1]));
+    if (samples) {
+        int ctr[(ER_MAX_ROUNDS + 1) * ER_CTR_STRIDE];
+        MF_CUDA(ctx, cudaMemcpy(ctr, s->counters, sizeof(ctr), cudaMemcpyDeviceToHost));
+        int64_t tot = 0;
+        for (int r = 0; r <= ER_MAX_ROUNDS; r++) tot += ctr[r * ER_CTR_STRIDE + 2];
+        *samples = tot;
+    }
     return MF_OK;
 }
 
@@ -1213,8 +1244,10 @@ extern "C" int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *f, uint8_t *
     {
         void *args[] = {&hp};
         const int grid = std::min(s->head_grid, std::max(1, (N + 31) / 32 / HEAD_WARPS + 1));
+        if (s->profile) MF_CUDA(ctx, cudaEventRecord(s->ev_head[0], stream));
         MF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_head, dim3(grid), dim3(HEAD_THREADS), args,
                                                  sizeof(HeadSmem), stream));
+        if (s->profile) MF_CUDA(ctx, cudaEventRecord(s->ev_head[1], stream));
         launches++;
     }
 
@@ -1317,6 +1350,12 @@ extern "C" int mf_grid_encode_forward(mf_ctx *ctx, const float *inputs, const vo
     k_grid_encode<<<dim3((B + 255) / 256, L), 256, 0, stream>>>(inputs, embeddings, lv, outputs, B, C, embeddings_is_half);
     MF_CUDA(ctx, cudaGetLastError());
     return MF_OK;
+}
+
+extern "C" int mf_grid_level_scales(mf_ctx *ctx, float S, uint32_t H, uint32_t L, float *scales_host) {
+    if (!ctx) return MF_E_INVALID;
+    MF_REQUIRE(ctx, scales_host && L >= 1 && L <= 16, "mf_grid_level_scales: bad arguments");
+    return compute_scales(ctx, S, H, (int)L, scales_host);
 }
 
 extern "C" int mf_sh_encode_forward(mf_ctx *ctx, const float *inputs, float *outputs, uint32_t B, uint32_t D,

@@ -35,6 +35,31 @@ class ErnerfRenderer:
     def reset(self):
         check(self.ctx.handle, lib().mf_ernerf_reset_state(self.ctx.handle), "mf_ernerf_reset_state")
 
+    def profile(self, enable=True):
+        check(self.ctx.handle, lib().mf_ernerf_profile(self.ctx.handle, int(enable)), "mf_ernerf_profile")
+
+    def last_head_ms(self):
+        """(duration of the last k_head launch in ms, samples it processed); synchronises"""
+        ms, n = ctypes.c_float(), ctypes.c_int64()
+        check(self.ctx.handle, lib().mf_ernerf_last_head_ms(self.ctx.handle, ctypes.byref(ms), ctypes.byref(n)),
+              "mf_ernerf_last_head_ms")
+        return ms.value, n.value
+
+    def render_host(self, pose, intrinsics, H, W, auds_pinned, eye, out_pinned, stage=None, **kw):
+        """end-to-end call with HOST buffers: pinned fp32 auds in, pinned u8 frame out; both copies are
+        enqueued on the current stream around the render (what NeRFReal.test_step does per frame)."""
+        if stage is None:
+            stage = self._stage = getattr(self, "_stage", None) or {}
+        key = (tuple(auds_pinned.shape), tuple(out_pinned.shape))
+        if key not in stage:
+            stage[key] = (torch.empty(auds_pinned.shape, dtype=torch.float32, device=self.device),
+                          torch.empty(out_pinned.shape, dtype=torch.uint8, device=self.device))
+        d_auds, d_out = stage[key]
+        d_auds.copy_(auds_pinned, non_blocking=True)
+        self.render(pose, intrinsics, H, W, d_auds, eye, out=d_out, **kw)
+        out_pinned.copy_(d_out, non_blocking=True)
+        return out_pinned
+
     @property
     def last_launches(self):
         return lib().mf_ernerf_last_launches(self.ctx.handle)

@@ -220,12 +220,16 @@ static inline uint32_t grid_index2(uint32_t gridtype, int align_corners, uint32_
 }
 
 /* gridencoder.cu:75-175, D = 2.  outputs are [L, B, C] like the kernel's; the permute to
- * [B, L*C] (gridencoder/grid.py:52) is done by the caller.  S = log2(per_level_scale) as float. */
+ * [B, L*C] (gridencoder/grid.py:52) is done by the caller.  S = log2(per_level_scale) as float.
+ * `scales` (nullable) overrides the per-level scale: CUDA's exp2f is a 2-ulp approximation
+ * (MUFU.EX2), so glibc's exp2f differs from it in the last bit on some levels; feeding the
+ * device-evaluated scales (tests/golden/ernerf_level_scales.json, or mf_grid_level_scales on the
+ * GPU box) makes this restatement bit-exact against the reference kernel. */
 #define GRID_BODY(SCALAR, ACCUM)                                                                   \
     for (uint32_t level = 0; level < L; level++) {                                                 \
         const SCALAR *g = grid + (size_t)(uint32_t)offsets[level] * C;                             \
         const uint32_t hashmap_size = offsets[level + 1] - offsets[level];                         \
-        const float scale = exp2f(level * S) * H - 1.0f;                                           \
+        const float scale = scales ? scales[level] : exp2f(level * S) * H - 1.0f;                  \
         const uint32_t resolution = (uint32_t)ceilf(scale) + 1;                                    \
         _Pragma("omp parallel for schedule(static)")                                               \
         for (uint32_t b = 0; b < B; b++) {                                                         \
@@ -259,7 +263,7 @@ static inline uint32_t grid_index2(uint32_t gridtype, int align_corners, uint32_
  * contracted to an fma by nvcc */
 void orc_grid_encode_f32(const float *inputs, const float *grid, const int *offsets, float *outputs,
                          uint32_t B, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
-                         int align_corners) {
+                         int align_corners, const float *scales) {
     GRID_BODY(float, res[ch] = fmaf(w, g[gi + ch], res[ch]))
 }
 
@@ -268,7 +272,7 @@ void orc_grid_encode_f32(const float *inputs, const float *grid, const int *offs
  * (c10/util/Half-inl.h operator+= / operator+) */
 void orc_grid_encode_f16(const float *inputs, const half_t *grid, const int *offsets, half_t *outputs,
                          uint32_t B, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
-                         int align_corners) {
+                         int align_corners, const float *scales) {
     GRID_BODY(half_t, res[ch] = (half_t)((float)res[ch] + (float)(half_t)(w * (float)g[gi + ch])))
 }
 

@@ -1,10 +1,12 @@
 """GPU parity: sm_100a ErNeRF kernels (through the C ABI) vs the CPU oracle, real checkpoint."""
 import ctypes
+import json
+import os
 
 import numpy as np
 import pytest
 
-from helpers import ernerf_inputs, load_ernerf_fixture, psnr
+from helpers import GOLD, ernerf_inputs, load_ernerf_fixture, psnr
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -18,6 +20,14 @@ def env():
     sd, md = load_ernerf_fixture()
     ren = ErnerfRenderer(sd, md, device=0)
     orc = ErnerfOracle(sd, md)
+    # the oracle uses the level scales as the device evaluates them (CUDA exp2f is approximate)
+    ctx = ren.ctx
+    for name, S, base, L in (("head_scales", ren.cfg.head_log2_scale, 64, 12), ("torso_scales", ren.cfg.torso_log2_scale, 16, 16)):
+        buf = (ctypes.c_float * L)()
+        assert lib().mf_grid_level_scales(ctx.handle, S, base, L, buf) == 0
+        setattr(orc, name, np.array(list(buf), np.float32))
+    gold = json.load(open(os.path.join(GOLD, "ernerf_level_scales.json")))
+    assert gold["head"] == [float(v) for v in orc.head_scales] and gold["torso"] == [float(v) for v in orc.torso_scales]
     return dict(sd=sd, md=md, ren=ren, orc=orc, lib=lib(), ctx=Context(0))
 
 
@@ -25,8 +35,22 @@ def P(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_KEEP = []
+
+
 def cu(a):
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    """host array -> cuda tensor, kept alive until the end of the test (kernels are asynchronous
+    and only see raw pointers)"""
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    _KEEP.append(t)
+    return t
+
+
+@pytest.fixture(autouse=True)
+def _release():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
 
 
 def _rays(H=96, frame=0):
@@ -119,7 +143,7 @@ def test_grid_encode_head_plane(env):
     x[:5] = [[0, 0], [1, 1], [0, 1], [0.5, 0.5], [1.0000001, 0.2]]     # corners + one out-of-range point
     emb = env["sd"]["encoder_xy.embeddings"].astype(np.float32)
     off = env["sd"]["encoder_xy.offsets"].astype(np.int32)
-    ref = O.grid_encode(x, emb, off, env["orc"].hs, 64, 0)
+    ref = O.grid_encode(x, emb, off, env["orc"].hs, 64, 0, scales=env["orc"].head_scales)
     out = torch.empty(12, B, 1, device="cuda")
     rc = env["lib"].mf_grid_encode_forward(env["ctx"].handle, P(cu(x)), P(cu(emb)), P(cu(off)), P(out), B, 2, 1, 12,
                                            float(np.log2(env["orc"].hs)), 64, 0, 0, 0, None)
@@ -136,7 +160,7 @@ def test_grid_encode_torso_fp16(env):
     x = rng.random((B, 2)).astype(np.float32)
     emb = env["sd"]["torso_encoder.embeddings"].astype(np.float16)
     off = env["sd"]["torso_encoder.offsets"].astype(np.int32)
-    ref = O.grid_encode(x, emb, off, env["orc"].ts, 16, 1, half=True)
+    ref = O.grid_encode(x, emb, off, env["orc"].ts, 16, 1, half=True, scales=env["orc"].torso_scales)
     out = torch.empty(16, B, 2, device="cuda", dtype=torch.float16)
     rc = env["lib"].mf_grid_encode_forward(env["ctx"].handle, P(cu(x)), P(cu(emb)), P(cu(off)), P(out), B, 2, 2, 16,
                                            float(np.log2(env["orc"].ts)), 16, 1, 0, 1, None)
@@ -165,7 +189,7 @@ def test_sh_and_freq(env):
 
 def test_unsupported_and_errors(env):
     L, ctx = env["lib"], env["ctx"]
-    assert L.mf_sh_encode_forward(ctx.handle, P(torch.zeros(3, device="cuda")), P(torch.zeros(16, device="cuda")), 1, 3, 6, None) == -4
+    assert L.mf_sh_encode_forward(ctx.handle, P(cu(np.zeros(3, np.float32))), P(cu(np.zeros(16, np.float32))), 1, 3, 6, None) == -4
     assert L.mf_near_far_from_aabb(ctx.handle, None, None, None, 1, 0.05, None, None, None) == -1
     assert b"null pointer" in L.mf_last_error(ctx.handle)
     from mere_fusion_b200._lib import Context, MfErnerfFrame

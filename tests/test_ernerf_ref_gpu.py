@@ -2,12 +2,14 @@
 /root/reference/ernerf/*/src for sm_100).  This is what pins the C oracle and the sm_100a
 kernels to the reference: integer-valued outputs and fp32 paths are compared bit-exactly."""
 import ctypes
+import json
+import os
 
 import numpy as np
 import pytest
 
 import ref_ernerf
-from helpers import ernerf_inputs, load_ernerf_fixture
+from helpers import GOLD, ernerf_inputs, load_ernerf_fixture
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -20,15 +22,33 @@ def env():
     from mere_fusion_b200._lib import Context, lib
     from oracle.ernerf_oracle import ErnerfOracle
     sd, md = load_ernerf_fixture()
-    return dict(sd=sd, ref=ref_ernerf.load(), lib=lib(), ctx=Context(0), orc=ErnerfOracle(sd, md))
+    orc = ErnerfOracle(sd, md)
+    gold = json.load(open(os.path.join(GOLD, "ernerf_level_scales.json")))   # device-evaluated exp2f
+    orc.head_scales = np.array(gold["head"], np.float32)
+    orc.torso_scales = np.array(gold["torso"], np.float32)
+    return dict(sd=sd, ref=ref_ernerf.load(), lib=lib(), ctx=Context(0), orc=orc)
 
 
 def P(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_KEEP = []
+
+
 def cu(a):
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    """host array -> cuda tensor, kept alive until the end of the test (kernels are asynchronous
+    and only see raw pointers)"""
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    _KEEP.append(t)
+    return t
+
+
+@pytest.fixture(autouse=True)
+def _release():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
 
 
 def _setup(H=128, frame=0):
@@ -128,7 +148,7 @@ def test_encoders_vs_reference(env):
     torch.cuda.synchronize()
     assert torch.equal(o_r, o_m)
     from oracle import ernerf_oracle as O
-    o_o = O.grid_encode(x.cpu().numpy(), emb.cpu().numpy(), off.cpu().numpy(), orc.hs, 64, 0)
+    o_o = O.grid_encode(x.cpu().numpy(), emb.cpu().numpy(), off.cpu().numpy(), orc.hs, 64, 0, scales=orc.head_scales)
     assert np.array_equal(o_o, o_r.cpu().numpy().transpose(1, 0, 2).reshape(B, 12))
     # torso, fp16, tiled
     emb = cu(env["sd"]["torso_encoder.embeddings"].astype(np.float16))
@@ -140,7 +160,7 @@ def test_encoders_vs_reference(env):
     assert L.mf_grid_encode_forward(ctx.handle, P(x), P(emb), P(off), P(o_m), B, 2, 2, 16, S, 16, 1, 0, 1, None) == 0
     torch.cuda.synchronize()
     assert torch.equal(o_r, o_m)
-    o_o = O.grid_encode(x.cpu().numpy(), emb.cpu().numpy(), off.cpu().numpy(), orc.ts, 16, 1, half=True)
+    o_o = O.grid_encode(x.cpu().numpy(), emb.cpu().numpy(), off.cpu().numpy(), orc.ts, 16, 1, half=True, scales=orc.torso_scales)
     assert np.array_equal(o_o, o_r.cpu().numpy().transpose(1, 0, 2).reshape(B, 32))
     # SH degree 4
     d = rng.standard_normal((B, 3)).astype(np.float32)
