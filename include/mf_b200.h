@@ -172,6 +172,32 @@ int mf_ernerf_last_head_ms(mf_ctx *ctx, float *ms /*host*/, int64_t *samples /*h
 /* kernels launched by the last mf_ernerf_render on this context */
 int mf_ernerf_last_launches(const mf_ctx *ctx);
 
+/* ------------------------------------------------------------------------------------------
+ * Wav2Lip: replaces the model(mel_batch, img_batch) call and the batch build / x255 around it in
+ * the reference's inference() loop (lipreal.py:108-126; network wav2lip/models/wav2lip.py:87-125).
+ * ------------------------------------------------------------------------------------------ */
+
+/* `blob` = DEVICE-resident conv-net program + weights from mere_fusion_b200.wav2lip_pack.pack_wav2lip
+ * (BatchNorm folded to per-channel scale/shift, weights bf16).  Activation buffers are allocated
+ * for max_batch frames.  The blob must stay alive until mf_destroy.  Synchronises. */
+int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int max_batch);
+
+/* mel    : device fp32 [B,1,80,16]   (LipASR.run_step chunks, lipasr.py:29-35)
+ * faces  : device u8  [B,S,S,3] BGR  (the avatar face crops, lipreal.py:109-111); the lower-half mask,
+ *          the 6-channel concat and /255 happen inside
+ * out_u8 : device u8  [B,S,S,3] = (sigmoid * 255) truncated  (lipreal.py:126,209), nullable
+ * out_f32: device fp32 [B,S,S,3] in (0,1) (what `pred.cpu().numpy().transpose(0,2,3,1)` holds), nullable */
+int mf_wav2lip_forward(mf_ctx *ctx, const float *mel, const uint8_t *faces, uint8_t *out_u8, float *out_f32,
+                       int B, void *stream);
+int mf_wav2lip_last_launches(const mf_ctx *ctx);
+/* measurement hooks: record CUDA events around conv op `op_index` (-1 = off) on the launching stream */
+int mf_wav2lip_profile(mf_ctx *ctx, int op_index);
+int mf_wav2lip_last_op_ms(mf_ctx *ctx, float *ms /*host*/);
+/* unit-test entry: run the loaded program on an fp32 NHWC tensor placed in buffer in_buf and read
+ * buffer out_buf back as fp32 NHWC (programs without an output head only) */
+int mf_convnet_debug_run(mf_ctx *ctx, int in_buf, const float *in_f32, int out_buf, float *out_f32, int B,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

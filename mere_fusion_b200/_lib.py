@@ -74,6 +74,12 @@ def lib():
         L.mf_grid_level_scales.argtypes = [c_vp, c_f, c_u32, c_u32, ctypes.POINTER(c_f)]
         L.mf_sh_encode_forward.argtypes = [c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_vp]
         L.mf_freq_encode_forward.argtypes = [c_vp, c_vp, c_u32, c_u32, c_u32, c_u32, c_vp, c_vp]
+        L.mf_wav2lip_load.argtypes = [c_vp, c_vp, ctypes.c_size_t, ctypes.c_int]
+        L.mf_wav2lip_forward.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]
+        L.mf_wav2lip_last_launches.argtypes = [c_vp]
+        L.mf_wav2lip_profile.argtypes = [c_vp, ctypes.c_int]
+        L.mf_wav2lip_last_op_ms.argtypes = [c_vp, ctypes.POINTER(c_f)]
+        L.mf_convnet_debug_run.argtypes = [c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp]
         _lib = L
     return _lib
 

@@ -1,0 +1,164 @@
+"""Program builder for the sm_100a conv-net executor (csrc/wav2lip.cu).
+
+A network is described as a list of implicit-GEMM conv ops over NHWC bf16 buffers; the builder
+turns PyTorch-layout weights (+ BatchNorm statistics) into the padded K-major weight matrices,
+per-channel scale/shift vectors and op records the C side consumes.  Pure host code (numpy).
+"""
+import struct
+
+import numpy as np
+
+from .ernerf_pack import build_blob
+
+CONV_MAX_TAPS = 52
+CONV_BK = 64
+ID_PROGRAM = 1
+ID_FIRST_TENSOR = 16
+SM_COUNT = 148
+
+
+def f32_to_bf16_bits(a):
+    """round-to-nearest-even fp32 -> bf16, returned as uint16"""
+    a = np.ascontiguousarray(a, np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    u = u + 0x7FFF + ((u >> 16) & 1)
+    return (u >> 16).astype(np.uint16)
+
+
+def bn_fold(conv_bias, bn, cout, eps=1e-5):
+    """Conv2d bias + eval-mode BatchNorm2d -> per-channel (scale, shift) applied to the raw conv sum
+    (wav2lip/models/conv.py:8-11)"""
+    bias = np.zeros(cout, np.float32) if conv_bias is None else np.asarray(conv_bias, np.float32)
+    if bn is None:
+        return np.ones(cout, np.float32), bias
+    gamma, beta, mean, var = [np.asarray(t, np.float32) for t in bn]
+    scale = gamma / np.sqrt(var + np.float32(eps))
+    return scale.astype(np.float32), ((bias - mean) * scale + beta).astype(np.float32)
+
+
+class ProgramBuilder:
+    def __init__(self, nominal_batch=16):
+        self.buffers = []
+        self.ops = []
+        self.tensors = {}
+        self.next_id = ID_FIRST_TENSOR
+        self.nominal_batch = nominal_batch
+        self.hdr = dict(in_face_buf=-1, in_mel_buf=-1, face_hw=0, mel_h=0, mel_w=0, out_hw=0)
+        self.flops_per_sample = 0      # algorithmic: 2 * MACs of the original (unpadded) layers
+
+    def buffer(self, H, W, C):
+        assert C % 8 == 0
+        self.buffers.append((H, W, C))
+        return len(self.buffers) - 1
+
+    def _tensor(self, data):
+        i = self.next_id
+        self.next_id += 1
+        self.tensors[i] = data
+        return i
+
+    def _pick_bn(self, cout, M):
+        bn = 128
+        while bn > 16 and (cout % bn != 0 and cout < bn):
+            bn //= 2
+        if cout <= 16:
+            return 16
+        bn = min(bn, 128)
+        while cout % bn != 0 and bn > 16:
+            bn //= 2
+        # small-M layers are weight-bandwidth bound: spread the weight reads over more CTAs
+        while bn > 32 and ((M + 127) // 128) * ((cout + bn - 1) // bn) < SM_COUNT:
+            bn //= 2
+        return bn
+
+    def _emit(self, in_buf, in_coff, cin_pad, out_buf, out_coff, Wm, taps, scale, shift, Mh, Mw, oy0, ox0, osy, osx,
+              isy, isx, res, relu, mode, cout):
+        ntaps = len(taps)
+        assert ntaps <= CONV_MAX_TAPS
+        M = self.nominal_batch * Mh * Mw
+        bn = self._pick_bn(cout, M)
+        cout_pad = (cout + bn - 1) // bn * bn
+        K = ntaps * cin_pad
+        kpad = (K + CONV_BK - 1) // CONV_BK * CONV_BK
+        Wp = np.zeros((cout_pad, kpad), np.float32)
+        Wp[:cout, :K] = Wm
+        sc = np.zeros(cout_pad, np.float32)
+        sh = np.zeros(cout_pad, np.float32)
+        sc[:cout] = scale
+        sh[:cout] = shift
+        w_id = self._tensor(f32_to_bf16_bits(Wp).tobytes())
+        s_id = self._tensor(sc.tobytes())
+        h_id = self._tensor(sh.tobytes())
+        dy = [t[0] for t in taps] + [0] * (CONV_MAX_TAPS - ntaps)
+        dx = [t[1] for t in taps] + [0] * (CONV_MAX_TAPS - ntaps)
+        rb, rc = res if res is not None else (-1, 0)
+        rec = struct.pack("<26i", in_buf, in_coff, out_buf, out_coff, rb, rc, Mh, Mw, oy0, ox0, osy, osx, isy, isx,
+                          ntaps, cin_pad, kpad, cout, cout_pad, bn, int(relu), mode, w_id, s_id, h_id, 0)
+        rec += struct.pack(f"<{CONV_MAX_TAPS}b", *dy) + struct.pack(f"<{CONV_MAX_TAPS}b", *dx)
+        self.ops.append(rec)
+        return len(self.ops) - 1
+
+    def conv(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, bn=None, stride=1, padding=0, res=None,
+             relu=True, mode=0):
+        """nn.Conv2d (+BatchNorm2d, +residual, +ReLU).  weight [Cout, Cin, kh, kw]"""
+        weight = np.asarray(weight, np.float32)
+        cout, cin, kh, kw = weight.shape
+        sy, sx = (stride, stride) if np.isscalar(stride) else stride
+        py, px = (padding, padding) if np.isscalar(padding) else padding
+        Hin, Win, _ = self.buffers[in_buf]
+        Hout, Wout = (Hin + 2 * py - kh) // sy + 1, (Win + 2 * px - kw) // sx + 1
+        if mode == 0:
+            assert self.buffers[out_buf][:2] == (Hout, Wout), (self.buffers[out_buf], Hout, Wout)
+        cin_pad = (cin + 7) // 8 * 8
+        taps = [(ky - py, kx - px) for ky in range(kh) for kx in range(kw)]
+        Wm = np.zeros((cout, len(taps), cin_pad), np.float32)
+        Wm[:, :, :cin] = weight.transpose(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+        scale, shift = bn_fold(bias, bn, cout)
+        self.flops_per_sample += 2 * cout * cin * kh * kw * Hout * Wout
+        return self._emit(in_buf, in_coff, cin_pad, out_buf, out_coff, Wm.reshape(cout, -1), taps, scale, shift, Hout,
+                          Wout, 0, 0, 1, 1, sy, sx, res, relu, mode, cout)
+
+    def conv_transpose(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, bn=None, stride=1, padding=0,
+                       output_padding=0, relu=True):
+        """nn.ConvTranspose2d (+BatchNorm2d +ReLU).  weight [Cin, Cout, kh, kw].  out[oy] gathers
+        in[(oy + p - ky) / s] for the taps where the division is exact: one op per output-parity
+        class, each with only its live taps."""
+        weight = np.asarray(weight, np.float32)
+        cin, cout, kh, kw = weight.shape
+        s, p = stride, padding
+        Hin, Win, _ = self.buffers[in_buf]
+        Hout = (Hin - 1) * s - 2 * p + kh + output_padding
+        Wout = (Win - 1) * s - 2 * p + kw + output_padding
+        assert self.buffers[out_buf][:2] == (Hout, Wout), (self.buffers[out_buf], Hout, Wout)
+        assert cin % 8 == 0
+        scale, shift = bn_fold(bias, bn, cout)
+        self.flops_per_sample += 2 * cout * cin * kh * kw * Hin * Win
+        ids = []
+        for cy in range(s):
+            for cx in range(s):
+                ty = [(ky, (cy + p - ky) // s) for ky in range(kh) if (cy + p - ky) % s == 0]
+                tx = [(kx, (cx + p - kx) // s) for kx in range(kw) if (cx + p - kx) % s == 0]
+                Mh = (Hout - cy + s - 1) // s
+                Mw = (Wout - cx + s - 1) // s
+                if not ty or not tx or Mh <= 0 or Mw <= 0:
+                    raise NotImplementedError("conv_transpose: parity class without taps needs a bias-only op")
+                taps, cols = [], []
+                for ky, dy in ty:
+                    for kx, dx in tx:
+                        taps.append((dy, dx))
+                        cols.append(weight[:, :, ky, kx].T)          # [Cout, Cin]
+                Wm = np.stack(cols, 1).reshape(cout, -1)
+                ids.append(self._emit(in_buf, in_coff, cin, out_buf, out_coff, Wm, taps, scale, shift, Mh, Mw, cy, cx,
+                                      s, s, 1, 1, None, relu, 0, cout))
+        return ids
+
+    def finish(self):
+        h = self.hdr
+        prog = struct.pack("<8i", len(self.buffers), len(self.ops), h["in_face_buf"], h["in_mel_buf"], h["face_hw"],
+                           h["mel_h"], h["mel_w"], h["out_hw"])
+        for (H, W, C) in self.buffers:
+            prog += struct.pack("<4i", H, W, C, 0)
+        prog += b"".join(self.ops)
+        entries = {ID_PROGRAM: prog}
+        entries.update(self.tensors)
+        return build_blob(entries, kind=2)

@@ -35,8 +35,17 @@ using namespace ernerf;
 #define ER_CTR_STRIDE 32 /* ints per counter row */
 // counters layout (ints): [0] n_alive[r], [1] tile ticket[r], [2] samples emitted[r], [3] n_step[r]
 
-struct HeadLevels { GridLevel lv[MF_ERNERF_HEAD_LEVELS]; };
-struct TorsoLevels { GridLevel lv[MF_ERNERF_TORSO_LEVELS]; };
+// levels [0, n_dense) are IDX_DENSE, the rest IDX_HASH2 (head) / IDX_TILE2 (torso); n_dense < 0: generic
+struct HeadLevels { GridLevel lv[MF_ERNERF_HEAD_LEVELS]; int n_dense; };
+struct TorsoLevels { GridLevel lv[MF_ERNERF_TORSO_LEVELS]; int n_dense; };
+
+static int classify_levels(const GridLevel *lv, int L, int tail_class) {
+    int n = 0;
+    while (n < L && grid_level_class(lv[n]) == IDX_DENSE) n++;
+    for (int l = n; l < L; l++)
+        if (grid_level_class(lv[l]) != tail_class) return -1;
+    return n;
+}
 
 struct FrameGeom {
     int N, H, W;
@@ -445,6 +454,32 @@ __device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, __half *xs, co
     }
 }
 
+// enc_x of one sample -> fp16 row of the warp's tile.  ND = number of leading dense levels (the shipped
+// architecture has 4: base 64, 512 desired, 2^14 hash rows); ND < 0 = generic indexing.
+template <int ND>
+__device__ __forceinline__ void gather_planes(const HeadParams &p, float x, float y, float z, __half *row) {
+    const float rb = 1.0f / (2.0f * p.bound);
+    const float u[3] = {(x + p.bound) * rb, (y + p.bound) * rb, (z + p.bound) * rb};
+#pragma unroll
+    for (int pl = 0; pl < 3; pl++) {
+        const float a = (pl == 1) ? u[1] : u[0];
+        const float b = (pl == 0) ? u[1] : u[2];
+        const float *tab = p.planes + (size_t)pl * p.plane_rows;
+        float f[12];
+#pragma unroll
+        for (int l = 0; l < 12; l++) {
+            if (ND < 0) f[l] = grid_level_f32<IDX_ANY>(tab, p.hl.lv[l], a, b);
+            else if (l < ND) f[l] = grid_level_f32<IDX_DENSE>(tab, p.hl.lv[l], a, b);
+            else f[l] = grid_level_f32<IDX_HASH2>(tab, p.hl.lv[l], a, b);
+        }
+#pragma unroll
+        for (int l = 0; l < 6; l++)
+            *reinterpret_cast<uint32_t *>(row + pl * 12 + 2 * l) = pack_half2(f[2 * l], f[2 * l + 1]);
+    }
+#pragma unroll
+    for (int i = 18; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
+}
+
 __global__ void __launch_bounds__(HEAD_THREADS, 2) k_head(const __grid_constant__ HeadParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     HeadSmem &sm = *reinterpret_cast<HeadSmem *>(smem_raw);
@@ -534,22 +569,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) k_head(const __grid_constant_
                 // ---- tri-plane gather: 3 planes x 12 levels x 4 corners, fp32 (gridencoder.cu:75-175)
                 __half *row = xs + lane * XS_STRIDE;
                 if (has) {
-                    const float rb = 1.0f / (2.0f * p.bound);
-                    const float u[3] = {(x + p.bound) * rb, (y + p.bound) * rb, (z + p.bound) * rb};
-#pragma unroll
-                    for (int pl = 0; pl < 3; pl++) {
-                        const float a = (pl == 1) ? u[1] : u[0];
-                        const float b = (pl == 0) ? u[1] : u[2];
-                        const float *tab = p.planes + (size_t)pl * p.plane_rows;
-                        float f[12];
-#pragma unroll
-                        for (int l = 0; l < 12; l++) f[l] = grid_level_f32(tab, p.hl.lv[l], a, b);
-#pragma unroll
-                        for (int l = 0; l < 6; l++)
-                            *reinterpret_cast<uint32_t *>(row + pl * 12 + 2 * l) = pack_half2(f[2 * l], f[2 * l + 1]);
-                    }
-#pragma unroll
-                    for (int i = 18; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
+                    if (p.hl.n_dense == 4) gather_planes<4>(p, x, y, z, row);
+                    else gather_planes<-1>(p, x, y, z, row);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
@@ -742,7 +763,9 @@ __global__ void __launch_bounds__(TORSO_THREADS) k_torso_compose(const __grid_co
 #pragma unroll
                 for (int l = 0; l < MF_ERNERF_TORSO_LEVELS; l++) {
                     float o0, o1;
-                    grid_level_f16x2(p.table, p.tl.lv[l], u, v, o0, o1);
+                    if (p.tl.n_dense < 0) grid_level_f16x2<IDX_ANY>(p.table, p.tl.lv[l], u, v, o0, o1);
+                    else if (l < p.tl.n_dense) grid_level_f16x2<IDX_DENSE>(p.table, p.tl.lv[l], u, v, o0, o1);
+                    else grid_level_f16x2<IDX_TILE2>(p.table, p.tl.lv[l], u, v, o0, o1);
                     *reinterpret_cast<uint32_t *>(row + 2 * l) = pack_half2(o0, o1);
                 }
             } else {
@@ -949,10 +972,10 @@ __global__ void k_grid_encode(const float *__restrict__ inputs, const void *__re
     const float u = inputs[b * 2], v = inputs[b * 2 + 1];
     if (!is_half) {  // C == 1
         reinterpret_cast<float *>(outputs)[(size_t)level * B + b] =
-            grid_level_f32(reinterpret_cast<const float *>(table), lv.lv[level], u, v);
+            grid_level_f32<IDX_ANY>(reinterpret_cast<const float *>(table), lv.lv[level], u, v);
     } else {  // C == 2
         float o0, o1;
-        grid_level_f16x2(reinterpret_cast<const __half2 *>(table), lv.lv[level], u, v, o0, o1);
+        grid_level_f16x2<IDX_ANY>(reinterpret_cast<const __half2 *>(table), lv.lv[level], u, v, o0, o1);
         reinterpret_cast<__half2 *>(outputs)[(size_t)level * B + b] = __floats2half2_rn(o0, o1);
     }
 }
@@ -1078,9 +1101,11 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
     int rc = compute_scales(ctx, cfg->head_log2_scale, cfg->head_base, MF_ERNERF_HEAD_LEVELS, sc);
     if (rc) return rc;
     fill_levels(s->hl.lv, MF_ERNERF_HEAD_LEVELS, sc, cfg->head_offsets, 0);
+    s->hl.n_dense = classify_levels(s->hl.lv, MF_ERNERF_HEAD_LEVELS, IDX_HASH2);
     rc = compute_scales(ctx, cfg->torso_log2_scale, cfg->torso_base, MF_ERNERF_TORSO_LEVELS, sc);
     if (rc) return rc;
     fill_levels(s->tl.lv, MF_ERNERF_TORSO_LEVELS, sc, cfg->torso_offsets, 1);
+    s->tl.n_dense = classify_levels(s->tl.lv, MF_ERNERF_TORSO_LEVELS, IDX_TILE2);
 
     MF_CUDA(ctx, cudaMalloc(&s->state, 128 * sizeof(float)));
     MF_CUDA(ctx, cudaMemset(s->state, 0, 128 * sizeof(float)));

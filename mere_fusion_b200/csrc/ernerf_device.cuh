@@ -29,7 +29,33 @@ __device__ __forceinline__ uint32_t grid_index2(const GridLevel &lv, uint32_t x,
     return index % lv.size;
 }
 
+// Index classes.  get_grid_index is a run-time function of (gridtype, resolution, hashmap_size) in the
+// reference; per level it always reduces to one of three closed forms, selected here at compile time so
+// the 144 corner indices of a sample cost 2-3 instructions each instead of a generic `%`:
+//   IDX_DENSE : x + y * stride1            ((res+1)^2 <= size: no wrap possible)
+//   IDX_HASH2 : (x ^ y * 2654435761) & (size - 1)   (hashed level, size = 2^n)
+//   IDX_TILE2 : (x + y * stride1) & (size - 1)      (tiled level that wraps, size = 2^n)
+//   IDX_ANY   : the generic form
+enum { IDX_ANY = 0, IDX_DENSE = 1, IDX_HASH2 = 2, IDX_TILE2 = 3 };
+
+__host__ __device__ __forceinline__ int grid_level_class(const GridLevel &lv) {
+    const bool yterm = lv.mode & 1u, hashed = lv.mode & 2u, pow2 = lv.mode & 4u;
+    if (hashed) return pow2 ? IDX_HASH2 : IDX_ANY;
+    if (yterm && (uint64_t)lv.stride1 * lv.stride1 <= lv.size) return IDX_DENSE;
+    if (yterm && pow2) return IDX_TILE2;
+    return IDX_ANY;
+}
+
+template <int CLS>
+__device__ __forceinline__ uint32_t grid_index2c(const GridLevel &lv, uint32_t x, uint32_t y) {
+    if (CLS == IDX_DENSE) return x + y * lv.stride1;
+    if (CLS == IDX_HASH2) return (x ^ (y * 2654435761u)) & (lv.size - 1u);
+    if (CLS == IDX_TILE2) return (x + y * lv.stride1) & (lv.size - 1u);
+    return grid_index2(lv, x, y);
+}
+
 // gridencoder.cu:75-175 for D = 2, C = 1, fp32 table: one level of one plane
+template <int CLS>
 __device__ __forceinline__ float grid_level_f32(const float *__restrict__ table, const GridLevel &lv, float u,
                                                 float v) {
     if (u < 0.f || u > 1.f || v < 0.f || v > 1.f) return 0.f;
@@ -39,10 +65,10 @@ __device__ __forceinline__ float grid_level_f32(const float *__restrict__ table,
     const uint32_t gx = (uint32_t)flu, gy = (uint32_t)flv;
     pu -= (float)gx;
     pv -= (float)gy;
-    const float v00 = __ldg(g + grid_index2(lv, gx, gy));
-    const float v10 = __ldg(g + grid_index2(lv, gx + 1, gy));
-    const float v01 = __ldg(g + grid_index2(lv, gx, gy + 1));
-    const float v11 = __ldg(g + grid_index2(lv, gx + 1, gy + 1));
+    const float v00 = __ldg(g + grid_index2c<CLS>(lv, gx, gy));
+    const float v10 = __ldg(g + grid_index2c<CLS>(lv, gx + 1, gy));
+    const float v01 = __ldg(g + grid_index2c<CLS>(lv, gx, gy + 1));
+    const float v11 = __ldg(g + grid_index2c<CLS>(lv, gx + 1, gy + 1));
     float r = 0.f;
     r = fmaf((1 - pu) * (1 - pv), v00, r);
     r = fmaf(pu * (1 - pv), v10, r);
@@ -53,6 +79,7 @@ __device__ __forceinline__ float grid_level_f32(const float *__restrict__ table,
 
 // same kernel instantiated for scalar_t = at::Half, C = 2 (torso encoder under autocast):
 // `results[ch] += w * grid[..]` is Half += float: product rounded to half, sum rounded to half
+template <int CLS>
 __device__ __forceinline__ void grid_level_f16x2(const __half2 *__restrict__ table, const GridLevel &lv, float u,
                                                  float v, float &o0, float &o1) {
     o0 = 0.f;
@@ -64,8 +91,8 @@ __device__ __forceinline__ void grid_level_f16x2(const __half2 *__restrict__ tab
     pu -= (float)gx;
     pv -= (float)gy;
     const float w[4] = {(1 - pu) * (1 - pv), pu * (1 - pv), (1 - pu) * pv, pu * pv};
-    const uint32_t idx[4] = {grid_index2(lv, gx, gy), grid_index2(lv, gx + 1, gy), grid_index2(lv, gx, gy + 1),
-                             grid_index2(lv, gx + 1, gy + 1)};
+    const uint32_t idx[4] = {grid_index2c<CLS>(lv, gx, gy), grid_index2c<CLS>(lv, gx + 1, gy),
+                             grid_index2c<CLS>(lv, gx, gy + 1), grid_index2c<CLS>(lv, gx + 1, gy + 1)};
     __half2 val[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) val[i] = __ldg(g + idx[i]);
@@ -130,7 +157,10 @@ __device__ __forceinline__ void near_far_aabb(float ox, float oy, float oz, floa
 
 struct MarchParams {
     float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Cf;
+    float mip_bound0, mip_rbound0, halfH;  // level-0 constants of the fast path
     uint32_t H;
+    bool fast;  // cascade == 1 and H a power of two: level is always 0 and the double sub-expression
+                // 0.5 * (x * rbound + 1) * H is an exact power-of-two scaling, so fp32 gives the same bits
     const uint8_t *grid;
 };
 
@@ -147,6 +177,10 @@ __device__ __forceinline__ MarchParams make_march_params(float bound, float dt_g
     p.Cf = (float)C;
     p.H = H;
     p.grid = grid;
+    p.mip_bound0 = fminf(1.0f, bound);
+    p.mip_rbound0 = 1 / p.mip_bound0;
+    p.halfH = 0.5f * (float)H;
+    p.fast = (C == 1) && ((H & (H - 1)) == 0);
     return p;
 }
 
@@ -157,20 +191,33 @@ struct Ray {
 // body of the while-loop of kernel_march_rays (raymarching.cu:872-928): advance t until the
 // next occupied voxel; returns true and the sample (x, y, z, dt; t advanced past it), or false
 // once t >= far.
-__device__ __forceinline__ bool march_next(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
-                                           float &y, float &z, float &dt_out, uint32_t &vox) {
+template <bool FAST>
+__device__ __forceinline__ bool march_next_t(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
+                                             float &y, float &z, float &dt_out, uint32_t &vox) {
     while (t < far) {
         x = clampf_(fmaf(t, r.dx, r.ox), -p.bound, p.bound);
         y = clampf_(fmaf(t, r.dy, r.oy), -p.bound, p.bound);
         z = clampf_(fmaf(t, r.dz, r.oz), -p.bound, p.bound);
         const float dt = clampf_(t * p.dt_gamma, p.dt_min, p.dt_max);
-        const int level = max(mip_from_pos(x, y, z, p.Cf), mip_from_dt(dt, p.Hf, p.Cf));
-        const float mip_bound = fminf(scalbnf(1, level), p.bound);
-        const float mip_rbound = 1 / mip_bound;
-        const int nx = clampf_(0.5 * fmaf(x, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
-        const int ny = clampf_(0.5 * fmaf(y, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
-        const int nz = clampf_(0.5 * fmaf(z, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
-        const uint32_t index = level * p.H3 + morton3D(nx, ny, nz);
+        float mip_bound;
+        int nx, ny, nz;
+        uint32_t index;
+        if (FAST) {
+            mip_bound = p.mip_bound0;
+            const float hi = (float)(p.H - 1);
+            nx = clampf_(fmaf(x, p.mip_rbound0, 1.0f) * p.halfH, 0.0f, hi);
+            ny = clampf_(fmaf(y, p.mip_rbound0, 1.0f) * p.halfH, 0.0f, hi);
+            nz = clampf_(fmaf(z, p.mip_rbound0, 1.0f) * p.halfH, 0.0f, hi);
+            index = morton3D(nx, ny, nz);
+        } else {
+            const int level = max(mip_from_pos(x, y, z, p.Cf), mip_from_dt(dt, p.Hf, p.Cf));
+            mip_bound = fminf(scalbnf(1, level), p.bound);
+            const float mip_rbound = 1 / mip_bound;
+            nx = clampf_(0.5 * fmaf(x, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
+            ny = clampf_(0.5 * fmaf(y, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
+            nz = clampf_(0.5 * fmaf(z, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
+            index = level * p.H3 + morton3D(nx, ny, nz);
+        }
         const bool occ = __ldg(p.grid + index / 8) & (1 << (index % 8));
         if (occ) {
             t += dt;
@@ -187,6 +234,12 @@ __device__ __forceinline__ bool march_next(const MarchParams &p, const Ray &r, f
         } while (t < tt);
     }
     return false;
+}
+
+__device__ __forceinline__ bool march_next(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
+                                           float &y, float &z, float &dt_out, uint32_t &vox) {
+    return p.fast ? march_next_t<true>(p, r, t, far, x, y, z, dt_out, vox)
+                  : march_next_t<false>(p, r, t, far, x, y, z, dt_out, vox);
 }
 
 // shencoder.cu:43-68, degree 4

@@ -1,0 +1,121 @@
+"""Pack a reference Wav2Lip state_dict (wav2lip/models/wav2lip.py:12-85, loaded as in
+lipreal.py:42-53) into the conv-net program blob of csrc/wav2lip.cu.
+
+torch.cat((x, feats[-1]), dim=1) (wav2lip.py:107) is realised by letting the decoder block and
+the matching encoder block write into disjoint channel ranges of one "cat" buffer.
+"""
+import numpy as np
+
+from .convnet_pack import ProgramBuilder
+
+# (cout, k, stride, pad, residual) per Conv2d of the reference
+FACE_ENC = [[(16, 7, 1, 3, False)],
+            [(32, 3, 2, 1, False), (32, 3, 1, 1, True), (32, 3, 1, 1, True)],
+            [(64, 3, 2, 1, False), (64, 3, 1, 1, True), (64, 3, 1, 1, True), (64, 3, 1, 1, True)],
+            [(128, 3, 2, 1, False), (128, 3, 1, 1, True), (128, 3, 1, 1, True)],
+            [(256, 3, 2, 1, False), (256, 3, 1, 1, True), (256, 3, 1, 1, True)],
+            [(512, 3, 2, 1, False), (512, 3, 1, 1, True)],
+            [(512, 3, 1, 0, False), (512, 1, 1, 0, False)]]
+AUDIO_ENC = [(32, 3, (1, 1), 1, False), (32, 3, (1, 1), 1, True), (32, 3, (1, 1), 1, True),
+             (64, 3, (3, 1), 1, False), (64, 3, (1, 1), 1, True), (64, 3, (1, 1), 1, True),
+             (128, 3, (3, 3), 1, False), (128, 3, (1, 1), 1, True), (128, 3, (1, 1), 1, True),
+             (256, 3, (3, 2), 1, False), (256, 3, (1, 1), 1, True),
+             (512, 3, (1, 1), 0, False), (512, 1, (1, 1), 0, False)]
+# decoder blocks: first layer + residual convs; ('c' conv | 't' transpose, cout, k, stride, pad, out_pad)
+FACE_DEC = [[("c", 512, 1, 1, 0, 0)],
+            [("t", 512, 3, 1, 0, 0), ("r", 512)],
+            [("t", 512, 3, 2, 1, 1), ("r", 512), ("r", 512)],
+            [("t", 384, 3, 2, 1, 1), ("r", 384), ("r", 384)],
+            [("t", 256, 3, 2, 1, 1), ("r", 256), ("r", 256)],
+            [("t", 128, 3, 2, 1, 1), ("r", 128), ("r", 128)],
+            [("t", 64, 3, 2, 1, 1), ("r", 64), ("r", 64)]]
+
+
+def _np(v):
+    return v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+
+
+def strip_module_prefix(sd):
+    """lipreal.py:47-50"""
+    return {k.replace("module.", ""): v for k, v in sd.items()}
+
+
+def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
+    sd = {k: _np(v) for k, v in strip_module_prefix(sd).items()}
+
+    def block(prefix):
+        cb = prefix + ".conv_block"
+        return (sd[cb + ".0.weight"], sd[cb + ".0.bias"],
+                (sd[cb + ".1.weight"], sd[cb + ".1.bias"], sd[cb + ".1.running_mean"], sd[cb + ".1.running_var"]))
+
+    pb = ProgramBuilder(nominal_batch)
+    S = face_hw
+    # spatial size of every encoder stage (96, 48, 24, 12, 6, 3, 1 for 96x96)
+    sizes = [S]
+    for blk in FACE_ENC[1:]:
+        _, k, s, p, _ = blk[0]
+        sizes.append((sizes[-1] + 2 * p - k) // s + 1)
+    enc_c = [blk[-1][0] for blk in FACE_ENC]                      # 16, 32, 64, 128, 256, 512, 512
+    dec_c = [blk[0][1] for blk in FACE_DEC]                       # 512, 512, 512, 384, 256, 128, 64
+    # cat buffer i holds [decoder block (6 - i) output | encoder block i output] at resolution sizes[i]
+    cat = [pb.buffer(sizes[i], sizes[i], dec_c[6 - i] + enc_c[i]) for i in range(7)]
+    cat_off = [dec_c[6 - i] for i in range(7)]
+
+    in_face = pb.buffer(S, S, 8)
+    in_mel = pb.buffer(80, 16, 8)
+    pb.hdr.update(in_face_buf=in_face, in_mel_buf=in_mel, face_hw=S, mel_h=80, mel_w=16, out_hw=S)
+
+    # ---- audio encoder (wav2lip.py:38-55)
+    cur, coff, H, W = in_mel, 0, 80, 16
+    for j, (cout, k, st, p, resid) in enumerate(AUDIO_ENC):
+        w, b, bn = block(f"audio_encoder.{j}")
+        Ho, Wo = (H + 2 * p - k) // st[0] + 1, (W + 2 * p - k) // st[1] + 1
+        out = pb.buffer(Ho, Wo, cout)
+        pb.conv(cur, coff, out, 0, w, b, bn, stride=st, padding=p, res=(cur, coff) if resid else None)
+        cur, coff, H, W = out, 0, Ho, Wo
+    audio_emb = cur                                               # [B, 1, 1, 512]
+
+    # ---- face encoder (wav2lip.py:13-36); the last conv of block i lands in cat[i][..., cat_off[i]:]
+    cur, coff = in_face, 0
+    for i, blk in enumerate(FACE_ENC):
+        for j, (cout, k, s, p, resid) in enumerate(blk):
+            w, b, bn = block(f"face_encoder_blocks.{i}.{j}")
+            last = j == len(blk) - 1
+            if last:
+                out, ooff = cat[i], cat_off[i]
+            else:
+                Hi = pb.buffers[cur][0]
+                Ho = (Hi + 2 * p - k) // s + 1
+                out, ooff = pb.buffer(Ho, Ho, cout), 0
+            pb.conv(cur, coff, out, ooff, w, b, bn, stride=s, padding=p, res=(cur, coff) if resid else None)
+            cur, coff = out, ooff
+
+    # ---- face decoder (wav2lip.py:57-81,102-112)
+    cur, coff = audio_emb, 0
+    for i, blk in enumerate(FACE_DEC):
+        tgt = cat[6 - i]
+        for j, spec in enumerate(blk):
+            last = j == len(blk) - 1
+            res_t = tgt[0] if False else None
+            Ht = pb.buffers[tgt][0]
+            if last:
+                out, ooff = tgt, 0
+            else:
+                out, ooff = pb.buffer(Ht, Ht, spec[1]), 0
+            w, b, bn = block(f"face_decoder_blocks.{i}.{j}")
+            if spec[0] == "c":
+                pb.conv(cur, coff, out, ooff, w, b, bn, stride=spec[3], padding=spec[4])
+            elif spec[0] == "t":
+                pb.conv_transpose(cur, coff, out, ooff, w, b, bn, stride=spec[3], padding=spec[4], output_padding=spec[5])
+            else:
+                pb.conv(cur, coff, out, ooff, w, b, bn, stride=1, padding=1, res=(cur, coff))
+            cur, coff = out, ooff
+        cur, coff = tgt, 0                                        # x = cat(x, feats[-1]): the whole cat buffer
+
+    # ---- output block (wav2lip.py:83-85)
+    w, b, bn = block("output_block.0")
+    o1 = pb.buffer(S, S, 32)
+    pb.conv(cat[0], 0, o1, 0, w, b, bn, stride=1, padding=1)
+    pb.conv(o1, 0, -1, 0, sd["output_block.1.weight"], sd["output_block.1.bias"], None, stride=1, padding=0,
+            relu=False, mode=1)
+    return pb.finish(), pb

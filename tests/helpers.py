@@ -32,3 +32,80 @@ def psnr(a, b, peak=1.0):
     b = np.asarray(b, np.float64)
     mse = np.mean((a - b) ** 2)
     return 99.0 if mse == 0 else 10 * np.log10(peak * peak / mse)
+
+
+# ------------------------------------------------------------------------------------------------
+# Wav2Lip: seeded weights (the reference ships no checkpoint: ./models/wav2lip.pth is external)
+# ------------------------------------------------------------------------------------------------
+def wav2lip_param_shapes():
+    """name -> shape for every tensor of the reference Wav2Lip generator state_dict
+    (wav2lip/models/wav2lip.py:12-85); verified against the reference module by
+    tests/golden/make_wav2lip_golden.py (strict load)."""
+    shapes = {}
+
+    def block(prefix, cin, cout, k, transpose=False):
+        kh, kw = (k, k) if isinstance(k, int) else k
+        shapes[prefix + ".conv_block.0.weight"] = (cin, cout, kh, kw) if transpose else (cout, cin, kh, kw)
+        shapes[prefix + ".conv_block.0.bias"] = (cout,)
+        for n in ("weight", "bias", "running_mean", "running_var"):
+            shapes[prefix + ".conv_block.1." + n] = (cout,)
+        shapes[prefix + ".conv_block.1.num_batches_tracked"] = ()
+
+    enc = [[(6, 16, 7)], [(16, 32, 3), (32, 32, 3), (32, 32, 3)], [(32, 64, 3)] + [(64, 64, 3)] * 3,
+           [(64, 128, 3)] + [(128, 128, 3)] * 2, [(128, 256, 3)] + [(256, 256, 3)] * 2, [(256, 512, 3), (512, 512, 3)],
+           [(512, 512, 3), (512, 512, 1)]]
+    for i, blk in enumerate(enc):
+        for j, (ci, co, k) in enumerate(blk):
+            block(f"face_encoder_blocks.{i}.{j}", ci, co, k)
+    aud = [(1, 32, 3), (32, 32, 3), (32, 32, 3), (32, 64, 3), (64, 64, 3), (64, 64, 3), (64, 128, 3), (128, 128, 3),
+           (128, 128, 3), (128, 256, 3), (256, 256, 3), (256, 512, 3), (512, 512, 1)]
+    for j, (ci, co, k) in enumerate(aud):
+        block(f"audio_encoder.{j}", ci, co, k)
+    dec = [[(512, 512, 1, False)], [(1024, 512, 3, True), (512, 512, 3, False)],
+           [(1024, 512, 3, True)] + [(512, 512, 3, False)] * 2, [(768, 384, 3, True)] + [(384, 384, 3, False)] * 2,
+           [(512, 256, 3, True)] + [(256, 256, 3, False)] * 2, [(320, 128, 3, True)] + [(128, 128, 3, False)] * 2,
+           [(160, 64, 3, True)] + [(64, 64, 3, False)] * 2]
+    for i, blk in enumerate(dec):
+        for j, (ci, co, k, t) in enumerate(blk):
+            block(f"face_decoder_blocks.{i}.{j}", ci, co, k, transpose=t)
+    block("output_block.0", 80, 32, 3)
+    shapes["output_block.1.weight"] = (3, 32, 1, 1)
+    shapes["output_block.1.bias"] = (3,)
+    return shapes
+
+
+def seeded_wav2lip_state(seed=2):
+    """deterministic (numpy RNG, key order) weights with NON-trivial BatchNorm running statistics --
+    eval-mode BN is part of the arithmetic."""
+    import torch
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for name, shp in wav2lip_param_shapes().items():
+        if name.endswith("num_batches_tracked"):
+            sd[name] = torch.tensor(100, dtype=torch.long)
+        elif name.endswith("conv_block.0.weight") or name == "output_block.1.weight":
+            if "face_decoder" in name and len(shp) == 4 and ".0.conv_block" in name and shp[0] > shp[1] and shp[2] == 3 \
+                    and not name.startswith("face_decoder_blocks.0"):
+                fan_in = shp[0] * shp[2] * shp[3] / 4.0          # ConvTranspose2d: ~1/4 of the taps hit a pixel
+            else:
+                fan_in = shp[1] * shp[2] * shp[3]
+            if "face_decoder_blocks.1.0" in name:
+                fan_in = shp[0]
+            v = rng.standard_normal(shp) * np.sqrt(1.0 / fan_in)
+            sd[name] = torch.from_numpy(v.astype(np.float32))
+        elif name.endswith("running_var"):
+            sd[name] = torch.from_numpy(rng.uniform(0.6, 1.6, shp).astype(np.float32))
+        elif name.endswith("running_mean"):
+            sd[name] = torch.from_numpy((rng.standard_normal(shp) * 0.2).astype(np.float32))
+        elif name.endswith("conv_block.1.weight"):
+            sd[name] = torch.from_numpy(rng.uniform(0.7, 1.3, shp).astype(np.float32))
+        else:   # conv biases, BN beta
+            sd[name] = torch.from_numpy((rng.standard_normal(shp) * 0.1).astype(np.float32))
+    return sd
+
+
+def wav2lip_inputs(B, mel_seed=3, face_seed=4, S=96):
+    """config 2 of SURVEY.md 8(d): mel ~ N(0,1) clipped to +-4 [B,1,80,16]; faces u8 uniform [B,S,S,3]"""
+    mel = np.clip(np.random.default_rng(mel_seed).standard_normal((B, 1, 80, 16)), -4, 4).astype(np.float32)
+    faces = np.random.default_rng(face_seed).integers(0, 256, (B, S, S, 3), dtype=np.uint8)
+    return mel, faces

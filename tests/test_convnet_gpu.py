@@ -1,0 +1,119 @@
+"""GPU unit tests of the tcgen05 implicit-GEMM conv executor (csrc/wav2lip.cu) through the C ABI,
+one op at a time, against torch.nn.functional on the bf16-rounded operands (fp32 math).
+Tolerance: bf16 output rounding (2^-8 relative) plus fp32 accumulation-order noise."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+F = torch.nn.functional
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def run_case(B, Hin, Win, cin, cout, k, stride, pad, transpose=False, out_pad=0, residual=False, in_coff=0, in_C=None,
+             out_coff=0, out_C=None, bn=True, relu=True, seed=0):
+    from mere_fusion_b200.convnet_pack import ProgramBuilder
+    from mere_fusion_b200.wav2lip import ConvNet
+    g = torch.Generator().manual_seed(seed)
+    in_C = in_C or (cin + 7) // 8 * 8
+    x = torch.randn(B, Hin, Win, in_C, generator=g)
+    if transpose:
+        w = torch.randn(cin, cout, k, k, generator=g) / np.sqrt(cin * k * k / 4)
+    else:
+        w = torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)
+    bias = torch.randn(cout, generator=g) * 0.1
+    bnp = None
+    if bn:
+        bnp = (torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1,
+               torch.randn(cout, generator=g) * 0.2, torch.rand(cout, generator=g) + 0.5)
+    xin = bf(x)[..., in_coff:in_coff + cin].permute(0, 3, 1, 2)
+    if transpose:
+        y = F.conv_transpose2d(xin, bf(w), None, stride, pad, out_pad)
+    else:
+        y = F.conv2d(xin, bf(w), None, stride, pad)
+    Hout, Wout = y.shape[2:]
+    pb = ProgramBuilder(nominal_batch=B)
+    ib = pb.buffer(Hin, Win, in_C)
+    out_C = out_C or cout
+    ob = pb.buffer(Hout, Wout, out_C)
+    npw = w.numpy()
+    nbn = None if bnp is None else tuple(t.numpy() for t in bnp)
+    if transpose:
+        pb.conv_transpose(ib, in_coff, ob, out_coff, npw, bias.numpy(), nbn, stride=stride, padding=pad,
+                          output_padding=out_pad, relu=relu)
+    else:
+        pb.conv(ib, in_coff, ob, out_coff, npw, bias.numpy(), nbn, stride=stride, padding=pad,
+                res=(ib, in_coff) if residual else None, relu=relu)
+    # reference epilogue in fp32: BatchNorm(eval) folded exactly like the packer does
+    from mere_fusion_b200.convnet_pack import bn_fold
+    sc, sh = bn_fold(bias.numpy(), nbn, cout)
+    y = y * torch.from_numpy(sc).view(1, -1, 1, 1) + torch.from_numpy(sh).view(1, -1, 1, 1)
+    if residual:
+        y = y + xin
+    if relu:
+        y = F.relu(y)
+    net = ConvNet(pb.finish(), max_batch=B)
+    got = net.debug_run(ib, x, ob, (B, Hout, Wout, out_C)).cpu()
+    torch.cuda.synchronize()
+    got_c = got[..., out_coff:out_coff + cout].permute(0, 3, 1, 2)
+    err = (got_c - y).abs()
+    tol = 1e-2 + 1e-2 * y.abs()
+    assert bool((err <= tol).all()), f"max err {err.max().item():.4f} at |y| max {y.abs().max().item():.3f}"
+    # untouched channels of a wider (concat) buffer stay zero
+    if out_C != cout:
+        mask = torch.ones(out_C, dtype=torch.bool)
+        mask[out_coff:out_coff + cout] = False
+        assert float(got[..., mask].abs().max()) == 0.0
+    return float(err.max())
+
+
+def test_gemm_1x1():
+    run_case(2, 16, 16, 64, 64, 1, 1, 0)             # plain GEMM: M=512, K=64, N=64
+
+
+def test_gemm_1x1_bn_variants():
+    for cout in (16, 32, 128, 256):
+        run_case(3, 10, 10, 128, cout, 1, 1, 0, seed=cout)   # ragged M = 300
+
+
+def test_conv3x3_pad_residual():
+    run_case(2, 24, 24, 64, 64, 3, 1, 1, residual=True)
+
+
+def test_conv3x3_stride2_and_rect_stride():
+    run_case(2, 48, 48, 32, 64, 3, 2, 1)
+    run_case(2, 80, 16, 32, 64, 3, (3, 1), 1)
+    run_case(2, 9, 6, 128, 256, 3, (3, 2), 1)
+
+
+def test_conv7x7_padded_input_channels():
+    run_case(1, 96, 96, 6, 16, 7, 1, 3)              # Cin 6 -> 8, 49 taps, K = 392 -> 448
+
+
+def test_conv_single_channel_audio_first_layer():
+    run_case(2, 80, 16, 1, 32, 3, 1, 1)              # Cin 1 -> 8
+
+
+def test_conv3x3_valid_to_1x1_and_big_k():
+    run_case(4, 3, 3, 512, 512, 3, 1, 0)             # K = 4608, M = 4
+
+
+def test_conv_transpose_stride2():
+    run_case(2, 6, 6, 768, 384, 3, 2, 1, transpose=True, out_pad=1)
+    run_case(1, 48, 48, 160, 64, 3, 2, 1, transpose=True, out_pad=1)
+
+
+def test_conv_transpose_stride1_nopad():
+    run_case(3, 1, 1, 1024, 512, 3, 1, 0, transpose=True)
+
+
+def test_concat_channel_offsets():
+    # read channels [64:80) of an 80-wide buffer, write channels [128:160) of a 160-wide one
+    run_case(2, 96, 96, 16, 32, 3, 2, 1, in_coff=64, in_C=80, out_coff=128, out_C=160)
+
+
+def test_no_bn_no_relu():
+    run_case(2, 12, 12, 80, 32, 3, 1, 1, bn=False, relu=False)
