@@ -198,6 +198,17 @@ int mf_wav2lip_last_op_ms(mf_ctx *ctx, float *ms /*host*/);
 int mf_convnet_debug_run(mf_ctx *ctx, int in_buf, const float *in_f32, int out_buf, float *out_f32, int B,
                          void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Paste-back (lipreal.py:207-214): out[i] = frames[idx_i] with faces[i] resized (cv2.resize, u8,
+ * INTER_LINEAR, bit-exact) into the box (y1:y2, x1:x2).  coords order as wav2lip/genavatar.py:96.
+ *   frames : device u8 [n_frames,H,W,3] the avatar's full frames, resident
+ *   faces  : device u8 [B,S,S,3]        the generated crops (mf_wav2lip_forward out_u8)
+ *   idx_bbox_host : HOST int32 [B,5] = (frame index, y1, y2, x1, x2) per item, B <= 64
+ *   out    : device u8 [B,H,W,3]
+ * ------------------------------------------------------------------------------------------ */
+int mf_paste_resize_u8(mf_ctx *ctx, const uint8_t *frames, int n_frames, int H, int W, const uint8_t *faces,
+                       int S, int B, const int32_t *idx_bbox_host, uint8_t *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,1 +1,99 @@
+// paste.cu -- paste-back of the generated face crop into the avatar's full frame, on the GPU.
+//
+// Replaces, per output frame (lipreal.py:207-214):
+//     combine_frame = copy.deepcopy(frame_list_cycle[idx])
+//     res_frame = cv2.resize(res_frame.astype(np.uint8), (x2 - x1, y2 - y1))
+//     combine_frame[y1:y2, x1:x2] = res_frame
+// cv2.resize(u8, INTER_LINEAR) is restated bit-exactly: OpenCV's fixed-point bilinear
+// (imgproc/src/resize.cpp: coordinates (dx + 0.5) * scale - 0.5 evaluated in double and narrowed to
+// float, 11-bit coefficients saturate_cast<short>(c * 2048), horizontal pass in int, vertical pass
+// ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2), including its switch to the 2x2
+// area average when both scale factors are exactly 2 (INTER_LINEAR -> INTER_AREA fast path).
+// HBM-bound byte work: one thread per output pixel, coalesced 3-byte pixels, no staging needed
+// (every source byte is read at most ~4 times and stays in L1/L2).
 #include "mf_common.cuh"
+
+#define PASTE_MAX_BATCH 64
+
+struct PasteParams {
+    const uint8_t *frames;   // [n_frames, H, W, 3]
+    const uint8_t *faces;    // [B, S, S, 3]
+    uint8_t *out;            // [B, H, W, 3]
+    int H, W, S, B;
+    int idx[PASTE_MAX_BATCH];
+    int y1[PASTE_MAX_BATCH], y2[PASTE_MAX_BATCH], x1[PASTE_MAX_BATCH], x2[PASTE_MAX_BATCH];
+};
+
+// OpenCV resize.cpp, INTER_LINEAR coefficient set-up for one axis
+// x axis: the fraction is zeroed when a tap falls off either end; y axis (VERTICAL): OpenCV keeps the
+// fraction and clamps the two row indices instead, which rounds differently on the border rows.
+template <bool VERTICAL>
+__device__ __forceinline__ void cv_linear_coef(int d, int ssize, double scale, int &s0, int &s1, int &a0, int &a1) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= s;
+    if (!VERTICAL) {
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+    }
+    s0 = max(0, min(s, ssize - 1));
+    s1 = max(0, min(s + 1, ssize - 1));
+    a0 = max(-32768, min(32767, __float2int_rn((1.f - f) * 2048.f)));
+    a1 = max(-32768, min(32767, __float2int_rn(f * 2048.f)));
+}
+
+__global__ void __launch_bounds__(256) k_paste_resize(const __grid_constant__ PasteParams p) {
+    const int b = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.H * p.W) return;
+    const int y = pix / p.W, x = pix - y * p.W;
+    const uint8_t *src = p.frames + ((size_t)p.idx[b] * p.H * p.W + pix) * 3;
+    uint8_t *dst = p.out + ((size_t)b * p.H * p.W + pix) * 3;
+    const int y1 = p.y1[b], y2 = p.y2[b], x1 = p.x1[b], x2 = p.x2[b];
+    if (y < y1 || y >= y2 || x < x1 || x >= x2) {
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        return;
+    }
+    const int dw = x2 - x1, dh = y2 - y1, S = p.S;
+    const uint8_t *face = p.faces + (size_t)b * S * S * 3;
+    const int dx = x - x1, dy = y - y1;
+    if (S == 2 * dw && S == 2 * dh) {  // INTER_AREA fast path (exact 2x decimation)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int s = face[((2 * dy) * S + 2 * dx) * 3 + c] + face[((2 * dy) * S + 2 * dx + 1) * 3 + c] +
+                          face[((2 * dy + 1) * S + 2 * dx) * 3 + c] + face[((2 * dy + 1) * S + 2 * dx + 1) * 3 + c];
+            dst[c] = (uint8_t)((s + 2) >> 2);
+        }
+        return;
+    }
+    int sx0, sx1, ax0, ax1, sy0, sy1, by0, by1;
+    cv_linear_coef<false>(dx, S, (double)S / dw, sx0, sx1, ax0, ax1);
+    cv_linear_coef<true>(dy, S, (double)S / dh, sy0, sy1, by0, by1);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int r0 = face[(sy0 * S + sx0) * 3 + c] * ax0 + face[(sy0 * S + sx1) * 3 + c] * ax1;
+        const int r1 = face[(sy1 * S + sx0) * 3 + c] * ax0 + face[(sy1 * S + sx1) * 3 + c] * ax1;
+        const int v = (((by0 * (r0 >> 4)) >> 16) + ((by1 * (r1 >> 4)) >> 16) + 2) >> 2;
+        dst[c] = (uint8_t)max(0, min(255, v));
+    }
+}
+
+extern "C" int mf_paste_resize_u8(mf_ctx *ctx, const uint8_t *frames, int n_frames, int H, int W, const uint8_t *faces,
+                                  int S, int B, const int32_t *idx_bbox_host, uint8_t *out, void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    MF_REQUIRE(ctx, frames && faces && out && idx_bbox_host, "mf_paste_resize_u8: null pointer");
+    MF_REQUIRE(ctx, B >= 1 && B <= PASTE_MAX_BATCH && H > 0 && W > 0 && S > 1 && n_frames > 0, "mf_paste_resize_u8: bad sizes");
+    PasteParams p;
+    p.frames = frames; p.faces = faces; p.out = out; p.H = H; p.W = W; p.S = S; p.B = B;
+    for (int i = 0; i < B; i++) {
+        const int32_t *r = idx_bbox_host + i * 5;
+        MF_REQUIRE(ctx, r[0] >= 0 && r[0] < n_frames, "mf_paste_resize_u8: frame index %d out of range", r[0]);
+        MF_REQUIRE(ctx, 0 <= r[1] && r[1] < r[2] && r[2] <= H && 0 <= r[3] && r[3] < r[4] && r[4] <= W,
+                   "mf_paste_resize_u8: bbox (y1,y2,x1,x2)=(%d,%d,%d,%d) outside the %dx%d frame", r[1], r[2], r[3], r[4], H, W);
+        p.idx[i] = r[0]; p.y1[i] = r[1]; p.y2[i] = r[2]; p.x1[i] = r[3]; p.x2[i] = r[4];
+    }
+    dim3 grid((H * W + 255) / 256, B);
+    k_paste_resize<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    MF_CUDA(ctx, cudaGetLastError());
+    return MF_OK;
+}

@@ -31,8 +31,6 @@
 
 #define CONV_BM 128
 #define CONV_BK 64
-#define CONV_STAGES 4
-#define CONV_LAG 2
 #define CONV_THREADS 160
 #define CONV_MAX_TAPS 52
 #define A_STAGE_BYTES (CONV_BM * CONV_BK * 2)
@@ -132,20 +130,24 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN>
+// CONV_STAGES smem stages; the producers keep CONV_LAG + 1 k-blocks of loads in flight.  Two depths per
+// tile width: 4 stages (2 CTAs / SM: one CTA's epilogue overlaps the other's main loop) for layers with
+// many tiles, and a deep ring (1 CTA / SM) for the few-tile, long-K, load-latency-bound layers.
+template <int BN, int CONV_STAGES>
 struct ConvSmem {
     static constexpr int B_STAGE = BN * CONV_BK * 2;
     static constexpr int BAR_OFF = CONV_STAGES * (A_STAGE_BYTES + B_STAGE);
-    static constexpr int TOTAL = BAR_OFF + 128 + 1024;  // + barriers/slot + alignment slack
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + barriers/slot + alignment slack
 };
 
-template <int BN>
+template <int BN, int CONV_STAGES>
 __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ ConvParams p) {
+    constexpr int CONV_LAG = CONV_STAGES - 2;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char *sA = smem;
     unsigned char *sB = smem + CONV_STAGES * A_STAGE_BYTES;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + ConvSmem<BN>::BAR_OFF);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + ConvSmem<BN, CONV_STAGES>::BAR_OFF);
     uint64_t *empty = full + CONV_STAGES;
     uint64_t *accum = empty + CONV_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
@@ -182,8 +184,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
             const int s = kb % CONV_STAGES;
             if (kb >= CONV_STAGES) mbar_wait(&empty[s], ((kb / CONV_STAGES) - 1) & 1);
             if (threadIdx.x == 0) {
-                mbar_expect_tx(&full[s], ConvSmem<BN>::B_STAGE);
-                tma_load_2d(sB + s * ConvSmem<BN>::B_STAGE, &p.wmap, kb * CONV_BK, blockIdx.y * BN, &full[s]);
+                mbar_expect_tx(&full[s], ConvSmem<BN, CONV_STAGES>::B_STAGE);
+                tma_load_2d(sB + s * ConvSmem<BN, CONV_STAGES>::B_STAGE, &p.wmap, kb * CONV_BK, blockIdx.y * BN, &full[s]);
             }
 #pragma unroll
             for (int c = 0; c < 8; c++) {
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
         cp_async_wait<0>();
         fence_proxy_async();
         for (int kb = (nkb > CONV_LAG ? nkb - CONV_LAG : 0); kb < nkb; kb++) mbar_arrive(&full[kb % CONV_STAGES]);
+        static_assert(CONV_LAG >= 1 && CONV_LAG < CONV_STAGES, "pipeline lag");
 
         // =========================== epilogue: TMEM lane == output pixel =======================
         mbar_wait(accum, 0);
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
             mbar_wait(&full[s], (kb / CONV_STAGES) & 1);
             tc_fence_after();
             const uint64_t adesc = make_sdesc(smem_u32(sA + s * A_STAGE_BYTES));
-            const uint64_t bdesc = make_sdesc(smem_u32(sB + s * ConvSmem<BN>::B_STAGE));
+            const uint64_t bdesc = make_sdesc(smem_u32(sB + s * ConvSmem<BN, CONV_STAGES>::B_STAGE));
 #pragma unroll
             for (int k = 0; k < CONV_BK / 16; k++)  // +32 B per UMMA_K inside the 128B swizzle atom
                 umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
@@ -361,17 +364,25 @@ void wav2lip_destroy(mf_ctx *ctx) {
     ctx->wav2lip = nullptr;
 }
 
-template <int BN>
-static cudaError_t launch_conv(const ConvParams &p, cudaStream_t st) {
+template <int BN, int STAGES>
+static cudaError_t launch_conv_s(const ConvParams &p, dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_conv<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN>::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(k_conv<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             ConvSmem<BN, STAGES>::TOTAL);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid((p.M + CONV_BM - 1) / CONV_BM, (p.Cout + BN - 1) / BN);
-    k_conv<BN><<<grid, CONV_THREADS, ConvSmem<BN>::TOTAL, st>>>(p);
+    k_conv<BN, STAGES><<<grid, CONV_THREADS, ConvSmem<BN, STAGES>::TOTAL, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int BN>
+static cudaError_t launch_conv(const ConvParams &p, cudaStream_t st) {
+    dim3 grid((p.M + CONV_BM - 1) / CONV_BM, (p.Cout + BN - 1) / BN);
+    constexpr int DEEP = BN <= 32 ? 10 : (BN == 64 ? 8 : 6);  // 200 / 192 / 192 KB
+    const bool deep = grid.x * grid.y <= 2 * 148 && p.nkb > 4;
+    return deep ? launch_conv_s<BN, DEEP>(p, grid, st) : launch_conv_s<BN, 4>(p, grid, st);
 }
 
 extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int max_batch) {

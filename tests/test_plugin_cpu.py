@@ -1,0 +1,211 @@
+"""CPU tests of the host-side plugin mirror (BaseASR / LipASR / LipReal / NerfASR plumbing):
+BASELINE config 1 -- Wav2Lip 96x96, 25 fps, mel feats, a 10 s clip, no GPU."""
+import os
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+import pytest
+
+from helpers import load_pose_fixture
+
+REF = "/root/reference"
+
+
+def make_opt(**kw):
+    o = types.SimpleNamespace(fps=50, l=10, m=8, r=10, batch_size=16, W=450, H=450, avatar_id="test", tts="none",
+                              customopt=[], att=2, asr_model="cpierse/wav2vec2-large-xlsr-53-esperanto", exp_eye=True,
+                              fix_eye=-1, fullbody=False, transport="rtc")
+    o.__dict__.update(kw)
+    return o
+
+
+def clip_10s():
+    """SURVEY.md 8(d) config 1 audio: 0.3 sin(2pi 220 t)(0.5 + 0.5 sin(2pi 3 t)) + 0.01 N(0,1), seed 0"""
+    t = np.arange(160000) / 16000.0
+    rng = np.random.default_rng(0)
+    return (0.3 * np.sin(2 * np.pi * 220 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 3 * t)) + 0.01 * rng.standard_normal(160000)).astype(np.float32)
+
+
+class FakeQueue:
+    def __init__(self):
+        self.items = []
+
+    async def put(self, x):
+        self.items.append(x)
+
+    def qsize(self):
+        return 0
+
+
+class FakeTrack:
+    def __init__(self):
+        self._queue = FakeQueue()
+
+
+def test_mel_shape_range_and_filterbank():
+    from mere_fusion_b200 import audio_mel
+    mel = audio_mel.melspectrogram(clip_10s()[:16640])
+    assert mel.shape == (80, 16640 // 200 + 1)                 # [80, 84] for the 52-chunk window
+    assert mel.min() >= -4.0 and mel.max() <= 4.0 and mel.std() > 0.5
+    fb = audio_mel.mel_filterbank()
+    assert fb.shape == (80, 401) and fb.dtype == np.float32 and (fb >= 0).all()
+    peaks = fb.argmax(1)
+    assert (np.diff(peaks) >= 0).all() and peaks[0] >= 2 and peaks[-1] <= 380     # 55 Hz .. 7600 Hz on a 20 Hz grid
+    # silence maps to the floor: 20 log10(1e-5) - 20 = -120 dB -> clipped to -4
+    assert np.allclose(audio_mel.melspectrogram(np.zeros(3200, np.float32)), -4.0)
+    # a pure tone lights up the band that contains it
+    tone = np.sin(2 * np.pi * 1000 * np.arange(16000) / 16000).astype(np.float32)
+    band = audio_mel.melspectrogram(tone)[:, 20:60].mean(1).argmax()
+    assert abs(int(fb[band].argmax()) * 20 - 1000) <= 60
+
+
+def test_mel_chunk_slicing_matches_reference_lipasr():
+    """the queue / window / slicing logic against the reference LipASR itself (librosa stubbed, the mel
+    function injected), when the reference tree is present"""
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present")
+    from mere_fusion_b200 import audio_mel
+    from mere_fusion_b200.plugin.lipasr import LipASR
+    for name in ("librosa", "librosa.filters"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.path.insert(0, REF)
+    try:
+        import lipasr as ref_lipasr
+        from wav2lip import audio as ref_audio
+    finally:
+        sys.path.remove(REF)
+    ref_audio.melspectrogram = audio_mel.melspectrogram
+    opt = make_opt()
+    wav = clip_10s()
+    outs = []
+    for cls in (ref_lipasr.LipASR, LipASR):
+        asr = cls(opt, None)
+        for i in range(100):                                    # 2 s of audio, then silence fill
+            asr.put_audio_frame(wav[i * 320:(i + 1) * 320])
+        asr.warm_up()
+        chunks = []
+        for _ in range(4):
+            asr.run_step()
+            chunks.append(asr.feat_queue.get())
+        types_ = []
+        while True:
+            try:
+                types_.append(asr.output_queue.get(timeout=0.05)[1])
+            except Exception:
+                break
+        outs.append((chunks, types_, len(asr.frames)))
+    (c0, t0, n0), (c1, t1, n1) = outs
+    assert n0 == n1 == 20 and t0 == t1
+    assert len(c0) == len(c1) == 4
+    for a, b in zip(c0, c1):
+        assert len(a) == len(b) == 16
+        for x, y in zip(a, b):
+            assert x.shape == (80, 16) and np.array_equal(x, y)
+
+
+def _fake_avatar(n=25, H=512, W=512):
+    from mere_fusion_b200.plugin.lipreal import Avatar
+    rng = np.random.default_rng(1)
+    frames, faces, coords = [], [], []
+    for i in range(n):
+        f = rng.integers(0, 200, (H, W, 3), dtype=np.uint8)
+        f[0, 0] = i                                             # index marker
+        frames.append(f)
+        faces.append(rng.integers(0, 256, (96, 96, 3), dtype=np.uint8))
+        coords.append((176, 368, 160, 352))                     # (y1, y2, x1, x2), SURVEY 8(d) config 1
+    return Avatar(frames, faces, coords)
+
+
+def test_config1_lipreal_plumbing_10s_clip():
+    from mere_fusion_b200.plugin.lipreal import LipReal, mirror_index
+
+    class HostLipReal(LipReal):
+        """the plumbing with a host stand-in for the engine: crop := 255 - face"""
+
+        def infer_batch(self, mel_batch, index):
+            assert len(mel_batch) == self.batch_size and mel_batch[0].shape == (80, 16)
+            n = len(self.face_list_cycle)
+            return [(255 - self.face_list_cycle[mirror_index(n, index + i)]).astype(np.float32) for i in range(self.batch_size)]
+
+    opt = make_opt()
+    real = HostLipReal(opt, engine=object(), avatar=_fake_avatar(), paste="cpu")
+    wav = clip_10s()
+    for i in range(500):
+        real.put_audio_frame(wav[i * 320:(i + 1) * 320])
+    quit_event = threading.Event()
+    vt, at = FakeTrack(), FakeTrack()
+    th = threading.Thread(target=real.render, args=(quit_event, None, at, vt))
+    th.start()
+    t0 = time.time()
+    while len(vt._queue.items) < 272 and time.time() - t0 < 120:
+        time.sleep(0.05)
+    quit_event.set()
+    th.join(timeout=30)
+    nv, na = len(vt._queue.items), len(at._queue.items)
+    assert nv >= 272
+    assert abs(na - 2 * nv) <= 2                                # exactly two audio frames per video frame
+    import cv2
+    speech_frames = 0
+    for k in range(250):
+        fr = vt._queue.items[k].to_ndarray()
+        assert fr.shape == (512, 512, 3) and fr.dtype == np.uint8
+        idx = mirror_index(25, k)
+        assert fr[0, 0, 0] == idx                               # ping-pong replay 0..24,24..0
+        a0, a1 = at._queue.items[2 * k], at._queue.items[2 * k + 1]
+        assert a0.samples == 320 and a0.sample_rate == 16000
+        face = real.face_list_cycle[idx]
+        expect = cv2.resize((255 - face), (192, 192))
+        if np.array_equal(fr[176:368, 160:352], expect):
+            speech_frames += 1
+        else:
+            assert np.array_equal(fr, real.frame_list_cycle[idx])   # idle frame: the untouched full frame
+    # warm_up() ran on an empty queue (20 silent chunks, the first 10 dropped from the output side,
+    # baseasr.py:53-59): output = 10 silent chunks (5 idle frames), then the 500 speech chunks
+    assert speech_frames == 245
+    pcm = np.concatenate([a.to_ndarray() for a in at._queue.items[:480]])
+    ref = (wav * 32767).astype(np.int16)
+    assert not pcm[:3200].any()
+    assert np.array_equal(pcm[3200:3200 + 320 * 400], ref[:320 * 400])
+
+
+def test_nerfasr_ring_and_window():
+    import torch
+    from mere_fusion_b200.plugin.nerfasr import NerfASR
+    opt = make_opt()
+    calls = []
+
+    def feature_fn(frame):      # wav2vec2 geometry: 25 ms receptive field, 20 ms hop -> 27 rows for 28 chunks
+        calls.append(len(frame))
+        n = (len(frame) - 400) // 320 + 1
+        base = float(len(calls))
+        return torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 44) + 100 * base
+
+    asr = NerfASR(opt, None, feature_fn=feature_fn, device="cpu")
+    asr.warm_up()                                               # 28 steps
+    assert calls == [] or all(c == 28 * 320 for c in calls)
+    for _ in range(16):
+        asr.run_step()
+    assert all(c == 28 * 320 for c in calls) and len(calls) >= 2
+    # rows written per call: logits[l : T - r + 1] = rows 10..17 (nerfasr.py:139-141), at ring offset idx * m
+    f = asr.get_next_feat()
+    assert f.shape == (8, 44, 16)
+    f2 = asr.get_next_feat()
+    assert torch.equal(f2[:-1], f[1:])                           # the attention window slides by one
+    assert asr.front == (32 - 8 + 2 * 5) % 32 and asr.tail == (8 + 2 * 5) % 32   # 4 + 1 windows consumed, 2 rows each
+
+
+def test_pose_provider_matches_reference_golden():
+    from mere_fusion_b200.ernerf_data import ErnerfPoseProvider, mirror_index
+    pf = load_pose_fixture()
+    tr = dict(cx=float(pf["cx"]), cy=float(pf["cy"]), focal_len=float(pf["focal_len"]),
+              frames=[dict(transform_matrix=pf["raw"][i].tolist(), img_id=int(pf["img_id"][i])) for i in range(304)])
+    au = np.zeros(int(pf["img_id"][:304].max()) + 1)
+    au[:len(pf["au"])] = pf["au"][:len(au)]
+    prov = ErnerfPoseProvider(tr, au)
+    assert prov.H == 450 and prov.W == 450
+    np.testing.assert_allclose(prov.poses[:296], pf["poses"][:296], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(prov.eye_area[:296], pf["eye"][:296], rtol=0, atol=1e-7)
+    assert [mirror_index(3, i) for i in range(8)] == [0, 1, 2, 2, 1, 0, 0, 1]
