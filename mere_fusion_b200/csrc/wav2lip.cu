@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "mf_common.cuh"
@@ -65,6 +66,7 @@ struct ConvParams {
     int res_stride, res_coff;
     int Mh, Mw, oy0, ox0, osy, osx, isy, isx;
     int ntaps, Cin, nkb, Cout, M, relu, mode;
+    int dbg;  // timing experiments only (MF_CONV_DBG): 1 skip A loads, 2 skip B TMA, 4 skip MMA
     int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];
 };
 
@@ -74,6 +76,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -130,7 +135,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// CONV_STAGES smem stages; the producers keep CONV_LAG + 1 k-blocks of loads in flight.  Two depths per
+// CONV_STAGES smem stages = k-blocks of loads in flight per CTA.  Two depths per
 // tile width: 4 stages (2 CTAs / SM: one CTA's epilogue overlaps the other's main loop) for layers with
 // many tiles, and a deep ring (1 CTA / SM) for the few-tile, long-K, load-latency-bound layers.
 template <int BN, int CONV_STAGES>
@@ -142,7 +147,6 @@ struct ConvSmem {
 
 template <int BN, int CONV_STAGES>
 __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ ConvParams p) {
-    constexpr int CONV_LAG = CONV_STAGES - 2;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char *sA = smem;
@@ -184,33 +188,40 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
             const int s = kb % CONV_STAGES;
             if (kb >= CONV_STAGES) mbar_wait(&empty[s], ((kb / CONV_STAGES) - 1) & 1);
             if (threadIdx.x == 0) {
+                if (p.dbg & 2) mbar_arrive(&full[s]);
+                else {
                 mbar_expect_tx(&full[s], ConvSmem<BN, CONV_STAGES>::B_STAGE);
                 tma_load_2d(sB + s * ConvSmem<BN, CONV_STAGES>::B_STAGE, &p.wmap, kb * CONV_BK, blockIdx.y * BN, &full[s]);
-            }
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                bool ok = row_ok && tap < p.ntaps;
-                const __nv_bfloat16 *src = p.in;
-                if (ok) {
-                    const int iy = iy0 + p.tap_dy[tap], ix = ix0 + p.tap_dx[tap];
-                    ok = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-                    if (ok) src = in_b + ((size_t)iy * p.Win + ix) * p.in_stride + ch;
                 }
-                cp_async16(a_row + s * A_STAGE_BYTES + ((c ^ sw) << 4), src, ok ? 16u : 0u);
-                ch += 8;
-                if (ch >= p.Cin) { ch = 0; tap++; }
             }
-            cp_async_commit();
-            if (kb >= CONV_LAG) {
-                cp_async_wait<CONV_LAG>();
-                fence_proxy_async();
-                mbar_arrive(&full[(kb - CONV_LAG) % CONV_STAGES]);
+            if (p.dbg & 1) { mbar_arrive(&full[s]); continue; }
+            // the 8 16-byte chunks of this k-block, walked as runs that stay inside one filter tap: the
+            // bounds test and the source pointer are computed once per run, not once per chunk
+            {
+                const uint32_t dst0 = a_row + s * A_STAGE_BYTES;
+                int c = 0;
+                while (c < 8) {
+                    const int n = min(8 - c, (p.Cin - ch) >> 3);
+                    bool ok = row_ok && tap < p.ntaps;
+                    const __nv_bfloat16 *src = p.in;
+                    if (ok) {
+                        const int iy = iy0 + p.tap_dy[tap], ix = ix0 + p.tap_dx[tap];
+                        ok = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+                        if (ok) src = in_b + (iy * p.Win + ix) * p.in_stride + ch;
+                    }
+                    const uint32_t nbytes = ok ? 16u : 0u;
+                    const int step = ok ? 8 : 0;
+                    for (int j = 0; j < n; j++) cp_async16(dst0 + (((c + j) ^ sw) << 4), src + j * step, nbytes);
+                    c += n;
+                    ch += n << 3;
+                    if (ch >= p.Cin) { ch = 0; tap++; }
+                }
             }
+            // this thread's arrival on full[s] fires when its cp.asyncs above have landed: no wait_group,
+            // no per-k-block proxy fence (a fence.proxy.async here drains every copy in flight and
+            // serialises the ring: measured 1.25 us per k-block regardless of depth)
+            cp_async_mbar_arrive_noinc(&full[s]);
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (int kb = (nkb > CONV_LAG ? nkb - CONV_LAG : 0); kb < nkb; kb++) mbar_arrive(&full[kb % CONV_STAGES]);
-        static_assert(CONV_LAG >= 1 && CONV_LAG < CONV_STAGES, "pipeline lag");
 
         // =========================== epilogue: TMEM lane == output pixel =======================
         mbar_wait(accum, 0);
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
             const uint64_t bdesc = make_sdesc(smem_u32(sB + s * ConvSmem<BN, CONV_STAGES>::B_STAGE));
 #pragma unroll
             for (int k = 0; k < CONV_BK / 16; k++)  // +32 B per UMMA_K inside the 128B swizzle atom
-                umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                if (!(p.dbg & 4)) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
             umma_commit(&empty[s]);
         }
         umma_commit(accum);
@@ -326,6 +337,12 @@ __global__ void k_bf16_to_f32(const __nv_bfloat16 *__restrict__ in, float *__res
 }
 
 // ---- host --------------------------------------------------------------------------------------
+struct LaunchDesc {
+    void *func;
+    dim3 grid;
+    int smem;
+};
+
 struct Wav2LipState {
     W2LHeader hdr;
     std::vector<W2LBuffer> bufs;
@@ -337,6 +354,22 @@ struct Wav2LipState {
     bool profile = false;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int profile_op = -1;
+    // one instantiated CUDA graph per batch size: the ~70 launches of a forward are replayed with a single
+    // cudaGraphLaunch; only the three nodes that see caller pointers are re-parameterised per call
+    struct GraphEntry {
+        int B = 0;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t n_face = nullptr, n_mel = nullptr, n_out = nullptr;
+        const float *mel = nullptr;
+        const uint8_t *faces = nullptr;
+        uint8_t *out_u8 = nullptr;
+        float *out_f32 = nullptr;
+        ConvParams out_params;
+        LaunchDesc out_desc;
+    };
+    std::vector<GraphEntry> graphs;
+    bool use_graph = true;
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -359,13 +392,17 @@ void wav2lip_destroy(mf_ctx *ctx) {
     Wav2LipState *s = ctx->wav2lip;
     if (!s) return;
     for (auto p : s->dbuf) cudaFree(p);
+    for (auto &g : s->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
     if (s->ev[0]) { cudaEventDestroy(s->ev[0]); cudaEventDestroy(s->ev[1]); }
     delete s;
     ctx->wav2lip = nullptr;
 }
 
 template <int BN, int STAGES>
-static cudaError_t launch_conv_s(const ConvParams &p, dim3 grid, cudaStream_t st) {
+static cudaError_t conv_desc_s(dim3 grid, LaunchDesc *d) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_conv<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -373,16 +410,27 @@ static cudaError_t launch_conv_s(const ConvParams &p, dim3 grid, cudaStream_t st
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_conv<BN, STAGES><<<grid, CONV_THREADS, ConvSmem<BN, STAGES>::TOTAL, st>>>(p);
-    return cudaGetLastError();
+    d->func = (void *)k_conv<BN, STAGES>;
+    d->grid = grid;
+    d->smem = ConvSmem<BN, STAGES>::TOTAL;
+    return cudaSuccess;
 }
 
 template <int BN>
-static cudaError_t launch_conv(const ConvParams &p, cudaStream_t st) {
+static cudaError_t conv_desc(const ConvParams &p, LaunchDesc *d) {
     dim3 grid((p.M + CONV_BM - 1) / CONV_BM, (p.Cout + BN - 1) / BN);
     constexpr int DEEP = BN <= 32 ? 10 : (BN == 64 ? 8 : 6);  // 200 / 192 / 192 KB
-    const bool deep = grid.x * grid.y <= 2 * 148 && p.nkb > 4;
-    return deep ? launch_conv_s<BN, DEEP>(p, grid, st) : launch_conv_s<BN, 4>(p, grid, st);
+    const bool deep = grid.x * grid.y <= 148 && p.nkb > 4;
+    return deep ? conv_desc_s<BN, DEEP>(grid, d) : conv_desc_s<BN, 4>(grid, d);
+}
+
+static cudaError_t conv_desc_any(int BN, const ConvParams &p, LaunchDesc *d) {
+    switch (BN) {
+        case 16: return conv_desc<16>(p, d);
+        case 32: return conv_desc<32>(p, d);
+        case 64: return conv_desc<64>(p, d);
+        default: return conv_desc<128>(p, d);
+    }
 }
 
 extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int max_batch) {
@@ -421,6 +469,7 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
     s->bufs.assign(pb, pb + s->hdr.n_buffers);
     s->ops.assign(po, po + s->hdr.n_ops);
     s->max_batch = max_batch;
+    { const char *e = getenv("MF_NO_GRAPH"); s->use_graph = !(e && atoi(e)); }
     s->dbuf.assign(s->hdr.n_buffers, nullptr);
     for (int i = 0; i < s->hdr.n_buffers; i++) {
         const size_t bytes = (size_t)max_batch * s->bufs[i].H * s->bufs[i].W * s->bufs[i].C * 2;
@@ -489,22 +538,108 @@ static int run_ops(mf_ctx *ctx, Wav2LipState *s, int B, uint8_t *out_u8, float *
     for (int i = 0; i < s->hdr.n_ops; i++) {
         ConvParams p = s->params[i];
         p.M = B * p.Mh * p.Mw;
+        {
+            static int dbg = -1;
+            if (dbg < 0) { const char *e = getenv("MF_CONV_DBG"); dbg = e ? atoi(e) : 0; }
+            p.dbg = dbg;
+        }
         if (p.mode == 1) {
             p.out = out_u8;
             p.out_f32 = out_f32;
         }
         if (s->profile && i == s->profile_op) cudaEventRecord(s->ev[0], st);
-        cudaError_t e;
-        switch (s->ops[i].BN) {
-            case 16: e = launch_conv<16>(p, st); break;
-            case 32: e = launch_conv<32>(p, st); break;
-            case 64: e = launch_conv<64>(p, st); break;
-            default: e = launch_conv<128>(p, st); break;
+        LaunchDesc d;
+        cudaError_t e = conv_desc_any(s->ops[i].BN, p, &d);
+        if (e == cudaSuccess) {
+            void *args[] = {&p};
+            e = cudaLaunchKernel(d.func, d.grid, dim3(CONV_THREADS), args, d.smem, st);
         }
         if (s->profile && i == s->profile_op) cudaEventRecord(s->ev[1], st);
         if (e != cudaSuccess) return mf_fail(ctx, MF_E_CUDA, "conv op %d launch: %s", i, cudaGetErrorString(e));
         (*launches)++;
     }
+    return MF_OK;
+}
+
+static int add_kernel_node(mf_ctx *ctx, cudaGraph_t g, cudaGraphNode_t *prev, cudaGraphNode_t *out, void *func, dim3 grid,
+                           dim3 block, int smem, void **args) {
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = func; kp.gridDim = grid; kp.blockDim = block; kp.sharedMemBytes = (unsigned)smem; kp.kernelParams = args;
+    MF_CUDA(ctx, cudaGraphAddKernelNode(out, g, *prev ? prev : nullptr, *prev ? 1 : 0, &kp));
+    *prev = *out;
+    return MF_OK;
+}
+
+static int set_kernel_node(mf_ctx *ctx, cudaGraphExec_t ex, cudaGraphNode_t node, void *func, dim3 grid, dim3 block, int smem,
+                           void **args) {
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = func; kp.gridDim = grid; kp.blockDim = block; kp.sharedMemBytes = (unsigned)smem; kp.kernelParams = args;
+    MF_CUDA(ctx, cudaGraphExecKernelNodeSetParams(ex, node, &kp));
+    return MF_OK;
+}
+
+// the whole forward as one graph launch; returns MF_E_UNSUPPORTED when the graph path must be skipped
+static int forward_graph(mf_ctx *ctx, Wav2LipState *s, const float *mel, const uint8_t *faces, uint8_t *out_u8,
+                         float *out_f32, int B, cudaStream_t st) {
+    const int S = s->hdr.face_hw;
+    int nf = B * S * S, nm = B * s->hdr.mel_h * s->hdr.mel_w, Bv = B, Sv = S;
+    __nv_bfloat16 *fbuf = s->dbuf[s->hdr.in_face_buf], *mbuf = s->dbuf[s->hdr.in_mel_buf];
+    Wav2LipState::GraphEntry *ge = nullptr;
+    for (auto &g : s->graphs) if (g.B == B) ge = &g;
+    if (!ge) {
+        if (s->ops.empty() || s->ops.back().mode != 1) return MF_E_UNSUPPORTED;
+        s->graphs.emplace_back();
+        ge = &s->graphs.back();
+        ge->B = B;
+        MF_CUDA(ctx, cudaGraphCreate(&ge->graph, 0));
+        cudaGraphNode_t prev = nullptr, node = nullptr;
+        {
+            void *a0[] = {(void *)&faces, (void *)&fbuf, &Bv, &Sv};
+            int rc = add_kernel_node(ctx, ge->graph, &prev, &ge->n_face, (void *)k_w2l_prep_face, dim3((nf + 255) / 256), dim3(256), 0, a0);
+            if (rc) return rc;
+            void *a1[] = {(void *)&mel, (void *)&mbuf, &nm};
+            rc = add_kernel_node(ctx, ge->graph, &prev, &ge->n_mel, (void *)k_w2l_prep_mel, dim3((nm + 255) / 256), dim3(256), 0, a1);
+            if (rc) return rc;
+        }
+        for (int i = 0; i < s->hdr.n_ops; i++) {
+            ConvParams p = s->params[i];
+            p.M = B * p.Mh * p.Mw;
+            p.dbg = 0;
+            if (p.mode == 1) { p.out = out_u8; p.out_f32 = out_f32; }
+            LaunchDesc d;
+            MF_CUDA(ctx, conv_desc_any(s->ops[i].BN, p, &d));
+            void *a[] = {&p};
+            int rc = add_kernel_node(ctx, ge->graph, &prev, &node, d.func, d.grid, dim3(CONV_THREADS), d.smem, a);
+            if (rc) return rc;
+            if (p.mode == 1) { ge->n_out = node; ge->out_params = p; ge->out_desc = d; }
+        }
+        MF_CUDA(ctx, cudaGraphInstantiate(&ge->exec, ge->graph, 0));
+        ge->mel = mel; ge->faces = faces; ge->out_u8 = out_u8; ge->out_f32 = out_f32;
+    }
+    if (ge->faces != faces) {
+        void *a0[] = {(void *)&faces, (void *)&fbuf, &Bv, &Sv};
+        int rc = set_kernel_node(ctx, ge->exec, ge->n_face, (void *)k_w2l_prep_face, dim3((nf + 255) / 256), dim3(256), 0, a0);
+        if (rc) return rc;
+        ge->faces = faces;
+    }
+    if (ge->mel != mel) {
+        void *a1[] = {(void *)&mel, (void *)&mbuf, &nm};
+        int rc = set_kernel_node(ctx, ge->exec, ge->n_mel, (void *)k_w2l_prep_mel, dim3((nm + 255) / 256), dim3(256), 0, a1);
+        if (rc) return rc;
+        ge->mel = mel;
+    }
+    if (ge->out_u8 != out_u8 || ge->out_f32 != out_f32) {
+        ge->out_params.out = out_u8;
+        ge->out_params.out_f32 = out_f32;
+        void *a[] = {&ge->out_params};
+        int rc = set_kernel_node(ctx, ge->exec, ge->n_out, ge->out_desc.func, ge->out_desc.grid, dim3(CONV_THREADS), ge->out_desc.smem, a);
+        if (rc) return rc;
+        ge->out_u8 = out_u8; ge->out_f32 = out_f32;
+    }
+    MF_CUDA(ctx, cudaGraphLaunch(ge->exec, st));
+    s->last_launches = 2 + s->hdr.n_ops;
     return MF_OK;
 }
 
@@ -521,6 +656,10 @@ extern "C" int mf_wav2lip_forward(mf_ctx *ctx, const float *mel, const uint8_t *
     int launches = 0;
     const int S = s->hdr.face_hw;
     const int nf = B * S * S, nm = B * s->hdr.mel_h * s->hdr.mel_w;
+    if (s->use_graph && !s->profile) {
+        int rc = forward_graph(ctx, s, mel, faces, out_u8, out_f32, B, st);
+        if (rc != MF_E_UNSUPPORTED) return rc;
+    }
     k_w2l_prep_face<<<(nf + 255) / 256, 256, 0, st>>>(faces, s->dbuf[s->hdr.in_face_buf], B, S);
     k_w2l_prep_mel<<<(nm + 255) / 256, 256, 0, st>>>(mel, s->dbuf[s->hdr.in_mel_buf], nm);
     launches += 2;
