@@ -1,0 +1,61 @@
+"""world_size-2 gloo tests of the N > 1 path: weight-blob broadcast from rank 0 and session sharding."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mere_fusion_b200.dist import broadcast_bytes, mixed_sessions, shard
+    from helpers import seeded_wav2lip_state
+    blob = None
+    if rank == 0:
+        # a real packed blob (single conv layer program) so the header survives the trip
+        from mere_fusion_b200.convnet_pack import ProgramBuilder
+        pb = ProgramBuilder(2)
+        a, b = pb.buffer(8, 8, 16), pb.buffer(8, 8, 32)
+        pb.conv(a, 0, b, 0, np.random.default_rng(0).standard_normal((32, 16, 3, 3)).astype(np.float32), padding=1)
+        blob = pb.finish()
+    t = broadcast_bytes(blob, src=0)
+    import struct
+    magic, kind, ver, n = struct.unpack("<IIII", t[:16].numpy().tobytes())
+    mine = shard(mixed_sessions(64))
+    q.put((rank, int(t.numel()), int(t.sum().item()), magic, kind, [m[0] for m in mine]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_blob_broadcast_and_sharding_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, n0, s0, m0, k0, h0), (r1, n1, s1, m1, k1, h1) = res
+    assert n0 == n1 > 0 and s0 == s1 and m0 == m1 == 0x3242464D and k0 == k1 == 2
+    assert len(h0) + len(h1) == 64 and abs(len(h0) - len(h1)) <= 1
+    for h in (h0, h1):                                   # every GPU hosts all three heads
+        assert {"ernerf", "musetalk", "wav2lip"} <= set(h)
+
+
+def test_shard_is_a_partition():
+    from mere_fusion_b200.dist import mixed_sessions, shard
+    s = mixed_sessions(64)
+    assert len(s) == 64 and sorted(x[0] for x in s).count("ernerf") == 22
+    parts = [shard(s, 8, r) for r in range(8)]
+    assert sorted(sum(parts, [])) == sorted(s) and all(len(p) == 8 for p in parts)
