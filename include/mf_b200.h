@@ -199,6 +199,21 @@ int mf_convnet_debug_run(mf_ctx *ctx, int in_buf, const float *in_f32, int out_b
                          void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * MuseTalk: replaces pe(whisper) -> unet.model(latents, t=0, encoder_hidden_states).sample ->
+ * vae.decode_latents(pred) of the reference's inference() loop (musereal.py:99-108,
+ * musetalk/models/unet.py:12-27, musetalk/models/vae.py:96-108).  The program blob comes from
+ * mere_fusion_b200.musetalk_pack.pack_musetalk and is loaded with mf_wav2lip_load (same executor).
+ *   latents_f16 : device fp16 [B,8,32,32] NCHW  (masked || reference latents, vae.py:110-122)
+ *   whisper_f16 : device fp16 [B,50,384]        (MuseASR chunks, BEFORE the positional encoding)
+ *   out_u8      : device u8  [B,256,256,3] BGR  = ((x/2+0.5).clamp(0,1)*255).round(), nullable
+ *   out_f32     : device fp32 [B,256,256,3] RGB in [0,1], nullable
+ * ------------------------------------------------------------------------------------------ */
+int mf_musetalk_forward(mf_ctx *ctx, const void *latents_f16, const void *whisper_f16, uint8_t *out_u8,
+                        float *out_f32, int B, void *stream);
+/* unit-test helper: write an fp32 NHWC tensor into program buffer `buf` (second input of debug programs) */
+int mf_convnet_debug_set(mf_ctx *ctx, int buf, const float *in_f32, int B, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Paste-back (lipreal.py:207-214): out[i] = frames[idx_i] with faces[i] resized (cv2.resize, u8,
  * INTER_LINEAR, bit-exact) into the box (y1:y2, x1:x2).  coords order as wav2lip/genavatar.py:96.
  *   frames : device u8 [n_frames,H,W,3] the avatar's full frames, resident

@@ -80,6 +80,8 @@ def lib():
         L.mf_wav2lip_profile.argtypes = [c_vp, ctypes.c_int]
         L.mf_wav2lip_last_op_ms.argtypes = [c_vp, ctypes.POINTER(c_f)]
         L.mf_convnet_debug_run.argtypes = [c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp]
+        L.mf_musetalk_forward.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]
+        L.mf_convnet_debug_set.argtypes = [c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp]
         L.mf_paste_resize_u8.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int,
                                          ctypes.c_int, ctypes.POINTER(c_i32), c_vp, c_vp]
         _lib = L

@@ -72,9 +72,15 @@ class ProgramBuilder:
         return bn
 
     def _emit(self, in_buf, in_coff, cin_pad, out_buf, out_coff, Wm, taps, scale, shift, Mh, Mw, oy0, ox0, osy, osx,
-              isy, isx, res, relu, mode, cout):
+              isy, isx, res, relu, mode, cout, ups=0):
         ntaps = len(taps)
         assert ntaps <= CONV_MAX_TAPS
+        if mode == 0 and cout % 16 != 0:              # the bf16 epilogue stores 16 channels at a time: pad with zero rows
+            pad = (cout + 15) // 16 * 16
+            Wm = np.concatenate([Wm, np.zeros((pad - cout, Wm.shape[1]), np.float32)])
+            scale = np.concatenate([scale, np.ones(pad - cout, np.float32)])
+            shift = np.concatenate([shift, np.zeros(pad - cout, np.float32)])
+            cout = pad
         M = self.nominal_batch * Mh * Mw
         bn = self._pick_bn(cout, M)
         cout_pad = (cout + bn - 1) // bn * bn
@@ -92,31 +98,85 @@ class ProgramBuilder:
         dy = [t[0] for t in taps] + [0] * (CONV_MAX_TAPS - ntaps)
         dx = [t[1] for t in taps] + [0] * (CONV_MAX_TAPS - ntaps)
         rb, rc = res if res is not None else (-1, 0)
-        rec = struct.pack("<26i", in_buf, in_coff, out_buf, out_coff, rb, rc, Mh, Mw, oy0, ox0, osy, osx, isy, isx,
-                          ntaps, cin_pad, kpad, cout, cout_pad, bn, int(relu), mode, w_id, s_id, h_id, 0)
+        rec = struct.pack("<28i", in_buf, in_coff, out_buf, out_coff, rb, rc, Mh, Mw, oy0, ox0, osy, osx, isy, isx,
+                          ntaps, cin_pad, kpad, cout, cout_pad, bn, int(relu), mode, w_id, s_id, h_id, 0, ups, 0)
         rec += struct.pack(f"<{CONV_MAX_TAPS}b", *dy) + struct.pack(f"<{CONV_MAX_TAPS}b", *dx)
         self.ops.append(rec)
         return len(self.ops) - 1
 
     def conv(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, bn=None, stride=1, padding=0, res=None,
-             relu=True, mode=0):
-        """nn.Conv2d (+BatchNorm2d, +residual, +ReLU).  weight [Cout, Cin, kh, kw]"""
+             relu=True, mode=0, ups=0, extra_shift=None, wscale=1.0):
+        """nn.Conv2d (+BatchNorm2d, +residual, +ReLU).  weight [Cout, Cin, kh, kw].  ups = 1: the conv runs on the
+        nearest-neighbour 2x upsampling of the input buffer (F.interpolate(scale_factor=2) folded into the gather).
+        extra_shift: per-channel constant added after the conv (e.g. a time-embedding projection)."""
         weight = np.asarray(weight, np.float32)
         cout, cin, kh, kw = weight.shape
         sy, sx = (stride, stride) if np.isscalar(stride) else stride
         py, px = (padding, padding) if np.isscalar(padding) else padding
         Hin, Win, _ = self.buffers[in_buf]
+        Hin, Win = Hin << ups, Win << ups
         Hout, Wout = (Hin + 2 * py - kh) // sy + 1, (Win + 2 * px - kw) // sx + 1
         if mode == 0:
             assert self.buffers[out_buf][:2] == (Hout, Wout), (self.buffers[out_buf], Hout, Wout)
         cin_pad = (cin + 7) // 8 * 8
         taps = [(ky - py, kx - px) for ky in range(kh) for kx in range(kw)]
         Wm = np.zeros((cout, len(taps), cin_pad), np.float32)
-        Wm[:, :, :cin] = weight.transpose(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+        Wm[:, :, :cin] = weight.transpose(0, 2, 3, 1).reshape(cout, kh * kw, cin) * np.float32(wscale)
         scale, shift = bn_fold(bias, bn, cout)
+        if extra_shift is not None:
+            shift = (shift + np.asarray(extra_shift, np.float32) * scale).astype(np.float32)
         self.flops_per_sample += 2 * cout * cin * kh * kw * Hout * Wout
         return self._emit(in_buf, in_coff, cin_pad, out_buf, out_coff, Wm.reshape(cout, -1), taps, scale, shift, Hout,
-                          Wout, 0, 0, 1, 1, sy, sx, res, relu, mode, cout)
+                          Wout, 0, 0, 1, 1, sy, sx, res, relu, mode, cout, ups=ups)
+
+    def linear(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, res=None):
+        """nn.Linear on a token buffer = 1x1 conv.  weight [Cout, Cin]"""
+        w = np.asarray(weight, np.float32)
+        return self.conv(in_buf, in_coff, out_buf, out_coff, w[:, :, None, None], bias, None, res=res, relu=False)
+
+    def _misc(self, kind, in_buf, out_buf, **f):
+        v = dict(in_coff=0, out_coff=0, res_buf=-1, res_coff=0, Mh=0, Mw=0, ntaps=0, Cin=0, Kpad=0, relu=0, s_id=-1, h_id=-1)
+        v.update(f)
+        rec = struct.pack("<28i", in_buf, v["in_coff"], out_buf, v["out_coff"], v["res_buf"], v["res_coff"], v["Mh"], v["Mw"],
+                          0, 0, 1, 1, 1, 1, v["ntaps"], v["Cin"], v["Kpad"], 0, 0, 0, v["relu"], 0, -1, v["s_id"], v["h_id"],
+                          kind, 0, 0)
+        rec += bytes(2 * CONV_MAX_TAPS)
+        self.ops.append(rec)
+        return len(self.ops) - 1
+
+    @staticmethod
+    def _fbits(x):
+        return struct.unpack("<i", struct.pack("<f", float(x)))[0]
+
+    def group_norm(self, in_buf, out_buf, gamma, beta, groups=32, eps=1e-5, silu=False, in_coff=0):
+        """input = channels [in_coff, in_coff + C) of in_buf (C = len(gamma)); output buffer is dense [H, W, C]"""
+        C = len(gamma)
+        assert self.buffers[out_buf] == self.buffers[in_buf][:2] + (C,) and in_coff + C <= self.buffers[in_buf][2]
+        slot = getattr(self, "_gn_slots", 0)
+        self._gn_slots = slot + 1
+        return self._misc(1, in_buf, out_buf, in_coff=in_coff, Cin=C, ntaps=groups, relu=int(silu), Kpad=self._fbits(eps), Mh=slot,
+                          s_id=self._tensor(np.asarray(gamma, np.float32).tobytes()),
+                          h_id=self._tensor(np.asarray(beta, np.float32).tobytes()))
+
+    def layer_norm(self, in_buf, out_buf, gamma, beta, eps=1e-5):
+        C = self.buffers[in_buf][2]
+        assert self.buffers[out_buf] == self.buffers[in_buf] and len(gamma) == C
+        return self._misc(2, in_buf, out_buf, Cin=C, Kpad=self._fbits(eps),
+                          s_id=self._tensor(np.asarray(gamma, np.float32).tobytes()),
+                          h_id=self._tensor(np.asarray(beta, np.float32).tobytes()))
+
+    def attention(self, q, k, v, out, heads, dim_head):
+        """q, k, v, out: (buffer, channel offset).  softmax(q k^T / sqrt(dim_head)) v per head"""
+        nq = self.buffers[q[0]][0] * self.buffers[q[0]][1]
+        nk = self.buffers[k[0]][0] * self.buffers[k[0]][1]
+        self.flops_per_sample += 2 * 2 * heads * nq * nk * dim_head
+        return self._misc(3, q[0], out[0], in_coff=q[1], out_coff=out[1], res_buf=k[0], res_coff=k[1], Mh=v[0], Mw=v[1],
+                          ntaps=heads, Cin=dim_head, Kpad=self._fbits(dim_head ** -0.5))
+
+    def geglu(self, in_buf, out_buf):
+        Hd = self.buffers[out_buf][2]
+        assert self.buffers[in_buf][2] == 2 * Hd
+        return self._misc(4, in_buf, out_buf, Cin=Hd)
 
     def conv_transpose(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, bn=None, stride=1, padding=0,
                        output_padding=0, relu=True):

@@ -28,7 +28,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "mf_common.cuh"
+#include "convnet_ops.cuh"
 
 #define CONV_BM 128
 #define CONV_BK 64
@@ -46,11 +46,18 @@ struct W2LHeader {
 struct W2LBuffer {
     int32_t H, W, C, reserved;
 };
+// kind 0 = conv (fields as named).  Other kinds reuse the integer fields (see the packer, convnet_pack.py):
+//   1 GroupNorm(+SiLU): in_buf -> out_buf, Cin = C, ntaps = groups, relu = silu, Kpad = eps (float bits),
+//                       scale_entry / shift_entry = gamma / beta (fp32), Mh = stats slot
+//   2 LayerNorm       : in_buf -> out_buf, Cin = C, Kpad = eps bits, gamma / beta as above
+//   3 attention       : q = (in_buf, in_coff), k = (res_buf, res_coff), v = (Mh, Mw), out = (out_buf, out_coff),
+//                       ntaps = heads, Cin = dim_head, Kpad = scale (float bits)
+//   4 GEGLU           : in_buf [.., 2 * Cin] -> out_buf [.., Cin]
 struct W2LOp {
     int32_t in_buf, in_coff, out_buf, out_coff, res_buf, res_coff;
     int32_t Mh, Mw, oy0, ox0, osy, osx, isy, isx;
     int32_t ntaps, Cin, Kpad, Cout, Cout_pad, BN, relu, mode;
-    int32_t w_entry, scale_entry, shift_entry, reserved;
+    int32_t w_entry, scale_entry, shift_entry, kind, ups, reserved;
     int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];
 };
 
@@ -66,6 +73,7 @@ struct ConvParams {
     int res_stride, res_coff;
     int Mh, Mw, oy0, ox0, osy, osx, isy, isx;
     int ntaps, Cin, nkb, Cout, M, relu, mode;
+    int ups;  // input is a nearest-neighbour 2^ups upsampling of the stored tensor (folded into the gather)
     int dbg;  // timing experiments only (MF_CONV_DBG): 1 skip A loads, 2 skip B TMA, 4 skip MMA
     int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];
 };
@@ -206,8 +214,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
                     const __nv_bfloat16 *src = p.in;
                     if (ok) {
                         const int iy = iy0 + p.tap_dy[tap], ix = ix0 + p.tap_dx[tap];
-                        ok = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-                        if (ok) src = in_b + (iy * p.Win + ix) * p.in_stride + ch;
+                        ok = iy >= 0 && iy < (p.Hin << p.ups) && ix >= 0 && ix < (p.Win << p.ups);
+                        if (ok) src = in_b + ((iy >> p.ups) * p.Win + (ix >> p.ups)) * p.in_stride + ch;
                     }
                     const uint32_t nbytes = ok ? 16u : 0u;
                     const int step = ok ? 8 : 0;
@@ -263,6 +271,16 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
                 uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + opix * p.out_stride + p.out_coff + n0);
                 op[0] = make_uint4(o[0], o[1], o[2], o[3]);
                 op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            } else if (p.mode == 2) {
+                // VAE output head (musetalk/models/vae.py:102-107): (x / 2 + 0.5).clamp(0, 1) -> * 255 -> round -> u8,
+                // channels reversed RGB -> BGR; optional fp32 copy in [0,1], RGB
+                if (c0 != 0) continue;
+                for (int j = 0; j < p.Cout; j++) {
+                    const float a = fmaf(__uint_as_float(v[j]), __ldg(p.scale + j), __ldg(p.shift + j));
+                    const float im = fminf(fmaxf(a * 0.5f + 0.5f, 0.f), 1.f);
+                    if (p.out_f32) p.out_f32[opix * p.Cout + j] = im;
+                    if (p.out) reinterpret_cast<uint8_t *>(p.out)[opix * p.Cout + (p.Cout - 1 - j)] = (uint8_t)rintf(im * 255.f);
+                }
             } else {
                 // output head: bare conv + bias -> sigmoid (wav2lip.py:83-85) -> x255 truncated to u8
                 // (lipreal.py:126 `* 255.`, :209 `astype(np.uint8)`), NHWC
@@ -297,109 +315,14 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
     if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// ---- input preparation (lipreal.py:108-122) ---------------------------------------------------
-// faces u8 [B,S,S,3] BGR -> bf16 [B,S,S,8]: ch 0-2 = face with rows >= S/2 zeroed, ch 3-5 = face, /255
-__global__ void k_w2l_prep_face(const uint8_t *__restrict__ faces, __nv_bfloat16 *__restrict__ out, int B, int S) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * S * S) return;
-    const int row = (i / S) % S;
-    float v[8];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const float f = (float)faces[(size_t)i * 3 + c] / 255.f;
-        v[c] = row >= S / 2 ? 0.f : f;
-        v[3 + c] = f;
-    }
-    v[6] = v[7] = 0.f;
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-        o[j] = *reinterpret_cast<uint32_t *>(&h);
-    }
-    reinterpret_cast<uint4 *>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
-}
-// mel fp32 [B,1,80,16] -> bf16 [B,80,16,8] (channel 0)
-__global__ void k_w2l_prep_mel(const float *__restrict__ mel, __nv_bfloat16 *__restrict__ out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    __nv_bfloat162 h = __floats2bfloat162_rn(mel[i], 0.f);
-    reinterpret_cast<uint4 *>(out)[i] = make_uint4(*reinterpret_cast<uint32_t *>(&h), 0u, 0u, 0u);
-}
-// generic bf16 <-> fp32 NHWC converters for the unit-test entry point
-__global__ void k_f32_to_bf16(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, size_t n) {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
-}
-__global__ void k_bf16_to_f32(const __nv_bfloat16 *__restrict__ in, float *__restrict__ out, size_t n) {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __bfloat162float(in[i]);
-}
-
-// ---- host --------------------------------------------------------------------------------------
+// =====================================================================================================
+// host: program loader, launch list, direct / CUDA-graph execution
+// =====================================================================================================
 struct LaunchDesc {
     void *func;
     dim3 grid;
     int smem;
 };
-
-struct Wav2LipState {
-    W2LHeader hdr;
-    std::vector<W2LBuffer> bufs;
-    std::vector<W2LOp> ops;
-    std::vector<ConvParams> params;  // per op, batch-independent fields filled at load
-    std::vector<__nv_bfloat16 *> dbuf;
-    int max_batch = 0;
-    int last_launches = 0;
-    bool profile = false;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    int profile_op = -1;
-    // one instantiated CUDA graph per batch size: the ~70 launches of a forward are replayed with a single
-    // cudaGraphLaunch; only the three nodes that see caller pointers are re-parameterised per call
-    struct GraphEntry {
-        int B = 0;
-        cudaGraph_t graph = nullptr;
-        cudaGraphExec_t exec = nullptr;
-        cudaGraphNode_t n_face = nullptr, n_mel = nullptr, n_out = nullptr;
-        const float *mel = nullptr;
-        const uint8_t *faces = nullptr;
-        uint8_t *out_u8 = nullptr;
-        float *out_f32 = nullptr;
-        ConvParams out_params;
-        LaunchDesc out_desc;
-    };
-    std::vector<GraphEntry> graphs;
-    bool use_graph = true;
-};
-
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-    }
-    return fn;
-}
-
-void wav2lip_destroy(mf_ctx *ctx) {
-    Wav2LipState *s = ctx->wav2lip;
-    if (!s) return;
-    for (auto p : s->dbuf) cudaFree(p);
-    for (auto &g : s->graphs) {
-        if (g.exec) cudaGraphExecDestroy(g.exec);
-        if (g.graph) cudaGraphDestroy(g.graph);
-    }
-    if (s->ev[0]) { cudaEventDestroy(s->ev[0]); cudaEventDestroy(s->ev[1]); }
-    delete s;
-    ctx->wav2lip = nullptr;
-}
 
 template <int BN, int STAGES>
 static cudaError_t conv_desc_s(dim3 grid, LaunchDesc *d) {
@@ -433,6 +356,92 @@ static cudaError_t conv_desc_any(int BN, const ConvParams &p, LaunchDesc *d) {
     }
 }
 
+// one kernel launch with its by-value parameter struct; io != 0 marks the launches that see caller pointers
+enum { IO_NONE = 0, IO_IN0 = 1, IO_IN1 = 2, IO_OUT = 3 };
+struct Launch {
+    void *func = nullptr;
+    dim3 grid, block;
+    int smem = 0;
+    int io = IO_NONE;
+    int op = -1;  // program op index (conv ops: profiling hook), -1 for helper kernels
+    std::vector<unsigned char> params;
+    template <class T>
+    void set(const T &p) { params.assign((const unsigned char *)&p, (const unsigned char *)&p + sizeof(T)); }
+    template <class T>
+    T &as() { return *reinterpret_cast<T *>(params.data()); }
+};
+
+struct Wav2LipState {
+    W2LHeader hdr;
+    std::vector<W2LBuffer> bufs;
+    std::vector<W2LOp> ops;
+    std::vector<ConvParams> params;  // conv ops: batch-independent fields filled at load
+    std::vector<__nv_bfloat16 *> dbuf;
+    const unsigned char *blob = nullptr;
+    std::vector<unsigned char> *entry_table = nullptr;  // host copy of the blob's entry table
+    std::vector<const mf_blob_entry *> ent_of_op_scale, ent_of_op_shift;
+    float *stats = nullptr;   // GroupNorm statistics, [n_gn_slots][max_batch][64][2]
+    int n_gn_slots = 0;
+    float *scores = nullptr;  // attention scratch: fp32 scores
+    __nv_bfloat16 *probs = nullptr;
+    size_t score_elems = 0;
+    int max_batch = 0;
+    int last_launches = 0;
+    bool profile = false;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int profile_op = -1;
+    // cached launch list + instantiated CUDA graph per batch size: a forward is ONE cudaGraphLaunch; only the nodes
+    // that see caller pointers are re-parameterised when those change
+    struct Plan {
+        int B = 0;
+        std::vector<Launch> launches;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        std::vector<cudaGraphNode_t> nodes;
+        const void *in0 = nullptr, *in1 = nullptr;
+        void *out_u8 = nullptr;
+        float *out_f32 = nullptr;
+    };
+    std::vector<Plan *> plans;
+    bool use_graph = true;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+void wav2lip_destroy(mf_ctx *ctx) {
+    Wav2LipState *s = ctx->wav2lip;
+    if (!s) return;
+    for (auto p : s->dbuf) cudaFree(p);
+    for (auto pl : s->plans) {
+        if (pl->exec) cudaGraphExecDestroy(pl->exec);
+        if (pl->graph) cudaGraphDestroy(pl->graph);
+        delete pl;
+    }
+    delete s->entry_table;
+    cudaFree(s->stats);
+    cudaFree(s->scores);
+    cudaFree(s->probs);
+    if (s->ev[0]) { cudaEventDestroy(s->ev[0]); cudaEventDestroy(s->ev[1]); }
+    delete s;
+    ctx->wav2lip = nullptr;
+}
+
+static inline float bits_to_float(int32_t v) { float f; memcpy(&f, &v, 4); return f; }
+
 extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int max_batch) {
     if (!ctx) return MF_E_INVALID;
     MF_REQUIRE(ctx, blob && max_batch >= 1 && max_batch <= 256, "mf_wav2lip_load: bad arguments");
@@ -440,20 +449,23 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
     wav2lip_destroy(ctx);
     PFN_encodeTiled encode = get_encode();
     if (!encode) return mf_fail(ctx, MF_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
-    std::vector<unsigned char> head(sizeof(mf_blob_header) + MF_BLOB_MAX_ENTRIES * sizeof(mf_blob_entry));
-    const size_t hbytes = std::min(head.size(), nbytes);
-    MF_CUDA(ctx, cudaMemcpy(head.data(), blob, hbytes, cudaMemcpyDeviceToHost));
-    const mf_blob_header *h = reinterpret_cast<const mf_blob_header *>(head.data());
+    std::vector<unsigned char> *head = new std::vector<unsigned char>(sizeof(mf_blob_header) + 4096 * sizeof(mf_blob_entry));
+    const size_t hbytes = std::min(head->size(), nbytes);
+    MF_CUDA(ctx, cudaMemcpy(head->data(), blob, hbytes, cudaMemcpyDeviceToHost));
+    const mf_blob_header *h = reinterpret_cast<const mf_blob_header *>(head->data());
     MF_REQUIRE(ctx, hbytes >= sizeof(mf_blob_header) && h->magic == MF_BLOB_MAGIC && h->kind == 2,
                "mf_wav2lip_load: not a conv-net blob");
-    MF_REQUIRE(ctx, h->n_entries <= MF_BLOB_MAX_ENTRIES, "mf_wav2lip_load: too many entries");
-    const mf_blob_entry *ent = reinterpret_cast<const mf_blob_entry *>(head.data() + sizeof(mf_blob_header));
+    MF_REQUIRE(ctx, h->n_entries <= 4096 && sizeof(mf_blob_header) + h->n_entries * sizeof(mf_blob_entry) <= hbytes,
+               "mf_wav2lip_load: too many entries");
+    const mf_blob_entry *ent = reinterpret_cast<const mf_blob_entry *>(head->data() + sizeof(mf_blob_header));
     const unsigned char *base = reinterpret_cast<const unsigned char *>(blob);
-    auto find = [&](uint32_t id) -> const mf_blob_entry * {
-        for (uint32_t i = 0; i < h->n_entries; i++)
-            if (ent[i].id == id && ent[i].offset + ent[i].nbytes <= nbytes) return &ent[i];
-        return nullptr;
-    };
+    std::vector<const mf_blob_entry *> by_id;
+    for (uint32_t i = 0; i < h->n_entries; i++) {
+        if (ent[i].offset + ent[i].nbytes > nbytes) continue;
+        if (ent[i].id >= by_id.size()) by_id.resize(ent[i].id + 1, nullptr);
+        by_id[ent[i].id] = &ent[i];
+    }
+    auto find = [&](int32_t id) -> const mf_blob_entry * { return (id >= 0 && (size_t)id < by_id.size()) ? by_id[id] : nullptr; };
     const mf_blob_entry *pe = find(W2L_ID_PROGRAM);
     MF_REQUIRE(ctx, pe && pe->nbytes >= sizeof(W2LHeader), "mf_wav2lip_load: program entry missing");
     std::vector<unsigned char> prog(pe->nbytes);
@@ -461,6 +473,8 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
     Wav2LipState *s = new (std::nothrow) Wav2LipState();
     MF_REQUIRE(ctx, s, "out of host memory");
     ctx->wav2lip = s;
+    s->blob = base;
+    s->entry_table = head;
     s->hdr = *reinterpret_cast<const W2LHeader *>(prog.data());
     const size_t need = sizeof(W2LHeader) + (size_t)s->hdr.n_buffers * sizeof(W2LBuffer) + (size_t)s->hdr.n_ops * sizeof(W2LOp);
     MF_REQUIRE(ctx, s->hdr.n_buffers > 0 && s->hdr.n_ops > 0 && need == pe->nbytes, "mf_wav2lip_load: program size mismatch");
@@ -477,16 +491,43 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
         MF_CUDA(ctx, cudaMemset(s->dbuf[i], 0, bytes));
     }
     s->params.resize(s->hdr.n_ops);
+    s->ent_of_op_scale.assign(s->hdr.n_ops, nullptr);
+    s->ent_of_op_shift.assign(s->hdr.n_ops, nullptr);
+    auto okbuf = [&](int b) { return b >= 0 && b < s->hdr.n_buffers; };
     for (int i = 0; i < s->hdr.n_ops; i++) {
         const W2LOp &o = s->ops[i];
+        if (o.kind != 0) {
+            MF_REQUIRE(ctx, o.kind >= 1 && o.kind <= 4, "op %d: unknown kind %d", i, o.kind);
+            MF_REQUIRE(ctx, okbuf(o.in_buf) && okbuf(o.out_buf), "op %d: bad buffer id", i);
+            if (o.kind == 1 || o.kind == 2) {
+                const mf_blob_entry *se = find(o.scale_entry), *he = find(o.shift_entry);
+                MF_REQUIRE(ctx, se && he && se->nbytes == (size_t)o.Cin * 4 && he->nbytes == (size_t)o.Cin * 4 &&
+                                    o.in_coff % 8 == 0 && o.in_coff + o.Cin <= s->bufs[o.in_buf].C &&
+                                    (o.kind == 1 || s->bufs[o.in_buf].C == o.Cin) && s->bufs[o.out_buf].C == o.Cin && o.Cin % 8 == 0,
+                           "op %d: norm parameters do not match the buffers", i);
+                s->ent_of_op_scale[i] = se;
+                s->ent_of_op_shift[i] = he;
+                if (o.kind == 1) {
+                    MF_REQUIRE(ctx, o.ntaps >= 1 && o.ntaps <= 64 && o.Cin % o.ntaps == 0, "op %d: bad group count", i);
+                    s->n_gn_slots = std::max(s->n_gn_slots, o.Mh + 1);
+                }
+            } else if (o.kind == 3) {
+                MF_REQUIRE(ctx, okbuf(o.res_buf) && okbuf(o.Mh) && o.Cin % 8 == 0 && o.ntaps >= 1, "op %d: bad attention op", i);
+                const size_t nq = (size_t)s->bufs[o.in_buf].H * s->bufs[o.in_buf].W;
+                const size_t nk = (size_t)s->bufs[o.res_buf].H * s->bufs[o.res_buf].W;
+                s->score_elems = std::max(s->score_elems, (size_t)max_batch * o.ntaps * nq * ((nk + 63) / 64 * 64));
+            } else {
+                MF_REQUIRE(ctx, s->bufs[o.in_buf].C == 2 * o.Cin && s->bufs[o.out_buf].C == o.Cin && o.Cin % 8 == 0, "op %d: bad GEGLU op", i);
+            }
+            continue;
+        }
         ConvParams &p = s->params[i];
         memset(&p, 0, sizeof(p));
-        auto okbuf = [&](int b) { return b >= 0 && b < s->hdr.n_buffers; };
-        MF_REQUIRE(ctx, okbuf(o.in_buf) && (o.mode == 1 || okbuf(o.out_buf)) && (o.res_buf < 0 || okbuf(o.res_buf)),
+        MF_REQUIRE(ctx, okbuf(o.in_buf) && (o.mode != 0 || okbuf(o.out_buf)) && (o.res_buf < 0 || okbuf(o.res_buf)),
                    "op %d: bad buffer id", i);
         MF_REQUIRE(ctx, o.BN == 16 || o.BN == 32 || o.BN == 64 || o.BN == 128, "op %d: BN %d unsupported", i, o.BN);
         MF_REQUIRE(ctx, o.ntaps >= 1 && o.ntaps <= CONV_MAX_TAPS && o.Cin % 8 == 0 && o.Kpad % CONV_BK == 0 &&
-                            o.Kpad >= o.ntaps * o.Cin && o.Cout_pad % o.BN == 0 && o.Cout <= o.Cout_pad,
+                            o.Kpad >= o.ntaps * o.Cin && o.Cout_pad % o.BN == 0 && o.Cout <= o.Cout_pad && o.ups >= 0 && o.ups <= 2,
                    "op %d: bad geometry", i);
         const mf_blob_entry *we = find(o.w_entry), *se = find(o.scale_entry), *he = find(o.shift_entry);
         MF_REQUIRE(ctx, we && se && he && we->nbytes == (size_t)o.Cout_pad * o.Kpad * 2 &&
@@ -495,7 +536,7 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
         const W2LBuffer &ib = s->bufs[o.in_buf];
         MF_REQUIRE(ctx, o.in_coff % 8 == 0 && ib.C % 8 == 0 && o.in_coff + o.Cin <= ib.C, "op %d: input channels out of range", i);
         p.in = s->dbuf[o.in_buf];
-        p.in_stride = ib.C; p.in_coff = o.in_coff; p.Hin = ib.H; p.Win = ib.W;
+        p.in_stride = ib.C; p.in_coff = o.in_coff; p.Hin = ib.H; p.Win = ib.W; p.ups = o.ups;
         if (o.mode == 0) {
             const W2LBuffer &ob = s->bufs[o.out_buf];
             MF_REQUIRE(ctx, o.out_coff % 8 == 0 && ob.C % 8 == 0 && o.out_coff + o.Cout <= ob.C && o.Cout % 16 == 0,
@@ -503,7 +544,7 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
             p.out = s->dbuf[o.out_buf];
             p.out_stride = ob.C; p.out_coff = o.out_coff; p.Hout = ob.H; p.Wout = ob.W;
         } else {
-            MF_REQUIRE(ctx, o.Cout <= 16 && o.BN == 16, "op %d: output head must have Cout <= 16", i);
+            MF_REQUIRE(ctx, o.Cout <= 16 && o.BN == 16 && (o.mode == 1 || o.mode == 2), "op %d: output head must have Cout <= 16", i);
             p.Hout = s->hdr.out_hw; p.Wout = s->hdr.out_hw;
         }
         MF_REQUIRE(ctx, o.oy0 + o.osy * (o.Mh - 1) < p.Hout && o.ox0 + o.osx * (o.Mw - 1) < p.Wout, "op %d: output grid out of range", i);
@@ -530,12 +571,19 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return mf_fail(ctx, MF_E_CUDA, "op %d: cuTensorMapEncodeTiled failed (%d)", i, (int)cr);
     }
+    if (s->n_gn_slots) MF_CUDA(ctx, cudaMalloc(&s->stats, (size_t)s->n_gn_slots * max_batch * 128 * sizeof(float)));
+    if (s->score_elems) {
+        MF_CUDA(ctx, cudaMalloc(&s->scores, s->score_elems * sizeof(float)));
+        MF_CUDA(ctx, cudaMalloc(&s->probs, s->score_elems * sizeof(__nv_bfloat16)));
+    }
     MF_CUDA(ctx, cudaDeviceSynchronize());
     return MF_OK;
 }
 
-static int run_ops(mf_ctx *ctx, Wav2LipState *s, int B, uint8_t *out_u8, float *out_f32, cudaStream_t st, int *launches) {
-    for (int i = 0; i < s->hdr.n_ops; i++) {
+// ---- launch list -----------------------------------------------------------------------------------
+static int add_op_launches(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<Launch> &L) {
+    const W2LOp &o = s->ops[i];
+    if (o.kind == 0) {
         ConvParams p = s->params[i];
         p.M = B * p.Mh * p.Mw;
         {
@@ -543,103 +591,186 @@ static int run_ops(mf_ctx *ctx, Wav2LipState *s, int B, uint8_t *out_u8, float *
             if (dbg < 0) { const char *e = getenv("MF_CONV_DBG"); dbg = e ? atoi(e) : 0; }
             p.dbg = dbg;
         }
-        if (p.mode == 1) {
-            p.out = out_u8;
-            p.out_f32 = out_f32;
-        }
-        if (s->profile && i == s->profile_op) cudaEventRecord(s->ev[0], st);
         LaunchDesc d;
-        cudaError_t e = conv_desc_any(s->ops[i].BN, p, &d);
-        if (e == cudaSuccess) {
-            void *args[] = {&p};
-            e = cudaLaunchKernel(d.func, d.grid, dim3(CONV_THREADS), args, d.smem, st);
+        MF_CUDA(ctx, conv_desc_any(o.BN, p, &d));
+        Launch l;
+        l.func = d.func; l.grid = d.grid; l.block = dim3(CONV_THREADS); l.smem = d.smem; l.op = i;
+        l.io = p.mode != 0 ? IO_OUT : IO_NONE;
+        l.set(p);
+        L.push_back(std::move(l));
+        return MF_OK;
+    }
+    const W2LBuffer &ib = s->bufs[o.in_buf];
+    if (o.kind == 1 || o.kind == 2) {
+        NormParams n;
+        n.in = s->dbuf[o.in_buf]; n.out = s->dbuf[o.out_buf];
+        n.gamma = reinterpret_cast<const float *>(s->blob + s->ent_of_op_scale[i]->offset);
+        n.beta = reinterpret_cast<const float *>(s->blob + s->ent_of_op_shift[i]->offset);
+        n.C = o.Cin; n.G = o.ntaps; n.silu = o.relu; n.eps = bits_to_float(o.Kpad);
+        n.stats = nullptr; n.pix_per_cta = 0; n.in_stride = ib.C; n.in_coff = o.in_coff;
+        if (o.kind == 1) {
+            n.npix = ib.H * ib.W;
+            n.stats = s->stats + (size_t)o.Mh * s->max_batch * 128;
+            const int target = std::max(1, (148 * 8) / B);
+            n.pix_per_cta = std::max(32, (n.npix + target - 1) / target);
+            Launch a;
+            a.func = (void *)k_gn_stats; a.grid = dim3((n.npix + n.pix_per_cta - 1) / n.pix_per_cta, B); a.block = dim3(256); a.op = -1;
+            a.set(n);
+            L.push_back(std::move(a));
+            Launch b;
+            b.func = (void *)k_gn_apply; b.grid = dim3((unsigned)(((size_t)n.npix * (n.C / 8) + 255) / 256), B); b.block = dim3(256);
+            b.set(n);
+            L.push_back(std::move(b));
+        } else {
+            n.npix = B * ib.H * ib.W;
+            Launch a;
+            a.func = (void *)k_layernorm; a.grid = dim3((n.npix + 7) / 8); a.block = dim3(256);
+            a.set(n);
+            L.push_back(std::move(a));
         }
-        if (s->profile && i == s->profile_op) cudaEventRecord(s->ev[1], st);
-        if (e != cudaSuccess) return mf_fail(ctx, MF_E_CUDA, "conv op %d launch: %s", i, cudaGetErrorString(e));
-        (*launches)++;
+        return MF_OK;
+    }
+    if (o.kind == 4) {
+        GegluParams g;
+        g.in = s->dbuf[o.in_buf]; g.out = s->dbuf[o.out_buf]; g.tokens = (size_t)B * ib.H * ib.W; g.Hd = o.Cin;
+        Launch a;
+        a.func = (void *)k_geglu; a.grid = dim3((unsigned)((g.tokens * (g.Hd / 8) + 255) / 256)); a.block = dim3(256);
+        a.set(g);
+        L.push_back(std::move(a));
+        return MF_OK;
+    }
+    // attention: scores = Q K^T -> softmax -> P V
+    const W2LBuffer &kb = s->bufs[o.res_buf], &vb = s->bufs[o.Mh], &ob = s->bufs[o.out_buf];
+    const int nq = ib.H * ib.W, nk = kb.H * kb.W, heads = o.ntaps, dh = o.Cin, ld = (nk + 63) / 64 * 64;
+    GemmParams g1;
+    g1.A = s->dbuf[o.in_buf] + o.in_coff; g1.lda = ib.C; g1.a_bs = (long long)nq * ib.C; g1.a_hs = dh;
+    g1.B = s->dbuf[o.res_buf] + o.res_coff; g1.ldb = kb.C; g1.b_bs = (long long)nk * kb.C; g1.b_hs = dh;
+    g1.C = s->scores; g1.ldc = ld; g1.c_bs = (long long)heads * nq * ld; g1.c_hs = (long long)nq * ld;
+    g1.M = nq; g1.N = nk; g1.K = dh; g1.heads = heads;
+    Launch a;
+    a.func = (void *)k_bgemm<false, false>; a.grid = dim3((nk + 63) / 64, (nq + 63) / 64, B * heads); a.block = dim3(128);
+    a.set(g1);
+    L.push_back(std::move(a));
+    SoftmaxParams sp;
+    sp.S = s->scores; sp.P = s->probs; sp.rows = (size_t)B * heads * nq; sp.n = nk; sp.ld = ld; sp.scale = bits_to_float(o.Kpad);
+    Launch b;
+    b.func = (void *)k_softmax; b.grid = dim3((unsigned)((sp.rows + 7) / 8)); b.block = dim3(256);
+    b.set(sp);
+    L.push_back(std::move(b));
+    GemmParams g2;
+    g2.A = s->probs; g2.lda = ld; g2.a_bs = (long long)heads * nq * ld; g2.a_hs = (long long)nq * ld;
+    g2.B = s->dbuf[o.Mh] + o.Mw; g2.ldb = vb.C; g2.b_bs = (long long)nk * vb.C; g2.b_hs = dh;
+    g2.C = s->dbuf[o.out_buf] + o.out_coff; g2.ldc = ob.C; g2.c_bs = (long long)nq * ob.C; g2.c_hs = dh;
+    g2.M = nq; g2.N = dh; g2.K = nk; g2.heads = heads;
+    Launch c;
+    c.func = (void *)k_bgemm<true, true>; c.grid = dim3((dh + 63) / 64, (nq + 63) / 64, B * heads); c.block = dim3(128);
+    c.set(g2);
+    L.push_back(std::move(c));
+    return MF_OK;
+}
+
+// program inputs: wav2lip (in_face_buf >= 0): in0 = faces u8, in1 = mel fp32;  musetalk (mel_h == 0 marks it):
+// in0 = latents fp16 NCHW [B,C,H,W], in1 = whisper fp16 [B,T,D]
+static bool is_musetalk(const Wav2LipState *s) { return s->hdr.mel_w < 0; }
+
+static int build_plan(mf_ctx *ctx, Wav2LipState *s, Wav2LipState::Plan *pl, int B) {
+    std::vector<Launch> &L = pl->launches;
+    pl->B = B;
+    const W2LBuffer &b0 = s->bufs[s->hdr.in_face_buf], &b1 = s->bufs[s->hdr.in_mel_buf];
+    {
+        PrepParams p0, p1;
+        Launch l0, l1;
+        if (!is_musetalk(s)) {
+            p0 = {nullptr, s->dbuf[s->hdr.in_face_buf], B, s->hdr.face_hw, 0, 0};
+            l0.func = (void *)k_prep_face; l0.grid = dim3((B * b0.H * b0.W + 255) / 256);
+            p1 = {nullptr, s->dbuf[s->hdr.in_mel_buf], B * b1.H * b1.W, 0, 0, 0};
+            l1.func = (void *)k_prep_mel; l1.grid = dim3((B * b1.H * b1.W + 255) / 256);
+        } else {
+            p0 = {nullptr, s->dbuf[s->hdr.in_face_buf], B, s->hdr.face_hw /* real latent channels */, b0.H * b0.W, b0.C};
+            l0.func = (void *)k_prep_latents; l0.grid = dim3((B * b0.H * b0.W * b0.C + 255) / 256);
+            p1 = {nullptr, s->dbuf[s->hdr.in_mel_buf], B, b1.H * b1.W, b1.C, 0};
+            l1.func = (void *)k_prep_ctx; l1.grid = dim3((B * b1.H * b1.W * b1.C + 255) / 256);
+        }
+        l0.block = l1.block = dim3(256);
+        l0.io = IO_IN0; l1.io = IO_IN1;
+        l0.set(p0); l1.set(p1);
+        L.push_back(std::move(l0));
+        L.push_back(std::move(l1));
+    }
+    for (int i = 0; i < s->hdr.n_ops; i++) {
+        int rc = add_op_launches(ctx, s, i, B, L);
+        if (rc) return rc;
     }
     return MF_OK;
 }
 
-static int add_kernel_node(mf_ctx *ctx, cudaGraph_t g, cudaGraphNode_t *prev, cudaGraphNode_t *out, void *func, dim3 grid,
-                           dim3 block, int smem, void **args) {
-    cudaKernelNodeParams kp;
-    memset(&kp, 0, sizeof(kp));
-    kp.func = func; kp.gridDim = grid; kp.blockDim = block; kp.sharedMemBytes = (unsigned)smem; kp.kernelParams = args;
-    MF_CUDA(ctx, cudaGraphAddKernelNode(out, g, *prev ? prev : nullptr, *prev ? 1 : 0, &kp));
-    *prev = *out;
+static void patch_io(Wav2LipState::Plan *pl, const void *in0, const void *in1, void *out_u8, float *out_f32) {
+    for (auto &l : pl->launches) {
+        if (l.io == IO_IN0) l.as<PrepParams>().src = in0;
+        else if (l.io == IO_IN1) l.as<PrepParams>().src = in1;
+        else if (l.io == IO_OUT) { l.as<ConvParams>().out = out_u8; l.as<ConvParams>().out_f32 = out_f32; }
+    }
+    pl->in0 = in0; pl->in1 = in1; pl->out_u8 = out_u8; pl->out_f32 = out_f32;
+}
+
+static int launch_direct(mf_ctx *ctx, Wav2LipState *s, std::vector<Launch> &L, cudaStream_t st) {
+    if (s->stats) MF_CUDA(ctx, cudaMemsetAsync(s->stats, 0, (size_t)s->n_gn_slots * s->max_batch * 128 * sizeof(float), st));
+    for (auto &l : L) {
+        const bool prof = s->profile && l.op >= 0 && l.op == s->profile_op;
+        if (prof) cudaEventRecord(s->ev[0], st);
+        void *args[] = {l.params.data()};
+        MF_CUDA(ctx, cudaLaunchKernel(l.func, l.grid, l.block, args, l.smem, st));
+        if (prof) cudaEventRecord(s->ev[1], st);
+    }
     return MF_OK;
 }
 
-static int set_kernel_node(mf_ctx *ctx, cudaGraphExec_t ex, cudaGraphNode_t node, void *func, dim3 grid, dim3 block, int smem,
-                           void **args) {
-    cudaKernelNodeParams kp;
-    memset(&kp, 0, sizeof(kp));
-    kp.func = func; kp.gridDim = grid; kp.blockDim = block; kp.sharedMemBytes = (unsigned)smem; kp.kernelParams = args;
-    MF_CUDA(ctx, cudaGraphExecKernelNodeSetParams(ex, node, &kp));
-    return MF_OK;
-}
-
-// the whole forward as one graph launch; returns MF_E_UNSUPPORTED when the graph path must be skipped
-static int forward_graph(mf_ctx *ctx, Wav2LipState *s, const float *mel, const uint8_t *faces, uint8_t *out_u8,
-                         float *out_f32, int B, cudaStream_t st) {
-    const int S = s->hdr.face_hw;
-    int nf = B * S * S, nm = B * s->hdr.mel_h * s->hdr.mel_w, Bv = B, Sv = S;
-    __nv_bfloat16 *fbuf = s->dbuf[s->hdr.in_face_buf], *mbuf = s->dbuf[s->hdr.in_mel_buf];
-    Wav2LipState::GraphEntry *ge = nullptr;
-    for (auto &g : s->graphs) if (g.B == B) ge = &g;
-    if (!ge) {
-        if (s->ops.empty() || s->ops.back().mode != 1) return MF_E_UNSUPPORTED;
-        s->graphs.emplace_back();
-        ge = &s->graphs.back();
-        ge->B = B;
-        MF_CUDA(ctx, cudaGraphCreate(&ge->graph, 0));
-        cudaGraphNode_t prev = nullptr, node = nullptr;
-        {
-            void *a0[] = {(void *)&faces, (void *)&fbuf, &Bv, &Sv};
-            int rc = add_kernel_node(ctx, ge->graph, &prev, &ge->n_face, (void *)k_w2l_prep_face, dim3((nf + 255) / 256), dim3(256), 0, a0);
-            if (rc) return rc;
-            void *a1[] = {(void *)&mel, (void *)&mbuf, &nm};
-            rc = add_kernel_node(ctx, ge->graph, &prev, &ge->n_mel, (void *)k_w2l_prep_mel, dim3((nm + 255) / 256), dim3(256), 0, a1);
-            if (rc) return rc;
+static int forward_common(mf_ctx *ctx, Wav2LipState *s, const void *in0, const void *in1, void *out_u8, float *out_f32,
+                          int B, cudaStream_t st) {
+    Wav2LipState::Plan *pl = nullptr;
+    for (auto q : s->plans) if (q->B == B) pl = q;
+    if (!pl) {
+        pl = new Wav2LipState::Plan();
+        s->plans.push_back(pl);
+        int rc = build_plan(ctx, s, pl, B);
+        if (rc) return rc;
+    }
+    const bool io_changed = pl->in0 != in0 || pl->in1 != in1 || pl->out_u8 != out_u8 || pl->out_f32 != out_f32;
+    if (io_changed) patch_io(pl, in0, in1, out_u8, out_f32);
+    s->last_launches = (int)pl->launches.size();
+    if (!s->use_graph || s->profile) return launch_direct(ctx, s, pl->launches, st);
+    if (!pl->exec) {
+        MF_CUDA(ctx, cudaGraphCreate(&pl->graph, 0));
+        cudaGraphNode_t prev = nullptr;
+        if (s->stats) {
+            cudaMemsetParams mp;
+            memset(&mp, 0, sizeof(mp));
+            mp.dst = s->stats; mp.value = 0; mp.elementSize = 4; mp.width = (size_t)s->n_gn_slots * s->max_batch * 128; mp.height = 1;
+            MF_CUDA(ctx, cudaGraphAddMemsetNode(&prev, pl->graph, nullptr, 0, &mp));
         }
-        for (int i = 0; i < s->hdr.n_ops; i++) {
-            ConvParams p = s->params[i];
-            p.M = B * p.Mh * p.Mw;
-            p.dbg = 0;
-            if (p.mode == 1) { p.out = out_u8; p.out_f32 = out_f32; }
-            LaunchDesc d;
-            MF_CUDA(ctx, conv_desc_any(s->ops[i].BN, p, &d));
-            void *a[] = {&p};
-            int rc = add_kernel_node(ctx, ge->graph, &prev, &node, d.func, d.grid, dim3(CONV_THREADS), d.smem, a);
-            if (rc) return rc;
-            if (p.mode == 1) { ge->n_out = node; ge->out_params = p; ge->out_desc = d; }
+        pl->nodes.resize(pl->launches.size());
+        for (size_t i = 0; i < pl->launches.size(); i++) {
+            Launch &l = pl->launches[i];
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof(kp));
+            void *args[] = {l.params.data()};
+            kp.func = l.func; kp.gridDim = l.grid; kp.blockDim = l.block; kp.sharedMemBytes = (unsigned)l.smem; kp.kernelParams = args;
+            MF_CUDA(ctx, cudaGraphAddKernelNode(&pl->nodes[i], pl->graph, prev ? &prev : nullptr, prev ? 1 : 0, &kp));
+            prev = pl->nodes[i];
         }
-        MF_CUDA(ctx, cudaGraphInstantiate(&ge->exec, ge->graph, 0));
-        ge->mel = mel; ge->faces = faces; ge->out_u8 = out_u8; ge->out_f32 = out_f32;
+        MF_CUDA(ctx, cudaGraphInstantiate(&pl->exec, pl->graph, 0));
+    } else if (io_changed) {
+        for (size_t i = 0; i < pl->launches.size(); i++) {
+            Launch &l = pl->launches[i];
+            if (l.io == IO_NONE) continue;
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof(kp));
+            void *args[] = {l.params.data()};
+            kp.func = l.func; kp.gridDim = l.grid; kp.blockDim = l.block; kp.sharedMemBytes = (unsigned)l.smem; kp.kernelParams = args;
+            MF_CUDA(ctx, cudaGraphExecKernelNodeSetParams(pl->exec, pl->nodes[i], &kp));
+        }
     }
-    if (ge->faces != faces) {
-        void *a0[] = {(void *)&faces, (void *)&fbuf, &Bv, &Sv};
-        int rc = set_kernel_node(ctx, ge->exec, ge->n_face, (void *)k_w2l_prep_face, dim3((nf + 255) / 256), dim3(256), 0, a0);
-        if (rc) return rc;
-        ge->faces = faces;
-    }
-    if (ge->mel != mel) {
-        void *a1[] = {(void *)&mel, (void *)&mbuf, &nm};
-        int rc = set_kernel_node(ctx, ge->exec, ge->n_mel, (void *)k_w2l_prep_mel, dim3((nm + 255) / 256), dim3(256), 0, a1);
-        if (rc) return rc;
-        ge->mel = mel;
-    }
-    if (ge->out_u8 != out_u8 || ge->out_f32 != out_f32) {
-        ge->out_params.out = out_u8;
-        ge->out_params.out_f32 = out_f32;
-        void *a[] = {&ge->out_params};
-        int rc = set_kernel_node(ctx, ge->exec, ge->n_out, ge->out_desc.func, ge->out_desc.grid, dim3(CONV_THREADS), ge->out_desc.smem, a);
-        if (rc) return rc;
-        ge->out_u8 = out_u8; ge->out_f32 = out_f32;
-    }
-    MF_CUDA(ctx, cudaGraphLaunch(ge->exec, st));
-    s->last_launches = 2 + s->hdr.n_ops;
+    MF_CUDA(ctx, cudaGraphLaunch(pl->exec, st));
     return MF_OK;
 }
 
@@ -650,27 +781,27 @@ extern "C" int mf_wav2lip_forward(mf_ctx *ctx, const float *mel, const uint8_t *
     if (!s) return mf_fail(ctx, MF_E_STATE, "mf_wav2lip_forward: weights not loaded");
     MF_REQUIRE(ctx, mel && faces && (out_u8 || out_f32), "mf_wav2lip_forward: null pointer");
     MF_REQUIRE(ctx, B >= 1 && B <= s->max_batch, "mf_wav2lip_forward: batch %d outside [1, %d]", B, s->max_batch);
-    MF_REQUIRE(ctx, s->hdr.in_face_buf >= 0 && s->hdr.in_mel_buf >= 0, "program has no wav2lip inputs");
-    cudaStream_t st = (cudaStream_t)stream;
+    MF_REQUIRE(ctx, s->hdr.in_face_buf >= 0 && s->hdr.in_mel_buf >= 0 && !is_musetalk(s) && s->ops.back().mode == 1,
+               "the loaded program is not a wav2lip program");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
-    int launches = 0;
-    const int S = s->hdr.face_hw;
-    const int nf = B * S * S, nm = B * s->hdr.mel_h * s->hdr.mel_w;
-    if (s->use_graph && !s->profile) {
-        int rc = forward_graph(ctx, s, mel, faces, out_u8, out_f32, B, st);
-        if (rc != MF_E_UNSUPPORTED) return rc;
-    }
-    k_w2l_prep_face<<<(nf + 255) / 256, 256, 0, st>>>(faces, s->dbuf[s->hdr.in_face_buf], B, S);
-    k_w2l_prep_mel<<<(nm + 255) / 256, 256, 0, st>>>(mel, s->dbuf[s->hdr.in_mel_buf], nm);
-    launches += 2;
-    int rc = run_ops(ctx, s, B, out_u8, out_f32, st, &launches);
-    if (rc) return rc;
-    s->last_launches = launches;
-    return MF_OK;
+    return forward_common(ctx, s, faces, mel, out_u8, out_f32, B, (cudaStream_t)stream);
 }
 
-// unit-test entry: run the loaded program on an fp32 NHWC tensor written into buffer `in_buf`
-// (all of its channels) and read buffer `out_buf` back as fp32 NHWC.
+extern "C" int mf_musetalk_forward(mf_ctx *ctx, const void *latents_f16, const void *whisper_f16, uint8_t *out_u8,
+                                   float *out_f32, int B, void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    Wav2LipState *s = ctx->wav2lip;
+    if (!s) return mf_fail(ctx, MF_E_STATE, "mf_musetalk_forward: weights not loaded");
+    MF_REQUIRE(ctx, latents_f16 && whisper_f16 && (out_u8 || out_f32), "mf_musetalk_forward: null pointer");
+    MF_REQUIRE(ctx, B >= 1 && B <= s->max_batch, "mf_musetalk_forward: batch %d outside [1, %d]", B, s->max_batch);
+    MF_REQUIRE(ctx, s->hdr.in_face_buf >= 0 && s->hdr.in_mel_buf >= 0 && is_musetalk(s) && s->ops.back().mode == 2,
+               "the loaded program is not a musetalk program");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    return forward_common(ctx, s, latents_f16, whisper_f16, out_u8, out_f32, B, (cudaStream_t)stream);
+}
+
+// unit-test entry: run the loaded program on an fp32 NHWC tensor written into buffer `in_buf` (all of its channels)
+// and read buffer `out_buf` back as fp32 NHWC (programs without an output head).
 extern "C" int mf_convnet_debug_run(mf_ctx *ctx, int in_buf, const float *in_f32, int out_buf, float *out_f32, int B,
                                     void *stream) {
     if (!ctx) return MF_E_INVALID;
@@ -682,14 +813,42 @@ extern "C" int mf_convnet_debug_run(mf_ctx *ctx, int in_buf, const float *in_f32
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n_in = (size_t)B * s->bufs[in_buf].H * s->bufs[in_buf].W * s->bufs[in_buf].C;
     const size_t n_out = (size_t)B * s->bufs[out_buf].H * s->bufs[out_buf].W * s->bufs[out_buf].C;
-    k_f32_to_bf16<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(in_f32, s->dbuf[in_buf], n_in);
-    int launches = 1;
-    for (int i = 0; i < s->hdr.n_ops; i++) MF_REQUIRE(ctx, s->ops[i].mode == 0, "debug run supports mode-0 ops only");
-    int rc = run_ops(ctx, s, B, nullptr, nullptr, st, &launches);
+    std::vector<Launch> L;
+    {
+        PrepParams p = {in_f32, s->dbuf[in_buf], (int)(n_in & 0xffffffffu), (int)(n_in >> 32), 0, 0};
+        Launch l;
+        l.func = (void *)k_f32_to_bf16; l.grid = dim3((unsigned)((n_in + 255) / 256)); l.block = dim3(256);
+        l.set(p);
+        L.push_back(std::move(l));
+    }
+    for (int i = 0; i < s->hdr.n_ops; i++) {
+        MF_REQUIRE(ctx, s->ops[i].kind != 0 || s->ops[i].mode == 0, "debug run supports programs without an output head");
+        int rc = add_op_launches(ctx, s, i, B, L);
+        if (rc) return rc;
+    }
+    {
+        PrepParams p = {s->dbuf[out_buf], out_f32, (int)(n_out & 0xffffffffu), (int)(n_out >> 32), 0, 0};
+        Launch l;
+        l.func = (void *)k_bf16_to_f32; l.grid = dim3((unsigned)((n_out + 255) / 256)); l.block = dim3(256);
+        l.set(p);
+        L.push_back(std::move(l));
+    }
+    int rc = launch_direct(ctx, s, L, st);
     if (rc) return rc;
-    k_bf16_to_f32<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(s->dbuf[out_buf], out_f32, n_out);
+    s->last_launches = (int)L.size();
+    return MF_OK;
+}
+
+// second input of a two-input debug program (e.g. the attention context): fp32 NHWC -> buffer, synchronous helper
+extern "C" int mf_convnet_debug_set(mf_ctx *ctx, int buf, const float *in_f32, int B, void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    Wav2LipState *s = ctx->wav2lip;
+    if (!s) return mf_fail(ctx, MF_E_STATE, "mf_convnet_debug_set: program not loaded");
+    MF_REQUIRE(ctx, in_f32 && B >= 1 && B <= s->max_batch && buf >= 0 && buf < s->hdr.n_buffers, "mf_convnet_debug_set: bad arguments");
+    const size_t n = (size_t)B * s->bufs[buf].H * s->bufs[buf].W * s->bufs[buf].C;
+    PrepParams p = {in_f32, s->dbuf[buf], (int)(n & 0xffffffffu), (int)(n >> 32), 0, 0};
+    k_f32_to_bf16<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
     MF_CUDA(ctx, cudaGetLastError());
-    s->last_launches = launches + 1;
     return MF_OK;
 }
 

@@ -26,6 +26,13 @@ class ConvNet:
         check(self.ctx.handle, lib().mf_wav2lip_load(self.ctx.handle, _ptr(self.blob), self.blob.numel(), max_batch),
               "mf_wav2lip_load")
 
+    def debug_set(self, buf, x_nhwc):
+        x = x_nhwc.contiguous().float().to(self.device)
+        s = torch.cuda.current_stream(self.device)
+        check(self.ctx.handle, lib().mf_convnet_debug_set(self.ctx.handle, buf, _ptr(x), x.shape[0], ctypes.c_void_p(s.cuda_stream)),
+              "mf_convnet_debug_set")
+        torch.cuda.synchronize()
+
     def debug_run(self, in_buf, x_nhwc, out_buf, out_shape):
         x = x_nhwc.contiguous().float().to(self.device)
         out = torch.empty(out_shape, dtype=torch.float32, device=self.device)

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py --steps 100 --warmup 5 2>&1 | tail -2 | tee gpurun_out/bench_n1.json
-timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_ref.json
+timeout -s KILL 600 python -m pytest tests/test_musetalk_gpu.py -m gpu -q -s -k small_config 2>&1 | grep -E "PSNR|passed|failed" | tee gpurun_out/pytest_muse.log
+timeout -s KILL 900 python scripts/time_musetalk.py 16 2>&1 | tail -4 | tee gpurun_out/time_muse.log
+timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 700 --csv --log-file gpurun_out/launches_muse.csv python scripts/time_musetalk.py 16 > gpurun_out/ncu_muse.log 2>&1
+tail -2 gpurun_out/ncu_muse.log
