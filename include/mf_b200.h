@@ -214,6 +214,18 @@ int mf_musetalk_forward(mf_ctx *ctx, const void *latents_f16, const void *whispe
 int mf_convnet_debug_set(mf_ctx *ctx, int buf, const float *in_f32, int B, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Whisper audio features for MuseTalk: replaces Audio2Feature.audio2feat -> Whisper.transcribe ->
+ * log_mel_spectrogram + AudioEncoder.forward(include_embeddings=True)
+ * (musetalk/whisper/audio2feature.py:99-112, whisper/transcribe.py:85-128, whisper/audio.py:92-125,
+ * whisper/model.py:143-171).  The program blob comes from mere_fusion_b200.whisper_pack.pack_whisper and
+ * is loaded with mf_wav2lip_load(max_batch = 1) into its own context.
+ *   audio   : device fp32 [n_samples], 16 kHz mono, one segment (n_samples / 160 <= 3000 frames)
+ *   out_f32 : device fp32 [T, n_layer + 1, n_state] = embeddings.transpose(0,2,1,3)[0][:T]
+ *             (T = int(n_frames / 2) is what audio2feat keeps)
+ * ------------------------------------------------------------------------------------------ */
+int mf_whisper_features(mf_ctx *ctx, const float *audio, int n_samples, float *out_f32, int T, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Paste-back (lipreal.py:207-214): out[i] = frames[idx_i] with faces[i] resized (cv2.resize, u8,
  * INTER_LINEAR, bit-exact) into the box (y1:y2, x1:x2).  coords order as wav2lip/genavatar.py:96.
  *   frames : device u8 [n_frames,H,W,3] the avatar's full frames, resident
@@ -223,6 +235,21 @@ int mf_convnet_debug_set(mf_ctx *ctx, int buf, const float *in_f32, int B, void 
  * ------------------------------------------------------------------------------------------ */
 int mf_paste_resize_u8(mf_ctx *ctx, const uint8_t *frames, int n_frames, int H, int W, const uint8_t *faces,
                        int S, int B, const int32_t *idx_bbox_host, uint8_t *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MuseTalk paste-back (musereal.py:229-250 -> musetalk/utils/blending.py:103-125 get_image_blending):
+ * faces[i] is resized (cv2.resize, bit-exact) into its bbox inside a copy of the body crop, then
+ *   body[ys:ye, xs:xe] = cv2.blendLinear(face_large, body_crop, m, 1 - m),  m = gray(mask) / 255
+ * bit-exact against OpenCV 4.x (cvtColor BGR2GRAY 15-bit fixed point, blendLinear fp32 without FMA).
+ *   rows_host     : HOST int32 [B,9] = (frame index, y1, y2, x1, x2 of the face bbox, ys, ye, xs, xe of
+ *                   the mask crop box); note musereal.py keeps bboxes as (x1, y1, x2, y2)
+ *   masks         : device u8, the avatar's masks packed back to back, each BGR [ye-ys, xe-xs, 3]
+ *                   (mask/*.png as cv2.imread returns them, musereal.py:176-179)
+ *   mask_off_host : HOST int64 [B] byte offset of each row's mask inside `masks`
+ * ------------------------------------------------------------------------------------------ */
+int mf_paste_blend_u8(mf_ctx *ctx, const uint8_t *frames, int n_frames, int H, int W, const uint8_t *faces,
+                      int S, int B, const int32_t *rows_host, const uint8_t *masks, size_t masks_nbytes,
+                      const int64_t *mask_off_host, uint8_t *out, void *stream);
 
 #ifdef __cplusplus
 }

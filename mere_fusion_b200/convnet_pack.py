@@ -13,6 +13,8 @@ from .ernerf_pack import build_blob
 CONV_MAX_TAPS = 52
 CONV_BK = 64
 ID_PROGRAM = 1
+ID_AUX = 2
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 ID_FIRST_TENSOR = 16
 SM_COUNT = 148
 
@@ -41,14 +43,22 @@ class ProgramBuilder:
         self.buffers = []
         self.ops = []
         self.tensors = {}
+        self.buffer_init = {}
+        self.aux = None                # optional int32 list stored as blob entry ID_AUX (program-kind specific)
         self.next_id = ID_FIRST_TENSOR
         self.nominal_batch = nominal_batch
         self.hdr = dict(in_face_buf=-1, in_mel_buf=-1, face_hw=0, mel_h=0, mel_w=0, out_hw=0)
         self.flops_per_sample = 0      # algorithmic: 2 * MACs of the original (unpadded) layers
 
-    def buffer(self, H, W, C):
+    def buffer(self, H, W, C, init=None):
+        """init: optional constant content [H, W, C] (fp32, rounded to bf16), replicated over the batch at load; such a
+        buffer must never be an op output"""
         assert C % 8 == 0
         self.buffers.append((H, W, C))
+        if init is not None:
+            init = np.asarray(init, np.float32)
+            assert init.shape == (H, W, C)
+            self.buffer_init[len(self.buffers) - 1] = self._tensor(f32_to_bf16_bits(init).tobytes())
         return len(self.buffers) - 1
 
     def _tensor(self, data):
@@ -72,7 +82,7 @@ class ProgramBuilder:
         return bn
 
     def _emit(self, in_buf, in_coff, cin_pad, out_buf, out_coff, Wm, taps, scale, shift, Mh, Mw, oy0, ox0, osy, osx,
-              isy, isx, res, relu, mode, cout, ups=0):
+              isy, isx, res, relu, mode, cout, ups=0, flags=0):
         ntaps = len(taps)
         assert ntaps <= CONV_MAX_TAPS
         if mode == 0 and cout % 16 != 0:              # the bf16 epilogue stores 16 channels at a time: pad with zero rows
@@ -99,14 +109,15 @@ class ProgramBuilder:
         dx = [t[1] for t in taps] + [0] * (CONV_MAX_TAPS - ntaps)
         rb, rc = res if res is not None else (-1, 0)
         rec = struct.pack("<28i", in_buf, in_coff, out_buf, out_coff, rb, rc, Mh, Mw, oy0, ox0, osy, osx, isy, isx,
-                          ntaps, cin_pad, kpad, cout, cout_pad, bn, int(relu), mode, w_id, s_id, h_id, 0, ups, 0)
+                          ntaps, cin_pad, kpad, cout, cout_pad, bn, int(relu), mode, w_id, s_id, h_id, 0, ups, flags)
         rec += struct.pack(f"<{CONV_MAX_TAPS}b", *dy) + struct.pack(f"<{CONV_MAX_TAPS}b", *dx)
         self.ops.append(rec)
         return len(self.ops) - 1
 
     def conv(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, bn=None, stride=1, padding=0, res=None,
-             relu=True, mode=0, ups=0, extra_shift=None, wscale=1.0):
-        """nn.Conv2d (+BatchNorm2d, +residual, +ReLU).  weight [Cout, Cin, kh, kw].  ups = 1: the conv runs on the
+             relu=True, mode=0, ups=0, extra_shift=None, wscale=1.0, res_after_act=False):
+        """nn.Conv2d (+BatchNorm2d, +residual, +activation).  weight [Cout, Cin, kh, kw].  relu: False / True / ACT_GELU.
+        res_after_act: out = act(conv) + res instead of act(conv + res).  ups = 1: the conv runs on the
         nearest-neighbour 2x upsampling of the input buffer (F.interpolate(scale_factor=2) folded into the gather).
         extra_shift: per-channel constant added after the conv (e.g. a time-embedding projection)."""
         weight = np.asarray(weight, np.float32)
@@ -127,12 +138,12 @@ class ProgramBuilder:
             shift = (shift + np.asarray(extra_shift, np.float32) * scale).astype(np.float32)
         self.flops_per_sample += 2 * cout * cin * kh * kw * Hout * Wout
         return self._emit(in_buf, in_coff, cin_pad, out_buf, out_coff, Wm.reshape(cout, -1), taps, scale, shift, Hout,
-                          Wout, 0, 0, 1, 1, sy, sx, res, relu, mode, cout, ups=ups)
+                          Wout, 0, 0, 1, 1, sy, sx, res, relu, mode, cout, ups=ups, flags=int(bool(res_after_act)))
 
-    def linear(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, res=None):
+    def linear(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, res=None, act=False):
         """nn.Linear on a token buffer = 1x1 conv.  weight [Cout, Cin]"""
         w = np.asarray(weight, np.float32)
-        return self.conv(in_buf, in_coff, out_buf, out_coff, w[:, :, None, None], bias, None, res=res, relu=False)
+        return self.conv(in_buf, in_coff, out_buf, out_coff, w[:, :, None, None], bias, None, res=res, relu=act)
 
     def _misc(self, kind, in_buf, out_buf, **f):
         v = dict(in_coff=0, out_coff=0, res_buf=-1, res_coff=0, Mh=0, Mw=0, ntaps=0, Cin=0, Kpad=0, relu=0, s_id=-1, h_id=-1)
@@ -216,9 +227,11 @@ class ProgramBuilder:
         h = self.hdr
         prog = struct.pack("<8i", len(self.buffers), len(self.ops), h["in_face_buf"], h["in_mel_buf"], h["face_hw"],
                            h["mel_h"], h["mel_w"], h["out_hw"])
-        for (H, W, C) in self.buffers:
-            prog += struct.pack("<4i", H, W, C, 0)
+        for i, (H, W, C) in enumerate(self.buffers):
+            prog += struct.pack("<4i", H, W, C, self.buffer_init.get(i, 0))
         prog += b"".join(self.ops)
         entries = {ID_PROGRAM: prog}
+        if self.aux is not None:
+            entries[ID_AUX] = np.asarray(self.aux, np.int32).tobytes()
         entries.update(self.tensors)
         return build_blob(entries, kind=2)

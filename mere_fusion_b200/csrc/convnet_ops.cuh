@@ -68,6 +68,96 @@ __global__ void k_prep_ctx(const PrepParams p) {
     const __half s = __hadd(x, __float2half_rn(pe));
     reinterpret_cast<__nv_bfloat16 *>(p.dst)[i] = __float2bfloat16_rn(__half2float(s));
 }
+// ---------------------------------------------------------------------------------------------------
+// Whisper front-end (musetalk/whisper/whisper/audio.py:92-125 log_mel_spectrogram + transcribe.py:99 pad_or_trim):
+// centred STFT (n_fft 400, hop 160, periodic Hann, reflect padding) as a direct 400-point DFT per frame (104 frames
+// for the 52-chunk live window: 33 MFLOP, not worth an FFT), power, 80-band mel filterbank, log10, and in a second
+// pass max(., global max - 8), (x + 4) / 4 and zero padding to the 3000-frame context.
+// ---------------------------------------------------------------------------------------------------
+struct WhisperPrep {
+    const float *audio;       // device fp32 [n_samples]
+    float *logspec;           // scratch fp32 [n_ctx_frames][80]
+    const float *filters;     // fp32 [80][201]
+    int *maxslot;             // float bits of (max log10 + 16); reset to 0 by k_whisper_gather at the end of the program
+    __nv_bfloat16 *melbuf;    // program input buffer [n_ctx_frames][1][80]
+    int n_samples, n_frames, n_ctx_frames;
+};
+#define WH_NFFT 400
+#define WH_HOP 160
+#define WH_BINS 201
+#define WH_MELS 80
+
+__global__ void __launch_bounds__(256) k_logmel_frames(const WhisperPrep p) {
+    __shared__ float xs[WH_NFFT], ct[WH_NFFT], st[WH_NFFT], pw[WH_BINS + 7];
+    __shared__ float red[8];
+    const int t = blockIdx.x;
+    for (int i = threadIdx.x; i < WH_NFFT; i += blockDim.x) {
+        float sn, cs;
+        sincospif((float)i / 200.0f, &sn, &cs);   // 2 pi i / 400
+        ct[i] = cs; st[i] = sn;
+        int src = t * WH_HOP + i - WH_NFFT / 2;   // torch.stft(center=True, pad_mode="reflect")
+        if (src < 0) src = -src;
+        if (src >= p.n_samples) src = 2 * (p.n_samples - 1) - src;
+        xs[i] = p.audio[src] * (0.5f - 0.5f * cs);  // torch.hann_window(400) (periodic)
+    }
+    __syncthreads();
+    if (threadIdx.x < WH_BINS) {
+        const int k = threadIdx.x;
+        float re = 0.f, im = 0.f;
+        int idx = 0;
+        for (int n = 0; n < WH_NFFT; n++) {
+            re = fmaf(xs[n], ct[idx], re);
+            im = fmaf(xs[n], st[idx], im);
+            idx += k;
+            if (idx >= WH_NFFT) idx -= WH_NFFT;
+        }
+        pw[k] = re * re + im * im;
+    }
+    __syncthreads();
+    float v = -1e30f;
+    if (threadIdx.x < WH_MELS) {
+        const float *f = p.filters + threadIdx.x * WH_BINS;
+        float acc = 0.f;
+        for (int k = 0; k < WH_BINS; k++) acc = fmaf(__ldg(f + k), pw[k], acc);
+        v = log10f(fmaxf(acc, 1e-10f));
+        p.logspec[t * WH_MELS + threadIdx.x] = v;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) v = fmaxf(v, red[w]);
+        atomicMax(p.maxslot, __float_as_int(v + 16.0f));   // v >= -10: positive floats order like ints
+    }
+}
+__global__ void __launch_bounds__(256) k_logmel_finish(const WhisperPrep p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_ctx_frames * WH_MELS) return;
+    const int t = i / WH_MELS;
+    float v = 0.f;                                         // pad_or_trim pads the finished log-mel with zeros
+    if (t < p.n_frames) {
+        const float mx = __int_as_float(*p.maxslot) - 16.0f;
+        v = (fmaxf(p.logspec[i], mx - 8.0f) + 4.0f) / 4.0f;
+    }
+    p.melbuf[i] = __float2bfloat16_rn(v);
+}
+// embeddings = stack([x0, block outputs...], axis=1) -> transpose(0,2,1,3) -> first T rows (model.py:155-167,
+// audio2feature.py:103-110): out fp32 [T][n_src][C]
+struct GatherParams {
+    const __nv_bfloat16 *src[8];
+    float *out;
+    int *maxslot;
+    int n_src, T, C;
+};
+__global__ void __launch_bounds__(256) k_whisper_gather(const GatherParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *p.maxslot = 0;
+    if (i >= p.T * p.n_src * p.C) return;
+    const int c = i % p.C, j = (i / p.C) % p.n_src, t = i / (p.C * p.n_src);
+    p.out[i] = __bfloat162float(p.src[j][(size_t)t * p.C + c]);
+}
+
 __global__ void k_f32_to_bf16(const PrepParams p) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t n = ((size_t)(uint32_t)p.a) | ((size_t)(uint32_t)p.b << 32);
@@ -80,34 +170,44 @@ __global__ void k_bf16_to_f32(const PrepParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// GroupNorm (+ SiLU): statistics by atomics into a per-op fp32 slot [B][G][2], then an element-wise pass
+// GroupNorm (+ SiLU).  Deterministic: every CTA of k_gn_stats reduces its pixel range in a fixed order and
+// writes one partial (sum, sum of squares) per group; the CTA that arrives last at a per-batch-item counter
+// adds the partials in index order and turns them into per-channel coefficients (a, b) with
+// y = x * a + b  (a = rstd * gamma, b = beta - mean * a).  k_gn_apply is then one fused multiply-add per
+// element.  Run-to-run results are bit-identical (no floating-point atomics anywhere).
 // ---------------------------------------------------------------------------------------------------
+#define GN_MAX_C 2560
 struct NormParams {
     const __nv_bfloat16 *in;
     __nv_bfloat16 *out;
     const float *gamma, *beta;
-    float *stats;  // [B][G][2] (sum, sum of squares), zeroed once per forward
+    float *coef;          // [B][C][2] per-channel (a, b); scratch shared by all GroupNorm ops (ops run in order)
+    float *partial;       // [B][gridDim.x][G][2] scratch
+    unsigned *counter;    // [B], zero between launches (the finalising CTA resets it)
     int npix, C, G, silu;
     float eps;
     int pix_per_cta;
     int in_stride, in_coff;  // GroupNorm input may be a channel range of a wider (concat) buffer; output is dense
 };
 
-// grid (ceil(npix / pix_per_cta), B).  A thread owns fixed 8-channel chunk columns (so the group of each of its 8
-// channels is fixed and sums stay in registers) and walks the CTA's pixel range with a stride.
+// grid (ceil(npix / pix_per_cta), B).  A thread owns fixed 8-channel chunk columns (so the sums of its channels
+// stay in registers) and walks the CTA's pixel range with a stride.
 __global__ void __launch_bounds__(256) k_gn_stats(const NormParams p) {
-    __shared__ float acc[64][2];
+    __shared__ float part[2][GN_MAX_C];
+    __shared__ float red[8][128];
+    __shared__ float mr[64][2];
+    __shared__ bool is_last;
     const int chunks = p.C >> 3;
     const int cpp = min(chunks, (int)blockDim.x);          // chunk columns handled per pass
     const int lanes = ((int)blockDim.x / cpp) * cpp;
-    for (int i = threadIdx.x; i < p.G * 2; i += blockDim.x) (&acc[0][0])[i] = 0.f;
-    __syncthreads();
+    const int pstep = lanes / cpp;
+    const int cpg = p.C / p.G;
+    const int b = blockIdx.y;
     if ((int)threadIdx.x < lanes) {
-        const int prow = threadIdx.x / cpp, pstep = lanes / cpp;
-        const int cpg = p.C / p.G;
+        const int prow = threadIdx.x / cpp;
         const int p0 = blockIdx.x * p.pix_per_cta, p1 = min(p.npix, p0 + p.pix_per_cta);
         for (int chunk = threadIdx.x % cpp; chunk < chunks; chunk += cpp) {
-            const __nv_bfloat16 *base = p.in + (size_t)blockIdx.y * p.npix * p.in_stride + p.in_coff + chunk * 8;
+            const __nv_bfloat16 *base = p.in + (size_t)b * p.npix * p.in_stride + p.in_coff + chunk * 8;
             float s[8], q[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) s[j] = q[j] = 0.f;
@@ -117,63 +217,99 @@ __global__ void __launch_bounds__(256) k_gn_stats(const NormParams p) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[j]);
-                    const float a = __bfloat162float(h.x), b = __bfloat162float(h.y);
+                    const float a = __bfloat162float(h.x), c = __bfloat162float(h.y);
                     s[2 * j] += a; q[2 * j] += a * a;
-                    s[2 * j + 1] += b; q[2 * j + 1] += b * b;
+                    s[2 * j + 1] += c; q[2 * j + 1] += c * c;
                 }
             }
+            // pstep > 1 only when all chunks fit one pass (C = cpp * 8), so prow * C + c < 2048
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const int g = (chunk * 8 + j) / cpg;
-                atomicAdd(&acc[g][0], s[j]);
-                atomicAdd(&acc[g][1], q[j]);
+                part[0][prow * p.C + chunk * 8 + j] = s[j];
+                part[1][prow * p.C + chunk * 8 + j] = q[j];
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < p.G * 2; i += blockDim.x)
-        atomicAdd(p.stats + (size_t)blockIdx.y * p.G * 2 + i, (&acc[0][0])[i]);
+    float *mine = p.partial + ((size_t)b * gridDim.x + blockIdx.x) * p.G * 2;
+    if ((int)threadIdx.x < 2 * p.G) {
+        const int g = threadIdx.x >> 1, st = threadIdx.x & 1;
+        float t = 0.f;
+        for (int r = 0; r < pstep; r++)
+            for (int c = 0; c < cpg; c++) t += part[st][r * p.C + g * cpg + c];
+        mine[threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(p.counter + b, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- finalise (one CTA per batch item): partials in index order -> mean / rstd -> per-channel coefficients
+    const int items = 2 * p.G, nl = min(8, (int)blockDim.x / items);   // G <= 64: nl >= 2
+    const int item = threadIdx.x % items, ln = threadIdx.x / items;
+    if (ln < nl) {
+        const volatile float *pp = p.partial + (size_t)b * gridDim.x * items;
+        float t = 0.f;
+        for (int c = ln; c < (int)gridDim.x; c += nl) t += pp[(size_t)c * items + item];
+        red[ln][item] = t;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < p.G) {
+        float s = 0.f, q = 0.f;
+        for (int l = 0; l < nl; l++) { s += red[l][2 * threadIdx.x]; q += red[l][2 * threadIdx.x + 1]; }
+        const float inv_n = 1.0f / ((float)p.npix * (float)cpg);
+        const float mean = s * inv_n;
+        const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+        mr[threadIdx.x][0] = mean;
+        mr[threadIdx.x][1] = rsqrtf(var + p.eps);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float a = mr[g][1] * __ldg(p.gamma + c);
+        reinterpret_cast<float2 *>(p.coef)[(size_t)b * p.C + c] = make_float2(a, __ldg(p.beta + c) - mr[g][0] * a);
+    }
+    if (threadIdx.x == 0) p.counter[b] = 0u;
 }
 
-// one thread per 8-channel chunk
+// grid (ceil(npix / pix_per_cta), B): same thread -> channel-chunk mapping as the statistics pass, so the 16
+// coefficients of a thread's chunk are loaded once and the pixel loop is pure streaming (16-B loads / stores)
 __global__ void __launch_bounds__(256) k_gn_apply(const NormParams p) {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const int chunks = p.C >> 3;
-    const size_t total = (size_t)p.npix * chunks;  // per batch item
-    if (i >= total) return;
+    const int cpp = min(chunks, (int)blockDim.x);
+    const int lanes = ((int)blockDim.x / cpp) * cpp;
+    if ((int)threadIdx.x >= lanes) return;
+    const int pstep = lanes / cpp, prow = threadIdx.x / cpp;
     const int b = blockIdx.y;
-    const int chunk = (int)(i % chunks);
-    const size_t off = ((size_t)b * p.npix + i / chunks) * p.C + chunk * 8;
-    const size_t ioff = ((size_t)b * p.npix + i / chunks) * p.in_stride + p.in_coff + chunk * 8;
-    const int cpg = p.C / p.G;
-    const float inv_n = 1.0f / ((float)p.npix * (float)cpg);
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.in + ioff));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    float x[8];
+    const int p0 = blockIdx.x * p.pix_per_cta, p1 = min(p.npix, p0 + p.pix_per_cta);
+    for (int chunk = threadIdx.x % cpp; chunk < chunks; chunk += cpp) {
+        float ca[8], cb[8];
+        const float4 *cf = reinterpret_cast<const float4 *>(p.coef + ((size_t)b * p.C + chunk * 8) * 2);
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[j]);
-        x[2 * j] = __bfloat162float(h.x);
-        x[2 * j + 1] = __bfloat162float(h.y);
-    }
-    uint32_t o[4];
-    float y[8];
+        for (int j = 0; j < 4; j++) {
+            const float4 t = cf[j];
+            ca[2 * j] = t.x; cb[2 * j] = t.y; ca[2 * j + 1] = t.z; cb[2 * j + 1] = t.w;
+        }
+        const __nv_bfloat16 *ib = p.in + (size_t)b * p.npix * p.in_stride + p.in_coff + chunk * 8;
+        __nv_bfloat16 *ob = p.out + (size_t)b * p.npix * p.C + chunk * 8;
+#pragma unroll 4
+        for (int px = p0 + prow; px < p1; px += pstep) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ib + (size_t)px * p.in_stride));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t o[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int c = chunk * 8 + j, g = c / cpg;
-        const float sum = p.stats[((size_t)b * p.G + g) * 2], sq = p.stats[((size_t)b * p.G + g) * 2 + 1];
-        const float mean = sum * inv_n;
-        const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
-        float t = (x[j] - mean) * rsqrtf(var + p.eps) * __ldg(p.gamma + c) + __ldg(p.beta + c);
-        if (p.silu) t = t / (1.0f + __expf(-t));
-        y[j] = t;
+            for (int j = 0; j < 4; j++) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[j]);
+                float y0 = fmaf(__bfloat162float(h.x), ca[2 * j], cb[2 * j]);
+                float y1 = fmaf(__bfloat162float(h.y), ca[2 * j + 1], cb[2 * j + 1]);
+                if (p.silu) { y0 = y0 / (1.0f + __expf(-y0)); y1 = y1 / (1.0f + __expf(-y1)); }
+                __nv_bfloat162 r = __floats2bfloat162_rn(y0, y1);
+                o[j] = *reinterpret_cast<uint32_t *>(&r);
+            }
+            *reinterpret_cast<uint4 *>(ob + (size_t)px * p.C) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-        o[j] = *reinterpret_cast<uint32_t *>(&h);
-    }
-    *reinterpret_cast<uint4 *>(p.out + off) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // LayerNorm over C per token: one warp per token (npix = total tokens over the batch), C <= 2048, C % 8 == 0

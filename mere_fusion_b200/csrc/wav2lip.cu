@@ -35,16 +35,17 @@
 #define CONV_THREADS 160
 #define CONV_MAX_TAPS 52
 #define A_STAGE_BYTES (CONV_BM * CONV_BK * 2)
+#define GN_MAX_CTAS (148 * 8)
 
 // blob entry ids (kind = 2)
-enum { W2L_ID_PROGRAM = 1, W2L_ID_FIRST_TENSOR = 16 };
+enum { W2L_ID_PROGRAM = 1, W2L_ID_AUX = 2, W2L_ID_FIRST_TENSOR = 16 };
 
 // ---- program records written by the packer (all int32, little endian) ----------------------
 struct W2LHeader {
     int32_t n_buffers, n_ops, in_face_buf, in_mel_buf, face_hw, mel_h, mel_w, out_hw;
 };
 struct W2LBuffer {
-    int32_t H, W, C, reserved;
+    int32_t H, W, C, init_entry;  // init_entry > 0: constant buffer, bf16 [H,W,C] blob entry copied into every batch slot at load
 };
 // kind 0 = conv (fields as named).  Other kinds reuse the integer fields (see the packer, convnet_pack.py):
 //   1 GroupNorm(+SiLU): in_buf -> out_buf, Cin = C, ntaps = groups, relu = silu, Kpad = eps (float bits),
@@ -57,7 +58,7 @@ struct W2LOp {
     int32_t in_buf, in_coff, out_buf, out_coff, res_buf, res_coff;
     int32_t Mh, Mw, oy0, ox0, osy, osx, isy, isx;
     int32_t ntaps, Cin, Kpad, Cout, Cout_pad, BN, relu, mode;
-    int32_t w_entry, scale_entry, shift_entry, kind, ups, reserved;
+    int32_t w_entry, scale_entry, shift_entry, kind, ups, flags;
     int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];
 };
 
@@ -74,6 +75,7 @@ struct ConvParams {
     int Mh, Mw, oy0, ox0, osy, osx, isy, isx;
     int ntaps, Cin, nkb, Cout, M, relu, mode;
     int ups;  // input is a nearest-neighbour 2^ups upsampling of the stored tensor (folded into the gather)
+    int flags;  // bit 0: residual is added AFTER the activation (Whisper: gelu(conv2(x)) + positional embedding)
     int dbg;  // timing experiments only (MF_CONV_DBG): 1 skip A loads, 2 skip B TMA, 4 skip MMA
     int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];
 };
@@ -130,6 +132,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // start address >> 4 [0,14), LBO >> 4 [16,30) (unused for swizzled K-major, 1), SBO >> 4 [32,46) = 1024 B between
@@ -249,6 +253,11 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++) f[j] = fmaf(__uint_as_float(v[j]), __ldg(p.scale + n0 + j), __ldg(p.shift + n0 + j));
+                const bool res_late = p.flags & 1;
+                if (res_late) {  // activation first (relu field: 0 none, 1 ReLU, 2 exact-erf GELU)
+#pragma unroll
+                    for (int j = 0; j < 16; j++) f[j] = p.relu == 1 ? fmaxf(f[j], 0.f) : (p.relu == 2 ? gelu_erf(f[j]) : f[j]);
+                }
                 if (p.res) {
                     const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + opix * p.res_stride + p.res_coff + n0);
                     const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
@@ -264,7 +273,10 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     float a = f[2 * j], c = f[2 * j + 1];
-                    if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+                    if (!res_late) {
+                        if (p.relu == 1) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+                        else if (p.relu == 2) { a = gelu_erf(a); c = gelu_erf(c); }
+                    }
                     __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
                     o[j] = *reinterpret_cast<uint32_t *>(&h);
                 }
@@ -357,7 +369,7 @@ static cudaError_t conv_desc_any(int BN, const ConvParams &p, LaunchDesc *d) {
 }
 
 // one kernel launch with its by-value parameter struct; io != 0 marks the launches that see caller pointers
-enum { IO_NONE = 0, IO_IN0 = 1, IO_IN1 = 2, IO_OUT = 3 };
+enum { IO_NONE = 0, IO_IN0 = 1, IO_IN1 = 2, IO_OUT = 3, IO_WH_FRAMES = 4, IO_WH_FINISH = 5, IO_WH_OUT = 6 };
 struct Launch {
     void *func = nullptr;
     dim3 grid, block;
@@ -380,8 +392,10 @@ struct Wav2LipState {
     const unsigned char *blob = nullptr;
     std::vector<unsigned char> *entry_table = nullptr;  // host copy of the blob's entry table
     std::vector<const mf_blob_entry *> ent_of_op_scale, ent_of_op_shift;
-    float *stats = nullptr;   // GroupNorm statistics, [n_gn_slots][max_batch][64][2]
-    int n_gn_slots = 0;
+    float *gn_coef = nullptr;       // GroupNorm scratch shared by all GN ops (ops run in order): [max_batch][GN_MAX_C][2]
+    float *gn_partial = nullptr;    // per-CTA partial sums [<= GN_MAX_CTAS + max_batch][64][2]
+    unsigned *gn_counter = nullptr; // [max_batch], zero between launches
+    bool has_gn = false;
     float *scores = nullptr;  // attention scratch: fp32 scores
     __nv_bfloat16 *probs = nullptr;
     size_t score_elems = 0;
@@ -394,6 +408,7 @@ struct Wav2LipState {
     // that see caller pointers are re-parameterised when those change
     struct Plan {
         int B = 0;
+        int n_samples = 0, T = 0;  // whisper plans
         std::vector<Launch> launches;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
@@ -404,7 +419,16 @@ struct Wav2LipState {
     };
     std::vector<Plan *> plans;
     bool use_graph = true;
+    // Whisper program (hdr.mel_w == -2): log-mel scratch, embedding buffers to gather, filterbank
+    float *wh_logspec = nullptr;
+    int *wh_maxslot = nullptr;
+    const float *wh_filters = nullptr;
+    std::vector<int> wh_embed_bufs;
 };
+
+// program kinds (hdr.mel_w): >= 0 wav2lip, -1 musetalk, -2 whisper encoder
+static bool is_musetalk(const Wav2LipState *s) { return s->hdr.mel_w == -1; }
+static bool is_whisper(const Wav2LipState *s) { return s->hdr.mel_w == -2; }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -432,7 +456,11 @@ void wav2lip_destroy(mf_ctx *ctx) {
         delete pl;
     }
     delete s->entry_table;
-    cudaFree(s->stats);
+    cudaFree(s->wh_logspec);
+    cudaFree(s->wh_maxslot);
+    cudaFree(s->gn_coef);
+    cudaFree(s->gn_partial);
+    cudaFree(s->gn_counter);
     cudaFree(s->scores);
     cudaFree(s->probs);
     if (s->ev[0]) { cudaEventDestroy(s->ev[0]); cudaEventDestroy(s->ev[1]); }
@@ -489,6 +517,13 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
         const size_t bytes = (size_t)max_batch * s->bufs[i].H * s->bufs[i].W * s->bufs[i].C * 2;
         MF_CUDA(ctx, cudaMalloc(&s->dbuf[i], bytes));
         MF_CUDA(ctx, cudaMemset(s->dbuf[i], 0, bytes));
+        if (s->bufs[i].init_entry > 0) {
+            const mf_blob_entry *ie = find(s->bufs[i].init_entry);
+            MF_REQUIRE(ctx, ie && ie->nbytes == bytes / max_batch, "buffer %d: init tensor does not match the buffer shape", i);
+            for (int b = 0; b < max_batch; b++)
+                MF_CUDA(ctx, cudaMemcpy(reinterpret_cast<unsigned char *>(s->dbuf[i]) + (size_t)b * ie->nbytes, base + ie->offset,
+                                        ie->nbytes, cudaMemcpyDeviceToDevice));
+        }
     }
     s->params.resize(s->hdr.n_ops);
     s->ent_of_op_scale.assign(s->hdr.n_ops, nullptr);
@@ -508,8 +543,8 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
                 s->ent_of_op_scale[i] = se;
                 s->ent_of_op_shift[i] = he;
                 if (o.kind == 1) {
-                    MF_REQUIRE(ctx, o.ntaps >= 1 && o.ntaps <= 64 && o.Cin % o.ntaps == 0, "op %d: bad group count", i);
-                    s->n_gn_slots = std::max(s->n_gn_slots, o.Mh + 1);
+                    MF_REQUIRE(ctx, o.ntaps >= 1 && o.ntaps <= 64 && o.Cin % o.ntaps == 0 && o.Cin <= GN_MAX_C, "op %d: bad group count", i);
+                    s->has_gn = true;
                 }
             } else if (o.kind == 3) {
                 MF_REQUIRE(ctx, okbuf(o.res_buf) && okbuf(o.Mh) && o.Cin % 8 == 0 && o.ntaps >= 1, "op %d: bad attention op", i);
@@ -558,7 +593,7 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
         p.scale = reinterpret_cast<const float *>(base + se->offset);
         p.shift = reinterpret_cast<const float *>(base + he->offset);
         p.Mh = o.Mh; p.Mw = o.Mw; p.oy0 = o.oy0; p.ox0 = o.ox0; p.osy = o.osy; p.osx = o.osx; p.isy = o.isy; p.isx = o.isx;
-        p.ntaps = o.ntaps; p.Cin = o.Cin; p.nkb = o.Kpad / CONV_BK; p.Cout = o.Cout; p.relu = o.relu; p.mode = o.mode;
+        p.ntaps = o.ntaps; p.Cin = o.Cin; p.nkb = o.Kpad / CONV_BK; p.Cout = o.Cout; p.relu = o.relu; p.mode = o.mode; p.flags = o.flags;
         memcpy(p.tap_dy, o.tap_dy, CONV_MAX_TAPS);
         memcpy(p.tap_dx, o.tap_dx, CONV_MAX_TAPS);
         // weights [Cout_pad][Kpad] bf16, K contiguous: TMA box = 64 (K) x BN rows, 128B swizzle
@@ -571,7 +606,33 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return mf_fail(ctx, MF_E_CUDA, "op %d: cuTensorMapEncodeTiled failed (%d)", i, (int)cr);
     }
-    if (s->n_gn_slots) MF_CUDA(ctx, cudaMalloc(&s->stats, (size_t)s->n_gn_slots * max_batch * 128 * sizeof(float)));
+    if (is_whisper(s)) {
+        const mf_blob_entry *ae = find(W2L_ID_AUX);
+        MF_REQUIRE(ctx, ae && ae->nbytes >= 12 && ae->nbytes % 4 == 0, "whisper program: aux entry missing");
+        std::vector<int32_t> aux(ae->nbytes / 4);
+        MF_CUDA(ctx, cudaMemcpy(aux.data(), base + ae->offset, ae->nbytes, cudaMemcpyDeviceToHost));
+        const int n = aux[0];
+        MF_REQUIRE(ctx, n >= 1 && n <= 8 && (size_t)n + 2 <= aux.size(), "whisper program: bad aux entry");
+        const W2LBuffer &mb = s->bufs[s->hdr.in_face_buf];
+        MF_REQUIRE(ctx, mb.C == WH_MELS && mb.W == 1, "whisper program: input buffer must be [frames,1,80]");
+        for (int i = 0; i < n; i++) {
+            MF_REQUIRE(ctx, okbuf(aux[1 + i]) && s->bufs[aux[1 + i]].W == 1 && s->bufs[aux[1 + i]].C == s->bufs[aux[1]].C,
+                       "whisper program: bad embedding buffer");
+            s->wh_embed_bufs.push_back(aux[1 + i]);
+        }
+        const mf_blob_entry *fe = find(aux[1 + n]);
+        MF_REQUIRE(ctx, fe && fe->nbytes == (size_t)WH_MELS * WH_BINS * 4, "whisper program: mel filterbank entry missing");
+        s->wh_filters = reinterpret_cast<const float *>(base + fe->offset);
+        MF_CUDA(ctx, cudaMalloc(&s->wh_logspec, (size_t)mb.H * WH_MELS * sizeof(float)));
+        MF_CUDA(ctx, cudaMalloc(&s->wh_maxslot, sizeof(int)));
+        MF_CUDA(ctx, cudaMemset(s->wh_maxslot, 0, sizeof(int)));
+    }
+    if (s->has_gn) {
+        MF_CUDA(ctx, cudaMalloc(&s->gn_coef, (size_t)max_batch * GN_MAX_C * 2 * sizeof(float)));
+        MF_CUDA(ctx, cudaMalloc(&s->gn_partial, (size_t)(GN_MAX_CTAS + 2 * max_batch) * 128 * sizeof(float)));
+        MF_CUDA(ctx, cudaMalloc(&s->gn_counter, (size_t)max_batch * sizeof(unsigned)));
+        MF_CUDA(ctx, cudaMemset(s->gn_counter, 0, (size_t)max_batch * sizeof(unsigned)));
+    }
     if (s->score_elems) {
         MF_CUDA(ctx, cudaMalloc(&s->scores, s->score_elems * sizeof(float)));
         MF_CUDA(ctx, cudaMalloc(&s->probs, s->score_elems * sizeof(__nv_bfloat16)));
@@ -607,18 +668,18 @@ static int add_op_launches(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vect
         n.gamma = reinterpret_cast<const float *>(s->blob + s->ent_of_op_scale[i]->offset);
         n.beta = reinterpret_cast<const float *>(s->blob + s->ent_of_op_shift[i]->offset);
         n.C = o.Cin; n.G = o.ntaps; n.silu = o.relu; n.eps = bits_to_float(o.Kpad);
-        n.stats = nullptr; n.pix_per_cta = 0; n.in_stride = ib.C; n.in_coff = o.in_coff;
+        n.coef = s->gn_coef; n.partial = s->gn_partial; n.counter = s->gn_counter;
+        n.pix_per_cta = 0; n.in_stride = ib.C; n.in_coff = o.in_coff;
         if (o.kind == 1) {
             n.npix = ib.H * ib.W;
-            n.stats = s->stats + (size_t)o.Mh * s->max_batch * 128;
-            const int target = std::max(1, (148 * 8) / B);
+            const int target = std::max(1, GN_MAX_CTAS / B);
             n.pix_per_cta = std::max(32, (n.npix + target - 1) / target);
             Launch a;
             a.func = (void *)k_gn_stats; a.grid = dim3((n.npix + n.pix_per_cta - 1) / n.pix_per_cta, B); a.block = dim3(256); a.op = -1;
             a.set(n);
             L.push_back(std::move(a));
             Launch b;
-            b.func = (void *)k_gn_apply; b.grid = dim3((unsigned)(((size_t)n.npix * (n.C / 8) + 255) / 256), B); b.block = dim3(256);
+            b.func = (void *)k_gn_apply; b.grid = dim3((n.npix + n.pix_per_cta - 1) / n.pix_per_cta, B); b.block = dim3(256);
             b.set(n);
             L.push_back(std::move(b));
         } else {
@@ -671,11 +732,34 @@ static int add_op_launches(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vect
 
 // program inputs: wav2lip (in_face_buf >= 0): in0 = faces u8, in1 = mel fp32;  musetalk (mel_h == 0 marks it):
 // in0 = latents fp16 NCHW [B,C,H,W], in1 = whisper fp16 [B,T,D]
-static bool is_musetalk(const Wav2LipState *s) { return s->hdr.mel_w < 0; }
 
 static int build_plan(mf_ctx *ctx, Wav2LipState *s, Wav2LipState::Plan *pl, int B) {
     std::vector<Launch> &L = pl->launches;
     pl->B = B;
+    if (is_whisper(s)) {
+        const W2LBuffer &mb = s->bufs[s->hdr.in_face_buf];
+        WhisperPrep w;
+        w.audio = nullptr; w.logspec = s->wh_logspec; w.filters = s->wh_filters; w.maxslot = s->wh_maxslot;
+        w.melbuf = s->dbuf[s->hdr.in_face_buf]; w.n_samples = 0; w.n_frames = 0; w.n_ctx_frames = mb.H;
+        Launch l0, l1;
+        l0.func = (void *)k_logmel_frames; l0.grid = dim3(1); l0.block = dim3(256); l0.io = IO_WH_FRAMES; l0.set(w);
+        l1.func = (void *)k_logmel_finish; l1.grid = dim3((mb.H * WH_MELS + 255) / 256); l1.block = dim3(256); l1.io = IO_WH_FINISH; l1.set(w);
+        L.push_back(std::move(l0));
+        L.push_back(std::move(l1));
+        for (int i = 0; i < s->hdr.n_ops; i++) {
+            int rc = add_op_launches(ctx, s, i, B, L);
+            if (rc) return rc;
+        }
+        GatherParams g;
+        memset(&g, 0, sizeof(g));
+        g.n_src = (int)s->wh_embed_bufs.size();
+        for (int i = 0; i < g.n_src; i++) g.src[i] = s->dbuf[s->wh_embed_bufs[i]];
+        g.C = s->bufs[s->wh_embed_bufs[0]].C; g.maxslot = s->wh_maxslot;
+        Launch lg;
+        lg.func = (void *)k_whisper_gather; lg.grid = dim3(1); lg.block = dim3(256); lg.io = IO_WH_OUT; lg.set(g);
+        L.push_back(std::move(lg));
+        return MF_OK;
+    }
     const W2LBuffer &b0 = s->bufs[s->hdr.in_face_buf], &b1 = s->bufs[s->hdr.in_mel_buf];
     {
         PrepParams p0, p1;
@@ -709,12 +793,20 @@ static void patch_io(Wav2LipState::Plan *pl, const void *in0, const void *in1, v
         if (l.io == IO_IN0) l.as<PrepParams>().src = in0;
         else if (l.io == IO_IN1) l.as<PrepParams>().src = in1;
         else if (l.io == IO_OUT) { l.as<ConvParams>().out = out_u8; l.as<ConvParams>().out_f32 = out_f32; }
+        else if (l.io == IO_WH_FRAMES || l.io == IO_WH_FINISH) {
+            WhisperPrep &w = l.as<WhisperPrep>();
+            w.audio = reinterpret_cast<const float *>(in0); w.n_samples = pl->n_samples; w.n_frames = pl->n_samples / WH_HOP;
+            if (l.io == IO_WH_FRAMES) l.grid = dim3(w.n_frames);
+        } else if (l.io == IO_WH_OUT) {
+            GatherParams &g = l.as<GatherParams>();
+            g.out = out_f32; g.T = pl->T;
+            l.grid = dim3((g.T * g.n_src * g.C + 255) / 256);
+        }
     }
     pl->in0 = in0; pl->in1 = in1; pl->out_u8 = out_u8; pl->out_f32 = out_f32;
 }
 
 static int launch_direct(mf_ctx *ctx, Wav2LipState *s, std::vector<Launch> &L, cudaStream_t st) {
-    if (s->stats) MF_CUDA(ctx, cudaMemsetAsync(s->stats, 0, (size_t)s->n_gn_slots * s->max_batch * 128 * sizeof(float), st));
     for (auto &l : L) {
         const bool prof = s->profile && l.op >= 0 && l.op == s->profile_op;
         if (prof) cudaEventRecord(s->ev[0], st);
@@ -726,7 +818,7 @@ static int launch_direct(mf_ctx *ctx, Wav2LipState *s, std::vector<Launch> &L, c
 }
 
 static int forward_common(mf_ctx *ctx, Wav2LipState *s, const void *in0, const void *in1, void *out_u8, float *out_f32,
-                          int B, cudaStream_t st) {
+                          int B, cudaStream_t st, int n_samples = 0, int T = 0) {
     Wav2LipState::Plan *pl = nullptr;
     for (auto q : s->plans) if (q->B == B) pl = q;
     if (!pl) {
@@ -735,19 +827,15 @@ static int forward_common(mf_ctx *ctx, Wav2LipState *s, const void *in0, const v
         int rc = build_plan(ctx, s, pl, B);
         if (rc) return rc;
     }
-    const bool io_changed = pl->in0 != in0 || pl->in1 != in1 || pl->out_u8 != out_u8 || pl->out_f32 != out_f32;
+    const bool io_changed = pl->in0 != in0 || pl->in1 != in1 || pl->out_u8 != out_u8 || pl->out_f32 != out_f32 ||
+                            pl->n_samples != n_samples || pl->T != T;
+    pl->n_samples = n_samples; pl->T = T;
     if (io_changed) patch_io(pl, in0, in1, out_u8, out_f32);
     s->last_launches = (int)pl->launches.size();
     if (!s->use_graph || s->profile) return launch_direct(ctx, s, pl->launches, st);
     if (!pl->exec) {
         MF_CUDA(ctx, cudaGraphCreate(&pl->graph, 0));
         cudaGraphNode_t prev = nullptr;
-        if (s->stats) {
-            cudaMemsetParams mp;
-            memset(&mp, 0, sizeof(mp));
-            mp.dst = s->stats; mp.value = 0; mp.elementSize = 4; mp.width = (size_t)s->n_gn_slots * s->max_batch * 128; mp.height = 1;
-            MF_CUDA(ctx, cudaGraphAddMemsetNode(&prev, pl->graph, nullptr, 0, &mp));
-        }
         pl->nodes.resize(pl->launches.size());
         for (size_t i = 0; i < pl->launches.size(); i++) {
             Launch &l = pl->launches[i];
@@ -798,6 +886,20 @@ extern "C" int mf_musetalk_forward(mf_ctx *ctx, const void *latents_f16, const v
                "the loaded program is not a musetalk program");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     return forward_common(ctx, s, latents_f16, whisper_f16, out_u8, out_f32, B, (cudaStream_t)stream);
+}
+
+extern "C" int mf_whisper_features(mf_ctx *ctx, const float *audio, int n_samples, float *out_f32, int T, void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    Wav2LipState *s = ctx->wav2lip;
+    if (!s) return mf_fail(ctx, MF_E_STATE, "mf_whisper_features: weights not loaded");
+    MF_REQUIRE(ctx, is_whisper(s), "the loaded program is not a whisper program");
+    MF_REQUIRE(ctx, audio && out_f32, "mf_whisper_features: null pointer");
+    const int n_ctx_frames = s->bufs[s->hdr.in_face_buf].H;
+    MF_REQUIRE(ctx, n_samples > WH_NFFT / 2 && n_samples / WH_HOP <= n_ctx_frames,
+               "mf_whisper_features: %d samples outside (200, %d] (one 30 s segment per call)", n_samples, n_ctx_frames * WH_HOP);
+    MF_REQUIRE(ctx, T >= 1 && T <= s->bufs[s->wh_embed_bufs[0]].H, "mf_whisper_features: T = %d rows out of range", T);
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    return forward_common(ctx, s, audio, nullptr, nullptr, out_f32, 1, (cudaStream_t)stream, n_samples, T);
 }
 
 // unit-test entry: run the loaded program on an fp32 NHWC tensor written into buffer `in_buf` (all of its channels)

@@ -50,3 +50,37 @@ def resize_linear_u8(img, dw, dh):
     r0, r1 = rows[sy0], rows[sy1]
     v = (((by0[:, None, None] * (r0 >> 4)) >> 16) + ((by1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
     return np.clip(v, 0, 255).astype(np.uint8)
+
+
+def blend_cv2(frame, face_u8, bbox, mask_bgr, crop_box):
+    """musereal.py:240-248 + musetalk/utils/blending.py:103-125 verbatim semantics (bbox = (x1, y1, x2, y2),
+    crop_box = (x_s, y_s, x_e, y_e)); OpenCV itself is the oracle"""
+    import cv2
+    body = copy.deepcopy(frame)
+    x, y, x1, y1 = bbox
+    face = cv2.resize(face_u8.astype(np.uint8), (x1 - x, y1 - y))
+    x_s, y_s, x_e, y_e = crop_box
+    face_large = copy.deepcopy(body[y_s:y_e, x_s:x_e])
+    face_large[y - y_s:y1 - y_s, x - x_s:x1 - x_s] = face
+    mask_image = cv2.cvtColor(mask_bgr, cv2.COLOR_BGR2GRAY)
+    mask_image = (mask_image / 255).astype(np.float32)
+    body[y_s:y_e, x_s:x_e] = cv2.blendLinear(face_large, body[y_s:y_e, x_s:x_e], mask_image, 1 - mask_image)
+    return body
+
+
+def blend_numpy(frame, face_u8, bbox, mask_bgr, crop_box):
+    """the arithmetic the CUDA kernel restates: 15-bit fixed-point BGR2GRAY, float64 `/ 255` narrowed to fp32, fp32 blend
+    with separately rounded products, round-half-even"""
+    body = frame.copy()
+    x, y, x1, y1 = bbox
+    x_s, y_s, x_e, y_e = crop_box
+    fl = body[y_s:y_e, x_s:x_e].copy()
+    fl[y - y_s:y1 - y_s, x - x_s:x1 - x_s] = resize_linear_u8(face_u8, x1 - x, y1 - y)
+    m = mask_bgr.astype(np.int64)
+    gray = (m[..., 0] * 3735 + m[..., 1] * 19235 + m[..., 2] * 9798 + (1 << 14)) >> 15
+    w1 = (gray / 255).astype(np.float32)[..., None]
+    w2 = np.float32(1) - w1
+    den = (w1 + w2) + np.float32(1e-5)
+    num = fl.astype(np.float32) * w1 + body[y_s:y_e, x_s:x_e].astype(np.float32) * w2
+    body[y_s:y_e, x_s:x_e] = np.clip(np.rint(num / den), 0, 255).astype(np.uint8)
+    return body

@@ -109,3 +109,58 @@ def wav2lip_inputs(B, mel_seed=3, face_seed=4, S=96):
     mel = np.clip(np.random.default_rng(mel_seed).standard_normal((B, 1, 80, 16)), -4, 4).astype(np.float32)
     faces = np.random.default_rng(face_seed).integers(0, 256, (B, S, S, 3), dtype=np.uint8)
     return mel, faces
+
+
+# ------------------------------------------------------------------------------------------------
+# Whisper encoder (tiny dims): seeded weights (./models/whisper/tiny.pt is external) and the synthetic audio of
+# SURVEY.md 8(d) config 1; golden features come from the vendored reference (tests/golden/make_whisper_golden.py)
+# ------------------------------------------------------------------------------------------------
+WHISPER_TINY = dict(n_mels=80, n_audio_ctx=1500, n_audio_state=384, n_audio_head=6, n_audio_layer=4)
+
+
+def whisper_encoder_shapes(d=WHISPER_TINY):
+    D, M = d["n_audio_state"], d["n_mels"]
+    s = {"conv1.weight": (D, M, 3), "conv1.bias": (D,), "conv2.weight": (D, D, 3), "conv2.bias": (D,),
+         "positional_embedding": (d["n_audio_ctx"], D)}
+    for i in range(d["n_audio_layer"]):
+        p = f"blocks.{i}."
+        for n in ("query", "key", "value", "out"):
+            s[p + f"attn.{n}.weight"] = (D, D)
+            if n != "key":
+                s[p + f"attn.{n}.bias"] = (D,)
+        for n in ("attn_ln", "mlp_ln"):
+            s[p + n + ".weight"] = (D,)
+            s[p + n + ".bias"] = (D,)
+        s[p + "mlp.0.weight"], s[p + "mlp.0.bias"] = (4 * D, D), (4 * D,)
+        s[p + "mlp.2.weight"], s[p + "mlp.2.bias"] = (D, 4 * D), (D,)
+    s["ln_post.weight"], s["ln_post.bias"] = (D,), (D,)
+    return s
+
+
+def seeded_whisper_state(seed=7, d=WHISPER_TINY):
+    """numpy arrays keyed like AudioEncoder.state_dict(); attention weights are scaled up a little so that the softmax
+    is not uniform (a uniform softmax would hide indexing mistakes)"""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for name, shp in whisper_encoder_shapes(d).items():
+        if name == "positional_embedding":
+            inc = np.log(10000) / (shp[1] // 2 - 1)
+            inv = np.exp(-inc * np.arange(shp[1] // 2))
+            t = np.arange(shp[0])[:, None] * inv[None, :]
+            sd[name] = np.concatenate([np.sin(t), np.cos(t)], axis=1).astype(np.float32)
+        elif name.endswith("ln.weight") or name == "ln_post.weight":
+            sd[name] = rng.uniform(0.7, 1.3, shp).astype(np.float32)
+        elif name.endswith(".bias"):
+            sd[name] = (rng.standard_normal(shp) * 0.1).astype(np.float32)
+        else:
+            fan_in = int(np.prod(shp[1:]))
+            gain = 2.5 if (".query." in name or ".key." in name) else 1.0
+            sd[name] = (rng.standard_normal(shp) * gain / np.sqrt(fan_in)).astype(np.float32)
+    return sd
+
+
+def synthetic_speech(n, seed=0):
+    """SURVEY.md 8(d) config 1 waveform: 0.3 sin(2 pi 220 t) (0.5 + 0.5 sin(2 pi 3 t)) + 0.01 N(0,1), 16 kHz"""
+    t = np.arange(n) / 16000.0
+    x = 0.3 * np.sin(2 * np.pi * 220 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 3 * t)) + 0.01 * np.random.default_rng(seed).standard_normal(n)
+    return x.astype(np.float32)

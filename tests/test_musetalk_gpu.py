@@ -136,10 +136,9 @@ def test_musetalk_small_config_vs_oracle():
     assert d.mean() < 3.0
     assert out.shape == (B, 256, 256, 3) and eng.last_launches > 400
     print(f"musetalk small config: PSNR vs oracle {p:.2f} dB, mean |du8| {d.mean():.3f}, launches {eng.last_launches}")
-    # graph replay with re-parameterised output nodes; GroupNorm statistics are accumulated with fp32 atomics, so
-    # two runs agree to rounding, not to the bit
+    # graph replay with re-parameterised output nodes: GroupNorm statistics are reduced in a fixed order (no
+    # floating-point atomics), so two runs agree to the bit
     out2 = torch.empty_like(out)
     eng.forward(torch.from_numpy(lat).cuda(), torch.from_numpy(wh).cuda(), out=out2)
     torch.cuda.synchronize()
-    d2 = (out.int() - out2.int()).abs().float()
-    assert float(d2.mean()) < 0.25 and psnr(out2.cpu().numpy(), out.cpu().numpy(), peak=255.0) > 45.0
+    assert torch.equal(out, out2)

@@ -14,6 +14,15 @@ from helpers import load_pose_fixture
 REF = "/root/reference"
 
 
+def _stub_module(name):
+    """an empty stand-in for an absent third-party module (with a spec, so importlib.util.find_spec keeps working)"""
+    import importlib.machinery
+    if name not in sys.modules:
+        m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+        sys.modules[name] = m
+
+
 def make_opt(**kw):
     o = types.SimpleNamespace(fps=50, l=10, m=8, r=10, batch_size=16, W=450, H=450, avatar_id="test", tts="none",
                               customopt=[], att=2, asr_model="cpierse/wav2vec2-large-xlsr-53-esperanto", exp_eye=True,
@@ -70,7 +79,7 @@ def test_mel_chunk_slicing_matches_reference_lipasr():
     from mere_fusion_b200 import audio_mel
     from mere_fusion_b200.plugin.lipasr import LipASR
     for name in ("librosa", "librosa.filters"):
-        sys.modules.setdefault(name, types.ModuleType(name))
+        _stub_module(name)
     sys.path.insert(0, REF)
     try:
         import lipasr as ref_lipasr
@@ -209,3 +218,139 @@ def test_pose_provider_matches_reference_golden():
     np.testing.assert_allclose(prov.poses[:296], pf["poses"][:296], rtol=0, atol=1e-6)
     np.testing.assert_allclose(prov.eye_area[:296], pf["eye"][:296], rtol=0, atol=1e-7)
     assert [mirror_index(3, i) for i in range(8)] == [0, 1, 2, 2, 1, 0, 0, 1]
+
+
+# ------------------------------------------------------------------------------------------------
+# MuseTalk plumbing (config 3 host side)
+# ------------------------------------------------------------------------------------------------
+class FakeAudioProcessor:
+    """stands in for Audio2Feature: feature row t = mean |audio| of 20 ms chunk t, recognisable per row"""
+
+    def audio2feat(self, audio):
+        n = int((len(audio) // 160) / 2)
+        rows = np.abs(np.asarray(audio[:n * 320], np.float32)).reshape(n, 320).mean(1)
+        return np.broadcast_to(rows[:, None, None], (n, 5, 384)).astype(np.float32).copy()
+
+    def feature2chunks(self, feature_array, fps, batch_size, audio_feat_length=[2, 2], start=0):
+        from mere_fusion_b200.whisper import feature2chunks
+        return feature2chunks(feature_array, fps, batch_size, audio_feat_length, start)
+
+
+def test_museasr_matches_reference_museasr():
+    """queue / window / slicing logic against the reference MuseASR itself (soundfile / ffmpeg stubbed, a fake audio processor
+    injected in both), when the reference tree is present"""
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present")
+    from mere_fusion_b200.plugin.museasr import MuseASR
+    for name in ("soundfile", "ffmpeg"):
+        _stub_module(name)
+    sys.path.insert(0, REF)
+    try:
+        import museasr as ref_museasr
+        from musetalk.whisper.audio2feature import Audio2Feature as RefA2F
+    finally:
+        sys.path.remove(REF)
+    ref_proc = RefA2F.__new__(RefA2F)
+    ref_proc.audio2feat = FakeAudioProcessor().audio2feat            # the model call only; slicing stays the reference's
+    opt = make_opt()
+    wav = clip_10s()
+    outs = []
+    for cls, proc in ((ref_museasr.MuseASR, ref_proc), (MuseASR, FakeAudioProcessor())):
+        asr = cls(opt, None, proc)
+        for i in range(100):
+            asr.put_audio_frame(wav[i * 320:(i + 1) * 320])
+        asr.warm_up()
+        chunks = []
+        for _ in range(4):
+            asr.run_step()
+            chunks.append(asr.feat_queue.get())
+        types_ = []
+        while True:
+            try:
+                types_.append(asr.output_queue.get(timeout=0.05)[1])
+            except Exception:
+                break
+        outs.append((chunks, types_, len(asr.frames)))
+    (c0, t0, n0), (c1, t1, n1) = outs
+    assert n0 == n1 == 20 and t0 == t1 and len(c0) == len(c1) == 4
+    for a, b in zip(c0, c1):
+        assert len(a) == len(b) == 16
+        for x, y in zip(a, b):
+            assert x.shape == (50, 384) and np.array_equal(x, y)
+
+
+def _fake_muse_avatar(n=12, H=512, W=512):
+    from mere_fusion_b200.plugin.musereal import MuseAvatar
+    rng = np.random.default_rng(11)
+    frames, coords, lat, masks, mcoords = [], [], [], [], []
+    for i in range(n):
+        f = rng.integers(0, 200, (H, W, 3), dtype=np.uint8)
+        f[0, 0] = i
+        frames.append(f)
+        x1, y1 = 150 + i, 140 + 2 * i
+        coords.append((x1, y1, x1 + 200 + i, y1 + 210))                         # (x1, y1, x2, y2), musereal.py:238
+        xs, ys, xe, ye = x1 - 40, y1 - 30, x1 + 200 + i + 35, y1 + 210 + 45      # crop box around the face box
+        mcoords.append((xs, ys, xe, ye))
+        m = np.zeros((ye - ys, xe - xs, 3), np.uint8)
+        yy, xx = np.mgrid[0:ye - ys, 0:xe - xs]
+        ramp = np.clip(255 - 3 * np.hypot(yy - (ye - ys) / 2, xx - (xe - xs) / 2) + 200, 0, 255).astype(np.uint8)   # soft-edged blob
+        m[:] = ramp[:, :, None]
+        masks.append(m)
+        lat.append((rng.standard_normal((1, 8, 32, 32)) * 0.18215 * 5).astype(np.float32))
+    return MuseAvatar(frames, coords, lat, masks, mcoords)
+
+
+def test_musereal_plumbing_host_blend():
+    """MuseReal plumbing with a host stand-in for the engine: frame count, 2 audio frames per video frame, mirror indices,
+    and the paste = get_image_blending (the reference's cv2 arithmetic) for speech frames"""
+    from mere_fusion_b200.plugin.musereal import MuseReal
+    from mere_fusion_b200.plugin.lipreal import mirror_index
+    from oracle.paste_oracle import blend_cv2
+    av = _fake_muse_avatar()
+
+    class HostMuseReal(MuseReal):
+        def infer_batch(self, whisper_chunks, index):
+            assert len(whisper_chunks) == self.batch_size and whisper_chunks[0].shape == (50, 384)
+            n = len(self.input_latent_list_cycle)
+            return [np.full((256, 256, 3), 10 * mirror_index(n, index + i) + 5, np.float32) for i in range(self.batch_size)]
+
+    real = HostMuseReal(make_opt(), engine=object(), audio_processor=FakeAudioProcessor(), avatar=av, paste="cpu")
+    wav = clip_10s()
+    for i in range(200):
+        real.put_audio_frame(wav[i * 320:(i + 1) * 320])
+    quit_event = threading.Event()
+    vt, at = FakeTrack(), FakeTrack()
+    th = threading.Thread(target=real.render, args=(quit_event, None, at, vt))
+    th.start()
+    t0 = time.time()
+    while len(vt._queue.items) < 112 and time.time() - t0 < 120:
+        time.sleep(0.05)
+    quit_event.set()
+    th.join(timeout=30)
+    nv, na = len(vt._queue.items), len(at._queue.items)
+    assert nv >= 112 and abs(na - 2 * nv) <= 2
+    speech = 0
+    for k in range(100):
+        fr = vt._queue.items[k].to_ndarray()
+        idx = mirror_index(12, k)
+        assert fr[0, 0, 0] == idx
+        face = np.full((256, 256, 3), 10 * idx + 5, np.uint8)
+        expect = blend_cv2(av.frame_list_cycle[idx], face, av.coord_list_cycle[idx], av.mask_list_cycle[idx], av.mask_coords_list_cycle[idx])
+        if np.array_equal(fr, expect):
+            speech += 1
+        else:
+            assert np.array_equal(fr, av.frame_list_cycle[idx])
+    assert speech == 95                                        # 5 idle frames from the silent warm-up, then speech
+
+
+def test_blend_restatement_equals_cv2():
+    from oracle.paste_oracle import blend_cv2, blend_numpy
+    av = _fake_muse_avatar(4)
+    rng = np.random.default_rng(5)
+    for i in range(4):
+        face = rng.integers(0, 256, (256, 256, 3), dtype=np.uint8)
+        mask = av.mask_list_cycle[i].copy()
+        mask[..., 1] = rng.integers(0, 256, mask.shape[:2], dtype=np.uint8)        # exercise the BGR2GRAY weights
+        a = blend_cv2(av.frame_list_cycle[i], face, av.coord_list_cycle[i], mask, av.mask_coords_list_cycle[i])
+        b = blend_numpy(av.frame_list_cycle[i], face, av.coord_list_cycle[i], mask, av.mask_coords_list_cycle[i])
+        assert np.array_equal(a, b)

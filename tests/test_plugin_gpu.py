@@ -110,3 +110,93 @@ def test_nerfreal_end_to_end():
     assert img.shape == (256, 256, 3) and img.dtype == np.uint8
     assert img[:20].mean() > 250 and 40 < img[100:200, 80:180].mean() < 230     # white background, a face in the middle
     assert not np.array_equal(v[10].to_ndarray(), v[20].to_ndarray())           # pose / audio advance
+
+
+def test_paste_blend_bit_exact_vs_cv2():
+    """mf_paste_blend_u8 == cv2.resize + get_image_blending (cvtColor + blendLinear) of the reference, bit for bit"""
+    from mere_fusion_b200._lib import Context, lib
+    from oracle.paste_oracle import blend_cv2
+    from test_plugin_cpu import _fake_muse_avatar
+    ctx = Context(0)
+    av = _fake_muse_avatar(6)
+    rng = np.random.default_rng(9)
+    n, H, W, S = 6, 512, 512, 256
+    B = 8
+    faces = rng.integers(0, 256, (B, S, S, 3), dtype=np.uint8)
+    masks, offs, off = [], [], 0
+    for i in range(n):
+        m = av.mask_list_cycle[i].copy()
+        if i % 2:
+            m[..., 1] = rng.integers(0, 256, m.shape[:2], dtype=np.uint8)
+            m[..., 2] = rng.integers(0, 256, m.shape[:2], dtype=np.uint8)
+        av.mask_list_cycle[i] = m
+        offs.append(off)
+        masks.append(m.reshape(-1))
+        off += m.size
+    rows = np.empty((B, 9), np.int32)
+    moff = np.empty(B, np.int64)
+    for i in range(B):
+        k = (i * 5) % n
+        x1, y1, x2, y2 = av.coord_list_cycle[k]
+        xs, ys, xe, ye = av.mask_coords_list_cycle[k]
+        rows[i] = (k, y1, y2, x1, x2, ys, ye, xs, xe)
+        moff[i] = offs[k]
+    d_frames = torch.from_numpy(np.stack(av.frame_list_cycle)).cuda()
+    d_faces = torch.from_numpy(faces).cuda()
+    d_masks = torch.from_numpy(np.concatenate(masks)).cuda()
+    out = torch.empty(B, H, W, 3, dtype=torch.uint8, device="cuda")
+
+    def call(r, mo, b):
+        return lib().mf_paste_blend_u8(ctx.handle, ctypes.c_void_p(d_frames.data_ptr()), n, H, W, ctypes.c_void_p(d_faces.data_ptr()), S, b,
+                                       r.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_void_p(d_masks.data_ptr()), d_masks.numel(),
+                                       mo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.c_void_p(out.data_ptr()), None)
+
+    assert call(rows, moff, B) == 0
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    for i in range(B):
+        k = int(rows[i, 0])
+        ref = blend_cv2(av.frame_list_cycle[k], faces[i], av.coord_list_cycle[k], av.mask_list_cycle[k], av.mask_coords_list_cycle[k])
+        assert np.array_equal(got[i], ref), f"item {i}: {(got[i] != ref).sum()} bytes differ"
+    bad = rows[:1].copy()
+    bad[0, 5] = bad[0, 1] + 1                                     # crop box starts below the face box
+    assert call(bad, moff[:1], 1) == -1
+    far = moff[:1].copy()
+    far[0] = d_masks.numel() - 10                                 # mask would run past the buffer
+    assert call(rows[:1], far, 1) == -1
+
+
+def test_musereal_end_to_end_gpu_blend_equals_cpu_blend():
+    """MuseReal on the GPU engines (Whisper features -> UNet + VAE -> blend) with fake tracks: the GPU blend path and the
+    reference's host cv2 path give identical frames; speech frames differ from the avatar frame inside the crop box only"""
+    from helpers import WHISPER_TINY, seeded_whisper_state
+    from mere_fusion_b200.musetalk import MuseTalkEngine
+    from mere_fusion_b200.plugin.musereal import MuseReal
+    from mere_fusion_b200.plugin.lipreal import mirror_index
+    from mere_fusion_b200.whisper import Audio2Feature, WhisperEngine
+    from oracle import musetalk_oracle as M
+    from test_plugin_cpu import _fake_muse_avatar
+    u, v = M.small_cfgs()
+    eng = MuseTalkEngine(M.seeded_state(M.unet_param_shapes(u), 5), M.seeded_state(M.vae_decoder_param_shapes(v), 6), u, v, max_batch=16)
+    a2f = Audio2Feature(engine=WhisperEngine(seeded_whisper_state(7), WHISPER_TINY))
+    wav = clip_10s()
+    chunks = [wav[i * 320:(i + 1) * 320] for i in range(200)]
+    outs = []
+    for mode in ("gpu", "cpu"):
+        real = MuseReal(make_opt(), engine=eng, audio_processor=a2f, avatar=_fake_muse_avatar(), paste=mode)
+        vfr, afr = _run(real, 64, chunks)
+        outs.append([f.to_ndarray().copy() for f in vfr[:64]])
+        assert abs(len(afr) - 2 * len(vfr)) <= 2
+    for k, (g, c) in enumerate(zip(*outs)):
+        assert np.array_equal(g, c), f"frame {k}"
+    av = _fake_muse_avatar()
+    changed = 0
+    for k in range(5, 64):
+        idx = mirror_index(12, k)
+        f, base = outs[0][k], av.frame_list_cycle[idx]
+        xs, ys, xe, ye = av.mask_coords_list_cycle[idx]
+        outside = np.ones((512, 512), bool)
+        outside[ys:ye, xs:xe] = False
+        assert np.array_equal(f[outside], base[outside])
+        changed += int(not np.array_equal(f, base))
+    assert changed >= 55
