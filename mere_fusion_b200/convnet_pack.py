@@ -49,6 +49,7 @@ class ProgramBuilder:
         self.nominal_batch = nominal_batch
         self.hdr = dict(in_face_buf=-1, in_mel_buf=-1, face_hw=0, mel_h=0, mel_w=0, out_hw=0)
         self.flops_per_sample = 0      # algorithmic: 2 * MACs of the original (unpadded) layers
+        self.decompose_ups = True      # run upsample + 3x3 conv as four 2x2-tap parity convs
 
     def buffer(self, H, W, C, init=None):
         """init: optional constant content [H, W, C] (fp32, rounded to bf16), replicated over the batch at load; such a
@@ -137,6 +138,24 @@ class ProgramBuilder:
         if extra_shift is not None:
             shift = (shift + np.asarray(extra_shift, np.float32) * scale).astype(np.float32)
         self.flops_per_sample += 2 * cout * cin * kh * kw * Hout * Wout
+        if ups == 1 and (kh, kw, sy, sx, py, px) == (3, 3, 1, 1, 1, 1) and cin % CONV_BK == 0 and mode == 0 and self.decompose_ups:
+            # nearest-2x upsampling followed by a 3x3 conv == four 2x2-tap convs on the LOW-resolution input, one per output
+            # parity class, with the taps that read the same input pixel summed (4/9 of the MACs, exact in real arithmetic):
+            #   parity 0: rows (2y-1, 2y, 2y+1) -> input rows (y-1, y, y): taps {-1: k0, 0: k1+k2};  parity 1: {0: k0+k1, +1: k2}
+            sets = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
+            w = weight * np.float32(wscale)
+            ids = []
+            for cy in (0, 1):
+                for cx in (0, 1):
+                    ptaps, cols = [], []
+                    for dy, kys in sets[cy]:
+                        for dx, kxs in sets[cx]:
+                            ptaps.append((dy, dx))
+                            cols.append(sum(w[:, :, ky, kx] for ky in kys for kx in kxs))          # [Cout, Cin]
+                    Wp = np.stack(cols, 1).reshape(cout, -1)
+                    ids.append(self._emit(in_buf, in_coff, cin_pad, out_buf, out_coff, Wp, ptaps, scale, shift, Hin >> 1, Win >> 1,
+                                          cy, cx, 2, 2, 1, 1, res, relu, mode, cout, ups=0, flags=int(bool(res_after_act))))
+            return ids
         return self._emit(in_buf, in_coff, cin_pad, out_buf, out_coff, Wm.reshape(cout, -1), taps, scale, shift, Hout,
                           Wout, 0, 0, 1, 1, sy, sx, res, relu, mode, cout, ups=ups, flags=int(bool(res_after_act)))
 

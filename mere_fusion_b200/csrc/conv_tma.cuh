@@ -1,0 +1,281 @@
+// conv_tma.cuh -- k_conv_tma: the stride-1 implicit-GEMM convolution (and every Linear / 1x1 conv) with BOTH operands
+// staged by TMA, persistent over a static tile schedule, accumulators double-buffered in TMEM.
+//
+//   D[128 px, BN ch] (fp32, TMEM) += A[128 px, 64 ch of one tap] (bf16) x B[BN, 64]^T (bf16),  UMMA 128 x BN x 16
+//
+//   * A: the activation tensor is NHWC bf16; one output tile is a TW x TH x TB box of output pixels (TW*TH*TB = 128, all
+//     powers of two, chosen per layer to minimise the tile count).  The A tile of filter tap (dy, dx) and channel block c
+//     is ONE 4-D TMA box {64 ch, TW, TH, TB} at (c, x0 + dx, y0 + dy, b0): its 128 rows of 128 bytes land in exactly the
+//     K-major SWIZZLE_128B layout tcgen05 reads; zero padding and ragged edges are TMA out-of-bounds zero fill.  No thread
+//     touches the operand bytes (the cp.async im2col producer of k_conv measured 2x slower than its own MMA pipe:
+//     profiles/r01_conv_bound_experiment.md).
+//   * B: weights [Cout_pad][K], K = tap * Cin + channel, 2-D TMA box {64, BN}.
+//   * roles (192 threads): warp 5 lane 0 = TMA producer, warp 4 lane 0 = MMA issuer (also owns the TMEM allocation),
+//     warps 0-3 = epilogue (TMEM lane == tile row == output pixel).  Rings: smem full/empty (TMA <-> MMA) and TMEM
+//     full/empty (MMA <-> epilogue, 2 accumulators): the epilogue of tile i overlaps the main loop of tile i + 1.
+//   * BN is a runtime value (any multiple of 16 up to 256): idesc, stage size and ring depth are computed per launch, so a
+//     320-channel layer runs as 2 x 160 instead of 5 x 64.
+//   * split-K for small-M layers (the 8x8 / 16x16 UNet levels): every split writes its fp32 partial tile to a workspace; the
+//     split that arrives last at the tile's counter adds all partials in split order (deterministic) and runs the epilogue.
+//
+// Eligibility (host, add_conv_tma): kind 0, bf16 output (mode 0), input stride 1, no folded upsampling, Cin % 64 == 0.
+#pragma once
+
+#define CT_THREADS 192
+#define CT_MAX_STAGES 8
+#define CT_SMEM_LIMIT (227 * 1024)
+#define CT_ACC_STRIDE 256  // TMEM columns between the two accumulators
+
+struct ConvTmaParams {
+    alignas(64) CUtensorMap amap;
+    alignas(64) CUtensorMap wmap;
+    void *out;
+    const __nv_bfloat16 *res;
+    const float *scale, *shift;
+    float *ws;            // split-K partial tiles [m_tile][n_tile][split][128][BN] fp32
+    unsigned *counters;   // [m_tile * n_tiles], zero between launches
+    int out_stride, out_coff, Hout, Wout;
+    int res_stride, res_coff;
+    int Mh, Mw, B, oy0, ox0, osy, osx;
+    int in_coff, ntaps, cblocks, nkb, Cout, relu, flags;
+    int BN, n_tiles, splits, stages;
+    int lTW, lTH, tiles_x, tiles_y, total_items;
+    int dbg;
+    int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];
+};
+
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+// scale/shift -> (+residual) -> activation -> bf16, 16 channels of one pixel
+__device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[16], int n0, size_t opix) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) f[j] = fmaf(f[j], __ldg(p.scale + n0 + j), __ldg(p.shift + n0 + j));
+    const bool res_late = p.flags & 1;
+    if (res_late) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) f[j] = p.relu == 1 ? fmaxf(f[j], 0.f) : (p.relu == 2 ? gelu_erf(f[j]) : f[j]);
+    }
+    if (p.res) {
+        const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + opix * p.res_stride + p.res_coff + n0);
+        const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&rw[j]);
+            f[2 * j] += __bfloat162float(h.x);
+            f[2 * j + 1] += __bfloat162float(h.y);
+        }
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        float a = f[2 * j], c = f[2 * j + 1];
+        if (!res_late) {
+            if (p.relu == 1) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+            else if (p.relu == 2) { a = gelu_erf(a); c = gelu_erf(c); }
+        }
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
+        o[j] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + opix * p.out_stride + p.out_coff + n0);
+    op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constant__ ConvTmaParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int ST = p.stages;
+    const uint32_t B_STAGE = (uint32_t)p.BN * 128u;
+    unsigned char *sA = smem;
+    unsigned char *sB = smem + ST * A_STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)ST * B_STAGE);
+    uint64_t *full = bars, *empty = bars + CT_MAX_STAGES, *tfull = bars + 2 * CT_MAX_STAGES, *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    volatile int *last_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < ST; i++) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int total = p.total_items;
+    const int per_tile = p.n_tiles * p.splits;
+
+    if (warp == 5) {
+        // =========================== TMA producer ==============================================
+        if (lane == 0) {
+            tma_prefetch_desc(&p.amap);
+            tma_prefetch_desc(&p.wmap);
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x) {
+                const int mt = item / per_tile, rem = item - mt * per_tile;
+                const int nt = rem / p.splits, sp = rem - nt * p.splits;
+                const int txi = mt % p.tiles_x, tyi = (mt / p.tiles_x) % p.tiles_y, tbi = mt / (p.tiles_x * p.tiles_y);
+                const int x0 = txi << p.lTW, y0 = tyi << p.lTH, b0 = tbi << (7 - p.lTW - p.lTH);
+                const int kb0 = (int)((long long)sp * p.nkb / p.splits), kb1 = (int)((long long)(sp + 1) * p.nkb / p.splits);
+                int tap = kb0 / p.cblocks, cb = kb0 - tap * p.cblocks;
+                for (int kb = kb0; kb < kb1; kb++, it++) {
+                    const int s = it % ST;
+                    if (it >= (uint32_t)ST) mbar_wait(&empty[s], ((it / ST) - 1) & 1);
+                    mbar_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE);
+                    if (!(p.dbg & 1))
+                        tma_load_4d(sA + s * A_STAGE_BYTES, &p.amap, p.in_coff + cb * CONV_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0, &full[s]);
+                    else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"((uint32_t)A_STAGE_BYTES) : "memory");
+                    if (!(p.dbg & 2))
+                        tma_load_2d(sB + (size_t)s * B_STAGE, &p.wmap, kb * CONV_BK, nt * p.BN, &full[s]);
+                    else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"(B_STAGE) : "memory");
+                    if (++cb == p.cblocks) { cb = 0; tap++; }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // =========================== MMA issuer ================================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(CONV_BM, p.BN);
+            uint32_t it = 0, n = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x, n++) {
+                const int rem = item % per_tile;
+                const int sp = rem % p.splits;
+                const int kb0 = (int)((long long)sp * p.nkb / p.splits), kb1 = (int)((long long)(sp + 1) * p.nkb / p.splits);
+                const uint32_t acc = n & 1;
+                if (n >= 2) mbar_wait(&tempty[acc], ((n >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * CT_ACC_STRIDE;
+                for (int kb = kb0; kb < kb1; kb++, it++) {
+                    const int s = it % ST;
+                    mbar_wait(&full[s], (it / ST) & 1);
+                    tc_fence_after();
+                    const uint64_t adesc = make_sdesc(smem_u32(sA + s * A_STAGE_BYTES));
+                    const uint64_t bdesc = make_sdesc(smem_u32(sB + (size_t)s * B_STAGE));
+#pragma unroll
+                    for (int k = 0; k < CONV_BK / 16; k++)
+                        if (!(p.dbg & 4)) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0) || (k != 0));
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        // =========================== epilogue: TMEM lane == tile row == output pixel ===========
+        const int r = threadIdx.x;  // 0..127
+        const int TWm = (1 << p.lTW) - 1, THm = (1 << p.lTH) - 1;
+        uint32_t n = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x, n++) {
+            const int mt = item / per_tile, rem = item - mt * per_tile;
+            const int nt = rem / p.splits, sp = rem - nt * p.splits;
+            const int txi = mt % p.tiles_x, tyi = (mt / p.tiles_x) % p.tiles_y, tbi = mt / (p.tiles_x * p.tiles_y);
+            const int mx = (txi << p.lTW) + (r & TWm), my = (tyi << p.lTH) + ((r >> p.lTW) & THm);
+            const int b = (tbi << (7 - p.lTW - p.lTH)) + (r >> (p.lTW + p.lTH));
+            const bool row_ok = mx < p.Mw && my < p.Mh && b < p.B;
+            const size_t opix = ((size_t)b * p.Hout + (p.oy0 + p.osy * my)) * p.Wout + (p.ox0 + p.osx * mx);
+            const uint32_t acc = n & 1;
+            mbar_wait(&tfull[acc], (n >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * CT_ACC_STRIDE + ((uint32_t)(warp * 32) << 16);
+            const int n_base = nt * p.BN;
+            if (p.splits == 1) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16_nowait(taddr + c0, v0);
+                    if (c0 + 16 < p.BN) tmem_ld16_nowait(taddr + c0 + 16, v1);
+                    tmem_ld_wait();
+                    if (!row_ok) continue;
+                    if (n_base + c0 < p.Cout) {
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v0[j]);
+                        ct_finish16(p, f, n_base + c0, opix);
+                    }
+                    if (c0 + 16 < p.BN && n_base + c0 + 16 < p.Cout) {
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v1[j]);
+                        ct_finish16(p, f, n_base + c0 + 16, opix);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty[acc]);
+            } else {
+                // split-K: dump the fp32 partial, then the last-arriving split reduces in split order
+                float *wtile = p.ws + ((size_t)(mt * p.n_tiles + nt) * p.splits) * (128 * (size_t)p.BN);
+                float *mine = wtile + ((size_t)sp * 128 + r) * p.BN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16_nowait(taddr + c0, v);
+                    tmem_ld_wait();
+                    float4 *d = reinterpret_cast<float4 *>(mine + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty[acc]);
+                __threadfence();
+                epi_bar_sync();
+                if (r == 0) *last_flag = atomicAdd(p.counters + mt * p.n_tiles + nt, 1u) == (unsigned)(p.splits - 1);
+                epi_bar_sync();
+                const bool last = *last_flag != 0;
+                epi_bar_sync();  // everyone has read the flag before the next item may overwrite it
+                if (last) {
+                    __threadfence();
+                    if (row_ok) {
+#pragma unroll 1
+                        for (int c0 = 0; c0 < p.BN && n_base + c0 < p.Cout; c0 += 16) {
+                            float f[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j++) f[j] = 0.f;
+                            for (int s2 = 0; s2 < p.splits; s2++) {
+                                const float4 *q = reinterpret_cast<const float4 *>(wtile + ((size_t)s2 * 128 + r) * p.BN + c0);
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const float4 t = __ldcg(q + j);
+                                    f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                                }
+                            }
+                            ct_finish16(p, f, n_base + c0, opix);
+                        }
+                    }
+                    if (r == 0) p.counters[mt * p.n_tiles + nt] = 0u;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 512);
+}

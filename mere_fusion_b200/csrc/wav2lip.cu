@@ -327,6 +327,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
     if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+#include "conv_tma.cuh"
+
 // =====================================================================================================
 // host: program loader, launch list, direct / CUDA-graph execution
 // =====================================================================================================
@@ -376,12 +378,30 @@ struct Launch {
     int smem = 0;
     int io = IO_NONE;
     int op = -1;  // program op index (conv ops: profiling hook), -1 for helper kernels
+    size_t ws_bytes = 0;  // k_conv_tma split-K: workspace / counter requirement (patched in by finish_launch_list)
+    int ws_counters = 0;
     std::vector<unsigned char> params;
     template <class T>
     void set(const T &p) { params.assign((const unsigned char *)&p, (const unsigned char *)&p + sizeof(T)); }
     template <class T>
     T &as() { return *reinterpret_cast<T *>(params.data()); }
 };
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
 
 struct Wav2LipState {
     W2LHeader hdr;
@@ -409,6 +429,8 @@ struct Wav2LipState {
     struct Plan {
         int B = 0;
         int n_samples = 0, T = 0;  // whisper plans
+        float *ws = nullptr;       // split-K workspace + tile counters of this plan's k_conv_tma launches
+        unsigned *counters = nullptr;
         std::vector<Launch> launches;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
@@ -424,27 +446,17 @@ struct Wav2LipState {
     int *wh_maxslot = nullptr;
     const float *wh_filters = nullptr;
     std::vector<int> wh_embed_bufs;
+    float *dbg_ws = nullptr;        // workspace of the ad-hoc launch lists of mf_convnet_debug_run
+    unsigned *dbg_counters = nullptr;
+    size_t dbg_ws_bytes = 0;
+    int dbg_n_counters = 0;
+    PFN_encodeTiled encode = nullptr;
+    int sm_count = 148;
 };
 
 // program kinds (hdr.mel_w): >= 0 wav2lip, -1 musetalk, -2 whisper encoder
 static bool is_musetalk(const Wav2LipState *s) { return s->hdr.mel_w == -1; }
 static bool is_whisper(const Wav2LipState *s) { return s->hdr.mel_w == -2; }
-
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-    }
-    return fn;
-}
 
 void wav2lip_destroy(mf_ctx *ctx) {
     Wav2LipState *s = ctx->wav2lip;
@@ -453,9 +465,13 @@ void wav2lip_destroy(mf_ctx *ctx) {
     for (auto pl : s->plans) {
         if (pl->exec) cudaGraphExecDestroy(pl->exec);
         if (pl->graph) cudaGraphDestroy(pl->graph);
+        cudaFree(pl->ws);
+        cudaFree(pl->counters);
         delete pl;
     }
     delete s->entry_table;
+    cudaFree(s->dbg_ws);
+    cudaFree(s->dbg_counters);
     cudaFree(s->wh_logspec);
     cudaFree(s->wh_maxslot);
     cudaFree(s->gn_coef);
@@ -511,6 +527,8 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
     s->bufs.assign(pb, pb + s->hdr.n_buffers);
     s->ops.assign(po, po + s->hdr.n_ops);
     s->max_batch = max_batch;
+    s->encode = encode;
+    s->sm_count = ctx->sm_count > 0 ? ctx->sm_count : 148;
     { const char *e = getenv("MF_NO_GRAPH"); s->use_graph = !(e && atoi(e)); }
     s->dbuf.assign(s->hdr.n_buffers, nullptr);
     for (int i = 0; i < s->hdr.n_buffers; i++) {
@@ -641,16 +659,144 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
     return MF_OK;
 }
 
+
+// ---- k_conv_tma planning: tile box, BN, split-K, ring depth -------------------------------------------
+static bool conv_tma_eligible(const W2LOp &o) {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("MF_CONV_TMA"); on = e ? atoi(e) : 1; }
+    return on && o.kind == 0 && o.mode == 0 && o.isy == 1 && o.isx == 1 && o.ups == 0 && o.Cin % CONV_BK == 0 &&
+           o.Kpad == o.ntaps * o.Cin;
+}
+
+static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<Launch> &L) {
+    const W2LOp &o = s->ops[i];
+    const ConvParams &cp = s->params[i];
+    ConvTmaParams p;
+    memset(&p, 0, sizeof(p));
+    // tile box TW x TH x TB = 128 output pixels: fewest tiles, ties to the widest rows
+    int best_tiles = 1 << 30, lTW = 0, lTH = 0;
+    for (int a = 7; a >= 0; a--)
+        for (int b = 7 - a; b >= 0; b--) {
+            const int TW = 1 << a, TH = 1 << b, TB = 1 << (7 - a - b);
+            if (TW > 256 || TH > 256 || TB > 256) continue;
+            const int t = ((o.Mw + TW - 1) / TW) * ((o.Mh + TH - 1) / TH) * ((B + TB - 1) / TB);
+            if (t < best_tiles) { best_tiles = t; lTW = a; lTH = b; }
+        }
+    const int TW = 1 << lTW, TH = 1 << lTH, TB = 1 << (7 - lTW - lTH);
+    p.lTW = lTW; p.lTH = lTH;
+    p.tiles_x = (o.Mw + TW - 1) / TW; p.tiles_y = (o.Mh + TH - 1) / TH;
+    const int m_tiles = best_tiles;
+    const int nkb = o.Kpad / CONV_BK;
+    // BN / split-K: minimise a simple cost model (cycles): per k-block max(MMA, smem traffic), per item a pipeline fill
+    const int sms = s->sm_count;
+    double best = 1e30;
+    int BN = 0, S = 1;
+    for (int nt = (o.Cout + 255) / 256; nt <= std::max(1, o.Cout / 32); nt++) {
+        const int bn = (((o.Cout + nt - 1) / nt) + 15) / 16 * 16;
+        if (bn > 256) continue;
+        const double kb_cost = std::max(2.0 * bn, 1.5 * (128 + bn));
+        static const int splits[] = {1, 2, 3, 4, 6, 8};
+        for (int sp : splits) {
+            if (sp > 1 && nkb / sp < 6) break;
+            const long items = (long)m_tiles * nt * sp;
+            const long waves = (items + sms - 1) / sms;
+            const double per_item = (double)((nkb + sp - 1) / sp) * kb_cost + 2500.0 + (sp > 1 ? 1500.0 + 12.0 * bn * sp : 0.0);
+            const double cost = (double)waves * per_item;
+            if (cost < best * 0.999) { best = cost; BN = bn; S = sp; }
+        }
+    }
+    MF_REQUIRE(ctx, BN >= 16, "op %d: no BN for the TMA conv", i);
+    p.BN = BN; p.n_tiles = (o.Cout + BN - 1) / BN; p.splits = S;
+    const int stage = A_STAGE_BYTES + BN * 128;
+    p.stages = std::min(CT_MAX_STAGES, (CT_SMEM_LIMIT - 1024 - 256) / stage);
+    p.total_items = m_tiles * p.n_tiles * S;
+    p.out = cp.out; p.res = cp.res; p.scale = cp.scale; p.shift = cp.shift;
+    p.out_stride = cp.out_stride; p.out_coff = cp.out_coff; p.Hout = cp.Hout; p.Wout = cp.Wout;
+    p.res_stride = cp.res_stride; p.res_coff = cp.res_coff;
+    p.Mh = o.Mh; p.Mw = o.Mw; p.B = B; p.oy0 = o.oy0; p.ox0 = o.ox0; p.osy = o.osy; p.osx = o.osx;
+    p.in_coff = o.in_coff; p.ntaps = o.ntaps; p.cblocks = o.Cin / CONV_BK; p.nkb = nkb; p.Cout = o.Cout; p.relu = o.relu; p.flags = o.flags;
+    memcpy(p.tap_dy, o.tap_dy, CONV_MAX_TAPS);
+    memcpy(p.tap_dx, o.tap_dx, CONV_MAX_TAPS);
+    { const char *e = getenv("MF_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
+    // activation map: NHWC bf16 buffer [max_batch][H][W][C]
+    const W2LBuffer &ib = s->bufs[o.in_buf];
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)ib.C, (cuuint64_t)ib.W, (cuuint64_t)ib.H, (cuuint64_t)s->max_batch};
+        cuuint64_t strides[3] = {(cuuint64_t)ib.C * 2, (cuuint64_t)ib.W * ib.C * 2, (cuuint64_t)ib.H * ib.W * ib.C * 2};
+        cuuint32_t box[4] = {CONV_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult cr = s->encode(&p.amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)s->dbuf[o.in_buf], dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return mf_fail(ctx, MF_E_CUDA, "op %d: activation cuTensorMapEncodeTiled failed (%d)", i, (int)cr);
+    }
+    {
+        const mf_blob_entry *we = nullptr;
+        const mf_blob_entry *ent = reinterpret_cast<const mf_blob_entry *>(s->entry_table->data() + sizeof(mf_blob_header));
+        const mf_blob_header *h = reinterpret_cast<const mf_blob_header *>(s->entry_table->data());
+        for (uint32_t e = 0; e < h->n_entries; e++) if ((int32_t)ent[e].id == o.w_entry) we = &ent[e];
+        MF_REQUIRE(ctx, we, "op %d: weight entry missing", i);
+        cuuint64_t dims[2] = {(cuuint64_t)o.Kpad, (cuuint64_t)o.Cout_pad};
+        cuuint64_t strides[1] = {(cuuint64_t)o.Kpad * 2};
+        cuuint32_t box[2] = {CONV_BK, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult cr = s->encode(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)(s->blob + we->offset), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return mf_fail(ctx, MF_E_CUDA, "op %d: weight cuTensorMapEncodeTiled failed (%d)", i, (int)cr);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        MF_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_LIMIT));
+        attr_set = true;
+    }
+    Launch l;
+    l.func = (void *)k_conv_tma; l.grid = dim3(std::min(p.total_items, sms)); l.block = dim3(CT_THREADS);
+    l.smem = p.stages * stage + 256 + 1024; l.op = i; l.io = IO_NONE;
+    if (S > 1) {
+        l.ws_bytes = (size_t)m_tiles * p.n_tiles * S * 128 * BN * sizeof(float);
+        l.ws_counters = m_tiles * p.n_tiles;
+    }
+    l.set(p);
+    L.push_back(std::move(l));
+    return MF_OK;
+}
+
+// allocate (or grow) the split-K workspace for a finished launch list and patch it into the k_conv_tma launches
+static int finish_launch_list(mf_ctx *ctx, std::vector<Launch> &L, float **ws, unsigned **counters, size_t *ws_bytes, int *n_counters) {
+    size_t need = 0;
+    int nc = 0;
+    for (auto &l : L) { need = std::max(need, l.ws_bytes); nc = std::max(nc, l.ws_counters); }
+    if (need > *ws_bytes) {
+        MF_CUDA(ctx, cudaDeviceSynchronize());
+        cudaFree(*ws);
+        *ws = nullptr;
+        MF_CUDA(ctx, cudaMalloc(ws, need));
+        *ws_bytes = need;
+    }
+    if (nc > *n_counters) {
+        MF_CUDA(ctx, cudaDeviceSynchronize());
+        cudaFree(*counters);
+        *counters = nullptr;
+        MF_CUDA(ctx, cudaMalloc(counters, (size_t)nc * sizeof(unsigned)));
+        MF_CUDA(ctx, cudaMemset(*counters, 0, (size_t)nc * sizeof(unsigned)));
+        *n_counters = nc;
+    }
+    for (auto &l : L)
+        if (l.func == (void *)k_conv_tma) { l.as<ConvTmaParams>().ws = *ws; l.as<ConvTmaParams>().counters = *counters; }
+    return MF_OK;
+}
+
 // ---- launch list -----------------------------------------------------------------------------------
 static int add_op_launches(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<Launch> &L) {
     const W2LOp &o = s->ops[i];
+    if (conv_tma_eligible(o)) return add_conv_tma(ctx, s, i, B, L);
     if (o.kind == 0) {
         ConvParams p = s->params[i];
         p.M = B * p.Mh * p.Mw;
         {
-            static int dbg = -1;
-            if (dbg < 0) { const char *e = getenv("MF_CONV_DBG"); dbg = e ? atoi(e) : 0; }
-            p.dbg = dbg;
+            const char *e = getenv("MF_CONV_DBG");  // timing experiments only (scripts/bench_conv.py)
+            p.dbg = e ? atoi(e) : 0;
         }
         LaunchDesc d;
         MF_CUDA(ctx, conv_desc_any(o.BN, p, &d));
@@ -826,6 +972,10 @@ static int forward_common(mf_ctx *ctx, Wav2LipState *s, const void *in0, const v
         s->plans.push_back(pl);
         int rc = build_plan(ctx, s, pl, B);
         if (rc) return rc;
+        size_t wsb = 0;
+        int ncnt = 0;
+        rc = finish_launch_list(ctx, pl->launches, &pl->ws, &pl->counters, &wsb, &ncnt);
+        if (rc) return rc;
     }
     const bool io_changed = pl->in0 != in0 || pl->in1 != in1 || pl->out_u8 != out_u8 || pl->out_f32 != out_f32 ||
                             pl->n_samples != n_samples || pl->T != T;
@@ -935,7 +1085,9 @@ extern "C" int mf_convnet_debug_run(mf_ctx *ctx, int in_buf, const float *in_f32
         l.set(p);
         L.push_back(std::move(l));
     }
-    int rc = launch_direct(ctx, s, L, st);
+    int rc = finish_launch_list(ctx, L, &s->dbg_ws, &s->dbg_counters, &s->dbg_ws_bytes, &s->dbg_n_counters);
+    if (rc) return rc;
+    rc = launch_direct(ctx, s, L, st);
     if (rc) return rc;
     s->last_launches = (int)L.size();
     return MF_OK;

@@ -47,13 +47,18 @@ def test_vs_oracle_batches(engine, B):
     p = psnr(f32.cpu().numpy(), pred)
     assert p >= PSNR_MIN_DB, f"PSNR {p:.2f} dB"
     assert np.abs(f32.cpu().numpy() - pred).max() <= MAX_ABS
-    # batch independence: frame i of a batch equals the same frame run alone (bit-exact: same tiles? no --
-    # tile membership changes with B, accumulation order does not) -> exact
+    # batch independence: frame i of a batch vs the same frame run alone.  The split-K factor of the small-M layers depends on
+    # the batch size, so the fp32 accumulation order (not the operands) differs: agreement to rounding; the SAME batch size
+    # is bit-reproducible (fixed split order, no floating-point atomics)
     if B == 5:
         f1 = torch.empty(1, 96, 96, 3, device="cuda")
         engine.forward(torch.from_numpy(mel[2:3]).cuda(), torch.from_numpy(faces[2:3]).cuda(), out_f32=f1)
         torch.cuda.synchronize()
-        assert torch.equal(f1[0], f32[2])
+        assert float((f1[0] - f32[2]).abs().max()) < 2e-2 and psnr(f1[0].cpu().numpy(), f32[2].cpu().numpy()) > 50.0
+        g32 = torch.empty_like(f32)
+        engine.forward(torch.from_numpy(mel).cuda(), torch.from_numpy(faces).cuda(), out_f32=g32)
+        torch.cuda.synchronize()
+        assert torch.equal(g32, f32)
 
 
 def test_errors(engine):
