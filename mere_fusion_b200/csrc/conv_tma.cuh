@@ -41,6 +41,8 @@ struct ConvTmaParams {
     int BN, n_tiles, splits, stages;
     int lTW, lTH, tiles_x, tiles_y, total_items;
     int dbg;
+    int mode;        // 0 bf16 NHWC; 1 wav2lip head (sigmoid, x255 truncated, u8 + fp32); 2 VAE head ((x/2+.5).clamp, round, BGR u8 + RGB fp32)
+    float *out_f32;  // modes 1 / 2
     int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];
 };
 
@@ -205,7 +207,28 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * CT_ACC_STRIDE + ((uint32_t)(warp * 32) << 16);
             const int n_base = nt * p.BN;
-            if (p.splits == 1) {
+            if (p.mode != 0) {
+                // output heads (Cout <= 16, one 16-column chunk; splits == 1)
+                uint32_t v[16];
+                tmem_ld16_nowait(taddr, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&tempty[acc]);
+                if (row_ok) {
+                    for (int j = 0; j < p.Cout; j++) {
+                        const float a = fmaf(__uint_as_float(v[j]), __ldg(p.scale + j), __ldg(p.shift + j));
+                        if (p.mode == 2) {   // musetalk/models/vae.py:102-107
+                            const float im = fminf(fmaxf(a * 0.5f + 0.5f, 0.f), 1.f);
+                            if (p.out_f32) p.out_f32[opix * p.Cout + j] = im;
+                            if (p.out) reinterpret_cast<uint8_t *>(p.out)[opix * p.Cout + (p.Cout - 1 - j)] = (uint8_t)rintf(im * 255.f);
+                        } else {             // wav2lip.py:83-85 sigmoid; lipreal.py:126,209 x255 truncated
+                            const float sg = 1.0f / (1.0f + __expf(-a));
+                            if (p.out_f32) p.out_f32[opix * p.Cout + j] = sg;
+                            if (p.out) reinterpret_cast<uint8_t *>(p.out)[opix * p.Cout + j] = (uint8_t)(sg * 255.f);
+                        }
+                    }
+                }
+            } else if (p.splits == 1) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < p.BN; c0 += 32) {
                     uint32_t v0[16], v1[16];

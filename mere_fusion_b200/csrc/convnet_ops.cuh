@@ -211,8 +211,7 @@ __global__ void __launch_bounds__(256) k_gn_stats(const NormParams p) {
             float s[8], q[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) s[j] = q[j] = 0.f;
-            for (int px = p0 + prow; px < p1; px += pstep) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)px * p.in_stride));
+            auto acc8 = [&](const uint4 &v) {
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -221,7 +220,16 @@ __global__ void __launch_bounds__(256) k_gn_stats(const NormParams p) {
                     s[2 * j] += a; q[2 * j] += a * a;
                     s[2 * j + 1] += c; q[2 * j + 1] += c * c;
                 }
+            };
+            int px = p0 + prow;
+            for (; px + 3 * pstep < p1; px += 4 * pstep) {   // 4 independent 16-B loads in flight per thread
+                const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)px * p.in_stride));
+                const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(px + pstep) * p.in_stride));
+                const uint4 v2 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(px + 2 * pstep) * p.in_stride));
+                const uint4 v3 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(px + 3 * pstep) * p.in_stride));
+                acc8(v0); acc8(v1); acc8(v2); acc8(v3);
             }
+            for (; px < p1; px += pstep) acc8(__ldg(reinterpret_cast<const uint4 *>(base + (size_t)px * p.in_stride)));
             // pstep > 1 only when all chunks fit one pass (C = cpp * 8), so prow * C + c < 2048
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -293,9 +301,7 @@ __global__ void __launch_bounds__(256) k_gn_apply(const NormParams p) {
         }
         const __nv_bfloat16 *ib = p.in + (size_t)b * p.npix * p.in_stride + p.in_coff + chunk * 8;
         __nv_bfloat16 *ob = p.out + (size_t)b * p.npix * p.C + chunk * 8;
-#pragma unroll 4
-        for (int px = p0 + prow; px < p1; px += pstep) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ib + (size_t)px * p.in_stride));
+        auto apply8 = [&](const uint4 &v, int px) {
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
             uint32_t o[4];
 #pragma unroll
@@ -308,7 +314,86 @@ __global__ void __launch_bounds__(256) k_gn_apply(const NormParams p) {
                 o[j] = *reinterpret_cast<uint32_t *>(&r);
             }
             *reinterpret_cast<uint4 *>(ob + (size_t)px * p.C) = make_uint4(o[0], o[1], o[2], o[3]);
+        };
+        int px = p0 + prow;
+        for (; px + 3 * pstep < p1; px += 4 * pstep) {
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(ib + (size_t)px * p.in_stride));
+            const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(ib + (size_t)(px + pstep) * p.in_stride));
+            const uint4 v2 = __ldg(reinterpret_cast<const uint4 *>(ib + (size_t)(px + 2 * pstep) * p.in_stride));
+            const uint4 v3 = __ldg(reinterpret_cast<const uint4 *>(ib + (size_t)(px + 3 * pstep) * p.in_stride));
+            apply8(v0, px); apply8(v1, px + pstep); apply8(v2, px + 2 * pstep); apply8(v3, px + 3 * pstep);
         }
+        for (; px < p1; px += pstep) apply8(__ldg(reinterpret_cast<const uint4 *>(ib + (size_t)px * p.in_stride)), px);
+    }
+}
+
+// small tensors (npix * C * 2 bytes <= ~200 KB per batch item, channels-per-group a multiple of 8): ONE kernel, one CTA per
+// batch item: the slab is staged in shared memory, statistics are reduced in a fixed order, and the normalised values are
+// written from shared memory -- one global read, one global write, one launch instead of two latency-bound ones.
+#define GN_SMALL_THREADS 1024
+__global__ void __launch_bounds__(GN_SMALL_THREADS) k_gn_small(const NormParams p) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    uint4 *slab = reinterpret_cast<uint4 *>(gsm);                                     // [npix][C / 8]
+    float2 *tsum = reinterpret_cast<float2 *>(gsm + (size_t)p.npix * p.C * 2);        // [threads]
+    float2 *mr = tsum + GN_SMALL_THREADS;                                             // [G] (mean, rstd)
+    const int chunks = p.C >> 3, cpg = p.C / p.G, cpgc = cpg >> 3;
+    const int cpp = min(chunks, (int)blockDim.x);
+    const int lanes = ((int)blockDim.x / cpp) * cpp, pstep = lanes / cpp;
+    const int b = blockIdx.x;
+    const int chunk0 = threadIdx.x % cpp, prow = threadIdx.x / cpp;
+    // chunks > blockDim never happens here (C <= 2560 -> 320 chunks <= 1024)
+    float s = 0.f, q = 0.f;
+    if ((int)threadIdx.x < lanes) {
+        const __nv_bfloat16 *base = p.in + (size_t)b * p.npix * p.in_stride + p.in_coff + chunk0 * 8;
+        for (int px = prow; px < p.npix; px += pstep) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)px * p.in_stride));
+            slab[px * chunks + chunk0] = v;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[j]);
+                const float a = __bfloat162float(h.x), c = __bfloat162float(h.y);
+                s += a + c; q += a * a + c * c;
+            }
+        }
+    }
+    tsum[threadIdx.x] = make_float2(s, q);
+    __syncthreads();
+    if ((int)threadIdx.x < p.G) {   // group g = chunk columns [g * cpgc, (g + 1) * cpgc) of every pixel row, fixed order
+        float S = 0.f, Q = 0.f;
+        for (int r = 0; r < pstep; r++)
+            for (int c = 0; c < cpgc; c++) {
+                const float2 t = tsum[r * cpp + threadIdx.x * cpgc + c];
+                S += t.x; Q += t.y;
+            }
+        const float inv_n = 1.0f / ((float)p.npix * (float)cpg);
+        const float mean = S * inv_n;
+        mr[threadIdx.x] = make_float2(mean, rsqrtf(fmaxf(Q * inv_n - mean * mean, 0.f) + p.eps));
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= lanes) return;
+    const float2 m = mr[chunk0 / cpgc];
+    float ca[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        ca[j] = m.y * __ldg(p.gamma + chunk0 * 8 + j);
+        cb[j] = __ldg(p.beta + chunk0 * 8 + j) - m.x * ca[j];
+    }
+    __nv_bfloat16 *ob = p.out + (size_t)b * p.npix * p.C + chunk0 * 8;
+    for (int px = prow; px < p.npix; px += pstep) {
+        const uint4 v = slab[px * chunks + chunk0];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[j]);
+            float y0 = fmaf(__bfloat162float(h.x), ca[2 * j], cb[2 * j]);
+            float y1 = fmaf(__bfloat162float(h.y), ca[2 * j + 1], cb[2 * j + 1]);
+            if (p.silu) { y0 = y0 / (1.0f + __expf(-y0)); y1 = y1 / (1.0f + __expf(-y1)); }
+            __nv_bfloat162 r = __floats2bfloat162_rn(y0, y1);
+            o[j] = *reinterpret_cast<uint32_t *>(&r);
+        }
+        *reinterpret_cast<uint4 *>(ob + (size_t)px * p.C) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -497,6 +582,140 @@ __global__ void __launch_bounds__(128) k_bgemm(const GemmParams p) {
                     if (col + 1 < p.N) C[1] = v1;
                 }
             }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused attention (flash-attention style, warp-level mma.sync bf16): O = softmax(Q K^T * scale) V per (batch, head) without
+// materialising the score matrix (the unfused path writes nq x nk fp32 scores + bf16 probabilities to HBM: 0.8 GB per
+// 32x32 self-attention at batch 16).  One CTA = 64 query rows (4 warps x 16), K / V streamed in 64-key tiles through
+// shared memory; online softmax in fp32; P is rounded to bf16 before P V exactly like the unfused path.
+// DP = head dim rounded up to 16 (zero padded in shared memory): 48 (dh 40), 64, 80, 160.
+// ---------------------------------------------------------------------------------------------------
+struct FlashParams {
+    const __nv_bfloat16 *Q, *K, *V;
+    __nv_bfloat16 *O;
+    int nq, nk, dh, heads;
+    int ldq, ldk, ldv, ldo;             // token strides (elements)
+    long long q_bs, k_bs, v_bs, o_bs;   // batch strides (elements); head h starts at column h * dh
+    float scale_log2;                   // scale * log2(e)
+};
+
+template <int DP>
+__global__ void __launch_bounds__(128) k_flash(const FlashParams p) {
+    constexpr int LD = DP + 8;          // +16 B per row: conflict-free ldmatrix
+    constexpr int KS = DP / 16;         // k-steps of Q K^T
+    constexpr int NT = DP / 8;          // n-tiles of P V
+    __shared__ __align__(16) __nv_bfloat16 sK[64][LD];
+    __shared__ __align__(16) __nv_bfloat16 sV[64][LD];
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const __nv_bfloat16 *Q = p.Q + b * p.q_bs + h * p.dh;
+    const __nv_bfloat16 *K = p.K + b * p.k_bs + h * p.dh;
+    const __nv_bfloat16 *V = p.V + b * p.v_bs + h * p.dh;
+    const int dchunks = DP / 8;
+    const int dvalid = p.dh / 8;        // dh % 8 == 0
+
+    // ---- Q fragments (A operand, 16 rows x DP) via shared memory (reuse sK as staging)
+    for (int c = threadIdx.x; c < 64 * dchunks; c += 128) {
+        const int r = c / dchunks, dc = c % dchunks;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (q0 + r < p.nq && dc < dvalid) v = __ldg(reinterpret_cast<const uint4 *>(Q + (size_t)(q0 + r) * p.ldq + dc * 8));
+        *reinterpret_cast<uint4 *>(&sK[r][dc * 8]) = v;
+    }
+    __syncthreads();
+    uint32_t qf[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+        const int qd = lane >> 3;
+        ldmatrix_x4(qf[ks], smem_u32(&sK[warp * 16 + (lane & 7) + 8 * (qd & 1)][ks * 16 + 8 * (qd >> 1)]));
+    }
+    __syncthreads();
+
+    float o[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;   // rows g and g + 8 of this warp's 16
+
+    for (int k0 = 0; k0 < p.nk; k0 += 64) {
+        for (int c = threadIdx.x; c < 64 * dchunks; c += 128) {
+            const int r = c / dchunks, dc = c % dchunks;
+            uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+            if (k0 + r < p.nk && dc < dvalid) {
+                kv = __ldg(reinterpret_cast<const uint4 *>(K + (size_t)(k0 + r) * p.ldk + dc * 8));
+                vv = __ldg(reinterpret_cast<const uint4 *>(V + (size_t)(k0 + r) * p.ldv + dc * 8));
+            }
+            *reinterpret_cast<uint4 *>(&sK[r][dc * 8]) = kv;
+            *reinterpret_cast<uint4 *>(&sV[r][dc * 8]) = vv;
+        }
+        __syncthreads();
+        // ---- S = Q K^T : 16 x 64 per warp
+        float sc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                uint32_t b0, b1;
+                const int l = lane & 15;
+                ldmatrix_x2(b0, b1, smem_u32(&sK[nt * 8 + (l & 7)][ks * 16 + 8 * (l >> 3)]));
+                mma_bf16(sc[nt], qf[ks], b0, b1);
+            }
+        // ---- online softmax (exp2 domain); keys beyond nk are masked
+        float mx0 = m0, mx1 = m1;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const int key = k0 + nt * 8 + 2 * t;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const bool ok = key + (e & 1) < p.nk;
+                sc[nt][e] = ok ? sc[nt][e] * p.scale_log2 : -1e30f;
+            }
+            mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float c0 = exp2f(m0 - mx0), c1 = exp2f(m1 - mx1);
+        m0 = mx0; m1 = mx1;
+        l0 *= c0; l1 *= c1;
+#pragma unroll
+        for (int i = 0; i < NT; i++) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+        uint32_t pf[4][4];   // P as A fragments: k-step j = keys [16 j, 16 j + 16)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const float e0 = exp2f(sc[nt][0] - m0), e1 = exp2f(sc[nt][1] - m0), e2 = exp2f(sc[nt][2] - m1), e3 = exp2f(sc[nt][3] - m1);
+            __nv_bfloat162 h01 = __floats2bfloat162_rn(e0, e1), h23 = __floats2bfloat162_rn(e2, e3);
+            // the row sums use the ROUNDED probabilities, so that sum(P) and P V see the same numbers
+            l0 += __bfloat162float(h01.x) + __bfloat162float(h01.y);
+            l1 += __bfloat162float(h23.x) + __bfloat162float(h23.y);
+            pf[nt >> 1][(nt & 1) * 2] = *reinterpret_cast<uint32_t *>(&h01);
+            pf[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t *>(&h23);
+        }
+        // ---- O += P V : V^T fragments via ldmatrix.trans
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+                uint32_t b0, b1;
+                ldmatrix_x2_trans(b0, b1, smem_u32(&sV[j * 16 + (lane & 15)][nt * 8]));
+                mma_bf16(o[nt], pf[j], b0, b1);
+            }
+        __syncthreads();
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    __nv_bfloat16 *O = p.O + b * p.o_bs + h * p.dh;
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+        const int d = nt * 8 + 2 * t;
+        if (d >= p.dh) continue;
+        if (r0 < p.nq) *reinterpret_cast<__nv_bfloat162 *>(O + (size_t)r0 * p.ldo + d) = __floats2bfloat162_rn(o[nt][0] * i0, o[nt][1] * i0);
+        if (r1 < p.nq) *reinterpret_cast<__nv_bfloat162 *>(O + (size_t)r1 * p.ldo + d) = __floats2bfloat162_rn(o[nt][2] * i1, o[nt][3] * i1);
+    }
 }
 
 // row softmax: S fp32 [rows][ld] (valid cols n) * scale -> P bf16 [rows][ld], padding columns zeroed.  One warp per row.

@@ -25,7 +25,8 @@ def _close(got, ref, atol=2e-2, rtol=2e-2):
     assert bool((err <= atol + rtol * ref.abs()).all()), f"max err {err.max().item():.4f} (|ref| max {ref.abs().max().item():.2f})"
 
 
-@pytest.mark.parametrize("C,H,silu,coff", [(320, 32, True, 0), (64, 16, False, 0), (2560, 4, True, 0), (128, 24, True, 64)])
+@pytest.mark.parametrize("C,H,silu,coff", [(320, 32, True, 0), (64, 16, False, 0), (2560, 4, True, 0), (128, 24, True, 64), (1280, 8, True, 0),
+                                            (1280, 4, False, 256), (2560, 8, True, 0), (128, 64, True, 0)])
 def test_group_norm(C, H, silu, coff):
     from mere_fusion_b200.convnet_pack import ProgramBuilder
     B = 3
@@ -63,7 +64,8 @@ def test_layer_norm_and_geglu():
     _close(got, h * F.gelu(gate))
 
 
-@pytest.mark.parametrize("heads,dh,H,nk", [(8, 40, 32, None), (8, 160, 8, None), (1, 512, 32, None), (8, 40, 16, 50), (8, 8, 8, 50)])
+@pytest.mark.parametrize("heads,dh,H,nk", [(8, 40, 32, None), (8, 160, 8, None), (1, 512, 32, None), (8, 40, 16, 50), (8, 8, 8, 50),
+                                            (6, 64, 10, None), (8, 80, 16, None), (8, 160, 4, 50), (2, 80, 9, 130)])
 def test_attention(heads, dh, H, nk):
     """self-attention (q, k, v = channel ranges of one qkv buffer) and cross-attention over nk context tokens"""
     from mere_fusion_b200.convnet_pack import ProgramBuilder
