@@ -210,6 +210,101 @@ def wav2lip_leg(args, dev, local, rank, world, flush, timed_fn, pk):
                          "ms_per_launch": m * 1e3, "traffic": None, "peak_source": pk["src"] + " burst"}}
 
 
+def musetalk_leg(args, dev, local, rank, world, flush, timed_fn, pk):
+    """BASELINE configs[2]-shaped leg: MuseTalk v1 architecture (SD-1.x UNet + sd-vae-ft-mse decoder, random weights), 16
+    frames per step: 52-chunk audio window -> Whisper-tiny features (log-mel + encoder on the GPU) -> [16,50,384] chunks ->
+    PE + UNet (t = 0) + VAE decode -> cv2-exact resize + mask blend into the 512x512 avatar frames."""
+    import ctypes
+    import struct
+    import torch
+    from helpers import WHISPER_TINY, seeded_whisper_state, synthetic_speech
+    from oracle import musetalk_oracle as M          # parameter shapes + seeded weights only (no oracle compute on this path)
+    from mere_fusion_b200._lib import check, lib
+    from mere_fusion_b200.musetalk import MuseTalkEngine
+    from mere_fusion_b200.whisper import Audio2Feature, WhisperEngine
+    B = 16
+    u, v = M.UNET_CFG, M.VAE_CFG
+    eng = MuseTalkEngine(M.seeded_state(M.unet_param_shapes(u), 5), M.seeded_state(M.vae_decoder_param_shapes(v), 6), u, v,
+                         max_batch=B, device=local)
+    a2f = Audio2Feature(engine=WhisperEngine(seeded_whisper_state(7), WHISPER_TINY, device=local))
+    rng = np.random.default_rng(11 + rank)
+    n_av = 12
+    frames = torch.from_numpy(rng.integers(0, 200, (n_av, H, W, 3), dtype=np.uint8)).to(dev)
+    lat_all = torch.from_numpy((rng.standard_normal((n_av, 8, 32, 32)) * 0.18215 * 5).astype(np.float16)).to(dev)
+    boxes, crops, moffs, masks, off = [], [], [], [], 0
+    for i in range(n_av):
+        x1, y1 = 150 + i, 140 + 2 * i
+        x2, y2 = x1 + 200 + i, y1 + 210
+        xs, ys, xe, ye = x1 - 40, y1 - 30, x2 + 35, y2 + 45
+        yy, xx = np.mgrid[0:ye - ys, 0:xe - xs]
+        ramp = np.clip(255 - 3 * np.hypot(yy - (ye - ys) / 2, xx - (xe - xs) / 2) + 200, 0, 255).astype(np.uint8)
+        m = np.repeat(ramp[:, :, None], 3, axis=2)
+        boxes.append((y1, y2, x1, x2)); crops.append((ys, ye, xs, xe)); moffs.append(off)
+        masks.append(m.reshape(-1)); off += m.size
+    masks_d = torch.from_numpy(np.concatenate(masks)).to(dev)
+    audio = [torch.from_numpy(synthetic_speech(52 * 320, 100 + rank * 8 + i)) for i in range(8)]
+    audio_dev = [a.to(dev) for a in audio]
+    audio_pin = [a.pin_memory() for a in audio]
+    audio_stage = torch.empty_like(audio_dev[0])
+    sel = torch.empty((B, 8, 32, 32), dtype=torch.float16, device=dev)
+    pred = torch.empty((B, 256, 256, 3), dtype=torch.uint8, device=dev)
+    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+    out_pin = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
+    rows_all = []
+    for k in range(8):
+        idxs = [(k * B + i) % n_av for i in range(B)]
+        rows = np.array([(j,) + boxes[j] + crops[j] for j in idxs], np.int32)
+        rows_all.append((torch.as_tensor(idxs, device=dev), rows, np.array([moffs[j] for j in idxs], np.int64)))
+    h = eng.ctx.handle
+
+    def core(k, audio_t):
+        idx_t, rows, mo = rows_all[k % 8]
+        chunks = a2f.audio2chunks_device(None, fps=25.0, batch_size=B, start=5.0, audio_dev=audio_t)   # MuseASR.run_step (museasr.py:26-27)
+        torch.index_select(lat_all, 0, idx_t, out=sel)
+        eng.forward(sel, chunks, out=pred)
+        st = torch.cuda.current_stream(dev)
+        check(h, lib().mf_paste_blend_u8(h, ctypes.c_void_p(frames.data_ptr()), n_av, H, W, ctypes.c_void_p(pred.data_ptr()), 256, B,
+                                         rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_void_p(masks_d.data_ptr()),
+                                         masks_d.numel(), mo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                         ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(st.cuda_stream)), "mf_paste_blend_u8")
+
+    def step(k):
+        core(k, audio_dev[k % 8])
+
+    def step_host(k):
+        audio_stage.copy_(audio_pin[k % 8], non_blocking=True)
+        core(k, audio_stage)
+        out_pin.copy_(out, non_blocking=True)
+
+    K = max(10, args.steps // 10)
+    tot, per, _ = timed_fn(step, K, args.warmup)
+    e2e, _, _ = timed_fn(step_host, K, args.warmup)
+    launches = eng.last_launches + a2f.engine.last_launches + 1
+    # dominant kernel by time share: the 128 -> 128 3x3 convs of the last VAE up block at 256x256 (k_conv_tma), one of them timed live
+    op = next(i for i, rec in enumerate(eng.op_records) if struct.unpack("<28i", rec[:112])[14:18] == (9, 128, 1152, 128))
+    eng.profile_op(op)
+    ms = []
+    for k in range(5):
+        flush.fill_(k)
+        step(k)
+        ms.append(eng.last_op_ms())
+    eng.profile_op(-1)
+    flop = 2 * 128 * 128 * 9 * 256 * 256 * B
+    m = float(np.mean(ms)) * 1e-3
+    fl_step = eng.flops_per_frame * B + a2f.engine.flops_per_call
+    return {"workload": "musetalk_v1 (SD-1.x UNet t=0 + sd-vae-ft-mse decoder) 256x256 B16 + whisper-tiny features per batch -> blend into 512x512 "
+                        "(BASELINE configs[2]; random weights: parity unpinned, DESIGN.md 6)",
+            "value": world * K * B / (tot / 1e3), "unit": "frames/s", "ms_per_step": tot / K, "frames_per_step": B,
+            "e2e": {"value": world * K * B / (e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(audio_pin[0].numel() * 4),
+                    "d2h_bytes_per_step": int(out_pin.numel())},
+            "gpu_launches_per_step": int(launches), "dtype": "bf16",
+            "algorithmic_tflops": fl_step / (tot / K * 1e-3) / 1e12,
+            "gflop_per_frame": {"unet": eng.unet_flops / 1e9, "vae_decoder": eng.vae_flops / 1e9, "whisper_per_batch": a2f.engine.flops_per_call / 1e9},
+            "roofline": {"kernel": "k_conv_tma (vae decoder up_blocks.3 resnet conv 3x3 128->128 @256x256, B=16)", "bound": "tensor",
+                         "achieved": flop / m / 1e12, "peak": pk["tf"], "unit": "TFLOP/s", "frac": flop / m / 1e12 / pk["tf"],
+                         "ms_per_launch": m * 1e3, "traffic": None, "peak_source": pk["src"] + " burst"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -219,6 +314,7 @@ def main():
     ap.add_argument("--workload", default="ernerf")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wav2lip", action="store_true")
+    ap.add_argument("--no-musetalk", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -335,6 +431,8 @@ def main():
     heads = {}
     if not args.no_wav2lip:
         heads["wav2lip"] = wav2lip_leg(args, dev, local, rank, world, flush, timed, peaks())
+    if not args.no_musetalk:
+        heads["musetalk"] = musetalk_leg(args, dev, local, rank, world, flush, timed, peaks())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

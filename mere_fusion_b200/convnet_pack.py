@@ -103,12 +103,18 @@ class ProgramBuilder:
         sh = np.zeros(cout_pad, np.float32)
         sc[:cout] = scale
         sh[:cout] = shift
-        w_id = self._tensor(f32_to_bf16_bits(Wp).tobytes())
+        # stored re-tiled as [Cout_pad / 16][Kpad / 64][16][64]: every 16-row x 64-k piece of a B tile is one contiguous 2 KB
+        # run in HBM (a row-major [Cout][K] matrix would be fetched as 128-byte pieces 2 * K bytes apart, one DRAM page each:
+        # the weight-streaming 4x4 / 8x8 UNet layers measured 1.2 TB/s that way)
+        Wt = Wp.reshape(cout_pad // 16, 16, kpad // CONV_BK, CONV_BK).transpose(0, 2, 1, 3)
+        w_id = self._tensor(f32_to_bf16_bits(np.ascontiguousarray(Wt)).tobytes())
         s_id = self._tensor(sc.tobytes())
         h_id = self._tensor(sh.tobytes())
         dy = [t[0] for t in taps] + [0] * (CONV_MAX_TAPS - ntaps)
         dx = [t[1] for t in taps] + [0] * (CONV_MAX_TAPS - ntaps)
         rb, rc = res if res is not None else (-1, 0)
+        if np.all(sc[:cout] == 1.0):
+            flags |= 2                                  # unit scale: the epilogue adds the bias only
         rec = struct.pack("<28i", in_buf, in_coff, out_buf, out_coff, rb, rc, Mh, Mw, oy0, ox0, osy, osx, isy, isx,
                           ntaps, cin_pad, kpad, cout, cout_pad, bn, int(relu), mode, w_id, s_id, h_id, 0, ups, flags)
         rec += struct.pack(f"<{CONV_MAX_TAPS}b", *dy) + struct.pack(f"<{CONV_MAX_TAPS}b", *dx)

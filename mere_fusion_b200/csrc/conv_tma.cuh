@@ -9,19 +9,20 @@
 //     K-major SWIZZLE_128B layout tcgen05 reads; zero padding and ragged edges are TMA out-of-bounds zero fill.  No thread
 //     touches the operand bytes (the cp.async im2col producer of k_conv measured 2x slower than its own MMA pipe:
 //     profiles/r01_conv_bound_experiment.md).
-//   * B: weights [Cout_pad][K], K = tap * Cin + channel, 2-D TMA box {64, BN}.
-//   * roles (192 threads): warp 5 lane 0 = TMA producer, warp 4 lane 0 = MMA issuer (also owns the TMEM allocation),
-//     warps 0-3 = epilogue (TMEM lane == tile row == output pixel).  Rings: smem full/empty (TMA <-> MMA) and TMEM
+//   * B: weights, K = tap * Cin + channel, stored re-tiled [Cout_pad / 16][K / 64][16][64] (2 KB contiguous pieces), 4-D TMA
+//     box {64, 16, 1, BN / 16}: lands as BN rows of 128 bytes, the same K-major SWIZZLE_128B layout.
+//   * roles (320 threads): warp 5 lane 0 = TMA producer, warp 4 lane 0 = MMA issuer (also owns the TMEM allocation),
+//     warps 0-3 and 6-9 = epilogue (TMEM lane == tile row == output pixel; the two groups split the tile's columns).  Rings: smem full/empty (TMA <-> MMA) and TMEM
 //     full/empty (MMA <-> epilogue, 2 accumulators): the epilogue of tile i overlaps the main loop of tile i + 1.
 //   * BN is a runtime value (any multiple of 16 up to 256): idesc, stage size and ring depth are computed per launch, so a
 //     320-channel layer runs as 2 x 160 instead of 5 x 64.
 //   * split-K for small-M layers (the 8x8 / 16x16 UNet levels): every split writes its fp32 partial tile to a workspace; the
 //     split that arrives last at the tile's counter adds all partials in split order (deterministic) and runs the epilogue.
 //
-// Eligibility (host, add_conv_tma): kind 0, bf16 output (mode 0), input stride 1, no folded upsampling, Cin % 64 == 0.
+// Eligibility (host, add_conv_tma): kind 0, input stride 1, no folded upsampling, Cin % 64 == 0.
 #pragma once
 
-#define CT_THREADS 192
+#define CT_THREADS 320   // warps 0-3 and 6-9: epilogue (two column halves), warp 4: MMA, warp 5: TMA producer
 #define CT_MAX_STAGES 8
 #define CT_SMEM_LIMIT (227 * 1024)
 #define CT_ACC_STRIDE 256  // TMEM columns between the two accumulators
@@ -46,13 +47,6 @@ struct ConvTmaParams {
     int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];
 };
 
-__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
-            "r"(smem_u32(smem_dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
 }
@@ -65,12 +59,28 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 // scale/shift -> (+residual) -> activation -> bf16, 16 channels of one pixel
 __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[16], int n0, size_t opix) {
+    {
+        const float4 *sh = reinterpret_cast<const float4 *>(p.shift + n0);
+        if (p.flags & 2) {   // every scale is 1 (no folded BatchNorm): bias only
 #pragma unroll
-    for (int j = 0; j < 16; j++) f[j] = fmaf(f[j], __ldg(p.scale + n0 + j), __ldg(p.shift + n0 + j));
+            for (int j = 0; j < 4; j++) {
+                const float4 t = __ldg(sh + j);
+                f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+            }
+        } else {
+            const float4 *sc = reinterpret_cast<const float4 *>(p.scale + n0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float4 t = __ldg(sh + j), u = __ldg(sc + j);
+                f[4 * j] = fmaf(f[4 * j], u.x, t.x); f[4 * j + 1] = fmaf(f[4 * j + 1], u.y, t.y);
+                f[4 * j + 2] = fmaf(f[4 * j + 2], u.z, t.z); f[4 * j + 3] = fmaf(f[4 * j + 3], u.w, t.w);
+            }
+        }
+    }
     const bool res_late = p.flags & 1;
     if (res_late) {
 #pragma unroll
@@ -123,7 +133,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 128);
+            mbar_init(&tempty[i], 256);
         }
         fence_barrier_init();
     }
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                         tma_load_4d(sA + s * A_STAGE_BYTES, &p.amap, p.in_coff + cb * CONV_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0, &full[s]);
                     else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"((uint32_t)A_STAGE_BYTES) : "memory");
                     if (!(p.dbg & 2))
-                        tma_load_2d(sB + (size_t)s * B_STAGE, &p.wmap, kb * CONV_BK, nt * p.BN, &full[s]);
+                        tma_load_4d(sB + (size_t)s * B_STAGE, &p.wmap, 0, 0, kb, (nt * p.BN) >> 4, &full[s]);
                     else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"(B_STAGE) : "memory");
                     if (++cb == p.cblocks) { cb = 0; tap++; }
                 }
@@ -191,7 +201,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
         }
     } else {
         // =========================== epilogue: TMEM lane == tile row == output pixel ===========
-        const int r = threadIdx.x;  // 0..127
+        // a warp may only touch TMEM lanes [32 (warp % 4), +32): warps 0-3 take the first half of the tile's columns,
+        // warps 6-9 the second half
+        const int r = (warp & 3) * 32 + lane;                 // tile row 0..127
+        const int half = warp < 4 ? 0 : 1;
+        const int c_half = ((p.BN + 31) / 32) * 16;           // columns [0, c_half) and [c_half, BN)
+        const int cb = half ? c_half : 0, ce = half ? p.BN : min(c_half, p.BN);
+        const bool leader = threadIdx.x == 0;
         const int TWm = (1 << p.lTW) - 1, THm = (1 << p.lTH) - 1;
         uint32_t n = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, n++) {
@@ -205,7 +221,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
             const uint32_t acc = n & 1;
             mbar_wait(&tfull[acc], (n >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * CT_ACC_STRIDE + ((uint32_t)(warp * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * CT_ACC_STRIDE + ((uint32_t)((warp & 3) * 32) << 16);
             const int n_base = nt * p.BN;
             if (p.mode != 0) {
                 // output heads (Cout <= 16, one 16-column chunk; splits == 1)
@@ -214,7 +230,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&tempty[acc]);
-                if (row_ok) {
+                if (row_ok && half == 0) {
                     for (int j = 0; j < p.Cout; j++) {
                         const float a = fmaf(__uint_as_float(v[j]), __ldg(p.scale + j), __ldg(p.shift + j));
                         if (p.mode == 2) {   // musetalk/models/vae.py:102-107
@@ -230,10 +246,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                 }
             } else if (p.splits == 1) {
 #pragma unroll 1
-                for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                for (int c0 = cb; c0 < ce; c0 += 32) {
                     uint32_t v0[16], v1[16];
                     tmem_ld16_nowait(taddr + c0, v0);
-                    if (c0 + 16 < p.BN) tmem_ld16_nowait(taddr + c0 + 16, v1);
+                    if (c0 + 16 < ce) tmem_ld16_nowait(taddr + c0 + 16, v1);
                     tmem_ld_wait();
                     if (!row_ok) continue;
                     if (n_base + c0 < p.Cout) {
@@ -242,7 +258,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                         for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v0[j]);
                         ct_finish16(p, f, n_base + c0, opix);
                     }
-                    if (c0 + 16 < p.BN && n_base + c0 + 16 < p.Cout) {
+                    if (c0 + 16 < ce && n_base + c0 + 16 < p.Cout) {
                         float f[16];
 #pragma unroll
                         for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v1[j]);
@@ -256,7 +272,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                 float *wtile = p.ws + ((size_t)(mt * p.n_tiles + nt) * p.splits) * (128 * (size_t)p.BN);
                 float *mine = wtile + ((size_t)sp * 128 + r) * p.BN;
 #pragma unroll 1
-                for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                for (int c0 = cb; c0 < ce; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16_nowait(taddr + c0, v);
                     tmem_ld_wait();
@@ -269,7 +285,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                 mbar_arrive(&tempty[acc]);
                 __threadfence();
                 epi_bar_sync();
-                if (r == 0) *last_flag = atomicAdd(p.counters + mt * p.n_tiles + nt, 1u) == (unsigned)(p.splits - 1);
+                if (leader) *last_flag = atomicAdd(p.counters + mt * p.n_tiles + nt, 1u) == (unsigned)(p.splits - 1);
                 epi_bar_sync();
                 const bool last = *last_flag != 0;
                 epi_bar_sync();  // everyone has read the flag before the next item may overwrite it
@@ -277,7 +293,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                     __threadfence();
                     if (row_ok) {
 #pragma unroll 1
-                        for (int c0 = 0; c0 < p.BN && n_base + c0 < p.Cout; c0 += 16) {
+                        for (int c0 = cb; c0 < ce && n_base + c0 < p.Cout; c0 += 16) {
                             float f[16];
 #pragma unroll
                             for (int j = 0; j < 16; j++) f[j] = 0.f;
@@ -292,7 +308,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                             ct_finish16(p, f, n_base + c0, opix);
                         }
                     }
-                    if (r == 0) p.counters[mt * p.n_tiles + nt] = 0u;
+                    if (leader) p.counters[mt * p.n_tiles + nt] = 0u;
                 }
             }
         }

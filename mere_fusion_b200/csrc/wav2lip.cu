@@ -102,6 +102,13 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
                 if (p.dbg & 2) mbar_arrive(&full[s]);
                 else {
                 mbar_expect_tx(&full[s], ConvSmem<BN, CONV_STAGES>::B_STAGE);
-                tma_load_2d(sB + s * ConvSmem<BN, CONV_STAGES>::B_STAGE, &p.wmap, kb * CONV_BK, blockIdx.y * BN, &full[s]);
+                tma_load_4d(sB + s * ConvSmem<BN, CONV_STAGES>::B_STAGE, &p.wmap, 0, 0, kb, (blockIdx.y * BN) >> 4, &full[s]);
                 }
             }
             if (p.dbg & 1) { mbar_arrive(&full[s]); continue; }
@@ -614,12 +621,12 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
         p.ntaps = o.ntaps; p.Cin = o.Cin; p.nkb = o.Kpad / CONV_BK; p.Cout = o.Cout; p.relu = o.relu; p.mode = o.mode; p.flags = o.flags;
         memcpy(p.tap_dy, o.tap_dy, CONV_MAX_TAPS);
         memcpy(p.tap_dx, o.tap_dx, CONV_MAX_TAPS);
-        // weights [Cout_pad][Kpad] bf16, K contiguous: TMA box = 64 (K) x BN rows, 128B swizzle
-        cuuint64_t dims[2] = {(cuuint64_t)o.Kpad, (cuuint64_t)o.Cout_pad};
-        cuuint64_t strides[1] = {(cuuint64_t)o.Kpad * 2};
-        cuuint32_t box[2] = {CONV_BK, (cuuint32_t)o.BN};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult cr = encode(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)(base + we->offset), dims, strides, box,
+        // weights re-tiled [Cout_pad / 16][Kpad / 64][16][64] bf16: TMA box = {64 k, 16 rows, 1 k-block, BN / 16 row groups}
+        cuuint64_t dims[4] = {CONV_BK, 16, (cuuint64_t)(o.Kpad / CONV_BK), (cuuint64_t)(o.Cout_pad / 16)};
+        cuuint64_t strides[3] = {CONV_BK * 2, 16 * CONV_BK * 2, (cuuint64_t)(o.Kpad / CONV_BK) * 16 * CONV_BK * 2};
+        cuuint32_t box[4] = {CONV_BK, 16, 1, (cuuint32_t)(o.BN / 16)};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult cr = encode(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)(base + we->offset), dims, strides, box,
                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return mf_fail(ctx, MF_E_CUDA, "op %d: cuTensorMapEncodeTiled failed (%d)", i, (int)cr);
@@ -736,11 +743,11 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
         const mf_blob_header *h = reinterpret_cast<const mf_blob_header *>(s->entry_table->data());
         for (uint32_t e = 0; e < h->n_entries; e++) if ((int32_t)ent[e].id == o.w_entry) we = &ent[e];
         MF_REQUIRE(ctx, we, "op %d: weight entry missing", i);
-        cuuint64_t dims[2] = {(cuuint64_t)o.Kpad, (cuuint64_t)o.Cout_pad};
-        cuuint64_t strides[1] = {(cuuint64_t)o.Kpad * 2};
-        cuuint32_t box[2] = {CONV_BK, (cuuint32_t)BN};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult cr = s->encode(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)(s->blob + we->offset), dims, strides, box, estr,
+        cuuint64_t dims[4] = {CONV_BK, 16, (cuuint64_t)(o.Kpad / CONV_BK), (cuuint64_t)(o.Cout_pad / 16)};
+        cuuint64_t strides[3] = {CONV_BK * 2, 16 * CONV_BK * 2, (cuuint64_t)(o.Kpad / CONV_BK) * 16 * CONV_BK * 2};
+        cuuint32_t box[4] = {CONV_BK, 16, 1, (cuuint32_t)(BN / 16)};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult cr = s->encode(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)(s->blob + we->offset), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return mf_fail(ctx, MF_E_CUDA, "op %d: weight cuTensorMapEncodeTiled failed (%d)", i, (int)cr);

@@ -17,6 +17,7 @@ class MuseTalkEngine(ConvNet):
             self.flops_per_frame = pb.flops_per_sample
             self.unet_flops, self.vae_flops = pb.unet_flops, pb.vae_flops
             self.n_ops = len(pb.ops)
+            self.op_records = list(pb.ops)
         self.out_hw = 256
         super().__init__(blob, max_batch, device)
 

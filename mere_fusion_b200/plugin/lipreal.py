@@ -88,6 +88,7 @@ class LipReal(BaseReal):
         self.asr.warm_up()
         self.render_event = Event()
         self.infer_frames = 0
+        self._render_alive = False
 
     # lipreal.py:42-53: checkpoint["state_dict"], "module." prefix stripped (by the packer)
     def _load_engine(self, state_dict):
@@ -163,6 +164,15 @@ class LipReal(BaseReal):
         pred = d["pred_pin"].numpy()
         return [pred[i].copy() for i in range(B)]
 
+    def _put_result(self, item, quit_event):
+        """res_frame_queue.put that gives up once the session quits (the consumer thread is gone by then)"""
+        while not quit_event.is_set():
+            try:
+                self.res_frame_queue.put(item, timeout=0.1)
+                return
+            except queue.Full:
+                pass
+
     def inference(self, quit_event):
         """lipreal.py:75-141, in-process"""
         length = len(self.face_list_cycle)
@@ -185,7 +195,7 @@ class LipReal(BaseReal):
                     is_all_silence = False
             if is_all_silence:
                 for i in range(self.batch_size):
-                    self.res_frame_queue.put((None, mirror_index(length, index), audio_frames[i * 2:i * 2 + 2]))
+                    self._put_result((None, mirror_index(length, index), audio_frames[i * 2:i * 2 + 2]), quit_event)
                     index = index + 1
             else:
                 t = time.perf_counter()
@@ -197,8 +207,14 @@ class LipReal(BaseReal):
                     print(f"------actual avg infer fps:{count / counttime:.4f}")
                     count, counttime = 0, 0.0
                 for i, res_frame in enumerate(results):
-                    self.res_frame_queue.put((res_frame, mirror_index(length, index), audio_frames[i * 2:i * 2 + 2]))
+                    self._put_result((res_frame, mirror_index(length, index), audio_frames[i * 2:i * 2 + 2]), quit_event)
                     index = index + 1
+        # the render loop may be blocked in feat_queue.put (depth 2) when the quit event arrives: keep draining until it is out
+        while self._render_alive:
+            try:
+                self.asr.feat_queue.get(timeout=0.05)
+            except queue.Empty:
+                pass
 
     def _emit(self, coro, loop):
         if loop is not None:
@@ -254,9 +270,10 @@ class LipReal(BaseReal):
         """lipreal.py:232-250"""
         self.tts.render(quit_event)
         self.init_customindex()
-        process_thread = Thread(target=self.process_frames, args=(quit_event, loop, audio_track, video_track))
+        self._render_alive = True
+        process_thread = Thread(target=self.process_frames, args=(quit_event, loop, audio_track, video_track), daemon=True)
         process_thread.start()
-        infer_thread = Thread(target=self.inference, args=(quit_event,))
+        infer_thread = Thread(target=self.inference, args=(quit_event,), daemon=True)
         infer_thread.start()
         self.render_event.set()
         while not quit_event.is_set():
@@ -264,5 +281,6 @@ class LipReal(BaseReal):
             if video_track._queue.qsize() >= 5:
                 time.sleep(0.04 * video_track._queue.qsize() * 0.8)
         self.render_event.clear()
+        self._render_alive = False
         process_thread.join()
         infer_thread.join()

@@ -88,6 +88,7 @@ class MuseReal(BaseReal):
         self.asr.warm_up()
         self.render_event = Event()
         self.infer_frames = 0
+        self._render_alive = False
 
     # musetalk/utils/utils.py:70-75 load_all_model: diffusers-format state dicts
     def _load_engine(self, unet_sd, vae_sd):
@@ -152,8 +153,11 @@ class MuseReal(BaseReal):
         B = self.batch_size
         length = len(self.input_latent_list_cycle)
         idxs = [mirror_index(length, index + i) for i in range(B)]
-        d["wh_pin"].copy_(torch.from_numpy(np.stack(whisper_chunks).astype(np.float16)))      # .to(dtype=half), musereal.py:99-101
-        d["wh"].copy_(d["wh_pin"], non_blocking=True)
+        if torch.is_tensor(whisper_chunks):                       # device-resident chunks from MuseASR (already fp16)
+            d["wh"].copy_(whisper_chunks, non_blocking=True)
+        else:
+            d["wh_pin"].copy_(torch.from_numpy(np.stack(whisper_chunks).astype(np.float16)))  # .to(dtype=half), musereal.py:99-101
+            d["wh"].copy_(d["wh_pin"], non_blocking=True)
         torch.index_select(d["latents"], 0, torch.as_tensor(idxs, device=d["latents"].device), out=d["sel"])
         self.engine.forward(d["sel"], d["wh"], out=d["pred"])
         if self.paste == "gpu":
@@ -204,7 +208,7 @@ class MuseReal(BaseReal):
                     is_all_silence = False
             if is_all_silence:
                 for i in range(self.batch_size):
-                    self.res_frame_queue.put((None, mirror_index(length, index), audio_frames[i * 2:i * 2 + 2]))
+                    self._put_result((None, mirror_index(length, index), audio_frames[i * 2:i * 2 + 2]), quit_event)
                     index = index + 1
             else:
                 t = time.perf_counter()
@@ -216,10 +220,17 @@ class MuseReal(BaseReal):
                     print(f"------actual avg infer fps:{count / counttime:.4f}")
                     count, counttime = 0, 0.0
                 for i, res_frame in enumerate(results):
-                    self.res_frame_queue.put((res_frame, mirror_index(length, index), audio_frames[i * 2:i * 2 + 2]))
+                    self._put_result((res_frame, mirror_index(length, index), audio_frames[i * 2:i * 2 + 2]), quit_event)
                     index = index + 1
+        # the render loop may be blocked in feat_queue.put (depth 2) when the quit event arrives: keep draining until it is out
+        while self._render_alive:
+            try:
+                self.asr.feat_queue.get(timeout=0.05)
+            except queue.Empty:
+                pass
 
     _emit = LipReal._emit
+    _put_result = LipReal._put_result
 
     def process_frames(self, quit_event, loop=None, audio_track=None, video_track=None):
         """musereal.py:222-264"""
@@ -266,9 +277,10 @@ class MuseReal(BaseReal):
         """musereal.py:267-290"""
         self.tts.render(quit_event)
         self.init_customindex()
-        process_thread = Thread(target=self.process_frames, args=(quit_event, loop, audio_track, video_track))
+        self._render_alive = True
+        process_thread = Thread(target=self.process_frames, args=(quit_event, loop, audio_track, video_track), daemon=True)
         process_thread.start()
-        infer_thread = Thread(target=self.inference, args=(quit_event,))
+        infer_thread = Thread(target=self.inference, args=(quit_event,), daemon=True)
         infer_thread.start()
         self.render_event.set()
         while not quit_event.is_set():
@@ -276,6 +288,7 @@ class MuseReal(BaseReal):
             if video_track._queue.qsize() >= 1.5 * self.opt.batch_size:
                 time.sleep(0.04 * video_track._queue.qsize() * 0.8)
         self.render_event.clear()
+        self._render_alive = False
         process_thread.join()
         infer_thread.join()
 

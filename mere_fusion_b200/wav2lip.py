@@ -45,6 +45,14 @@ class ConvNet:
     def last_launches(self):
         return lib().mf_wav2lip_last_launches(self.ctx.handle)
 
+    def profile_op(self, op_index):
+        check(self.ctx.handle, lib().mf_wav2lip_profile(self.ctx.handle, int(op_index)), "mf_wav2lip_profile")
+
+    def last_op_ms(self):
+        ms = ctypes.c_float()
+        check(self.ctx.handle, lib().mf_wav2lip_last_op_ms(self.ctx.handle, ctypes.byref(ms)), "mf_wav2lip_last_op_ms")
+        return ms.value
+
 
 class Wav2LipEngine(ConvNet):
     def __init__(self, state_dict=None, max_batch=16, device=0, blob=None, face_hw=96):
@@ -81,10 +89,3 @@ class Wav2LipEngine(ConvNet):
         out_pinned.copy_(st[2], non_blocking=True)
         return out_pinned
 
-    def profile_op(self, op_index):
-        check(self.ctx.handle, lib().mf_wav2lip_profile(self.ctx.handle, int(op_index)), "mf_wav2lip_profile")
-
-    def last_op_ms(self):
-        ms = ctypes.c_float()
-        check(self.ctx.handle, lib().mf_wav2lip_last_op_ms(self.ctx.handle, ctypes.byref(ms)), "mf_wav2lip_last_op_ms")
-        return ms.value

@@ -68,16 +68,49 @@ class Audio2Feature:
             engine = WhisperEngine(state_dict, device=device)
         self.engine = engine
         self._pin = None
+        self._h2d_done = None
 
     get_sliced_feature = staticmethod(get_sliced_feature)
     feature2chunks = staticmethod(feature2chunks)
 
+    def chunk_indices(self, n_rows, fps, batch_size, audio_feat_length=(2, 2), start=0):
+        """row indices feature2chunks would select (audio2feature.py:16-45, 82-97): int64 [batch_size, 10]"""
+        idx = []
+        for i in range(batch_size):
+            c = int((i + start) * 50 / fps)
+            idx.append([min(n_rows - 1, max(0, j)) for j in range(c - audio_feat_length[0] * 2, c + (audio_feat_length[1] + 1) * 2)])
+        return np.asarray(idx, np.int64)
+
+    def audio2chunks_device(self, audio, fps, batch_size, start=0, audio_dev=None):
+        """audio2feat + feature2chunks without leaving the GPU: float32 waveform -> cuda fp16 [batch_size, 50, 384] (the gather
+        is index plumbing on device memory; the indices are the reference's integer arithmetic, computed on the host)"""
+        if audio_dev is None:
+            a = np.ascontiguousarray(audio, np.float32)
+            self._stage(a.size)
+            if self._h2d_done is not None:
+                self._h2d_done.synchronize()       # the previous window's async H2D must have read the pinned buffer
+            self._pin[:a.size].copy_(torch.from_numpy(a))
+            audio_dev = self._dev[:a.size]
+            audio_dev.copy_(self._pin[:a.size], non_blocking=True)
+            if self._h2d_done is None:
+                self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record(torch.cuda.current_stream(self.engine.device))
+        feat = self.engine.features(audio_dev)                                      # [T, 5, 384] fp32
+        key = (int(feat.shape[0]), float(fps), int(batch_size), float(start))
+        if getattr(self, "_idx_key", None) != key:
+            self._idx = torch.from_numpy(self.chunk_indices(feat.shape[0], fps, batch_size, start=start).reshape(-1)).to(feat.device)
+            self._idx_key = key
+        return feat.index_select(0, self._idx).reshape(batch_size, -1, feat.shape[2]).to(torch.float16)
+
+    def _stage(self, n):
+        if self._pin is None or self._pin.numel() < n:
+            self._pin = torch.empty(max(n, 16640), dtype=torch.float32).pin_memory()
+            self._dev = torch.empty(self._pin.numel(), dtype=torch.float32, device=self.engine.device)
+
     def audio2feat(self, audio):
         """float32 waveform (16 kHz) -> np.float32 [T, 5, 384]; one 30 s segment (the live window is 0.33 s)"""
         a = np.ascontiguousarray(audio, np.float32)
-        if self._pin is None or self._pin.numel() < a.size:
-            self._pin = torch.empty(max(a.size, 16640), dtype=torch.float32).pin_memory()
-            self._dev = torch.empty(self._pin.numel(), dtype=torch.float32, device=self.engine.device)
+        self._stage(a.size)
         self._pin[:a.size].copy_(torch.from_numpy(a))
         d = self._dev[:a.size]
         d.copy_(self._pin[:a.size], non_blocking=True)

@@ -146,7 +146,7 @@ def test_config1_lipreal_plumbing_10s_clip():
         real.put_audio_frame(wav[i * 320:(i + 1) * 320])
     quit_event = threading.Event()
     vt, at = FakeTrack(), FakeTrack()
-    th = threading.Thread(target=real.render, args=(quit_event, None, at, vt))
+    th = threading.Thread(target=real.render, args=(quit_event, None, at, vt), daemon=True)
     th.start()
     t0 = time.time()
     while len(vt._queue.items) < 272 and time.time() - t0 < 120:
@@ -320,7 +320,7 @@ def test_musereal_plumbing_host_blend():
         real.put_audio_frame(wav[i * 320:(i + 1) * 320])
     quit_event = threading.Event()
     vt, at = FakeTrack(), FakeTrack()
-    th = threading.Thread(target=real.render, args=(quit_event, None, at, vt))
+    th = threading.Thread(target=real.render, args=(quit_event, None, at, vt), daemon=True)
     th.start()
     t0 = time.time()
     while len(vt._queue.items) < 112 and time.time() - t0 < 120:

@@ -45,7 +45,7 @@ def _run(real, n_frames, chunks, timeout=120):
     vt, at = FakeTrack(), FakeTrack()
     for c in chunks:
         real.put_audio_frame(c)
-    th = threading.Thread(target=real.render, args=(quit_event, None, at, vt))
+    th = threading.Thread(target=real.render, args=(quit_event, None, at, vt), daemon=True)
     th.start()
     t0 = time.time()
     while len(vt._queue.items) < n_frames and time.time() - t0 < timeout:

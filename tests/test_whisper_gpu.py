@@ -64,6 +64,17 @@ def test_audio2feature_mirror(engine):
     assert _rel(np.stack(chunks), np.stack(a2f.feature2chunks(feature_array=ref, fps=25, batch_size=16, start=5))) < 2e-2
 
 
+def test_device_chunks_equal_host_chunks(engine):
+    """audio2chunks_device (gather on the GPU) == feature2chunks(audio2feat(...)) (the reference's host path)"""
+    from mere_fusion_b200.whisper import Audio2Feature
+    a2f = Audio2Feature(engine=engine)
+    audio = synthetic_speech(52 * 320, 0)
+    host = np.stack(a2f.feature2chunks(feature_array=a2f.audio2feat(audio), fps=25.0, batch_size=16, start=5.0)).astype(np.float16)
+    dev = a2f.audio2chunks_device(audio, fps=25.0, batch_size=16, start=5.0)
+    assert dev.shape == (16, 50, 384) and dev.dtype == torch.float16
+    assert np.array_equal(dev.cpu().numpy(), host)
+
+
 def test_rejects_bad_arguments(engine):
     from mere_fusion_b200._lib import MfError
     with pytest.raises(MfError):
