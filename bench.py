@@ -139,6 +139,21 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def packed_on_all_ranks(pack_fn, rank, world, dev):
+    """rank 0 packs the checkpoint once, ONE NCCL broadcast hands the blob to the peers (plus a small pickled
+    metadata record); pack_fn() -> (blob ndarray, meta dict)"""
+    import torch
+    import torch.distributed as dist
+    from mere_fusion_b200.dist import broadcast_bytes
+    blob, meta = pack_fn() if rank == 0 else (None, None)
+    if world == 1:
+        return torch.from_numpy(blob).to(dev), meta
+    t = broadcast_bytes(blob, src=0, device=dev)
+    box = [meta]
+    dist.broadcast_object_list(box, src=0, device=dev)
+    return t, box[0]
+
+
 def wav2lip_leg(args, dev, local, rank, world, flush, timed_fn, pk):
     """BASELINE configs[1]-shaped leg on the architecture the reference actually ships (96x96 crop):
     16 frames per step: mel windows -> Wav2Lip (tcgen05 implicit-GEMM convs, bf16) -> cv2-exact resize + paste into
@@ -149,7 +164,15 @@ def wav2lip_leg(args, dev, local, rank, world, flush, timed_fn, pk):
     from mere_fusion_b200._lib import check, lib
     from mere_fusion_b200.wav2lip import Wav2LipEngine
     B = 16
-    eng = Wav2LipEngine(seeded_wav2lip_state(2), max_batch=B, device=local)
+
+    def pack():
+        from mere_fusion_b200.wav2lip_pack import pack_wav2lip
+        blob, pb = pack_wav2lip(seeded_wav2lip_state(2), nominal_batch=B)
+        return blob, dict(flops=pb.flops_per_sample, n_ops=len(pb.ops))
+
+    blob, meta = packed_on_all_ranks(pack, rank, world, dev)
+    eng = Wav2LipEngine(blob=blob, max_batch=B, device=local)
+    eng.flops_per_frame, eng.n_ops = meta["flops"], meta["n_ops"]
     rng = np.random.default_rng(1)
     n_av = 25
     frames = torch.from_numpy(rng.integers(0, 256, (n_av, H, W, 3), dtype=np.uint8)).to(dev)
@@ -224,9 +247,26 @@ def musetalk_leg(args, dev, local, rank, world, flush, timed_fn, pk):
     from mere_fusion_b200.whisper import Audio2Feature, WhisperEngine
     B = 16
     u, v = M.UNET_CFG, M.VAE_CFG
-    eng = MuseTalkEngine(M.seeded_state(M.unet_param_shapes(u), 5), M.seeded_state(M.vae_decoder_param_shapes(v), 6), u, v,
-                         max_batch=B, device=local)
-    a2f = Audio2Feature(engine=WhisperEngine(seeded_whisper_state(7), WHISPER_TINY, device=local))
+
+    def pack_m():
+        from mere_fusion_b200.musetalk_pack import pack_musetalk
+        blob, pb = pack_musetalk(M.seeded_state(M.unet_param_shapes(u), 5), M.seeded_state(M.vae_decoder_param_shapes(v), 6), u, v,
+                                 nominal_batch=B)
+        op = next(i for i, rec in enumerate(pb.ops) if struct.unpack("<28i", rec[:112])[14:18] == (9, 128, 1152, 128))
+        return blob, dict(flops=pb.flops_per_sample, unet=pb.unet_flops, vae=pb.vae_flops, op=op)
+
+    def pack_w():
+        from mere_fusion_b200.whisper_pack import pack_whisper
+        blob, pb = pack_whisper(seeded_whisper_state(7), WHISPER_TINY)
+        return blob, dict(flops=pb.flops_per_sample)
+
+    blob_m, meta_m = packed_on_all_ranks(pack_m, rank, world, dev)
+    blob_w, meta_w = packed_on_all_ranks(pack_w, rank, world, dev)
+    eng = MuseTalkEngine(blob=blob_m, max_batch=B, device=local)
+    eng.flops_per_frame, eng.unet_flops, eng.vae_flops = meta_m["flops"], meta_m["unet"], meta_m["vae"]
+    wh = WhisperEngine(blob=blob_w, dims=WHISPER_TINY, device=local)
+    wh.flops_per_call = meta_w["flops"]
+    a2f = Audio2Feature(engine=wh)
     rng = np.random.default_rng(11 + rank)
     n_av = 12
     frames = torch.from_numpy(rng.integers(0, 200, (n_av, H, W, 3), dtype=np.uint8)).to(dev)
@@ -281,8 +321,7 @@ def musetalk_leg(args, dev, local, rank, world, flush, timed_fn, pk):
     e2e, _, _ = timed_fn(step_host, K, args.warmup)
     launches = eng.last_launches + a2f.engine.last_launches + 1
     # dominant kernel by time share: the 128 -> 128 3x3 convs of the last VAE up block at 256x256 (k_conv_tma), one of them timed live
-    op = next(i for i, rec in enumerate(eng.op_records) if struct.unpack("<28i", rec[:112])[14:18] == (9, 128, 1152, 128))
-    eng.profile_op(op)
+    eng.profile_op(meta_m["op"])
     ms = []
     for k in range(5):
         flush.fill_(k)
@@ -454,7 +493,7 @@ def main():
                    "checkpoint": "tests/golden/ernerf_ckpt_infer.npz (reference data/pretrained/ngp_kf.pth)",
                    "inputs": "real poses (data_kf.json), N(0,1) audio windows [8,44,16], white background",
                    "l2": "flushed between steps (256 MiB write), flush outside the per-step CUDA events",
-                   "parallelism": f"{world} independent frame streams, weights NCCL-broadcast at init"},
+                   "parallelism": f"{world} independent frame streams (one process per GPU), every head's packed blob NCCL-broadcast from rank 0 at init, no collective on the frame path"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(auds_pin[0].numel() * 4 + 64 + 20),
                 "d2h_bytes_per_step": int(out_pin.numel()), "ms_per_step": e2e_ms / args.steps},
         "p50_chunk_to_frame_ms": float(np.median(lat)),

@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch();
+    pdl_wait();   // barrier init, TMEM allocation and descriptor fetch above overlap the predecessor's tail
     const int total = p.total_items;
     const int per_tile = p.n_tiles * p.splits;
 
@@ -292,17 +294,31 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                 if (last) {
                     __threadfence();
                     if (row_ok) {
+                        // all partials of a 16-column chunk are requested before the first add (up to 4 splits x 4 float4 in
+                        // flight per thread; a dependent load-add chain here cost ~0.6 us of L2 latency per split per chunk);
+                        // the adds run in split order, so the result does not depend on arrival order
 #pragma unroll 1
                         for (int c0 = cb; c0 < ce && n_base + c0 < p.Cout; c0 += 16) {
                             float f[16];
 #pragma unroll
                             for (int j = 0; j < 16; j++) f[j] = 0.f;
-                            for (int s2 = 0; s2 < p.splits; s2++) {
-                                const float4 *q = reinterpret_cast<const float4 *>(wtile + ((size_t)s2 * 128 + r) * p.BN + c0);
+                            for (int s0 = 0; s0 < p.splits; s0 += 4) {
+                                float4 t[4][4];
 #pragma unroll
-                                for (int j = 0; j < 4; j++) {
-                                    const float4 t = __ldcg(q + j);
-                                    f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                                for (int u = 0; u < 4; u++) {
+                                    const int s2 = min(s0 + u, p.splits - 1);
+                                    const float4 *q = reinterpret_cast<const float4 *>(wtile + ((size_t)s2 * 128 + r) * p.BN + c0);
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) t[u][j] = __ldcg(q + j);
+                                }
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    if (s0 + u < p.splits) {
+#pragma unroll
+                                        for (int j = 0; j < 4; j++) {
+                                            f[4 * j] += t[u][j].x; f[4 * j + 1] += t[u][j].y; f[4 * j + 2] += t[u][j].z; f[4 * j + 3] += t[u][j].w;
+                                        }
+                                    }
                                 }
                             }
                             ct_finish16(p, f, n_base + c0, opix);

@@ -18,6 +18,8 @@ struct PrepParams {
 // wav2lip faces u8 [B,S,S,3] BGR -> bf16 [B,S,S,8]: ch 0-2 = face with rows >= S/2 zeroed, ch 3-5 = face, /255
 // (lipreal.py:108-122).  a = B, b = S
 __global__ void k_prep_face(const PrepParams p) {
+    pdl_launch();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int S = p.b;
     if (i >= p.a * S * S) return;
@@ -41,6 +43,8 @@ __global__ void k_prep_face(const PrepParams p) {
 }
 // wav2lip mel fp32 [B,1,80,16] -> bf16 [B,80,16,8] (channel 0).  a = element count
 __global__ void k_prep_mel(const PrepParams p) {
+    pdl_launch();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.a) return;
     __nv_bfloat162 h = __floats2bfloat162_rn(reinterpret_cast<const float *>(p.src)[i], 0.f);
@@ -48,6 +52,8 @@ __global__ void k_prep_mel(const PrepParams p) {
 }
 // musetalk latents fp16 NCHW [B,C,H,W] -> bf16 NHWC [B,H,W,Cpad].  a = B, b = C, c = H*W, d = Cpad
 __global__ void k_prep_latents(const PrepParams p) {
+    pdl_launch();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.a * p.c * p.d) return;
     const int ch = i % p.d, pix = (i / p.d) % p.c, b = i / (p.d * p.c);
@@ -58,6 +64,8 @@ __global__ void k_prep_latents(const PrepParams p) {
 // musetalk audio context: whisper fp16 [B,T,D] + sinusoidal PE in fp16 (musetalk/models/unet.py:12-27 with
 // pe.half(), musereal.py:60,102) -> bf16 [B,T,1,D].  a = B, b = T, c = D
 __global__ void k_prep_ctx(const PrepParams p) {
+    pdl_launch();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.a * p.b * p.c) return;
     const int dch = i % p.c, t = (i / p.c) % p.b;
@@ -88,6 +96,8 @@ struct WhisperPrep {
 #define WH_MELS 80
 
 __global__ void __launch_bounds__(256) k_logmel_frames(const WhisperPrep p) {
+    pdl_launch();
+    pdl_wait();
     __shared__ float xs[WH_NFFT], ct[WH_NFFT], st[WH_NFFT], pw[WH_BINS + 7];
     __shared__ float red[8];
     const int t = blockIdx.x;
@@ -132,6 +142,8 @@ __global__ void __launch_bounds__(256) k_logmel_frames(const WhisperPrep p) {
     }
 }
 __global__ void __launch_bounds__(256) k_logmel_finish(const WhisperPrep p) {
+    pdl_launch();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_ctx_frames * WH_MELS) return;
     const int t = i / WH_MELS;
@@ -151,6 +163,8 @@ struct GatherParams {
     int n_src, T, C;
 };
 __global__ void __launch_bounds__(256) k_whisper_gather(const GatherParams p) {
+    pdl_launch();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *p.maxslot = 0;
     if (i >= p.T * p.n_src * p.C) return;
@@ -159,11 +173,15 @@ __global__ void __launch_bounds__(256) k_whisper_gather(const GatherParams p) {
 }
 
 __global__ void k_f32_to_bf16(const PrepParams p) {
+    pdl_launch();
+    pdl_wait();
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t n = ((size_t)(uint32_t)p.a) | ((size_t)(uint32_t)p.b << 32);
     if (i < n) reinterpret_cast<__nv_bfloat16 *>(p.dst)[i] = __float2bfloat16_rn(reinterpret_cast<const float *>(p.src)[i]);
 }
 __global__ void k_bf16_to_f32(const PrepParams p) {
+    pdl_launch();
+    pdl_wait();
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t n = ((size_t)(uint32_t)p.a) | ((size_t)(uint32_t)p.b << 32);
     if (i < n) reinterpret_cast<float *>(p.dst)[i] = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p.src)[i]);
@@ -193,6 +211,8 @@ struct NormParams {
 // grid (ceil(npix / pix_per_cta), B).  A thread owns fixed 8-channel chunk columns (so the sums of its channels
 // stay in registers) and walks the CTA's pixel range with a stride.
 __global__ void __launch_bounds__(256) k_gn_stats(const NormParams p) {
+    pdl_launch();
+    pdl_wait();
     __shared__ float part[2][GN_MAX_C];
     __shared__ float red[8][128];
     __shared__ float mr[64][2];
@@ -284,6 +304,8 @@ __global__ void __launch_bounds__(256) k_gn_stats(const NormParams p) {
 // grid (ceil(npix / pix_per_cta), B): same thread -> channel-chunk mapping as the statistics pass, so the 16
 // coefficients of a thread's chunk are loaded once and the pixel loop is pure streaming (16-B loads / stores)
 __global__ void __launch_bounds__(256) k_gn_apply(const NormParams p) {
+    pdl_launch();
+    pdl_wait();
     const int chunks = p.C >> 3;
     const int cpp = min(chunks, (int)blockDim.x);
     const int lanes = ((int)blockDim.x / cpp) * cpp;
@@ -332,6 +354,8 @@ __global__ void __launch_bounds__(256) k_gn_apply(const NormParams p) {
 // written from shared memory -- one global read, one global write, one launch instead of two latency-bound ones.
 #define GN_SMALL_THREADS 1024
 __global__ void __launch_bounds__(GN_SMALL_THREADS) k_gn_small(const NormParams p) {
+    pdl_launch();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char gsm[];
     uint4 *slab = reinterpret_cast<uint4 *>(gsm);                                     // [npix][C / 8]
     float2 *tsum = reinterpret_cast<float2 *>(gsm + (size_t)p.npix * p.C * 2);        // [threads]
@@ -399,6 +423,8 @@ __global__ void __launch_bounds__(GN_SMALL_THREADS) k_gn_small(const NormParams 
 
 // LayerNorm over C per token: one warp per token (npix = total tokens over the batch), C <= 2048, C % 8 == 0
 __global__ void __launch_bounds__(256) k_layernorm(const NormParams p) {
+    pdl_launch();
+    pdl_wait();
     const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (tok >= p.npix) return;
     const __nv_bfloat16 *in = p.in + (size_t)tok * p.C;
@@ -447,6 +473,8 @@ struct GegluParams {
     int Hd;
 };
 __global__ void __launch_bounds__(256) k_geglu(const GegluParams p) {
+    pdl_launch();
+    pdl_wait();
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const int chunks = p.Hd >> 3;
     if (i >= p.tokens * chunks) return;
@@ -498,6 +526,8 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t &r0, uint32_t &r1, ui
 // CTA tile 64 x 64, K step 32, 4 warps (2 x 2), each warp 32 x 32
 template <bool TRANSB, bool OUT_BF16>
 __global__ void __launch_bounds__(128) k_bgemm(const GemmParams p) {
+    pdl_launch();
+    pdl_wait();
     __shared__ __align__(16) __nv_bfloat16 sA[64][40];
     __shared__ __align__(16) __nv_bfloat16 sB[TRANSB ? 32 : 64][TRANSB ? 72 : 40];
     const int z = blockIdx.z, bb = z / p.heads, hh = z % p.heads;
@@ -602,6 +632,8 @@ struct FlashParams {
 
 template <int DP>
 __global__ void __launch_bounds__(128) k_flash(const FlashParams p) {
+    pdl_launch();
+    pdl_wait();
     constexpr int LD = DP + 8;          // +16 B per row: conflict-free ldmatrix
     constexpr int KS = DP / 16;         // k-steps of Q K^T
     constexpr int NT = DP / 8;          // n-tiles of P V
@@ -727,6 +759,8 @@ struct SoftmaxParams {
     float scale;
 };
 __global__ void __launch_bounds__(256) k_softmax(const SoftmaxParams p) {
+    pdl_launch();
+    pdl_wait();
     const size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= p.rows) return;

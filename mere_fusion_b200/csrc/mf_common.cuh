@@ -65,6 +65,11 @@ struct mf_blob_header {
 // device helpers
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+// programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor drains; pdl_wait() blocks until the predecessor grid has completed and its writes are visible (no-op otherwise)
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }

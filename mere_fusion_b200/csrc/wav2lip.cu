@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch();
+    pdl_wait();   // everything above is CTA-local set-up and overlaps the predecessor's tail
 
     if (warp < 4) {
         // =========================== A producer: one output pixel per thread ===================
@@ -448,6 +450,8 @@ struct Wav2LipState {
     };
     std::vector<Plan *> plans;
     bool use_graph = true;
+    bool use_pdl = true;
+    cudaStream_t capture_stream = nullptr;
     // Whisper program (hdr.mel_w == -2): log-mel scratch, embedding buffers to gather, filterbank
     float *wh_logspec = nullptr;
     int *wh_maxslot = nullptr;
@@ -477,6 +481,7 @@ void wav2lip_destroy(mf_ctx *ctx) {
         delete pl;
     }
     delete s->entry_table;
+    if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
     cudaFree(s->dbg_ws);
     cudaFree(s->dbg_counters);
     cudaFree(s->wh_logspec);
@@ -537,6 +542,7 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
     s->encode = encode;
     s->sm_count = ctx->sm_count > 0 ? ctx->sm_count : 148;
     { const char *e = getenv("MF_NO_GRAPH"); s->use_graph = !(e && atoi(e)); }
+    { const char *e = getenv("MF_PDL"); s->use_pdl = !(e && !atoi(e)); }
     s->dbuf.assign(s->hdr.n_buffers, nullptr);
     for (int i = 0; i < s->hdr.n_buffers; i++) {
         const size_t bytes = (size_t)max_batch * s->bufs[i].H * s->bufs[i].W * s->bufs[i].C * 2;
@@ -694,7 +700,9 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
     p.tiles_x = (o.Mw + TW - 1) / TW; p.tiles_y = (o.Mh + TH - 1) / TH;
     const int m_tiles = best_tiles;
     const int nkb = o.Kpad / CONV_BK;
-    // BN / split-K: minimise a simple cost model (cycles): per k-block max(MMA, smem traffic), per item a pipeline fill
+    // BN / split-K: minimise a simple cost model (cycles): per k-block max(MMA, smem traffic), per item a pipeline fill, per split
+    // a reduction term.  Sweeps over forced (BN, S) (profiles/r01_conv_planner_sweep.log) show it within ~20 % of the best
+    // measured choice on the small-M layers; a fitted per-SM ingest / split-latency model did worse and was dropped.
     const int sms = s->sm_count;
     double best = 1e30;
     int BN = 0, S = 1;
@@ -713,6 +721,16 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
         }
     }
     MF_REQUIRE(ctx, BN >= 16, "op %d: no BN for the TMA conv", i);
+    {   // experiments (scripts/bench_conv.py): MF_CONV_FORCE="BN,S" overrides the cost model, MF_CONV_VERBOSE=1 prints the choice
+        const char *e = getenv("MF_CONV_FORCE");
+        int fbn = 0, fs = 0;
+        if (e && sscanf(e, "%d,%d", &fbn, &fs) == 2 && fbn >= 16 && fbn <= 256 && fbn % 16 == 0 && fs >= 1 && fs <= 8 && nkb / fs >= 1 &&
+            (o.mode == 0 || fs == 1)) { BN = fbn; S = fs; }
+        const char *v = getenv("MF_CONV_VERBOSE");
+        if (v && atoi(v))
+            fprintf(stderr, "[conv_tma] op %d Cin %d Cout %d taps %d M %dx%dx%d: tile %dx%dx%d, m_tiles %d, BN %d, splits %d, nkb %d\n", i, o.Cin,
+                    o.Cout, o.ntaps, B, o.Mh, o.Mw, TW, TH, TB, m_tiles, BN, S, nkb);
+    }
     p.BN = BN; p.n_tiles = (o.Cout + BN - 1) / BN; p.splits = S;
     const int stage = A_STAGE_BYTES + BN * 128;
     p.stages = std::min(CT_MAX_STAGES, (CT_SMEM_LIMIT - 1024 - 256) / stage);
@@ -997,14 +1015,29 @@ static void patch_io(Wav2LipState::Plan *pl, const void *in0, const void *in1, v
     pl->in0 = in0; pl->in1 = in1; pl->out_u8 = out_u8; pl->out_f32 = out_f32;
 }
 
-static int launch_direct(mf_ctx *ctx, Wav2LipState *s, std::vector<Launch> &L, cudaStream_t st) {
-    bool started = false;
+static int launch_direct(mf_ctx *ctx, Wav2LipState *s, std::vector<Launch> &L, cudaStream_t st, bool pdl = false) {
+    bool started = false, first = true;
     for (auto &l : L) {
         // profiling: events around ALL launches of the profiled op (an op may expand to several kernels)
         const bool prof = s->profile && l.op >= 0 && l.op == s->profile_op;
         if (prof && !started) { cudaEventRecord(s->ev[0], st); started = true; }
         void *args[] = {l.params.data()};
-        MF_CUDA(ctx, cudaLaunchKernel(l.func, l.grid, l.block, args, l.smem, st));
+        if (pdl && !first) {
+            // programmatic dependent launch: this kernel's CTA-local prologue may overlap the predecessor's tail; every executor
+            // kernel calls griddepcontrol.wait before its first global access
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = l.grid; cfg.blockDim = l.block; cfg.dynamicSmemBytes = (size_t)l.smem; cfg.stream = st;
+            cudaLaunchAttribute at;
+            memset(&at, 0, sizeof(at));
+            at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at.val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = &at; cfg.numAttrs = 1;
+            MF_CUDA(ctx, cudaLaunchKernelExC(&cfg, l.func, args));
+        } else {
+            MF_CUDA(ctx, cudaLaunchKernel(l.func, l.grid, l.block, args, l.smem, st));
+        }
+        first = false;
         if (prof) cudaEventRecord(s->ev[1], st);
     }
     return MF_OK;
@@ -1030,30 +1063,18 @@ static int forward_common(mf_ctx *ctx, Wav2LipState *s, const void *in0, const v
     if (io_changed) patch_io(pl, in0, in1, out_u8, out_f32);
     s->last_launches = (int)pl->launches.size();
     if (!s->use_graph || s->profile) return launch_direct(ctx, s, pl->launches, st);
-    if (!pl->exec) {
-        MF_CUDA(ctx, cudaGraphCreate(&pl->graph, 0));
-        cudaGraphNode_t prev = nullptr;
-        pl->nodes.resize(pl->launches.size());
-        for (size_t i = 0; i < pl->launches.size(); i++) {
-            Launch &l = pl->launches[i];
-            cudaKernelNodeParams kp;
-            memset(&kp, 0, sizeof(kp));
-            void *args[] = {l.params.data()};
-            kp.func = l.func; kp.gridDim = l.grid; kp.blockDim = l.block; kp.sharedMemBytes = (unsigned)l.smem; kp.kernelParams = args;
-            MF_CUDA(ctx, cudaGraphAddKernelNode(&pl->nodes[i], pl->graph, prev ? &prev : nullptr, prev ? 1 : 0, &kp));
-            prev = pl->nodes[i];
-        }
+    if (!pl->exec || io_changed) {
+        // (re)build the graph by capturing the launch list on a private stream: capture keeps the programmatic-dependency
+        // edges of the PDL launches.  Caller pointers change rarely (the plugins reuse their staging buffers).
+        if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
+        if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
+        if (!s->capture_stream) MF_CUDA(ctx, cudaStreamCreateWithFlags(&s->capture_stream, cudaStreamNonBlocking));
+        MF_CUDA(ctx, cudaStreamBeginCapture(s->capture_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = launch_direct(ctx, s, pl->launches, s->capture_stream, s->use_pdl);
+        cudaError_t ce = cudaStreamEndCapture(s->capture_stream, &pl->graph);
+        if (rc) { if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; } return rc; }
+        MF_CUDA(ctx, ce);
         MF_CUDA(ctx, cudaGraphInstantiate(&pl->exec, pl->graph, 0));
-    } else if (io_changed) {
-        for (size_t i = 0; i < pl->launches.size(); i++) {
-            Launch &l = pl->launches[i];
-            if (l.io == IO_NONE) continue;
-            cudaKernelNodeParams kp;
-            memset(&kp, 0, sizeof(kp));
-            void *args[] = {l.params.data()};
-            kp.func = l.func; kp.gridDim = l.grid; kp.blockDim = l.block; kp.sharedMemBytes = (unsigned)l.smem; kp.kernelParams = args;
-            MF_CUDA(ctx, cudaGraphExecKernelNodeSetParams(pl->exec, pl->nodes[i], &kp));
-        }
     }
     MF_CUDA(ctx, cudaGraphLaunch(pl->exec, st));
     return MF_OK;

@@ -25,10 +25,16 @@ SHAPES = [  # (name, cin, cout, H, k, B, ups)
     ("unet 1280->1280 @8", 1280, 1280, 8, 3, 16, 0),
     ("unet 2560->1280 @8", 2560, 1280, 8, 3, 16, 0),
     ("unet lin 1280->1280 @8 (1x1)", 1280, 1280, 8, 1, 16, 0),
+    ("unet lin 320->320 @32 (1x1)", 320, 320, 32, 1, 16, 0),
+    ("unet lin 640->640 @16 (1x1)", 640, 640, 16, 1, 16, 0),
+    ("unet 1280->1280 @4", 1280, 1280, 4, 3, 16, 0),
+    ("w2l 512->512 @1 (1x1)", 512, 512, 1, 1, 16, 0),
+    ("w2l 512->512 @3", 512, 512, 3, 3, 16, 0),
     ("w2l 64->64 @96", 64, 64, 96, 3, 16, 0),
     ("w2l 128->128 @48", 128, 128, 48, 3, 16, 0),
 ]
 modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["0"])]
+forces = os.environ.get("FORCES", "").split(";") if os.environ.get("FORCES") else [None]   # e.g. FORCES="256,1;128,2;64,1"
 only = sys.argv[2] if len(sys.argv) > 2 else None
 g = torch.Generator().manual_seed(0)
 for name, cin, cout, H, k, B, ups in SHAPES:
@@ -36,8 +42,10 @@ for name, cin, cout, H, k, B, ups in SHAPES:
         continue
     w = (torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)).numpy()
     row = []
-    for mode in modes:
+    for mode, force in [(m, f) for m in modes for f in forces]:
         os.environ["MF_CONV_DBG"] = str(mode)
+        if force:
+            os.environ["MF_CONV_FORCE"] = force
         pb = ProgramBuilder(B)
         a, b = pb.buffer(H, H, cin), pb.buffer(H << ups, H << ups, cout)
         pb.conv(a, 0, b, 0, w, np.zeros(cout, np.float32), padding=k // 2, relu=False, ups=ups)
@@ -53,6 +61,6 @@ for name, cin, cout, H, k, B, ups in SHAPES:
             ms.append(v.value)
         t = float(np.median(ms[2:]))
         fl = pb.flops_per_sample * B
-        row.append(f"m{mode}: {t * 1e3:8.1f} us {fl / t / 1e9:7.1f} TF/s")
+        row.append(f"m{mode}{'[' + force + ']' if force else ''}: {t * 1e3:8.1f} us {fl / t / 1e9:7.1f} TF/s")
         del net
     print(f"{name:34s} " + " | ".join(row), flush=True)
