@@ -61,6 +61,47 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
+// ---- cta_group::2 (CTA pair) helpers: PTX forms as in cute/arch/copy_sm100_tma.hpp, mma_sm100_umma.hpp, cutlass/arch/barrier.h ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// the pair leader's copy of a barrier: shared::cluster address of CTA rank 0 = own shared::cta address with the peer bit cleared
+#define CT_PEER_BIT_MASK 0xFEFFFFFFu
+__device__ __forceinline__ void tma_load_4d_2sm(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & CT_PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive on CTA rank 0's copy of `bar`
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote) : "memory");
+}
+
 // scale/shift -> (+residual) -> activation -> bf16, 16 channels of one pixel
 __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[16], int n0, size_t opix) {
     {
@@ -113,11 +154,30 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
     op[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile: each CTA stages
+// its own 128-row A tile and HALF of the B tile, the leader issues UMMA 256 x BN x 16 for both, each CTA keeps its 128 rows of the
+// accumulator in its own TMEM and runs its own epilogue.  Per CTA and k-block that is 16 KB + BN * 64 B of TMA ingest and shared-
+// memory operand reads instead of 16 KB + BN * 128 B -- the measured bound of the CG = 1 kernel.
+// the epilogue is done with accumulator `acc`: CG 1 every thread arrives (count 256); CG 2 one elected thread per CTA arrives on
+// the leader's barrier (count 2), after all 256 epilogue threads of this CTA have finished their TMEM loads
+#define CT_RELEASE_ACC()                                                  \
+    do {                                                                  \
+        tc_fence_before();                                                \
+        if (CG == 2) {                                                    \
+            epi_bar_sync();                                               \
+            if (threadIdx.x == 0) mbar_arrive_leader(&tempty[acc]);       \
+        } else {                                                          \
+            mbar_arrive(&tempty[acc]);                                    \
+        }                                                                 \
+    } while (0)
+
+template <int CG>
 __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constant__ ConvTmaParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int ST = p.stages;
-    const uint32_t B_STAGE = (uint32_t)p.BN * 128u;
+    const uint32_t B_STAGE = (uint32_t)p.BN * (128u / CG);   // this CTA's share of the B tile
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
     unsigned char *sA = smem;
     unsigned char *sB = smem + ST * A_STAGE_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)ST * B_STAGE);
@@ -133,53 +193,73 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 256);
+            mbar_init(&tempty[i], CG == 2 ? 2 : 256);   // CG 2: one elected arrival per CTA of the pair, on the leader's copy
         }
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    if (warp == 4) {
+        if (CG == 2) tmem_alloc_2sm(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything can signal them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch();
     pdl_wait();   // barrier init, TMEM allocation and descriptor fetch above overlap the predecessor's tail
-    const int total = p.total_items;
+    const int total = p.total_items;            // work items of a CTA (CG 1) or of a CTA pair (CG 2)
     const int per_tile = p.n_tiles * p.splits;
+    const int item0 = blockIdx.x / CG, item_step = gridDim.x / CG;
 
     if (warp == 5) {
         // =========================== TMA producer ==============================================
         if (lane == 0) {
             tma_prefetch_desc(&p.amap);
             tma_prefetch_desc(&p.wmap);
-            uint32_t it = 0;
-            for (int item = blockIdx.x; item < total; item += gridDim.x) {
-                const int mt = item / per_tile, rem = item - mt * per_tile;
+            int s = 0;
+            uint32_t ph = 1;   // parity to wait for on empty[s]: a fresh barrier passes a wait on parity 1 (first lap = free)
+            for (int item = item0; item < total; item += item_step) {
+                const int mp = item / per_tile, rem = item - mp * per_tile;
+                const int mt = mp * CG + (int)cta_rank;   // an m-tile past the end is all out-of-bounds: TMA zero-fills it
                 const int nt = rem / p.splits, sp = rem - nt * p.splits;
                 const int txi = mt % p.tiles_x, tyi = (mt / p.tiles_x) % p.tiles_y, tbi = mt / (p.tiles_x * p.tiles_y);
                 const int x0 = txi << p.lTW, y0 = tyi << p.lTH, b0 = tbi << (7 - p.lTW - p.lTH);
                 const int kb0 = (int)((long long)sp * p.nkb / p.splits), kb1 = (int)((long long)(sp + 1) * p.nkb / p.splits);
                 int tap = kb0 / p.cblocks, cb = kb0 - tap * p.cblocks;
-                for (int kb = kb0; kb < kb1; kb++, it++) {
-                    const int s = it % ST;
-                    if (it >= (uint32_t)ST) mbar_wait(&empty[s], ((it / ST) - 1) & 1);
-                    mbar_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE);
-                    if (!(p.dbg & 1))
-                        tma_load_4d(sA + s * A_STAGE_BYTES, &p.amap, p.in_coff + cb * CONV_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0, &full[s]);
-                    else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"((uint32_t)A_STAGE_BYTES) : "memory");
-                    if (!(p.dbg & 2))
-                        tma_load_4d(sB + (size_t)s * B_STAGE, &p.wmap, 0, 0, kb, (nt * p.BN) >> 4, &full[s]);
-                    else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"(B_STAGE) : "memory");
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&empty[s], ph);
+                    if (CG == 2) {
+                        // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
+                        if (cta_rank == 0) mbar_expect_tx(&full[s], 2 * (A_STAGE_BYTES + B_STAGE));
+                        tma_load_4d_2sm(sA + s * A_STAGE_BYTES, &p.amap, p.in_coff + cb * CONV_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0, &full[s]);
+                        tma_load_4d_2sm(sB + (size_t)s * B_STAGE, &p.wmap, 0, 0, kb, (nt * p.BN + (int)cta_rank * (p.BN >> 1)) >> 4, &full[s]);
+                    } else {
+                        mbar_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE);
+                        if (!(p.dbg & 1))
+                            tma_load_4d(sA + s * A_STAGE_BYTES, &p.amap, p.in_coff + cb * CONV_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0, &full[s]);
+                        else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"((uint32_t)A_STAGE_BYTES) : "memory");
+                        if (!(p.dbg & 2))
+                            tma_load_4d(sB + (size_t)s * B_STAGE, &p.wmap, 0, 0, kb, (nt * p.BN) >> 4, &full[s]);
+                        else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"(B_STAGE) : "memory");
+                    }
                     if (++cb == p.cblocks) { cb = 0; tap++; }
+                    if (++s == ST) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 4) {
         // =========================== MMA issuer ================================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(CONV_BM, p.BN);
-            uint32_t it = 0, n = 0;
-            for (int item = blockIdx.x; item < total; item += gridDim.x, n++) {
+        if (lane == 0 && cta_rank == 0) {
+            // the issue loop runs on ONE thread: every instruction in it delays the next UMMA (at BN = 128 a k-block of four
+            // 128x128x16 UMMAs is only 256 tensor cycles), so no division / modulo / descriptor rebuild per k-block
+            const uint32_t idesc = make_idesc(CONV_BM * CG, p.BN);
+            const uint64_t adesc0 = make_sdesc(smem_u32(sA)), bdesc0 = make_sdesc(smem_u32(sB));
+            const uint32_t a_step = A_STAGE_BYTES >> 4, b_step = B_STAGE >> 4;   // descriptor start-address units of 16 B
+            int s = 0;
+            uint32_t ph = 0, n = 0;
+            uint64_t adesc = adesc0, bdesc = bdesc0;
+            for (int item = item0; item < total; item += item_step, n++) {
                 const int rem = item % per_tile;
                 const int sp = rem % p.splits;
                 const int kb0 = (int)((long long)sp * p.nkb / p.splits), kb1 = (int)((long long)(sp + 1) * p.nkb / p.splits);
@@ -187,18 +267,30 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                 if (n >= 2) mbar_wait(&tempty[acc], ((n >> 1) - 1) & 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * CT_ACC_STRIDE;
-                for (int kb = kb0; kb < kb1; kb++, it++) {
-                    const int s = it % ST;
-                    mbar_wait(&full[s], (it / ST) & 1);
+                uint32_t accum = 0;
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint64_t adesc = make_sdesc(smem_u32(sA + s * A_STAGE_BYTES));
-                    const uint64_t bdesc = make_sdesc(smem_u32(sB + (size_t)s * B_STAGE));
-#pragma unroll
-                    for (int k = 0; k < CONV_BK / 16; k++)
-                        if (!(p.dbg & 4)) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0) || (k != 0));
-                    umma_commit(&empty[s]);
+                    if (CG == 2) {
+                        umma_f16_2sm(d_tmem, adesc, bdesc, idesc, accum);
+                        umma_f16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                        umma_f16_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                        umma_f16_2sm(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                        umma_commit_2sm(&empty[s]);
+                    } else {
+                        if (!(p.dbg & 4)) {
+                            umma_f16(d_tmem, adesc, bdesc, idesc, accum);
+                            umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                            umma_f16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                            umma_f16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                        }
+                        umma_commit(&empty[s]);
+                    }
+                    accum = 1;
+                    adesc += a_step; bdesc += b_step;
+                    if (++s == ST) { s = 0; ph ^= 1; adesc = adesc0; bdesc = bdesc0; }
                 }
-                umma_commit(&tfull[acc]);
+                if (CG == 2) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);
             }
         }
     } else {
@@ -212,8 +304,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
         const bool leader = threadIdx.x == 0;
         const int TWm = (1 << p.lTW) - 1, THm = (1 << p.lTH) - 1;
         uint32_t n = 0;
-        for (int item = blockIdx.x; item < total; item += gridDim.x, n++) {
-            const int mt = item / per_tile, rem = item - mt * per_tile;
+        for (int item = item0; item < total; item += item_step, n++) {
+            const int mp = item / per_tile, rem = item - mp * per_tile;
+            const int mt = mp * CG + (int)cta_rank;
             const int nt = rem / p.splits, sp = rem - nt * p.splits;
             const int txi = mt % p.tiles_x, tyi = (mt / p.tiles_x) % p.tiles_y, tbi = mt / (p.tiles_x * p.tiles_y);
             const int mx = (txi << p.lTW) + (r & TWm), my = (tyi << p.lTH) + ((r >> p.lTW) & THm);
@@ -230,8 +323,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                 uint32_t v[16];
                 tmem_ld16_nowait(taddr, v);
                 tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&tempty[acc]);
+                CT_RELEASE_ACC();
                 if (row_ok && half == 0) {
                     for (int j = 0; j < p.Cout; j++) {
                         const float a = fmaf(__uint_as_float(v[j]), __ldg(p.scale + j), __ldg(p.shift + j));
@@ -267,8 +359,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                         ct_finish16(p, f, n_base + c0 + 16, opix);
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(&tempty[acc]);
+                CT_RELEASE_ACC();
             } else {
                 // split-K: dump the fp32 partial, then the last-arriving split reduces in split order
                 float *wtile = p.ws + ((size_t)(mt * p.n_tiles + nt) * p.splits) * (128 * (size_t)p.BN);
@@ -283,8 +374,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                     for (int j = 0; j < 4; j++)
                         d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 }
-                tc_fence_before();
-                mbar_arrive(&tempty[acc]);
+                CT_RELEASE_ACC();
                 __threadfence();
                 epi_bar_sync();
                 if (leader) *last_flag = atomicAdd(p.counters + mt * p.n_tiles + nt, 1u) == (unsigned)(p.splits - 1);
@@ -331,6 +421,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
     }
     __syncwarp();
     tc_fence_before();
-    __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 512);
+    if (CG == 2) cluster_sync_all();   // the peer may still signal this CTA's barriers / read its operands until it is done too
+    else __syncthreads();
+    if (warp == 4) {
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
 }

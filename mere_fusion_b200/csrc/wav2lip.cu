@@ -386,6 +386,7 @@ struct Launch {
     dim3 grid, block;
     int smem = 0;
     int io = IO_NONE;
+    int cluster = 1;  // thread-block cluster size (k_conv_tma<2>: CTA pairs)
     int op = -1;  // program op index (conv ops: profiling hook), -1 for helper kernels
     size_t ws_bytes = 0;  // k_conv_tma split-K: workspace / counter requirement (patched in by finish_launch_list)
     int ws_counters = 0;
@@ -674,6 +675,8 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
 
 
 // ---- k_conv_tma planning: tile box, BN, split-K, ring depth -------------------------------------------
+static bool is_conv_tma(const void *f) { return f == (void *)k_conv_tma<1> || f == (void *)k_conv_tma<2>; }
+
 static bool conv_tma_eligible(const W2LOp &o) {
     static int on = -1;
     if (on < 0) { const char *e = getenv("MF_CONV_TMA"); on = e ? atoi(e) : 1; }
@@ -731,10 +734,15 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
             fprintf(stderr, "[conv_tma] op %d Cin %d Cout %d taps %d M %dx%dx%d: tile %dx%dx%d, m_tiles %d, BN %d, splits %d, nkb %d\n", i, o.Cin,
                     o.Cout, o.ntaps, B, o.Mh, o.Mw, TW, TH, TB, m_tiles, BN, S, nkb);
     }
+    // BN of a CTA pair must split into two halves of whole 16-row weight pieces
+    // CTA pairs (cta_group::2) for the layers with enough 128-row tiles to fill the SM pairs: halves the per-CTA B traffic
+    int CG = (m_tiles >= sms && BN % 32 == 0 && o.mode == 0) ? 2 : 1;
+    { const char *e = getenv("MF_CONV_CG"); if (e && atoi(e) == 1) CG = 1; if (e && atoi(e) == 2 && BN % 32 == 0 && m_tiles >= 2) CG = 2; }
     p.BN = BN; p.n_tiles = (o.Cout + BN - 1) / BN; p.splits = S;
-    const int stage = A_STAGE_BYTES + BN * 128;
+    const int stage = A_STAGE_BYTES + BN * 128 / CG;
     p.stages = std::min(CT_MAX_STAGES, (CT_SMEM_LIMIT - 1024 - 256) / stage);
-    p.total_items = m_tiles * p.n_tiles * S;
+    const int m_groups = (m_tiles + CG - 1) / CG;          // work items are 128-row tiles (CG 1) or 256-row tile pairs (CG 2)
+    p.total_items = m_groups * p.n_tiles * S;
     p.out = cp.out; p.res = cp.res; p.scale = cp.scale; p.shift = cp.shift;
     p.out_stride = cp.out_stride; p.out_coff = cp.out_coff; p.Hout = cp.Hout; p.Wout = cp.Wout;
     p.res_stride = cp.res_stride; p.res_coff = cp.res_coff;
@@ -763,7 +771,7 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
         MF_REQUIRE(ctx, we, "op %d: weight entry missing", i);
         cuuint64_t dims[4] = {CONV_BK, 16, (cuuint64_t)(o.Kpad / CONV_BK), (cuuint64_t)(o.Cout_pad / 16)};
         cuuint64_t strides[3] = {CONV_BK * 2, 16 * CONV_BK * 2, (cuuint64_t)(o.Kpad / CONV_BK) * 16 * CONV_BK * 2};
-        cuuint32_t box[4] = {CONV_BK, 16, 1, (cuuint32_t)(BN / 16)};
+        cuuint32_t box[4] = {CONV_BK, 16, 1, (cuuint32_t)(BN / 16 / CG)};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult cr = s->encode(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)(s->blob + we->offset), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -772,16 +780,19 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
     }
     static bool attr_set = false;
     if (!attr_set) {
-        MF_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_LIMIT));
+        MF_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_LIMIT));
+        MF_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_LIMIT));
         attr_set = true;
     }
     Launch l;
-    l.func = (void *)k_conv_tma; l.grid = dim3(std::min(p.total_items, sms)); l.block = dim3(CT_THREADS);
+    l.func = CG == 2 ? (void *)k_conv_tma<2> : (void *)k_conv_tma<1>;
+    l.cluster = CG;
+    l.grid = dim3(CG * std::min(p.total_items, sms / CG)); l.block = dim3(CT_THREADS);
     p.mode = o.mode;
     l.smem = p.stages * stage + 256 + 1024; l.op = i; l.io = o.mode != 0 ? IO_OUT : IO_NONE;
     if (S > 1) {
-        l.ws_bytes = (size_t)m_tiles * p.n_tiles * S * 128 * BN * sizeof(float);
-        l.ws_counters = m_tiles * p.n_tiles;
+        l.ws_bytes = (size_t)m_groups * CG * p.n_tiles * S * 128 * BN * sizeof(float);
+        l.ws_counters = m_groups * CG * p.n_tiles;
     }
     l.set(p);
     L.push_back(std::move(l));
@@ -809,7 +820,7 @@ static int finish_launch_list(mf_ctx *ctx, std::vector<Launch> &L, float **ws, u
         *n_counters = nc;
     }
     for (auto &l : L)
-        if (l.func == (void *)k_conv_tma) { l.as<ConvTmaParams>().ws = *ws; l.as<ConvTmaParams>().counters = *counters; }
+        if (is_conv_tma(l.func)) { l.as<ConvTmaParams>().ws = *ws; l.as<ConvTmaParams>().counters = *counters; }
     return MF_OK;
 }
 
@@ -1000,7 +1011,7 @@ static void patch_io(Wav2LipState::Plan *pl, const void *in0, const void *in1, v
     for (auto &l : pl->launches) {
         if (l.io == IO_IN0) l.as<PrepParams>().src = in0;
         else if (l.io == IO_IN1) l.as<PrepParams>().src = in1;
-        else if (l.io == IO_OUT && l.func == (void *)k_conv_tma) { l.as<ConvTmaParams>().out = out_u8; l.as<ConvTmaParams>().out_f32 = out_f32; }
+        else if (l.io == IO_OUT && is_conv_tma(l.func)) { l.as<ConvTmaParams>().out = out_u8; l.as<ConvTmaParams>().out_f32 = out_f32; }
         else if (l.io == IO_OUT) { l.as<ConvParams>().out = out_u8; l.as<ConvParams>().out_f32 = out_f32; }
         else if (l.io == IO_WH_FRAMES || l.io == IO_WH_FINISH) {
             WhisperPrep &w = l.as<WhisperPrep>();
@@ -1022,17 +1033,26 @@ static int launch_direct(mf_ctx *ctx, Wav2LipState *s, std::vector<Launch> &L, c
         const bool prof = s->profile && l.op >= 0 && l.op == s->profile_op;
         if (prof && !started) { cudaEventRecord(s->ev[0], st); started = true; }
         void *args[] = {l.params.data()};
-        if (pdl && !first) {
+        if ((pdl && !first) || l.cluster > 1) {
             // programmatic dependent launch: this kernel's CTA-local prologue may overlap the predecessor's tail; every executor
-            // kernel calls griddepcontrol.wait before its first global access
+            // kernel calls griddepcontrol.wait before its first global access.  CTA pairs are launched as clusters of 2.
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
             cfg.gridDim = l.grid; cfg.blockDim = l.block; cfg.dynamicSmemBytes = (size_t)l.smem; cfg.stream = st;
-            cudaLaunchAttribute at;
-            memset(&at, 0, sizeof(at));
-            at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at.val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = &at; cfg.numAttrs = 1;
+            cudaLaunchAttribute at[2];
+            memset(at, 0, sizeof(at));
+            int na = 0;
+            if (pdl && !first) {
+                at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[na].val.programmaticStreamSerializationAllowed = 1;
+                na++;
+            }
+            if (l.cluster > 1) {
+                at[na].id = cudaLaunchAttributeClusterDimension;
+                at[na].val.clusterDim.x = (unsigned)l.cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+                na++;
+            }
+            cfg.attrs = at; cfg.numAttrs = (unsigned)na;
             MF_CUDA(ctx, cudaLaunchKernelExC(&cfg, l.func, args));
         } else {
             MF_CUDA(ctx, cudaLaunchKernel(l.func, l.grid, l.block, args, l.smem, st));
