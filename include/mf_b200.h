@@ -237,6 +237,18 @@ int mf_paste_resize_u8(mf_ctx *ctx, const uint8_t *frames, int n_frames, int H, 
                        int S, int B, const int32_t *idx_bbox_host, uint8_t *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Wav2Lip mel front-end: replaces audio.melspectrogram (wav2lip/audio.py:45-51: preemphasis, STFT n_fft 800 /
+ * hop 200 / Hann, 80-band mel 55-7600 Hz, 20 log10 - 20, clip(8 (S + 100) / 100 - 4, +-4)) and the chunk slicing
+ * of LipASR.run_step (lipasr.py:24-35) for one window.
+ *   audio          : device fp32 [n_samples] (the l + 2B + r chunk window, 16 kHz)
+ *   filters        : device fp32 [80][401], the mel basis (mere_fusion_b200.audio_mel.mel_filterbank())
+ *   start_idx_host : HOST int32 [B] first mel column of each chunk (lipasr.py:29-33, tail clamp included)
+ *   out            : device fp32 [B,1,80,16], what mf_wav2lip_forward takes as `mel`
+ * ------------------------------------------------------------------------------------------ */
+int mf_wav2lip_mel_chunks(mf_ctx *ctx, const float *audio, int n_samples, const float *filters,
+                          const int32_t *start_idx_host, int B, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * MuseTalk paste-back (musereal.py:229-250 -> musetalk/utils/blending.py:103-125 get_image_blending):
  * faces[i] is resized (cv2.resize, bit-exact) into its bbox inside a copy of the body crop, then
  *   body[ys:ye, xs:xe] = cv2.blendLinear(face_large, body_crop, m, 1 - m),  m = gray(mask) / 255

@@ -29,6 +29,7 @@ extern "C" void mf_destroy(mf_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ernerf_destroy(ctx);
     wav2lip_destroy(ctx);
+    cudaFree(ctx->mel_scratch);
     delete ctx;
 }
 

@@ -21,6 +21,8 @@ struct mf_ctx {
     char err[512] = {0};
     ErnerfState *ernerf = nullptr;
     Wav2LipState *wav2lip = nullptr;
+    float *mel_scratch = nullptr;   // Wav2Lip mel front-end: [frames][80] fp32
+    int mel_frames_cap = 0;
 };
 
 static inline int mf_fail(mf_ctx *ctx, int code, const char *fmt, ...) {

@@ -182,3 +182,93 @@ extern "C" int mf_paste_blend_u8(mf_ctx *ctx, const uint8_t *frames, int n_frame
     MF_CUDA(ctx, cudaGetLastError());
     return MF_OK;
 }
+
+// =====================================================================================================
+// Wav2Lip mel front-end on the GPU: replaces audio.melspectrogram (wav2lip/audio.py:45-51 with :20-23 preemphasis,
+// :57-61 librosa.stft n_fft 800 / hop 200 / Hann, :92-122 mel basis 80 x 401 (55-7600 Hz), amp_to_db, normalize) and the chunk
+// slicing of LipASR.run_step (lipasr.py:24-35) for one l + 2B + r window: float audio in, [B,1,80,16] mel chunks out, in
+// the layout mf_wav2lip_forward consumes.  Direct 800-point DFT per frame (84 frames per window: 27 MMAC).
+// librosa >= 0.10 semantics (centre padding with zeros), like mere_fusion_b200/audio_mel.py: PARITY UNPINNED.
+// =====================================================================================================
+#define WM_NFFT 800
+#define WM_HOP 200
+#define WM_BINS 401
+#define WM_MELS 80
+
+struct W2lMelParams {
+    const float *audio;      // device fp32 [n_samples]
+    const float *filters;    // device fp32 [80][401]
+    float *mel;              // scratch [n_frames][80]
+    float *out;              // [B][1][80][16]
+    int n_samples, n_frames, B;
+    int start[PASTE_MAX_BATCH];
+};
+
+__global__ void __launch_bounds__(256) k_w2l_mel_frames(const __grid_constant__ W2lMelParams p) {
+    __shared__ float xs[WM_NFFT], ct[WM_NFFT], st[WM_NFFT], mag[WM_BINS + 3];
+    const int t = blockIdx.x;
+    for (int i = threadIdx.x; i < WM_NFFT; i += blockDim.x) {
+        float sn, cs;
+        sincospif((float)i / 400.0f, &sn, &cs);   // 2 pi i / 800
+        ct[i] = cs; st[i] = sn;
+        const int src = t * WM_HOP + i - WM_NFFT / 2;   // centred frame, zero padding
+        float v = 0.f;
+        if (src >= 0 && src < p.n_samples) v = p.audio[src] - (src > 0 ? 0.97f * p.audio[src - 1] : 0.f);   // lfilter([1, -0.97], [1], wav)
+        xs[i] = v * (0.5f - 0.5f * cs);           // periodic Hann(800)
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < WM_BINS; k += blockDim.x) {
+        float re = 0.f, im = 0.f;
+        int idx = 0;
+        for (int n = 0; n < WM_NFFT; n++) {
+            re = fmaf(xs[n], ct[idx], re);
+            im = fmaf(xs[n], st[idx], im);
+            idx += k;
+            if (idx >= WM_NFFT) idx -= WM_NFFT;
+        }
+        mag[k] = sqrtf(re * re + im * im);
+    }
+    __syncthreads();
+    if (threadIdx.x < WM_MELS) {
+        const float *f = p.filters + threadIdx.x * WM_BINS;
+        float acc = 0.f;
+        for (int k = 0; k < WM_BINS; k++) acc = fmaf(__ldg(f + k), mag[k], acc);
+        const float db = 20.0f * log10f(fmaxf(1e-5f, acc)) - 20.0f;                       // _amp_to_db - ref_level_db
+        p.mel[t * WM_MELS + threadIdx.x] = fminf(fmaxf(8.0f * ((db + 100.0f) / 100.0f) - 4.0f, -4.0f), 4.0f);   // _normalize
+    }
+}
+__global__ void __launch_bounds__(256) k_w2l_mel_chunks(const __grid_constant__ W2lMelParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.B * WM_MELS * 16) return;
+    const int c = i & 15, m = (i >> 4) % WM_MELS, b = i / (16 * WM_MELS);
+    p.out[i] = p.mel[(p.start[b] + c) * WM_MELS + m];
+}
+
+extern "C" int mf_wav2lip_mel_chunks(mf_ctx *ctx, const float *audio, int n_samples, const float *filters, const int32_t *start_idx_host,
+                                     int B, float *out, void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    MF_REQUIRE(ctx, audio && filters && start_idx_host && out, "mf_wav2lip_mel_chunks: null pointer");
+    MF_REQUIRE(ctx, n_samples >= 1 && n_samples <= 16000 * 60 && B >= 1 && B <= PASTE_MAX_BATCH, "mf_wav2lip_mel_chunks: bad sizes");
+    W2lMelParams p;
+    p.audio = audio; p.filters = filters; p.out = out; p.n_samples = n_samples; p.B = B;
+    p.n_frames = n_samples / WM_HOP + 1;
+    for (int i = 0; i < B; i++) {
+        MF_REQUIRE(ctx, start_idx_host[i] >= 0 && start_idx_host[i] + 16 <= p.n_frames, "mf_wav2lip_mel_chunks: chunk %d starts at column %d of %d",
+                   i, start_idx_host[i], p.n_frames);
+        p.start[i] = start_idx_host[i];
+    }
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (p.n_frames > ctx->mel_frames_cap) {
+        MF_CUDA(ctx, cudaDeviceSynchronize());
+        cudaFree(ctx->mel_scratch);
+        ctx->mel_scratch = nullptr;
+        ctx->mel_frames_cap = 0;
+        MF_CUDA(ctx, cudaMalloc(&ctx->mel_scratch, (size_t)p.n_frames * WM_MELS * sizeof(float)));
+        ctx->mel_frames_cap = p.n_frames;
+    }
+    p.mel = ctx->mel_scratch;
+    k_w2l_mel_frames<<<p.n_frames, 256, 0, (cudaStream_t)stream>>>(p);
+    k_w2l_mel_chunks<<<(B * WM_MELS * 16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+    MF_CUDA(ctx, cudaGetLastError());
+    return MF_OK;
+}

@@ -15,8 +15,13 @@ class LipASR(BaseASR):
         if len(self.frames) <= self.stride_left_size + self.stride_right_size:
             return
         inputs = np.concatenate(self.frames)
-        mel = audio_mel.melspectrogram(inputs)
-        self.feat_queue.put(mel_chunks(mel, len(self.frames), self.stride_left_size, self.stride_right_size, self.fps))
+        fe = getattr(self.parent, "mel_front_end", None)
+        if fe is not None:
+            # mel + chunk slicing on the GPU: a cuda fp32 [B,1,80,16] tensor goes through feat_queue instead of B numpy chunks
+            self.feat_queue.put(fe.chunks(inputs, len(self.frames), self.stride_left_size, self.stride_right_size, self.fps))
+        else:
+            mel = audio_mel.melspectrogram(inputs)
+            self.feat_queue.put(mel_chunks(mel, len(self.frames), self.stride_left_size, self.stride_right_size, self.fps))
         self.frames = self.frames[-(self.stride_left_size + self.stride_right_size):]
 
 

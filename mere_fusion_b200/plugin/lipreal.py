@@ -66,7 +66,7 @@ class _Pasted:
 
 
 class LipReal(BaseReal):
-    def __init__(self, opt, engine=None, avatar=None, state_dict=None, device=0, paste="gpu"):
+    def __init__(self, opt, engine=None, avatar=None, state_dict=None, device=0, paste="gpu", mel="gpu"):
         super().__init__(opt)
         self.W = opt.W
         self.H = opt.H
@@ -84,6 +84,10 @@ class LipReal(BaseReal):
         self.engine = engine if engine is not None else self._load_engine(state_dict)
         self.paste = paste
         self._dev = None
+        self.mel_front_end = None
+        if mel == "gpu" and hasattr(self.engine, "ctx"):
+            from ..wav2lip import MelFrontEnd
+            self.mel_front_end = MelFrontEnd(self.engine)
         self.asr = LipASR(opt, self)
         self.asr.warm_up()
         self.render_event = Event()
@@ -138,8 +142,11 @@ class LipReal(BaseReal):
         B = self.batch_size
         length = len(self.face_list_cycle)
         idxs = [mirror_index(length, index + i) for i in range(B)]
-        d["mel_pin"].copy_(torch.from_numpy(np.asarray(mel_batch, dtype=np.float32).reshape(B, 1, 80, 16)))
-        d["mel"].copy_(d["mel_pin"], non_blocking=True)
+        if torch.is_tensor(mel_batch):                           # device-resident chunks from LipASR (GPU mel front-end)
+            d["mel"].copy_(mel_batch, non_blocking=True)
+        else:
+            d["mel_pin"].copy_(torch.from_numpy(np.asarray(mel_batch, dtype=np.float32).reshape(B, 1, 80, 16)))
+            d["mel"].copy_(d["mel_pin"], non_blocking=True)
         torch.index_select(d["faces"], 0, torch.as_tensor(idxs, device=d["faces"].device), out=d["sel"])
         self.engine.forward(d["mel"], d["sel"], out=d["pred"])
         if self.paste == "gpu":

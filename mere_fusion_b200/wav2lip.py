@@ -89,3 +89,51 @@ class Wav2LipEngine(ConvNet):
         out_pinned.copy_(st[2], non_blocking=True)
         return out_pinned
 
+
+
+class MelFrontEnd:
+    """Wav2Lip mel + chunk slicing on the GPU (mf_wav2lip_mel_chunks): replaces audio.melspectrogram + the slicing loop of
+    LipASR.run_step (wav2lip/audio.py:45-51, lipasr.py:24-35) for one window; the chunk start columns are the reference's
+    integer arithmetic, computed on the host."""
+
+    def __init__(self, engine):
+        from .audio_mel import mel_filterbank
+        self.ctx = engine.ctx
+        self.device = engine.device
+        self.filters = torch.from_numpy(np.ascontiguousarray(mel_filterbank(), np.float32)).to(self.device)
+        self._pin = None
+        self._h2d_done = None
+
+    @staticmethod
+    def chunk_starts(n_chunks, left_size, right_size, fps, n_cols):
+        """lipasr.py:24-35: chunk i starts at int(left * 80 / 50 + i * 160 / fps), clamped so that 16 columns fit"""
+        left = max(0, left_size * 80 / 50)
+        mult = 80. * 2 / fps
+        starts, i = [], 0
+        while i < (n_chunks - left_size - right_size) / 2:
+            s0 = int(left + i * mult)
+            starts.append(n_cols - 16 if s0 + 16 > n_cols else s0)
+            i += 1
+        return np.asarray(starts, np.int32)
+
+    def chunks(self, audio, n_chunks, left_size, right_size, fps):
+        """float32 waveform of the whole window -> cuda fp32 [B, 1, 80, 16]"""
+        a = np.ascontiguousarray(audio, np.float32)
+        if self._pin is None or self._pin.numel() < a.size:
+            self._pin = torch.empty(max(a.size, 16640), dtype=torch.float32).pin_memory()
+            self._dev = torch.empty(self._pin.numel(), dtype=torch.float32, device=self.device)
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()
+        self._pin[:a.size].copy_(torch.from_numpy(a))
+        d = self._dev[:a.size]
+        d.copy_(self._pin[:a.size], non_blocking=True)
+        if self._h2d_done is None:
+            self._h2d_done = torch.cuda.Event()
+        s = torch.cuda.current_stream(self.device)
+        self._h2d_done.record(s)
+        starts = self.chunk_starts(n_chunks, left_size, right_size, fps, a.size // 200 + 1)
+        out = torch.empty((len(starts), 1, 80, 16), dtype=torch.float32, device=self.device)
+        check(self.ctx.handle, lib().mf_wav2lip_mel_chunks(self.ctx.handle, _ptr(d), a.size, _ptr(self.filters),
+                                                           starts.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(starts), _ptr(out),
+                                                           ctypes.c_void_p(s.cuda_stream)), "mf_wav2lip_mel_chunks")
+        return out

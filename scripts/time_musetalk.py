@@ -21,7 +21,7 @@ for _ in range(3):
     eng.forward(lat, wh, out=out)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-n = 10
+n = int(os.environ.get('N_ITERS', '10'))
 e0.record()
 for _ in range(n):
     eng.forward(lat, wh, out=out)

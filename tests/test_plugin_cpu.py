@@ -12,6 +12,10 @@ import pytest
 from helpers import load_pose_fixture
 
 REF = "/root/reference"
+try:                                   # before any test stubs librosa (transformers probes for it at import time)
+    import transformers.audio_utils as _TU
+except Exception:                      # noqa: BLE001
+    _TU = None
 
 
 def _stub_module(name):
@@ -354,3 +358,30 @@ def test_blend_restatement_equals_cv2():
         a = blend_cv2(av.frame_list_cycle[i], face, av.coord_list_cycle[i], mask, av.mask_coords_list_cycle[i])
         b = blend_numpy(av.frame_list_cycle[i], face, av.coord_list_cycle[i], mask, av.mask_coords_list_cycle[i])
         assert np.array_equal(a, b)
+
+
+def test_mel_front_end_against_independent_librosa_compatible_implementation():
+    """librosa itself is absent (requirements.txt:6, unpinned), so the restatement in audio_mel.py is cross-checked against an
+    independent implementation written to reproduce librosa (transformers.audio_utils: slaney mel filterbank, centred STFT
+    with constant padding, periodic Hann): filterbanks to 1e-8, STFT magnitudes to 1e-5 relative, the whole melspectrogram to
+    1e-4.  Not the reference's own output (none exists offline) -- DESIGN.md keeps the row "parity unpinned"."""
+    if _TU is None:
+        pytest.skip("transformers.audio_utils not importable")
+    tu = _TU
+    from mere_fusion_b200 import audio_mel
+    from mere_fusion_b200.whisper_pack import whisper_filters
+    fb = tu.mel_filter_bank(num_frequency_bins=401, num_mel_filters=80, min_frequency=55, max_frequency=7600, sampling_rate=16000,
+                            norm="slaney", mel_scale="slaney")
+    assert np.abs(fb.T - audio_mel.mel_filterbank()).max() < 1e-8
+    fbw = tu.mel_filter_bank(num_frequency_bins=201, num_mel_filters=80, min_frequency=0, max_frequency=8000, sampling_rate=16000,
+                             norm="slaney", mel_scale="slaney")
+    assert np.abs(fbw.T - whisper_filters()).max() < 1e-8
+    wav = clip_10s()[:16640]
+    pre = np.append(wav[0], wav[1:] - 0.97 * wav[:-1]).astype(np.float64)            # lfilter([1, -0.97], [1], wav)
+    S = tu.spectrogram(pre, tu.window_function(800, "hann"), frame_length=800, hop_length=200, fft_length=800, power=1.0,
+                       center=True, pad_mode="constant")
+    D = np.abs(audio_mel.stft(pre))
+    assert S.shape == D.shape == (401, 84) and np.abs(S - D).max() < 1e-5 * np.abs(D).max()
+    mel_ref = 20 * np.log10(np.maximum(np.exp(-100 / 20 * np.log(10)), fb.T @ S)) - 20
+    mel_ref = np.clip(8.0 * ((mel_ref + 100) / 100) - 4.0, -4.0, 4.0)
+    assert np.abs(audio_mel.melspectrogram(wav) - mel_ref).max() < 1e-4

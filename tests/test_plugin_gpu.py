@@ -200,3 +200,28 @@ def test_musereal_end_to_end_gpu_blend_equals_cpu_blend():
         assert np.array_equal(f[outside], base[outside])
         changed += int(not np.array_equal(f, base))
     assert changed >= 55
+
+
+def test_wav2lip_mel_front_end_gpu_vs_host():
+    """mf_wav2lip_mel_chunks (preemphasis + 800-point DFT + mel + dB + normalise + chunk slicing on the GPU) against the numpy
+    restatement + the reference's slicing loop (audio_mel.melspectrogram, lipasr.mel_chunks); also the tail clamp"""
+    from mere_fusion_b200 import audio_mel
+    from mere_fusion_b200.plugin.lipasr import mel_chunks
+    from mere_fusion_b200.wav2lip import ConvNet, MelFrontEnd
+    from mere_fusion_b200.convnet_pack import ProgramBuilder
+    pb = ProgramBuilder(1)
+    a, b = pb.buffer(4, 4, 64), pb.buffer(4, 4, 64)
+    pb.conv(a, 0, b, 0, np.zeros((64, 64, 1, 1), np.float32))
+    fe = MelFrontEnd(ConvNet(pb.finish(), max_batch=1))          # any loaded context will do
+    wav = clip_10s()
+    for n_chunks, B in ((52, 16), (36, 8), (22, 1)):
+        audio = wav[3000:3000 + n_chunks * 320]
+        got = fe.chunks(audio, n_chunks, 10, 10, 50).cpu().numpy()
+        mel = audio_mel.melspectrogram(audio)
+        ref = np.stack(mel_chunks(mel, n_chunks, 10, 10, 50)).astype(np.float32)[:, None]
+        assert got.shape == ref.shape == (B, 1, 80, 16)
+        assert np.abs(got - ref).max() < 5e-3, np.abs(got - ref).max()
+    # a window whose last chunk would run past the mel: clamped to the last 16 columns (lipasr.py:31-32)
+    starts = MelFrontEnd.chunk_starts(52, 10, 10, 50, 60)
+    assert starts.max() == 60 - 16 and len(starts) == 16
+    assert list(MelFrontEnd.chunk_starts(52, 10, 10, 50, 84)[:4]) == [16, 19, 22, 25]
