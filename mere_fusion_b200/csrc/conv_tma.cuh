@@ -102,21 +102,23 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive 
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote) : "memory");
 }
 
-// scale/shift -> (+residual) -> activation -> bf16, 16 channels of one pixel
-__device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[16], int n0, size_t opix) {
+// scale/shift (staged in shared memory per tile: cs = scale[256] | shift[256], indexed by the column inside the tile) ->
+// (+residual, already loaded: r0 | r1 = 16 bf16) -> activation -> bf16, 16 channels of one pixel
+__device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[16], const float *cs, int c, int n0, size_t opix,
+                                            const uint4 &r0, const uint4 &r1) {
     {
-        const float4 *sh = reinterpret_cast<const float4 *>(p.shift + n0);
+        const float4 *sh = reinterpret_cast<const float4 *>(cs + 256 + c);
         if (p.flags & 2) {   // every scale is 1 (no folded BatchNorm): bias only
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float4 t = __ldg(sh + j);
+                const float4 t = sh[j];
                 f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
             }
         } else {
-            const float4 *sc = reinterpret_cast<const float4 *>(p.scale + n0);
+            const float4 *sc = reinterpret_cast<const float4 *>(cs + c);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float4 t = __ldg(sh + j), u = __ldg(sc + j);
+                const float4 t = sh[j], u = sc[j];
                 f[4 * j] = fmaf(f[4 * j], u.x, t.x); f[4 * j + 1] = fmaf(f[4 * j + 1], u.y, t.y);
                 f[4 * j + 2] = fmaf(f[4 * j + 2], u.z, t.z); f[4 * j + 3] = fmaf(f[4 * j + 3], u.w, t.w);
             }
@@ -128,8 +130,6 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
         for (int j = 0; j < 16; j++) f[j] = p.relu == 1 ? fmaxf(f[j], 0.f) : (p.relu == 2 ? gelu_erf(f[j]) : f[j]);
     }
     if (p.res) {
-        const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + opix * p.res_stride + p.res_coff + n0);
-        const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
         const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
     uint64_t *full = bars, *empty = bars + CT_MAX_STAGES, *tfull = bars + 2 * CT_MAX_STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     volatile int *last_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
+    float *coef = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [2 (item parity)][scale 256 | shift 256]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -314,10 +315,18 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
             const bool row_ok = mx < p.Mw && my < p.Mh && b < p.B;
             const size_t opix = ((size_t)b * p.Hout + (p.oy0 + p.osy * my)) * p.Wout + (p.ox0 + p.osx * mx);
             const uint32_t acc = n & 1;
+            const int n_base = nt * p.BN;
+            // this tile's scale / shift go to shared memory once (the loads are in flight while the accumulator is awaited):
+            // per-chunk __ldg of the bias was the largest stall of the epilogue (profiles/r01_conv_bound_experiment.md)
+            const int et = half * 128 + r;
+            float my_sc = 1.f, my_sh = 0.f;
+            if (et < p.BN && n_base + et < p.Cout) { my_sc = __ldg(p.scale + n_base + et); my_sh = __ldg(p.shift + n_base + et); }
             mbar_wait(&tfull[acc], (n >> 1) & 1);
             tc_fence_after();
+            float *cs = coef + (n & 1) * 512;
+            cs[et] = my_sc; cs[256 + et] = my_sh;
+            epi_bar_sync();
             const uint32_t taddr = tmem_base + acc * CT_ACC_STRIDE + ((uint32_t)((warp & 3) * 32) << 16);
-            const int n_base = nt * p.BN;
             if (p.mode != 0) {
                 // output heads (Cout <= 16, one 16-column chunk; splits == 1)
                 uint32_t v[16];
@@ -341,22 +350,28 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
             } else if (p.splits == 1) {
 #pragma unroll 1
                 for (int c0 = cb; c0 < ce; c0 += 32) {
+                    const bool do0 = row_ok && n_base + c0 < p.Cout, do1 = row_ok && c0 + 16 < ce && n_base + c0 + 16 < p.Cout;
+                    uint4 ra0 = make_uint4(0u, 0u, 0u, 0u), ra1 = ra0, rb0 = ra0, rb1 = ra0;
+                    if (p.res) {   // residual loads go out before the TMEM loads are awaited
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + opix * p.res_stride + p.res_coff + n_base + c0);
+                        if (do0) { ra0 = __ldg(rp); ra1 = __ldg(rp + 1); }
+                        if (do1) { rb0 = __ldg(rp + 2); rb1 = __ldg(rp + 3); }
+                    }
                     uint32_t v0[16], v1[16];
                     tmem_ld16_nowait(taddr + c0, v0);
                     if (c0 + 16 < ce) tmem_ld16_nowait(taddr + c0 + 16, v1);
                     tmem_ld_wait();
-                    if (!row_ok) continue;
-                    if (n_base + c0 < p.Cout) {
+                    if (do0) {
                         float f[16];
 #pragma unroll
                         for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v0[j]);
-                        ct_finish16(p, f, n_base + c0, opix);
+                        ct_finish16(p, f, cs, c0, n_base + c0, opix, ra0, ra1);
                     }
-                    if (c0 + 16 < ce && n_base + c0 + 16 < p.Cout) {
+                    if (do1) {
                         float f[16];
 #pragma unroll
                         for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v1[j]);
-                        ct_finish16(p, f, n_base + c0 + 16, opix);
+                        ct_finish16(p, f, cs, c0 + 16, n_base + c0 + 16, opix, rb0, rb1);
                     }
                 }
                 CT_RELEASE_ACC();
@@ -411,7 +426,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                                     }
                                 }
                             }
-                            ct_finish16(p, f, n_base + c0, opix);
+                            uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0;
+                            if (p.res) {
+                                const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + opix * p.res_stride + p.res_coff + n_base + c0);
+                                q0 = __ldg(rp); q1 = __ldg(rp + 1);
+                            }
+                            ct_finish16(p, f, cs, c0, n_base + c0, opix, q0, q1);
                         }
                     }
                     if (leader) p.counters[mt * p.n_tiles + nt] = 0u;

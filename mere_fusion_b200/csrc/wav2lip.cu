@@ -740,7 +740,7 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
     { const char *e = getenv("MF_CONV_CG"); if (e && atoi(e) == 1) CG = 1; if (e && atoi(e) == 2 && BN % 32 == 0 && m_tiles >= 2) CG = 2; }
     p.BN = BN; p.n_tiles = (o.Cout + BN - 1) / BN; p.splits = S;
     const int stage = A_STAGE_BYTES + BN * 128 / CG;
-    p.stages = std::min(CT_MAX_STAGES, (CT_SMEM_LIMIT - 1024 - 256) / stage);
+    p.stages = std::min(CT_MAX_STAGES, (CT_SMEM_LIMIT - 1024 - 256 - 4096) / stage);
     const int m_groups = (m_tiles + CG - 1) / CG;          // work items are 128-row tiles (CG 1) or 256-row tile pairs (CG 2)
     p.total_items = m_groups * p.n_tiles * S;
     p.out = cp.out; p.res = cp.res; p.scale = cp.scale; p.shift = cp.shift;
@@ -789,7 +789,7 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
     l.cluster = CG;
     l.grid = dim3(CG * std::min(p.total_items, sms / CG)); l.block = dim3(CT_THREADS);
     p.mode = o.mode;
-    l.smem = p.stages * stage + 256 + 1024; l.op = i; l.io = o.mode != 0 ? IO_OUT : IO_NONE;
+    l.smem = p.stages * stage + 256 + 4096 + 1024; l.op = i; l.io = o.mode != 0 ? IO_OUT : IO_NONE;
     if (S > 1) {
         l.ws_bytes = (size_t)m_groups * CG * p.n_tiles * S * 128 * BN * sizeof(float);
         l.ws_counters = m_groups * CG * p.n_tiles;
