@@ -542,6 +542,25 @@ def main():
             dt = time.perf_counter() - t0
             heads["wav2lip"]["cpu_baseline"] = {"value": 16 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                                 "sample": f"one batch of 16 frames through the fp32 PyTorch oracle (pinned on the reference nn.Module's golden output), {dt:.2f} s, network only (no paste)"}
+        if "musetalk" in heads:
+            import torch as _t
+            from helpers import WHISPER_TINY as _WT, seeded_whisper_state as _sws, synthetic_speech as _ss
+            from oracle import musetalk_oracle as _M, whisper_oracle as _WO
+            _t.set_num_threads(os.cpu_count())
+            _u, _v = _M.UNET_CFG, _M.VAE_CFG
+            _usd, _vsd = _M.seeded_state(_M.unet_param_shapes(_u), 5), _M.seeded_state(_M.vae_decoder_param_shapes(_v), 6)
+            _rng = np.random.default_rng(0)
+            _lat = (_rng.standard_normal((1, 8, 32, 32)) * 0.9).astype(np.float32)
+            _wh = _rng.standard_normal((1, 50, 384)).astype(np.float32)
+            t0 = time.perf_counter()
+            _M.infer(_usd, _vsd, _lat, _wh, _u, _v)
+            t_net = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            _WO.audio2feat(_sws(7), _ss(52 * 320, 0), _WT)
+            t_wh = time.perf_counter() - t0
+            heads["musetalk"]["cpu_baseline"] = {"value": 1.0 / (t_net + t_wh / 16), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                                 "sample": f"ONE frame through the fp32 PyTorch restatement of UNet + VAE decoder ({t_net:.2f} s) plus 1/16 of one "
+                                                           f"52-chunk Whisper window through the oracle ({t_wh:.2f} s per window); diffusers is absent, so no reference CPU run exists"}
         fps, t, cores = oracle_sample_fps(128, frames=3)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": f"128x128 sub-grid of the 512x512 ray grid (16384 of {RAYS} rays), full pipeline, "

@@ -104,6 +104,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive 
 
 // scale/shift (staged in shared memory per tile: cs = scale[256] | shift[256], indexed by the column inside the tile) ->
 // (+residual, already loaded: r0 | r1 = 16 bf16) -> activation -> bf16, 16 channels of one pixel
+template <int ACT>   // 0 none, 1 ReLU, 2 exact-erf GELU: compile-time, so that the epilogue loop stays a few hundred instructions
 __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[16], const float *cs, int c, int n0, size_t opix,
                                             const uint4 &r0, const uint4 &r1) {
     {
@@ -125,9 +126,9 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
         }
     }
     const bool res_late = p.flags & 1;
-    if (res_late) {
+    if (ACT != 0 && res_late) {
 #pragma unroll
-        for (int j = 0; j < 16; j++) f[j] = p.relu == 1 ? fmaxf(f[j], 0.f) : (p.relu == 2 ? gelu_erf(f[j]) : f[j]);
+        for (int j = 0; j < 16; j++) f[j] = ACT == 1 ? fmaxf(f[j], 0.f) : gelu_erf(f[j]);
     }
     if (p.res) {
         const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -142,9 +143,9 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         float a = f[2 * j], c = f[2 * j + 1];
-        if (!res_late) {
-            if (p.relu == 1) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-            else if (p.relu == 2) { a = gelu_erf(a); c = gelu_erf(c); }
+        if (ACT != 0 && !res_late) {
+            if (ACT == 1) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+            else { a = gelu_erf(a); c = gelu_erf(c); }
         }
         __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
         o[j] = *reinterpret_cast<uint32_t *>(&h);
@@ -171,7 +172,7 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
         }                                                                 \
     } while (0)
 
-template <int CG>
+template <int CG, int ACT>
 __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constant__ ConvTmaParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -349,29 +350,34 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                 }
             } else if (p.splits == 1) {
 #pragma unroll 1
-                for (int c0 = cb; c0 < ce; c0 += 32) {
-                    const bool do0 = row_ok && n_base + c0 < p.Cout, do1 = row_ok && c0 + 16 < ce && n_base + c0 + 16 < p.Cout;
-                    uint4 ra0 = make_uint4(0u, 0u, 0u, 0u), ra1 = ra0, rb0 = ra0, rb1 = ra0;
-                    if (p.res) {   // residual loads go out before the TMEM loads are awaited
-                        const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + opix * p.res_stride + p.res_coff + n_base + c0);
-                        if (do0) { ra0 = __ldg(rp); ra1 = __ldg(rp + 1); }
-                        if (do1) { rb0 = __ldg(rp + 2); rb1 = __ldg(rp + 3); }
+                for (int c0 = cb; c0 < ce; c0 += 64) {
+                    // one group = up to four 16-column chunks: their TMEM loads and residual loads are all issued before the
+                    // single wait (the per-chunk load -> wait -> use chain was the epilogue's largest stall)
+                    bool doc[4];
+                    uint4 ra[4], rb[4];
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int cc = c0 + 16 * u;
+                        doc[u] = row_ok && cc < ce && n_base + cc < p.Cout;
+                        ra[u] = make_uint4(0u, 0u, 0u, 0u); rb[u] = ra[u];
+                        if (p.res && doc[u]) {
+                            const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + opix * p.res_stride + p.res_coff + n_base + cc);
+                            ra[u] = __ldg(rp); rb[u] = __ldg(rp + 1);
+                        }
                     }
-                    uint32_t v0[16], v1[16];
-                    tmem_ld16_nowait(taddr + c0, v0);
-                    if (c0 + 16 < ce) tmem_ld16_nowait(taddr + c0 + 16, v1);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (c0 + 16 * u < ce) tmem_ld16_nowait(taddr + c0 + 16 * u, v[u]);
                     tmem_ld_wait();
-                    if (do0) {
-                        float f[16];
 #pragma unroll
-                        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v0[j]);
-                        ct_finish16(p, f, cs, c0, n_base + c0, opix, ra0, ra1);
-                    }
-                    if (do1) {
-                        float f[16];
+                    for (int u = 0; u < 4; u++) {
+                        if (doc[u]) {
+                            float f[16];
 #pragma unroll
-                        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v1[j]);
-                        ct_finish16(p, f, cs, c0 + 16, n_base + c0 + 16, opix, rb0, rb1);
+                            for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[u][j]);
+                            ct_finish16<ACT>(p, f, cs, c0 + 16 * u, n_base + c0 + 16 * u, opix, ra[u], rb[u]);
+                        }
                     }
                 }
                 CT_RELEASE_ACC();
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                                 const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + opix * p.res_stride + p.res_coff + n_base + c0);
                                 q0 = __ldg(rp); q1 = __ldg(rp + 1);
                             }
-                            ct_finish16(p, f, cs, c0, n_base + c0, opix, q0, q1);
+                            ct_finish16<ACT>(p, f, cs, c0, n_base + c0, opix, q0, q1);
                         }
                     }
                     if (leader) p.counters[mt * p.n_tiles + nt] = 0u;

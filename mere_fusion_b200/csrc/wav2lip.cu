@@ -675,7 +675,17 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
 
 
 // ---- k_conv_tma planning: tile box, BN, split-K, ring depth -------------------------------------------
-static bool is_conv_tma(const void *f) { return f == (void *)k_conv_tma<1> || f == (void *)k_conv_tma<2>; }
+static void *conv_tma_func(int cg, int act) {
+    static void *const tab[2][3] = {{(void *)k_conv_tma<1, 0>, (void *)k_conv_tma<1, 1>, (void *)k_conv_tma<1, 2>},
+                                    {(void *)k_conv_tma<2, 0>, (void *)k_conv_tma<2, 1>, (void *)k_conv_tma<2, 2>}};
+    return tab[cg - 1][act];
+}
+static bool is_conv_tma(const void *f) {
+    for (int c = 1; c <= 2; c++)
+        for (int a = 0; a < 3; a++)
+            if (f == conv_tma_func(c, a)) return true;
+    return false;
+}
 
 static bool conv_tma_eligible(const W2LOp &o) {
     static int on = -1;
@@ -780,12 +790,13 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
     }
     static bool attr_set = false;
     if (!attr_set) {
-        MF_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_LIMIT));
-        MF_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_LIMIT));
+        for (int f = 0; f < 6; f++)
+            MF_CUDA(ctx, cudaFuncSetAttribute(conv_tma_func(f / 3 + 1, f % 3), cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_LIMIT));
         attr_set = true;
     }
+    MF_REQUIRE(ctx, o.relu >= 0 && o.relu <= 2, "op %d: unknown activation %d", i, o.relu);
     Launch l;
-    l.func = CG == 2 ? (void *)k_conv_tma<2> : (void *)k_conv_tma<1>;
+    l.func = conv_tma_func(CG, o.relu);
     l.cluster = CG;
     l.grid = dim3(CG * std::min(p.total_items, sms / CG)); l.block = dim3(CT_THREADS);
     p.mode = o.mode;
