@@ -65,6 +65,7 @@ struct ErnerfState {
     const float *torso_density = nullptr;
     const __half *head_mlp = nullptr, *torso_mlp = nullptr, *audio = nullptr, *torso_const = nullptr;
     const float *misc = nullptr;
+    size_t audio_halfs = 0;
     HeadLevels hl;
     TorsoLevels tl;
     // persistent device state
@@ -126,6 +127,7 @@ struct SetupParams {
     int A;
     int N;
     int smooth;
+    int audio_halfs;          // size of the audio weight image (fp16 elements)
     float wa[6];              // wrapped anchor (fp16-rounded), network.py:175-176
     float *dbg_enc_a;
 };
@@ -151,13 +153,25 @@ __device__ void conv1d_k3(const float *x, float *y, const __half *W, const __hal
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_setup(SetupParams p) {
-    __shared__ float bufA[8 * 64 * 16];  // activations (values already rounded to fp16)
-    __shared__ float bufB[8 * 32 * 8];
-    __shared__ float enc[8 * 32];
-    __shared__ float att[8];
-    __shared__ float anchor[42];
+#define SETUP_THREADS 1024
+#define SETUP_FLOATS (8 * 64 * 16 + 8 * 32 * 8 + 8 * 32 + 8 + 48)
+__global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams p) {
+    // the whole audio-net weight image (66 KB fp16) is staged in shared memory with coalesced 16-byte loads first: read straight
+    // from global inside the dot-product loops, the 2-byte weight loads formed ~1000-long dependent latency chains per thread
+    // (125 us for 0.1 MFLOP: 18 % of the frame)
+    extern __shared__ __align__(16) unsigned char setup_smem[];
+    float *bufA = reinterpret_cast<float *>(setup_smem);  // activations (values already rounded to fp16)
+    float *bufB = bufA + 8 * 64 * 16;
+    float *enc = bufB + 8 * 32 * 8;
+    float *att = enc + 8 * 32;
+    float *anchor = att + 8;
+    __half *w_sm = reinterpret_cast<__half *>(bufA + SETUP_FLOATS);
     const int tid = threadIdx.x;
+    if (!p.enc_a_in) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.audio);   // blob entries are 256-byte aligned and padded
+        uint4 *dst = reinterpret_cast<uint4 *>(w_sm);
+        for (int i = tid; i < (p.audio_halfs * 2 + 15) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
 
     // counters: round 0 has all N rays alive (renderer.py:240-241)
     for (int i = tid; i < (ER_MAX_ROUNDS + 1) * ER_CTR_STRIDE; i += blockDim.x) p.counters[i] = 0;
@@ -187,7 +201,7 @@ __global__ void __launch_bounds__(256) k_setup(SetupParams p) {
 
     // ---- AudioNet (network.py:40-66): x[:, :, 0:16] -> 4x conv(k3,s2,p1)+LeakyReLU -> fc
     const int A = p.A;
-    const __half *w = p.audio;
+    const __half *w = w_sm;
     for (int i = tid; i < 8 * A * 16; i += blockDim.x) bufA[i] = round_half(p.auds[i]);
     __syncthreads();
     conv1d_k3(bufA, bufB, w, w + 32 * A * 3, 8, A, 16, 32, 2);  w += 32 * A * 3 + 32;
@@ -1084,6 +1098,7 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
         delete s;
         return mf_fail(ctx, MF_E_INVALID, "mf_ernerf_load: blob entry sizes do not match cfg (strict loader)");
     }
+    s->audio_halfs = audio_halfs;
     s->planes = (const float *)ptr[ER_ID_HEAD_PLANES];
     s->plane_rows = head_rows;
     s->bitfield = (const uint8_t *)ptr[ER_ID_BITFIELD];
@@ -1251,8 +1266,16 @@ extern "C" int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *f, uint8_t *
     sp.auds = f->auds; sp.enc_a_in = f->enc_a; sp.audio = s->audio; sp.torso_const = s->torso_const;
     sp.misc = s->misc; sp.state = s->state; sp.counters = s->counters; sp.A = (int)s->cfg.audio_in_dim;
     sp.N = N; sp.smooth = (int)s->cfg.smooth_lips; sp.dbg_enc_a = dbg ? dbg->enc_a : nullptr;
+    sp.audio_halfs = (int)s->audio_halfs;
     int launches = 0;
-    k_setup<<<1, 256, 0, stream>>>(sp);
+    const size_t setup_smem = SETUP_FLOATS * sizeof(float) + (s->audio_halfs * 2 + 15) / 16 * 16;
+    static bool setup_attr = false;
+    if (!setup_attr) {
+        MF_CUDA(ctx, cudaFuncSetAttribute(k_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        setup_attr = true;
+    }
+    MF_REQUIRE(ctx, setup_smem <= 200 * 1024, "audio weight image too large for k_setup");
+    k_setup<<<1, SETUP_THREADS, setup_smem, stream>>>(sp);
     launches++;
 
     HeadParams hp;
