@@ -9,6 +9,9 @@
 //     K-major SWIZZLE_128B layout tcgen05 reads; zero padding and ragged edges are TMA out-of-bounds zero fill.  No thread
 //     touches the operand bytes (the cp.async im2col producer of k_conv measured 2x slower than its own MMA pipe:
 //     profiles/r01_conv_bound_experiment.md).
+//   * A row-halo reuse: when the tile is one 128-pixel row segment and the taps come in runs of consecutive dx (3x3: three runs of
+//     3), ONE box of 128 + ndx - 1 pixels is loaded per (dy, channel block) and the ndx shifted A operands are descriptors into it
+//     (start address + j * 128 B): A ingest drops 3x for 3x3 convs.
 //   * B: weights, K = tap * Cin + channel, stored re-tiled [Cout_pad / 16][K / 64][16][64] (2 KB contiguous pieces), 4-D TMA
 //     box {64, 16, 1, BN / 16}: lands as BN rows of 128 bytes, the same K-major SWIZZLE_128B layout.
 //   * roles (320 threads): warp 5 lane 0 = TMA producer, warp 4 lane 0 = MMA issuer (also owns the TMEM allocation),
@@ -41,10 +44,12 @@ struct ConvTmaParams {
     int in_coff, ntaps, cblocks, nkb, Cout, relu, flags;
     int BN, n_tiles, splits, stages;
     int lTW, lTH, tiles_x, tiles_y, total_items;
+    int ndx, n_groups, a_stage_bytes;   // row-halo A reuse: a k-step is (tap group, channel block): one A load, ndx B loads, 4 ndx UMMAs
     int dbg;
     int mode;        // 0 bf16 NHWC; 1 wav2lip head (sigmoid, x255 truncated, u8 + fp32); 2 VAE head ((x/2+.5).clamp, round, BGR u8 + RGB fp32)
     float *out_f32;  // modes 1 / 2
-    int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];
+    int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];   // per tap GROUP: dy, first dx
+    int8_t grp_tap0[CONV_MAX_TAPS];                         // per tap group: index of its first tap in the weight K order
 };
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
@@ -180,8 +185,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
     const uint32_t B_STAGE = (uint32_t)p.BN * (128u / CG);   // this CTA's share of the B tile
     const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
     unsigned char *sA = smem;
-    unsigned char *sB = smem + ST * A_STAGE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)ST * B_STAGE);
+    const uint32_t A_STAGE = (uint32_t)p.a_stage_bytes;              // 16 KB, or 17 KB with the row halo
+    const uint32_t A_TX = (uint32_t)(CONV_BM + p.ndx - 1) * 128u;       // bytes one A box delivers
+    const int NDX = p.ndx;
+    unsigned char *sB = smem + ST * A_STAGE;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)ST * NDX * B_STAGE);
     uint64_t *full = bars, *empty = bars + CT_MAX_STAGES, *tfull = bars + 2 * CT_MAX_STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     volatile int *last_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
@@ -228,24 +236,29 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                 const int txi = mt % p.tiles_x, tyi = (mt / p.tiles_x) % p.tiles_y, tbi = mt / (p.tiles_x * p.tiles_y);
                 const int x0 = txi << p.lTW, y0 = tyi << p.lTH, b0 = tbi << (7 - p.lTW - p.lTH);
                 const int kb0 = (int)((long long)sp * p.nkb / p.splits), kb1 = (int)((long long)(sp + 1) * p.nkb / p.splits);
-                int tap = kb0 / p.cblocks, cb = kb0 - tap * p.cblocks;
+                int grp = kb0 / p.cblocks, cb = kb0 - grp * p.cblocks;
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&empty[s], ph);
+                    unsigned char *a_dst = sA + (size_t)s * A_STAGE, *b_dst = sB + (size_t)s * NDX * B_STAGE;
+                    const int ax = x0 + p.tap_dx[grp], ay = y0 + p.tap_dy[grp], ac = p.in_coff + cb * CONV_BK;
+                    const int tap0 = p.grp_tap0[grp];
                     if (CG == 2) {
                         // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
-                        if (cta_rank == 0) mbar_expect_tx(&full[s], 2 * (A_STAGE_BYTES + B_STAGE));
-                        tma_load_4d_2sm(sA + s * A_STAGE_BYTES, &p.amap, p.in_coff + cb * CONV_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0, &full[s]);
-                        tma_load_4d_2sm(sB + (size_t)s * B_STAGE, &p.wmap, 0, 0, kb, (nt * p.BN + (int)cta_rank * (p.BN >> 1)) >> 4, &full[s]);
+                        if (cta_rank == 0) mbar_expect_tx(&full[s], 2 * (A_TX + NDX * B_STAGE));
+                        tma_load_4d_2sm(a_dst, &p.amap, ac, ax, ay, b0, &full[s]);
+                        for (int j = 0; j < NDX; j++)
+                            tma_load_4d_2sm(b_dst + (size_t)j * B_STAGE, &p.wmap, 0, 0, (tap0 + j) * p.cblocks + cb,
+                                            (nt * p.BN + (int)cta_rank * (p.BN >> 1)) >> 4, &full[s]);
                     } else {
-                        mbar_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE);
-                        if (!(p.dbg & 1))
-                            tma_load_4d(sA + s * A_STAGE_BYTES, &p.amap, p.in_coff + cb * CONV_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0, &full[s]);
-                        else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"((uint32_t)A_STAGE_BYTES) : "memory");
-                        if (!(p.dbg & 2))
-                            tma_load_4d(sB + (size_t)s * B_STAGE, &p.wmap, 0, 0, kb, (nt * p.BN) >> 4, &full[s]);
-                        else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"(B_STAGE) : "memory");
+                        mbar_expect_tx(&full[s], A_TX + NDX * B_STAGE);
+                        if (!(p.dbg & 1)) tma_load_4d(a_dst, &p.amap, ac, ax, ay, b0, &full[s]);
+                        else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"(A_TX) : "memory");
+                        for (int j = 0; j < NDX; j++) {
+                            if (!(p.dbg & 2)) tma_load_4d(b_dst + (size_t)j * B_STAGE, &p.wmap, 0, 0, (tap0 + j) * p.cblocks + cb, (nt * p.BN) >> 4, &full[s]);
+                            else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full[s])), "r"(B_STAGE) : "memory");
+                        }
                     }
-                    if (++cb == p.cblocks) { cb = 0; tap++; }
+                    if (++cb == p.cblocks) { cb = 0; grp++; }
                     if (++s == ST) { s = 0; ph ^= 1; }
                 }
             }
@@ -257,7 +270,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
             // 128x128x16 UMMAs is only 256 tensor cycles), so no division / modulo / descriptor rebuild per k-block
             const uint32_t idesc = make_idesc(CONV_BM * CG, p.BN);
             const uint64_t adesc0 = make_sdesc(smem_u32(sA)), bdesc0 = make_sdesc(smem_u32(sB));
-            const uint32_t a_step = A_STAGE_BYTES >> 4, b_step = B_STAGE >> 4;   // descriptor start-address units of 16 B
+            const uint32_t a_step = A_STAGE >> 4, b_step = (NDX * B_STAGE) >> 4;   // descriptor start-address units of 16 B
+            const uint32_t b_tap = B_STAGE >> 4;
+            // shifted A operand j of the row halo: start address + j * 128 B, nothing else: the 128B swizzle is a function of the
+            // absolute shared-memory address bits (TMA wrote it that way and UMMA reads it that way), so the descriptor's matrix
+            // base offset stays 0 (measured: setting it to j gives wrong results; tests/test_convnet_gpu.py row-halo cases)
+            const uint64_t a_shift = 8ull;
             int s = 0;
             uint32_t ph = 0, n = 0;
             uint64_t adesc = adesc0, bdesc = bdesc0;
@@ -273,22 +291,23 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    if (CG == 2) {
-                        umma_f16_2sm(d_tmem, adesc, bdesc, idesc, accum);
-                        umma_f16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
-                        umma_f16_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
-                        umma_f16_2sm(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
-                        umma_commit_2sm(&empty[s]);
-                    } else {
-                        if (!(p.dbg & 4)) {
-                            umma_f16(d_tmem, adesc, bdesc, idesc, accum);
-                            umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
-                            umma_f16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
-                            umma_f16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                    uint64_t ad = adesc, bd = bdesc;
+                    for (int j = 0; j < NDX; j++) {
+                        if (CG == 2) {
+                            umma_f16_2sm(d_tmem, ad, bd, idesc, accum);
+                            umma_f16_2sm(d_tmem, ad + 2, bd + 2, idesc, 1);
+                            umma_f16_2sm(d_tmem, ad + 4, bd + 4, idesc, 1);
+                            umma_f16_2sm(d_tmem, ad + 6, bd + 6, idesc, 1);
+                        } else if (!(p.dbg & 4)) {
+                            umma_f16(d_tmem, ad, bd, idesc, accum);
+                            umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1);
+                            umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1);
+                            umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1);
                         }
-                        umma_commit(&empty[s]);
+                        accum = 1;
+                        ad += a_shift; bd += b_tap;
                     }
-                    accum = 1;
+                    if (CG == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
                     adesc += a_step; bdesc += b_step;
                     if (++s == ST) { s = 0; ph ^= 1; adesc = adesc0; bdesc = bdesc0; }
                 }

@@ -712,7 +712,21 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
     p.lTW = lTW; p.lTH = lTH;
     p.tiles_x = (o.Mw + TW - 1) / TW; p.tiles_y = (o.Mh + TH - 1) / TH;
     const int m_tiles = best_tiles;
-    const int nkb = o.Kpad / CONV_BK;
+    // tap groups for the row-halo A reuse: runs of taps with the same dy and consecutive dx (3x3: three runs of 3; upsample parity
+    // convs: two runs of 2), only for single-row tiles (TW = 128); otherwise every tap is its own group (ndx = 1)
+    int ndx = 1, n_groups = o.ntaps;
+    {
+        static int halo = -1;
+        if (halo < 0) { const char *e = getenv("MF_CONV_HALO"); halo = e ? atoi(e) : 1; }
+        int run = 1;
+        while (run < o.ntaps && o.tap_dy[run] == o.tap_dy[0] && o.tap_dx[run] == o.tap_dx[run - 1] + 1) run++;
+        bool ok = halo && lTW == 7 && run >= 2 && run <= 3 && o.ntaps % run == 0;
+        for (int t = 0; ok && t < o.ntaps; t++)
+            if (t % run != 0 && (o.tap_dy[t] != o.tap_dy[t - 1] || o.tap_dx[t] != o.tap_dx[t - 1] + 1)) ok = false;
+        if (ok) { ndx = run; n_groups = o.ntaps / run; }
+    }
+    const int cblocks = o.Cin / CONV_BK;
+    const int nkb = n_groups * cblocks;   // k-steps: (tap group, channel block), each 4 * ndx UMMAs
     // BN / split-K: minimise a simple cost model (cycles): per k-block max(MMA, smem traffic), per item a pipeline fill, per split
     // a reduction term.  Sweeps over forced (BN, S) (profiles/r01_conv_planner_sweep.log) show it within ~20 % of the best
     // measured choice on the small-M layers; a fitted per-SM ingest / split-latency model did worse and was dropped.
@@ -722,7 +736,7 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
     for (int nt = (o.Cout + 255) / 256; nt <= std::max(1, o.Cout / 32); nt++) {
         const int bn = (((o.Cout + nt - 1) / nt) + 15) / 16 * 16;
         if (bn > 256) continue;
-        const double kb_cost = std::max(2.0 * bn, 1.5 * (128 + bn));
+        const double kb_cost = ndx * std::max(2.0 * bn, 1.5 * (128 + bn));
         static const int splits[] = {1, 2, 3, 4, 6, 8};
         for (int sp : splits) {
             if (sp > 1 && (nkb / sp < 6 || o.mode != 0)) break;
@@ -741,32 +755,34 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
             (o.mode == 0 || fs == 1)) { BN = fbn; S = fs; }
         const char *v = getenv("MF_CONV_VERBOSE");
         if (v && atoi(v))
-            fprintf(stderr, "[conv_tma] op %d Cin %d Cout %d taps %d M %dx%dx%d: tile %dx%dx%d, m_tiles %d, BN %d, splits %d, nkb %d\n", i, o.Cin,
-                    o.Cout, o.ntaps, B, o.Mh, o.Mw, TW, TH, TB, m_tiles, BN, S, nkb);
+            fprintf(stderr, "[conv_tma] op %d Cin %d Cout %d taps %d M %dx%dx%d: tile %dx%dx%d, m_tiles %d, BN %d, splits %d, k-steps %d x %d taps\n", i, o.Cin,
+                    o.Cout, o.ntaps, B, o.Mh, o.Mw, TW, TH, TB, m_tiles, BN, S, nkb, ndx);
     }
     // BN of a CTA pair must split into two halves of whole 16-row weight pieces
     // CTA pairs (cta_group::2) for the layers with enough 128-row tiles to fill the SM pairs: halves the per-CTA B traffic
     int CG = (m_tiles >= sms && BN % 32 == 0 && o.mode == 0) ? 2 : 1;
     { const char *e = getenv("MF_CONV_CG"); if (e && atoi(e) == 1) CG = 1; if (e && atoi(e) == 2 && BN % 32 == 0 && m_tiles >= 2) CG = 2; }
     p.BN = BN; p.n_tiles = (o.Cout + BN - 1) / BN; p.splits = S;
-    const int stage = A_STAGE_BYTES + BN * 128 / CG;
+    p.ndx = ndx; p.n_groups = n_groups;
+    p.a_stage_bytes = ndx > 1 ? 17 * 1024 : A_STAGE_BYTES;   // 128 + ndx - 1 pixel rows of 128 B, rounded up to the 1024-B swizzle period
+    const int stage = p.a_stage_bytes + ndx * (BN * 128 / CG);
     p.stages = std::min(CT_MAX_STAGES, (CT_SMEM_LIMIT - 1024 - 256 - 4096) / stage);
+    MF_REQUIRE(ctx, p.stages >= 2, "op %d: a pipeline stage of %d bytes does not fit twice", i, stage);
     const int m_groups = (m_tiles + CG - 1) / CG;          // work items are 128-row tiles (CG 1) or 256-row tile pairs (CG 2)
     p.total_items = m_groups * p.n_tiles * S;
     p.out = cp.out; p.res = cp.res; p.scale = cp.scale; p.shift = cp.shift;
     p.out_stride = cp.out_stride; p.out_coff = cp.out_coff; p.Hout = cp.Hout; p.Wout = cp.Wout;
     p.res_stride = cp.res_stride; p.res_coff = cp.res_coff;
     p.Mh = o.Mh; p.Mw = o.Mw; p.B = B; p.oy0 = o.oy0; p.ox0 = o.ox0; p.osy = o.osy; p.osx = o.osx;
-    p.in_coff = o.in_coff; p.ntaps = o.ntaps; p.cblocks = o.Cin / CONV_BK; p.nkb = nkb; p.Cout = o.Cout; p.relu = o.relu; p.flags = o.flags;
-    memcpy(p.tap_dy, o.tap_dy, CONV_MAX_TAPS);
-    memcpy(p.tap_dx, o.tap_dx, CONV_MAX_TAPS);
+    p.in_coff = o.in_coff; p.ntaps = o.ntaps; p.cblocks = cblocks; p.nkb = nkb; p.Cout = o.Cout; p.relu = o.relu; p.flags = o.flags;
+    for (int g = 0; g < n_groups; g++) { p.tap_dy[g] = o.tap_dy[g * ndx]; p.tap_dx[g] = o.tap_dx[g * ndx]; p.grp_tap0[g] = (int8_t)(g * ndx); }
     { const char *e = getenv("MF_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
     // activation map: NHWC bf16 buffer [max_batch][H][W][C]
     const W2LBuffer &ib = s->bufs[o.in_buf];
     {
         cuuint64_t dims[4] = {(cuuint64_t)ib.C, (cuuint64_t)ib.W, (cuuint64_t)ib.H, (cuuint64_t)s->max_batch};
         cuuint64_t strides[3] = {(cuuint64_t)ib.C * 2, (cuuint64_t)ib.W * ib.C * 2, (cuuint64_t)ib.H * ib.W * ib.C * 2};
-        cuuint32_t box[4] = {CONV_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+        cuuint32_t box[4] = {CONV_BK, (cuuint32_t)(TW + ndx - 1), (cuuint32_t)TH, (cuuint32_t)TB};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult cr = s->encode(&p.amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)s->dbuf[o.in_buf], dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -117,3 +117,15 @@ def test_concat_channel_offsets():
 
 def test_no_bn_no_relu():
     run_case(2, 12, 12, 80, 32, 3, 1, 1, bn=False, relu=False)
+
+
+def test_conv3x3_row_halo_tiles():
+    """single-row 128-pixel tiles (TW = 128): the three dx taps of a filter row are descriptors into ONE loaded row segment of
+    130 pixels (start address + 0 / 128 / 256 B); widths of one and two tiles, a ragged width, channel offsets, a residual, CTA
+    pairs on the larger one"""
+    run_case(2, 6, 128, 64, 64, 3, 1, 1, seed=11)
+    run_case(1, 5, 256, 128, 128, 3, 1, 1, residual=True, seed=12)
+    run_case(2, 4, 160, 64, 32, 3, 1, 1, seed=13)                              # 2 tiles per row, the second one ragged
+    run_case(1, 3, 128, 64, 48, 3, 1, 1, in_coff=64, in_C=192, out_coff=16, out_C=96, seed=14)
+    run_case(16, 40, 128, 64, 64, 3, 1, 1, bn=False, relu=False, seed=15)      # 640 row tiles: CTA pairs (cta_group::2)
+    run_case(2, 6, 128, 64, 64, (1, 3)[1], 1, (0, 1)[1], seed=16)

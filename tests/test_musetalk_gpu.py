@@ -99,7 +99,7 @@ def test_attention(heads, dh, H, nk):
     _close(got, ref, atol=3e-2, rtol=3e-2)
 
 
-@pytest.mark.parametrize("cin,H", [(64, 12), (128, 20), (40, 12)])
+@pytest.mark.parametrize("cin,H", [(64, 12), (128, 20), (40, 12), (64, 128)])
 def test_upsample_conv_and_time_shift(cin, H):
     """cin % 64 == 0: four 2x2-tap parity convs on the low-resolution input (TMA conv); otherwise the upsampling is folded
     into the gather of the cp.async conv"""
