@@ -109,22 +109,27 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive 
 
 // scale/shift (staged in shared memory per tile: cs = scale[256] | shift[256], indexed by the column inside the tile) ->
 // (+residual, already loaded: r0 | r1 = 16 bf16) -> activation -> bf16, 16 channels of one pixel
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {   // explicit ld.shared (a generic pointer compiles to LD.E: long scoreboard)
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
 template <int ACT>   // 0 none, 1 ReLU, 2 exact-erf GELU: compile-time, so that the epilogue loop stays a few hundred instructions
-__device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[16], const float *cs, int c, int n0, size_t opix,
+__device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[16], uint32_t cs, int c, int n0, size_t opix,
                                             const uint4 &r0, const uint4 &r1) {
-    {
-        const float4 *sh = reinterpret_cast<const float4 *>(cs + 256 + c);
+    {   // cs = shared-memory address of scale[256] | shift[256]
+        const uint32_t sh = cs + (256 + c) * 4, sc = cs + c * 4;
         if (p.flags & 2) {   // every scale is 1 (no folded BatchNorm): bias only
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float4 t = sh[j];
+                const float4 t = lds_f4(sh + 16 * j);
                 f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
             }
         } else {
-            const float4 *sc = reinterpret_cast<const float4 *>(cs + c);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float4 t = sh[j], u = sc[j];
+                const float4 t = lds_f4(sh + 16 * j), u = lds_f4(sc + 16 * j);
                 f[4 * j] = fmaf(f[4 * j], u.x, t.x); f[4 * j + 1] = fmaf(f[4 * j + 1], u.y, t.y);
                 f[4 * j + 2] = fmaf(f[4 * j + 2], u.z, t.z); f[4 * j + 3] = fmaf(f[4 * j + 3], u.w, t.w);
             }
@@ -343,8 +348,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
             if (et < p.BN && n_base + et < p.Cout) { my_sc = __ldg(p.scale + n_base + et); my_sh = __ldg(p.shift + n_base + et); }
             mbar_wait(&tfull[acc], (n >> 1) & 1);
             tc_fence_after();
-            float *cs = coef + (n & 1) * 512;
-            cs[et] = my_sc; cs[256 + et] = my_sh;
+            float *csp = coef + (n & 1) * 512;
+            csp[et] = my_sc; csp[256 + et] = my_sh;
+            const uint32_t cs = smem_u32(csp);
             epi_bar_sync();
             const uint32_t taddr = tmem_base + acc * CT_ACC_STRIDE + ((uint32_t)((warp & 3) * 32) << 16);
             if (p.mode != 0) {
