@@ -44,6 +44,8 @@ struct ConvTmaParams {
     int in_coff, ntaps, cblocks, nkb, Cout, relu, flags;
     int BN, n_tiles, splits, stages;
     int lTW, lTH, tiles_x, tiles_y, total_items;
+    float *gn_partial;   // fused GroupNorm statistics of the OUTPUT tensor (nullable): [B][tiles per image * 4][G][2]
+    int gn_cpg, gn_G;    // channels per group (4 / 8 / 16) and number of groups
     int ndx, n_groups, a_stage_bytes;   // row-halo A reuse: a k-step is (tap group, channel block): one A load, ndx B loads, 4 ndx UMMAs
     int dbg;
     int mode;        // 0 bf16 NHWC; 1 wav2lip head (sigmoid, x255 truncated, u8 + fp32); 2 VAE head ((x/2+.5).clamp, round, BGR u8 + RGB fp32)
@@ -159,6 +161,8 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
         }
         __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
         o[j] = *reinterpret_cast<uint32_t *>(&h);
+        f[2 * j] = __bfloat162float(h.x);      // the values as stored (fused GroupNorm statistics are taken from these)
+        f[2 * j + 1] = __bfloat162float(h.y);
     }
     uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + opix * p.out_stride + p.out_coff + n0);
     op[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -169,6 +173,35 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
 // its own 128-row A tile and HALF of the B tile, the leader issues UMMA 256 x BN x 16 for both, each CTA keeps its 128 rows of the
 // accumulator in its own TMEM and runs its own epilogue.  Per CTA and k-block that is 16 KB + BN * 64 B of TMA ingest and shared-
 // memory operand reads instead of 16 KB + BN * 128 B -- the measured bound of the CG = 1 kernel.
+// fused GroupNorm statistics: per-group (sum, sum of squares) of one 16-channel chunk over the 32 rows of this warp, reduced with
+// shuffles and written by lane 0 to a FIXED slot (tile, 32-row quarter, group): no atomics, the finalise kernel adds the slots in
+// index order.  NG = groups per chunk = 16 / channels-per-group.  Rows that are not stored contribute zeros.
+template <int NG>
+__device__ __forceinline__ void ct_gn_chunk(const float (&f)[16], bool valid, float *dst, int lane) {
+    constexpr int CPG = 16 / NG;
+    float gs[NG], gq[NG];
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        gs[g] = 0.f; gq[g] = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPG; j++) {
+            const float v = valid ? f[g * CPG + j] : 0.f;
+            gs[g] += v; gq[g] = fmaf(v, v, gq[g]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
+            gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
+        }
+    if (lane == 0) {
+#pragma unroll
+        for (int g = 0; g < NG; g++) reinterpret_cast<float2 *>(dst)[g] = make_float2(gs[g], gq[g]);
+    }
+}
+
 // the epilogue is done with accumulator `acc`: CG 1 every thread arrives (count 256); CG 2 one elected thread per CTA arrives on
 // the leader's barrier (count 2), after all 256 epilogue threads of this CTA have finished their TMEM loads
 #define CT_RELEASE_ACC()                                                  \
@@ -397,11 +430,19 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
                     tmem_ld_wait();
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        if (doc[u]) {
-                            float f[16];
+                        float f[16];
 #pragma unroll
-                            for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[u][j]);
-                            ct_finish16<ACT>(p, f, cs, c0 + 16 * u, n_base + c0 + 16 * u, opix, ra[u], rb[u]);
+                        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[u][j]);
+                        if (doc[u]) ct_finish16<ACT>(p, f, cs, c0 + 16 * u, n_base + c0 + 16 * u, opix, ra[u], rb[u]);
+                        const int cc = c0 + 16 * u;
+                        if (p.gn_partial && cc < ce && n_base + cc < p.Cout && tbi < p.B) {   // warp-uniform condition
+                            // tiles are single-image here (TB = 1): slot = (image, tile in image, 32-row quarter)
+                            const int tiles_img = p.tiles_x * p.tiles_y;
+                            float *dst = p.gn_partial + ((((size_t)tbi * tiles_img + (mt - tbi * tiles_img)) * 4 + (warp & 3)) * p.gn_G +
+                                                         (n_base + cc) / p.gn_cpg) * 2;
+                            if (p.gn_cpg == 4) ct_gn_chunk<4>(f, doc[u], dst, lane);
+                            else if (p.gn_cpg == 8) ct_gn_chunk<2>(f, doc[u], dst, lane);
+                            else ct_gn_chunk<1>(f, doc[u], dst, lane);
                         }
                     }
                 }

@@ -301,6 +301,49 @@ __global__ void __launch_bounds__(256) k_gn_stats(const NormParams p) {
     if (threadIdx.x == 0) p.counter[b] = 0u;
 }
 
+// GroupNorm statistics fused into the producing conv's epilogue (k_conv_tma writes one (sum, sum of squares) per (image, tile,
+// 32-row quarter, group) into fixed slots): this kernel adds the slots of a batch item in index order and writes the per-channel
+// coefficients, replacing the k_gn_stats pass (one full read of the tensor).  grid B, block GN_FIN_THREADS.
+#define GN_FIN_THREADS 1024
+struct GnFinalParams {
+    const float *partial;   // [B][slots][G][2]
+    const float *gamma, *beta;
+    float *coef;            // [B][C][2]
+    int slots, C, G, npix;
+    float eps;
+};
+__global__ void __launch_bounds__(GN_FIN_THREADS) k_gn_finalize(const GnFinalParams p) {
+    pdl_launch();
+    pdl_wait();
+    __shared__ float red[16][128];
+    __shared__ float mr[64][2];
+    const int b = blockIdx.x, items = 2 * p.G;
+    const int nl = min(16, (int)blockDim.x / items);
+    const int item = threadIdx.x % items, ln = threadIdx.x / items;
+    if (ln < nl) {
+        const float *pp = p.partial + (size_t)b * p.slots * items;
+        float t = 0.f;
+        for (int c = ln; c < p.slots; c += nl) t += __ldcg(pp + (size_t)c * items + item);
+        red[ln][item] = t;
+    }
+    __syncthreads();
+    const int cpg = p.C / p.G;
+    if ((int)threadIdx.x < p.G) {
+        float s = 0.f, q = 0.f;
+        for (int l = 0; l < nl; l++) { s += red[l][2 * threadIdx.x]; q += red[l][2 * threadIdx.x + 1]; }
+        const float inv_n = 1.0f / ((float)p.npix * (float)cpg);
+        const float mean = s * inv_n;
+        mr[threadIdx.x][0] = mean;
+        mr[threadIdx.x][1] = rsqrtf(fmaxf(q * inv_n - mean * mean, 0.f) + p.eps);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float a = mr[g][1] * __ldg(p.gamma + c);
+        reinterpret_cast<float2 *>(p.coef)[(size_t)b * p.C + c] = make_float2(a, __ldg(p.beta + c) - mr[g][0] * a);
+    }
+}
+
 // grid (ceil(npix / pix_per_cta), B): same thread -> channel-chunk mapping as the statistics pass, so the 16
 // coefficients of a thread's chunk are loaded once and the pixel loop is pure streaming (16-B loads / stores)
 __global__ void __launch_bounds__(256) k_gn_apply(const NormParams p) {

@@ -458,6 +458,11 @@ struct Wav2LipState {
     int *wh_maxslot = nullptr;
     const float *wh_filters = nullptr;
     std::vector<int> wh_embed_bufs;
+    // GroupNorm statistics fused into the producing conv (k_conv_tma epilogue): per conv op its consumer GN op (or -1), per GN op
+    // its producer conv (or -1), the per-conv slot buffers, and the slot count chosen while the current launch list is built
+    std::vector<int> gn_consumer, gn_producer, gn_fused_slots;
+    std::vector<float *> gn_fused_buf;
+    std::vector<size_t> gn_fused_cap;
     float *dbg_ws = nullptr;        // workspace of the ad-hoc launch lists of mf_convnet_debug_run
     unsigned *dbg_counters = nullptr;
     size_t dbg_ws_bytes = 0;
@@ -483,6 +488,7 @@ void wav2lip_destroy(mf_ctx *ctx) {
     }
     delete s->entry_table;
     if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
+    for (auto b : s->gn_fused_buf) cudaFree(b);
     cudaFree(s->dbg_ws);
     cudaFree(s->dbg_counters);
     cudaFree(s->wh_logspec);
@@ -498,6 +504,8 @@ void wav2lip_destroy(mf_ctx *ctx) {
 }
 
 static inline float bits_to_float(int32_t v) { float f; memcpy(&f, &v, 4); return f; }
+
+static bool conv_tma_eligible(const W2LOp &o);
 
 extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int max_batch) {
     if (!ctx) return MF_E_INVALID;
@@ -637,6 +645,34 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return mf_fail(ctx, MF_E_CUDA, "op %d: cuTensorMapEncodeTiled failed (%d)", i, (int)cr);
+    }
+    // ---- GroupNorm <- producing conv pairs (statistics fused into the conv epilogue)
+    s->gn_consumer.assign(s->hdr.n_ops, -1);
+    s->gn_producer.assign(s->hdr.n_ops, -1);
+    s->gn_fused_slots.assign(s->hdr.n_ops, 0);
+    s->gn_fused_buf.assign(s->hdr.n_ops, nullptr);
+    s->gn_fused_cap.assign(s->hdr.n_ops, 0);
+    {
+        static int fuse = -1;
+        if (fuse < 0) { const char *e = getenv("MF_GN_FUSE"); fuse = e ? atoi(e) : 1; }
+        for (int i = 0; fuse && i < s->hdr.n_ops; i++) {
+            const W2LOp &g = s->ops[i];
+            if (g.kind != 1 || g.in_coff != 0 || s->bufs[g.in_buf].C != g.Cin) continue;
+            const int cpg = g.Cin / g.ntaps;
+            if (cpg != 4 && cpg != 8 && cpg != 16) continue;
+            for (int j = i - 1; j >= 0; j--) {
+                const W2LOp &c = s->ops[j];
+                const bool writes = (c.kind == 0 && c.mode == 0 && c.out_buf == g.in_buf) || (c.kind != 0 && c.out_buf == g.in_buf);
+                if (!writes) continue;
+                const W2LBuffer &ob = s->bufs[g.in_buf];
+                if (c.kind == 0 && conv_tma_eligible(c) && c.out_coff == 0 && c.Cout == g.Cin && c.Mh == ob.H && c.Mw == ob.W && c.osy == 1 &&
+                    c.osx == 1 && c.oy0 == 0 && c.ox0 == 0 && (s->gn_consumer[j] < 0)) {
+                    s->gn_consumer[j] = i;
+                    s->gn_producer[i] = j;
+                }
+                break;   // the last writer decides
+            }
+        }
     }
     if (is_whisper(s)) {
         const mf_blob_entry *ae = find(W2L_ID_AUX);
@@ -804,6 +840,23 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return mf_fail(ctx, MF_E_CUDA, "op %d: weight cuTensorMapEncodeTiled failed (%d)", i, (int)cr);
     }
+    // fused GroupNorm statistics for the consumer GN op (single-image tiles, no split-K)
+    s->gn_fused_slots[i] = 0;
+    if (s->gn_consumer[i] >= 0 && S == 1 && TB == 1 && o.mode == 0) {
+        const W2LOp &g = s->ops[s->gn_consumer[i]];
+        const int tiles_img = p.tiles_x * p.tiles_y, slots = tiles_img * 4;
+        const size_t need = (size_t)s->max_batch * slots * g.ntaps * 2 * sizeof(float);
+        if (!s->gn_fused_buf[i]) {
+            // capacity for any tile decomposition of this layer (ragged shapes can need up to ~2x the minimal tile count)
+            const size_t cap = (size_t)s->max_batch * (2 * ((size_t)o.Mh * o.Mw + 127) / 128 + 4) * 4 * g.ntaps * 2 * sizeof(float);
+            MF_CUDA(ctx, cudaMalloc(&s->gn_fused_buf[i], cap));
+            s->gn_fused_cap[i] = cap;
+        }
+        if (need <= s->gn_fused_cap[i]) {
+            p.gn_partial = s->gn_fused_buf[i]; p.gn_cpg = g.Cin / g.ntaps; p.gn_G = g.ntaps;
+            s->gn_fused_slots[i] = slots;
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         for (int f = 0; f < 6; f++)
@@ -899,10 +952,22 @@ static int add_op_launches(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vect
             }
             const int target = std::max(1, GN_MAX_CTAS / B);
             n.pix_per_cta = std::max(8, (n.npix + target - 1) / target);
-            Launch a;
-            a.func = (void *)k_gn_stats; a.grid = dim3((n.npix + n.pix_per_cta - 1) / n.pix_per_cta, B); a.block = dim3(256); a.op = i;
-            a.set(n);
-            L.push_back(std::move(a));
+            const int prod = s->gn_producer[i];
+            if (prod >= 0 && s->gn_fused_slots[prod] > 0) {
+                // the producing conv already left per-tile statistics: add them up instead of re-reading the tensor
+                GnFinalParams f;
+                f.partial = s->gn_fused_buf[prod]; f.gamma = n.gamma; f.beta = n.beta; f.coef = n.coef;
+                f.slots = s->gn_fused_slots[prod]; f.C = n.C; f.G = n.G; f.npix = n.npix; f.eps = n.eps;
+                Launch a;
+                a.func = (void *)k_gn_finalize; a.grid = dim3(B); a.block = dim3(GN_FIN_THREADS); a.op = i;
+                a.set(f);
+                L.push_back(std::move(a));
+            } else {
+                Launch a;
+                a.func = (void *)k_gn_stats; a.grid = dim3((n.npix + n.pix_per_cta - 1) / n.pix_per_cta, B); a.block = dim3(256); a.op = i;
+                a.set(n);
+                L.push_back(std::move(a));
+            }
             Launch b;
             b.func = (void *)k_gn_apply; b.grid = dim3((n.npix + n.pix_per_cta - 1) / n.pix_per_cta, B); b.block = dim3(256); b.op = i;
             b.set(n);

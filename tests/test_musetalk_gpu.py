@@ -147,3 +147,24 @@ def test_musetalk_small_config_vs_oracle():
     eng.forward(torch.from_numpy(lat).cuda(), torch.from_numpy(wh).cuda(), out=out2)
     torch.cuda.synchronize()
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("C,H,W,B", [(128, 6, 128, 2), (256, 16, 16, 3), (512, 8, 8, 2), (128, 3, 256, 1), (128, 40, 128, 16)])
+def test_conv_then_group_norm_fused_statistics(C, H, W, B):
+    """conv -> GroupNorm(+SiLU): the conv epilogue leaves per-tile (sum, sum of squares) per group, k_gn_finalize adds them up and
+    k_gn_apply normalises -- against F.conv2d (rounded to bf16 like the stored tensor) + F.group_norm.  Covers 4 / 8 / 16 channels
+    per group, row-halo tiles, CTA pairs (the 16 x 40 x 128 case) and multi-image tiles (8x8: falls back to the statistics pass)."""
+    from mere_fusion_b200.convnet_pack import ProgramBuilder
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, H, W, 64, generator=g)
+    w = torch.randn(C, 64, 3, 3, generator=g) / np.sqrt(64 * 9)
+    bias = torch.randn(C, generator=g) * 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    pb = ProgramBuilder(B)
+    a, h, o = pb.buffer(H, W, 64), pb.buffer(H, W, C), pb.buffer(H, W, C)
+    pb.conv(a, 0, h, 0, w.numpy(), bias.numpy(), padding=1, relu=False)
+    pb.group_norm(h, o, gamma.numpy(), beta.numpy(), 32, 1e-6, True)
+    got = _net(pb, B).debug_run(a, x, o, (B, H, W, C)).cpu()
+    y = bf(F.conv2d(bf(x).permute(0, 3, 1, 2), bf(w), bias, padding=1))
+    ref = F.silu(F.group_norm(y, 32, gamma, beta, 1e-6)).permute(0, 2, 3, 1)
+    _close(got, ref)
