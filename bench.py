@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def result(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
