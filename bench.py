@@ -372,6 +372,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wav2lip", action="store_true")
     ap.add_argument("--no-musetalk", action="store_true")
+    ap.add_argument("--no-asr", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -507,6 +508,28 @@ def main():
         head_samples.append(n)
     ren.profile(False)
 
+    # ---- the acoustic model behind NerfASR.run_step (wav2vec2 XLSR-53 shape, random weights): one 28-chunk window every 8 chunks
+    # (= every 4 video frames, nerfasr.py:105-124); reported beside the render, not inside its step (SURVEY 8(d) config 4 feeds
+    # synthetic logit windows)
+    asr = None
+    if not args.no_asr:
+        from helpers import W2V_XLSR53, seeded_w2v_state, synthetic_speech
+        from mere_fusion_b200.wav2vec2 import Wav2Vec2Engine
+
+        def pack_a():
+            from mere_fusion_b200.wav2vec2_pack import pack_wav2vec2
+            b, pb_ = pack_wav2vec2(seeded_w2v_state(22, W2V_XLSR53), W2V_XLSR53)
+            return b, dict(flops=pb_.flops_per_sample, frames=pb_.n_frames)
+
+        blob_a, meta_a = packed_on_all_ranks(pack_a, rank, world, dev)
+        w2v = Wav2Vec2Engine(blob=blob_a, cfg=W2V_XLSR53, device=local, n_frames=meta_a["frames"])
+        wins = [synthetic_speech(8960, 200 + rank * 8 + i) for i in range(8)]
+        asr_ms, _, _ = timed(lambda k: w2v.feature_fn(wins[k % 8]), max(20, args.steps // 4), args.warmup)
+        asr = {"workload": "wav2vec2 XLSR-53-large CTC (315 M parameters, random weights), one 8960-sample window per call, host window in",
+               "ms_per_window": asr_ms / max(20, args.steps // 4), "ms_per_video_frame_amortised": asr_ms / max(20, args.steps // 4) / 4,
+               "gpu_launches_per_window": w2v.last_launches, "gflop_per_window": meta_a["flops"] / 1e9}
+        del w2v, blob_a
+
     value = world * args.steps / (total_ms / 1e3)
     e2e_value = world * args.steps / (e2e_ms / 1e3)
     heads = {}
@@ -541,6 +564,7 @@ def main():
         "p50_chunk_to_frame_ms": float(np.median(lat)),
         "rays_2048_per_frame": {"value": world * args.steps / (sub_ms / 1e3), "unit": "frames/s", "ms_per_step": sub_ms / args.steps,
                                 "note": "SURVEY 8(d) config 4 (i): 2048 explicit rays (every 128th pixel of the 512x512 grid) per frame"},
+        "nerfasr_acoustic_model": asr,
         "gpu_launches": int(launches),
         "kernels_per_step": ["k_setup", "k_head", "k_torso_compose"],
         "clocks": sampler.result(),

@@ -226,6 +226,16 @@ int mf_convnet_debug_set(mf_ctx *ctx, int buf, const float *in_f32, int B, void 
 int mf_whisper_features(mf_ctx *ctx, const float *audio, int n_samples, float *out_f32, int T, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * wav2vec2 CTC logits for ErNeRF: replaces `processor(frame) -> model(input_values).logits` of
+ * NerfASR.__frame_to_text (nerfasr.py:128-143; third-party HF Wav2Vec2ForCTC, XLSR-53 large).  The program blob comes
+ * from mere_fusion_b200.wav2vec2_pack.pack_wav2vec2 (built for one window length) and is loaded with
+ * mf_wav2lip_load(max_batch = 1) into its own context.
+ *   audio   : device fp32 [n_samples] (the (l + m + r) x 20 ms window: 8960 samples for the live defaults)
+ *   out_f32 : device fp32 [n_frames, vocab] (27 x 44); NerfASR keeps rows [l : T - r + 1]
+ * ------------------------------------------------------------------------------------------ */
+int mf_wav2vec2_logits(mf_ctx *ctx, const float *audio, int n_samples, float *out_f32, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Paste-back (lipreal.py:207-214): out[i] = frames[idx_i] with faces[i] resized (cv2.resize, u8,
  * INTER_LINEAR, bit-exact) into the box (y1:y2, x1:x2).  coords order as wav2lip/genavatar.py:96.
  *   frames : device u8 [n_frames,H,W,3] the avatar's full frames, resident

@@ -10,7 +10,7 @@ import numpy as np
 
 from .ernerf_pack import build_blob
 
-CONV_MAX_TAPS = 52
+CONV_MAX_TAPS = 128
 CONV_BK = 64
 ID_PROGRAM = 1
 ID_AUX = 2
@@ -165,10 +165,25 @@ class ProgramBuilder:
         return self._emit(in_buf, in_coff, cin_pad, out_buf, out_coff, Wm.reshape(cout, -1), taps, scale, shift, Hout,
                           Wout, 0, 0, 1, 1, sy, sx, res, relu, mode, cout, ups=ups, flags=int(bool(res_after_act)))
 
-    def linear(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, res=None, act=False):
-        """nn.Linear on a token buffer = 1x1 conv.  weight [Cout, Cin]"""
+    def linear(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, res=None, act=False, mode=0):
+        """nn.Linear on a token buffer = 1x1 conv.  weight [Cout, Cin].  mode = 3: fp32 [tokens, Cout] to the caller's buffer"""
         w = np.asarray(weight, np.float32)
-        return self.conv(in_buf, in_coff, out_buf, out_coff, w[:, :, None, None], bias, None, res=res, relu=act)
+        return self.conv(in_buf, in_coff, out_buf, out_coff, w[:, :, None, None], bias, None, res=res, relu=act, mode=mode)
+
+    def conv1d_same(self, in_buf, in_coff, out_buf, out_coff, weight, bias, left_pad, act=False, res=None, res_after_act=False):
+        """nn.Conv1d over the token axis of [T, 1, C] buffers with `left_pad` zeros in front and as many behind as needed to
+        keep T outputs (an even kernel with padding k/2 followed by dropping the last output: HF Wav2Vec2SamePadLayer).
+        weight [Cout, Cin, k]"""
+        w = np.asarray(weight, np.float32)
+        cout, cin, k = w.shape
+        T = self.buffers[in_buf][0]
+        assert self.buffers[in_buf][1] == 1 and self.buffers[out_buf][:2] == (T, 1) and cin % 8 == 0
+        taps = [(j - left_pad, 0) for j in range(k)]
+        Wm = w.transpose(0, 2, 1).reshape(cout, k * cin)
+        scale, shift = bn_fold(bias, None, cout)
+        self.flops_per_sample += 2 * cout * cin * k * T
+        return self._emit(in_buf, in_coff, cin, out_buf, out_coff, Wm, taps, scale, shift, T, 1, 0, 0, 1, 1, 1, 1, res, act, 0, cout,
+                          flags=int(bool(res_after_act)))
 
     def _misc(self, kind, in_buf, out_buf, **f):
         v = dict(in_coff=0, out_coff=0, res_buf=-1, res_coff=0, Mh=0, Mw=0, ntaps=0, Cin=0, Kpad=0, relu=0, s_id=-1, h_id=-1)
@@ -194,10 +209,11 @@ class ProgramBuilder:
                           s_id=self._tensor(np.asarray(gamma, np.float32).tobytes()),
                           h_id=self._tensor(np.asarray(beta, np.float32).tobytes()))
 
-    def layer_norm(self, in_buf, out_buf, gamma, beta, eps=1e-5):
+    def layer_norm(self, in_buf, out_buf, gamma, beta, eps=1e-5, act=ACT_NONE):
+        """act = ACT_GELU: LayerNorm followed by exact GELU in the same kernel (wav2vec2 feature encoder)"""
         C = self.buffers[in_buf][2]
-        assert self.buffers[out_buf] == self.buffers[in_buf] and len(gamma) == C
-        return self._misc(2, in_buf, out_buf, Cin=C, Kpad=self._fbits(eps),
+        assert self.buffers[out_buf] == self.buffers[in_buf] and len(gamma) == C and act in (ACT_NONE, ACT_GELU)
+        return self._misc(2, in_buf, out_buf, Cin=C, Kpad=self._fbits(eps), relu=int(act),
                           s_id=self._tensor(np.asarray(gamma, np.float32).tobytes()),
                           h_id=self._tensor(np.asarray(beta, np.float32).tobytes()))
 

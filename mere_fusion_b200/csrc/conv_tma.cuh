@@ -48,7 +48,8 @@ struct ConvTmaParams {
     int gn_cpg, gn_G;    // channels per group (4 / 8 / 16) and number of groups
     int ndx, n_groups, a_stage_bytes;   // row-halo A reuse: a k-step is (tap group, channel block): one A load, ndx B loads, 4 ndx UMMAs
     int dbg;
-    int mode;        // 0 bf16 NHWC; 1 wav2lip head (sigmoid, x255 truncated, u8 + fp32); 2 VAE head ((x/2+.5).clamp, round, BGR u8 + RGB fp32)
+    int mode;        // 0 bf16 NHWC; 1 wav2lip head (sigmoid, x255 truncated, u8 + fp32); 2 VAE head ((x/2+.5).clamp, round, BGR u8 + RGB fp32);
+                     // 3 fp32 tokens x Cout to out_f32 (wav2vec2 logits)
     float *out_f32;  // modes 1 / 2
     int8_t tap_dy[CONV_MAX_TAPS], tap_dx[CONV_MAX_TAPS];   // per tap GROUP: dy, first dx
     int8_t grp_tap0[CONV_MAX_TAPS];                         // per tap group: index of its first tap in the weight K order
@@ -152,6 +153,7 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
         }
     }
     uint32_t o[8];
+    float f32keep[16];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         float a = f[2 * j], c = f[2 * j + 1];
@@ -159,10 +161,21 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
             if (ACT == 1) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
             else { a = gelu_erf(a); c = gelu_erf(c); }
         }
+        f32keep[2 * j] = a; f32keep[2 * j + 1] = c;
         __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
         o[j] = *reinterpret_cast<uint32_t *>(&h);
         f[2 * j] = __bfloat162float(h.x);      // the values as stored (fused GroupNorm statistics are taken from these)
         f[2 * j + 1] = __bfloat162float(h.y);
+    }
+    if (p.mode == 3) {   // fp32 output head: the unrounded values, only the real columns
+        float *dst = p.out_f32 + opix * p.Cout + n0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float a = f32keep[2 * j], c = f32keep[2 * j + 1];
+            if (n0 + 2 * j < p.Cout) dst[2 * j] = a;
+            if (n0 + 2 * j + 1 < p.Cout) dst[2 * j + 1] = c;
+        }
+        return;
     }
     uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + opix * p.out_stride + p.out_coff + n0);
     op[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -386,8 +399,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
             const uint32_t cs = smem_u32(csp);
             epi_bar_sync();
             const uint32_t taddr = tmem_base + acc * CT_ACC_STRIDE + ((uint32_t)((warp & 3) * 32) << 16);
-            if (p.mode != 0) {
-                // output heads (Cout <= 16, one 16-column chunk; splits == 1)
+            if (p.mode == 1 || p.mode == 2) {
+                // image output heads (Cout <= 16, one 16-column chunk; splits == 1)
                 uint32_t v[16];
                 tmem_ld16_nowait(taddr, v);
                 tmem_ld_wait();

@@ -172,6 +172,65 @@ __global__ void __launch_bounds__(256) k_whisper_gather(const GatherParams p) {
     p.out[i] = __bfloat162float(p.src[j][(size_t)t * p.C + c]);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// wav2vec2 front-end (HF Wav2Vec2FeatureExtractor do_normalize + the first conv layer of Wav2Vec2FeatureEncoder): the waveform is
+// normalised to zero mean / unit variance ((x - mean) / sqrt(var + 1e-7)) and convolved (Cin = 1, k = 10, stride 5) in fp32 --
+// the raw audio never gets rounded to bf16; the 512-channel output is the program's first bf16 buffer.
+// ---------------------------------------------------------------------------------------------------
+struct W2vPrep {
+    const float *audio;     // device fp32 [n_samples]
+    const float *conv0;     // fp32 [C0][k0] then [C0] bias
+    float *stats;           // (mean, rstd)
+    __nv_bfloat16 *out;     // [n_frames][1][C0]
+    int n_samples, n_frames, C0, k0, s0;
+};
+__global__ void __launch_bounds__(1024) k_w2v_stats(const W2vPrep p) {
+    pdl_launch();
+    pdl_wait();
+    __shared__ double red[32];
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < p.n_samples; i += blockDim.x) { const double v = p.audio[i]; s += v; q += v * v; }
+    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double S = 0.0;
+    if (threadIdx.x < 32) { S = red[threadIdx.x]; for (int o = 16; o; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o); }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double Q = red[threadIdx.x];
+        for (int o = 16; o; o >>= 1) Q += __shfl_xor_sync(0xffffffffu, Q, o);
+        if (threadIdx.x == 0) {
+            const double mean = S / p.n_samples, var = Q / p.n_samples - mean * mean;   // numpy var (population)
+            p.stats[0] = (float)mean;
+            p.stats[1] = (float)(1.0 / sqrt(var + 1e-7));
+        }
+    }
+}
+// 8 output frames per CTA, one thread per (frame, channel pair ...): weights in shared memory
+__global__ void __launch_bounds__(256) k_w2v_conv0(const W2vPrep p) {
+    pdl_launch();
+    pdl_wait();
+    __shared__ float xs[7 * 16 + 16];   // s0, k0 <= 16 (checked at load)
+    const int t0 = blockIdx.x * 8;
+    const float mean = p.stats[0], rstd = p.stats[1];
+    const int span = 7 * p.s0 + p.k0;   // samples touched by the CTA's 8 frames
+    for (int i = threadIdx.x; i < span; i += blockDim.x) {
+        const int src = t0 * p.s0 + i;
+        xs[i] = src < p.n_samples ? (p.audio[src] - mean) * rstd : 0.f;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 8 * p.C0; o += blockDim.x) {
+        const int c = o % p.C0, f = o / p.C0;
+        if (t0 + f >= p.n_frames) continue;
+        const float *w = p.conv0 + c * p.k0;
+        float acc = __ldg(p.conv0 + p.C0 * p.k0 + c);
+        for (int k = 0; k < p.k0; k++) acc = fmaf(__ldg(w + k), xs[f * p.s0 + k], acc);
+        p.out[(size_t)(t0 + f) * p.C0 + c] = __float2bfloat16_rn(acc);
+    }
+}
+
 __global__ void k_f32_to_bf16(const PrepParams p) {
     pdl_launch();
     pdl_wait();
@@ -499,8 +558,12 @@ __global__ void __launch_bounds__(256) k_layernorm(const NormParams p) {
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const float a = (x[k + 2 * j] - mean) * rstd * __ldg(p.gamma + c + 2 * j) + __ldg(p.beta + c + 2 * j);
-            const float b = (x[k + 2 * j + 1] - mean) * rstd * __ldg(p.gamma + c + 2 * j + 1) + __ldg(p.beta + c + 2 * j + 1);
+            float a = (x[k + 2 * j] - mean) * rstd * __ldg(p.gamma + c + 2 * j) + __ldg(p.beta + c + 2 * j);
+            float b = (x[k + 2 * j + 1] - mean) * rstd * __ldg(p.gamma + c + 2 * j + 1) + __ldg(p.beta + c + 2 * j + 1);
+            if (p.silu == 2) {   // LayerNorm -> exact GELU (wav2vec2 feature encoder)
+                a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752f));
+                b = 0.5f * b * (1.0f + erff(b * 0.70710678118654752f));
+            }
             __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
             o[j] = *reinterpret_cast<uint32_t *>(&h);
         }

@@ -33,7 +33,7 @@
 #define CONV_BM 128
 #define CONV_BK 64
 #define CONV_THREADS 160
-#define CONV_MAX_TAPS 52
+#define CONV_MAX_TAPS 128
 #define A_STAGE_BYTES (CONV_BM * CONV_BK * 2)
 #define GN_MAX_CTAS (148 * 8)
 
@@ -380,7 +380,7 @@ static cudaError_t conv_desc_any(int BN, const ConvParams &p, LaunchDesc *d) {
 }
 
 // one kernel launch with its by-value parameter struct; io != 0 marks the launches that see caller pointers
-enum { IO_NONE = 0, IO_IN0 = 1, IO_IN1 = 2, IO_OUT = 3, IO_WH_FRAMES = 4, IO_WH_FINISH = 5, IO_WH_OUT = 6 };
+enum { IO_NONE = 0, IO_IN0 = 1, IO_IN1 = 2, IO_OUT = 3, IO_WH_FRAMES = 4, IO_WH_FINISH = 5, IO_WH_OUT = 6, IO_W2V_IN = 7 };
 struct Launch {
     void *func = nullptr;
     dim3 grid, block;
@@ -458,6 +458,10 @@ struct Wav2LipState {
     int *wh_maxslot = nullptr;
     const float *wh_filters = nullptr;
     std::vector<int> wh_embed_bufs;
+    // wav2vec2 program (hdr.mel_w == -3): fixed window length, first conv layer in fp32, waveform statistics scratch
+    int w2v_samples = 0, w2v_frames = 0, w2v_vocab = 0, w2v_c0 = 0, w2v_k0 = 0, w2v_s0 = 0;
+    const float *w2v_conv0 = nullptr;   // [C0][k0] weights then [C0] bias, fp32
+    float *w2v_stats = nullptr;         // (mean, rstd) of the window
     // GroupNorm statistics fused into the producing conv (k_conv_tma epilogue): per conv op its consumer GN op (or -1), per GN op
     // its producer conv (or -1), the per-conv slot buffers, and the slot count chosen while the current launch list is built
     std::vector<int> gn_consumer, gn_producer, gn_fused_slots;
@@ -471,9 +475,10 @@ struct Wav2LipState {
     int sm_count = 148;
 };
 
-// program kinds (hdr.mel_w): >= 0 wav2lip, -1 musetalk, -2 whisper encoder
+// program kinds (hdr.mel_w): >= 0 wav2lip, -1 musetalk, -2 whisper encoder, -3 wav2vec2 CTC
 static bool is_musetalk(const Wav2LipState *s) { return s->hdr.mel_w == -1; }
 static bool is_whisper(const Wav2LipState *s) { return s->hdr.mel_w == -2; }
+static bool is_wav2vec2(const Wav2LipState *s) { return s->hdr.mel_w == -3; }
 
 void wav2lip_destroy(mf_ctx *ctx) {
     Wav2LipState *s = ctx->wav2lip;
@@ -491,6 +496,7 @@ void wav2lip_destroy(mf_ctx *ctx) {
     for (auto b : s->gn_fused_buf) cudaFree(b);
     cudaFree(s->dbg_ws);
     cudaFree(s->dbg_counters);
+    cudaFree(s->w2v_stats);
     cudaFree(s->wh_logspec);
     cudaFree(s->wh_maxslot);
     cudaFree(s->gn_coef);
@@ -619,8 +625,13 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
             p.out = s->dbuf[o.out_buf];
             p.out_stride = ob.C; p.out_coff = o.out_coff; p.Hout = ob.H; p.Wout = ob.W;
         } else {
-            MF_REQUIRE(ctx, o.Cout <= 16 && o.BN == 16 && (o.mode == 1 || o.mode == 2), "op %d: output head must have Cout <= 16", i);
-            p.Hout = s->hdr.out_hw; p.Wout = s->hdr.out_hw;
+            if (o.mode == 3) {   // fp32 token output (wav2vec2 logits): [Mh * Mw tokens][Cout]
+                MF_REQUIRE(ctx, o.Cout <= 256 && conv_tma_eligible(o), "op %d: fp32 output head must be a TMA-eligible Linear with Cout <= 256", i);
+                p.Hout = o.Mh; p.Wout = o.Mw;
+            } else {
+                MF_REQUIRE(ctx, o.Cout <= 16 && o.BN == 16 && (o.mode == 1 || o.mode == 2), "op %d: output head must have Cout <= 16", i);
+                p.Hout = s->hdr.out_hw; p.Wout = s->hdr.out_hw;
+            }
         }
         MF_REQUIRE(ctx, o.oy0 + o.osy * (o.Mh - 1) < p.Hout && o.ox0 + o.osx * (o.Mw - 1) < p.Wout, "op %d: output grid out of range", i);
         if (o.res_buf >= 0) {
@@ -694,6 +705,21 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
         MF_CUDA(ctx, cudaMalloc(&s->wh_logspec, (size_t)mb.H * WH_MELS * sizeof(float)));
         MF_CUDA(ctx, cudaMalloc(&s->wh_maxslot, sizeof(int)));
         MF_CUDA(ctx, cudaMemset(s->wh_maxslot, 0, sizeof(int)));
+    }
+    if (is_wav2vec2(s)) {
+        const mf_blob_entry *ae = find(W2L_ID_AUX);
+        MF_REQUIRE(ctx, ae && ae->nbytes == 7 * 4, "wav2vec2 program: aux entry missing");
+        int32_t aux[7];
+        MF_CUDA(ctx, cudaMemcpy(aux, base + ae->offset, sizeof(aux), cudaMemcpyDeviceToHost));
+        s->w2v_samples = aux[0]; s->w2v_frames = aux[1]; s->w2v_vocab = aux[2]; s->w2v_c0 = aux[4]; s->w2v_k0 = aux[5]; s->w2v_s0 = aux[6];
+        const mf_blob_entry *ce = find(aux[3]);
+        const W2LBuffer &b0 = s->bufs[s->hdr.in_face_buf];
+        MF_REQUIRE(ctx, ce && ce->nbytes == (size_t)(s->w2v_c0 * s->w2v_k0 + s->w2v_c0) * 4 && b0.C == s->w2v_c0 && b0.W == 1 &&
+                            b0.H == (s->w2v_samples - s->w2v_k0) / s->w2v_s0 + 1 && s->w2v_c0 <= 1024 && s->w2v_k0 >= 1 && s->w2v_k0 <= 16 && s->w2v_s0 >= 1 && s->w2v_s0 <= 16 &&
+                            s->ops.back().kind == 0 && s->ops.back().mode == 3 && s->ops.back().Cout == s->w2v_vocab,
+                   "wav2vec2 program: first-layer entry / buffers do not match the aux record");
+        s->w2v_conv0 = reinterpret_cast<const float *>(base + ce->offset);
+        MF_CUDA(ctx, cudaMalloc(&s->w2v_stats, 2 * sizeof(float)));
     }
     if (s->has_gn) {
         MF_CUDA(ctx, cudaMalloc(&s->gn_coef, (size_t)max_batch * GN_MAX_C * 2 * sizeof(float)));
@@ -1071,6 +1097,21 @@ static int build_plan(mf_ctx *ctx, Wav2LipState *s, Wav2LipState::Plan *pl, int 
         L.push_back(std::move(lg));
         return MF_OK;
     }
+    if (is_wav2vec2(s)) {
+        W2vPrep w;
+        w.audio = nullptr; w.conv0 = s->w2v_conv0; w.stats = s->w2v_stats; w.out = s->dbuf[s->hdr.in_face_buf];
+        w.n_samples = s->w2v_samples; w.n_frames = s->bufs[s->hdr.in_face_buf].H; w.C0 = s->w2v_c0; w.k0 = s->w2v_k0; w.s0 = s->w2v_s0;
+        Launch l0, l1;
+        l0.func = (void *)k_w2v_stats; l0.grid = dim3(1); l0.block = dim3(1024); l0.io = IO_W2V_IN; l0.set(w);
+        l1.func = (void *)k_w2v_conv0; l1.grid = dim3((w.n_frames + 7) / 8); l1.block = dim3(256); l1.io = IO_W2V_IN; l1.set(w);
+        L.push_back(std::move(l0));
+        L.push_back(std::move(l1));
+        for (int i = 0; i < s->hdr.n_ops; i++) {
+            int rc = add_op_launches(ctx, s, i, B, L);
+            if (rc) return rc;
+        }
+        return MF_OK;
+    }
     const W2LBuffer &b0 = s->bufs[s->hdr.in_face_buf], &b1 = s->bufs[s->hdr.in_mel_buf];
     {
         PrepParams p0, p1;
@@ -1105,6 +1146,7 @@ static void patch_io(Wav2LipState::Plan *pl, const void *in0, const void *in1, v
         else if (l.io == IO_IN1) l.as<PrepParams>().src = in1;
         else if (l.io == IO_OUT && is_conv_tma(l.func)) { l.as<ConvTmaParams>().out = out_u8; l.as<ConvTmaParams>().out_f32 = out_f32; }
         else if (l.io == IO_OUT) { l.as<ConvParams>().out = out_u8; l.as<ConvParams>().out_f32 = out_f32; }
+        else if (l.io == IO_W2V_IN) l.as<W2vPrep>().audio = reinterpret_cast<const float *>(in0);
         else if (l.io == IO_WH_FRAMES || l.io == IO_WH_FINISH) {
             WhisperPrep &w = l.as<WhisperPrep>();
             w.audio = reinterpret_cast<const float *>(in0); w.n_samples = pl->n_samples; w.n_frames = pl->n_samples / WH_HOP;
@@ -1230,6 +1272,18 @@ extern "C" int mf_whisper_features(mf_ctx *ctx, const float *audio, int n_sample
     MF_REQUIRE(ctx, T >= 1 && T <= s->bufs[s->wh_embed_bufs[0]].H, "mf_whisper_features: T = %d rows out of range", T);
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     return forward_common(ctx, s, audio, nullptr, nullptr, out_f32, 1, (cudaStream_t)stream, n_samples, T);
+}
+
+extern "C" int mf_wav2vec2_logits(mf_ctx *ctx, const float *audio, int n_samples, float *out_f32, void *stream) {
+    if (!ctx) return MF_E_INVALID;
+    Wav2LipState *s = ctx->wav2lip;
+    if (!s) return mf_fail(ctx, MF_E_STATE, "mf_wav2vec2_logits: weights not loaded");
+    MF_REQUIRE(ctx, is_wav2vec2(s), "the loaded program is not a wav2vec2 program");
+    MF_REQUIRE(ctx, audio && out_f32, "mf_wav2vec2_logits: null pointer");
+    MF_REQUIRE(ctx, n_samples == s->w2v_samples, "mf_wav2vec2_logits: the program was packed for windows of %d samples, got %d", s->w2v_samples,
+               n_samples);
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    return forward_common(ctx, s, audio, nullptr, nullptr, out_f32, 1, (cudaStream_t)stream);
 }
 
 // unit-test entry: run the loaded program on an fp32 NHWC tensor written into buffer `in_buf` (all of its channels)

@@ -1,10 +1,10 @@
 """NerfASR -- mirror of /root/reference/nerfasr.py:15-151: the 32-slot logits ring and the
 [8, audio_dim, 16] attention window.
 
-The acoustic model itself (a 315 M-parameter HF wav2vec2 / HuBERT CTC head, nerfasr.py:40-45,128-143)
-is third-party weights + architecture and out of the hot-path scope: it is
-injected as `feature_fn(float32[n_samples]) -> tensor [T, audio_dim]` (logits of one window).  When
-none is given and the HF weights are loadable, the reference's own call is used.
+The acoustic model (a 315 M-parameter HF wav2vec2 CTC head, nerfasr.py:40-45,128-143) is injected as
+`feature_fn(float32[n_samples]) -> tensor [T, audio_dim]` (logits of one window).  When none is given, the checkpoint named by
+opt.asr_model is loaded through transformers (weights only) and run on the sm_100a engine (mere_fusion_b200.wav2vec2:
+mf_wav2vec2_logits); architectures outside the XLSR-53 wav2vec2 family (HuBERT, deepspeech) are refused, not emulated.
 """
 import queue
 
@@ -13,17 +13,17 @@ import numpy as np
 from .baseasr import BaseASR
 
 
-def _hf_feature_fn(opt, device):
+def _gpu_feature_fn(opt, device):
+    """AutoModelForCTC.from_pretrained(opt.asr_model) only supplies the weights; the forward pass is mf_wav2vec2_logits"""
     import torch
-    from transformers import AutoModelForCTC, AutoProcessor
-    processor = AutoProcessor.from_pretrained(opt.asr_model)
-    model = AutoModelForCTC.from_pretrained(opt.asr_model).to(device)
-
-    def fn(frame):
-        inputs = processor(frame, sampling_rate=16000, return_tensors="pt", padding=True)
-        with torch.no_grad():
-            return model(inputs.input_values.to(device)).logits[0]
-    return fn
+    from transformers import AutoModelForCTC
+    from ..wav2vec2 import engine_from_hf
+    model = AutoModelForCTC.from_pretrained(opt.asr_model)
+    n_samples = (opt.l + opt.m + opt.r) * (16000 // opt.fps)
+    dev = torch.device(device)
+    engine = engine_from_hf(model, n_samples=n_samples, device=dev.index or 0)
+    del model
+    return engine.feature_fn
 
 
 class NerfASR(BaseASR):
@@ -44,7 +44,7 @@ class NerfASR(BaseASR):
         self.stride_right_size = opt.r
         if self.stride_left_size > 0:                                   # nerfasr.py:35-36
             self.frames.extend([np.zeros(self.chunk, dtype=np.float32)] * self.stride_left_size)
-        self.feature_fn = feature_fn if feature_fn is not None else _hf_feature_fn(opt, self.device)
+        self.feature_fn = feature_fn if feature_fn is not None else _gpu_feature_fn(opt, self.device)
         self.feat_buffer_size = 4
         self.feat_buffer_idx = 0
         self.feat_queue = torch.zeros(self.feat_buffer_size * self.context_size, self.audio_dim, dtype=torch.float32,

@@ -1,0 +1,61 @@
+"""Wav2Vec2Engine: the CTC acoustic model of the ErNeRF audio path on the GPU.  Replaces `processor(frame) -> model(input_values)
+.logits` of NerfASR.__frame_to_text (nerfasr.py:128-143) with ONE C-ABI call (mf_wav2vec2_logits): waveform normalisation, the
+7-layer conv feature encoder, the positional conv, the transformer and the lm_head all run on the device."""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .wav2lip import ConvNet, _ptr
+from .wav2vec2_pack import XLSR53_CFG, pack_wav2vec2
+
+
+class Wav2Vec2Engine(ConvNet):
+    def __init__(self, state_dict=None, cfg=XLSR53_CFG, n_samples=8960, device=0, blob=None, n_frames=None):
+        self.n_samples, self.vocab = n_samples, cfg["vocab"]
+        if blob is None:
+            blob, pb = pack_wav2vec2(state_dict, cfg, n_samples)
+            self.flops_per_call = pb.flops_per_sample
+            n_frames = pb.n_frames
+        self.n_frames = n_frames
+        super().__init__(blob, 1, device)
+        self._pin = torch.empty(n_samples, dtype=torch.float32).pin_memory()
+        self._dev = torch.empty(n_samples, dtype=torch.float32, device=self.device)
+        self._h2d_done = None
+
+    def logits(self, audio, out=None, stream=None):
+        """audio: cuda fp32 [n_samples] -> cuda fp32 [n_frames, vocab]"""
+        assert audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous() and audio.numel() == self.n_samples
+        if out is None:
+            out = torch.empty((self.n_frames, self.vocab), dtype=torch.float32, device=self.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        check(self.ctx.handle, lib().mf_wav2vec2_logits(self.ctx.handle, _ptr(audio), self.n_samples, _ptr(out), ctypes.c_void_p(s.cuda_stream)),
+              "mf_wav2vec2_logits")
+        return out
+
+    def feature_fn(self, frame):
+        """NerfASR's `feature_fn(float32[n_samples]) -> [T, audio_dim]` (device tensor)"""
+        a = np.ascontiguousarray(frame, np.float32)
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()
+        self._pin.copy_(torch.from_numpy(a))
+        self._dev.copy_(self._pin, non_blocking=True)
+        if self._h2d_done is None:
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.device))
+        return self.logits(self._dev)
+
+
+def engine_from_hf(model, n_samples=8960, device=0):
+    """build the engine from a loaded HF `Wav2Vec2ForCTC` (what AutoModelForCTC.from_pretrained(opt.asr_model) returns for the
+    default cpierse/wav2vec2-large-xlsr-53-esperanto, nerfasr.py:44-45).  Only the architecture family the live default uses is
+    supported (layer-norm feature encoder, stable-layer-norm transformer, no adapter); anything else is refused, not emulated."""
+    c = model.config
+    if getattr(c, "model_type", "") != "wav2vec2" or c.feat_extract_norm != "layer" or not c.do_stable_layer_norm or \
+            getattr(c, "add_adapter", False) or c.feat_extract_activation != "gelu" or c.hidden_act != "gelu" or not c.conv_bias:
+        raise ValueError("mere_fusion_b200.wav2vec2: unsupported acoustic-model architecture (expected the XLSR-53 wav2vec2 family)")
+    cfg = dict(vocab=c.vocab_size, hidden=c.hidden_size, layers=c.num_hidden_layers, heads=c.num_attention_heads, inter=c.intermediate_size,
+               conv_dim=tuple(c.conv_dim), conv_stride=tuple(c.conv_stride), conv_kernel=tuple(c.conv_kernel),
+               pos_k=c.num_conv_pos_embeddings, pos_groups=c.num_conv_pos_embedding_groups, eps=c.layer_norm_eps)
+    return Wav2Vec2Engine(model.state_dict(), cfg, n_samples=n_samples, device=device)

@@ -164,3 +164,57 @@ def synthetic_speech(n, seed=0):
     t = np.arange(n) / 16000.0
     x = 0.3 * np.sin(2 * np.pi * 220 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 3 * t)) + 0.01 * np.random.default_rng(seed).standard_normal(n)
     return x.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# wav2vec2 CTC (HF Wav2Vec2ForCTC, layer-norm feature encoder + stable-layer-norm transformer): seeded weights for the
+# XLSR-53-large shape NerfASR loads (nerfasr.py:44-45; the checkpoint is external) and for a small config of identical structure
+# ------------------------------------------------------------------------------------------------
+W2V_XLSR53 = dict(vocab=44, hidden=1024, layers=24, heads=16, inter=4096, conv_dim=(512,) * 7, conv_stride=(5, 2, 2, 2, 2, 2, 2),
+                  conv_kernel=(10, 3, 3, 3, 3, 2, 2), pos_k=128, pos_groups=16, eps=1e-5)
+W2V_SMALL = dict(W2V_XLSR53, hidden=256, layers=3, heads=4, inter=512, conv_dim=(64,) * 7, pos_groups=4)
+
+
+def w2v_param_shapes(c):
+    D, I, V = c["hidden"], c["inter"], c["vocab"]
+    s = {"wav2vec2.masked_spec_embed": (D,)}
+    cin = 1
+    for i, (co, k) in enumerate(zip(c["conv_dim"], c["conv_kernel"])):
+        p = f"wav2vec2.feature_extractor.conv_layers.{i}."
+        s[p + "conv.weight"], s[p + "conv.bias"] = (co, cin, k), (co,)
+        s[p + "layer_norm.weight"], s[p + "layer_norm.bias"] = (co,), (co,)
+        cin = co
+    s["wav2vec2.feature_projection.layer_norm.weight"], s["wav2vec2.feature_projection.layer_norm.bias"] = (cin,), (cin,)
+    s["wav2vec2.feature_projection.projection.weight"], s["wav2vec2.feature_projection.projection.bias"] = (D, cin), (D,)
+    pc = "wav2vec2.encoder.pos_conv_embed.conv."
+    s[pc + "bias"] = (D,)
+    s[pc + "parametrizations.weight.original0"] = (1, 1, c["pos_k"])
+    s[pc + "parametrizations.weight.original1"] = (D, D // c["pos_groups"], c["pos_k"])
+    s["wav2vec2.encoder.layer_norm.weight"], s["wav2vec2.encoder.layer_norm.bias"] = (D,), (D,)
+    for i in range(c["layers"]):
+        p = f"wav2vec2.encoder.layers.{i}."
+        for n in ("k", "v", "q", "out"):
+            s[p + f"attention.{n}_proj.weight"], s[p + f"attention.{n}_proj.bias"] = (D, D), (D,)
+        for n in ("layer_norm", "final_layer_norm"):
+            s[p + n + ".weight"], s[p + n + ".bias"] = (D,), (D,)
+        s[p + "feed_forward.intermediate_dense.weight"], s[p + "feed_forward.intermediate_dense.bias"] = (I, D), (I,)
+        s[p + "feed_forward.output_dense.weight"], s[p + "feed_forward.output_dense.bias"] = (D, I), (D,)
+    s["lm_head.weight"], s["lm_head.bias"] = (V, D), (V,)
+    return s
+
+
+def seeded_w2v_state(seed, c):
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for name, shp in w2v_param_shapes(c).items():
+        if name.endswith("layer_norm.weight"):
+            sd[name] = rng.uniform(0.7, 1.3, shp).astype(np.float32)
+        elif name.endswith(".bias") or name.endswith("masked_spec_embed"):
+            sd[name] = (rng.standard_normal(shp, dtype=np.float32) * 0.1)
+        elif name.endswith("original0"):
+            sd[name] = rng.uniform(0.5, 1.5, shp).astype(np.float32)
+        else:
+            fan_in = int(np.prod(shp[1:]))
+            gain = 2.0 if (".q_proj." in name or ".k_proj." in name) else 1.0
+            sd[name] = rng.standard_normal(shp, dtype=np.float32) * np.float32(gain / np.sqrt(fan_in))
+    return sd

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_shim_binds_the_hot_path_entry_points():
     from mere_fusion_b200 import _lib
     L = _lib.lib()
-    for n in ("mf_ernerf_load", "mf_ernerf_render", "mf_wav2lip_load", "mf_wav2lip_forward", "mf_musetalk_forward", "mf_whisper_features",
+    for n in ("mf_ernerf_load", "mf_ernerf_render", "mf_wav2lip_load", "mf_wav2lip_forward", "mf_musetalk_forward", "mf_whisper_features", "mf_wav2vec2_logits",
               "mf_wav2lip_mel_chunks", "mf_paste_resize_u8", "mf_paste_blend_u8", "mf_march_rays", "mf_composite_rays_triplane",
               "mf_grid_encode_forward"):
         assert getattr(L, n).argtypes is not None, n
