@@ -1287,10 +1287,9 @@ extern "C" int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *f, uint8_t *
     sp.audio_halfs = (int)s->audio_halfs;
     int launches = 0;
     const size_t setup_smem = SETUP_FLOATS * sizeof(float) + (s->audio_halfs * 2 + 15) / 16 * 16;
-    static bool setup_attr = false;
-    if (!setup_attr) {
+    static mf_per_device_flag setup_attr;
+    if (!setup_attr.test_and_set(ctx->device)) {
         MF_CUDA(ctx, cudaFuncSetAttribute(k_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        setup_attr = true;
     }
     MF_REQUIRE(ctx, setup_smem <= 200 * 1024, "audio weight image too large for k_setup");
     k_setup<<<1, SETUP_THREADS, setup_smem, stream>>>(sp);

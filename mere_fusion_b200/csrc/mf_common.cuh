@@ -43,6 +43,17 @@ static inline int mf_fail(mf_ctx *ctx, int code, const char *fmt, ...) {
                            cudaGetErrorString(e__));                                              \
     } while (0)
 
+// cudaFuncSetAttribute is per DEVICE: remember per (call site, device) whether it has been done
+struct mf_per_device_flag {
+    bool done[64] = {false};
+    bool test_and_set(int device) {
+        const int d = device & 63;
+        const bool was = done[d];
+        done[d] = true;
+        return was;
+    }
+};
+
 #define MF_REQUIRE(ctx, cond, ...)                                                                \
     do {                                                                                          \
         if (!(cond)) return mf_fail((ctx), MF_E_INVALID, __VA_ARGS__);                            \

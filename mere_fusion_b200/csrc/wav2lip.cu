@@ -95,13 +95,6 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
-            "r"(smem_u32(smem_dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
@@ -349,12 +342,13 @@ struct LaunchDesc {
 
 template <int BN, int STAGES>
 static cudaError_t conv_desc_s(dim3 grid, LaunchDesc *d) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static mf_per_device_flag attr_set;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set.test_and_set(dev)) {
         cudaError_t e = cudaFuncSetAttribute(k_conv<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              ConvSmem<BN, STAGES>::TOTAL);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     d->func = (void *)k_conv<BN, STAGES>;
     d->grid = grid;
@@ -883,11 +877,10 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
             s->gn_fused_slots[i] = slots;
         }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static mf_per_device_flag attr_set;
+    if (!attr_set.test_and_set(ctx->device)) {
         for (int f = 0; f < 6; f++)
             MF_CUDA(ctx, cudaFuncSetAttribute(conv_tma_func(f / 3 + 1, f % 3), cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_LIMIT));
-        attr_set = true;
     }
     MF_REQUIRE(ctx, o.relu >= 0 && o.relu <= 2, "op %d: unknown activation %d", i, o.relu);
     Launch l;
@@ -964,11 +957,9 @@ static int add_op_launches(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vect
             const size_t slab = (size_t)n.npix * n.C * 2;
             const int cpg = n.C / n.G;
             if (slab <= 200 * 1024 && cpg % 8 == 0 && n.C / 8 <= GN_SMALL_THREADS) {
-                static bool attr_set = false;
-                if (!attr_set) {
+                static mf_per_device_flag attr_set;
+                if (!attr_set.test_and_set(ctx->device))
                     MF_CUDA(ctx, cudaFuncSetAttribute(k_gn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                    attr_set = true;
-                }
                 Launch a;
                 a.func = (void *)k_gn_small; a.grid = dim3(B); a.block = dim3(GN_SMALL_THREADS); a.op = i;
                 a.smem = (int)(slab + GN_SMALL_THREADS * 8 + 64 * 8);
