@@ -168,8 +168,9 @@ def packed_on_all_ranks(pack_fn, rank, world, dev):
     return t, box[0]
 
 
-def wav2lip_leg(args, dev, local, rank, world, flush, timed_fn, pk):
-    """BASELINE configs[1]-shaped leg on the architecture the reference actually ships (96x96 crop):
+def wav2lip_leg(args, dev, local, rank, world, flush, timed_fn, pk, S=96, shared=None):
+    """BASELINE configs[1]-shaped leg.  S = 96: the architecture the reference actually ships (96x96 crop, SURVEY M2);
+    S = 256: the 256x256 EXTENSION of SURVEY 8(d) config 2 (ii) (not a reference net; parity vs our own fp32 restatement).
     16 frames per step: mel windows -> Wav2Lip (tcgen05 implicit-GEMM convs, bf16) -> cv2-exact resize + paste into
     the 512x512 avatar frame.  Returns the sub-object reported under "heads"."""
     import ctypes
@@ -181,21 +182,23 @@ def wav2lip_leg(args, dev, local, rank, world, flush, timed_fn, pk):
 
     def pack():
         from mere_fusion_b200.wav2lip_pack import pack_wav2lip
-        blob, pb = pack_wav2lip(seeded_wav2lip_state(2), nominal_batch=B)
+        blob, pb = pack_wav2lip(seeded_wav2lip_state(2, face_hw=S), nominal_batch=B, face_hw=S)
         return blob, dict(flops=pb.flops_per_sample, n_ops=len(pb.ops))
 
     blob, meta = packed_on_all_ranks(pack, rank, world, dev)
-    eng = Wav2LipEngine(blob=blob, max_batch=B, device=local)
+    eng = Wav2LipEngine(blob=blob, max_batch=B, device=local, face_hw=S)
     eng.flops_per_frame, eng.n_ops = meta["flops"], meta["n_ops"]
+    if shared is not None:
+        shared["wav2lip_blob"] = blob
     rng = np.random.default_rng(1)
     n_av = 25
     frames = torch.from_numpy(rng.integers(0, 256, (n_av, H, W, 3), dtype=np.uint8)).to(dev)
-    faces_all = torch.from_numpy(rng.integers(0, 256, (n_av, 96, 96, 3), dtype=np.uint8)).to(dev)
+    faces_all = torch.from_numpy(rng.integers(0, 256, (n_av, S, S, 3), dtype=np.uint8)).to(dev)
     mels = [torch.from_numpy(wav2lip_inputs(B, mel_seed=100 + rank * 16 + i)[0]) for i in range(8)]
     mel_dev = [m.to(dev) for m in mels]
     mel_pin = [m.pin_memory() for m in mels]
     mel_stage = torch.empty_like(mel_dev[0])
-    sel = torch.empty((B, 96, 96, 3), dtype=torch.uint8, device=dev)
+    sel = torch.empty((B, S, S, 3), dtype=torch.uint8, device=dev)
     pred = torch.empty_like(sel)
     out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
     out_pin = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
@@ -210,7 +213,7 @@ def wav2lip_leg(args, dev, local, rank, world, flush, timed_fn, pk):
         torch.index_select(faces_all, 0, idx_t, out=sel)
         eng.forward(mel, sel, out=pred)
         s = torch.cuda.current_stream(dev)
-        check(h, lib().mf_paste_resize_u8(h, ctypes.c_void_p(frames.data_ptr()), n_av, H, W, ctypes.c_void_p(pred.data_ptr()), 96, B,
+        check(h, lib().mf_paste_resize_u8(h, ctypes.c_void_p(frames.data_ptr()), n_av, H, W, ctypes.c_void_p(pred.data_ptr()), S, B,
                                           rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_void_p(out.data_ptr()),
                                           ctypes.c_void_p(s.cuda_stream)), "mf_paste_resize_u8")
 
@@ -226,7 +229,7 @@ def wav2lip_leg(args, dev, local, rank, world, flush, timed_fn, pk):
     tot, per, _ = timed_fn(step, K, args.warmup)
     e2e, _, _ = timed_fn(step_host, K, args.warmup)
     p50 = p50_latency_ms(step_host)
-    # dominant kernel by time share: the two 64->64 3x3 convs at 96x96 (decoder block 6), one of them timed live
+    # dominant kernel by time share: the two 64->64 3x3 convs at SxS (last decoder block), one of them timed live
     op = eng.n_ops - 4
     eng.profile_op(op)
     ms = []
@@ -235,21 +238,25 @@ def wav2lip_leg(args, dev, local, rank, world, flush, timed_fn, pk):
         step(k)
         ms.append(eng.last_op_ms())
     eng.profile_op(-1)
-    flop = 2 * 64 * 64 * 9 * 96 * 96 * B
+    flop = 2 * 64 * 64 * 9 * S * S * B
     m = float(np.mean(ms)) * 1e-3
-    return {"workload": "wav2lip_96x96_B16 -> paste into 512x512 (reference architecture; the 256x256 net of configs[1] does not exist in the reference, SURVEY M2)",
+    wl = ("wav2lip_96x96_B16 -> paste into 512x512 (reference architecture; the 256x256 net of configs[1] does not exist in the reference, SURVEY M2)"
+          if S == 96 else
+          "wav2lip_256x256_B16 -> paste into 512x512 (BASELINE configs[1]; EXTENDED generator of SURVEY 8(d) config 2 (ii) / section 7 step 4 -- "
+          "not a reference architecture, random weights, parity vs our own fp32 restatement only)")
+    return {"workload": wl, "gflop_per_frame": eng.flops_per_frame / 1e9,
             "value": world * K * B / (tot / 1e3), "unit": "frames/s", "ms_per_step": tot / K, "frames_per_step": B,
             "e2e": {"value": world * K * B / (e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(mel_pin[0].numel() * 4),
                     "d2h_bytes_per_step": int(out_pin.numel())},
             "p50_chunk_to_frame_ms": p50,
             "gpu_launches_per_step": eng.last_launches + 1, "dtype": "bf16",
             "algorithmic_tflops": eng.flops_per_frame * B / (tot / K * 1e-3) / 1e12,
-            "roofline": {"kernel": "k_conv_tma<2> (face_decoder_blocks.6 3x3 64->64 @96x96, B=16)", "bound": "tensor",
+            "roofline": {"kernel": f"k_conv_tma<2> (last face_decoder_block 3x3 64->64 @{S}x{S}, B=16)", "bound": "tensor",
                          "achieved": flop / m / 1e12, "peak": pk["tf"], "unit": "TFLOP/s", "frac": flop / m / 1e12 / pk["tf"],
                          "ms_per_launch": m * 1e3, "traffic": None, "peak_source": pk["src"] + " burst"}}
 
 
-def musetalk_leg(args, dev, local, rank, world, flush, timed_fn, pk):
+def musetalk_leg(args, dev, local, rank, world, flush, timed_fn, pk, shared=None):
     """BASELINE configs[2]-shaped leg: MuseTalk v1 architecture (SD-1.x UNet + sd-vae-ft-mse decoder, random weights), 16
     frames per step: 52-chunk audio window -> Whisper-tiny features (log-mel + encoder on the GPU) -> [16,50,384] chunks ->
     PE + UNet (t = 0) + VAE decode -> cv2-exact resize + mask blend into the 512x512 avatar frames."""
@@ -283,6 +290,8 @@ def musetalk_leg(args, dev, local, rank, world, flush, timed_fn, pk):
     wh = WhisperEngine(blob=blob_w, dims=WHISPER_TINY, device=local)
     wh.flops_per_call = meta_w["flops"]
     a2f = Audio2Feature(engine=wh)
+    if shared is not None:
+        shared["musetalk_engine"], shared["a2f"] = eng, a2f
     rng = np.random.default_rng(11 + rank)
     n_av = 12
     frames = torch.from_numpy(rng.integers(0, 200, (n_av, H, W, 3), dtype=np.uint8)).to(dev)
@@ -362,6 +371,154 @@ def musetalk_leg(args, dev, local, rank, world, flush, timed_fn, pk):
                          "ms_per_launch": m * 1e3, "traffic": None, "peak_source": pk["src"] + " burst"}}
 
 
+def mixed_leg(args, dev, local, rank, world, flush, timed_fn, shared, ernerf_blob, ernerf_cfg):
+    """BASELINE configs[4] / SURVEY 8(d) config 5: 64 concurrent mixed sessions on 8 GPUs = 8 sessions per GPU, heads round-robin by
+    session id (22 ErNeRF + 21 MuseTalk + 21 Wav2Lip in total, every GPU hosts all three heads).  This rank runs ITS 8 sessions
+    (global ids rank*8 .. rank*8+7): at --gpus 1 the line is the per-GPU slice, at --gpus 8 the full config.
+    One step = every session advances 16 video frames (0.64 s of video): ErNeRF 16 sequential frame renders on the session's own
+    context (per-session EMA state); MuseTalk one Whisper window + one 16-frame UNet/VAE pass + blend per session on the shared
+    engine; Wav2Lip one 16-frame pass per session, the same-GPU sessions COALESCED into one launch sequence by
+    scheduler.SharedEngine, + paste.  value = sessions x 16 frames / step time, aggregate over ranks."""
+    import ctypes
+    import torch
+    from helpers import ernerf_inputs, synthetic_speech, wav2lip_inputs
+    from mere_fusion_b200._lib import check, lib
+    from mere_fusion_b200.ernerf import ErnerfRenderer
+    from mere_fusion_b200.scheduler import SharedEngine, mixed_session_heads
+    from mere_fusion_b200.wav2lip import Wav2LipEngine
+    B, PER_GPU = 16, 8
+    n_total = PER_GPU * world
+    heads_all = mixed_session_heads(n_total)
+    # config 5 layout: 8 consecutive session ids per GPU (so that every GPU hosts all three heads)
+    mine = [(sid, heads_all[sid]) for sid in range(rank * PER_GPU, (rank + 1) * PER_GPU)]
+    n_lip = sum(1 for _, h in mine if h == "wav2lip")
+    lip_eng = SharedEngine(Wav2LipEngine(blob=shared["wav2lip_blob"], max_batch=B * max(1, n_lip), device=local), threaded=False)
+    muse_eng, a2f = shared["musetalk_engine"], shared["a2f"]
+    hL, hM = lip_eng.ctx.handle, muse_eng.ctx.handle
+    sessions = []
+    pins = []                                   # (pinned host result, device result) per session for the e2e arm
+    h2d = 0
+    for sid, head in mine:
+        rng = np.random.default_rng(1000 + sid)
+        out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+        out_pin = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
+        pins.append((out_pin, out))
+        if head == "ernerf":
+            ren = ErnerfRenderer(blob=ernerf_blob, cfg=ernerf_cfg, device=local)
+            ins = [ernerf_inputs((sid * 37 + f) % 300, H, W) for f in range(B)]
+            auds_pin = torch.from_numpy(np.stack([i[2] for i in ins])).pin_memory()
+            auds_dev = auds_pin.to(dev)
+            stage = torch.empty_like(auds_dev)
+            h2d += auds_pin.numel() * 4 + B * 84
+
+            def run(k, host, ren=ren, ins=ins, auds_dev=auds_dev, auds_pin=auds_pin, stage=stage, out=out):
+                src = auds_dev
+                if host:
+                    stage.copy_(auds_pin, non_blocking=True)
+                    src = stage
+                for f in range(B):
+                    p, intr, _, eye = ins[(f + k) % B]
+                    ren.render(p, intr, H, W, src[(f + k) % B], eye, out=out[f])
+            sessions.append((head, run, None))
+        elif head == "musetalk":
+            n_av = 12
+            frames = torch.from_numpy(rng.integers(0, 200, (n_av, H, W, 3), dtype=np.uint8)).to(dev)
+            lat_all = torch.from_numpy((rng.standard_normal((n_av, 8, 32, 32)) * 0.18215 * 5).astype(np.float16)).to(dev)
+            boxes, crops, moffs, masks, off = [], [], [], [], 0
+            for i in range(n_av):
+                x1, y1 = 150 + i, 140 + 2 * i
+                x2, y2 = x1 + 200 + i, y1 + 210
+                xs, ys, xe, ye = x1 - 40, y1 - 30, x2 + 35, y2 + 45
+                m = np.full((ye - ys, xe - xs, 3), 180, np.uint8)
+                boxes.append((y1, y2, x1, x2)); crops.append((ys, ye, xs, xe)); moffs.append(off)
+                masks.append(m.reshape(-1)); off += m.size
+            masks_d = torch.from_numpy(np.concatenate(masks)).to(dev)
+            audio_pin = torch.from_numpy(synthetic_speech(52 * 320, 300 + sid)).pin_memory()
+            audio_dev = audio_pin.to(dev)
+            audio_stage = torch.empty_like(audio_dev)
+            sel = torch.empty((B, 8, 32, 32), dtype=torch.float16, device=dev)
+            pred = torch.empty((B, 256, 256, 3), dtype=torch.uint8, device=dev)
+            h2d += audio_pin.numel() * 4
+
+            def run(k, host, frames=frames, lat_all=lat_all, boxes=boxes, crops=crops, moffs=moffs, masks_d=masks_d, audio_dev=audio_dev,
+                    audio_pin=audio_pin, audio_stage=audio_stage, sel=sel, pred=pred, out=out, n_av=n_av):
+                src = audio_dev
+                if host:
+                    audio_stage.copy_(audio_pin, non_blocking=True)
+                    src = audio_stage
+                idxs = [(k * B + i) % n_av for i in range(B)]
+                rows = np.array([(j,) + boxes[j] + crops[j] for j in idxs], np.int32)
+                mo = np.array([moffs[j] for j in idxs], np.int64)
+                chunks = a2f.audio2chunks_device(None, fps=25.0, batch_size=B, start=5.0, audio_dev=src)
+                torch.index_select(lat_all, 0, torch.as_tensor(idxs, device=dev), out=sel)
+                muse_eng.forward(sel, chunks, out=pred)
+                st = torch.cuda.current_stream(dev)
+                check(hM, lib().mf_paste_blend_u8(hM, ctypes.c_void_p(frames.data_ptr()), n_av, H, W, ctypes.c_void_p(pred.data_ptr()), 256, B,
+                                                  rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_void_p(masks_d.data_ptr()),
+                                                  masks_d.numel(), mo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                                  ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(st.cuda_stream)), "mf_paste_blend_u8")
+            sessions.append((head, run, None))
+        else:
+            n_av = 25
+            frames = torch.from_numpy(rng.integers(0, 256, (n_av, H, W, 3), dtype=np.uint8)).to(dev)
+            faces_all = torch.from_numpy(rng.integers(0, 256, (n_av, 96, 96, 3), dtype=np.uint8)).to(dev)
+            mel_pin = torch.from_numpy(wav2lip_inputs(B, mel_seed=500 + sid)[0]).pin_memory()
+            mel_dev = mel_pin.to(dev)
+            mel_stage = torch.empty_like(mel_dev)
+            sel = torch.empty((B, 96, 96, 3), dtype=torch.uint8, device=dev)
+            pred = torch.empty_like(sel)
+            h2d += mel_pin.numel() * 4
+
+            def submit(k, host, faces_all=faces_all, mel_dev=mel_dev, mel_pin=mel_pin, mel_stage=mel_stage, sel=sel, pred=pred, n_av=n_av):
+                src = mel_dev
+                if host:
+                    mel_stage.copy_(mel_pin, non_blocking=True)
+                    src = mel_stage
+                idxs = [(k * B + i) % n_av for i in range(B)]
+                torch.index_select(faces_all, 0, torch.as_tensor(idxs, device=dev), out=sel)
+                return lip_eng.submit(src, sel, out=pred), idxs
+
+            def finish(req, idxs, frames=frames, pred=pred, out=out, n_av=n_av):
+                lip_eng.wait(req)
+                rows = np.array([(j, 176, 368, 160, 352) for j in idxs], np.int32)
+                st = torch.cuda.current_stream(dev)
+                check(hL, lib().mf_paste_resize_u8(hL, ctypes.c_void_p(frames.data_ptr()), n_av, H, W, ctypes.c_void_p(pred.data_ptr()), 96, B,
+                                                   rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_void_p(out.data_ptr()),
+                                                   ctypes.c_void_p(st.cuda_stream)), "mf_paste_resize_u8")
+            sessions.append((head, submit, finish))
+
+    def tick(k, host):
+        lip = []
+        for head, fn, fin in sessions:
+            if head == "wav2lip":
+                lip.append((fn(k, host), fin))
+            else:
+                fn(k, host)
+        lip_eng.flush()                                            # ONE coalesced Wav2Lip pass for this GPU's sessions
+        for (req, idxs), fin in lip:
+            fin(req, idxs)
+        if host:
+            for out_pin, out in pins:
+                out_pin.copy_(out, non_blocking=True)
+
+    K = max(5, args.steps // 25)
+    lip_b0 = lip_eng.batches
+    tot, per, _ = timed_fn(lambda k: tick(k, False), K, 3)
+    lip_calls = (lip_eng.batches - lip_b0) / (K + 3)
+    e2e, _, _ = timed_fn(lambda k: tick(k, True), K, 3)
+    counts = {h: sum(1 for _, hh in mine if hh == h) for h in ("ernerf", "musetalk", "wav2lip")}
+    frames_step = PER_GPU * B
+    return {"workload": f"{n_total} concurrent mixed sessions on {world} GPU(s), 8 per GPU, heads round-robin by session id "
+                        f"(all ranks: {heads_all.count('ernerf')} ErNeRF + {heads_all.count('musetalk')} MuseTalk + {heads_all.count('wav2lip')} Wav2Lip; "
+                        "BASELINE configs[4] is this at 8 GPUs); one step = 16 frames per session",
+            "sessions_on_rank0": counts, "value": world * K * frames_step / (tot / 1e3), "unit": "frames/s (aggregate, all sessions)",
+            "ms_per_step": tot / K, "frames_per_step_per_gpu": frames_step,
+            "realtime_sessions_capacity": world * K * frames_step / (tot / 1e3) / 25.0,
+            "e2e": {"value": world * K * frames_step / (e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(sum(p.numel() for p, _ in pins))},
+            "wav2lip_engine_calls_per_step": lip_calls, "wav2lip_sessions_coalesced": n_lip}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -373,6 +530,7 @@ def main():
     ap.add_argument("--no-wav2lip", action="store_true")
     ap.add_argument("--no-musetalk", action="store_true")
     ap.add_argument("--no-asr", action="store_true")
+    ap.add_argument("--no-mixed", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -533,10 +691,14 @@ def main():
     value = world * args.steps / (total_ms / 1e3)
     e2e_value = world * args.steps / (e2e_ms / 1e3)
     heads = {}
+    shared = {}
     if not args.no_wav2lip:
-        heads["wav2lip"] = wav2lip_leg(args, dev, local, rank, world, flush, timed, peaks())
+        heads["wav2lip"] = wav2lip_leg(args, dev, local, rank, world, flush, timed, peaks(), shared=shared)
+        heads["wav2lip_256"] = wav2lip_leg(args, dev, local, rank, world, flush, timed, peaks(), S=256)
     if not args.no_musetalk:
-        heads["musetalk"] = musetalk_leg(args, dev, local, rank, world, flush, timed, peaks())
+        heads["musetalk"] = musetalk_leg(args, dev, local, rank, world, flush, timed, peaks(), shared=shared)
+    if not args.no_mixed and "wav2lip_blob" in shared and "musetalk_engine" in shared:
+        heads["mixed_sessions"] = mixed_leg(args, dev, local, rank, world, flush, timed, shared, blob, cfg)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -11,6 +11,7 @@ What changes relative to the reference:
     VideoFrame(bgr24) + exactly two AudioFrame(s16, mono, 16 kHz, 320 samples) per video frame.
 """
 import asyncio
+import contextlib
 import copy
 import ctypes
 import glob
@@ -55,6 +56,9 @@ class Avatar:
         with open(os.path.join(avatar_path, "coords.pkl"), "rb") as f:
             coords = pickle.load(f)
         return cls(read_dir(os.path.join(avatar_path, "full_imgs")), read_dir(os.path.join(avatar_path, "face_imgs")), coords)
+
+
+_NOLOCK = contextlib.nullcontext()
 
 
 class _Pasted:
@@ -119,8 +123,12 @@ class LipReal(BaseReal):
         if self._dev is None:
             import torch
             dev = self.engine.device
-            faces = torch.from_numpy(np.stack(self.face_list_cycle)).to(dev)
-            frames = torch.from_numpy(np.stack(self.frame_list_cycle)).to(dev)
+            if hasattr(self.avatar, "device_tensors"):           # packed avatar (avatar_pack.DeviceAvatar): one upload, device views
+                t = self.avatar.device_tensors(dev)
+                faces, frames = t["faces"], t["frames"]
+            else:
+                faces = torch.from_numpy(np.stack(self.face_list_cycle)).to(dev)
+                frames = torch.from_numpy(np.stack(self.frame_list_cycle)).to(dev)
             B, S = self.batch_size, faces.shape[1]
             Hf, Wf = frames.shape[1:3]
             self._dev = dict(faces=faces, frames=frames, S=S,
@@ -156,12 +164,13 @@ class LipReal(BaseReal):
                 rows[i] = (k, y1, y2, x1, x2)
             s = torch.cuda.current_stream(d["out"].device)
             fr = d["frames"]
-            check(self.engine.ctx.handle,
-                  lib().mf_paste_resize_u8(self.engine.ctx.handle, ctypes.c_void_p(fr.data_ptr()), fr.shape[0], fr.shape[1],
-                                           fr.shape[2], ctypes.c_void_p(d["pred"].data_ptr()), d["S"], B,
-                                           rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-                                           ctypes.c_void_p(d["out"].data_ptr()), ctypes.c_void_p(s.cuda_stream)),
-                  "mf_paste_resize_u8")
+            with getattr(self.engine, "lock", _NOLOCK):          # a shared engine (scheduler.SharedEngine): one caller at a time on its context
+                check(self.engine.ctx.handle,
+                      lib().mf_paste_resize_u8(self.engine.ctx.handle, ctypes.c_void_p(fr.data_ptr()), fr.shape[0], fr.shape[1],
+                                               fr.shape[2], ctypes.c_void_p(d["pred"].data_ptr()), d["S"], B,
+                                               rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                               ctypes.c_void_p(d["out"].data_ptr()), ctypes.c_void_p(s.cuda_stream)),
+                      "mf_paste_resize_u8")
             d["out_pin"].copy_(d["out"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
             full = d["out_pin"].numpy()

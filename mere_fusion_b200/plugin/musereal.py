@@ -26,7 +26,7 @@ import numpy as np
 
 from .basereal import BaseReal
 from .frames import AudioFrame, VideoFrame
-from .lipreal import LipReal, _Pasted, mirror_index
+from .lipreal import _NOLOCK, LipReal, _Pasted, mirror_index
 from .museasr import MuseASR
 
 
@@ -120,19 +120,11 @@ class MuseReal(BaseReal):
         if self._dev is None:
             import torch
             dev = self.engine.device
-            frames = torch.from_numpy(np.stack(self.frame_list_cycle)).to(dev)
-            lat = torch.cat([torch.as_tensor(np.asarray(l)) if not torch.is_tensor(l) else l for l in self.input_latent_list_cycle], dim=0)
-            lat = lat.to(device=dev, dtype=torch.float16).contiguous()              # [n, 8, 32, 32] (musereal.py:103)
-            offs, parts, off = [], [], 0
-            for m, (xs, ys, xe, ye) in zip(self.mask_list_cycle, self.mask_coords_list_cycle):
-                m = np.ascontiguousarray(m, np.uint8)
-                if m.ndim == 2:
-                    m = np.repeat(m[:, :, None], 3, axis=2)
-                assert m.shape == (ye - ys, xe - xs, 3), "mask size must equal its crop box (blending.py:109-121)"
-                offs.append(off)
-                parts.append(m.reshape(-1))
-                off += m.size
-            masks = torch.from_numpy(np.concatenate(parts)).to(dev)
+            if hasattr(self.avatar, "device_tensors"):           # packed avatar (avatar_pack.DeviceAvatar): one upload, device views
+                t = self.avatar.device_tensors(dev)
+                frames, lat, masks, offs = t["frames"], t["latents"], t["masks"], t["mask_off"]
+            else:
+                frames, lat, masks, offs = self._upload_avatar(dev)
             B = self.batch_size
             Hf, Wf = frames.shape[1:3]
             self._dev = dict(frames=frames, latents=lat, masks=masks, mask_off=offs,
@@ -144,6 +136,23 @@ class MuseReal(BaseReal):
                              out_pin=torch.empty((B, Hf, Wf, 3), dtype=torch.uint8).pin_memory(),
                              pred_pin=torch.empty((B, 256, 256, 3), dtype=torch.uint8).pin_memory())
         return self._dev
+
+    def _upload_avatar(self, dev):
+        import torch
+        frames = torch.from_numpy(np.stack(self.frame_list_cycle)).to(dev)
+        lat = torch.cat([torch.as_tensor(np.asarray(l)) if not torch.is_tensor(l) else l for l in self.input_latent_list_cycle], dim=0)
+        lat = lat.to(device=dev, dtype=torch.float16).contiguous()              # [n, 8, 32, 32] (musereal.py:103)
+        offs, parts, off = [], [], 0
+        for m, (xs, ys, xe, ye) in zip(self.mask_list_cycle, self.mask_coords_list_cycle):
+            m = np.ascontiguousarray(m, np.uint8)
+            if m.ndim == 2:
+                m = np.repeat(m[:, :, None], 3, axis=2)
+            assert m.shape == (ye - ys, xe - xs, 3), "mask size must equal its crop box (blending.py:109-121)"
+            offs.append(off)
+            parts.append(m.reshape(-1))
+            off += m.size
+        masks = torch.from_numpy(np.concatenate(parts)).to(dev)
+        return frames, lat, masks, offs
 
     def infer_batch(self, whisper_chunks, index):
         """one pass of the hot path for `batch_size` frames starting at avatar index `index`"""
@@ -170,13 +179,14 @@ class MuseReal(BaseReal):
                 moff[i] = d["mask_off"][k]
             s = torch.cuda.current_stream(d["out"].device)
             fr = d["frames"]
-            check(self.engine.ctx.handle,
-                  lib().mf_paste_blend_u8(self.engine.ctx.handle, ctypes.c_void_p(fr.data_ptr()), fr.shape[0], fr.shape[1], fr.shape[2],
-                                          ctypes.c_void_p(d["pred"].data_ptr()), 256, B,
-                                          rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_void_p(d["masks"].data_ptr()),
-                                          d["masks"].numel(), moff.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                                          ctypes.c_void_p(d["out"].data_ptr()), ctypes.c_void_p(s.cuda_stream)),
-                  "mf_paste_blend_u8")
+            with getattr(self.engine, "lock", _NOLOCK):          # a shared engine (scheduler.SharedEngine): one caller at a time on its context
+                check(self.engine.ctx.handle,
+                      lib().mf_paste_blend_u8(self.engine.ctx.handle, ctypes.c_void_p(fr.data_ptr()), fr.shape[0], fr.shape[1], fr.shape[2],
+                                              ctypes.c_void_p(d["pred"].data_ptr()), 256, B,
+                                              rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_void_p(d["masks"].data_ptr()),
+                                              d["masks"].numel(), moff.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                              ctypes.c_void_p(d["out"].data_ptr()), ctypes.c_void_p(s.cuda_stream)),
+                      "mf_paste_blend_u8")
             d["out_pin"].copy_(d["out"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
             full = d["out_pin"].numpy()

@@ -31,6 +31,65 @@ FACE_DEC = [[("c", 512, 1, 1, 0, 0)],
             [("t", 64, 3, 2, 1, 1), ("r", 64), ("r", 64)]]
 
 
+# ---- the 256x256 EXTENSION (BASELINE configs[1]).  NOT a reference architecture: the
+# reference generator only accepts 96x96 (a 256 input fails at the first skip-concat, wav2lip.py:107).  Same block vocabulary,
+# one more stride-2 stage at 512 channels on each side, a 4x4 bottleneck conv / transposed conv instead of 3x3; the audio
+# encoder and the output block (80 -> 32 -> 3) are unchanged.  Parity for this net is against our own fp32 restatement only.
+FACE_ENC_256 = [[(16, 7, 1, 3, False)],
+                [(32, 3, 2, 1, False), (32, 3, 1, 1, True), (32, 3, 1, 1, True)],                       # 128
+                [(64, 3, 2, 1, False), (64, 3, 1, 1, True), (64, 3, 1, 1, True), (64, 3, 1, 1, True)],  # 64
+                [(128, 3, 2, 1, False), (128, 3, 1, 1, True), (128, 3, 1, 1, True)],                    # 32
+                [(256, 3, 2, 1, False), (256, 3, 1, 1, True), (256, 3, 1, 1, True)],                    # 16
+                [(512, 3, 2, 1, False), (512, 3, 1, 1, True)],                                          # 8
+                [(512, 3, 2, 1, False), (512, 3, 1, 1, True)],                                          # 4
+                [(512, 4, 1, 0, False), (512, 1, 1, 0, False)]]                                         # 1
+FACE_DEC_256 = [[("c", 512, 1, 1, 0, 0)],
+                [("t", 512, 4, 1, 0, 0), ("r", 512)],                                                   # 4
+                [("t", 512, 3, 2, 1, 1), ("r", 512), ("r", 512)],                                       # 8
+                [("t", 512, 3, 2, 1, 1), ("r", 512), ("r", 512)],                                       # 16
+                [("t", 384, 3, 2, 1, 1), ("r", 384), ("r", 384)],                                       # 32
+                [("t", 256, 3, 2, 1, 1), ("r", 256), ("r", 256)],                                       # 64
+                [("t", 128, 3, 2, 1, 1), ("r", 128), ("r", 128)],                                       # 128
+                [("t", 64, 3, 2, 1, 1), ("r", 64), ("r", 64)]]                                          # 256
+ARCHS = {96: (FACE_ENC, FACE_DEC), 256: (FACE_ENC_256, FACE_DEC_256)}
+
+
+def wav2lip_param_shapes(face_hw=96):
+    """name -> shape of every state_dict tensor of the generator for `face_hw` (96: the reference module,
+    wav2lip/models/wav2lip.py:12-85; 256: the extension above), same key naming"""
+    enc, dec = ARCHS[face_hw]
+    shapes = {}
+
+    def block(prefix, cin, cout, k, transpose=False):
+        shapes[prefix + ".conv_block.0.weight"] = (cin, cout, k, k) if transpose else (cout, cin, k, k)
+        shapes[prefix + ".conv_block.0.bias"] = (cout,)
+        for n in ("weight", "bias", "running_mean", "running_var"):
+            shapes[prefix + ".conv_block.1." + n] = (cout,)
+        shapes[prefix + ".conv_block.1.num_batches_tracked"] = ()
+
+    cin, enc_c = 6, []
+    for i, blk in enumerate(enc):
+        for j, (cout, k, s, p, r) in enumerate(blk):
+            block(f"face_encoder_blocks.{i}.{j}", cin, cout, k)
+            cin = cout
+        enc_c.append(cin)
+    cin = 1
+    for j, (cout, k, st, p, r) in enumerate(AUDIO_ENC):
+        block(f"audio_encoder.{j}", cin, cout, k)
+        cin = cout
+    for i, blk in enumerate(dec):
+        for j, spec in enumerate(blk):
+            cout = spec[1]
+            k = spec[2] if spec[0] != "r" else 3
+            block(f"face_decoder_blocks.{i}.{j}", cin, cout, k, transpose=spec[0] == "t")
+            cin = cout
+        cin += enc_c[len(enc) - 1 - i]
+    block("output_block.0", cin, 32, 3)
+    shapes["output_block.1.weight"] = (3, 32, 1, 1)
+    shapes["output_block.1.bias"] = (3,)
+    return shapes
+
+
 def _np(v):
     return v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
 
@@ -48,18 +107,22 @@ def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
         return (sd[cb + ".0.weight"], sd[cb + ".0.bias"],
                 (sd[cb + ".1.weight"], sd[cb + ".1.bias"], sd[cb + ".1.running_mean"], sd[cb + ".1.running_var"]))
 
+    if face_hw not in ARCHS:
+        raise ValueError(f"pack_wav2lip: no generator architecture for {face_hw}x{face_hw} crops (have {sorted(ARCHS)})")
+    FACE_ENC, FACE_DEC = ARCHS[face_hw]
+    n = len(FACE_ENC)
     pb = ProgramBuilder(nominal_batch)
     S = face_hw
-    # spatial size of every encoder stage (96, 48, 24, 12, 6, 3, 1 for 96x96)
+    # spatial size of every encoder stage (96, 48, 24, 12, 6, 3, 1 for 96x96; 256, 128, ..., 4, 1 for 256x256)
     sizes = [S]
     for blk in FACE_ENC[1:]:
         _, k, s, p, _ = blk[0]
         sizes.append((sizes[-1] + 2 * p - k) // s + 1)
     enc_c = [blk[-1][0] for blk in FACE_ENC]                      # 16, 32, 64, 128, 256, 512, 512
     dec_c = [blk[0][1] for blk in FACE_DEC]                       # 512, 512, 512, 384, 256, 128, 64
-    # cat buffer i holds [decoder block (6 - i) output | encoder block i output] at resolution sizes[i]
-    cat = [pb.buffer(sizes[i], sizes[i], dec_c[6 - i] + enc_c[i]) for i in range(7)]
-    cat_off = [dec_c[6 - i] for i in range(7)]
+    # cat buffer i holds [decoder block (n - 1 - i) output | encoder block i output] at resolution sizes[i]
+    cat = [pb.buffer(sizes[i], sizes[i], dec_c[n - 1 - i] + enc_c[i]) for i in range(n)]
+    cat_off = [dec_c[n - 1 - i] for i in range(n)]
 
     in_face = pb.buffer(S, S, 8)
     in_mel = pb.buffer(80, 16, 8)
@@ -93,10 +156,9 @@ def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
     # ---- face decoder (wav2lip.py:57-81,102-112)
     cur, coff = audio_emb, 0
     for i, blk in enumerate(FACE_DEC):
-        tgt = cat[6 - i]
+        tgt = cat[n - 1 - i]
         for j, spec in enumerate(blk):
             last = j == len(blk) - 1
-            res_t = tgt[0] if False else None
             Ht = pb.buffers[tgt][0]
             if last:
                 out, ooff = tgt, 0

@@ -35,6 +35,13 @@ FACE_DEC = [[("c", 1, 0)], [("t", 1, 0, 0), ("r",)], [("t", 2, 1, 1), ("r",), ("
             [("t", 2, 1, 1), ("r",), ("r",)], [("t", 2, 1, 1), ("r",), ("r",)], [("t", 2, 1, 1), ("r",), ("r",)]]
 
 
+# 256x256 EXTENSION (not a reference architecture): one more stride-2 512-channel stage on each
+# side and a 4x4 bottleneck.  PARITY UNPINNED by construction -- this restatement is the only oracle for that net.
+FACE_ENC_256 = FACE_ENC[:6] + [[(3, 2, 1, False), (3, 1, 1, True)], [(4, 1, 0, False), (1, 1, 0, False)]]
+FACE_DEC_256 = [FACE_DEC[0], [("t", 1, 0, 0), ("r",)]] + [[("t", 2, 1, 1), ("r",), ("r",)]] * 6
+ARCHS = {96: (FACE_ENC, FACE_DEC), 256: (FACE_ENC_256, FACE_DEC_256)}
+
+
 def _bn(sd, p, x):
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], False, 0.0, 1e-5)
 
@@ -56,7 +63,9 @@ def convT_block(sd, prefix, x, stride, padding, output_padding):
 
 
 def wav2lip_forward(sd, mel, img):
-    """wav2lip.py:87-125 for 4-D inputs.  mel [B,1,80,16], img [B,6,96,96] fp32 -> [B,3,96,96] in (0,1)"""
+    """wav2lip.py:87-125 for 4-D inputs.  mel [B,1,80,16], img [B,6,96,96] fp32 -> [B,3,96,96] in (0,1)
+    (a 256x256 img selects the extension above)"""
+    FACE_ENC, FACE_DEC = ARCHS[int(img.shape[-1])]
     x = mel
     for j, (st, p, r) in enumerate(AUDIO_ENC):
         x = conv_block(sd, f"audio_encoder.{j}", x, st, p, r)

@@ -74,17 +74,22 @@ def wav2lip_param_shapes():
     return shapes
 
 
-def seeded_wav2lip_state(seed=2):
+def seeded_wav2lip_state(seed=2, face_hw=96):
     """deterministic (numpy RNG, key order) weights with NON-trivial BatchNorm running statistics --
-    eval-mode BN is part of the arithmetic."""
+    eval-mode BN is part of the arithmetic.  face_hw=256: the extended generator (not in the reference)"""
     import torch
     rng = np.random.default_rng(seed)
     sd = {}
-    for name, shp in wav2lip_param_shapes().items():
+    if face_hw == 96:
+        shapes = wav2lip_param_shapes()
+    else:
+        from mere_fusion_b200.wav2lip_pack import wav2lip_param_shapes as pack_shapes
+        shapes = pack_shapes(face_hw)
+    for name, shp in shapes.items():
         if name.endswith("num_batches_tracked"):
             sd[name] = torch.tensor(100, dtype=torch.long)
         elif name.endswith("conv_block.0.weight") or name == "output_block.1.weight":
-            if "face_decoder" in name and len(shp) == 4 and ".0.conv_block" in name and shp[0] > shp[1] and shp[2] == 3 \
+            if "face_decoder" in name and len(shp) == 4 and ".0.conv_block" in name and shp[0] > shp[1] and shp[2] in (3, 4) \
                     and not name.startswith("face_decoder_blocks.0"):
                 fan_in = shp[0] * shp[2] * shp[3] / 4.0          # ConvTranspose2d: ~1/4 of the taps hit a pixel
             else:

@@ -1,0 +1,80 @@
+"""GPU side of the session scheduler: same-GPU Wav2Lip sessions coalesced into ONE engine pass give
+each session what it would have got alone (to the batch-size dependent split-K summation order, see
+tests/test_wav2lip_gpu.py), through the C ABI, from the main thread and from concurrent session threads."""
+import threading
+
+import numpy as np
+import pytest
+
+from helpers import psnr, seeded_wav2lip_state, wav2lip_inputs
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def shared():
+    from mere_fusion_b200.scheduler import SharedEngine
+    from mere_fusion_b200.wav2lip import Wav2LipEngine
+    sh = SharedEngine(Wav2LipEngine(seeded_wav2lip_state(2), max_batch=48, device=0), window_ms=50.0)
+    yield sh
+    sh.shutdown()
+
+
+def _session_inputs(i, n=16):
+    mel, faces = wav2lip_inputs(n, mel_seed=70 + i, face_seed=80 + i)
+    return mel, faces
+
+
+def test_coalesced_sessions_match_oracle_and_solo(shared):
+    from oracle import wav2lip_oracle as O
+    sd = seeded_wav2lip_state(2)
+    ins = [_session_inputs(i) for i in range(3)]
+    f32 = [torch.empty(16, 96, 96, 3, device="cuda") for _ in ins]
+    b0 = shared.batches
+    reqs = [shared.submit(torch.from_numpy(m).cuda(), torch.from_numpy(f).cuda(), out=torch.empty(16, 96, 96, 3, dtype=torch.uint8, device="cuda"),
+                          out_f32=o) for (m, f), o in zip(ins, f32)]
+    shared.flush()
+    outs = [shared.wait(r) for r in reqs]
+    torch.cuda.synchronize()
+    assert shared.batches == b0 + 1                               # three sessions, ONE launch sequence
+    for (m, f), o32, o8 in zip(ins, f32, outs):
+        pred, u8 = O.infer(sd, m, f)
+        assert psnr(o32.cpu().numpy(), pred) >= 38.0
+        assert np.abs(o8.cpu().numpy().astype(int) - u8.astype(int)).mean() < 1.5
+        solo = torch.empty(16, 96, 96, 3, device="cuda")
+        shared.engine.forward(torch.from_numpy(m).cuda(), torch.from_numpy(f).cuda(), out_f32=solo)
+        torch.cuda.synchronize()
+        assert psnr(solo.cpu().numpy(), o32.cpu().numpy()) > 50.0
+
+
+def test_concurrent_session_threads(shared):
+    ins = [_session_inputs(10 + i) for i in range(3)]
+    res, errs = {}, []
+    gate = threading.Barrier(3)
+
+    def session(i):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                m, f = ins[i]
+                md, fd = torch.from_numpy(m).cuda(), torch.from_numpy(f).cuda()
+                o32 = torch.empty(16, 96, 96, 3, device="cuda")
+                gate.wait()
+                shared.forward(md, fd, out_f32=o32)
+                torch.cuda.current_stream().synchronize()
+                res[i] = o32.cpu().numpy()
+        except Exception as e:                                    # noqa: BLE001
+            errs.append(e)
+
+    b0, r0 = shared.batches, shared.requests
+    th = [threading.Thread(target=session, args=(i,)) for i in range(3)]
+    [t.start() for t in th]
+    [t.join(timeout=120) for t in th]
+    assert not errs, errs
+    assert shared.requests == r0 + 3 and shared.batches - b0 <= 3
+    for i in range(3):
+        m, f = ins[i]
+        solo = torch.empty(16, 96, 96, 3, device="cuda")
+        shared.engine.forward(torch.from_numpy(m).cuda(), torch.from_numpy(f).cuda(), out_f32=solo)
+        torch.cuda.synchronize()
+        assert psnr(solo.cpu().numpy(), res[i]) > 50.0

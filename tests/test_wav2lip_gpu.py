@@ -66,3 +66,33 @@ def test_errors(engine):
     mel, faces = wav2lip_inputs(17)
     with pytest.raises(MfError):
         engine.forward(torch.from_numpy(mel).cuda(), torch.from_numpy(faces).cuda())
+
+
+# ---- the 256x256 extension (BASELINE configs[1]; not a reference architecture): parity vs our own fp32
+# restatement only -- "parity unpinned", stated in DESIGN.md 4.3.  Deeper net (8 stages): same tolerance.
+@pytest.fixture(scope="module")
+def engine256():
+    from mere_fusion_b200.wav2lip import Wav2LipEngine
+    return Wav2LipEngine(seeded_wav2lip_state(2, face_hw=256), max_batch=4, device=0, face_hw=256)
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_256_extension_vs_oracle(engine256, B):
+    from oracle import wav2lip_oracle as O
+    mel, faces = wav2lip_inputs(B, mel_seed=50 + B, face_seed=60 + B, S=256)
+    pred, u8 = O.infer(seeded_wav2lip_state(2, face_hw=256), mel, faces)
+    f32 = torch.empty(B, 256, 256, 3, device="cuda")
+    out = engine256.forward(torch.from_numpy(mel).cuda(), torch.from_numpy(faces).cuda(), out_f32=f32)
+    torch.cuda.synchronize()
+    got = f32.cpu().numpy()
+    p = psnr(got, pred)
+    assert p >= PSNR_MIN_DB, f"PSNR {p:.2f} dB"
+    assert np.abs(got - pred).max() <= 0.1
+    assert np.abs(out.cpu().numpy().astype(int) - u8.astype(int)).mean() < 1.5
+    assert abs(engine256.flops_per_frame / 1e9 - 55.88) < 0.1          # ~56 GFLOP/frame
+
+
+def test_unknown_crop_size_is_refused():
+    from mere_fusion_b200.wav2lip_pack import pack_wav2lip
+    with pytest.raises(ValueError):
+        pack_wav2lip(seeded_wav2lip_state(2), face_hw=128)
