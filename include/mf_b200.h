@@ -149,7 +149,7 @@ typedef struct mf_ernerf_frame {
 /* optional observability for the parity tests (all device pointers, any may be NULL) */
 typedef struct mf_ernerf_debug {
     float *nears, *fars;     /* [N] */
-    int32_t *round_info;     /* [17*4] per round: n_alive, n_step, samples emitted, 0 */
+    int32_t *round_info;     /* [17*4] per round: n_alive, tiles handed out, samples emitted, n_step */
     float *weights_sum;      /* [N] */
     float *image_head;       /* [N,3] composited head before background */
     float *enc_a;            /* [32] the (smoothed) audio feature used */
