@@ -386,7 +386,7 @@ def musetalk_leg(args, dev, local, rank, world, flush, timed_fn, pk, shared=None
 def mixed_leg(args, dev, local, rank, world, flush, timed_fn, shared, ernerf_blob, ernerf_cfg):
     """BASELINE configs[4] / SURVEY 8(d) config 5: 64 concurrent mixed sessions on 8 GPUs = 8 sessions per GPU, heads round-robin by
     session id (22 ErNeRF + 21 MuseTalk + 21 Wav2Lip in total, every GPU hosts all three heads).  This rank runs ITS 8 sessions
-    (global ids rank*8 .. rank*8+7): at --gpus 1 the line is the per-GPU slice, at --gpus 8 the full config.
+    (round-robin, dist.shard): at --gpus 1 the line is the per-GPU slice, at --gpus 8 the full config.
     One step = every session advances 16 video frames (0.64 s of video): ErNeRF 16 sequential frame renders on the session's own
     context (per-session EMA state); MuseTalk one Whisper window + one 16-frame UNet/VAE pass + blend per session on the shared
     engine; Wav2Lip one 16-frame pass per session, the same-GPU sessions COALESCED into one launch sequence by
@@ -396,13 +396,14 @@ def mixed_leg(args, dev, local, rank, world, flush, timed_fn, shared, ernerf_blo
     from helpers import ernerf_inputs, synthetic_speech, wav2lip_inputs
     from mere_fusion_b200._lib import check, lib
     from mere_fusion_b200.ernerf import ErnerfRenderer
-    from mere_fusion_b200.scheduler import SharedEngine, mixed_session_heads
+    from mere_fusion_b200.dist import mixed_sessions, shard
+    from mere_fusion_b200.scheduler import SharedEngine
     from mere_fusion_b200.wav2lip import Wav2LipEngine
     B, PER_GPU = 16, 8
     n_total = PER_GPU * world
-    heads_all = mixed_session_heads(n_total)
-    # config 5 layout: 8 consecutive session ids per GPU (so that every GPU hosts all three heads)
-    mine = [(sid, heads_all[sid]) for sid in range(rank * PER_GPU, (rank + 1) * PER_GPU)]
+    heads_all = [h for h, _ in mixed_sessions(n_total)]          # interleaved by head (22 + 21 + 21 at 64 sessions)
+    # session -> GPU: round-robin (dist.shard), which gives every GPU all three heads
+    mine = shard(list(enumerate(heads_all)), world, rank)
     n_lip = sum(1 for _, h in mine if h == "wav2lip")
     lip_eng = SharedEngine(Wav2LipEngine(blob=shared["wav2lip_blob"], max_batch=B * max(1, n_lip), device=local), threaded=False)
     muse_eng, a2f = shared["musetalk_engine"], shared["a2f"]

@@ -23,8 +23,10 @@ HEADS = ("ernerf", "musetalk", "wav2lip")
 
 
 def mixed_session_heads(n_sessions):
-    """heads assigned round-robin (64 sessions -> 22 ErNeRF + 21 MuseTalk + 21 Wav2Lip)"""
-    return [HEADS[i % 3] for i in range(n_sessions)]
+    """heads interleaved (64 sessions -> 22 ErNeRF + 21 MuseTalk + 21 Wav2Lip), same order as
+    dist.mixed_sessions"""
+    from .dist import mixed_sessions
+    return [h for h, _ in mixed_sessions(n_sessions)]
 
 
 class Placement:

@@ -1,5 +1,6 @@
 """Wav2LipEngine: torch tensors in/out around mf_wav2lip_forward (include/mf_b200.h).
 Replaces `model(mel_batch, img_batch)` plus the batch build and x255 of lipreal.py:108-126."""
+import contextlib
 import ctypes
 
 import numpy as np
@@ -100,6 +101,7 @@ class MelFrontEnd:
         from .audio_mel import mel_filterbank
         self.ctx = engine.ctx
         self.device = engine.device
+        self._lock = getattr(engine, "lock", None) or contextlib.nullcontext()   # scheduler.SharedEngine: one caller at a time per context
         self.filters = torch.from_numpy(np.ascontiguousarray(mel_filterbank(), np.float32)).to(self.device)
         self._pin = None
         self._h2d_done = None
@@ -133,7 +135,8 @@ class MelFrontEnd:
         self._h2d_done.record(s)
         starts = self.chunk_starts(n_chunks, left_size, right_size, fps, a.size // 200 + 1)
         out = torch.empty((len(starts), 1, 80, 16), dtype=torch.float32, device=self.device)
-        check(self.ctx.handle, lib().mf_wav2lip_mel_chunks(self.ctx.handle, _ptr(d), a.size, _ptr(self.filters),
-                                                           starts.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(starts), _ptr(out),
-                                                           ctypes.c_void_p(s.cuda_stream)), "mf_wav2lip_mel_chunks")
+        with self._lock:
+            check(self.ctx.handle, lib().mf_wav2lip_mel_chunks(self.ctx.handle, _ptr(d), a.size, _ptr(self.filters),
+                                                               starts.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(starts), _ptr(out),
+                                                               ctypes.c_void_p(s.cuda_stream)), "mf_wav2lip_mel_chunks")
         return out

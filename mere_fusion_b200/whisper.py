@@ -6,6 +6,7 @@ with ONE C-ABI call (mf_whisper_features): log-mel, zero padding to the 30 s con
 [T, n_layer + 1, n_state] embedding gather all happen on the device.  The index arithmetic of get_sliced_feature /
 feature2chunks (audio2feature.py:16-45, 82-97) is mirrored exactly on the host (it is a handful of integers)."""
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -23,6 +24,8 @@ class WhisperEngine(ConvNet):
             self.flops_per_call = pb.flops_per_sample
         self.n_embeds = dims["n_audio_layer"] + 1
         self.n_state = dims["n_audio_state"]
+        self._host_lock = threading.Lock()
+        self._last_done = None
         super().__init__(blob, 1, device)
 
     def features(self, audio, T=None, out=None, stream=None):
@@ -35,8 +38,16 @@ class WhisperEngine(ConvNet):
         if out is None:
             out = torch.empty((T, self.n_embeds, self.n_state), dtype=torch.float32, device=self.device)
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
-        check(self.ctx.handle, lib().mf_whisper_features(self.ctx.handle, _ptr(audio), n, _ptr(out), T, ctypes.c_void_p(s.cuda_stream)),
-              "mf_whisper_features")
+        # one audio processor may serve several MuseReal sessions (threads, each on its own stream): the context and its
+        # activation workspace are single-user, so calls are serialised on the host (lock) AND on the device (event chain)
+        with self._host_lock:
+            if self._last_done is not None:
+                s.wait_event(self._last_done)
+            check(self.ctx.handle, lib().mf_whisper_features(self.ctx.handle, _ptr(audio), n, _ptr(out), T, ctypes.c_void_p(s.cuda_stream)),
+                  "mf_whisper_features")
+            ev = torch.cuda.Event()
+            ev.record(s)
+            self._last_done = ev
         return out
 
 

@@ -78,3 +78,49 @@ def test_concurrent_session_threads(shared):
         shared.engine.forward(torch.from_numpy(m).cuda(), torch.from_numpy(f).cuda(), out_f32=solo)
         torch.cuda.synchronize()
         assert psnr(solo.cpu().numpy(), res[i]) > 50.0
+
+
+def test_two_lipreal_sessions_on_one_shared_engine():
+    """plugin level: two LipReal sessions (threads) driven concurrently through ONE SharedEngine and packed avatars emit the
+    frames a session on its own engine emits (pasted region equal to the batch-size dependent rounding, rest identical)"""
+    from test_plugin_cpu import _fake_avatar, clip_10s, make_opt
+    from test_plugin_gpu import _run
+    from mere_fusion_b200.avatar_pack import DeviceAvatar, pack_lip_avatar
+    from mere_fusion_b200.plugin.lipreal import LipReal
+    from mere_fusion_b200.scheduler import SessionScheduler
+    from mere_fusion_b200.wav2lip import Wav2LipEngine
+    sd = seeded_wav2lip_state(2)
+    wav = clip_10s()
+    chunks = [wav[i * 320:(i + 1) * 320] for i in range(140)]
+    solo = LipReal(make_opt(), engine=Wav2LipEngine(sd, max_batch=16, device=0), avatar=_fake_avatar())
+    v_ref, _ = _run(solo, 48, chunks)
+    ref = [f.to_ndarray().copy() for f in v_ref[:48]]
+
+    sched = SessionScheduler(n_gpus=1, sessions_per_engine=2, batch_size=16, window_ms=5.0)
+    packed = pack_lip_avatar(_fake_avatar())
+    reals, res = [], {}
+    for sid in ("a", "b"):
+        g, eng = sched.open(sid, "wav2lip", factory=lambda gpu, mb: Wav2LipEngine(sd, max_batch=mb, device=gpu))
+        assert g == 0 and eng.max_batch == 32
+        reals.append(LipReal(make_opt(), engine=eng, avatar=DeviceAvatar(packed), device=g))
+    assert reals[0].engine is reals[1].engine
+
+    def drive(i):
+        v, a = _run(reals[i], 48, chunks)
+        res[i] = ([f.to_ndarray().copy() for f in v[:48]], len(v), len(a))
+
+    th = [threading.Thread(target=drive, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    shared = reals[0].engine
+    assert shared.requests >= 2 * 3 and shared.batches <= shared.requests
+    for i in range(2):
+        frames, nv, na = res[i]
+        assert len(frames) == 48 and abs(na - 2 * nv) <= 2
+        for k, (f, r) in enumerate(zip(frames, ref)):
+            outside = np.ones(f.shape[:2], bool)
+            outside[176:368, 160:352] = False
+            assert np.array_equal(f[outside], r[outside]), f"session {i} frame {k}"
+            assert np.abs(f.astype(int) - r.astype(int)).max() <= 8 and np.abs(f.astype(int) - r.astype(int)).mean() < 0.1
+    sched.close("a"), sched.close("b")
+    assert not sched.engines()
