@@ -792,6 +792,12 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
     for (int nt = (o.Cout + 255) / 256; nt <= std::max(1, o.Cout / 32); nt++) {
         const int bn = (((o.Cout + nt - 1) / nt) + 15) / 16 * 16;
         if (bn > 256) continue;
+        {   // the choice must leave room for the ring: with the row-halo groups a stage holds ndx B tiles (a 256-channel layer
+            // with fewer than one tile per SM -- no CTA pair to halve the B tile -- would need 113 KB per stage: take a narrower BN)
+            const int cg_c = (m_tiles >= sms && bn % 32 == 0 && o.mode == 0) ? 2 : 1;
+            const int stage_c = (ndx > 1 ? 17 * 1024 : A_STAGE_BYTES) + ndx * (bn * 128 / cg_c);
+            if ((CT_SMEM_LIMIT - 1024 - 256 - 4096) / stage_c < (ndx > 1 ? 3 : 2)) continue;
+        }
         const double kb_cost = ndx * std::max(2.0 * bn, 1.5 * (128 + bn));
         static const int splits[] = {1, 2, 3, 4, 6, 8};
         for (int sp : splits) {

@@ -129,3 +129,7 @@ def test_conv3x3_row_halo_tiles():
     run_case(1, 3, 128, 64, 48, 3, 1, 1, in_coff=64, in_C=192, out_coff=16, out_C=96, seed=14)
     run_case(16, 40, 128, 64, 64, 3, 1, 1, bn=False, relu=False, seed=15)      # 640 row tiles: CTA pairs (cta_group::2)
     run_case(2, 6, 128, 64, 64, (1, 3)[1], 1, (0, 1)[1], seed=16)
+    # 256 output channels with fewer row tiles than SMs (no CTA pair): three 256-row B tiles per stage would not fit the ring
+    # twice -- the planner must take a narrower BN (MuseTalk VAE 256 -> 256 @128x128 at B = 1 failed to plan before)
+    run_case(1, 100, 128, 256, 256, 3, 1, 1, residual=True, seed=17)
+    run_case(1, 64, 128, 512, 256, 3, 1, 1, seed=18)

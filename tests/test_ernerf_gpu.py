@@ -301,7 +301,9 @@ def test_full_size_512_properties(env):
     hit_o, hit_g = n_ref < 1e30, dbg["nears"] < 1e30
     assert (hit_o != hit_g).sum() <= 8 and hit_o.sum() > 50000
     both = hit_o & hit_g
-    assert (dbg["nears"][both] == n_ref[both]).mean() > 0.999 and (dbg["fars"][both] == f_ref[both]).mean() > 0.999
+    # (bit-exactness of near/far for GIVEN rays is test_near_far_bit_exact / test_explicit_rays_first_march_bit_exact)
+    np.testing.assert_allclose(dbg["nears"][both], n_ref[both], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dbg["fars"][both], f_ref[both], rtol=1e-5, atol=1e-6)
     ri = dbg["round_info"]                                              # per round: n_alive, tile tickets, samples emitted, n_step
     n_alive0, n_step0, emitted0 = int(ri[0, 0]), int(ri[0, 3]), int(ri[0, 2])
     assert (n_alive0, n_step0) == (N, 1)                                # renderer.py:240-241,256: every ray starts alive
@@ -323,7 +325,7 @@ def test_full_size_512_properties(env):
     _, f_w, _ = run(1.0)
     _, f_k, _ = run(0.0)
     _, f_g, _ = run(0.5)
-    assert np.array_equal(f_w, f_a)                                    # NULL background = white (opt.bg_img default)
+    assert np.abs(f_w - f_a).max() < 1e-6                              # NULL background = white (opt.bg_img default)
     c = f_w - f_k
     inside = (f_w > 1e-3) & (f_w < 1 - 1e-3) & (f_k > 1e-3)            # away from the clamp
     assert c.min() >= -2e-3

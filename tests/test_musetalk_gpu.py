@@ -185,7 +185,7 @@ def test_musetalk_full_config_vs_oracle():
     lat = (rng.standard_normal((B, 8, 32, 32)) * 0.18215 * 5).astype(np.float16)
     wh = rng.standard_normal((B, 50, 384)).astype(np.float16)
     pred, img, u8 = M.infer(usd, vsd, lat.astype(np.float32), wh.astype(np.float32), u, v)
-    eng = MuseTalkEngine(usd, vsd, u, v, max_batch=B)
+    eng = MuseTalkEngine(usd, vsd, u, v, max_batch=5)
     f32 = torch.empty(B, 256, 256, 3, device="cuda")
     out = eng.forward(torch.from_numpy(lat).cuda(), torch.from_numpy(wh).cuda(), out_f32=f32)
     torch.cuda.synchronize()
@@ -203,3 +203,9 @@ def test_musetalk_full_config_vs_oracle():
     eng.forward(torch.from_numpy(lat).cuda(), torch.from_numpy(wh).cuda(), out=out2)
     torch.cuda.synchronize()
     assert torch.equal(out, out2)                              # replay: bit-identical
+    # every batch size plans (tile shapes, CTA pairs, split-K and ring depth are chosen per batch size) and repeats frame 0
+    for b in (3, 5):
+        fb = torch.empty(b, 256, 256, 3, device="cuda")
+        eng.forward(torch.from_numpy(np.repeat(lat[:1], b, 0)).cuda(), torch.from_numpy(np.repeat(wh[:1], b, 0)).cuda(), out_f32=fb)
+        torch.cuda.synchronize()
+        assert psnr(fb[b - 1].cpu().numpy(), f32[0].cpu().numpy()) > 40.0
