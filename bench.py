@@ -767,6 +767,16 @@ def main():
             dt = time.perf_counter() - t0
             heads["wav2lip"]["cpu_baseline"] = {"value": 16 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                                 "sample": f"one batch of 16 frames through the fp32 PyTorch oracle (pinned on the reference nn.Module's golden output), {dt:.2f} s, network only (no paste)"}
+        if "wav2lip_256" in heads:
+            _m, _f = _wi(4, S=256)
+            _sd = _sw(2, face_hw=256)
+            _O.infer(_sd, _m[:1], _f[:1])
+            t0 = time.perf_counter()
+            _O.infer(_sd, _m, _f)
+            dt = time.perf_counter() - t0
+            heads["wav2lip_256"]["cpu_baseline"] = {"value": 4 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                                    "sample": f"4 frames through the fp32 PyTorch restatement of the extended 256x256 generator, {dt:.2f} s, network only "
+                                                              "(no reference implementation of this net exists)"}
         if "musetalk" in heads:
             import torch as _t
             from helpers import WHISPER_TINY as _WT, seeded_whisper_state as _sws, synthetic_speech as _ss

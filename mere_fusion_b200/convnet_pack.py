@@ -122,11 +122,14 @@ class ProgramBuilder:
         return len(self.ops) - 1
 
     def conv(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, bn=None, stride=1, padding=0, res=None,
-             relu=True, mode=0, ups=0, extra_shift=None, wscale=1.0, res_after_act=False):
+             relu=True, mode=0, ups=0, extra_shift=None, wscale=1.0, res_after_act=False, cin_align=8):
         """nn.Conv2d (+BatchNorm2d, +residual, +activation).  weight [Cout, Cin, kh, kw].  relu: False / True / ACT_GELU.
         res_after_act: out = act(conv) + res instead of act(conv + res).  ups = 1: the conv runs on the
         nearest-neighbour 2x upsampling of the input buffer (F.interpolate(scale_factor=2) folded into the gather).
-        extra_shift: per-channel constant added after the conv (e.g. a time-embedding projection)."""
+        extra_shift: per-channel constant added after the conv (e.g. a time-embedding projection).
+        cin_align = 64: read the input channels up to the next multiple of 64 with ZERO weights for the extra ones (they must exist
+        in the buffer and hold finite values -- buffers are zero-filled at load and pad channels are never written), which makes a
+        stride-1 layer eligible for the TMA-fed kernel (Cin % 64 == 0) at the price of the padded MACs."""
         weight = np.asarray(weight, np.float32)
         cout, cin, kh, kw = weight.shape
         sy, sx = (stride, stride) if np.isscalar(stride) else stride
@@ -136,7 +139,8 @@ class ProgramBuilder:
         Hout, Wout = (Hin + 2 * py - kh) // sy + 1, (Win + 2 * px - kw) // sx + 1
         if mode == 0:
             assert self.buffers[out_buf][:2] == (Hout, Wout), (self.buffers[out_buf], Hout, Wout)
-        cin_pad = (cin + 7) // 8 * 8
+        cin_pad = (cin + cin_align - 1) // cin_align * cin_align
+        assert in_coff + cin_pad <= self.buffers[in_buf][2], (in_coff, cin_pad, self.buffers[in_buf])
         taps = [(ky - py, kx - px) for ky in range(kh) for kx in range(kw)]
         Wm = np.zeros((cout, len(taps), cin_pad), np.float32)
         Wm[:, :, :cin] = weight.transpose(0, 2, 3, 1).reshape(cout, kh * kw, cin) * np.float32(wscale)
@@ -231,7 +235,7 @@ class ProgramBuilder:
         return self._misc(4, in_buf, out_buf, Cin=Hd)
 
     def conv_transpose(self, in_buf, in_coff, out_buf, out_coff, weight, bias=None, bn=None, stride=1, padding=0,
-                       output_padding=0, relu=True):
+                       output_padding=0, relu=True, cin_align=8):
         """nn.ConvTranspose2d (+BatchNorm2d +ReLU).  weight [Cin, Cout, kh, kw].  out[oy] gathers
         in[(oy + p - ky) / s] for the taps where the division is exact: one op per output-parity
         class, each with only its live taps."""
@@ -242,7 +246,8 @@ class ProgramBuilder:
         Hout = (Hin - 1) * s - 2 * p + kh + output_padding
         Wout = (Win - 1) * s - 2 * p + kw + output_padding
         assert self.buffers[out_buf][:2] == (Hout, Wout), (self.buffers[out_buf], Hout, Wout)
-        assert cin % 8 == 0
+        cin_pad = (cin + cin_align - 1) // cin_align * cin_align              # zero weights for the pad channels (see conv)
+        assert cin_pad % 8 == 0 and in_coff + cin_pad <= self.buffers[in_buf][2]
         scale, shift = bn_fold(bias, bn, cout)
         self.flops_per_sample += 2 * cout * cin * kh * kw * Hin * Win
         ids = []
@@ -258,9 +263,11 @@ class ProgramBuilder:
                 for ky, dy in ty:
                     for kx, dx in tx:
                         taps.append((dy, dx))
-                        cols.append(weight[:, :, ky, kx].T)          # [Cout, Cin]
+                        col = np.zeros((cout, cin_pad), np.float32)
+                        col[:, :cin] = weight[:, :, ky, kx].T        # [Cout, Cin]
+                        cols.append(col)
                 Wm = np.stack(cols, 1).reshape(cout, -1)
-                ids.append(self._emit(in_buf, in_coff, cin, out_buf, out_coff, Wm, taps, scale, shift, Mh, Mw, cy, cx,
+                ids.append(self._emit(in_buf, in_coff, cin_pad, out_buf, out_coff, Wm, taps, scale, shift, Mh, Mw, cy, cx,
                                       s, s, 1, 1, None, relu, 0, cout))
         return ids
 

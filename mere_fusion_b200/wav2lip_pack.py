@@ -120,8 +120,13 @@ def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
         sizes.append((sizes[-1] + 2 * p - k) // s + 1)
     enc_c = [blk[-1][0] for blk in FACE_ENC]                      # 16, 32, 64, 128, 256, 512, 512
     dec_c = [blk[0][1] for blk in FACE_DEC]                       # 512, 512, 512, 384, 256, 128, 64
-    # cat buffer i holds [decoder block (n - 1 - i) output | encoder block i output] at resolution sizes[i]
-    cat = [pb.buffer(sizes[i], sizes[i], dec_c[n - 1 - i] + enc_c[i]) for i in range(n)]
+    # cat buffer i holds [decoder block (n - 1 - i) output | encoder block i output] at resolution sizes[i].  Widths that are not
+    # a multiple of 64 (80 and 160 channels at the two largest resolutions) get zero pad channels up to the next multiple: the
+    # layers that read the whole buffer then run on the TMA-fed kernel (Cin % 64 == 0) with zero weights for the pad channels --
+    # measured on the 256 net: 80 -> 32 @256^2 469 us and the four 160 -> 64 parity convs 382 us on the cp.async im2col kernel
+    def cat_width(c):
+        return c if c < 64 else (c + 63) // 64 * 64
+    cat = [pb.buffer(sizes[i], sizes[i], cat_width(dec_c[n - 1 - i] + enc_c[i])) for i in range(n)]
     cat_off = [dec_c[n - 1 - i] for i in range(n)]
 
     in_face = pb.buffer(S, S, 8)
@@ -165,10 +170,12 @@ def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
             else:
                 out, ooff = pb.buffer(Ht, Ht, spec[1]), 0
             w, b, bn = block(f"face_decoder_blocks.{i}.{j}")
+            align = 64 if (j == 0 and i > 0 and pb.buffers[cur][2] % 64 == 0) else 8   # first layer of a block reads a whole cat buffer
             if spec[0] == "c":
-                pb.conv(cur, coff, out, ooff, w, b, bn, stride=spec[3], padding=spec[4])
+                pb.conv(cur, coff, out, ooff, w, b, bn, stride=spec[3], padding=spec[4], cin_align=align)
             elif spec[0] == "t":
-                pb.conv_transpose(cur, coff, out, ooff, w, b, bn, stride=spec[3], padding=spec[4], output_padding=spec[5])
+                pb.conv_transpose(cur, coff, out, ooff, w, b, bn, stride=spec[3], padding=spec[4], output_padding=spec[5],
+                                  cin_align=align)
             else:
                 pb.conv(cur, coff, out, ooff, w, b, bn, stride=1, padding=1, res=(cur, coff))
             cur, coff = out, ooff
@@ -177,7 +184,7 @@ def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
     # ---- output block (wav2lip.py:83-85)
     w, b, bn = block("output_block.0")
     o1 = pb.buffer(S, S, 32)
-    pb.conv(cat[0], 0, o1, 0, w, b, bn, stride=1, padding=1)
+    pb.conv(cat[0], 0, o1, 0, w, b, bn, stride=1, padding=1, cin_align=64 if pb.buffers[cat[0]][2] % 64 == 0 else 8)
     pb.conv(o1, 0, -1, 0, sd["output_block.1.weight"], sd["output_block.1.bias"], None, stride=1, padding=0,
             relu=False, mode=1)
     return pb.finish(), pb

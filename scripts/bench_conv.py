@@ -32,6 +32,9 @@ SHAPES = [  # (name, cin, cout, H, k, B, ups)
     ("w2l 512->512 @3", 512, 512, 3, 3, 16, 0),
     ("w2l 64->64 @96", 64, 64, 96, 3, 16, 0),
     ("w2l 128->128 @48", 128, 128, 48, 3, 16, 0),
+    ("w2l256 64->64 @256", 64, 64, 256, 3, 16, 0),
+    ("w2l256 128->32 @256", 128, 32, 256, 3, 16, 0),
+    ("w2l256 128->128 @128", 128, 128, 128, 3, 16, 0),
 ]
 modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["0"])]
 forces = os.environ.get("FORCES", "").split(";") if os.environ.get("FORCES") else [None]   # e.g. FORCES="256,1;128,2;64,1"

@@ -1,7 +1,7 @@
 #!/bin/bash
 # one GPU call: the whole -m gpu suite, smoke(), the default bench line, the reference arm
 mkdir -p gpurun_out
-timeout -s KILL 700 python -m pytest tests -m gpu -q -x 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
+timeout -s KILL 700 python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
 timeout 1000 python bench.py > gpurun_out/bench_stdout.log 2> gpurun_out/bench_stderr.log

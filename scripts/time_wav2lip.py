@@ -7,8 +7,9 @@ from helpers import seeded_wav2lip_state, wav2lip_inputs
 from mere_fusion_b200.wav2lip import Wav2LipEngine
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-eng = Wav2LipEngine(seeded_wav2lip_state(2), max_batch=B)
-mel, faces = wav2lip_inputs(B)
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 96          # 96: reference generator; 256: the extended one (configs[1])
+eng = Wav2LipEngine(seeded_wav2lip_state(2, face_hw=S), max_batch=B, face_hw=S)
+mel, faces = wav2lip_inputs(B, S=S)
 mel, faces = torch.from_numpy(mel).cuda(), torch.from_numpy(faces).cuda()
 out = torch.empty_like(faces)
 for _ in range(5):
@@ -21,4 +22,4 @@ for _ in range(n):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 fl = eng.flops_per_frame * B
-print(f"B={B}: {ms:.3f} ms/batch = {B*1000/ms:.0f} frames/s; {fl/ms/1e9:.1f} TFLOP/s algorithmic; launches {eng.last_launches}", flush=True)
+print(f"S={S} B={B}: {ms:.3f} ms/batch = {B*1000/ms:.0f} frames/s; {fl/ms/1e9:.1f} TFLOP/s algorithmic; launches {eng.last_launches}", flush=True)
