@@ -154,8 +154,12 @@ def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
             else:
                 Hi = pb.buffers[cur][0]
                 Ho = (Hi + 2 * p - k) // s + 1
-                out, ooff = pb.buffer(Ho, Ho, cout), 0
-            pb.conv(cur, coff, out, ooff, w, b, bn, stride=s, padding=p, res=(cur, coff) if resid else None)
+                # the 32-channel intermediates are allocated 64 wide (zero pad channels, as for the cat buffers above) so that the
+                # stride-1 32 -> 32 residual convs of the second block read Cin = 64 and run on the TMA-fed kernel
+                out, ooff = pb.buffer(Ho, Ho, 64 if cout == 32 else cout), 0
+            wide_in = s == 1 and coff == 0 and w.shape[1] == 32 and pb.buffers[cur][2] == 64
+            pb.conv(cur, coff, out, ooff, w, b, bn, stride=s, padding=p, res=(cur, coff) if resid else None,
+                    cin_align=64 if wide_in else 8)
             cur, coff = out, ooff
 
     # ---- face decoder (wav2lip.py:57-81,102-112)
@@ -183,8 +187,8 @@ def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
 
     # ---- output block (wav2lip.py:83-85)
     w, b, bn = block("output_block.0")
-    o1 = pb.buffer(S, S, 32)
+    o1 = pb.buffer(S, S, 64)                                      # 32 channels + zero pad: the 1x1 head reads Cin = 64 (TMA kernel)
     pb.conv(cat[0], 0, o1, 0, w, b, bn, stride=1, padding=1, cin_align=64 if pb.buffers[cat[0]][2] % 64 == 0 else 8)
     pb.conv(o1, 0, -1, 0, sd["output_block.1.weight"], sd["output_block.1.bias"], None, stride=1, padding=0,
-            relu=False, mode=1)
+            relu=False, mode=1, cin_align=64)
     return pb.finish(), pb

@@ -33,6 +33,7 @@ SHAPES = [  # (name, cin, cout, H, k, B, ups)
     ("w2l 64->64 @96", 64, 64, 96, 3, 16, 0),
     ("w2l 128->128 @48", 128, 128, 48, 3, 16, 0),
     ("w2l256 64->64 @256", 64, 64, 256, 3, 16, 0),
+    ("w2l256 64->64 @256 +res", 64, 64, 256, 3, 16, 0),
     ("w2l256 128->32 @256", 128, 32, 256, 3, 16, 0),
     ("w2l256 128->128 @128", 128, 128, 128, 3, 16, 0),
 ]
@@ -51,7 +52,8 @@ for name, cin, cout, H, k, B, ups in SHAPES:
             os.environ["MF_CONV_FORCE"] = force
         pb = ProgramBuilder(B)
         a, b = pb.buffer(H, H, cin), pb.buffer(H << ups, H << ups, cout)
-        pb.conv(a, 0, b, 0, w, np.zeros(cout, np.float32), padding=k // 2, relu=False, ups=ups)
+        pb.conv(a, 0, b, 0, w, np.zeros(cout, np.float32), padding=k // 2, relu=False, ups=ups,
+                res=(a, 0) if "+res" in name else None)
         net = ConvNet(pb.finish(), max_batch=B)
         x = torch.randn(B, H, H, cin, generator=g)
         h = net.ctx.handle
