@@ -48,6 +48,7 @@ struct ConvTmaParams {
     int gn_cpg, gn_G;    // channels per group (4 / 8 / 16) and number of groups
     int ndx, n_groups, a_stage_bytes;   // row-halo A reuse: a k-step is (tap group, channel block): one A load, ndx B loads, 4 ndx UMMAs
     int dbg;
+    uint32_t mg_tx, mg_txy;   // ceil(2^32 / tiles_x), ceil(2^32 / (tiles_x * tiles_y)) for ct_fastdiv
     int mode;        // 0 bf16 NHWC; 1 wav2lip head (sigmoid, x255 truncated, u8 + fp32); 2 VAE head ((x/2+.5).clamp, round, BGR u8 + RGB fp32);
                      // 3 fp32 tokens x Cout to out_f32 (wav2vec2 logits)
     float *out_f32;  // modes 1 / 2
@@ -107,7 +108,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive on CTA rank 0's copy of `bar`
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote) : "memory");
+    // default semantics (.release at CTA scope), the form cutlass::arch::ClusterBarrier::arrive(cta_id) uses.  The barrier only
+    // says "this CTA's tcgen05.ld of the accumulator have completed" (tcgen05.wait::ld + fence::before_thread_sync + bar.sync come
+    // first), so nothing has to be made visible cluster-wide: `.release.cluster` compiled to MEMBAR.ALL.GPU + ERRBAR, i.e. thread 0
+    // waited for its output stores to drain once per tile and everyone waited for thread 0 at the next epilogue barrier
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(remote) : "memory");
 }
 
 // scale/shift (staged in shared memory per tile: cs = scale[256] | shift[256], indexed by the column inside the tile) ->
@@ -117,6 +122,9 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {   // explicit ld.shar
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
 }
+
+// n / d with m = ceil(2^32 / d) from the host: exact while n * d < 2^32 (checked when the launch is planned)
+__device__ __forceinline__ uint32_t ct_fastdiv(uint32_t n, uint32_t m, uint32_t d) { return d == 1u ? n : __umulhi(n, m); }
 
 template <int ACT>   // 0 none, 1 ReLU, 2 exact-erf GELU: compile-time, so that the epilogue loop stays a few hundred instructions
 __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[16], uint32_t cs, int c, int n0, size_t opix,
@@ -153,7 +161,6 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
         }
     }
     uint32_t o[8];
-    float f32keep[16];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         float a = f[2 * j], c = f[2 * j + 1];
@@ -161,25 +168,29 @@ __device__ __forceinline__ void ct_finish16(const ConvTmaParams &p, float (&f)[1
             if (ACT == 1) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
             else { a = gelu_erf(a); c = gelu_erf(c); }
         }
-        f32keep[2 * j] = a; f32keep[2 * j + 1] = c;
+        f[2 * j] = a; f[2 * j + 1] = c;
         __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
         o[j] = *reinterpret_cast<uint32_t *>(&h);
-        f[2 * j] = __bfloat162float(h.x);      // the values as stored (fused GroupNorm statistics are taken from these)
-        f[2 * j + 1] = __bfloat162float(h.y);
     }
     if (p.mode == 3) {   // fp32 output head: the unrounded values, only the real columns
         float *dst = p.out_f32 + opix * p.Cout + n0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            float a = f32keep[2 * j], c = f32keep[2 * j + 1];
-            if (n0 + 2 * j < p.Cout) dst[2 * j] = a;
-            if (n0 + 2 * j + 1 < p.Cout) dst[2 * j + 1] = c;
+            if (n0 + 2 * j < p.Cout) dst[2 * j] = f[2 * j];
+            if (n0 + 2 * j + 1 < p.Cout) dst[2 * j + 1] = f[2 * j + 1];
         }
         return;
     }
     uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + opix * p.out_stride + p.out_coff + n0);
     op[0] = make_uint4(o[0], o[1], o[2], o[3]);
     op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    if (p.gn_partial) {   // the fused GroupNorm statistics are taken from the values as stored (only the layers that feed a GroupNorm)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&o[j]);
+            f[2 * j] = __bfloat162float(h.x); f[2 * j + 1] = __bfloat162float(h.y);
+        }
+    }
 }
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile: each CTA stages
@@ -229,7 +240,7 @@ __device__ __forceinline__ void ct_gn_chunk(const float (&f)[16], bool valid, fl
     } while (0)
 
 template <int CG, int ACT>
-__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constant__ ConvTmaParams p) {
+__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constant__ ConvTmaParams p) {   // 10 warps = 3 on one SM sub-partition (16 K registers): 168 registers per thread is the hardware cap
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int ST = p.stages;
@@ -376,11 +387,23 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
         const bool leader = threadIdx.x == 0;
         const int TWm = (1 << p.lTW) - 1, THm = (1 << p.lTH) - 1;
         uint32_t n = 0;
+        // the epilogue is instruction-issue bound on the short-K layers (8 warps, ~700 instructions per warp and tile for 32
+        // columns, profiles/r01_conv64_ncu_summary.md): the tile coordinates come from two multiply-high divisions by constants
+        // prepared on the host instead of five integer divisions per tile (nothing is carried across tiles: the kernel sits at
+        // its register cap)
+        const bool simple = per_tile == 1;   // one n-tile, no split-K: an item IS an m-tile
         for (int item = item0; item < total; item += item_step, n++) {
-            const int mp = item / per_tile, rem = item - mp * per_tile;
-            const int mt = mp * CG + (int)cta_rank;
-            const int nt = rem / p.splits, sp = rem - nt * p.splits;
-            const int txi = mt % p.tiles_x, tyi = (mt / p.tiles_x) % p.tiles_y, tbi = mt / (p.tiles_x * p.tiles_y);
+            int mt, nt, sp;
+            if (simple) {
+                mt = item * CG + (int)cta_rank; nt = 0; sp = 0;
+            } else {
+                const int mp = item / per_tile, rem = item - mp * per_tile;
+                mt = mp * CG + (int)cta_rank;
+                nt = rem / p.splits; sp = rem - nt * p.splits;
+            }
+            const int q1 = (int)ct_fastdiv((uint32_t)mt, p.mg_tx, (uint32_t)p.tiles_x);
+            const int tbi = (int)ct_fastdiv((uint32_t)mt, p.mg_txy, (uint32_t)(p.tiles_x * p.tiles_y));
+            const int txi = mt - q1 * p.tiles_x, tyi = q1 - tbi * p.tiles_y;
             const int mx = (txi << p.lTW) + (r & TWm), my = (tyi << p.lTH) + ((r >> p.lTW) & THm);
             const int b = (tbi << (7 - p.lTW - p.lTH)) + (r >> (p.lTW + p.lTH));
             const bool row_ok = mx < p.Mw && my < p.Mh && b < p.B;
@@ -389,15 +412,19 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
             const int n_base = nt * p.BN;
             // this tile's scale / shift go to shared memory once (the loads are in flight while the accumulator is awaited):
             // per-chunk __ldg of the bias was the largest stall of the epilogue (profiles/r01_conv_bound_experiment.md)
+            // (a layer with ONE n-tile has the same coefficients for every item: staged once, no per-tile load / store / barrier)
             const int et = half * 128 + r;
+            const bool stage_coef = p.n_tiles > 1 || n == 0;
             float my_sc = 1.f, my_sh = 0.f;
-            if (et < p.BN && n_base + et < p.Cout) { my_sc = __ldg(p.scale + n_base + et); my_sh = __ldg(p.shift + n_base + et); }
+            if (stage_coef && et < p.BN && n_base + et < p.Cout) { my_sc = __ldg(p.scale + n_base + et); my_sh = __ldg(p.shift + n_base + et); }
             mbar_wait(&tfull[acc], (n >> 1) & 1);
             tc_fence_after();
-            float *csp = coef + (n & 1) * 512;
-            csp[et] = my_sc; csp[256 + et] = my_sh;
+            float *csp = coef + (p.n_tiles > 1 ? (n & 1) * 512 : 0);
             const uint32_t cs = smem_u32(csp);
-            epi_bar_sync();
+            if (stage_coef) {
+                csp[et] = my_sc; csp[256 + et] = my_sh;
+                epi_bar_sync();
+            }
             const uint32_t taddr = tmem_base + acc * CT_ACC_STRIDE + ((uint32_t)((warp & 3) * 32) << 16);
             if (p.mode == 1 || p.mode == 2) {
                 // image output heads (Cout <= 16, one 16-column chunk; splits == 1)

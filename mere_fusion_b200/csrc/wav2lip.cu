@@ -830,6 +830,12 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
     const int stage = p.a_stage_bytes + ndx * (BN * 128 / CG);
     p.stages = std::min(CT_MAX_STAGES, (CT_SMEM_LIMIT - 1024 - 256 - 4096) / stage);
     MF_REQUIRE(ctx, p.stages >= 2, "op %d: a pipeline stage of %d bytes does not fit twice", i, stage);
+    {   // multiply-high constants for the epilogue's tile-coordinate divisions (conv_tma.cuh ct_fastdiv)
+        const uint64_t dx = (uint64_t)p.tiles_x, dxy = (uint64_t)p.tiles_x * p.tiles_y;
+        MF_REQUIRE(ctx, ((uint64_t)m_tiles + 2) * dxy < (1ull << 32), "op %d: too many tiles for the 32-bit tile index arithmetic", i);
+        p.mg_tx = dx > 1 ? (uint32_t)(((1ull << 32) + dx - 1) / dx) : 0u;
+        p.mg_txy = dxy > 1 ? (uint32_t)(((1ull << 32) + dxy - 1) / dxy) : 0u;
+    }
     const int m_groups = (m_tiles + CG - 1) / CG;          // work items are 128-row tiles (CG 1) or 256-row tile pairs (CG 2)
     p.total_items = m_groups * p.n_tiles * S;
     p.out = cp.out; p.res = cp.res; p.scale = cp.scale; p.shift = cp.shift;
