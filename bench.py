@@ -246,11 +246,51 @@ def wav2lip_leg(args, dev, local, rank, world, flush, timed_fn, pk, S=96, shared
     eng.profile_op(-1)
     flop = 2 * 64 * 64 * 9 * S * S * B
     m = float(np.mean(ms)) * 1e-3
+    # ---- cross-session batching: four sessions' 16-frame requests as ONE pass of a shared engine
+    # (scheduler.SharedEngine) against the same four requests run one after the other on this engine
+    coalesce = None
+    if S == 96:
+        from mere_fusion_b200.scheduler import SharedEngine
+        NS = 4
+        sh = SharedEngine(Wav2LipEngine(blob=blob, max_batch=B * NS, device=local, face_hw=S), threaded=False)
+        sels = [torch.empty((B, S, S, 3), dtype=torch.uint8, device=dev) for _ in range(NS)]
+        preds = [torch.empty_like(sels[0]) for _ in range(NS)]
+        outs = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(NS)]
+
+        def paste(k, j):
+            idx_t, rows = rows_all[(k + j) % 8]
+            st = torch.cuda.current_stream(dev)
+            check(h, lib().mf_paste_resize_u8(h, ctypes.c_void_p(frames.data_ptr()), n_av, H, W, ctypes.c_void_p(preds[j].data_ptr()), S, B,
+                                              rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_void_p(outs[j].data_ptr()),
+                                              ctypes.c_void_p(st.cuda_stream)), "mf_paste_resize_u8")
+
+        def step_coalesced(k):
+            reqs = []
+            for j in range(NS):
+                torch.index_select(faces_all, 0, rows_all[(k + j) % 8][0], out=sels[j])
+                reqs.append(sh.submit(mel_dev[(k + j) % 8], sels[j], out=preds[j]))
+            sh.flush()
+            for j, rq in enumerate(reqs):
+                sh.wait(rq)
+                paste(k, j)
+
+        def step_sequential(k):
+            for j in range(NS):
+                torch.index_select(faces_all, 0, rows_all[(k + j) % 8][0], out=sels[j])
+                eng.forward(mel_dev[(k + j) % 8], sels[j], out=preds[j])
+                paste(k, j)
+
+        tc, _, _ = timed_fn(step_coalesced, K, args.warmup)
+        ts, _, _ = timed_fn(step_sequential, K, args.warmup)
+        coalesce = {"sessions": NS, "frames_per_step": NS * B, "coalesced_ms_per_step": tc / K, "sequential_ms_per_step": ts / K,
+                    "coalesced_frames_per_s": world * K * NS * B / (tc / 1e3), "sequential_frames_per_s": world * K * NS * B / (ts / 1e3),
+                    "engine_calls_per_step": 1}
+        sh.shutdown()
     wl = ("wav2lip_96x96_B16 -> paste into 512x512 (reference architecture; the 256x256 net of configs[1] does not exist in the reference, SURVEY M2)"
           if S == 96 else
           "wav2lip_256x256_B16 -> paste into 512x512 (BASELINE configs[1]; EXTENDED generator of SURVEY 8(d) config 2 (ii) / section 7 step 4 -- "
           "not a reference architecture, random weights, parity vs our own fp32 restatement only)")
-    return {"workload": wl, "gflop_per_frame": eng.flops_per_frame / 1e9,
+    return {"workload": wl, "gflop_per_frame": eng.flops_per_frame / 1e9, "cross_session_batching": coalesce,
             "value": world * K * B / (tot / 1e3), "unit": "frames/s", "ms_per_step": tot / K, "frames_per_step": B,
             "e2e": {"value": world * K * B / (e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(mel_pin[0].numel() * 4),
                     "d2h_bytes_per_step": int(out_pin.numel())},
