@@ -35,4 +35,8 @@ def test_packer_program_geometry():
     magic, kind, ver, n = struct.unpack("<IIII", blob[:16].tobytes())
     assert magic == 0x3242464D and kind == 2 and n == 1 + 3 * len(pb.ops)
     cat_c = [pb.buffers[i][2] for i in range(7)]
-    assert cat_c == [80, 160, 320, 512, 768, 1024, 1024]   # wav2lip.py:57-81 skip-concat widths
+    # wav2lip.py:57-81 skip-concat widths 80, 160, 320, 512, 768, 1024, 1024; the two that are not multiples of 64 carry zero pad
+    # channels (never written, zero weights) so that the layers reading them run on the TMA-fed kernel
+    assert cat_c == [128, 192, 320, 512, 768, 1024, 1024]
+    _, pb256 = pack_wav2lip(seeded_wav2lip_state(2, face_hw=256), face_hw=256)
+    assert len(pb256.ops) == 74 and abs(pb256.flops_per_sample / 1e9 - 55.879) < 1e-3      # ~56 GFLOP/frame
