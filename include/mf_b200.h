@@ -159,6 +159,13 @@ typedef struct mf_ernerf_debug {
 /* out_rgb: device u8 [outH,outW,3] RGB = (image*255) truncated (nerfreal.py:110). */
 int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *frame /*host*/, uint8_t *out_rgb,
                      const mf_ernerf_debug *dbg /*host, nullable*/, void *stream);
+/* The same render for n frames of n DIFFERENT sessions in one pass (n <= 4): ctxs[i] renders frames[i] into outs[i] (device u8
+ * [outH,outW,3]) with its own per-session state, exactly as n mf_ernerf_render calls would (bit-identical images), but with ONE
+ * launch of the fused march / encode / MLP / composite kernel for the whole batch -- the reference renders one session per
+ * process (app.py:331-392) and has no equivalent.  All contexts must live on the same GPU and have been loaded from the same
+ * device blob with the same configuration (one avatar model, many sessions).  Errors are reported on ctxs[0]. */
+int mf_ernerf_render_batch(mf_ctx *const *ctxs /*host*/, const mf_ernerf_frame *frames /*host, [n]*/,
+                           uint8_t *const *outs /*host array of device pointers*/, int n, void *stream);
 /* forget the audio-feature EMA (a new session on a reused context) */
 int mf_ernerf_reset_state(mf_ctx *ctx);
 /* offsets of the packed-blob MLP images (csrc/ernerf_layout.h) for the Python packer; returns the

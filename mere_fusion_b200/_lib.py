@@ -60,6 +60,7 @@ def lib():
         L.mf_ernerf_load.argtypes = [c_vp, c_vp, ctypes.c_size_t, ctypes.POINTER(MfErnerfCfg)]
         L.mf_ernerf_render.argtypes = [c_vp, ctypes.POINTER(MfErnerfFrame), c_vp,
                                        ctypes.POINTER(MfErnerfDebug), c_vp]
+        L.mf_ernerf_render_batch.argtypes = [ctypes.POINTER(c_vp), ctypes.POINTER(MfErnerfFrame), ctypes.POINTER(c_vp), ctypes.c_int, c_vp]
         L.mf_ernerf_reset_state.argtypes = [c_vp]
         L.mf_ernerf_last_launches.argtypes = [c_vp]
         L.mf_ernerf_profile.argtypes = [c_vp, ctypes.c_int]

@@ -155,7 +155,10 @@ __device__ void conv1d_k3(const float *x, float *y, const __half *W, const __hal
 
 #define SETUP_THREADS 1024
 #define SETUP_FLOATS (8 * 64 * 16 + 8 * 32 * 8 + 8 * 32 + 8 + 48)
-__global__ void __launch_bounds__(SETUP_THREADS) k_setup(SetupParams p) {
+struct SetupBatch { int n; SetupParams f[4]; };   // one CTA per frame of a batched render (HEAD_MAX_FRAMES)
+__device__ __forceinline__ void setup_body(const SetupParams &p);
+__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ SetupBatch b) { setup_body(b.f[blockIdx.x]); }
+__device__ __forceinline__ void setup_body(const SetupParams &p) {
     // the whole audio-net weight image (66 KB fp16) is staged in shared memory with coalesced 16-byte loads first: read straight
     // from global inside the dot-product loops, the 2-byte weight loads formed ~1000-long dependent latency chains per thread
     // (125 us for 0.1 MFLOP: 18 % of the frame)
@@ -318,28 +321,39 @@ __device__ __forceinline__ void load_a(uint32_t (&a)[4], const __half *tile, int
 #define XS_STRIDE 56 /* enc_x tile row stride in halfs (48 + 8) */
 #define SH_STRIDE 24 /* SH tile row stride in halfs (16 + 8) */
 
-struct HeadParams {
+// per-frame part of the k_head arguments: one launch renders up to HEAD_MAX_FRAMES frames of DIFFERENT sessions (contexts loaded from the
+// same blob) -- the round structure (one grid barrier per march round, 3-4 tiles per warp and round for ONE frame, less than one in
+// the last round) leaves ~45 % of the warp-time waiting at the barriers (profiles/r01_k_head_v4_ncu_summary.md); the frames of a
+// batch share the barriers and fill each other's round tails
+#define HEAD_MAX_FRAMES 4
+struct HeadFrame {
     FrameGeom g;
+    const float *state;  // enc_a at [0..31]
+    float eye;
+    int *alive0, *alive1;
+    int *counters;
+    float *rays_t, *nears, *fars, *weights_sum, *image;
+};
+
+struct HeadParams {
     HeadLevels hl;
     const float *planes;
     uint32_t plane_rows;
     const uint8_t *bitfield;
     const __half *mlp_image;
-    const float *state;  // enc_a at [0..31]
-    float eye;
     float bound, min_near, dt_gamma, T_thresh;
     uint32_t max_steps, cascade, grid_size;
     float aabb[6];
-    int *alive0, *alive1;
-    int *counters;
-    float *rays_t, *nears, *fars, *weights_sum, *image;
+    int n_frames;
+    HeadFrame f[HEAD_MAX_FRAMES];
 };
 
 struct HeadSmem {
     alignas(16) unsigned char mlp[ER_H_BYTES];
     alignas(16) __half xs[HEAD_WARPS][32 * XS_STRIDE];
     alignas(16) __half sh[HEAD_WARPS][32 * SH_STRIDE];
-    float enc_a[32];
+    float enc_a[HEAD_MAX_FRAMES][32];
+    int rnd[HEAD_MAX_FRAMES][4];   // this round, per frame: n_alive (0 = frame finished), n_step, first tile, end tile (cumulative)
     alignas(8) uint64_t bar;
 };
 
@@ -365,7 +379,7 @@ __device__ __forceinline__ void gen_ray(const FrameGeom &g, int idx, Ray &r) {
 
 // density + color for one 16-row tile (rows m*16..m*16+15 of the warp's 32-sample tile).
 // Returns in lane (t == 0): sigma logit of rows g / g+8; rgb in lanes t == 0 (r, g) and t == 1 (b).
-__device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, __half *xs, const __half *sh, int m, int lane,
+__device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, const float *enc_a, __half *xs, const __half *sh, int m, int lane,
                                               float eye, float &sig_lo, float &sig_hi, float (&rgb)[4]) {
     const __half *W = reinterpret_cast<const __half *>(sm.mlp);
     const float *colbias = reinterpret_cast<const float *>(sm.mlp + ER_H_COLBIAS_BYTES);
@@ -391,7 +405,7 @@ __device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, __half *xs, co
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int col = (2 * j + h) * 8 + 2 * t;
-                const float e0 = sm.enc_a[col], e1 = sm.enc_a[col + 1];
+                const float e0 = enc_a[col], e1 = enc_a[col + 1];
                 aw[j][2 * h + 0] = pack_half2(e0 * round_half(c2[2 * j + h][0]), e1 * round_half(c2[2 * j + h][1]));
                 aw[j][2 * h + 1] = pack_half2(e0 * round_half(c2[2 * j + h][2]), e1 * round_half(c2[2 * j + h][3]));
             }
@@ -510,39 +524,57 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) k_head(const __grid_constant_
         mbar_expect_tx(&sm.bar, ER_H_BYTES);
         bulk_g2s(sm.mlp, p.mlp_image, ER_H_BYTES, &sm.bar);
     }
-    if (threadIdx.x < 32) sm.enc_a[threadIdx.x] = p.state[threadIdx.x];
+    if (threadIdx.x < 32 * p.n_frames) sm.enc_a[threadIdx.x >> 5][threadIdx.x & 31] = p.f[threadIdx.x >> 5].state[threadIdx.x & 31];
     mbar_wait(&sm.bar, 0);
     __syncthreads();
 
     const MarchParams mp = make_march_params(p.bound, p.dt_gamma, p.max_steps, p.cascade, p.grid_size, p.bitfield);
     __half *xs = sm.xs[warp];
     __half *sh = sm.sh[warp];
-    const int N = p.g.N;
-    volatile int *ctr = p.counters;
+    const int F = p.n_frames;
+    int *ticket = p.f[0].counters;   // the batch draws its tiles from ONE ticket per round (frame 0's counter row, slot 1)
 
-    uint32_t step_total = 0;
+    uint32_t step_total = 0;   // marched steps so far, one byte per frame (<= 16 + 7)
     for (int r = 0; r < ER_MAX_ROUNDS; r++) {
-        const int n_alive = ctr[r * ER_CTR_STRIDE + 0];
-        if (n_alive <= 0 || step_total >= p.max_steps) break;
-        const int n_step = max(min(N / n_alive, 8), 1);
-        // A tile is 32 SAMPLES, not 32 rays: R = 32 / n_step rays, lane = q * n_step + k holds sample k of ray q.  The n_step
-        // samples of a ray are independent until the compositor (the march never looks at sigma), so they are gathered and
-        // shaded side by side -- like the reference, which shades all n_alive * n_step samples of a round in one batch
-        // (renderer.py:258-264) -- and only the compositing recurrence runs in order.  The critical path of a frame drops from
-        // sum(n_step) = 16..23 sample latencies to one per round (measured: 2048 rays took 0.42 ms, 262144 rays 0.62 ms).
-        const int R = 32 / n_step;
-        const int n_tiles = (n_alive + R - 1) / R;
-        const int *alive_in = (r & 1) ? p.alive1 : p.alive0;
-        int *alive_out = (r & 1) ? p.alive0 : p.alive1;
-        if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[r * ER_CTR_STRIDE + 3] = n_step;
-        const int q = lane / n_step, k = lane - q * n_step;   // ray inside the tile, sample inside the round
-        const int lead = q * n_step;                           // lane that owns the ray's state
+        // ---- this round's shape per frame (renderer.py:246-256), published once per CTA
+        if (threadIdx.x == 0) {
+            int end = 0;
+            for (int f = 0; f < F; f++) {
+                int n_alive = ((volatile int *)p.f[f].counters)[r * ER_CTR_STRIDE + 0];
+                if (n_alive <= 0 || ((step_total >> (8 * f)) & 0xffu) >= p.max_steps) n_alive = 0;
+                const int n_step = n_alive > 0 ? max(min(p.f[f].g.N / n_alive, 8), 1) : 0;
+                // A tile is 32 SAMPLES, not 32 rays: R = 32 / n_step rays, lane = q * n_step + k holds sample k of ray q.  The n_step
+                // samples of a ray are independent until the compositor (the march never looks at sigma), so they are gathered and
+                // shaded side by side -- like the reference, which shades all n_alive * n_step samples of a round in one batch
+                // (renderer.py:258-264) -- and only the compositing recurrence runs in order.  The critical path of a frame drops
+                // from sum(n_step) = 16..23 sample latencies to one per round (measured: 2048 rays 0.42 ms, 262144 rays 0.62 ms).
+                const int R = n_alive > 0 ? 32 / n_step : 1;
+                sm.rnd[f][0] = n_alive; sm.rnd[f][1] = n_step; sm.rnd[f][2] = end;
+                end += n_alive > 0 ? (n_alive + R - 1) / R : 0;
+                sm.rnd[f][3] = end;
+                if (blockIdx.x == 0 && n_alive > 0) p.f[f].counters[r * ER_CTR_STRIDE + 3] = n_step;
+            }
+        }
+        __syncthreads();
+        const int n_tiles = sm.rnd[F - 1][3];
+        if (n_tiles == 0) break;
+        for (int f = 0; f < F; f++) step_total += (uint32_t)sm.rnd[f][1] << (8 * f);
 
         while (true) {
             int tile = 0;
-            if (lane == 0) tile = atomicAdd(&p.counters[r * ER_CTR_STRIDE + 1], 1);
+            if (lane == 0) tile = atomicAdd(&ticket[r * ER_CTR_STRIDE + 1], 1);
             tile = __shfl_sync(0xffffffffu, tile, 0);
             if (tile >= n_tiles) break;
+            int fi = 0;
+            while (tile >= sm.rnd[fi][3]) fi++;
+            const HeadFrame &fr = p.f[fi];
+            const int n_alive = sm.rnd[fi][0], n_step = sm.rnd[fi][1];
+            tile -= sm.rnd[fi][2];
+            const int R = 32 / n_step;
+            const int *alive_in = (r & 1) ? fr.alive1 : fr.alive0;
+            int *alive_out = (r & 1) ? fr.alive0 : fr.alive1;
+            const int q = lane / n_step, k = lane - q * n_step;   // ray inside the tile, sample inside the round
+            const int lead = q * n_step;                           // lane that owns the ray's state
 
             const int slot = tile * R + q;
             const bool valid = q < R && slot < n_alive;
@@ -551,18 +583,18 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) k_head(const __grid_constant_
             float t = 0.f, far = 0.f, ws = 0.f, cr = 0.f, cg_ = 0.f, cb = 0.f;
             if (valid) {
                 ray = (r == 0) ? slot : alive_in[slot];
-                gen_ray(p.g, ray, ry);
+                gen_ray(fr.g, ray, ry);
                 if (r == 0) {   // n_step == 1 in round 0 (N / N): every lane is its ray's leader
                     float near;
                     near_far_aabb(ry.ox, ry.oy, ry.oz, ry.dx, ry.dy, ry.dz, p.aabb, p.min_near, near, far);
                     t = near;
-                    p.fars[ray] = far;
-                    if (p.nears) p.nears[ray] = near;
+                    fr.fars[ray] = far;
+                    if (fr.nears) fr.nears[ray] = near;
                 } else {
-                    t = p.rays_t[ray];
-                    far = p.fars[ray];
-                    ws = p.weights_sum[ray];
-                    cr = p.image[ray * 3]; cg_ = p.image[ray * 3 + 1]; cb = p.image[ray * 3 + 2];
+                    t = fr.rays_t[ray];
+                    far = fr.fars[ray];
+                    ws = fr.weights_sum[ray];
+                    cr = fr.image[ray * 3]; cg_ = fr.image[ray * 3 + 1]; cb = fr.image[ray * 3 + 2];
                 }
                 float shv[16];
                 sh4(ry.dx, ry.dy, ry.dz, shv);
@@ -599,7 +631,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) k_head(const __grid_constant_
                 for (int m = 0; m < 2; m++) {
                     if (((hasmask >> (16 * m)) & 0xffffu) == 0u) continue;
                     float slo, shi, rgb[4];
-                    head_mlp_tile(sm, xs, sh, m, lane, p.eye, slo, shi, rgb);
+                    head_mlp_tile(sm, sm.enc_a[fi], xs, sh, m, lane, fr.eye, slo, shi, rgb);
                     const int src0 = 4 * (lane & 7), src1 = src0 + 1;
                     const float v_slo = __shfl_sync(0xffffffffu, slo, src0), v_shi = __shfl_sync(0xffffffffu, shi, src0);
                     const float r_lo = __shfl_sync(0xffffffffu, rgb[0], src0), r_hi = __shfl_sync(0xffffffffu, rgb[2], src0);
@@ -645,23 +677,22 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) k_head(const __grid_constant_
             const bool leader = valid && k == 0;
             alive = alive && leader;
             if (leader) {
-                p.weights_sum[ray] = ws;
-                p.image[ray * 3] = cr; p.image[ray * 3 + 1] = cg_; p.image[ray * 3 + 2] = cb;
-                if (alive) p.rays_t[ray] = t_end;
+                fr.weights_sum[ray] = ws;
+                fr.image[ray * 3] = cr; fr.image[ray * 3 + 1] = cg_; fr.image[ray * 3 + 2] = cb;
+                if (alive) fr.rays_t[ray] = t_end;
             }
             // ---- compaction (renderer.py:266), warp-aggregated
             const uint32_t amask = __ballot_sync(0xffffffffu, alive);
             if (amask) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(&p.counters[(r + 1) * ER_CTR_STRIDE + 0], __popc(amask));
+                if (lane == 0) base = atomicAdd(&fr.counters[(r + 1) * ER_CTR_STRIDE + 0], __popc(amask));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (alive) alive_out[base + __popc(amask & ((1u << lane) - 1u))] = ray;
             }
             const int emitted = __popc(hasmask);
-            if (lane == 0 && emitted) atomicAdd(&p.counters[r * ER_CTR_STRIDE + 2], emitted);
+            if (lane == 0 && emitted) atomicAdd(&fr.counters[r * ER_CTR_STRIDE + 2], emitted);
             __syncwarp();
         }
-        step_total += n_step;
         grid.sync();
     }
 }
@@ -1150,6 +1181,10 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
     int per_sm = 0;
     MF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_head, HEAD_THREADS, sizeof(HeadSmem)));
     MF_REQUIRE(ctx, per_sm >= 1, "k_head does not fit on an SM");
+    {   // experiment hook: MF_HEAD_CTAS_PER_SM=1 runs one CTA per SM (twice the tiles per warp and round, half the resident warps)
+        const char *e = getenv("MF_HEAD_CTAS_PER_SM");
+        if (e && atoi(e) >= 1) per_sm = std::min(per_sm, atoi(e));
+    }
     s->head_grid = per_sm * ctx->sm_count;
     MF_CUDA(ctx, cudaDeviceSynchronize());
     return MF_OK;
@@ -1230,28 +1265,34 @@ static bool inv4(const double *m, double *out) {
 
 static inline float h16(float v) { return __half2float(__float2half_rn(v)); }
 
-extern "C" int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *f, uint8_t *out_rgb, const mf_ernerf_debug *dbg,
-                                void *stream_) {
-    if (!ctx) return MF_E_INVALID;
+// one frame of a (possibly batched) render: argument checks, workspace, geometry and the k_setup arguments
+struct PreparedFrame {
+    ErnerfState *s;
+    FrameGeom g;
+    SetupParams sp;
+    int N, outH, outW;
+    bool resize;
+};
+
+static int prepare_frame(mf_ctx *ctx, const mf_ernerf_frame *f, const mf_ernerf_debug *dbg, PreparedFrame &pf) {
     ErnerfState *s = ctx->ernerf;
     if (!s) return mf_fail(ctx, MF_E_STATE, "mf_ernerf_render: ErNeRF weights not loaded");
     MF_REQUIRE(ctx, f && f->pose, "mf_ernerf_render: null frame/pose");
     MF_REQUIRE(ctx, f->auds || f->enc_a, "mf_ernerf_render: need auds or enc_a");
-    cudaStream_t stream = (cudaStream_t)stream_;
     const bool explicit_rays = f->rays_o != nullptr;
     if (explicit_rays)
         MF_REQUIRE(ctx, f->rays_d && f->bg_coords && f->n_rays > 0, "explicit rays need rays_d, bg_coords, n_rays");
     else
         MF_REQUIRE(ctx, f->H > 1 && f->W > 1, "mf_ernerf_render: bad H/W");
     const int N = explicit_rays ? f->n_rays : f->H * f->W;
-    const int outH = explicit_rays ? 1 : (f->outH > 0 ? f->outH : f->H);
-    const int outW = explicit_rays ? N : (f->outW > 0 ? f->outW : f->W);
-    const bool resize = !explicit_rays && (outH != f->H || outW != f->W);
-    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    pf.s = s; pf.N = N;
+    pf.outH = explicit_rays ? 1 : (f->outH > 0 ? f->outH : f->H);
+    pf.outW = explicit_rays ? N : (f->outW > 0 ? f->outW : f->W);
+    pf.resize = !explicit_rays && (pf.outH != f->H || pf.outW != f->W);
     int rc = ensure_ws(ctx, s, N);
     if (rc) return rc;
 
-    FrameGeom g;
+    FrameGeom &g = pf.g;
     g.N = N; g.H = explicit_rays ? 1 : f->H; g.W = explicit_rays ? N : f->W;
     for (int i = 0; i < 3; i++) {
         for (int j = 0; j < 3; j++) g.R[i * 3 + j] = f->pose[i * 4 + j];
@@ -1264,7 +1305,7 @@ extern "C" int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *f, uint8_t *
 
     // wrapped anchor (network.py:175-176): anchor_points @ inverse(pose^T) runs as an fp16 matmul
     // under autocast, the two divisions in fp16
-    SetupParams sp;
+    SetupParams &sp = pf.sp;
     {
         double pt[16], inv[16];
         for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) pt[i * 4 + j] = f->pose[j * 4 + i];
@@ -1285,67 +1326,130 @@ extern "C" int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *f, uint8_t *
     sp.misc = s->misc; sp.state = s->state; sp.counters = s->counters; sp.A = (int)s->cfg.audio_in_dim;
     sp.N = N; sp.smooth = (int)s->cfg.smooth_lips; sp.dbg_enc_a = dbg ? dbg->enc_a : nullptr;
     sp.audio_halfs = (int)s->audio_halfs;
-    int launches = 0;
-    const size_t setup_smem = SETUP_FLOATS * sizeof(float) + (s->audio_halfs * 2 + 15) / 16 * 16;
+    return MF_OK;
+}
+
+// n frames of n contexts (n == 1: the plain render).  k_setup: one CTA per frame; k_head: ONE cooperative launch for the batch;
+// k_torso_compose (+ resize): per frame.
+static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uint8_t *const *outs, const mf_ernerf_debug *dbg,
+                         int n, cudaStream_t stream) {
+    mf_ctx *ctx = ctxs[0];
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PreparedFrame pf[HEAD_MAX_FRAMES];
+    for (int i = 0; i < n; i++) {
+        int rc = prepare_frame(ctxs[i], &frames[i], i == 0 ? dbg : nullptr, pf[i]);
+        if (rc) {
+            if (i > 0) mf_fail(ctx, rc, "mf_ernerf_render_batch: frame %d: %s", i, mf_last_error(ctxs[i]));
+            return rc;
+        }
+    }
+    ErnerfState *s0 = pf[0].s;
+    size_t setup_smem = 0;
+    SetupBatch sb;
+    sb.n = n;
+    for (int i = 0; i < n; i++) {
+        sb.f[i] = pf[i].sp;
+        setup_smem = std::max(setup_smem, SETUP_FLOATS * sizeof(float) + (pf[i].s->audio_halfs * 2 + 15) / 16 * 16);
+    }
     static mf_per_device_flag setup_attr;
     if (!setup_attr.test_and_set(ctx->device)) {
         MF_CUDA(ctx, cudaFuncSetAttribute(k_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     MF_REQUIRE(ctx, setup_smem <= 200 * 1024, "audio weight image too large for k_setup");
-    k_setup<<<1, SETUP_THREADS, setup_smem, stream>>>(sp);
-    launches++;
+    k_setup<<<n, SETUP_THREADS, setup_smem, stream>>>(sb);
+    int launches = 1;
 
     HeadParams hp;
-    hp.g = g; hp.hl = s->hl; hp.planes = s->planes; hp.plane_rows = s->plane_rows; hp.bitfield = s->bitfield;
-    hp.mlp_image = s->head_mlp; hp.state = s->state; hp.eye = f->eye;
-    hp.bound = s->cfg.bound; hp.min_near = s->cfg.min_near; hp.dt_gamma = s->cfg.dt_gamma; hp.T_thresh = s->cfg.T_thresh;
-    hp.max_steps = s->cfg.max_steps; hp.cascade = s->cfg.cascade; hp.grid_size = s->cfg.grid_size;
-    const float b = s->cfg.bound;  // renderer.py:86
+    hp.hl = s0->hl; hp.planes = s0->planes; hp.plane_rows = s0->plane_rows; hp.bitfield = s0->bitfield;
+    hp.mlp_image = s0->head_mlp;
+    hp.bound = s0->cfg.bound; hp.min_near = s0->cfg.min_near; hp.dt_gamma = s0->cfg.dt_gamma; hp.T_thresh = s0->cfg.T_thresh;
+    hp.max_steps = s0->cfg.max_steps; hp.cascade = s0->cfg.cascade; hp.grid_size = s0->cfg.grid_size;
+    const float b = s0->cfg.bound;  // renderer.py:86
     const float aabb[6] = {-b, -b / 2, -b, b, b / 2, b};
     for (int i = 0; i < 6; i++) hp.aabb[i] = aabb[i];
-    hp.alive0 = s->alive[0]; hp.alive1 = s->alive[1]; hp.counters = s->counters;
-    hp.rays_t = s->rays_t; hp.nears = dbg && dbg->nears ? dbg->nears : nullptr;
-    hp.fars = s->fars; hp.weights_sum = s->weights_sum; hp.image = s->image;
+    hp.n_frames = n;
+    long total_tiles = 0;
+    for (int i = 0; i < n; i++) {
+        ErnerfState *s = pf[i].s;
+        HeadFrame &hf = hp.f[i];
+        hf.g = pf[i].g; hf.state = s->state; hf.eye = frames[i].eye;
+        hf.alive0 = s->alive[0]; hf.alive1 = s->alive[1]; hf.counters = s->counters;
+        hf.rays_t = s->rays_t; hf.nears = (i == 0 && dbg && dbg->nears) ? dbg->nears : nullptr;
+        hf.fars = s->fars; hf.weights_sum = s->weights_sum; hf.image = s->image;
+        total_tiles += (pf[i].N + 31) / 32;
+    }
     {
         void *args[] = {&hp};
-        const int grid = std::min(s->head_grid, std::max(1, (N + 31) / 32 / HEAD_WARPS + 1));
-        if (s->profile) MF_CUDA(ctx, cudaEventRecord(s->ev_head[0], stream));
+        const int grid = (int)std::min<long>(s0->head_grid, std::max<long>(1, total_tiles / HEAD_WARPS + 1));
+        if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[0], stream));
         MF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_head, dim3(grid), dim3(HEAD_THREADS), args,
                                                  sizeof(HeadSmem), stream));
-        if (s->profile) MF_CUDA(ctx, cudaEventRecord(s->ev_head[1], stream));
+        if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[1], stream));
         launches++;
     }
 
-    TorsoParams tp;
-    tp.g = g; tp.tl = s->tl; tp.table = s->torso_table; tp.density = s->torso_density; tp.mlp_image = s->torso_mlp;
-    tp.state = s->state; tp.bg_color = (const __half *)f->bg_color; tp.thresh = s->cfg.density_thresh_torso;
-    tp.shrink = s->cfg.torso_shrink; tp.G = (int)s->cfg.grid_size; tp.weights_sum = s->weights_sum; tp.image = s->image;
-    tp.out_f32 = resize ? s->final_f32 : f->out_image_f32;
-    tp.out_u8 = resize ? nullptr : out_rgb;
-    tp.dbg_mask = dbg ? dbg->torso_mask : nullptr;
-    tp.dbg_image_head = dbg ? dbg->image_head : nullptr;
-    {
-        const int n_tiles = (N + 31) / 32;
-        const int grid = std::max(1, std::min((n_tiles + TORSO_WARPS - 1) / TORSO_WARPS, ctx->sm_count * 4));
-        k_torso_compose<<<grid, TORSO_THREADS, sizeof(TorsoSmem), stream>>>(tp);
-        launches++;
-    }
-    if (resize) {
-        const int tot = outH * outW;
-        k_resize_u8<<<(tot + 255) / 256, 256, 0, stream>>>(s->final_f32, f->H, f->W, outH, outW, f->out_image_f32, out_rgb);
-        launches++;
-    }
-    if (dbg) {
-        if (dbg->fars) MF_CUDA(ctx, cudaMemcpyAsync(dbg->fars, s->fars, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
-        if (dbg->weights_sum)
-            MF_CUDA(ctx, cudaMemcpyAsync(dbg->weights_sum, s->weights_sum, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
-        if (dbg->round_info)
-            MF_CUDA(ctx, cudaMemcpy2DAsync(dbg->round_info, 4 * sizeof(int), s->counters, ER_CTR_STRIDE * sizeof(int),
-                                           4 * sizeof(int), ER_MAX_ROUNDS + 1, cudaMemcpyDeviceToDevice, stream));
+    for (int i = 0; i < n; i++) {
+        ErnerfState *s = pf[i].s;
+        const mf_ernerf_frame *f = &frames[i];
+        const mf_ernerf_debug *d = i == 0 ? dbg : nullptr;
+        const int N = pf[i].N;
+        TorsoParams tp;
+        tp.g = pf[i].g; tp.tl = s->tl; tp.table = s->torso_table; tp.density = s->torso_density; tp.mlp_image = s->torso_mlp;
+        tp.state = s->state; tp.bg_color = (const __half *)f->bg_color; tp.thresh = s->cfg.density_thresh_torso;
+        tp.shrink = s->cfg.torso_shrink; tp.G = (int)s->cfg.grid_size; tp.weights_sum = s->weights_sum; tp.image = s->image;
+        tp.out_f32 = pf[i].resize ? s->final_f32 : f->out_image_f32;
+        tp.out_u8 = pf[i].resize ? nullptr : outs[i];
+        tp.dbg_mask = d ? d->torso_mask : nullptr;
+        tp.dbg_image_head = d ? d->image_head : nullptr;
+        {
+            const int n_tiles = (N + 31) / 32;
+            const int grid = std::max(1, std::min((n_tiles + TORSO_WARPS - 1) / TORSO_WARPS, ctx->sm_count * 4));
+            k_torso_compose<<<grid, TORSO_THREADS, sizeof(TorsoSmem), stream>>>(tp);
+            launches++;
+        }
+        if (pf[i].resize) {
+            const int tot = pf[i].outH * pf[i].outW;
+            k_resize_u8<<<(tot + 255) / 256, 256, 0, stream>>>(s->final_f32, f->H, f->W, pf[i].outH, pf[i].outW, f->out_image_f32, outs[i]);
+            launches++;
+        }
+        if (d) {
+            if (d->fars) MF_CUDA(ctx, cudaMemcpyAsync(d->fars, s->fars, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
+            if (d->weights_sum)
+                MF_CUDA(ctx, cudaMemcpyAsync(d->weights_sum, s->weights_sum, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
+            if (d->round_info)
+                MF_CUDA(ctx, cudaMemcpy2DAsync(d->round_info, 4 * sizeof(int), s->counters, ER_CTR_STRIDE * sizeof(int),
+                                               4 * sizeof(int), ER_MAX_ROUNDS + 1, cudaMemcpyDeviceToDevice, stream));
+        }
     }
     MF_CUDA(ctx, cudaGetLastError());
-    s->last_launches = launches;
+    for (int i = 0; i < n; i++) pf[i].s->last_launches = launches;
     return MF_OK;
+}
+
+extern "C" int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *f, uint8_t *out_rgb, const mf_ernerf_debug *dbg,
+                                void *stream_) {
+    if (!ctx) return MF_E_INVALID;
+    if (!ctx->ernerf) return mf_fail(ctx, MF_E_STATE, "mf_ernerf_render: ErNeRF weights not loaded");
+    MF_REQUIRE(ctx, f, "mf_ernerf_render: null frame/pose");
+    return render_frames(&ctx, f, &out_rgb, dbg, 1, (cudaStream_t)stream_);
+}
+
+extern "C" int mf_ernerf_render_batch(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uint8_t *const *outs, int n, void *stream_) {
+    if (!ctxs || n < 1 || !ctxs[0]) return MF_E_INVALID;
+    mf_ctx *ctx = ctxs[0];
+    MF_REQUIRE(ctx, frames && outs, "mf_ernerf_render_batch: null pointer");
+    MF_REQUIRE(ctx, n <= HEAD_MAX_FRAMES, "mf_ernerf_render_batch: %d frames, at most %d per call", n, HEAD_MAX_FRAMES);
+    for (int i = 0; i < n; i++) {
+        MF_REQUIRE(ctx, ctxs[i] && ctxs[i]->ernerf, "mf_ernerf_render_batch: context %d has no ErNeRF weights", i);
+        MF_REQUIRE(ctx, ctxs[i]->device == ctx->device, "mf_ernerf_render_batch: contexts on different devices");
+        for (int j = 0; j < i; j++) MF_REQUIRE(ctx, ctxs[j] != ctxs[i], "mf_ernerf_render_batch: a context appears twice (one frame per session)");
+        const ErnerfState *a = ctx->ernerf, *b = ctxs[i]->ernerf;
+        // one MLP image / one set of tables is staged per CTA: the sessions of a batch must render the same avatar model
+        MF_REQUIRE(ctx, a->head_mlp == b->head_mlp && a->planes == b->planes && a->bitfield == b->bitfield &&
+                            memcmp(&a->cfg, &b->cfg, sizeof(a->cfg)) == 0,
+                   "mf_ernerf_render_batch: context %d was loaded from a different blob / configuration", i);
+    }
+    return render_frames(ctxs, frames, outs, nullptr, n, (cudaStream_t)stream_);
 }
 
 // ---- kernel-level entry points ---------------------------------------------------------

@@ -64,6 +64,43 @@ class ErnerfRenderer:
     def last_launches(self):
         return lib().mf_ernerf_last_launches(self.ctx.handle)
 
+    @staticmethod
+    def render_batch(renderers, frames, outs=None, stream=None):
+        """One pass for up to 4 sessions of the same avatar model (mf_ernerf_render_batch): renderers[i] renders
+        frames[i] = dict(pose, intrinsics, H, W, auds | enc_a, eye[, outH, outW, bg_color]) into outs[i].  Same images
+        as renderers[i].render(**frames[i]), bit for bit; the fused head kernel is launched once for the batch."""
+        n = len(renderers)
+        assert n == len(frames) and n >= 1
+        dev = renderers[0].device
+        arr = (MfErnerfFrame * n)()
+        keep = []
+        if outs is None:
+            outs = [None] * n
+        outs = list(outs)
+        for i, (r, f) in enumerate(zip(renderers, frames)):
+            pose = np.ascontiguousarray(np.asarray(f["pose"], np.float32).reshape(16))
+            keep.append(pose)
+            fr = arr[i]
+            fr.pose = pose.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+            fr.fx, fr.fy, fr.cx, fr.cy = [float(v) for v in f["intrinsics"]]
+            fr.H, fr.W = int(f["H"]), int(f["W"])
+            fr.auds = _ptr(f.get("auds"))
+            fr.enc_a = _ptr(f.get("enc_a"))
+            fr.eye = float(f.get("eye", 0.25))
+            fr.bg_color = _ptr(f.get("bg_color"))
+            fr.rays_o = fr.rays_d = fr.bg_coords = None
+            fr.n_rays = 0
+            fr.outH, fr.outW = int(f.get("outH") or f["H"]), int(f.get("outW") or f["W"])
+            fr.out_image_f32 = _ptr(f.get("out_f32"))
+            if outs[i] is None:
+                outs[i] = torch.empty((fr.outH, fr.outW, 3), dtype=torch.uint8, device=dev)
+        ctxs = (ctypes.c_void_p * n)(*[r.ctx.handle for r in renderers])
+        optr = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+        s = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = lib().mf_ernerf_render_batch(ctxs, arr, optr, n, ctypes.c_void_p(s.cuda_stream))
+        check(renderers[0].ctx.handle, rc, "mf_ernerf_render_batch")
+        return outs
+
     def render(self, pose, intrinsics, H, W, auds=None, eye=0.25, out=None, outH=None, outW=None, enc_a=None,
                bg_color=None, rays_o=None, rays_d=None, bg_coords=None, out_f32=None, debug=False, stream=None):
         """pose: 16 floats (host, row-major cam2world); auds: cuda fp32 [8, A, 16];

@@ -26,3 +26,27 @@ for H in (450, 512):
     print(f"H={H}: {ms:.3f} ms/frame = {1000/ms:.1f} fps; rounds:", dbg["round_info"].cpu().numpy()[:8].tolist(), flush=True)
     import cv2
     cv2.imwrite(f"gpurun_out/ernerf_{H}.png", o.cpu().numpy()[..., ::-1])
+
+# ---- batched render (mf_ernerf_render_batch): F sessions of the same avatar model per pass
+H = 512
+rens = [ErnerfRenderer(blob=ren.blob, cfg=ren.cfg) for _ in range(4)]
+ins = [ernerf_inputs(f, H, H) for f in range(16)]
+auds = [torch.from_numpy(i[2]).cuda() for i in ins]
+for F in (1, 2, 3, 4):
+    outs = [torch.empty(H, H, 3, dtype=torch.uint8, device="cuda") for _ in range(F)]
+
+    def go(k):
+        fs = [dict(pose=ins[(k * F + j) % 16][0], intrinsics=ins[(k * F + j) % 16][1], H=H, W=H, auds=auds[(k * F + j) % 16],
+                   eye=ins[(k * F + j) % 16][3]) for j in range(F)]
+        ErnerfRenderer.render_batch(rens[:F], fs, outs=outs)
+    for k in range(5):
+        go(k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 40
+    e0.record()
+    for k in range(n):
+        go(k)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(f"batch F={F}: {ms:.3f} ms/pass = {ms / F:.3f} ms/frame = {1000 * F / ms:.1f} fps", flush=True)

@@ -334,3 +334,57 @@ def test_full_size_512_properties(env):
     assert ok.sum() > 1000 and np.abs(c[ok] - c[ok].mean(axis=1, keepdims=True)).max() < 4e-3     # channel-independent
     untouched = (ws == 0) & (dbg["torso_mask"] == 0)                   # no head sample, no torso: the pixel shows the background
     assert untouched.sum() > 1000 and np.abs(c.reshape(N, 3)[untouched] - 1).max() < 2e-3
+
+
+def test_render_batch_equals_single_renders(env):
+    """mf_ernerf_render_batch: frames of different sessions (contexts sharing one blob) rendered in ONE pass of the fused head kernel
+    are bit-identical to the same frames rendered one by one -- different poses, audio windows, eye values AND frame sizes in one
+    batch, per-session EMA state carried over two consecutive batches"""
+    from mere_fusion_b200._lib import MfError
+    from mere_fusion_b200.ernerf import ErnerfRenderer
+    base = env["ren"]
+    rens = [ErnerfRenderer(blob=base.blob, cfg=base.cfg, device=0) for _ in range(4)]
+    sizes = [(64, 64), (48, 80), (128, 128), (33, 50)]
+
+    def frames(step):
+        out = []
+        for i, (H, W) in enumerate(sizes):
+            pose, intr, auds, eye = ernerf_inputs(3 * i + step, max(H, W), max(H, W))
+            intr = (intr[0], intr[1], W / 2.0, H / 2.0)
+            out.append(dict(pose=pose, intrinsics=intr, H=H, W=W, auds=cu(auds), eye=eye))
+        return out
+
+    singles = []
+    for r in rens:
+        r.reset()
+    for step in (0, 1):                                    # two frames per session: the second one sees the EMA of the first
+        row = []
+        for r, f in zip(rens, frames(step)):
+            f32 = torch.empty(f["H"], f["W"], 3, device="cuda")
+            u8 = r.render(f["pose"], f["intrinsics"], f["H"], f["W"], f["auds"], f["eye"], out_f32=f32)
+            row.append((u8.clone(), f32))
+        singles.append(row)
+    torch.cuda.synchronize()
+    for r in rens:
+        r.reset()
+    for step in (0, 1):
+        fs = frames(step)
+        f32s = [torch.empty(f["H"], f["W"], 3, device="cuda") for f in fs]
+        for f, t in zip(fs, f32s):
+            f["out_f32"] = t
+        outs = ErnerfRenderer.render_batch(rens, fs)
+        torch.cuda.synchronize()
+        assert rens[0].last_launches == 1 + 1 + 4          # one k_setup grid, ONE k_head, four torso / compose launches
+        for i, (u8, f32) in enumerate(singles[step]):
+            assert torch.equal(outs[i], u8), f"step {step} session {i}: u8 differs"
+            assert torch.equal(f32s[i], f32), f"step {step} session {i}: fp32 differs"
+    # a batch of one is the plain render; refused batches
+    one = ErnerfRenderer.render_batch(rens[:1], frames(0)[:1])
+    assert one[0].shape == (64, 64, 3)
+    with pytest.raises(MfError):
+        ErnerfRenderer.render_batch([rens[0], rens[0]], frames(0)[:2])                 # one frame per session
+    other = ErnerfRenderer(env["sd"], env["md"], device=0)                            # its own copy of the blob
+    with pytest.raises(MfError):
+        ErnerfRenderer.render_batch([rens[0], other], frames(0)[:2])
+    with pytest.raises(MfError):
+        ErnerfRenderer.render_batch(rens + [other], frames(0) + frames(0)[:1])        # more than 4
