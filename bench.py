@@ -427,8 +427,8 @@ def mixed_leg(args, dev, local, rank, world, flush, timed_fn, shared, ernerf_blo
     """BASELINE configs[4] / SURVEY 8(d) config 5: 64 concurrent mixed sessions on 8 GPUs = 8 sessions per GPU, heads round-robin by
     session id (22 ErNeRF + 21 MuseTalk + 21 Wav2Lip in total, every GPU hosts all three heads).  This rank runs ITS 8 sessions
     (round-robin, dist.shard): at --gpus 1 the line is the per-GPU slice, at --gpus 8 the full config.
-    One step = every session advances 16 video frames (0.64 s of video): ErNeRF 16 sequential frame renders on the session's own
-    context (per-session EMA state); MuseTalk one Whisper window + one 16-frame UNet/VAE pass + blend per session on the shared
+    One step = every session advances 16 video frames (0.64 s of video): ErNeRF 16 passes, each rendering one frame of every ErNeRF
+    session of the GPU (mf_ernerf_render_batch; per-session contexts keep the EMA state); MuseTalk one Whisper window + one 16-frame UNet/VAE pass + blend per session on the shared
     engine; Wav2Lip one 16-frame pass per session, the same-GPU sessions COALESCED into one launch sequence by
     scheduler.SharedEngine, + paste.  value = sessions x 16 frames / step time, aggregate over ranks."""
     import ctypes
@@ -449,6 +449,7 @@ def mixed_leg(args, dev, local, rank, world, flush, timed_fn, shared, ernerf_blo
     muse_eng, a2f = shared["musetalk_engine"], shared["a2f"]
     hL, hM = lip_eng.ctx.handle, muse_eng.ctx.handle
     sessions = []
+    nerf_sessions = []                          # the GPU's ErNeRF sessions render their frames together (ErnerfRenderer.render_batch)
     pins = []                                   # (pinned host result, device result) per session for the e2e arm
     h2d = 0
     for sid, head in mine:
@@ -458,21 +459,14 @@ def mixed_leg(args, dev, local, rank, world, flush, timed_fn, shared, ernerf_blo
         pins.append((out_pin, out))
         if head == "ernerf":
             ren = ErnerfRenderer(blob=ernerf_blob, cfg=ernerf_cfg, device=local)
+            nerf_sessions.append(dict(ren=ren, sid=sid, out=out))
             ins = [ernerf_inputs((sid * 37 + f) % 300, H, W) for f in range(B)]
             auds_pin = torch.from_numpy(np.stack([i[2] for i in ins])).pin_memory()
             auds_dev = auds_pin.to(dev)
             stage = torch.empty_like(auds_dev)
             h2d += auds_pin.numel() * 4 + B * 84
 
-            def run(k, host, ren=ren, ins=ins, auds_dev=auds_dev, auds_pin=auds_pin, stage=stage, out=out):
-                src = auds_dev
-                if host:
-                    stage.copy_(auds_pin, non_blocking=True)
-                    src = stage
-                for f in range(B):
-                    p, intr, _, eye = ins[(f + k) % B]
-                    ren.render(p, intr, H, W, src[(f + k) % B], eye, out=out[f])
-            sessions.append((head, run, None))
+            nerf_sessions[-1].update(ins=ins, auds_dev=auds_dev, auds_pin=auds_pin, stage=stage)
         elif head == "musetalk":
             n_av = 12
             frames = torch.from_numpy(rng.integers(0, 200, (n_av, H, W, 3), dtype=np.uint8)).to(dev)
@@ -540,8 +534,25 @@ def mixed_leg(args, dev, local, rank, world, flush, timed_fn, shared, ernerf_blo
                                                    ctypes.c_void_p(st.cuda_stream)), "mf_paste_resize_u8")
             sessions.append((head, submit, finish))
 
+    def nerf_tick(k, host):
+        """16 frames of every ErNeRF session of this GPU: frame f of all sessions in one batched pass (<= 4 sessions per pass)"""
+        for ns in nerf_sessions:
+            if host:
+                ns["stage"].copy_(ns["auds_pin"], non_blocking=True)
+        for f in range(B):
+            for c0 in range(0, len(nerf_sessions), 4):
+                grp = nerf_sessions[c0:c0 + 4]
+                frs = []
+                for ns in grp:
+                    p, intr, _, eye = ns["ins"][(f + k) % B]
+                    src = ns["stage"] if host else ns["auds_dev"]
+                    frs.append(dict(pose=p, intrinsics=intr, H=H, W=W, auds=src[(f + k) % B], eye=eye))
+                ErnerfRenderer.render_batch([ns["ren"] for ns in grp], frs, outs=[ns["out"][f] for ns in grp])
+
     def tick(k, host):
         lip = []
+        if nerf_sessions:
+            nerf_tick(k, host)
         for head, fn, fin in sessions:
             if head == "wav2lip":
                 lip.append((fn(k, host), fin))
@@ -719,6 +730,44 @@ def main():
         head_samples.append(n)
     ren.profile(False)
 
+    # ---- batched sessions (mf_ernerf_render_batch): FB sessions of the same avatar model, one frame each per pass -- what a GPU
+    # that hosts several ErNeRF sessions runs (scheduler.ErnerfBatcher); images are bit-identical to single renders
+    FB = 4
+    rens_b = [ren] + [ErnerfRenderer(blob=blob, cfg=cfg, device=local) for _ in range(FB - 1)]
+    outs_b = [torch.empty(H, W, 3, dtype=torch.uint8, device=dev) for _ in range(FB)]
+    outs_b_pin = torch.empty(FB, H, W, 3, dtype=torch.uint8).pin_memory()
+    auds_b_stage = [torch.empty_like(auds_dev[0]) for _ in range(FB)]
+
+    def batch_frames(k, src):
+        return [dict(pose=ins[(k * FB + j) % n_in][0], intrinsics=ins[(k * FB + j) % n_in][1], H=H, W=W, auds=src(k, j),
+                     eye=ins[(k * FB + j) % n_in][3]) for j in range(FB)]
+
+    def step_batch(k):
+        ErnerfRenderer.render_batch(rens_b, batch_frames(k, lambda k, j: auds_dev[(k * FB + j) % n_in]), outs=outs_b)
+
+    def step_batch_host(k):
+        for j in range(FB):
+            auds_b_stage[j].copy_(auds_pin[(k * FB + j) % n_in], non_blocking=True)
+        ErnerfRenderer.render_batch(rens_b, batch_frames(k, lambda k, j: auds_b_stage[j]), outs=outs_b)
+        for j in range(FB):
+            outs_b_pin[j].copy_(outs_b[j], non_blocking=True)
+
+    Kb = max(20, args.steps // 4)
+    batch_ms, _, _ = timed(step_batch, Kb, args.warmup)
+    batch_e2e_ms, _, _ = timed(step_batch_host, Kb, args.warmup)
+    for r_ in rens_b:
+        r_.profile(True)
+    bh_ms, bh_samples = [], []
+    for k in range(min(20, args.steps)):
+        flush.fill_(k & 0xff)
+        step_batch(k)
+        ms, n = rens_b[0].last_head_ms()
+        bh_ms.append(ms)
+        bh_samples.append(n + sum(r_.last_head_ms(want_ms=False)[1] for r_ in rens_b[1:]))
+    for r_ in rens_b:
+        r_.profile(False)
+    ren.reset()
+
     # ---- the acoustic model behind NerfASR.run_step (wav2vec2 XLSR-53 shape, random weights): one 28-chunk window every 8 chunks
     # (= every 4 video frames, nerfasr.py:105-124); reported beside the render, not inside its step (SURVEY 8(d) config 4 feeds
     # synthetic logit windows)
@@ -779,6 +828,18 @@ def main():
         "p50_chunk_to_frame_ms": float(np.median(lat)),
         "rays_2048_per_frame": {"value": world * args.steps / (sub_ms / 1e3), "unit": "frames/s", "ms_per_step": sub_ms / args.steps,
                                 "note": "SURVEY 8(d) config 4 (i): 2048 explicit rays (every 128th pixel of the 512x512 grid) per frame"},
+        "ernerf_batched_sessions": {
+            "workload": f"{FB} ErNeRF sessions of one avatar model per GPU, one 512x512 frame each per pass (mf_ernerf_render_batch: ONE k_head "
+                        "launch per pass, shared round barriers); bit-identical to single renders",
+            "value": world * Kb * FB / (batch_ms / 1e3), "unit": "frames/s", "ms_per_pass": batch_ms / Kb, "ms_per_frame": batch_ms / Kb / FB,
+            "e2e": {"value": world * Kb * FB / (batch_e2e_ms / 1e3), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(FB * (auds_pin[0].numel() * 4 + 84)), "d2h_bytes_per_step": int(outs_b_pin.numel())},
+            "roofline": {"kernel": "k_head (4 frames per launch)", "bound": "hbm",
+                         "achieved": float(np.mean(bh_samples)) * BYTES_PER_SAMPLE / (float(np.mean(bh_ms)) * 1e-3) / 1e9,
+                         "peak": peaks()["hbm"], "unit": "GB/s",
+                         "frac": float(np.mean(bh_samples)) * BYTES_PER_SAMPLE / (float(np.mean(bh_ms)) * 1e-3) / 1e9 / peaks()["hbm"],
+                         "ms_per_launch": float(np.mean(bh_ms)), "samples_per_launch": float(np.mean(bh_samples)),
+                         "tensor_view_tflops": float(np.mean(bh_samples)) * FLOP_PER_SAMPLE / (float(np.mean(bh_ms)) * 1e-3) / 1e12}},
         "nerfasr_acoustic_model": asr,
         "gpu_launches": int(launches),
         "kernels_per_step": ["k_setup", "k_head", "k_torso_compose"],

@@ -38,10 +38,11 @@ class ErnerfRenderer:
     def profile(self, enable=True):
         check(self.ctx.handle, lib().mf_ernerf_profile(self.ctx.handle, int(enable)), "mf_ernerf_profile")
 
-    def last_head_ms(self):
-        """(duration of the last k_head launch in ms, samples it processed); synchronises"""
+    def last_head_ms(self, want_ms=True):
+        """(duration of the last k_head launch in ms, samples of THIS session's frame it processed); synchronises.  In a batched
+        render the launch is timed on the first session only: ask the others with want_ms=False (-> 0.0, samples)."""
         ms, n = ctypes.c_float(), ctypes.c_int64()
-        check(self.ctx.handle, lib().mf_ernerf_last_head_ms(self.ctx.handle, ctypes.byref(ms), ctypes.byref(n)),
+        check(self.ctx.handle, lib().mf_ernerf_last_head_ms(self.ctx.handle, ctypes.byref(ms) if want_ms else None, ctypes.byref(n)),
               "mf_ernerf_last_head_ms")
         return ms.value, n.value
 

@@ -145,3 +145,46 @@ def test_scheduler_shares_one_engine_per_gpu_and_head():
     sc.close("s2")
     assert (0, "wav2lip", None) not in sc.engines()
     sc.shutdown()
+
+
+class FakeRenderer:
+    calls = []
+
+    def __init__(self, i):
+        self.i, self.device, self.ctx = i, None, None
+
+    @staticmethod
+    def render_batch(rens, frames, outs=None):
+        FakeRenderer.calls.append([r.i for r in rens])
+        return [(r.i, f["eye"]) for r, f in zip(rens, frames)]
+
+
+def test_ernerf_batcher_one_frame_per_session_at_most_four():
+    from mere_fusion_b200.scheduler import ErnerfBatcher
+    FakeRenderer.calls = []
+    b = ErnerfBatcher(None, threaded=False)
+    rs = [FakeRenderer(i) for i in range(6)]
+    order = [0, 1, 0, 2, 3, 4, 5, 1]
+    reqs = [b.submit(rs[i], dict(eye=j)) for j, i in enumerate(order)]
+    b.flush()
+    assert FakeRenderer.calls == [[0, 1, 2, 3], [0, 4, 5, 1]]      # a session's second frame waits for the next pass (EMA order)
+    assert [b.wait(r) for r in reqs] == [(i, j) for j, i in enumerate(order)]
+    assert (b.batches, b.frames) == (2, 8)
+    proxy = b.wrap(rs[2])
+    assert proxy.render(None, None, 8, 8, eye=0.5) == (2, 0.5) and proxy.i == 2      # same call shape as ErnerfRenderer.render
+    b.shutdown()
+    with pytest.raises(RuntimeError):
+        b.submit(rs[0], dict(eye=0))
+
+
+def test_scheduler_hands_ernerf_sessions_a_batched_renderer():
+    sc = SessionScheduler(n_gpus=1, threaded=False)
+    g, r0 = sc.open("n0", "ernerf", factory=lambda gpu, _: FakeRenderer(10))
+    g, r1 = sc.open("n1", "ernerf", factory=lambda gpu, _: FakeRenderer(11))
+    assert r0._b is r1._b and r0.renderer.i == 10 and r1.renderer.i == 11
+    FakeRenderer.calls = []
+    q0, q1 = r0._b.submit(r0.renderer, dict(eye=1)), r1._b.submit(r1.renderer, dict(eye=2))
+    r0._b.flush()
+    assert FakeRenderer.calls == [[10, 11]] and r0._b.wait(q1) == (11, 2)
+    sc.close("n0"), sc.close("n1")
+    assert not sc.engines()

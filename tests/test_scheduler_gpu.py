@@ -124,3 +124,54 @@ def test_two_lipreal_sessions_on_one_shared_engine():
             assert np.abs(f.astype(int) - r.astype(int)).max() <= 8 and np.abs(f.astype(int) - r.astype(int)).mean() < 0.1
     sched.close("a"), sched.close("b")
     assert not sched.engines()
+
+
+def test_ernerf_batcher_threads_bit_identical():
+    """three ErNeRF sessions (threads, own streams, own contexts on one shared blob) rendering 4 consecutive frames each through
+    scheduler.ErnerfBatcher get exactly the images they get alone -- the EMA of the audio feature is per-session state"""
+    from helpers import ernerf_inputs, load_ernerf_fixture
+    from mere_fusion_b200.ernerf import ErnerfRenderer
+    from mere_fusion_b200.scheduler import SessionScheduler
+    sd, md = load_ernerf_fixture()
+    base = ErnerfRenderer(sd, md, device=0)
+    H = 96
+    n_sess, n_frames = 3, 4
+    ins = [[ernerf_inputs(10 * s + f, H, H) for f in range(n_frames)] for s in range(n_sess)]
+    solo = []
+    for s in range(n_sess):
+        r = ErnerfRenderer(blob=base.blob, cfg=base.cfg, device=0)
+        row = []
+        for f in range(n_frames):
+            p, intr, auds, eye = ins[s][f]
+            row.append(r.render(p, intr, H, H, torch.from_numpy(auds).cuda(), eye).clone())
+        solo.append(row)
+    torch.cuda.synchronize()
+
+    sched = SessionScheduler(n_gpus=1, window_ms=20.0)
+    proxies = [sched.open(f"n{s}", "ernerf", factory=lambda g, _: ErnerfRenderer(blob=base.blob, cfg=base.cfg, device=g))[1] for s in range(n_sess)]
+    batcher = proxies[0]._b
+    res, errs, gate = {}, [], threading.Barrier(n_sess)
+
+    def session(s):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                got = []
+                gate.wait()
+                for f in range(n_frames):
+                    p, intr, auds, eye = ins[s][f]
+                    got.append(proxies[s].render(p, intr, H, H, torch.from_numpy(auds).cuda(), eye).clone())
+                torch.cuda.current_stream().synchronize()
+                res[s] = got
+        except Exception as e:                                    # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=session, args=(s,)) for s in range(n_sess)]
+    [t.start() for t in th]
+    [t.join(timeout=120) for t in th]
+    assert not errs, errs
+    assert batcher.frames == n_sess * n_frames and batcher.batches < n_sess * n_frames      # some passes carried several sessions
+    for s in range(n_sess):
+        for f in range(n_frames):
+            assert torch.equal(res[s][f], solo[s][f]), f"session {s} frame {f}"
+    for s in range(n_sess):
+        sched.close(f"n{s}")
