@@ -34,8 +34,8 @@ def _adapt_provider(data_loader):
 
 def _adapt_renderer(trainer, opt, device):
     from ..ernerf import ErnerfRenderer
-    if isinstance(trainer, ErnerfRenderer):
-        return trainer
+    if isinstance(trainer, ErnerfRenderer) or isinstance(getattr(trainer, "renderer", None), ErnerfRenderer):
+        return trainer                                  # a renderer, or the scheduler's batched proxy around one (scheduler.ErnerfBatcher)
     model = getattr(trainer, "model", None)             # reference Trainer: take the loaded weights over
     if model is None:
         raise TypeError("trainer must be an ErnerfRenderer or the reference Trainer")

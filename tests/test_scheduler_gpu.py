@@ -175,3 +175,57 @@ def test_ernerf_batcher_threads_bit_identical():
             assert torch.equal(res[s][f], solo[s][f]), f"session {s} frame {f}"
     for s in range(n_sess):
         sched.close(f"n{s}")
+
+
+def test_two_nerfreal_sessions_behind_the_batcher():
+    """plugin level: two NeRFReal sessions whose renderers come from SessionScheduler.open(..., "ernerf") stream frames concurrently;
+    the frames equal those of a session on a plain ErnerfRenderer fed the same audio features"""
+    from helpers import load_ernerf_fixture, load_pose_fixture
+    from test_plugin_cpu import clip_10s, make_opt
+    from test_plugin_gpu import _run
+    from mere_fusion_b200.ernerf import ErnerfRenderer
+    from mere_fusion_b200.ernerf_data import ErnerfPoseProvider
+    from mere_fusion_b200.plugin.nerfreal import NeRFReal
+    from mere_fusion_b200.scheduler import SessionScheduler
+    sd, md = load_ernerf_fixture()
+    pf = load_pose_fixture()
+    tr = dict(cx=float(pf["cx"]), cy=float(pf["cy"]), focal_len=float(pf["focal_len"]),
+              frames=[dict(transform_matrix=pf["raw"][i].tolist(), img_id=int(pf["img_id"][i])) for i in range(40)])
+    au = np.zeros(int(pf["img_id"][:40].max()) + 1)
+    au[:min(len(au), len(pf["au"]))] = pf["au"][:len(au)]
+    base = ErnerfRenderer(sd, md, device=0)
+    wav = clip_10s()
+    chunks = [wav[i * 320:(i + 1) * 320] for i in range(100)]
+
+    def feature_fn_for(seed):
+        rng = np.random.default_rng(seed)
+        return lambda frame: torch.from_numpy(rng.standard_normal(((len(frame) - 400) // 320 + 1, 44)).astype(np.float32))
+
+    def make(renderer, seed):
+        return NeRFReal(make_opt(W=128, H=128), renderer, ErnerfPoseProvider(tr, au), feature_fn=feature_fn_for(seed), device=0)
+
+    n = 24
+    ref = []
+    for s in range(2):
+        v, a = _run(make(ErnerfRenderer(blob=base.blob, cfg=base.cfg, device=0), 100 + s), n, chunks)
+        ref.append([f.to_ndarray().copy() for f in v[:n]])
+    sched = SessionScheduler(n_gpus=1, window_ms=5.0)
+    reals = [make(sched.open(f"n{s}", "ernerf", factory=lambda g, _: ErnerfRenderer(blob=base.blob, cfg=base.cfg, device=g))[1], 100 + s)
+             for s in range(2)]
+    res = {}
+
+    def drive(s):
+        v, a = _run(reals[s], n, chunks)
+        res[s] = ([f.to_ndarray().copy() for f in v[:n]], len(v), len(a))
+
+    th = [threading.Thread(target=drive, args=(s,)) for s in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    batcher = reals[0].renderer._b
+    assert batcher.frames >= 2 * n
+    for s in range(2):
+        frames, nv, na = res[s]
+        assert len(frames) == n and abs(na - 2 * nv) <= 2
+        for k, (f, r) in enumerate(zip(frames, ref[s])):
+            assert np.array_equal(f, r), f"session {s} frame {k}"
+    sched.close("n0"), sched.close("n1")
