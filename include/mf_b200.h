@@ -241,6 +241,10 @@ int mf_whisper_features(mf_ctx *ctx, const float *audio, int n_samples, float *o
  *   out_f32 : device fp32 [n_frames, vocab] (27 x 44); NerfASR keeps rows [l : T - r + 1]
  * ------------------------------------------------------------------------------------------ */
 int mf_wav2vec2_logits(mf_ctx *ctx, const float *audio, int n_samples, float *out_f32, void *stream);
+/* the same for B windows at once (B <= the max_batch given to mf_wav2lip_load): the windows of B different ErNeRF sessions of one GPU in one
+ * pass over the 630 MB of weights (the model is weight-streaming / launch-latency bound at one window).
+ *   audio   : device fp32 [B, n_samples]          out_f32 : device fp32 [B, n_frames, vocab] */
+int mf_wav2vec2_logits_batch(mf_ctx *ctx, const float *audio, int n_samples, int B, float *out_f32, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Paste-back (lipreal.py:207-214): out[i] = frames[idx_i] with faces[i] resized (cv2.resize, u8,

@@ -86,6 +86,7 @@ def lib():
         L.mf_paste_resize_u8.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int,
                                          ctypes.c_int, ctypes.POINTER(c_i32), c_vp, c_vp]
         L.mf_wav2vec2_logits.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp, c_vp]
+        L.mf_wav2vec2_logits_batch.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp]
         L.mf_whisper_features.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp]
         L.mf_wav2lip_mel_chunks.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp, ctypes.POINTER(c_i32), ctypes.c_int, c_vp, c_vp]
         L.mf_paste_blend_u8.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int,

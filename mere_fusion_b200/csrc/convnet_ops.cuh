@@ -178,10 +178,10 @@ __global__ void __launch_bounds__(256) k_whisper_gather(const GatherParams p) {
 // the raw audio never gets rounded to bf16; the 512-channel output is the program's first bf16 buffer.
 // ---------------------------------------------------------------------------------------------------
 struct W2vPrep {
-    const float *audio;     // device fp32 [n_samples]
+    const float *audio;     // device fp32 [B][n_samples]: one window per batch item (blockIdx.y)
     const float *conv0;     // fp32 [C0][k0] then [C0] bias
-    float *stats;           // (mean, rstd)
-    __nv_bfloat16 *out;     // [n_frames][1][C0]
+    float *stats;           // [B] x (mean, rstd)
+    __nv_bfloat16 *out;     // [B][n_frames][1][C0]
     int n_samples, n_frames, C0, k0, s0;
 };
 __global__ void __launch_bounds__(1024) k_w2v_stats(const W2vPrep p) {
@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(1024) k_w2v_stats(const W2vPrep p) {
     pdl_wait();
     __shared__ double red[32];
     double s = 0.0, q = 0.0;
-    for (int i = threadIdx.x; i < p.n_samples; i += blockDim.x) { const double v = p.audio[i]; s += v; q += v * v; }
+    const float *audio = p.audio + (size_t)blockIdx.y * p.n_samples;
+    for (int i = threadIdx.x; i < p.n_samples; i += blockDim.x) { const double v = audio[i]; s += v; q += v * v; }
     for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -203,8 +204,8 @@ __global__ void __launch_bounds__(1024) k_w2v_stats(const W2vPrep p) {
         for (int o = 16; o; o >>= 1) Q += __shfl_xor_sync(0xffffffffu, Q, o);
         if (threadIdx.x == 0) {
             const double mean = S / p.n_samples, var = Q / p.n_samples - mean * mean;   // numpy var (population)
-            p.stats[0] = (float)mean;
-            p.stats[1] = (float)(1.0 / sqrt(var + 1e-7));
+            p.stats[2 * blockIdx.y] = (float)mean;
+            p.stats[2 * blockIdx.y + 1] = (float)(1.0 / sqrt(var + 1e-7));
         }
     }
 }
@@ -214,11 +215,12 @@ __global__ void __launch_bounds__(256) k_w2v_conv0(const W2vPrep p) {
     pdl_wait();
     __shared__ float xs[7 * 16 + 16];   // s0, k0 <= 16 (checked at load)
     const int t0 = blockIdx.x * 8;
-    const float mean = p.stats[0], rstd = p.stats[1];
+    const float mean = p.stats[2 * blockIdx.y], rstd = p.stats[2 * blockIdx.y + 1];
+    const float *audio = p.audio + (size_t)blockIdx.y * p.n_samples;
     const int span = 7 * p.s0 + p.k0;   // samples touched by the CTA's 8 frames
     for (int i = threadIdx.x; i < span; i += blockDim.x) {
         const int src = t0 * p.s0 + i;
-        xs[i] = src < p.n_samples ? (p.audio[src] - mean) * rstd : 0.f;
+        xs[i] = src < p.n_samples ? (audio[src] - mean) * rstd : 0.f;
     }
     __syncthreads();
     for (int o = threadIdx.x; o < 8 * p.C0; o += blockDim.x) {
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(256) k_w2v_conv0(const W2vPrep p) {
         const float *w = p.conv0 + c * p.k0;
         float acc = __ldg(p.conv0 + p.C0 * p.k0 + c);
         for (int k = 0; k < p.k0; k++) acc = fmaf(__ldg(w + k), xs[f * p.s0 + k], acc);
-        p.out[(size_t)(t0 + f) * p.C0 + c] = __float2bfloat16_rn(acc);
+        p.out[((size_t)blockIdx.y * p.n_frames + t0 + f) * p.C0 + c] = __float2bfloat16_rn(acc);
     }
 }
 

@@ -713,7 +713,7 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
                             s->ops.back().kind == 0 && s->ops.back().mode == 3 && s->ops.back().Cout == s->w2v_vocab,
                    "wav2vec2 program: first-layer entry / buffers do not match the aux record");
         s->w2v_conv0 = reinterpret_cast<const float *>(base + ce->offset);
-        MF_CUDA(ctx, cudaMalloc(&s->w2v_stats, 2 * sizeof(float)));
+        MF_CUDA(ctx, cudaMalloc(&s->w2v_stats, (size_t)max_batch * 2 * sizeof(float)));
     }
     if (s->has_gn) {
         MF_CUDA(ctx, cudaMalloc(&s->gn_coef, (size_t)max_batch * GN_MAX_C * 2 * sizeof(float)));
@@ -1105,8 +1105,8 @@ static int build_plan(mf_ctx *ctx, Wav2LipState *s, Wav2LipState::Plan *pl, int 
         w.audio = nullptr; w.conv0 = s->w2v_conv0; w.stats = s->w2v_stats; w.out = s->dbuf[s->hdr.in_face_buf];
         w.n_samples = s->w2v_samples; w.n_frames = s->bufs[s->hdr.in_face_buf].H; w.C0 = s->w2v_c0; w.k0 = s->w2v_k0; w.s0 = s->w2v_s0;
         Launch l0, l1;
-        l0.func = (void *)k_w2v_stats; l0.grid = dim3(1); l0.block = dim3(1024); l0.io = IO_W2V_IN; l0.set(w);
-        l1.func = (void *)k_w2v_conv0; l1.grid = dim3((w.n_frames + 7) / 8); l1.block = dim3(256); l1.io = IO_W2V_IN; l1.set(w);
+        l0.func = (void *)k_w2v_stats; l0.grid = dim3(1, B); l0.block = dim3(1024); l0.io = IO_W2V_IN; l0.set(w);
+        l1.func = (void *)k_w2v_conv0; l1.grid = dim3((w.n_frames + 7) / 8, B); l1.block = dim3(256); l1.io = IO_W2V_IN; l1.set(w);
         L.push_back(std::move(l0));
         L.push_back(std::move(l1));
         for (int i = 0; i < s->hdr.n_ops; i++) {
@@ -1277,16 +1277,21 @@ extern "C" int mf_whisper_features(mf_ctx *ctx, const float *audio, int n_sample
     return forward_common(ctx, s, audio, nullptr, nullptr, out_f32, 1, (cudaStream_t)stream, n_samples, T);
 }
 
-extern "C" int mf_wav2vec2_logits(mf_ctx *ctx, const float *audio, int n_samples, float *out_f32, void *stream) {
+extern "C" int mf_wav2vec2_logits_batch(mf_ctx *ctx, const float *audio, int n_samples, int B, float *out_f32, void *stream) {
     if (!ctx) return MF_E_INVALID;
     Wav2LipState *s = ctx->wav2lip;
     if (!s) return mf_fail(ctx, MF_E_STATE, "mf_wav2vec2_logits: weights not loaded");
     MF_REQUIRE(ctx, is_wav2vec2(s), "the loaded program is not a wav2vec2 program");
     MF_REQUIRE(ctx, audio && out_f32, "mf_wav2vec2_logits: null pointer");
+    MF_REQUIRE(ctx, B >= 1 && B <= s->max_batch, "mf_wav2vec2_logits: batch %d outside [1, %d]", B, s->max_batch);
     MF_REQUIRE(ctx, n_samples == s->w2v_samples, "mf_wav2vec2_logits: the program was packed for windows of %d samples, got %d", s->w2v_samples,
                n_samples);
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
-    return forward_common(ctx, s, audio, nullptr, nullptr, out_f32, 1, (cudaStream_t)stream);
+    return forward_common(ctx, s, audio, nullptr, nullptr, out_f32, B, (cudaStream_t)stream);
+}
+
+extern "C" int mf_wav2vec2_logits(mf_ctx *ctx, const float *audio, int n_samples, float *out_f32, void *stream) {
+    return mf_wav2vec2_logits_batch(ctx, audio, n_samples, 1, out_f32, stream);
 }
 
 // unit-test entry: run the loaded program on an fp32 NHWC tensor written into buffer `in_buf` (all of its channels)

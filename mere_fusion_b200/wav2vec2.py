@@ -12,14 +12,15 @@ from .wav2vec2_pack import XLSR53_CFG, pack_wav2vec2
 
 
 class Wav2Vec2Engine(ConvNet):
-    def __init__(self, state_dict=None, cfg=XLSR53_CFG, n_samples=8960, device=0, blob=None, n_frames=None):
+    def __init__(self, state_dict=None, cfg=XLSR53_CFG, n_samples=8960, device=0, blob=None, n_frames=None, max_batch=1):
+        """max_batch > 1: `logits_batch` runs the windows of several sessions in one pass (one engine per GPU)"""
         self.n_samples, self.vocab = n_samples, cfg["vocab"]
         if blob is None:
             blob, pb = pack_wav2vec2(state_dict, cfg, n_samples)
             self.flops_per_call = pb.flops_per_sample
             n_frames = pb.n_frames
         self.n_frames = n_frames
-        super().__init__(blob, 1, device)
+        super().__init__(blob, max_batch, device)
         self._pin = torch.empty(n_samples, dtype=torch.float32).pin_memory()
         self._dev = torch.empty(n_samples, dtype=torch.float32, device=self.device)
         self._h2d_done = None
@@ -32,6 +33,17 @@ class Wav2Vec2Engine(ConvNet):
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         check(self.ctx.handle, lib().mf_wav2vec2_logits(self.ctx.handle, _ptr(audio), self.n_samples, _ptr(out), ctypes.c_void_p(s.cuda_stream)),
               "mf_wav2vec2_logits")
+        return out
+
+    def logits_batch(self, audio, out=None, stream=None):
+        """audio: cuda fp32 [B, n_samples] (B <= max_batch) -> cuda fp32 [B, n_frames, vocab]"""
+        assert audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous() and audio.dim() == 2 and audio.shape[1] == self.n_samples
+        B = int(audio.shape[0])
+        if out is None:
+            out = torch.empty((B, self.n_frames, self.vocab), dtype=torch.float32, device=self.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        check(self.ctx.handle, lib().mf_wav2vec2_logits_batch(self.ctx.handle, _ptr(audio), self.n_samples, B, _ptr(out),
+                                                              ctypes.c_void_p(s.cuda_stream)), "mf_wav2vec2_logits_batch")
         return out
 
     def feature_fn(self, frame):

@@ -56,3 +56,28 @@ def test_nerfasr_with_the_gpu_acoustic_model():
     out = torch.empty(27, 44, device="cuda")
     bad = lib().mf_wav2vec2_logits(eng.ctx.handle, ctypes.c_void_p(out.data_ptr()), 4000, ctypes.c_void_p(out.data_ptr()), None)
     assert bad == -1 and b"8960" in lib().mf_last_error(eng.ctx.handle)          # wrong window length is refused
+
+
+@pytest.mark.parametrize("name,cfg,seed,B", [("small", W2V_SMALL, 21, 3), ("xlsr53", W2V_XLSR53, 22, 4)])
+def test_batched_windows_match_single_windows(name, cfg, seed, B):
+    """mf_wav2vec2_logits_batch: the windows of B sessions in one pass give each session the logits of its own window (per-window
+    normalisation statistics, no leakage across the batch through the 128-tap positional conv or the attention); window 0 is the
+    golden window"""
+    from mere_fusion_b200._lib import MfError
+    from mere_fusion_b200.wav2vec2 import Wav2Vec2Engine
+    eng = Wav2Vec2Engine(seeded_w2v_state(seed, cfg), cfg, max_batch=B)
+    wins = np.stack([synthetic_speech(8960, seed)] + [synthetic_speech(8960, 50 + i) * (0.5 + i) for i in range(B - 1)])
+    audio = torch.from_numpy(wins).cuda()
+    got = eng.logits_batch(audio).cpu().numpy()
+    assert got.shape == (B, 27, 44)
+    ref0 = G[name + "_logits"]
+    assert _rel(got[0], ref0) < 3e-2 and int((got[0].argmax(1) == ref0.argmax(1)).sum()) >= 25
+    for i in range(B):
+        solo = eng.logits(audio[i]).cpu().numpy()
+        # batch size changes tile shapes / split-K: same operands, another summation order
+        assert _rel(got[i], solo) < 1.5e-2, (i, _rel(got[i], solo))
+        assert int((got[i].argmax(1) == solo.argmax(1)).sum()) >= 25
+    assert _rel(got[1], got[0]) > 0.05                      # the windows really differ
+    assert np.array_equal(eng.logits_batch(audio).cpu().numpy(), got)          # replay: bit-identical
+    with pytest.raises(MfError):
+        eng.logits_batch(torch.zeros(B + 1, 8960, device="cuda"))
