@@ -413,6 +413,113 @@ class ErnerfBatcher:
             r.done.set()
 
 
+class AsrBatcher:
+    """The wav2vec2 acoustic model behind NerfASR.run_step (nerfasr.py:105-143: one 28-chunk window every 8 chunks per session) shared by
+    the ErNeRF sessions of a GPU: `feature_fn(frame)` calls that arrive within `window_ms` run as ONE mf_wav2vec2_logits_batch pass
+    over the 630 MB of weights (Wav2Vec2Engine(max_batch=n)).  `feature_fn` keeps NerfASR's contract: float32[n_samples] host
+    window in, device tensor [T, vocab] out."""
+
+    def __init__(self, engine, window_ms=2.0, threaded=True):
+        import torch
+        self._torch = torch
+        self.engine = engine
+        self.max_batch = engine.max_batch
+        self.device = getattr(engine, "device", None)
+        self.window_s = window_ms * 1e-3
+        self._cuda = self.device is not None and getattr(self.device, "type", "cpu") == "cuda"
+        self._stream = torch.cuda.Stream(self.device) if self._cuda else None
+        self._pending = []
+        self._cv = threading.Condition()
+        self._stop = False
+        self.batches = 0
+        self.windows = 0
+        n = engine.n_samples
+        self._pin = torch.empty((self.max_batch, n), dtype=torch.float32)
+        if self._cuda:
+            self._pin = self._pin.pin_memory()
+        self._dev = torch.empty((self.max_batch, n), dtype=torch.float32, device=self.device) if self._cuda else self._pin
+        self._thread = None
+        if threaded:
+            self._thread = threading.Thread(target=self._loop, name="mf-asr-batcher", daemon=True)
+            self._thread.start()
+
+    def feature_fn(self, frame):
+        req = _Request.__new__(_Request)
+        req.a, req.b, req.out, req.out_f32, req.n = frame, None, None, None, 1
+        req.ready, req.done, req.done_event, req.error = None, threading.Event(), None, None
+        with self._cv:
+            if self._stop:
+                raise RuntimeError("AsrBatcher is shut down")
+            self._pending.append(req)
+            self._cv.notify_all()
+        if self._thread is None:
+            self.flush()
+        req.done.wait()
+        if req.error is not None:
+            raise req.error
+        if self._cuda:
+            self._torch.cuda.current_stream(self.device).wait_event(req.done_event)
+        return req.out
+
+    def flush(self):
+        while True:
+            with self._cv:
+                take, self._pending = self._pending[:self.max_batch], self._pending[self.max_batch:]
+            if not take:
+                return
+            self._run(take)
+
+    def shutdown(self):
+        with self._cv:
+            self._stop = True
+            self._cv.notify_all()
+        if self._thread is not None:
+            self._thread.join(timeout=5.0)
+        self.flush()
+
+    def _loop(self):
+        while True:
+            with self._cv:
+                while not self._pending and not self._stop:
+                    self._cv.wait()
+                if self._stop and not self._pending:
+                    return
+                deadline = time.perf_counter() + self.window_s
+                while len(self._pending) < self.max_batch and not self._stop:
+                    left = deadline - time.perf_counter()
+                    if left <= 0:
+                        break
+                    self._cv.wait(left)
+            self.flush()
+
+    def _run(self, reqs):
+        torch = self._torch
+        try:
+            import numpy as np
+            with (torch.cuda.stream(self._stream) if self._cuda else _null()):
+                if self._cuda:
+                    self._stream.synchronize()               # the pinned staging buffer of the previous pass has been consumed
+                B = len(reqs)
+                for i, r in enumerate(reqs):
+                    self._pin[i].copy_(torch.from_numpy(np.ascontiguousarray(r.a, np.float32)))
+                if self._cuda:
+                    self._dev[:B].copy_(self._pin[:B], non_blocking=True)
+                out = self.engine.logits_batch(self._dev[:B])
+                ev = None
+                if self._cuda:
+                    ev = torch.cuda.Event()
+                    ev.record(self._stream)
+                for i, r in enumerate(reqs):
+                    r.out, r.done_event = out[i], ev
+            self.batches += 1
+            self.windows += len(reqs)
+        except Exception as e:                   # noqa: BLE001 -- handed to every caller of this batch
+            for r in reqs:
+                r.error = e
+        for r in reqs:
+            r.done.set()
+
+
 class SessionScheduler:
     """placement + one SharedEngine per (GPU, head, model key).  `factory(device_index, max_batch)` builds the engine
     the first time a head is used on a GPU (weights: one blob per GPU, NCCL-broadcast by the caller when multi-process)."""

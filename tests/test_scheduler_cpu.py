@@ -188,3 +188,33 @@ def test_scheduler_hands_ernerf_sessions_a_batched_renderer():
     assert FakeRenderer.calls == [[10, 11]] and r0._b.wait(q1) == (11, 2)
     sc.close("n0"), sc.close("n1")
     assert not sc.engines()
+
+
+def test_asr_batcher_coalesces_windows():
+    from mere_fusion_b200.scheduler import AsrBatcher
+
+    class FakeAsr:
+        max_batch, n_samples, device = 4, 64, None
+        calls = []
+
+        def logits_batch(self, audio):
+            FakeAsr.calls.append(int(audio.shape[0]))
+            return audio[:, :6].reshape(audio.shape[0], 3, 2) * 2.0
+
+    b = AsrBatcher(FakeAsr(), window_ms=300.0)
+    outs, gate = {}, threading.Barrier(4)
+
+    def session(i):
+        frame = np.full(64, float(i), np.float32)
+        gate.wait()
+        outs[i] = b.feature_fn(frame)
+
+    th = [threading.Thread(target=session, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join(timeout=30) for t in th]
+    b.shutdown()
+    assert FakeAsr.calls == [4]                                   # one pass for the four sessions' windows
+    for i in range(4):
+        assert outs[i].shape == (3, 2) and float(outs[i][0, 0]) == 2.0 * i
+    b2 = AsrBatcher(FakeAsr(), threaded=False)
+    assert float(b2.feature_fn(np.ones(64, np.float32))[1, 1]) == 2.0 and (b2.batches, b2.windows) == (1, 1)

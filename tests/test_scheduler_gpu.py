@@ -229,3 +229,36 @@ def test_two_nerfreal_sessions_behind_the_batcher():
         for k, (f, r) in enumerate(zip(frames, ref[s])):
             assert np.array_equal(f, r), f"session {s} frame {k}"
     sched.close("n0"), sched.close("n1")
+
+
+def test_asr_batcher_threads_on_the_gpu_engine():
+    """three sessions' NerfASR feature_fn calls through scheduler.AsrBatcher (one mf_wav2vec2_logits_batch pass) return each session
+    the logits of its own window"""
+    from helpers import W2V_SMALL, seeded_w2v_state, synthetic_speech
+    from mere_fusion_b200.scheduler import AsrBatcher
+    from mere_fusion_b200.wav2vec2 import Wav2Vec2Engine
+    eng = Wav2Vec2Engine(seeded_w2v_state(21, W2V_SMALL), W2V_SMALL, max_batch=4)
+    wins = [synthetic_speech(8960, 30 + i) * (1 + i) for i in range(3)]
+    solo = [eng.feature_fn(w).cpu().numpy() for w in wins]
+    b = AsrBatcher(eng, window_ms=200.0)
+    res, errs, gate = {}, [], threading.Barrier(3)
+
+    def session(i):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                gate.wait()
+                out = b.feature_fn(wins[i])
+                torch.cuda.current_stream().synchronize()
+                res[i] = out.cpu().numpy()
+        except Exception as e:                                    # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=session, args=(i,)) for i in range(3)]
+    [t.start() for t in th]
+    [t.join(timeout=120) for t in th]
+    b.shutdown()
+    assert not errs, errs
+    assert b.windows == 3 and b.batches <= 2
+    for i in range(3):
+        rel = float(np.linalg.norm(res[i] - solo[i]) / np.linalg.norm(solo[i]))
+        assert res[i].shape == (27, 44) and rel < 1.5e-2, (i, rel)
