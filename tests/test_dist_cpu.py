@@ -30,7 +30,16 @@ def _worker(rank, world, port, q):
     import struct
     magic, kind, ver, n = struct.unpack("<IIII", t[:16].numpy().tobytes())
     mine = shard(mixed_sessions(64))
-    q.put((rank, int(t.numel()), int(t.sum().item()), magic, kind, [m[0] for m in mine]))
+    # a packed avatar travels the same way: rank 0 packs, every rank slices its copy into views
+    from mere_fusion_b200.avatar_pack import DeviceAvatar, pack_lip_avatar
+    from test_plugin_cpu import _fake_avatar
+    av_blob = pack_lip_avatar(_fake_avatar(n=3)) if rank == 0 else None
+    at = broadcast_bytes(av_blob, src=0)
+    av = DeviceAvatar(at.numpy())
+    views = av.device_tensors("cpu", blob_on_device=at)
+    assert views["frames"].shape == (3, 512, 512, 3) and views["frames"].data_ptr() - at.data_ptr() == av.entries[2][0]
+    av_sum = int(views["frames"].sum().item()) + int(views["faces"].sum().item()) + sum(sum(c) for c in av.coord_list_cycle)
+    q.put((rank, int(t.numel()), int(t.sum().item()), magic, kind, [m[0] for m in mine], av_sum))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,7 +55,8 @@ def test_blob_broadcast_and_sharding_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, n0, s0, m0, k0, h0), (r1, n1, s1, m1, k1, h1) = res
+    (r0, n0, s0, m0, k0, h0, a0), (r1, n1, s1, m1, k1, h1, a1) = res
+    assert a0 == a1 > 0                                  # both ranks see the same avatar frames / faces / boxes
     assert n0 == n1 > 0 and s0 == s1 and m0 == m1 == 0x3242464D and k0 == k1 == 2
     assert len(h0) + len(h1) == 64 and abs(len(h0) - len(h1)) <= 1
     for h in (h0, h1):                                   # every GPU hosts all three heads
