@@ -91,6 +91,18 @@ class _Request:
         self.error = None
 
 
+class _Ticket:
+    """one queued request of ErnerfBatcher / AsrBatcher: `a` = who / what (renderer, audio window), `b` = the frame arguments"""
+    __slots__ = ("a", "b", "out", "ready", "done", "error", "done_event")
+
+    def __init__(self, a, b=None, out=None):
+        self.a, self.b, self.out = a, b, out
+        self.ready = None
+        self.done = threading.Event()
+        self.done_event = None
+        self.error = None
+
+
 class SharedEngine:
     """one conv-net engine (Wav2LipEngine / MuseTalkEngine: `forward(a, b, out=, out_f32=)`, `.max_batch`) shared by
     the same-head sessions of a GPU, with request coalescing.
@@ -324,9 +336,7 @@ class ErnerfBatcher:
 
     def submit(self, renderer, frame, out=None):
         torch = self._torch
-        req = _Request.__new__(_Request)
-        req.a, req.b, req.out, req.out_f32, req.n = renderer, frame, out, None, 1
-        req.ready, req.done, req.done_event, req.error = None, threading.Event(), None, None
+        req = _Ticket(renderer, frame, out)
         if self._cuda:
             req.ready = torch.cuda.Event()
             req.ready.record(torch.cuda.current_stream(self.device))
@@ -444,9 +454,7 @@ class AsrBatcher:
             self._thread.start()
 
     def feature_fn(self, frame):
-        req = _Request.__new__(_Request)
-        req.a, req.b, req.out, req.out_f32, req.n = frame, None, None, None, 1
-        req.ready, req.done, req.done_event, req.error = None, threading.Event(), None, None
+        req = _Ticket(frame)
         with self._cv:
             if self._stop:
                 raise RuntimeError("AsrBatcher is shut down")
