@@ -562,7 +562,9 @@ class SessionScheduler:
         k = (g, head, key)
         with self._lock:
             if k not in self._engines:
-                eng = factory(g, self.batch_size * self.sessions_per_engine)
+                # Wav2Lip is launch-latency bound at 16 frames: room for several sessions' batches in one pass.  MuseTalk fills the GPU
+                # at 16 frames (tensor-bound, ~0.5 GB of activations per frame): its sessions share the weights and take turns
+                eng = factory(g, self.batch_size * (self.sessions_per_engine if head == "wav2lip" else 1))
                 self._engines[k] = SharedEngine(eng, window_ms=self.window_ms, threaded=self.threaded)
             self._refs[k] += 1
             return g, self._engines[k]

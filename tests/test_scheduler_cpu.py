@@ -218,3 +218,15 @@ def test_asr_batcher_coalesces_windows():
         assert outs[i].shape == (3, 2) and float(outs[i][0, 0]) == 2.0 * i
     b2 = AsrBatcher(FakeAsr(), threaded=False)
     assert float(b2.feature_fn(np.ones(64, np.float32))[1, 1]) == 2.0 and (b2.batches, b2.windows) == (1, 1)
+
+
+def test_musetalk_sessions_share_weights_but_not_a_bigger_batch():
+    built = []
+    sc = SessionScheduler(n_gpus=1, sessions_per_engine=4, batch_size=16, threaded=False)
+    g, e0 = sc.open("m0", "musetalk", lambda gpu, mb: built.append(mb) or FakeEngine(mb))
+    g, e1 = sc.open("m1", "musetalk", lambda gpu, mb: built.append(mb) or FakeEngine(mb))
+    assert e0 is e1 and built == [16]
+    ra, rb = e0.submit(*_inputs(16, 1)), e0.submit(*_inputs(16, 2))
+    e0.flush()
+    assert e0.engine.calls == [16, 16]              # two passes of 16, one set of weights
+    sc.shutdown()
