@@ -484,8 +484,29 @@ __device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, const float *e
 
 // enc_x of one sample -> fp16 row of the warp's tile.  ND = number of leading dense levels (the shipped
 // architecture has 4: base 64, 512 desired, 2^14 hash rows); ND < 0 = generic indexing.
+// corner indices and fractions of one level (the first half of grid_level_f32, ernerf_device.cuh)
+template <int CLS>
+__device__ __forceinline__ void grid_level_prep(const GridLevel &lv, float u, float v, uint32_t (&idx)[4], float &pu, float &pv) {
+    pu = fmaf(u, lv.scale, 0.5f); pv = fmaf(v, lv.scale, 0.5f);
+    const float flu = floorf(pu), flv = floorf(pv);
+    const uint32_t gx = (uint32_t)flu, gy = (uint32_t)flv;
+    pu -= (float)gx;
+    pv -= (float)gy;
+    idx[0] = lv.offset + grid_index2c<CLS>(lv, gx, gy);
+    idx[1] = lv.offset + grid_index2c<CLS>(lv, gx + 1, gy);
+    idx[2] = lv.offset + grid_index2c<CLS>(lv, gx, gy + 1);
+    idx[3] = lv.offset + grid_index2c<CLS>(lv, gx + 1, gy + 1);
+}
+
+// enc_x of one sample -> fp16 row of the warp's tile.  ND = number of leading dense levels (the shipped
+// architecture has 4: base 64, 512 desired, 2^14 hash rows); ND < 0 = generic indexing.
+// The 12 levels of a plane are gathered GL at a time: indices of GL levels first, then their 4 * GL loads back to back, then the
+// bilinear sums -- with one level at a time only 4 loads were in flight per thread and every level exposed a full L1 / L2 latency
+// (36 of them per sample; long scoreboard is the kernel's top stall once the barrier wait is gone).  Same arithmetic per level as
+// grid_level_f32 (gridencoder.cu:75-175): bit-identical features.
 template <int ND>
 __device__ __forceinline__ void gather_planes(const HeadParams &p, float x, float y, float z, __half *row) {
+    constexpr int GL = 3;
     const float rb = 1.0f / (2.0f * p.bound);
     const float u[3] = {(x + p.bound) * rb, (y + p.bound) * rb, (z + p.bound) * rb};
 #pragma unroll
@@ -494,11 +515,36 @@ __device__ __forceinline__ void gather_planes(const HeadParams &p, float x, floa
         const float b = (pl == 0) ? u[1] : u[2];
         const float *tab = p.planes + (size_t)pl * p.plane_rows;
         float f[12];
+        if (ND < 0) {
 #pragma unroll
-        for (int l = 0; l < 12; l++) {
-            if (ND < 0) f[l] = grid_level_f32<IDX_ANY>(tab, p.hl.lv[l], a, b);
-            else if (l < ND) f[l] = grid_level_f32<IDX_DENSE>(tab, p.hl.lv[l], a, b);
-            else f[l] = grid_level_f32<IDX_HASH2>(tab, p.hl.lv[l], a, b);
+            for (int l = 0; l < 12; l++) f[l] = grid_level_f32<IDX_ANY>(tab, p.hl.lv[l], a, b);
+        } else if (a < 0.f || a > 1.f || b < 0.f || b > 1.f) {   // grid_level_f32's bounds test, once per plane
+#pragma unroll
+            for (int l = 0; l < 12; l++) f[l] = 0.f;
+        } else {
+#pragma unroll
+            for (int l0 = 0; l0 < 12; l0 += GL) {
+                uint32_t idx[GL][4];
+                float pu[GL], pv[GL], v[GL][4];
+#pragma unroll
+                for (int j = 0; j < GL; j++) {
+                    if (l0 + j < ND) grid_level_prep<IDX_DENSE>(p.hl.lv[l0 + j], a, b, idx[j], pu[j], pv[j]);
+                    else grid_level_prep<IDX_HASH2>(p.hl.lv[l0 + j], a, b, idx[j], pu[j], pv[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < GL; j++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) v[j][c] = __ldg(tab + idx[j][c]);
+#pragma unroll
+                for (int j = 0; j < GL; j++) {
+                    float r = 0.f;
+                    r = fmaf((1 - pu[j]) * (1 - pv[j]), v[j][0], r);
+                    r = fmaf(pu[j] * (1 - pv[j]), v[j][1], r);
+                    r = fmaf((1 - pu[j]) * pv[j], v[j][2], r);
+                    r = fmaf(pu[j] * pv[j], v[j][3], r);
+                    f[l0 + j] = r;
+                }
+            }
         }
 #pragma unroll
         for (int l = 0; l < 6; l++)
