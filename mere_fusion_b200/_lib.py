@@ -3,7 +3,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmf_b200.so")
+LIB_PATH = os.environ.get("MF_B200_LIB") or os.path.join(HERE, "libmf_b200.so")   # MF_B200_LIB: an experiment build of the same library
 
 MF_ERNERF_HEAD_LEVELS = 12
 MF_ERNERF_TORSO_LEVELS = 16

@@ -504,9 +504,12 @@ __device__ __forceinline__ void grid_level_prep(const GridLevel &lv, float u, fl
 // bilinear sums -- with one level at a time only 4 loads were in flight per thread and every level exposed a full L1 / L2 latency
 // (36 of them per sample; long scoreboard is the kernel's top stall once the barrier wait is gone).  Same arithmetic per level as
 // grid_level_f32 (gridencoder.cu:75-175): bit-identical features.
+#ifndef ER_GATHER_LEVELS
+#define ER_GATHER_LEVELS 3   /* levels gathered together: 3 measured; must divide 12 */
+#endif
 template <int ND>
 __device__ __forceinline__ void gather_planes(const HeadParams &p, float x, float y, float z, __half *row) {
-    constexpr int GL = 3;
+    constexpr int GL = ER_GATHER_LEVELS;
     const float rb = 1.0f / (2.0f * p.bound);
     const float u[3] = {(x + p.bound) * rb, (y + p.bound) * rb, (z + p.bound) * rb};
 #pragma unroll
