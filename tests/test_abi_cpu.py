@@ -51,3 +51,22 @@ def test_product_package_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "oracle/" in txt and f.endswith(".py") and "import" in txt.split("oracle/")[0][-40:]:
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_binding_argument_counts_match_the_header():
+    """every bound entry point takes as many arguments as include/mf_b200.h declares (a drifted ctypes prototype corrupts the
+    call silently)"""
+    from mere_fusion_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "mf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decl = {}
+    for m in re.finditer(r"\b(?:int|void|const char \*)\s*\*?\s*(mf_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        decl[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    assert len(decl) >= 30 and "mf_ernerf_render_batch" in decl and "mf_wav2vec2_logits_batch" in decl
+    L = _lib.lib()
+    bad = [(n, k, len(getattr(L, n).argtypes)) for n, k in decl.items()
+           if getattr(L, n).argtypes is not None and len(getattr(L, n).argtypes) != k]
+    assert not bad, bad
+    unbound = [n for n in decl if getattr(L, n).argtypes is None and decl[n] > 0]
+    assert not unbound, f"declared but without a ctypes prototype: {unbound}"
