@@ -103,6 +103,51 @@ def oracle_sample_fps(n_side, frames=1):
     return (n_side * n_side / RAYS) / t, t, os.cpu_count()
 
 
+def config1_cpu_plumbing(seconds=10.0):
+    """BASELINE configs[0] / SURVEY 8(d) config 1: the Wav2Lip 96x96 plugin path on the HOST only -- LipASR windows + numpy mel, the fp32
+    restatement of the reference generator (oracle, all host cores), cv2 resize + paste, fake tracks -- for a 10 s clip (500 chunks ->
+    250 frames).  A reported CPU baseline (kind "port": librosa / PyAV are absent, the mirrors of lipreal.py / lipasr.py stand in); it
+    never touches the GPU library."""
+    import threading
+    import torch
+    from helpers import seeded_wav2lip_state, synthetic_speech
+    from oracle import wav2lip_oracle as O
+    from test_plugin_cpu import FakeTrack, _fake_avatar, make_opt
+    from mere_fusion_b200.plugin.lipreal import LipReal, mirror_index
+    torch.set_num_threads(os.cpu_count())
+    sd = seeded_wav2lip_state(2)
+
+    class HostLipReal(LipReal):
+        def infer_batch(self, mel_batch, index):
+            n = len(self.face_list_cycle)
+            faces = np.stack([self.face_list_cycle[mirror_index(n, index + i)] for i in range(self.batch_size)])
+            mel = np.asarray(mel_batch, np.float32).reshape(self.batch_size, 1, 80, 16)
+            pred, _ = O.infer(sd, mel, faces)
+            return [pred[i] * 255. for i in range(self.batch_size)]          # lipreal.py:126
+
+    real = HostLipReal(make_opt(), engine=object(), avatar=_fake_avatar(), paste="cpu", mel="host")
+    n_chunks = int(seconds * 50)
+    wav = synthetic_speech(n_chunks * 320, 0)
+    for i in range(n_chunks):
+        real.put_audio_frame(wav[i * 320:(i + 1) * 320])
+    quit_event = threading.Event()
+    vt, at = FakeTrack(), FakeTrack()
+    want = n_chunks // 2
+    t0 = time.perf_counter()
+    th = threading.Thread(target=real.render, args=(quit_event, None, at, vt), daemon=True)
+    th.start()
+    while len(vt._queue.items) < want and time.perf_counter() - t0 < 300:
+        time.sleep(0.005)
+    dt = time.perf_counter() - t0
+    quit_event.set()
+    th.join(timeout=30)
+    nv, na = len(vt._queue.items), len(at._queue.items)
+    return {"value": want / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{seconds:.0f} s clip ({n_chunks} chunks -> {want} frames at 512x512) through LipReal.render on the host: numpy mel, fp32 oracle of the "
+                      f"reference generator, cv2 paste, fake tracks; {dt:.2f} s, {nv} video / {na} audio frames emitted "
+                      "(BASELINE configs[0]; the fake video track never fills, so no back-pressure sleep is taken)"}
+
+
 def run_reference(args):
     """--impl reference: the reference has NO CPU renderer for ErNeRF (renderer.py:664 always
     dispatches to run_cuda), so the CPU arm is the oracle port (kind "port") on all host cores,
@@ -878,6 +923,7 @@ def main():
             dt = time.perf_counter() - t0
             heads["wav2lip"]["cpu_baseline"] = {"value": 16 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                                 "sample": f"one batch of 16 frames through the fp32 PyTorch oracle (pinned on the reference nn.Module's golden output), {dt:.2f} s, network only (no paste)"}
+            heads["wav2lip"]["cpu_plumbing_config1"] = config1_cpu_plumbing()
         if "wav2lip_256" in heads:
             _m, _f = _wi(4, S=256)
             _sd = _sw(2, face_hw=256)
