@@ -923,7 +923,10 @@ def main():
             dt = time.perf_counter() - t0
             heads["wav2lip"]["cpu_baseline"] = {"value": 16 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                                 "sample": f"one batch of 16 frames through the fp32 PyTorch oracle (pinned on the reference nn.Module's golden output), {dt:.2f} s, network only (no paste)"}
-            heads["wav2lip"]["cpu_plumbing_config1"] = config1_cpu_plumbing()
+            try:
+                heads["wav2lip"]["cpu_plumbing_config1"] = config1_cpu_plumbing()
+            except Exception as e:                       # noqa: BLE001 -- a reported side baseline must not cost the bench line
+                heads["wav2lip"]["cpu_plumbing_config1"] = {"error": repr(e)}
         if "wav2lip_256" in heads:
             _m, _f = _wi(4, S=256)
             _sd = _sw(2, face_hw=256)
