@@ -27,42 +27,42 @@ except Exception:                                         # noqa: BLE001 (any mi
         def pause_talk(self):
             pass
 
+    def _numbered_images(directory):
+        """the images of a directory in the order of their integer file names"""
+        import cv2
+        paths = glob.glob(os.path.join(directory, "*.[jpJP][pnPN]*[gG]"))
+        return [cv2.imread(p) for p in sorted(paths, key=lambda p: int(os.path.splitext(os.path.basename(p))[0]))]
+
     class BaseReal:
+        """stand-in with the attributes the plugin classes and the orchestration read (`opt, tts, curr_state, recording, recordq_*,
+        custom_*` dictionaries keyed by audiotype) and the pure-logic methods of basereal.py:59-75,133-154"""
+
         def __init__(self, opt):
             self.opt = opt
             self.sample_rate = 16000
             self.chunk = self.sample_rate // opt.fps
             self.tts = _NoTTS()
             self.recording = False
-            self.recordq_video = Queue()
-            self.recordq_audio = Queue()
-            self.curr_state = 0
-            self.custom_img_cycle = {}
-            self.custom_audio_cycle = {}
-            self.custom_audio_index = {}
-            self.custom_index = {}
-            self.custom_opt = {}
-            self._loadcustom()
+            self.recordq_video, self.recordq_audio = Queue(), Queue()
+            self.curr_state = 0                      # 0 speech / 1 silence / > 1: a custom idle clip is playing
+            self.custom_img_cycle, self.custom_audio_cycle = {}, {}
+            self.custom_audio_index, self.custom_index, self.custom_opt = {}, {}, {}
+            for item in getattr(opt, "customopt", None) or ():
+                self._add_custom(item)
 
-        def _loadcustom(self):
-            """basereal.py:59-68"""
-            for item in getattr(self.opt, "customopt", []) or []:
-                import cv2
-                import soundfile as sf
-                lst = glob.glob(os.path.join(item["imgpath"], "*.[jpJP][pnPN]*[gG]"))
-                lst = sorted(lst, key=lambda x: int(os.path.splitext(os.path.basename(x))[0]))
-                self.custom_img_cycle[item["audiotype"]] = [cv2.imread(p) for p in lst]
-                self.custom_audio_cycle[item["audiotype"]], _ = sf.read(item["audiopath"], dtype="float32")
-                self.custom_audio_index[item["audiotype"]] = 0
-                self.custom_index[item["audiotype"]] = 0
-                self.custom_opt[item["audiotype"]] = item
+        def _add_custom(self, item):
+            """one entry of the custom-video config: frames from imgpath, mono float32 audio from audiopath, both rewound"""
+            import soundfile as sf
+            kind = item["audiotype"]
+            self.custom_img_cycle[kind] = _numbered_images(item["imgpath"])
+            self.custom_audio_cycle[kind] = sf.read(item["audiopath"], dtype="float32")[0]
+            self.custom_audio_index[kind] = self.custom_index[kind] = 0
+            self.custom_opt[kind] = item
 
         def init_customindex(self):
             self.curr_state = 0
-            for key in self.custom_audio_index:
-                self.custom_audio_index[key] = 0
-            for key in self.custom_index:
-                self.custom_index[key] = 0
+            for positions in (self.custom_audio_index, self.custom_index):
+                positions.update(dict.fromkeys(positions, 0))
 
         def start_recording(self, path):
             raise RuntimeError("recording needs PyAV and the reference BaseReal (basereal.py:77-131)")
@@ -71,20 +71,19 @@ except Exception:                                         # noqa: BLE001 (any mi
             self.recording = False
 
         def mirror_index(self, size, index):
-            turn = index // size
-            res = index % size
-            return res if turn % 2 == 0 else size - res - 1
+            """ping-pong over `size` items: 0 .. size-1, size-1 .. 0, 0 .. (basereal.py:133-139)"""
+            lap, pos = divmod(index, size)
+            return pos if lap % 2 == 0 else size - 1 - pos
 
         def get_audio_stream(self, audiotype):
-            idx = self.custom_audio_index[audiotype]
-            stream = self.custom_audio_cycle[audiotype][idx:idx + self.chunk]
-            self.custom_audio_index[audiotype] += self.chunk
-            if self.custom_audio_index[audiotype] >= self.custom_audio_cycle[audiotype].shape[0]:
+            """the next chunk of the custom clip; at its end the state falls back to silence"""
+            clip, at = self.custom_audio_cycle[audiotype], self.custom_audio_index[audiotype]
+            self.custom_audio_index[audiotype] = at + self.chunk
+            if at + self.chunk >= clip.shape[0]:
                 self.curr_state = 1
-            return stream
+            return clip[at:at + self.chunk]
 
         def set_curr_state(self, audiotype, reinit):
             self.curr_state = audiotype
             if reinit:
-                self.custom_audio_index[audiotype] = 0
-                self.custom_index[audiotype] = 0
+                self.custom_audio_index[audiotype] = self.custom_index[audiotype] = 0

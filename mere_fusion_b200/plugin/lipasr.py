@@ -1,42 +1,34 @@
-"""LipASR -- mirror of /root/reference/lipasr.py:12-37: 2*batch chunks per step, mel over the whole
-l + 2B + r window, B mel chunks of [80, 16]."""
-import numpy as np
-
+"""LipASR -- Wav2Lip's audio features (/root/reference/lipasr.py:12-37): every step takes 2 * batch chunks, computes the mel of the
+whole l + 2B + r window and hands the inference loop B slices of [80, 16]."""
 from .. import audio_mel
 from .baseasr import BaseASR
+
+MEL_COLS_PER_CHUNK = 80 / 50          # 80 mel frames per second at 50 chunks per second
+MEL_STEP = 16                         # columns per video frame (wav2lip hparams: syncnet_mel_step_size)
+
+
+def mel_chunk_starts(n_frames, left_size, right_size, fps, n_cols):
+    """first mel column of each of the (n_frames - l - r) / 2 video frames of a window: the look-behind chunks are skipped, a video
+    frame advances 160 / fps columns, and a slice that would run past the end is moved back to the last MEL_STEP columns"""
+    n = max(0, -(-(n_frames - left_size - right_size) // 2))
+    first, step = max(0, left_size * MEL_COLS_PER_CHUNK), 80. * 2 / fps
+    return [min(int(first + i * step), n_cols - MEL_STEP) for i in range(n)]
+
+
+def mel_chunks(mel, n_frames, left_size, right_size, fps):
+    return [mel[:, s:s + MEL_STEP] for s in mel_chunk_starts(n_frames, left_size, right_size, fps, mel.shape[1])]
 
 
 class LipASR(BaseASR):
     def run_step(self):
-        for _ in range(self.batch_size * 2):
-            frame, type = self.get_audio_frame()
-            self.frames.append(frame)
-            self.output_queue.put((frame, type))
-        if len(self.frames) <= self.stride_left_size + self.stride_right_size:
+        self._pull(2 * self.batch_size)
+        wave = self._window()
+        if wave is None:
             return
-        inputs = np.concatenate(self.frames)
-        fe = getattr(self.parent, "mel_front_end", None)
-        if fe is not None:
-            # mel + chunk slicing on the GPU: a cuda fp32 [B,1,80,16] tensor goes through feat_queue instead of B numpy chunks
-            self.feat_queue.put(fe.chunks(inputs, len(self.frames), self.stride_left_size, self.stride_right_size, self.fps))
+        front_end = getattr(self.parent, "mel_front_end", None)
+        if front_end is not None:      # mel + slicing on the GPU: one cuda fp32 [B, 1, 80, 16] tensor instead of B numpy slices
+            feats = front_end.chunks(wave, len(self.frames), self.stride_left_size, self.stride_right_size, self.fps)
         else:
-            mel = audio_mel.melspectrogram(inputs)
-            self.feat_queue.put(mel_chunks(mel, len(self.frames), self.stride_left_size, self.stride_right_size, self.fps))
-        self.frames = self.frames[-(self.stride_left_size + self.stride_right_size):]
-
-
-def mel_chunks(mel, n_frames, left_size, right_size, fps):
-    """lipasr.py:24-35: chunk i starts at int(left*80/50 + i * 160/fps), 16 columns, clamped to the tail"""
-    left = max(0, left_size * 80 / 50)
-    mel_idx_multiplier = 80. * 2 / fps
-    mel_step_size = 16
-    i = 0
-    chunks = []
-    while i < (n_frames - left_size - right_size) / 2:
-        start_idx = int(left + i * mel_idx_multiplier)
-        if start_idx + mel_step_size > len(mel[0]):
-            chunks.append(mel[:, len(mel[0]) - mel_step_size:])
-        else:
-            chunks.append(mel[:, start_idx: start_idx + mel_step_size])
-        i += 1
-    return chunks
+            feats = mel_chunks(audio_mel.melspectrogram(wave), len(self.frames), self.stride_left_size, self.stride_right_size, self.fps)
+        self.feat_queue.put(feats)
+        self._keep_context()

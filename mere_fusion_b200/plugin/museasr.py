@@ -1,7 +1,6 @@
-"""MuseASR -- mirror of /root/reference/museasr.py:10-29: 2 * batch chunks per step, Whisper features over the whole
-l + 2B + r window (one mf_whisper_features call on the GPU), B chunks of [50, 384] starting at video index l / 2."""
-import numpy as np
-
+"""MuseASR -- MuseTalk's audio features (/root/reference/museasr.py:10-29): every step takes 2 * batch chunks, runs Whisper over the
+whole l + 2B + r window (one mf_whisper_features call) and hands the inference loop B chunks of [50, 384]; video frame i of the
+batch is centred l / 2 frames into the window."""
 from .baseasr import BaseASR
 
 
@@ -9,23 +8,18 @@ class MuseASR(BaseASR):
     def __init__(self, opt, parent, audio_processor):
         super().__init__(opt, parent)
         self.audio_processor = audio_processor
-        self.device_chunks = True
+        self.device_chunks = True          # keep features and the [B, 50, 384] gather on the GPU when the processor can
 
     def run_step(self):
-        for _ in range(self.batch_size * 2):
-            audio_frame, type = self.get_audio_frame()
-            self.frames.append(audio_frame)
-            self.output_queue.put((audio_frame, type))
-        if len(self.frames) <= self.stride_left_size + self.stride_right_size:
+        self._pull(2 * self.batch_size)
+        wave = self._window()
+        if wave is None:
             return
-        inputs = np.concatenate(self.frames)
-        if self.device_chunks and hasattr(self.audio_processor, "audio2chunks_device"):
-            # features and the [B, 50, 384] chunk gather stay on the GPU (same rows as feature2chunks; tests compare the two)
-            whisper_chunks = self.audio_processor.audio2chunks_device(inputs, fps=self.fps / 2, batch_size=self.batch_size,
-                                                                      start=self.stride_left_size / 2)
+        ap = self.audio_processor
+        where = dict(fps=self.fps / 2, batch_size=self.batch_size, start=self.stride_left_size / 2)
+        if self.device_chunks and hasattr(ap, "audio2chunks_device"):
+            chunks = ap.audio2chunks_device(wave, **where)        # same rows as feature2chunks (tests compare the two)
         else:
-            whisper_feature = self.audio_processor.audio2feat(inputs)
-            whisper_chunks = self.audio_processor.feature2chunks(feature_array=whisper_feature, fps=self.fps / 2,
-                                                                 batch_size=self.batch_size, start=self.stride_left_size / 2)
-        self.feat_queue.put(whisper_chunks)
-        self.frames = self.frames[-(self.stride_left_size + self.stride_right_size):]
+            chunks = ap.feature2chunks(feature_array=ap.audio2feat(wave), **where)
+        self.feat_queue.put(chunks)
+        self._keep_context()

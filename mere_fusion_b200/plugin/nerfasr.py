@@ -6,8 +6,6 @@ The acoustic model (a 315 M-parameter HF wav2vec2 CTC head, nerfasr.py:40-45,128
 opt.asr_model is loaded through transformers (weights only) and run on the sm_100a engine (mere_fusion_b200.wav2vec2:
 mf_wav2vec2_logits); architectures outside the XLSR-53 wav2vec2 family (HuBERT, deepspeech) are refused, not emulated.
 """
-import queue
-
 import numpy as np
 
 from .baseasr import BaseASR
@@ -26,92 +24,68 @@ def _gpu_feature_fn(opt, device):
     return engine.feature_fn
 
 
+AUDIO_DIMS = (("esperanto", 44), ("deepspeech", 29), ("hubert", 1024))       # by acoustic-model family; anything else: 32
+
+
 class NerfASR(BaseASR):
+    """One chunk per step; every `m` chunks the (l + m + r)-chunk window goes through the acoustic model and its middle rows land in a
+    ring of 4 * m logit rows; `get_next_feat` reads a 16-row window of the ring (advancing 2 rows = one video frame) and, with
+    attention, stacks the last 8 of them: [8, audio_dim, 16]."""
+    poll_timeout = None                # never wait for audio: the render loop paces itself (nerfasr.py:60-73)
+    RING_SEGMENTS = 4
+    WINDOW_ROWS = 16
+
     def __init__(self, opt, parent, feature_fn=None, device=None):
         super().__init__(opt, parent)
         import torch
         self.device = device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu")
-        if "esperanto" in self.opt.asr_model:
-            self.audio_dim = 44
-        elif "deepspeech" in self.opt.asr_model:
-            self.audio_dim = 29
-        elif "hubert" in self.opt.asr_model:
-            self.audio_dim = 1024
-        else:
-            self.audio_dim = 32
+        self.audio_dim = next((d for key, d in AUDIO_DIMS if key in self.opt.asr_model), 32)
         self.context_size = opt.m
-        self.stride_left_size = opt.l
-        self.stride_right_size = opt.r
-        if self.stride_left_size > 0:                                   # nerfasr.py:35-36
-            self.frames.extend([np.zeros(self.chunk, dtype=np.float32)] * self.stride_left_size)
+        self.frames.extend(np.zeros(self.chunk, dtype=np.float32) for _ in range(max(0, self.stride_left_size)))   # left padding
         self.feature_fn = feature_fn if feature_fn is not None else _gpu_feature_fn(opt, self.device)
-        self.feat_buffer_size = 4
+        self.feat_buffer_size = self.RING_SEGMENTS
         self.feat_buffer_idx = 0
-        self.feat_queue = torch.zeros(self.feat_buffer_size * self.context_size, self.audio_dim, dtype=torch.float32,
-                                      device=self.device)
-        self.front = self.feat_buffer_size * self.context_size - 8
-        self.tail = 8
-        self.att_feats = [torch.zeros(self.audio_dim, 16, dtype=torch.float32, device=self.device)] * 4
-        self.warm_up_steps = self.context_size + self.stride_left_size + self.stride_right_size
+        rows = self.feat_buffer_size * self.context_size
+        self.feat_queue = torch.zeros(rows, self.audio_dim, dtype=torch.float32, device=self.device)
+        self.front, self.tail = rows - self.WINDOW_ROWS // 2, self.WINDOW_ROWS // 2      # the window straddles the ring's seam at start
+        self.att_feats = [torch.zeros(self.audio_dim, self.WINDOW_ROWS, dtype=torch.float32, device=self.device)] * 4
+        self.warm_up_steps = self.context_size + self._context()
 
-    def get_audio_frame(self):
-        """nerfasr.py:60-73: non-blocking variant"""
-        try:
-            frame = self.queue.get(block=False)
-            type = 0
-        except queue.Empty:
-            if self.parent and self.parent.curr_state > 1:
-                frame = self.parent.get_audio_stream(self.parent.curr_state)
-                type = self.parent.curr_state
-            else:
-                frame = np.zeros(self.chunk, dtype=np.float32)
-                type = 1
-        return frame, type
-
-    def _window(self):
+    def _ring_window(self):
+        """rows [front, tail) of the ring (wrapping), transposed to [audio_dim, 16]; then both ends move on by one video frame"""
         import torch
-        if self.front < self.tail:
-            feat = self.feat_queue[self.front:self.tail]
-        else:
-            feat = torch.cat([self.feat_queue[self.front:], self.feat_queue[:self.tail]], dim=0)
-        self.front = (self.front + 2) % self.feat_queue.shape[0]
-        self.tail = (self.tail + 2) % self.feat_queue.shape[0]
-        return feat
+        ring, n = self.feat_queue, self.feat_queue.shape[0]
+        rows = ring[self.front:self.tail] if self.front < self.tail else torch.cat((ring[self.front:], ring[:self.tail]))
+        self.front, self.tail = (self.front + 2) % n, (self.tail + 2) % n
+        return rows.permute(1, 0)
 
     def get_next_feat(self):
-        """nerfasr.py:75-103 -> [8, audio_dim, 16] (att > 0) or [1, audio_dim, 16]"""
         import torch
-        if self.opt.att > 0:
-            while len(self.att_feats) < 8:
-                self.att_feats.append(self._window().permute(1, 0))
-            att_feat = torch.stack(self.att_feats, dim=0)
-            self.att_feats = self.att_feats[1:]
-        else:
-            att_feat = self._window().permute(1, 0).unsqueeze(0)
-        return att_feat
+        if self.opt.att <= 0:
+            return self._ring_window().unsqueeze(0)
+        while len(self.att_feats) < 8:
+            self.att_feats.append(self._ring_window())
+        stacked = torch.stack(self.att_feats, dim=0)
+        del self.att_feats[0]
+        return stacked
 
     def run_step(self):
-        """nerfasr.py:105-124"""
-        frame, type = self.get_audio_frame()
-        self.frames.append(frame)
-        self.output_queue.put((frame, type))
-        if len(self.frames) < self.stride_left_size + self.context_size + self.stride_right_size:
+        self._pull(1)
+        wave = self._window(at_least=self._context() + self.context_size)
+        if wave is None:
             return
-        inputs = np.concatenate(self.frames)
-        self.frames = self.frames[-(self.stride_left_size + self.stride_right_size):]
-        feats = self._frame_to_text(inputs)
-        start = self.feat_buffer_idx * self.context_size
-        end = start + feats.shape[0]
-        self.feat_queue[start:end] = feats
+        self._keep_context()
+        rows = self._middle_logits(wave)
+        at = self.feat_buffer_idx * self.context_size
+        self.feat_queue[at:at + rows.shape[0]] = rows
         self.feat_buffer_idx = (self.feat_buffer_idx + 1) % self.feat_buffer_size
 
-    def _frame_to_text(self, frame):
-        """nerfasr.py:128-143: logits of the window, left/right stride rows cut"""
+    def _middle_logits(self, wave):
+        """logits of the window without its look-behind rows and all but one of its look-ahead rows (nerfasr.py:139-142)"""
         import torch
-        logits = torch.as_tensor(self.feature_fn(frame), dtype=torch.float32, device=self.device)
-        left = max(0, self.stride_left_size)
-        right = min(logits.shape[0], logits.shape[0] - self.stride_right_size + 1)
-        return logits[left:right]
+        logits = torch.as_tensor(self.feature_fn(wave), dtype=torch.float32, device=self.device)
+        T = logits.shape[0]
+        return logits[max(0, self.stride_left_size):min(T, T - self.stride_right_size + 1)]
 
     def warm_up(self):
         for _ in range(self.warm_up_steps):
