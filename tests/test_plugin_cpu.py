@@ -385,3 +385,30 @@ def test_mel_front_end_against_independent_librosa_compatible_implementation():
     mel_ref = 20 * np.log10(np.maximum(np.exp(-100 / 20 * np.log(10)), fb.T @ S)) - 20
     mel_ref = np.clip(8.0 * ((mel_ref + 100) / 100) - 4.0, -4.0, 4.0)
     assert np.abs(audio_mel.melspectrogram(wav) - mel_ref).max() < 1e-4
+
+
+def test_mel_chunk_starts_agree_between_host_and_gpu_front_ends():
+    """the host slicing (plugin.lipasr.mel_chunk_starts) and the start columns handed to mf_wav2lip_mel_chunks
+    (wav2lip.MelFrontEnd.chunk_starts) are the same integers, and both equal the loop of lipasr.py:24-35 written out"""
+    from mere_fusion_b200.plugin.lipasr import mel_chunk_starts
+    from mere_fusion_b200.wav2lip import MelFrontEnd
+
+    def reference_loop(n_frames, l, r, fps, n_cols):
+        left = max(0, l * 80 / 50)
+        mult = 80. * 2 / fps
+        out, i = [], 0
+        while i < (n_frames - l - r) / 2:
+            s = int(left + i * mult)
+            out.append(n_cols - 16 if s + 16 > n_cols else s)
+            i += 1
+        return out
+
+    for fps in (50, 25, 40):
+        for l, r in ((10, 10), (0, 0), (3, 7)):
+            for B in (1, 4, 16):
+                n_frames = l + 2 * B + r
+                for n_cols in (n_frames * 320 // 200 + 1, 40, 17):
+                    want = reference_loop(n_frames, l, r, fps, n_cols)
+                    assert mel_chunk_starts(n_frames, l, r, fps, n_cols) == want
+                    assert MelFrontEnd.chunk_starts(n_frames, l, r, fps, n_cols).tolist() == want
+    assert mel_chunk_starts(15, 10, 10, 50, 80) == []          # not more than the context: no video frame yet
