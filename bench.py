@@ -184,6 +184,207 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def reference_cuda_leg(dev, n_frames=24, warmup=4):
+    """SURVEY 8(d) config 4 baseline (2), "the number to beat": the REFERENCE'S OWN CUDA render on this same GPU -- the unmodified
+    reference Python (oracle/_ref/py, staged by oracle/build_ref.py) + the reference's own compiled kernels (oracle/_ref/*.so),
+    Trainer.test_gui_with_data (utils.py:1191-1223) -> (image*255).astype(u8) (nerfreal.py:109-110), same checkpoint / poses /
+    audio windows / 512x512 as our arm.  Timed the way the reference runs it: one frame per call, host clock around the call (the
+    call itself ends in .cpu().numpy(), i.e. it synchronises), plus CUDA events for the device-side share.  A baseline leg: it
+    may import the reference; nothing of it is on the product path."""
+    import torch
+    import ref_ernerf
+    from helpers import ernerf_inputs
+    if not ref_ernerf.render_available():
+        return {"unavailable": "oracle/_ref (reference kernels + staged reference python) not built"}
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = ref_ernerf.ReferenceErnerf(H=H, W=W, device=str(dev))
+    ins = [ernerf_inputs(f % 290, H, W) for f in range(n_frames + warmup)]
+    host, devt = [], []
+    for k, (pose, intr, auds, eye) in enumerate(ins):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a.record()
+        img = ref.render(k % 290, auds)
+        u8 = (img * 255).astype(np.uint8)
+        b.record()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        if k >= warmup:
+            host.append(t1 - t0)
+            devt.append(a.elapsed_time(b) * 1e-3)
+    assert u8.shape == (H, W, 3)
+    t = float(np.median(host))
+    return {"value": 1.0 / t, "unit": "frames/s", "ms_per_frame": t * 1e3, "ms_per_frame_mean": float(np.mean(host)) * 1e3,
+            "ms_per_frame_cuda_events": float(np.median(devt)) * 1e3, "frames": n_frames, "kind": "reference",
+            "what": "unmodified reference NeRFNetwork + Trainer.test_gui_with_data + its own CUDA extensions compiled for sm_100 "
+                    "(oracle/_ref), fp16 autocast, 512x512, same checkpoint / poses / audio windows; host buffers in (auds) and "
+                    "out (u8 frame), median of per-frame host times (the reference synchronises every frame)"}
+
+
+def _ref_py():
+    p = os.path.join(ROOT, "oracle", "_ref", "py")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    return p
+
+
+def _event_ms(fn, K, warm, flush):
+    """median device time of fn() over K calls (CUDA events on the current stream, L2 flushed outside the events)"""
+    import torch
+    for _ in range(warm):
+        fn()
+    ms = []
+    for k in range(K):
+        flush.fill_(k & 0xff)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return float(np.median(ms))
+
+
+def torch_gpu_wav2lip(dev, flush, B=16):
+    """SURVEY 2b "cuDNN/cuBLAS on B200 are the bar to beat for the dense heads": the REFERENCE's own Wav2Lip nn.Module
+    (wav2lip/models/wav2lip.py:87-125, staged unmodified in oracle/_ref/py) on this same GPU, same seeded weights / inputs / batch.
+    (a) fp32 exactly as lipreal.py:108-126 runs it (model.to(device), no autocast), (b) the strongest library setting: bf16,
+    channels_last, cudnn.benchmark.  net_ms = network only (inputs resident, CUDA events); e2e = the reference's own batch loop:
+    numpy batch build -> H2D -> net -> .cpu().numpy().transpose * 255 -> cv2 resize + paste of 16 frames (lipreal.py:207-214)."""
+    import cv2
+    import torch
+    from helpers import seeded_wav2lip_state, wav2lip_inputs
+    if not os.path.isdir(os.path.join(_ref_py(), "wav2lip", "models")):
+        return {"unavailable": "oracle/_ref/py/wav2lip/models not staged"}
+    from wav2lip.models import Wav2Lip
+    model = Wav2Lip().eval()
+    model.load_state_dict(seeded_wav2lip_state(2), strict=True)
+    model = model.to(dev)
+    mel_np, faces = wav2lip_inputs(B)
+
+    def build_batch():                                  # lipreal.py:108-116
+        img = faces.copy()
+        masked = img.copy()
+        masked[:, img.shape[1] // 2:] = 0
+        x = np.concatenate((masked, img), axis=3) / 255.
+        return torch.FloatTensor(np.transpose(x, (0, 3, 1, 2))), torch.FloatTensor(mel_np)
+
+    x_h, mel_h = build_batch()
+    x32, mel32 = x_h.to(dev), mel_h.to(dev)
+    out = {}
+    with torch.no_grad():
+        out["fp32_net_ms"] = _event_ms(lambda: model(mel32, x32), 20, 5, flush)
+        rng = np.random.default_rng(1)
+        full = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(B)]
+
+        def e2e():
+            x, m = build_batch()
+            pred = model(m.to(dev), x.to(dev))
+            pred = pred.cpu().numpy().transpose(0, 2, 3, 1) * 255.
+            for i in range(B):                          # lipreal.py:207-214 (process_frames; a second thread in the reference)
+                f = full[i].copy()
+                f[176:368, 160:352] = cv2.resize(pred[i].astype(np.uint8), (192, 192))
+        for _ in range(3):
+            e2e()
+        ts = []
+        for _ in range(10):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e()
+            ts.append(time.perf_counter() - t0)
+        out["fp32_e2e_ms"] = float(np.median(ts)) * 1e3
+        prev = torch.backends.cudnn.benchmark
+        torch.backends.cudnn.benchmark = True
+        m16 = model.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        x16 = x32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        mel16 = mel32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        out["bf16_channels_last_net_ms"] = _event_ms(lambda: m16(mel16, x16), 20, 8, flush)
+        g = torch.cuda.CUDAGraph()                      # the best a PyTorch user can do about launch latency
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                m16(mel16, x16)
+        torch.cuda.current_stream().wait_stream(s)
+        try:
+            with torch.cuda.graph(g):
+                m16(mel16, x16)
+            out["bf16_channels_last_cudagraph_net_ms"] = _event_ms(g.replay, 20, 3, flush)
+        except Exception as e:                          # noqa: BLE001
+            out["bf16_channels_last_cudagraph_net_ms"] = None
+            out["cudagraph_error"] = repr(e)[:200]
+        torch.backends.cudnn.benchmark = prev
+    out.update(batch=B, what="reference Wav2Lip nn.Module (unmodified, oracle/_ref/py) through PyTorch/cuDNN on the same GPU; ms per batch of 16 frames")
+    return out
+
+
+def torch_gpu_musetalk(dev, flush, B=16):
+    """The same-box PyTorch GPU baseline for MuseTalk: diffusers is absent, so the library arm is the oracle
+    restatement of UNet2DConditionModel + AutoencoderKL.decode run through PyTorch (cuDNN convs, cuBLAS GEMMs, SDPA attention) in
+    fp16 as the reference runs it (musereal.py:60-62), same seeded weights and input shapes as our arm.  Network only."""
+    import torch
+    from oracle import musetalk_oracle as M
+    u, v = M.UNET_CFG, M.VAE_CFG
+    usd = {k: t.to(dev, torch.float16) for k, t in M.seeded_state(M.unet_param_shapes(u), 5).items()}
+    vsd = {k: t.to(dev, torch.float16) for k, t in M.seeded_state(M.vae_decoder_param_shapes(v), 6).items()}
+    rng = np.random.default_rng(11)
+    lat = torch.from_numpy((rng.standard_normal((B, 8, 32, 32)) * 0.18215 * 5).astype(np.float16)).to(dev)
+    wh = torch.from_numpy(rng.standard_normal((B, 50, 384)).astype(np.float16)).to(dev)
+    M.USE_SDPA = True
+    prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    out = {}
+    try:
+        out["fp16_net_ms"] = _event_ms(lambda: M.infer_device(usd, vsd, lat, wh, u, v), 5, 3, flush)
+        usd_c = {k: (t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t) for k, t in usd.items()}
+        vsd_c = {k: (t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t) for k, t in vsd.items()}
+        lat_c = lat.contiguous(memory_format=torch.channels_last)
+        out["fp16_channels_last_net_ms"] = _event_ms(lambda: M.infer_device(usd_c, vsd_c, lat_c, wh, u, v), 5, 3, flush)
+    finally:
+        M.USE_SDPA = False
+        torch.backends.cudnn.benchmark = prev
+    out.update(batch=B, what="PyTorch restatement of the diffusers SD-1.x UNet (t=0) + sd-vae-ft-mse decoder (oracle/musetalk_oracle.py) on the same "
+                             "GPU, fp16, cuDNN benchmark mode, SDPA attention; ms per batch of 16 frames, network only (diffusers itself is absent)")
+    return out
+
+
+def torch_gpu_whisper(dev, flush):
+    """the vendored reference Whisper (musetalk/whisper, staged unmodified) on the same GPU: Audio2Feature.audio2feat on one
+    52-chunk window (audio2feature.py:99-112 -> transcribe -> log_mel + AudioEncoder, fp16 as transcribe defaults), host audio in,
+    numpy features out -- the call MuseASR.run_step makes per batch (museasr.py:23-27)."""
+    import types
+    import torch
+    from helpers import WHISPER_TINY, seeded_whisper_state, synthetic_speech
+    if not os.path.isdir(os.path.join(_ref_py(), "musetalk", "whisper")):
+        return {"unavailable": "oracle/_ref/py/musetalk/whisper not staged"}
+    for m in ("ffmpeg", "soundfile"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    from musetalk.whisper.audio2feature import Audio2Feature
+    from musetalk.whisper.whisper.model import ModelDimensions, Whisper
+    dims = ModelDimensions(n_vocab=51865, n_text_ctx=448, n_text_state=384, n_text_head=6, n_text_layer=4, **WHISPER_TINY)
+    model = Whisper(dims).eval()
+    model.encoder.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_whisper_state(7).items()}, strict=True)
+    model = model.to(dev)
+    a2f = Audio2Feature.__new__(Audio2Feature)
+    a2f.model = model
+    audio = synthetic_speech(52 * 320, 100)
+    with torch.no_grad():
+        for _ in range(3):
+            feat = a2f.audio2feat(audio)
+        ts = []
+        for _ in range(10):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            feat = a2f.audio2feat(audio)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+    return {"ms_per_window": float(np.median(ts)) * 1e3, "feature_shape": list(feat.shape),
+            "what": "vendored reference Whisper-tiny (unmodified, oracle/_ref/py) Audio2Feature.audio2feat on one 52-chunk window, host audio in / "
+                    "numpy out, on the same GPU (the reference pads every window to 30 s before the encoder, transcribe.py:108)"}
+
+
 def p50_latency_ms(step_host, n=30):
     """p50 audio-chunk -> frame: host clock from the call that receives the last chunk's features to the finished u8 frames
     in pinned host memory (excludes the reference's fixed look-ahead)"""
@@ -640,6 +841,7 @@ def main():
     ap.add_argument("--no-musetalk", action="store_true")
     ap.add_argument("--no-asr", action="store_true")
     ap.add_argument("--no-mixed", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -909,6 +1111,23 @@ def main():
         "wall_s_timed_region": wall,
         "heads": heads,
     }
+    if not args.no_reference_gpu:
+        for key, fn in (("wav2lip", lambda: torch_gpu_wav2lip(dev, flush)), ("musetalk", lambda: torch_gpu_musetalk(dev, flush)),
+                        ("musetalk_whisper", lambda: torch_gpu_whisper(dev, flush))):
+            hk = key.split("_")[0]
+            if hk not in heads:
+                continue
+            try:
+                r = fn()
+            except Exception as e:                       # noqa: BLE001 -- a side baseline must not cost the bench line
+                r = {"error": repr(e)[:300]}
+            heads[hk]["torch_gpu" if key == hk else "whisper_torch_gpu"] = r
+        try:
+            line["reference_cuda"] = reference_cuda_leg(dev)
+            if "value" in line["reference_cuda"]:
+                line["reference_cuda"]["ours_e2e_over_reference"] = e2e_value / world / line["reference_cuda"]["value"]
+        except Exception as e:                           # noqa: BLE001 -- a side baseline must not cost the bench line
+            line["reference_cuda"] = {"error": repr(e)}
     if not args.no_cpu_baseline:
         if "wav2lip" in heads:
             import torch as _t

@@ -363,11 +363,14 @@ __device__ __forceinline__ void gen_ray(const FrameGeom &g, int idx, Ray &r) {
         r.dx = g.rays_d[idx * 3]; r.dy = g.rays_d[idx * 3 + 1]; r.dz = g.rays_d[idx * 3 + 2];
     } else {
         // utils.py:274-277,318-328: i = col + 0.5, j = row + 0.5; (i - cx) / fx on CUDA is a multiply
-        // by the fp32 reciprocal; directions normalised, then @ R^T
+        // by the fp32 reciprocal; directions normalised, then @ R^T.  Evaluation order pinned bit for bit on the
+        // reference's own get_rays on the B200 (tests/test_ernerf_reference_render_gpu.py, scripts/diag_rays.py):
+        // torch.norm over the 3-vector reduces as (x*x + z*z) + y*y with separately rounded squares (two threads
+        // split the reduction: {x, z} and {y}); the [N,3] @ [3,3] sgemm accumulates k = 0, 1, 2 with FMAs.
         const int row = idx / g.W, col = idx - row * g.W;
         const float xs = ((float)col + 0.5f - g.cx) * g.inv_fx;
         const float ys = ((float)row + 0.5f - g.cy) * g.inv_fy;
-        const float nrm = sqrtf(fmaf(ys, ys, xs * xs) + 1.0f);
+        const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(xs, xs), 1.0f), __fmul_rn(ys, ys)));
         const float d0 = xs / nrm, d1 = ys / nrm, d2 = 1.0f / nrm;
         r.dx = fmaf(d2, g.R[2], fmaf(d1, g.R[1], d0 * g.R[0]));
         r.dy = fmaf(d2, g.R[5], fmaf(d1, g.R[4], d0 * g.R[3]));

@@ -11,6 +11,14 @@ pybind modules) land only in oracle/_ref/, which is git-ignored but travels to t
 
 The GPU-side tests import those modules (tests/ref_ernerf.py) to pin the C oracle and the
 sm_100a kernels against the reference's own kernels.  Without /root/reference this is a no-op.
+
+stage_python() additionally STAGES (file copy at build time, never into the git tree) the reference's
+own ErNeRF Python -- encoding.py, nerf_triplane/{network,renderer,utils,provider}.py and the four
+extension wrapper packages -- into the git-ignored oracle/_ref/py/ernerf/, so that on the GPU box
+(where /root/reference does not exist) tests/ref_ernerf.py can build the reference NeRFNetwork +
+Trainer and run the reference's OWN full render (Trainer.test_gui_with_data -> run_cuda + run_torso,
+utils.py:1191-1223, renderer.py:158-352) as the frame-level ground truth and as the same-box timed
+GPU baseline of bench.py (`reference_cuda`).
 """
 import os
 import sys
@@ -27,10 +35,45 @@ EXTS = {
 }
 
 
+PY_FILES = [
+    "encoding.py",
+    "nerf_triplane/network.py", "nerf_triplane/renderer.py", "nerf_triplane/utils.py", "nerf_triplane/provider.py",
+    "raymarching/__init__.py", "raymarching/raymarching.py", "raymarching/backend.py",
+    "gridencoder/__init__.py", "gridencoder/grid.py", "gridencoder/backend.py",
+    "shencoder/__init__.py", "shencoder/sphere_harmonics.py", "shencoder/backend.py",
+    "freqencoder/__init__.py", "freqencoder/freq.py", "freqencoder/backend.py",
+]
+
+
+def stage_python():
+    """copy the reference's ErNeRF Python (unmodified) into oracle/_ref/py/ernerf/ -- git-ignored, travels with gpurun"""
+    import shutil
+    src = os.path.join(REF, "ernerf")
+    if not os.path.isdir(src):
+        return []
+    out = []
+    for rel in PY_FILES:
+        dst = os.path.join(OUT, "py", "ernerf", rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        s = os.path.join(src, rel)
+        if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(s):
+            shutil.copyfile(s, dst)
+        out.append(dst)
+    # the reference's dense-head modules for the same-box cuDNN / cuBLAS baselines of bench.py (`heads.*.torch_gpu`):
+    # wav2lip/models (wav2lip.py:87-125, conv.py) and the vendored Whisper (musetalk/whisper, encoder model.py:143-171)
+    for sub in ("wav2lip/models", "musetalk/whisper"):
+        s_dir, d_dir = os.path.join(REF, sub), os.path.join(OUT, "py", sub)
+        if os.path.isdir(s_dir) and not os.path.isdir(d_dir):
+            shutil.copytree(s_dir, d_dir, ignore=shutil.ignore_patterns("__pycache__"))
+        out.append(d_dir)
+    return out
+
+
 def build(names=None, verbose=False):
     if not os.path.isdir(os.path.join(REF, "ernerf")):
         print(f"[oracle/build_ref] {REF} absent: nothing to build (prebuilt oracle/_ref is used as is)")
         return []
+    stage_python()
     os.environ["TORCH_CUDA_ARCH_LIST"] = "10.0"
     from torch.utils.cpp_extension import load
     built = []

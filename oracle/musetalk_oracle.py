@@ -173,7 +173,10 @@ def positional_encoding(x):
     div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
     pe[:, 0::2] = torch.sin(position * div_term)
     pe[:, 1::2] = torch.cos(position * div_term)
-    return x + pe.unsqueeze(0)
+    return x + pe.unsqueeze(0).to(device=x.device, dtype=x.dtype)
+
+
+USE_SDPA = False     # the GPU baseline leg of bench.py sets this: diffusers' AttnProcessor2_0 calls F.scaled_dot_product_attention
 
 
 def timestep_embedding_t0(dim):
@@ -209,8 +212,11 @@ def attention(sd, p, x, ctx, heads, bias_qkv=False):
     q = lin("to_q", x).view(B, N, heads, d).transpose(1, 2)
     k = lin("to_k", ctx).view(B, ctx.shape[1], heads, d).transpose(1, 2)
     v = lin("to_v", ctx).view(B, ctx.shape[1], heads, d).transpose(1, 2)
-    a = torch.softmax(q @ k.transpose(-1, -2) * (d ** -0.5), dim=-1)
-    o = (a @ v).transpose(1, 2).reshape(B, N, C)
+    if USE_SDPA:
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C)
+    else:
+        a = torch.softmax(q @ k.transpose(-1, -2) * (d ** -0.5), dim=-1)
+        o = (a @ v).transpose(1, 2).reshape(B, N, C)
     return F.linear(o, sd[f"{p}.to_out.0.weight"], sd[f"{p}.to_out.0.bias"])
 
 
@@ -237,7 +243,7 @@ def transformer2d(sd, p, x, ctx, heads, groups):
 def unet_forward(sd, latents, ctx, cfg=UNET_CFG):
     """UNet2DConditionModel.forward(sample, timestep=0, encoder_hidden_states).sample"""
     bo, L, heads, G, eps = cfg["block_out"], cfg["layers"], cfg["heads"], cfg["groups"], cfg["eps"]
-    temb = F.linear(F.silu(F.linear(timestep_embedding_t0(bo[0]), sd["time_embedding.linear_1.weight"],
+    temb = F.linear(F.silu(F.linear(timestep_embedding_t0(bo[0]).to(latents), sd["time_embedding.linear_1.weight"],
                                     sd["time_embedding.linear_1.bias"])),
                     sd["time_embedding.linear_2.weight"], sd["time_embedding.linear_2.bias"])
     x = F.conv2d(latents, sd["conv_in.weight"], sd["conv_in.bias"], padding=1)
@@ -302,3 +308,14 @@ def infer(unet_sd, vae_sd, latents, whisper, ucfg=UNET_CFG, vcfg=VAE_CFG):
         img = (img / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1)
     u8 = (img.numpy() * 255).round().astype("uint8")[..., ::-1]
     return pred.numpy(), img.numpy(), np.ascontiguousarray(u8)
+
+
+def infer_device(unet_sd, vae_sd, latents, whisper, ucfg=UNET_CFG, vcfg=VAE_CFG):
+    """the same arithmetic with every tensor where the caller put it (device, dtype): the same-box PyTorch GPU baseline of
+    bench.py (`heads.musetalk.torch_gpu`; the reference runs pe / unet / vae in fp16 on the GPU, musereal.py:60-62).
+    Returns the u8 BGR frames as a device tensor (vae.py:102-107)."""
+    with torch.no_grad():
+        pred = unet_forward(unet_sd, latents, positional_encoding(whisper), ucfg)
+        img = vae_decode(vae_sd, pred / vcfg["scaling_factor"], vcfg)
+        img = (img / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).float()
+        return (img * 255).round().to(torch.uint8).flip(-1)
