@@ -147,6 +147,7 @@ extern "C" int mf_paste_resize_u8(mf_ctx *ctx, const uint8_t *frames, int n_fram
                    "mf_paste_resize_u8: bbox (y1,y2,x1,x2)=(%d,%d,%d,%d) outside the %dx%d frame", r[1], r[2], r[3], r[4], H, W);
         p.idx[i] = r[0]; p.y1[i] = r[1]; p.y2[i] = r[2]; p.x1[i] = r[3]; p.x2[i] = r[4];
     }
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));   // the caller's thread may sit on another GPU (in-process multi-GPU scheduler)
     dim3 grid((H * W + 255) / 256, B);
     k_paste_resize<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     MF_CUDA(ctx, cudaGetLastError());
@@ -177,6 +178,7 @@ extern "C" int mf_paste_blend_u8(mf_ctx *ctx, const uint8_t *frames, int n_frame
         p.ys[i] = r[5]; p.ye[i] = r[6]; p.xs[i] = r[7]; p.xe[i] = r[8];
         p.moff[i] = mask_off_host[i];
     }
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
     dim3 grid((H * W + 255) / 256, B);
     k_paste_blend<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     MF_CUDA(ctx, cudaGetLastError());

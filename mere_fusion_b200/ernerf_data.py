@@ -54,7 +54,8 @@ class ErnerfPoseProvider:
     """poses [N,4,4] fp32, eye_area [N] fp32, intrinsics (fx, fy, cx, cy), H, W."""
 
     def __init__(self, transform, au_blink=None, scale=4.0, offset=(0, 0, 0), smooth_path=True,
-                 smooth_path_window=7, exp_eye=True, smooth_eye=True, data_range=(0, -1), downscale=1):
+                 smooth_path_window=7, exp_eye=True, smooth_eye=True, data_range=(0, -1), downscale=1, bg_img="white",
+                 torso_imgs=""):
         if isinstance(transform, str):
             with open(transform, "r") as f:
                 transform = json.load(f)
@@ -75,6 +76,10 @@ class ErnerfPoseProvider:
         fl = transform["focal_len"]
         self.intrinsics = np.array([fl, fl, transform["cx"] / downscale, transform["cy"] / downscale])
         self.index = 0
+        if torso_imgs != "":
+            raise NotImplementedError("opt.torso_imgs (per-frame torso composites as background, provider.py:316-328) is not supported by "
+                                      "the fused renderer: run with the torso model (torso_imgs='')")
+        self.bg_img = load_bg_img(bg_img, self.H, self.W)
 
     def __len__(self):
         return self.poses.shape[0]
@@ -92,6 +97,25 @@ class ErnerfPoseProvider:
         out = self.get(self.index)
         self.index += 1
         return out
+
+
+def load_bg_img(bg_img, H, W):
+    """provider.py:203-214: 'white' -> None (the renderer's default), 'black' -> zeros, else an image file read as RGB in
+    [0,1], resized with INTER_AREA when its size differs.  Returns fp32 [H,W,3] or None."""
+    if bg_img is None or (isinstance(bg_img, str) and bg_img == "white"):
+        return None
+    if isinstance(bg_img, str) and bg_img == "black":
+        return np.zeros((H, W, 3), np.float32)
+    if isinstance(bg_img, str):
+        import cv2
+        img = cv2.imread(bg_img, cv2.IMREAD_UNCHANGED)
+        if img is None:
+            raise FileNotFoundError(bg_img)
+        if img.shape[0] != H or img.shape[1] != W:
+            img = cv2.resize(img, (W, H), interpolation=cv2.INTER_AREA)
+        img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+        return img.astype(np.float32) / 255
+    return np.asarray(bg_img, np.float32).reshape(H, W, 3)
 
 
 def load_au_blink(path):

@@ -61,12 +61,25 @@ class Avatar:
 _NOLOCK = contextlib.nullcontext()
 
 
-class _Pasted:
-    """a full frame that already carries the pasted face (GPU paste path)"""
-    __slots__ = ("frame",)
+RING = 4     # pinned result buffers in flight: res_frame_queue holds <= 2 batches, one more is being written and one frame of a
+             # fourth may still be inside process_frames when its slot comes round again
 
-    def __init__(self, frame):
-        self.frame = frame
+
+class _Pasted:
+    """a full frame that already carries the pasted face (GPU paste path): a view into a pinned ring slot plus the CUDA event
+    of the device->host copy that fills it -- the consumer (process_frames) waits for the event, not the inference thread"""
+    __slots__ = ("_frame", "_event")
+
+    def __init__(self, frame, event=None):
+        self._frame = frame
+        self._event = event
+
+    @property
+    def frame(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+        return self._frame
 
 
 class LipReal(BaseReal):
@@ -137,8 +150,8 @@ class LipReal(BaseReal):
                              sel=torch.empty((B, S, S, 3), dtype=torch.uint8, device=dev),
                              pred=torch.empty((B, S, S, 3), dtype=torch.uint8, device=dev),
                              out=torch.empty((B, Hf, Wf, 3), dtype=torch.uint8, device=dev),
-                             out_pin=torch.empty((B, Hf, Wf, 3), dtype=torch.uint8).pin_memory(),
-                             pred_pin=torch.empty((B, S, S, 3), dtype=torch.uint8).pin_memory())
+                             out_pin=[torch.empty((B, Hf, Wf, 3), dtype=torch.uint8).pin_memory() for _ in range(RING)] if self.paste == "gpu" else None,
+                             pred_pin=torch.empty((B, S, S, 3), dtype=torch.uint8).pin_memory(), slot=0)
         return self._dev
 
     def infer_batch(self, mel_batch, index):
@@ -150,33 +163,39 @@ class LipReal(BaseReal):
         B = self.batch_size
         length = len(self.face_list_cycle)
         idxs = [mirror_index(length, index + i) for i in range(B)]
-        if torch.is_tensor(mel_batch):                           # device-resident chunks from LipASR (GPU mel front-end)
-            d["mel"].copy_(mel_batch, non_blocking=True)
-        else:
-            d["mel_pin"].copy_(torch.from_numpy(np.asarray(mel_batch, dtype=np.float32).reshape(B, 1, 80, 16)))
-            d["mel"].copy_(d["mel_pin"], non_blocking=True)
-        torch.index_select(d["faces"], 0, torch.as_tensor(idxs, device=d["faces"].device), out=d["sel"])
-        self.engine.forward(d["mel"], d["sel"], out=d["pred"])
-        if self.paste == "gpu":
-            rows = np.empty((B, 5), np.int32)
-            for i, k in enumerate(idxs):
-                y1, y2, x1, x2 = self.coord_list_cycle[k]
-                rows[i] = (k, y1, y2, x1, x2)
-            s = torch.cuda.current_stream(d["out"].device)
-            fr = d["frames"]
-            with getattr(self.engine, "lock", _NOLOCK):          # a shared engine (scheduler.SharedEngine): one caller at a time on its context
-                check(self.engine.ctx.handle,
-                      lib().mf_paste_resize_u8(self.engine.ctx.handle, ctypes.c_void_p(fr.data_ptr()), fr.shape[0], fr.shape[1],
-                                               fr.shape[2], ctypes.c_void_p(d["pred"].data_ptr()), d["S"], B,
-                                               rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-                                               ctypes.c_void_p(d["out"].data_ptr()), ctypes.c_void_p(s.cuda_stream)),
-                      "mf_paste_resize_u8")
-            d["out_pin"].copy_(d["out"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            full = d["out_pin"].numpy()
-            return [_Pasted(full[i].copy()) for i in range(B)]
-        d["pred_pin"].copy_(d["pred"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        dev = d["out"].device
+        with torch.cuda.device(dev):                             # this thread may never have selected the session's GPU
+            s = torch.cuda.current_stream(dev)
+            if torch.is_tensor(mel_batch):                       # device-resident chunks from LipASR (GPU mel front-end)
+                d["mel"].copy_(mel_batch, non_blocking=True)
+            else:
+                d["mel_pin"].copy_(torch.from_numpy(np.asarray(mel_batch, dtype=np.float32).reshape(B, 1, 80, 16)))
+                d["mel"].copy_(d["mel_pin"], non_blocking=True)
+            torch.index_select(d["faces"], 0, torch.as_tensor(idxs, device=dev), out=d["sel"])
+            self.engine.forward(d["mel"], d["sel"], out=d["pred"])
+            if self.paste == "gpu":
+                rows = np.empty((B, 5), np.int32)
+                for i, k in enumerate(idxs):
+                    y1, y2, x1, x2 = self.coord_list_cycle[k]
+                    rows[i] = (k, y1, y2, x1, x2)
+                fr = d["frames"]
+                with getattr(self.engine, "lock", _NOLOCK):      # a shared engine (scheduler.SharedEngine): one caller at a time on its context
+                    check(self.engine.ctx.handle,
+                          lib().mf_paste_resize_u8(self.engine.ctx.handle, ctypes.c_void_p(fr.data_ptr()), fr.shape[0], fr.shape[1],
+                                                   fr.shape[2], ctypes.c_void_p(d["pred"].data_ptr()), d["S"], B,
+                                                   rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                                   ctypes.c_void_p(d["out"].data_ptr()), ctypes.c_void_p(s.cuda_stream)),
+                          "mf_paste_resize_u8")
+                # event + pinned ring: no host wait here and no per-frame copy; process_frames waits on the event of the slot it reads
+                pin = d["out_pin"][d["slot"] % RING]
+                d["slot"] += 1
+                pin.copy_(d["out"], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s)
+                full = pin.numpy()
+                return [_Pasted(full[i], ev) for i in range(B)]
+            d["pred_pin"].copy_(d["pred"], non_blocking=True)
+            s.synchronize()
         pred = d["pred_pin"].numpy()
         return [pred[i].copy() for i in range(B)]
 

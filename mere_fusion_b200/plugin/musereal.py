@@ -26,7 +26,7 @@ import numpy as np
 
 from .basereal import BaseReal
 from .frames import AudioFrame, VideoFrame
-from .lipreal import _NOLOCK, LipReal, _Pasted, mirror_index
+from .lipreal import _NOLOCK, RING, LipReal, _Pasted, mirror_index
 from .museasr import MuseASR
 
 
@@ -133,8 +133,8 @@ class MuseReal(BaseReal):
                              sel=torch.empty((B,) + tuple(lat.shape[1:]), dtype=torch.float16, device=dev),
                              pred=torch.empty((B, 256, 256, 3), dtype=torch.uint8, device=dev),
                              out=torch.empty((B, Hf, Wf, 3), dtype=torch.uint8, device=dev),
-                             out_pin=torch.empty((B, Hf, Wf, 3), dtype=torch.uint8).pin_memory(),
-                             pred_pin=torch.empty((B, 256, 256, 3), dtype=torch.uint8).pin_memory())
+                             out_pin=[torch.empty((B, Hf, Wf, 3), dtype=torch.uint8).pin_memory() for _ in range(RING)] if self.paste == "gpu" else None,
+                             pred_pin=torch.empty((B, 256, 256, 3), dtype=torch.uint8).pin_memory(), slot=0)
         return self._dev
 
     def _upload_avatar(self, dev):
@@ -162,37 +162,43 @@ class MuseReal(BaseReal):
         B = self.batch_size
         length = len(self.input_latent_list_cycle)
         idxs = [mirror_index(length, index + i) for i in range(B)]
-        if torch.is_tensor(whisper_chunks):                       # device-resident chunks from MuseASR (already fp16)
-            d["wh"].copy_(whisper_chunks, non_blocking=True)
-        else:
-            d["wh_pin"].copy_(torch.from_numpy(np.stack(whisper_chunks).astype(np.float16)))  # .to(dtype=half), musereal.py:99-101
-            d["wh"].copy_(d["wh_pin"], non_blocking=True)
-        torch.index_select(d["latents"], 0, torch.as_tensor(idxs, device=d["latents"].device), out=d["sel"])
-        self.engine.forward(d["sel"], d["wh"], out=d["pred"])
-        if self.paste == "gpu":
-            rows = np.empty((B, 9), np.int32)
-            moff = np.empty(B, np.int64)
-            for i, k in enumerate(idxs):
-                x1, y1, x2, y2 = self.coord_list_cycle[k]
-                xs, ys, xe, ye = self.mask_coords_list_cycle[k]
-                rows[i] = (k, y1, y2, x1, x2, ys, ye, xs, xe)
-                moff[i] = d["mask_off"][k]
-            s = torch.cuda.current_stream(d["out"].device)
-            fr = d["frames"]
-            with getattr(self.engine, "lock", _NOLOCK):          # a shared engine (scheduler.SharedEngine): one caller at a time on its context
-                check(self.engine.ctx.handle,
-                      lib().mf_paste_blend_u8(self.engine.ctx.handle, ctypes.c_void_p(fr.data_ptr()), fr.shape[0], fr.shape[1], fr.shape[2],
-                                              ctypes.c_void_p(d["pred"].data_ptr()), 256, B,
-                                              rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_void_p(d["masks"].data_ptr()),
-                                              d["masks"].numel(), moff.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                                              ctypes.c_void_p(d["out"].data_ptr()), ctypes.c_void_p(s.cuda_stream)),
-                      "mf_paste_blend_u8")
-            d["out_pin"].copy_(d["out"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            full = d["out_pin"].numpy()
-            return [_Pasted(full[i].copy()) for i in range(B)]
-        d["pred_pin"].copy_(d["pred"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        dev = d["out"].device
+        with torch.cuda.device(dev):                              # this thread may never have selected the session's GPU
+            s = torch.cuda.current_stream(dev)
+            if torch.is_tensor(whisper_chunks):                   # device-resident chunks from MuseASR (already fp16)
+                d["wh"].copy_(whisper_chunks, non_blocking=True)
+            else:
+                d["wh_pin"].copy_(torch.from_numpy(np.stack(whisper_chunks).astype(np.float16)))  # .to(dtype=half), musereal.py:99-101
+                d["wh"].copy_(d["wh_pin"], non_blocking=True)
+            torch.index_select(d["latents"], 0, torch.as_tensor(idxs, device=dev), out=d["sel"])
+            self.engine.forward(d["sel"], d["wh"], out=d["pred"])
+            if self.paste == "gpu":
+                rows = np.empty((B, 9), np.int32)
+                moff = np.empty(B, np.int64)
+                for i, k in enumerate(idxs):
+                    x1, y1, x2, y2 = self.coord_list_cycle[k]
+                    xs, ys, xe, ye = self.mask_coords_list_cycle[k]
+                    rows[i] = (k, y1, y2, x1, x2, ys, ye, xs, xe)
+                    moff[i] = d["mask_off"][k]
+                fr = d["frames"]
+                with getattr(self.engine, "lock", _NOLOCK):       # a shared engine (scheduler.SharedEngine): one caller at a time on its context
+                    check(self.engine.ctx.handle,
+                          lib().mf_paste_blend_u8(self.engine.ctx.handle, ctypes.c_void_p(fr.data_ptr()), fr.shape[0], fr.shape[1], fr.shape[2],
+                                                  ctypes.c_void_p(d["pred"].data_ptr()), 256, B,
+                                                  rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_void_p(d["masks"].data_ptr()),
+                                                  d["masks"].numel(), moff.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                                  ctypes.c_void_p(d["out"].data_ptr()), ctypes.c_void_p(s.cuda_stream)),
+                          "mf_paste_blend_u8")
+                # event + pinned ring (plugin/lipreal.py): process_frames waits on the slot's event, no per-frame host copy
+                pin = d["out_pin"][d["slot"] % RING]
+                d["slot"] += 1
+                pin.copy_(d["out"], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s)
+                full = pin.numpy()
+                return [_Pasted(full[i], ev) for i in range(B)]
+            d["pred_pin"].copy_(d["pred"], non_blocking=True)
+            s.synchronize()
         pred = d["pred_pin"].numpy()
         return [pred[i].copy() for i in range(B)]
 

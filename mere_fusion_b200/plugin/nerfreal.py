@@ -29,6 +29,16 @@ def _adapt_provider(data_loader):
     prov.eye_area = ds.eye_area.detach().cpu().numpy().reshape(-1) if getattr(ds, "eye_area", None) is not None else None
     prov.intrinsics = np.asarray(ds.intrinsics)
     prov.H, prov.W, prov.index = ds.H, ds.W, 0
+    # background (provider.py:203-214,235-238,330-332): 'white' / 'black' / an image file, [H,W,3] in [0,1]
+    if getattr(getattr(ds, "opt", None), "torso_imgs", "") != "":
+        raise NotImplementedError("opt.torso_imgs (per-frame torso composites as background, provider.py:316-328) is not supported by "
+                                  "the fused renderer: run with the torso model (torso_imgs='')")
+    bg = getattr(ds, "bg_img", None)
+    if bg is not None:
+        bg = np.asarray(bg.detach().float().cpu().numpy() if hasattr(bg, "detach") else bg, np.float32).reshape(ds.H, ds.W, 3)
+        if np.all(bg == 1.0):
+            bg = None                                   # the kernel's default
+    prov.bg_img = bg
     return prov
 
 
@@ -64,6 +74,7 @@ class NeRFReal(BaseReal):
         self.asr.warm_up()
         self._out = None
         self._pin = None
+        self._bg = None
 
     @staticmethod
     def _has_cuda():
@@ -98,10 +109,14 @@ class NeRFReal(BaseReal):
         p = self.provider
         fix_eye = getattr(self.opt, "fix_eye", -1)
         eye = fix_eye if (self.opt.exp_eye and fix_eye >= 0) else eye            # utils.py:937-940
-        self.renderer.render(pose, p.intrinsics, p.H, p.W, auds.contiguous(), eye if eye is not None else 0.0,
-                             out=self._out, outH=self.H, outW=self.W)
-        self._pin.copy_(self._out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        dev = self.renderer.device
+        if self._bg is None and getattr(p, "bg_img", None) is not None:        # data['bg_color'] (provider.py:330-332), uploaded once
+            self._bg = torch.from_numpy(np.ascontiguousarray(p.bg_img, np.float32).reshape(-1, 3)).to(dev, torch.float16)
+        with torch.cuda.device(dev):                     # this thread may never have selected the session's GPU
+            self.renderer.render(pose, p.intrinsics, p.H, p.W, auds.contiguous(), eye if eye is not None else 0.0,
+                                 out=self._out, outH=self.H, outW=self.W, bg_color=self._bg)
+            self._pin.copy_(self._out, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
         return self._pin.numpy().copy()
 
     def test_step(self, loop=None, audio_track=None, video_track=None):

@@ -94,7 +94,7 @@ class ReferenceErnerf:
     fixture (tests/golden/ernerf_ckpt_infer.npz: the inference tensors of data/pretrained/ngp_kf.pth) and the pose /
     AU fixture written back into the on-disk formats the reference loader reads (transforms json + au.csv)."""
 
-    def __init__(self, H=450, W=450, device="cuda", n_frames=290, tmpdir=None):
+    def __init__(self, H=450, W=450, device="cuda", n_frames=290, tmpdir=None, **opt_over):
         import json
         import tempfile
 
@@ -118,7 +118,7 @@ class ReferenceErnerf:
             f.write("frame, AU45_r\n")
             for i, v in enumerate(au):
                 f.write(f"{i}, {float(v)!r}\n")
-        self.opt = live_opt(pose=os.path.join(tmp, "transforms.json"), au=os.path.join(tmp, "au.csv"), W=W, H=H)
+        self.opt = live_opt(pose=os.path.join(tmp, "transforms.json"), au=os.path.join(tmp, "au.csv"), W=W, H=H, **opt_over)
         self.device = torch.device(device)
         model = network.NeRFNetwork(self.opt)
         state = {k: torch.from_numpy(np.asarray(v)).float() if np.asarray(v).dtype in (np.float16, np.float32)

@@ -227,3 +227,25 @@ def test_reference_rays_fed_explicitly_are_bit_exact(ours):
     assert [int(r0[0]), int(r0[3]), int(r0[2])] == log["rounds"][0]
     assert torch.equal(dbg_e["torso_mask"], dbg_f["torso_mask"])
     assert torch.equal(u8_e.reshape(-1), u8_f.reshape(-1))
+
+
+def test_plugin_nerfreal_built_from_the_reference_trainer_and_loader():
+    """the drop-in constructor NeRFReal(opt, trainer, data_loader) (nerfreal.py:34-58, app.py:372-392) handed the REAL reference
+    objects: weights are taken from trainer.model, poses / eye / intrinsics / background from the reference loader; the frame it
+    renders equals the reference's own test_gui_with_data frame -- with a non-default (black) background, opt.bg_img"""
+    from mere_fusion_b200.plugin.nerfreal import NeRFReal
+    H = 450
+    ref = ref_ernerf.ReferenceErnerf(H=H, W=H, device="cuda", bg_img="black", tts="none", avatar_id="t", batch_size=16)
+    loader = ref.dataset.dataloader()
+    real = NeRFReal(ref.opt, ref.trainer, loader, feature_fn=lambda fr: torch.zeros(((len(fr) - 400) // 320 + 1, 44)), device=0)
+    assert real.provider.bg_img is not None and float(real.provider.bg_img.max()) == 0.0
+    frame = 5
+    _, _, auds, _ = ernerf_inputs(frame, H, H)
+    ref.reset()
+    img_ref = ref.render(frame, auds)
+    i, pose, eye = real.provider.get(frame)
+    img = real.render_image(pose, eye, torch.from_numpy(auds).cuda())
+    assert img.shape == (H, H, 3) and img.dtype == np.uint8
+    du8 = np.abs(img.astype(np.int32) - (img_ref * 255).astype(np.uint8).astype(np.int32))
+    assert img[:10].mean() < 2.0, "background must be black"
+    assert np.percentile(du8, 99) <= 2 and psnr(img / 255.0, (img_ref * 255).astype(np.uint8) / 255.0) >= 40.0

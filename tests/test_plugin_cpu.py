@@ -412,3 +412,23 @@ def test_mel_chunk_starts_agree_between_host_and_gpu_front_ends():
                     assert mel_chunk_starts(n_frames, l, r, fps, n_cols) == want
                     assert MelFrontEnd.chunk_starts(n_frames, l, r, fps, n_cols).tolist() == want
     assert mel_chunk_starts(15, 10, 10, 50, 80) == []          # not more than the context: no video frame yet
+
+
+def test_ernerf_background_image_is_carried_over(tmp_path):
+    """opt.bg_img (provider.py:203-214): 'white' = the renderer's default, 'black', or an image file (RGB, /255, INTER_AREA resize);
+    opt.torso_imgs is refused loudly (the fused renderer always runs the torso model)"""
+    import cv2
+    from mere_fusion_b200.ernerf_data import ErnerfPoseProvider, load_bg_img
+    assert load_bg_img("white", 8, 8) is None
+    assert np.array_equal(load_bg_img("black", 4, 6), np.zeros((4, 6, 3), np.float32))
+    img = np.random.default_rng(0).integers(0, 256, (20, 30, 3), dtype=np.uint8)
+    p = str(tmp_path / "bg.png")
+    cv2.imwrite(p, img)
+    got = load_bg_img(p, 20, 30)
+    assert np.array_equal(got, cv2.cvtColor(img, cv2.COLOR_BGR2RGB).astype(np.float32) / 255)
+    small = load_bg_img(p, 10, 15)
+    assert np.array_equal(small, cv2.cvtColor(cv2.resize(img, (15, 10), interpolation=cv2.INTER_AREA), cv2.COLOR_BGR2RGB).astype(np.float32) / 255)
+    tr = dict(cx=4.0, cy=4.0, focal_len=10.0, frames=[dict(transform_matrix=np.eye(4).tolist(), img_id=0)] * 3)
+    assert ErnerfPoseProvider(tr, None, bg_img="black").bg_img.shape == (8, 8, 3)
+    with pytest.raises(NotImplementedError):
+        ErnerfPoseProvider(tr, None, torso_imgs="data/torso")
