@@ -2,23 +2,35 @@
 //
 // Replaces, per frame, the ~400 launches + <=16 host syncs of the reference's
 // NeRFRenderer.run_cuda / run_torso (ernerf/nerf_triplane/renderer.py:158-352) by
-//   k_setup         1 CTA   : AudioNet + AudioAttNet + EMA (network.py:9-66,222-237), the
-//                             per-frame torso constants, and the round counters
-//   k_head          persistent cooperative kernel, one grid barrier per march round:
-//                   ray generation (utils.py:255-341) -> near/far (raymarching.cu:91-145) ->
-//                   march (raymarching.cu:827-929) -> tri-plane hash-grid gather
-//                   (gridencoder.cu:75-175) -> SH (shencoder.cu:27-68) -> aud_ch_att / eye_att /
-//                   sigma / color MLPs (network.py:249-308) on warp-level tensor-core tiles ->
-//                   composite (raymarching.cu:2141-2249) -> warp-aggregated alive-ray compaction
-//                   (renderer.py:266), all in registers / shared memory
-//   k_torso_compose torso occupancy + deformation + tiled grid + MLPs (network.py:166-201,
-//                   renderer.py:294-352), background blend, clamp, optional fp32 / u8 output
+//   k_setup         CTA f < n_frames : AudioNet + AudioAttNet + EMA (network.py:9-66,222-237) and the per-frame torso
+//                                      constants of frame f
+//                   the other CTAs   : the RAY PASS -- ray generation (utils.py:255-341) -> near/far
+//                                      (raymarching.cu:91-145) -> march to the first sample (raymarching.cu:827-929);
+//                                      rays that have one are appended to the frame's hit list (this is the reference's
+//                                      round 0 minus its shading: n_step = N / N = 1)
+//   k_head          persistent, NO grid barrier: each warp owns 32 / CH rays at a time, marches CH samples of each
+//                   side by side -> tri-plane hash-grid gather (gridencoder.cu:75-175) -> SH (shencoder.cu:27-68) ->
+//                   aud_ch_att / eye_att / sigma / color MLPs (network.py:249-308) on warp-level tensor-core tiles ->
+//                   composite (raymarching.cu:2141-2249) in sample order, and refills finished rays from the hit list
+//   k_torso_compose resolves the loop control from the life histogram, then torso occupancy + deformation + tiled grid
+//                   + MLPs (network.py:166-201, renderer.py:294-352), background blend, clamp, fp32 / u8 output
 //   k_resize_u8     bilinear resize (utils.py:1212) + u8 (nerfreal.py:110) when sizes differ
 //
-// Round semantics are the reference's: round r marches every alive ray n_step =
-// clamp(N / n_alive, 1, 8) samples, and the loop ends when the summed n_step reaches max_steps;
-// the alive count is a global quantity, hence the grid barrier between rounds.
-#include <cooperative_groups.h>
+// Round semantics WITHOUT rounds.  The reference marches every alive ray n_step = clamp(N / n_alive, 1, 8) samples per
+// round and stops when the summed n_step reaches max_steps (renderer.py:246-270); n_alive is a global quantity, which is
+// why round 1 of this kernel had one grid barrier per round (~45 % of its warp-time waited there, profiles/r01_k_head_v4).
+// But the samples of a ray do not depend on how they are cut into rounds: march_rays continues from rays_t with a
+// sigma-independent step (raymarching.cu:872-928), the compositor is a recurrence over the ray's samples in order with two
+// exits -- the ray runs out of samples (deltas[0] == 0) or T < T_thresh after accumulating a sample (:2189-2218).  So a
+// ray's result is the composite of its first min(C, own end) samples, where C = sum of n_step over the rounds is the ONLY
+// thing the round structure decides, and C follows from A(c) = number of rays still alive after c samples:
+//     c = 0; while c < max_steps: n_alive = A(c); n_step = clamp(N / n_alive, 1, 8); c += n_step;   C = c  (<= max_steps + 7)
+// A ray is alive after c samples iff life >= c, life = min(samples available, index of the T-exit sample - 1).  k_head
+// therefore shades every ray at its own pace (CH samples per pass, any order), counts rays by life in a histogram, and the
+// few rays that are still alive after max_steps samples go on speculatively to max_steps + 7 while recording their state
+// after each of the samples max_steps .. max_steps + 7; k_torso_compose derives the rounds (n_alive, n_step) and C from the
+// histogram and picks the snapshot C - max_steps for those rays.  Same arithmetic per ray, same samples, same exits: the
+// image is the round-structured one bit for bit (tests/test_ernerf_reference_render_gpu.py pins it on the reference render).
 
 #include <algorithm>
 #include <cmath>
@@ -28,12 +40,19 @@
 #include "ernerf_device.cuh"
 #include "ernerf_layout.h"
 
-namespace cg = cooperative_groups;
 using namespace ernerf;
 
 #define ER_MAX_ROUNDS 16
-#define ER_CTR_STRIDE 32 /* ints per counter row */
-// counters layout (ints): [0] n_alive[r], [1] tile ticket[r], [2] samples emitted[r], [3] n_step[r]
+#define ER_MAX_STEPS 32  /* cfg.max_steps supported by the life histogram */
+// per-frame counters (ints); two copies, alternating per frame of a context: k_setup of frame n zeroes the copy frame n+1 uses
+#define CT_NHIT 0     /* rays with a first sample = length of the hit list */
+#define CT_TICKET 1   /* next unclaimed hit-list slot (k_head refill) */
+#define CT_SAMPLES 2  /* samples shaded by k_head */
+#define CT_NSURV 3    /* rays alive after max_steps samples = snapshot slots in use */
+#define CT_HIST 8     /* [ER_MAX_STEPS + 1] rays by life; bin max_steps = alive after max_steps samples */
+#define CT_ROUNDS 48  /* [ER_MAX_ROUNDS + 1][4] derived by k_torso_compose: n_alive, 0, samples emitted (round 0; -1 = not tracked), n_step */
+#define CT_INTS 128
+#define ER_SNAPS 8    /* states recorded per surviving ray: after sample max_steps + j, j = 0..7 */
 
 // levels [0, n_dense) are IDX_DENSE, the rest IDX_HASH2 (head) / IDX_TILE2 (torso); n_dense < 0: generic
 struct HeadLevels { GridLevel lv[MF_ERNERF_HEAD_LEVELS]; int n_dense; };
@@ -70,13 +89,16 @@ struct ErnerfState {
     TorsoLevels tl;
     // persistent device state
     float *state = nullptr;  // [0..31] enc_a (smoothed), [32] has_prev flag, [64..95] bias_def, [96..127] bias_tor
-    int *counters = nullptr; // [ER_MAX_ROUNDS+1][ER_CTR_STRIDE]
+    int *counters = nullptr; // [2][CT_INTS]
+    unsigned frame_no = 0;   // parity selects the counter copy
     // per-N workspace
     int capN = 0;
-    int *alive[2] = {nullptr, nullptr};
-    float *rays_t = nullptr, *fars = nullptr, *nears = nullptr, *weights_sum = nullptr, *image = nullptr;
+    int *hits = nullptr;     // [N] ray ids with a first sample
+    float4 *snap = nullptr;  // [N][ER_SNAPS] (ws, r, g, b) of rays alive after max_steps samples
+    float *rays_t = nullptr, *fars = nullptr, *weights_sum = nullptr, *image = nullptr;
     float *final_f32 = nullptr;  // [N,3] when a resize follows
     int head_grid = 0;
+    int chunk = 4;           // CH: samples of a ray shaded side by side (MF_HEAD_CHUNK = 2 | 4 | 8)
     int last_launches = 0;
     float misc_host[24] = {0};
     bool profile = false;  // CUDA events around k_head on the launching stream (bench roofline)
@@ -123,7 +145,7 @@ struct SetupParams {
     const __half *torso_const;
     const float *misc;
     float *state;
-    int *counters;
+    int *counters_next;       // the counter copy of this context's NEXT frame: zeroed here
     int A;
     int N;
     int smooth;
@@ -155,9 +177,70 @@ __device__ void conv1d_k3(const float *x, float *y, const __half *W, const __hal
 
 #define SETUP_THREADS 1024
 #define SETUP_FLOATS (8 * 64 * 16 + 8 * 32 * 8 + 8 * 32 + 8 + 48)
-struct SetupBatch { int n; SetupParams f[4]; };   // one CTA per frame of a batched render (HEAD_MAX_FRAMES)
+// ray pass (the CTAs of k_setup beyond the first n): one lane per ray
+struct RayPassFrame {
+    FrameGeom g;
+    int *hits, *counters;
+    float *rays_t, *fars, *nears, *weights_sum, *image;
+};
+struct SetupBatch {   // one audio CTA per frame of a batched render (HEAD_MAX_FRAMES) + the ray-pass CTAs
+    int n;
+    SetupParams f[4];
+    RayPassFrame r[4];
+    float bound, min_near, dt_gamma;
+    uint32_t max_steps, cascade, grid_size;
+    const uint8_t *bitfield;
+    float aabb[6];
+};
 __device__ __forceinline__ void setup_body(const SetupParams &p);
-__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ SetupBatch b) { setup_body(b.f[blockIdx.x]); }
+__device__ __forceinline__ void gen_ray(const FrameGeom &g, int idx, Ray &r);
+
+// The reference's round 0 (n_alive = N, n_step = 1) without its shading: which rays have a first sample, and where.
+// rays_t[ray] = t AT the first sample (march_next from there finds it again at once), fars[ray]; rays without a sample get
+// their final head result here (weights_sum = 0, image = 0).
+__device__ __forceinline__ void ray_pass(const SetupBatch &b, int cta, int n_ctas) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const MarchParams mp = make_march_params(b.bound, b.dt_gamma, b.max_steps, b.cascade, b.grid_size, b.bitfield);
+    for (int f = 0; f < b.n; f++) {
+        const RayPassFrame &fr = b.r[f];
+        const int n_tiles = (fr.g.N + 31) / 32;
+        for (int tile = cta * warps + warp; tile < n_tiles; tile += n_ctas * warps) {
+            const int ray = tile * 32 + lane;
+            const bool valid = ray < fr.g.N;
+            bool has = false;
+            float t = 0.f;
+            if (valid) {
+                Ray ry;
+                gen_ray(fr.g, ray, ry);
+                float near, far, x, y, z, dt;
+                uint32_t vox;
+                near_far_aabb(ry.ox, ry.oy, ry.oz, ry.dx, ry.dy, ry.dz, b.aabb, b.min_near, near, far);
+                t = near;
+                has = march_find(mp, ry, t, far, x, y, z, dt, vox);
+                fr.fars[ray] = far;
+                if (fr.nears) fr.nears[ray] = near;
+                if (has) {
+                    fr.rays_t[ray] = t;
+                } else {
+                    fr.weights_sum[ray] = 0.f;
+                    fr.image[ray * 3] = 0.f; fr.image[ray * 3 + 1] = 0.f; fr.image[ray * 3 + 2] = 0.f;
+                }
+            }
+            const uint32_t hm = __ballot_sync(0xffffffffu, has);
+            if (hm) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&fr.counters[CT_NHIT], __popc(hm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (has) fr.hits[base + __popc(hm & ((1u << lane) - 1u))] = ray;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ SetupBatch b) {
+    if ((int)blockIdx.x < b.n) setup_body(b.f[blockIdx.x]);
+    else ray_pass(b, (int)blockIdx.x - b.n, (int)gridDim.x - b.n);
+}
 __device__ __forceinline__ void setup_body(const SetupParams &p) {
     // the whole audio-net weight image (66 KB fp16) is staged in shared memory with coalesced 16-byte loads first: read straight
     // from global inside the dot-product loops, the 2-byte weight loads formed ~1000-long dependent latency chains per thread
@@ -176,10 +259,8 @@ __device__ __forceinline__ void setup_body(const SetupParams &p) {
         for (int i = tid; i < (p.audio_halfs * 2 + 15) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
 
-    // counters: round 0 has all N rays alive (renderer.py:240-241)
-    for (int i = tid; i < (ER_MAX_ROUNDS + 1) * ER_CTR_STRIDE; i += blockDim.x) p.counters[i] = 0;
-    __syncthreads();
-    if (tid == 0) p.counters[0] = p.N;
+    // the counters of this context's next frame (this frame's copy is being written by the ray-pass CTAs right now)
+    for (int i = tid; i < CT_INTS; i += blockDim.x) p.counters_next[i] = 0;
 
     // per-frame torso constants: enc_anchor = freq(wrapped_anchor, deg 3) (network.py:177), then the
     // contribution of [enc_anchor(42) | ind_code_torso(8)] to the first layer of both torso MLPs
@@ -316,23 +397,23 @@ __device__ __forceinline__ void load_a(uint32_t (&a)[4], const __half *tile, int
 // =========================================================================================
 // k_head
 // =========================================================================================
-#define HEAD_THREADS 256
+#define HEAD_THREADS 512
 #define HEAD_WARPS (HEAD_THREADS / 32)
 #define XS_STRIDE 56 /* enc_x tile row stride in halfs (48 + 8) */
 #define SH_STRIDE 24 /* SH tile row stride in halfs (16 + 8) */
 
-// per-frame part of the k_head arguments: one launch renders up to HEAD_MAX_FRAMES frames of DIFFERENT sessions (contexts loaded from the
-// same blob) -- the round structure (one grid barrier per march round, 3-4 tiles per warp and round for ONE frame, less than one in
-// the last round) leaves ~45 % of the warp-time waiting at the barriers (profiles/r01_k_head_v4_ncu_summary.md); the frames of a
-// batch share the barriers and fill each other's round tails
+// per-frame part of the k_head arguments: one launch renders up to HEAD_MAX_FRAMES frames of DIFFERENT sessions (contexts loaded
+// from the same blob); their hit lists form one queue, a warp's rays may belong to different frames
 #define HEAD_MAX_FRAMES 4
 struct HeadFrame {
     FrameGeom g;
     const float *state;  // enc_a at [0..31]
     float eye;
-    int *alive0, *alive1;
+    const int *hits;
     int *counters;
-    float *rays_t, *nears, *fars, *weights_sum, *image;
+    const float *rays_t, *fars;
+    float *weights_sum, *image;
+    float4 *snap;
 };
 
 struct HeadParams {
@@ -343,7 +424,6 @@ struct HeadParams {
     const __half *mlp_image;
     float bound, min_near, dt_gamma, T_thresh;
     uint32_t max_steps, cascade, grid_size;
-    float aabb[6];
     int n_frames;
     HeadFrame f[HEAD_MAX_FRAMES];
 };
@@ -352,8 +432,12 @@ struct HeadSmem {
     alignas(16) unsigned char mlp[ER_H_BYTES];
     alignas(16) __half xs[HEAD_WARPS][32 * XS_STRIDE];
     alignas(16) __half sh[HEAD_WARPS][32 * SH_STRIDE];
+    float ray[HEAD_WARPS][9][32];      // per lane: origin, direction, 1 / direction (kept across the passes of a ray)
     float enc_a[HEAD_MAX_FRAMES][32];
-    int rnd[HEAD_MAX_FRAMES][4];   // this round, per frame: n_alive (0 = frame finished), n_step, first tile, end tile (cumulative)
+    float eye[HEAD_MAX_FRAMES];
+    int end[HEAD_MAX_FRAMES];          // cumulative hit-list lengths
+    int hist[HEAD_MAX_FRAMES][ER_MAX_STEPS + 1];
+    int samples[HEAD_MAX_FRAMES];
     alignas(8) uint64_t bar;
 };
 
@@ -382,8 +466,9 @@ __device__ __forceinline__ void gen_ray(const FrameGeom &g, int idx, Ray &r) {
 
 // density + color for one 16-row tile (rows m*16..m*16+15 of the warp's 32-sample tile).
 // Returns in lane (t == 0): sigma logit of rows g / g+8; rgb in lanes t == 0 (r, g) and t == 1 (b).
-__device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, const float *enc_a, __half *xs, const __half *sh, int m, int lane,
-                                              float eye, float &sig_lo, float &sig_hi, float (&rgb)[4]) {
+// ea_lo / eye_lo belong to the frame of row g, ea_hi / eye_hi to that of row g + 8 (a tile may mix sessions).
+__device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, const float *ea_lo, const float *ea_hi, __half *xs, const __half *sh,
+                                              int m, int lane, float eye_lo, float eye_hi, float &sig_lo, float &sig_hi, float (&rgb)[4]) {
     const __half *W = reinterpret_cast<const __half *>(sm.mlp);
     const float *colbias = reinterpret_cast<const float *>(sm.mlp + ER_H_COLBIAS_BYTES);
     const int g = lane >> 2, t = lane & 3;
@@ -408,9 +493,8 @@ __device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, const float *e
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int col = (2 * j + h) * 8 + 2 * t;
-                const float e0 = enc_a[col], e1 = enc_a[col + 1];
-                aw[j][2 * h + 0] = pack_half2(e0 * round_half(c2[2 * j + h][0]), e1 * round_half(c2[2 * j + h][1]));
-                aw[j][2 * h + 1] = pack_half2(e0 * round_half(c2[2 * j + h][2]), e1 * round_half(c2[2 * j + h][3]));
+                aw[j][2 * h + 0] = pack_half2(ea_lo[col] * round_half(c2[2 * j + h][0]), ea_lo[col + 1] * round_half(c2[2 * j + h][1]));
+                aw[j][2 * h + 1] = pack_half2(ea_hi[col] * round_half(c2[2 * j + h][2]), ea_hi[col + 1] * round_half(c2[2 * j + h][3]));
             }
     }
     {   // eye_att = sigmoid(MLP(36 -> 16 -> 1)); e = eye * eye_att -> column 36 of the enc_x block
@@ -432,8 +516,8 @@ __device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, const float *e
         hi += __shfl_xor_sync(0xffffffffu, hi, 1);
         hi += __shfl_xor_sync(0xffffffffu, hi, 2);
         if (t == 0) {
-            xt[g * XS_STRIDE + 36] = __float2half_rn(eye * sigmoid16(round_half(lo)));
-            xt[(g + 8) * XS_STRIDE + 36] = __float2half_rn(eye * sigmoid16(round_half(hi)));
+            xt[g * XS_STRIDE + 36] = __float2half_rn(eye_lo * sigmoid16(round_half(lo)));
+            xt[(g + 8) * XS_STRIDE + 36] = __float2half_rn(eye_hi * sigmoid16(round_half(hi)));
         }
         __syncwarp();
         load_a(ax[2], xt, XS_STRIDE, 2, lane);
@@ -560,11 +644,15 @@ __device__ __forceinline__ void gather_planes(const HeadParams &p, float x, floa
     for (int i = 18; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
 }
 
-__global__ void __launch_bounds__(HEAD_THREADS, 2) k_head(const __grid_constant__ HeadParams p) {
+// CH = samples of a ray shaded side by side in one pass: lane = q * CH + k holds sample k of the warp's ray slot q (32 / CH slots).
+// The CH samples of a ray are independent until the compositor (the march never looks at sigma), exactly like the n_step samples
+// of a reference round (renderer.py:258-264); samples shaded beyond a ray's exit are discarded by the compositing recurrence.
+template <int CH>
+__global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant__ HeadParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     HeadSmem &sm = *reinterpret_cast<HeadSmem *>(smem_raw);
-    cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int F = p.n_frames;
 
     // stage the MLP image with one bulk TMA copy
     if (threadIdx.x == 0) {
@@ -575,178 +663,190 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) k_head(const __grid_constant_
     if (threadIdx.x == 0) {
         mbar_expect_tx(&sm.bar, ER_H_BYTES);
         bulk_g2s(sm.mlp, p.mlp_image, ER_H_BYTES, &sm.bar);
+        int end = 0;
+        for (int f = 0; f < HEAD_MAX_FRAMES; f++) {
+            if (f < F) { end += p.f[f].counters[CT_NHIT]; sm.eye[f] = p.f[f].eye; }
+            sm.end[f] = end;
+            sm.samples[f] = 0;
+        }
     }
-    if (threadIdx.x < 32 * p.n_frames) sm.enc_a[threadIdx.x >> 5][threadIdx.x & 31] = p.f[threadIdx.x >> 5].state[threadIdx.x & 31];
+    if (threadIdx.x < 32 * F) sm.enc_a[threadIdx.x >> 5][threadIdx.x & 31] = p.f[threadIdx.x >> 5].state[threadIdx.x & 31];
+    for (int i = threadIdx.x; i < HEAD_MAX_FRAMES * (ER_MAX_STEPS + 1); i += HEAD_THREADS) (&sm.hist[0][0])[i] = 0;
     mbar_wait(&sm.bar, 0);
     __syncthreads();
 
     const MarchParams mp = make_march_params(p.bound, p.dt_gamma, p.max_steps, p.cascade, p.grid_size, p.bitfield);
     __half *xs = sm.xs[warp];
     __half *sh = sm.sh[warp];
-    const int F = p.n_frames;
-    int *ticket = p.f[0].counters;   // the batch draws its tiles from ONE ticket per round (frame 0's counter row, slot 1)
+    float (*rs)[32] = sm.ray[warp];
+    const int total = sm.end[HEAD_MAX_FRAMES - 1];
+    int *ticket = &p.f[0].counters[CT_TICKET];   // the batch draws its rays from ONE queue (frame 0's ticket)
+    const int max_steps = (int)p.max_steps, cap = max_steps + (ER_SNAPS - 1);
 
-    uint32_t step_total = 0;   // marched steps so far, one byte per frame (<= 16 + 7)
-    for (int r = 0; r < ER_MAX_ROUNDS; r++) {
-        // ---- this round's shape per frame (renderer.py:246-256), published once per CTA
-        if (threadIdx.x == 0) {
-            int end = 0;
-            for (int f = 0; f < F; f++) {
-                int n_alive = ((volatile int *)p.f[f].counters)[r * ER_CTR_STRIDE + 0];
-                if (n_alive <= 0 || ((step_total >> (8 * f)) & 0xffu) >= p.max_steps) n_alive = 0;
-                const int n_step = n_alive > 0 ? max(min(p.f[f].g.N / n_alive, 8), 1) : 0;
-                // A tile is 32 SAMPLES, not 32 rays: R = 32 / n_step rays, lane = q * n_step + k holds sample k of ray q.  The n_step
-                // samples of a ray are independent until the compositor (the march never looks at sigma), so they are gathered and
-                // shaded side by side -- like the reference, which shades all n_alive * n_step samples of a round in one batch
-                // (renderer.py:258-264) -- and only the compositing recurrence runs in order.  The critical path of a frame drops
-                // from sum(n_step) = 16..23 sample latencies to one per round (measured: 2048 rays 0.42 ms, 262144 rays 0.62 ms).
-                const int R = n_alive > 0 ? 32 / n_step : 1;
-                sm.rnd[f][0] = n_alive; sm.rnd[f][1] = n_step; sm.rnd[f][2] = end;
-                end += n_alive > 0 ? (n_alive + R - 1) / R : 0;
-                sm.rnd[f][3] = end;
-                if (blockIdx.x == 0 && n_alive > 0) p.f[f].counters[r * ER_CTR_STRIDE + 3] = n_step;
-            }
-        }
-        __syncthreads();
-        const int n_tiles = sm.rnd[F - 1][3];
-        if (n_tiles == 0) break;
-        for (int f = 0; f < F; f++) step_total += (uint32_t)sm.rnd[f][1] << (8 * f);
+    const int k = lane % CH, lead = lane - k;    // sample inside the pass, first lane of the ray slot
+    // per-lane ray state (identical in the CH lanes of a slot)
+    int ray = -1, fi = 0, cnt = 0, sidx = -1;    // cnt = samples accumulated so far, sidx = snapshot slot once alive after max_steps
+    float t = 0.f, far = 0.f, ws = 0.f, cr = 0.f, cg_ = 0.f, cb = 0.f;
+    bool exhausted = total == 0;
 
-        while (true) {
-            int tile = 0;
-            if (lane == 0) tile = atomicAdd(&ticket[r * ER_CTR_STRIDE + 1], 1);
-            tile = __shfl_sync(0xffffffffu, tile, 0);
-            if (tile >= n_tiles) break;
-            int fi = 0;
-            while (tile >= sm.rnd[fi][3]) fi++;
-            const HeadFrame &fr = p.f[fi];
-            const int n_alive = sm.rnd[fi][0], n_step = sm.rnd[fi][1];
-            tile -= sm.rnd[fi][2];
-            const int R = 32 / n_step;
-            const int *alive_in = (r & 1) ? fr.alive1 : fr.alive0;
-            int *alive_out = (r & 1) ? fr.alive0 : fr.alive1;
-            const int q = lane / n_step, k = lane - q * n_step;   // ray inside the tile, sample inside the round
-            const int lead = q * n_step;                           // lane that owns the ray's state
-
-            const int slot = tile * R + q;
-            const bool valid = q < R && slot < n_alive;
-            int ray = 0;
-            Ray ry;
-            float t = 0.f, far = 0.f, ws = 0.f, cr = 0.f, cg_ = 0.f, cb = 0.f;
-            if (valid) {
-                ray = (r == 0) ? slot : alive_in[slot];
-                gen_ray(fr.g, ray, ry);
-                if (r == 0) {   // n_step == 1 in round 0 (N / N): every lane is its ray's leader
-                    float near;
-                    near_far_aabb(ry.ox, ry.oy, ry.oz, ry.dx, ry.dy, ry.dz, p.aabb, p.min_near, near, far);
-                    t = near;
-                    fr.fars[ray] = far;
-                    if (fr.nears) fr.nears[ray] = near;
-                } else {
+    while (true) {
+        // ---- refill the empty ray slots from the hit list
+        const uint32_t empty = __ballot_sync(0xffffffffu, ray < 0 && k == 0);
+        if (empty && !exhausted) {
+            const int need = __popc(empty);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(ticket, need);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((empty >> lead) & 1u) {
+                const int idx = base + __popc(empty & ((1u << lead) - 1u));
+                if (idx < total) {
+                    int f = 0;
+                    while (idx >= sm.end[f]) f++;
+                    const HeadFrame &fr = p.f[f];
+                    ray = fr.hits[idx - (f ? sm.end[f - 1] : 0)];
+                    fi = f;
                     t = fr.rays_t[ray];
                     far = fr.fars[ray];
-                    ws = fr.weights_sum[ray];
-                    cr = fr.image[ray * 3]; cg_ = fr.image[ray * 3 + 1]; cb = fr.image[ray * 3 + 2];
-                }
-                float shv[16];
-                sh4(ry.dx, ry.dy, ry.dz, shv);
+                    ws = cr = cg_ = cb = 0.f;
+                    cnt = 0;
+                    sidx = -1;
+                    Ray ry;
+                    gen_ray(fr.g, ray, ry);
+                    rs[0][lane] = ry.ox; rs[1][lane] = ry.oy; rs[2][lane] = ry.oz;
+                    rs[3][lane] = ry.dx; rs[4][lane] = ry.dy; rs[5][lane] = ry.dz;
+                    rs[6][lane] = ry.rdx; rs[7][lane] = ry.rdy; rs[8][lane] = ry.rdz;
+                    float shv[16];
+                    sh4(ry.dx, ry.dy, ry.dz, shv);
 #pragma unroll
-                for (int i = 0; i < 8; i++)
-                    *reinterpret_cast<uint32_t *>(sh + lane * SH_STRIDE + 2 * i) = pack_half2(shv[2 * i], shv[2 * i + 1]);
+                    for (int i = 0; i < 8; i++)
+                        *reinterpret_cast<uint32_t *>(sh + lane * SH_STRIDE + 2 * i) = pack_half2(shv[2 * i], shv[2 * i + 1]);
+                }
+            }
+            if (base + need >= total) exhausted = true;
+        }
+        const bool valid = ray >= 0;
+        if (!__any_sync(0xffffffffu, valid)) break;
+        const HeadFrame &fr = p.f[fi];
+
+        // ---- march to this lane's sample: k + 1 steps from the ray's t (the same sequence the reference marches)
+        float x = 0.f, y = 0.f, z = 0.f, dt = 0.f, tt = t;
+        bool has = valid && cnt + k < cap;
+        if (has) {
+            Ray ry;
+            ry.ox = rs[0][lane]; ry.oy = rs[1][lane]; ry.oz = rs[2][lane];
+            ry.dx = rs[3][lane]; ry.dy = rs[4][lane]; ry.dz = rs[5][lane];
+            ry.rdx = rs[6][lane]; ry.rdy = rs[7][lane]; ry.rdz = rs[8][lane];
+            uint32_t vox;
+            for (int j = 0; j <= k && has; j++) has = march_next(mp, ry, tt, far, x, y, z, dt, vox);
+        }
+        const uint32_t hasmask = __ballot_sync(0xffffffffu, has);
+        float sigma_logit = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (hasmask != 0u) {
+            // ---- tri-plane gather: 3 planes x 12 levels x 4 corners, fp32 (gridencoder.cu:75-175)
+            __half *row = xs + lane * XS_STRIDE;
+            if (has) {
+                if (p.hl.n_dense == 4) gather_planes<4>(p, x, y, z, row);
+                else gather_planes<-1>(p, x, y, z, row);
             } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) *reinterpret_cast<uint32_t *>(sh + lane * SH_STRIDE + 2 * i) = 0u;
+                for (int i = 0; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
             }
-
-            // ---- march to this lane's sample: k + 1 steps from the ray's t (the same sequence the reference marches)
-            float x = 0.f, y = 0.f, z = 0.f, dt = 0.f;
-            uint32_t vox;
-            bool has = valid;
-            for (int j = 0; j <= k && has; j++) has = march_next(mp, ry, t, far, x, y, z, dt, vox);
-            const uint32_t hasmask = __ballot_sync(0xffffffffu, has);
-            bool alive = false;
-            if (hasmask != 0u) {
-                // ---- tri-plane gather: 3 planes x 12 levels x 4 corners, fp32 (gridencoder.cu:75-175)
-                __half *row = xs + lane * XS_STRIDE;
-                if (has) {
-                    if (p.hl.n_dense == 4) gather_planes<4>(p, x, y, z, row);
-                    else gather_planes<-1>(p, x, y, z, row);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
-                }
-                __syncwarp();
-
-                // ---- MLPs on two 16-row tensor-core tiles; results routed back to lane == sample
-                float sigma_logit = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll 1
-                for (int m = 0; m < 2; m++) {
-                    if (((hasmask >> (16 * m)) & 0xffffu) == 0u) continue;
-                    float slo, shi, rgb[4];
-                    head_mlp_tile(sm, sm.enc_a[fi], xs, sh, m, lane, fr.eye, slo, shi, rgb);
-                    const int src0 = 4 * (lane & 7), src1 = src0 + 1;
-                    const float v_slo = __shfl_sync(0xffffffffu, slo, src0), v_shi = __shfl_sync(0xffffffffu, shi, src0);
-                    const float r_lo = __shfl_sync(0xffffffffu, rgb[0], src0), r_hi = __shfl_sync(0xffffffffu, rgb[2], src0);
-                    const float g_lo = __shfl_sync(0xffffffffu, rgb[1], src0), g_hi = __shfl_sync(0xffffffffu, rgb[3], src0);
-                    const float b_lo = __shfl_sync(0xffffffffu, rgb[0], src1), b_hi = __shfl_sync(0xffffffffu, rgb[2], src1);
-                    if ((lane >> 4) == m) {
-                        const bool hi = lane & 8;
-                        sigma_logit = hi ? v_shi : v_slo;
-                        c0 = hi ? r_hi : r_lo;
-                        c1 = hi ? g_hi : g_lo;
-                        c2 = hi ? b_hi : b_lo;
-                    }
-                }
-                __syncwarp();
-
-                // ---- composite (raymarching.cu:2189-2218): the recurrence over the ray's samples, in order; every lane of a ray
-                // replays it from the shuffled per-sample values (identical arithmetic), the leader keeps the result
-                const float my_alpha = has ? 1.0f - __expf(-expf(sigma_logit) * dt) : 0.f;   // torch.exp runs in fp32 under autocast
-                alive = valid;
-                for (int j = 0; j < n_step; j++) {
-                    const int src = min(lead + j, 31);
-                    const bool h_j = (hasmask >> src) & 1u;
-                    const float a_j = __shfl_sync(0xffffffffu, my_alpha, src);
-                    const float r_j = __shfl_sync(0xffffffffu, c0, src), g_j = __shfl_sync(0xffffffffu, c1, src);
-                    const float b_j = __shfl_sync(0xffffffffu, c2, src);
-                    if (alive) {
-                        if (!h_j) {
-                            alive = false;   // deltas[0] == 0 in the reference compositor: the ray ended
-                        } else {
-                            const float T = 1 - ws;
-                            const float weight = a_j * T;
-                            ws += weight;
-                            cr = fmaf(weight, r_j, cr);
-                            cg_ = fmaf(weight, g_j, cg_);
-                            cb = fmaf(weight, b_j, cb);
-                            if (T < p.T_thresh) alive = false;
-                        }
-                    }
-                }
-            }
-            // t after the ray's last sample of this round (lane lead + n_step - 1 marched all of them)
-            const float t_end = __shfl_sync(0xffffffffu, t, min(lead + n_step - 1, 31));
-            const bool leader = valid && k == 0;
-            alive = alive && leader;
-            if (leader) {
-                fr.weights_sum[ray] = ws;
-                fr.image[ray * 3] = cr; fr.image[ray * 3 + 1] = cg_; fr.image[ray * 3 + 2] = cb;
-                if (alive) fr.rays_t[ray] = t_end;
-            }
-            // ---- compaction (renderer.py:266), warp-aggregated
-            const uint32_t amask = __ballot_sync(0xffffffffu, alive);
-            if (amask) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&fr.counters[(r + 1) * ER_CTR_STRIDE + 0], __popc(amask));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (alive) alive_out[base + __popc(amask & ((1u << lane) - 1u))] = ray;
-            }
-            const int emitted = __popc(hasmask);
-            if (lane == 0 && emitted) atomicAdd(&fr.counters[r * ER_CTR_STRIDE + 2], emitted);
             __syncwarp();
+
+            // ---- MLPs on two 16-row tensor-core tiles; results routed back to lane == sample
+#pragma unroll 1
+            for (int m = 0; m < 2; m++) {
+                if (((hasmask >> (16 * m)) & 0xffffu) == 0u) continue;
+                const int g = lane >> 2;
+                const int f_lo = __shfl_sync(0xffffffffu, fi, m * 16 + g), f_hi = __shfl_sync(0xffffffffu, fi, m * 16 + g + 8);
+                float slo, shi, rgb[4];
+                head_mlp_tile(sm, sm.enc_a[f_lo], sm.enc_a[f_hi], xs, sh, m, lane, sm.eye[f_lo], sm.eye[f_hi], slo, shi, rgb);
+                const int src0 = 4 * (lane & 7), src1 = src0 + 1;
+                const float v_slo = __shfl_sync(0xffffffffu, slo, src0), v_shi = __shfl_sync(0xffffffffu, shi, src0);
+                const float r_lo = __shfl_sync(0xffffffffu, rgb[0], src0), r_hi = __shfl_sync(0xffffffffu, rgb[2], src0);
+                const float g_lo = __shfl_sync(0xffffffffu, rgb[1], src0), g_hi = __shfl_sync(0xffffffffu, rgb[3], src0);
+                const float b_lo = __shfl_sync(0xffffffffu, rgb[0], src1), b_hi = __shfl_sync(0xffffffffu, rgb[2], src1);
+                if ((lane >> 4) == m) {
+                    const bool hi = lane & 8;
+                    sigma_logit = hi ? v_shi : v_slo;
+                    c0 = hi ? r_hi : r_lo;
+                    c1 = hi ? g_hi : g_lo;
+                    c2 = hi ? b_hi : b_lo;
+                }
+            }
+            __syncwarp();
+            for (int f = 0; f < F; f++) {
+                const int c = __popc(__ballot_sync(0xffffffffu, has && fi == f));
+                if (lane == 0 && c) atomicAdd(&sm.samples[f], c);
+            }
         }
-        grid.sync();
+
+        // ---- composite (raymarching.cu:2189-2218): the recurrence over the ray's samples, in order; every lane of a slot
+        // replays it from the shuffled per-sample values (identical arithmetic), the slot's first lane writes
+        const float my_alpha = has ? 1.0f - __expf(-expf(sigma_logit) * dt) : 0.f;   // torch.exp runs in fp32 under autocast
+        bool done = !valid;
+        int life = max_steps;
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const int src = lead + j;
+            const bool h_j = (hasmask >> src) & 1u;
+            const float a_j = __shfl_sync(0xffffffffu, my_alpha, src);
+            const float r_j = __shfl_sync(0xffffffffu, c0, src), g_j = __shfl_sync(0xffffffffu, c1, src);
+            const float b_j = __shfl_sync(0xffffffffu, c2, src);
+            if (!done) {
+                if (cnt >= cap) {
+                    done = true;             // every sample a reference round structure could reach has been accumulated
+                } else if (!h_j) {
+                    done = true;             // deltas[0] == 0 in the reference compositor: the ray ran out of samples
+                    life = min(cnt, max_steps);
+                } else {
+                    const float T = 1 - ws;
+                    const float weight = a_j * T;
+                    ws += weight;
+                    cr = fmaf(weight, r_j, cr);
+                    cg_ = fmaf(weight, g_j, cg_);
+                    cb = fmaf(weight, b_j, cb);
+                    cnt++;
+                    if (T < p.T_thresh) {
+                        done = true;         // the ray is dropped AFTER this sample was accumulated
+                        life = min(cnt - 1, max_steps);
+                    }
+                    if (cnt >= max_steps && k == 0) {   // the states a later cut-off C = max_steps + j may select
+                        if (cnt == max_steps && !done) sidx = atomicAdd(&fr.counters[CT_NSURV], 1);
+                        if (sidx >= 0) fr.snap[(size_t)sidx * ER_SNAPS + (cnt - max_steps)] = make_float4(ws, cr, cg_, cb);
+                    }
+                }
+            }
+        }
+        if (!done && cnt >= cap) done = true;
+        // t after the ray's last sample of this pass (lane lead + CH - 1 marched all of them)
+        const float t_end = __shfl_sync(0xffffffffu, tt, lead + CH - 1);
+        if (valid) {
+            if (done) {
+                if (k == 0) {
+                    if (sidx >= 0) {
+                        for (int j = cnt - max_steps + 1; j < ER_SNAPS; j++)
+                            fr.snap[(size_t)sidx * ER_SNAPS + j] = make_float4(ws, cr, cg_, cb);
+                        fr.weights_sum[ray] = -(float)(sidx + 1);   // resolved by k_torso_compose once C is known
+                    } else {
+                        fr.weights_sum[ray] = ws;
+                        fr.image[ray * 3] = cr; fr.image[ray * 3 + 1] = cg_; fr.image[ray * 3 + 2] = cb;
+                    }
+                    atomicAdd(&sm.hist[fi][life], 1);
+                }
+                ray = -1;
+            } else {
+                t = t_end;
+            }
+        }
+        __syncwarp();
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < F * (ER_MAX_STEPS + 1); i += HEAD_THREADS) {
+        const int f = i / (ER_MAX_STEPS + 1), b = i % (ER_MAX_STEPS + 1);
+        if (sm.hist[f][b]) atomicAdd(&p.f[f].counters[CT_HIST + b], sm.hist[f][b]);
+    }
+    if (threadIdx.x < F && sm.samples[threadIdx.x]) atomicAdd(&p.f[threadIdx.x].counters[CT_SAMPLES], sm.samples[threadIdx.x]);
 }
 
 // =========================================================================================
@@ -766,7 +866,10 @@ struct TorsoParams {
     const __half *bg_color; // [N,3] or null (white)
     float thresh, shrink;
     int G;
-    const float *weights_sum, *image;
+    float *weights_sum, *image;   // head result per ray; rays alive after max_steps samples hold -(snapshot slot + 1) in weights_sum
+    const float4 *snap;
+    int *counters;          // this frame's counters: life histogram in, derived rounds out
+    int max_steps;
     float *out_f32;         // [N,3] or null
     uint8_t *out_u8;        // [N,3] or null
     uint8_t *dbg_mask;
@@ -798,6 +901,27 @@ __device__ __forceinline__ float grid_sample_ac(const float *img, int G, float x
 __global__ void __launch_bounds__(TORSO_THREADS) k_torso_compose(const __grid_constant__ TorsoParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TorsoSmem &sm = *reinterpret_cast<TorsoSmem *>(smem_raw);
+    // ---- the reference's loop control (renderer.py:246-256) replayed on the life histogram k_head filled:
+    // A(0) = N, A(c) = hits - #{rays with life < c}; round r starts at c_r with n_alive = A(c_r), n_step = clamp(N / n_alive, 1, 8);
+    // the summed n_step C selects the snapshot of the rays that were still alive after max_steps samples
+    __shared__ int s_snap;
+    if (threadIdx.x == 0) {
+        const int N = p.g.N, nhit = p.counters[CT_NHIT];
+        int c = 0, r = 0, gone = 0, upto = 1;
+        while (c < p.max_steps && r < ER_MAX_ROUNDS) {
+            for (; upto < c; upto++) gone += p.counters[CT_HIST + upto];
+            const int n_alive = c == 0 ? N : nhit - gone;
+            if (n_alive <= 0) break;
+            const int n_step = max(min(N / n_alive, 8), 1);
+            if (blockIdx.x == 0) {
+                int *row = p.counters + CT_ROUNDS + 4 * r;
+                row[0] = n_alive; row[1] = 0; row[2] = r == 0 ? nhit : -1; row[3] = n_step;
+            }
+            c += n_step;
+            r++;
+        }
+        s_snap = min(max(c - p.max_steps, 0), ER_SNAPS - 1);
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < ER_T_HALFS / 8; i += blockDim.x)
         reinterpret_cast<uint4 *>(sm.mlp)[i] = __ldg(reinterpret_cast<const uint4 *>(p.mlp_image) + i);
@@ -939,14 +1063,22 @@ __global__ void __launch_bounds__(TORSO_THREADS) k_torso_compose(const __grid_co
                 bg[2] = __half2float(p.bg_color[pix * 3 + 2]);
             }
             const float tc[3] = {tc0, tc1, tc2};
-            const float ws = p.weights_sum[pix];
+            float ws = p.weights_sum[pix];
+            float hd[3];
+            if (ws < 0.f) {   // alive after max_steps samples: the state after C samples
+                const float4 v = p.snap[(size_t)((int)(-ws) - 1) * ER_SNAPS + s_snap];
+                ws = v.x; hd[0] = v.y; hd[1] = v.z; hd[2] = v.w;
+                p.weights_sum[pix] = ws;
+                p.image[pix * 3] = hd[0]; p.image[pix * 3 + 1] = hd[1]; p.image[pix * 3 + 2] = hd[2];
+            } else {
+                hd[0] = p.image[pix * 3]; hd[1] = p.image[pix * 3 + 1]; hd[2] = p.image[pix * 3 + 2];
+            }
             float out[3];
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const float b = tc[k] * alpha + bg[k] * (1 - alpha);
-                const float head = p.image[pix * 3 + k];
-                out[k] = fminf(fmaxf(head + (1 - ws) * b, 0.f), 1.f);
-                if (p.dbg_image_head) p.dbg_image_head[pix * 3 + k] = head;
+                out[k] = fminf(fmaxf(hd[k] + (1 - ws) * b, 0.f), 1.f);
+                if (p.dbg_image_head) p.dbg_image_head[pix * 3 + k] = hd[k];
             }
             if (p.out_f32) { p.out_f32[pix * 3] = out[0]; p.out_f32[pix * 3 + 1] = out[1]; p.out_f32[pix * 3 + 2] = out[2]; }
             if (p.out_u8) {
@@ -1134,10 +1266,11 @@ extern "C" int mf_ernerf_blob_layout(int32_t *out, int n) {
 }
 
 static void ernerf_free_ws(ErnerfState *s) {
-    cudaFree(s->alive[0]); cudaFree(s->alive[1]); cudaFree(s->rays_t); cudaFree(s->fars); cudaFree(s->nears);
+    cudaFree(s->hits); cudaFree(s->snap); cudaFree(s->rays_t); cudaFree(s->fars);
     cudaFree(s->weights_sum); cudaFree(s->image); cudaFree(s->final_f32);
-    s->alive[0] = s->alive[1] = nullptr;
-    s->rays_t = s->fars = s->nears = s->weights_sum = s->image = s->final_f32 = nullptr;
+    s->hits = nullptr;
+    s->snap = nullptr;
+    s->rays_t = s->fars = s->weights_sum = s->image = s->final_f32 = nullptr;
     s->capN = 0;
 }
 
@@ -1156,6 +1289,8 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
     if (!ctx) return MF_E_INVALID;
     MF_REQUIRE(ctx, blob && cfg, "mf_ernerf_load: null blob/cfg");
     MF_REQUIRE(ctx, cfg->cascade == 1, "mf_ernerf_load: only cascade == 1 (bound <= 1) is implemented");
+    MF_REQUIRE(ctx, cfg->max_steps >= 1 && cfg->max_steps <= ER_MAX_STEPS, "mf_ernerf_load: max_steps %u outside 1..%d", cfg->max_steps,
+               ER_MAX_STEPS);
     MF_REQUIRE(ctx, cfg->audio_in_dim >= 1 && cfg->audio_in_dim <= 64, "mf_ernerf_load: audio_in_dim %u unsupported",
                cfg->audio_in_dim);
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1225,19 +1360,22 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
 
     MF_CUDA(ctx, cudaMalloc(&s->state, 128 * sizeof(float)));
     MF_CUDA(ctx, cudaMemset(s->state, 0, 128 * sizeof(float)));
-    MF_CUDA(ctx, cudaMalloc(&s->counters, (ER_MAX_ROUNDS + 1) * ER_CTR_STRIDE * sizeof(int)));
+    MF_CUDA(ctx, cudaMalloc(&s->counters, 2 * CT_INTS * sizeof(int)));
+    MF_CUDA(ctx, cudaMemset(s->counters, 0, 2 * CT_INTS * sizeof(int)));
 
-    MF_CUDA(ctx, cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
+    MF_CUDA(ctx, cudaFuncSetAttribute(k_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
+    MF_CUDA(ctx, cudaFuncSetAttribute(k_head<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
+    MF_CUDA(ctx, cudaFuncSetAttribute(k_head<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     MF_CUDA(ctx, cudaFuncSetAttribute(k_torso_compose, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(TorsoSmem)));
     int per_sm = 0;
-    MF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_head, HEAD_THREADS, sizeof(HeadSmem)));
+    MF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_head<4>, HEAD_THREADS, sizeof(HeadSmem)));
     MF_REQUIRE(ctx, per_sm >= 1, "k_head does not fit on an SM");
-    {   // experiment hook: MF_HEAD_CTAS_PER_SM=1 runs one CTA per SM (twice the tiles per warp and round, half the resident warps)
-        const char *e = getenv("MF_HEAD_CTAS_PER_SM");
-        if (e && atoi(e) >= 1) per_sm = std::min(per_sm, atoi(e));
+    {   // experiment hook: MF_HEAD_CHUNK = samples of a ray shaded side by side per pass (2, 4 or 8)
+        const char *e = getenv("MF_HEAD_CHUNK");
+        if (e && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8)) s->chunk = atoi(e);
     }
-    s->head_grid = per_sm * ctx->sm_count;
+    s->head_grid = ctx->sm_count;
     MF_CUDA(ctx, cudaDeviceSynchronize());
     return MF_OK;
 }
@@ -1267,12 +1405,10 @@ extern "C" int mf_ernerf_last_head_ms(mf_ctx *ctx, float *ms, int64_t *samples) 
     if (!s || !s->ev_head[0]) return mf_fail(ctx, MF_E_STATE, "profiling not enabled");
     MF_CUDA(ctx, cudaEventSynchronize(s->ev_head[1]));
     if (ms) MF_CUDA(ctx, cudaEventElapsedTime(ms, s->ev_head[0], s->ev_head[1]));
-    if (samples) {
-        int ctr[(ER_MAX_ROUNDS + 1) * ER_CTR_STRIDE];
-        MF_CUDA(ctx, cudaMemcpy(ctr, s->counters, sizeof(ctr), cudaMemcpyDeviceToHost));
-        int64_t tot = 0;
-        for (int r = 0; r <= ER_MAX_ROUNDS; r++) tot += ctr[r * ER_CTR_STRIDE + 2];
-        *samples = tot;
+    if (samples) {   // samples shaded by the last k_head launch for this context's frame
+        int v = 0;
+        MF_CUDA(ctx, cudaMemcpy(&v, s->counters + ((s->frame_no + 1) & 1u) * CT_INTS + CT_SAMPLES, sizeof(int), cudaMemcpyDeviceToHost));
+        *samples = v;
     }
     return MF_OK;
 }
@@ -1282,11 +1418,10 @@ extern "C" int mf_ernerf_last_launches(const mf_ctx *ctx) { return (ctx && ctx->
 static int ensure_ws(mf_ctx *ctx, ErnerfState *s, int N) {
     if (N <= s->capN) return MF_OK;
     ernerf_free_ws(s);
-    MF_CUDA(ctx, cudaMalloc(&s->alive[0], (size_t)N * 4));
-    MF_CUDA(ctx, cudaMalloc(&s->alive[1], (size_t)N * 4));
+    MF_CUDA(ctx, cudaMalloc(&s->hits, (size_t)N * 4));
+    MF_CUDA(ctx, cudaMalloc(&s->snap, (size_t)N * ER_SNAPS * sizeof(float4)));
     MF_CUDA(ctx, cudaMalloc(&s->rays_t, (size_t)N * 4));
     MF_CUDA(ctx, cudaMalloc(&s->fars, (size_t)N * 4));
-    MF_CUDA(ctx, cudaMalloc(&s->nears, (size_t)N * 4));
     MF_CUDA(ctx, cudaMalloc(&s->weights_sum, (size_t)N * 4));
     MF_CUDA(ctx, cudaMalloc(&s->image, (size_t)N * 12));
     MF_CUDA(ctx, cudaMalloc(&s->final_f32, (size_t)N * 12));
@@ -1375,7 +1510,8 @@ static int prepare_frame(mf_ctx *ctx, const mf_ernerf_frame *f, const mf_ernerf_
         }
     }
     sp.auds = f->auds; sp.enc_a_in = f->enc_a; sp.audio = s->audio; sp.torso_const = s->torso_const;
-    sp.misc = s->misc; sp.state = s->state; sp.counters = s->counters; sp.A = (int)s->cfg.audio_in_dim;
+    sp.misc = s->misc; sp.state = s->state; sp.counters_next = s->counters + ((s->frame_no + 1) & 1u) * CT_INTS;
+    sp.A = (int)s->cfg.audio_in_dim;
     sp.N = N; sp.smooth = (int)s->cfg.smooth_lips; sp.dbg_enc_a = dbg ? dbg->enc_a : nullptr;
     sp.audio_halfs = (int)s->audio_halfs;
     return MF_OK;
@@ -1396,19 +1532,37 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
         }
     }
     ErnerfState *s0 = pf[0].s;
+    const float bnd = s0->cfg.bound;  // renderer.py:86
+    const float aabb[6] = {-bnd, -bnd / 2, -bnd, bnd, bnd / 2, bnd};
+    int *ctr[HEAD_MAX_FRAMES];   // this frame's counter copy per context (zeroed by the context's previous frame)
+    for (int i = 0; i < n; i++) ctr[i] = pf[i].s->counters + (pf[i].s->frame_no & 1u) * CT_INTS;
     size_t setup_smem = 0;
     SetupBatch sb;
     sb.n = n;
+    long total_tiles = 0;
     for (int i = 0; i < n; i++) {
+        ErnerfState *s = pf[i].s;
         sb.f[i] = pf[i].sp;
-        setup_smem = std::max(setup_smem, SETUP_FLOATS * sizeof(float) + (pf[i].s->audio_halfs * 2 + 15) / 16 * 16);
+        setup_smem = std::max(setup_smem, SETUP_FLOATS * sizeof(float) + (s->audio_halfs * 2 + 15) / 16 * 16);
+        RayPassFrame &rp = sb.r[i];
+        rp.g = pf[i].g; rp.hits = s->hits; rp.counters = ctr[i]; rp.rays_t = s->rays_t; rp.fars = s->fars;
+        rp.nears = (i == 0 && dbg && dbg->nears) ? dbg->nears : nullptr;
+        rp.weights_sum = s->weights_sum; rp.image = s->image;
+        total_tiles += (pf[i].N + 31) / 32;
     }
+    sb.bound = s0->cfg.bound; sb.min_near = s0->cfg.min_near; sb.dt_gamma = s0->cfg.dt_gamma;
+    sb.max_steps = s0->cfg.max_steps; sb.cascade = s0->cfg.cascade; sb.grid_size = s0->cfg.grid_size;
+    sb.bitfield = s0->bitfield;
+    for (int i = 0; i < 6; i++) sb.aabb[i] = aabb[i];
     static mf_per_device_flag setup_attr;
     if (!setup_attr.test_and_set(ctx->device)) {
         MF_CUDA(ctx, cudaFuncSetAttribute(k_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     MF_REQUIRE(ctx, setup_smem <= 200 * 1024, "audio weight image too large for k_setup");
-    k_setup<<<n, SETUP_THREADS, setup_smem, stream>>>(sb);
+    {   // audio CTAs first, then the ray pass: one CTA (32 warps, one ray per lane) per SM that the audio CTAs leave free
+        const int ray_ctas = (int)std::max<long>(1, std::min<long>(ctx->sm_count - n, (total_tiles + SETUP_THREADS / 32 - 1) / (SETUP_THREADS / 32)));
+        k_setup<<<n + ray_ctas, SETUP_THREADS, setup_smem, stream>>>(sb);
+    }
     int launches = 1;
 
     HeadParams hp;
@@ -1416,26 +1570,21 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
     hp.mlp_image = s0->head_mlp;
     hp.bound = s0->cfg.bound; hp.min_near = s0->cfg.min_near; hp.dt_gamma = s0->cfg.dt_gamma; hp.T_thresh = s0->cfg.T_thresh;
     hp.max_steps = s0->cfg.max_steps; hp.cascade = s0->cfg.cascade; hp.grid_size = s0->cfg.grid_size;
-    const float b = s0->cfg.bound;  // renderer.py:86
-    const float aabb[6] = {-b, -b / 2, -b, b, b / 2, b};
-    for (int i = 0; i < 6; i++) hp.aabb[i] = aabb[i];
     hp.n_frames = n;
-    long total_tiles = 0;
     for (int i = 0; i < n; i++) {
         ErnerfState *s = pf[i].s;
         HeadFrame &hf = hp.f[i];
         hf.g = pf[i].g; hf.state = s->state; hf.eye = frames[i].eye;
-        hf.alive0 = s->alive[0]; hf.alive1 = s->alive[1]; hf.counters = s->counters;
-        hf.rays_t = s->rays_t; hf.nears = (i == 0 && dbg && dbg->nears) ? dbg->nears : nullptr;
-        hf.fars = s->fars; hf.weights_sum = s->weights_sum; hf.image = s->image;
-        total_tiles += (pf[i].N + 31) / 32;
+        hf.hits = s->hits; hf.counters = ctr[i];
+        hf.rays_t = s->rays_t; hf.fars = s->fars; hf.weights_sum = s->weights_sum; hf.image = s->image; hf.snap = s->snap;
     }
     {
-        void *args[] = {&hp};
-        const int grid = (int)std::min<long>(s0->head_grid, std::max<long>(1, total_tiles / HEAD_WARPS + 1));
+        // one CTA per SM; small ray counts (explicit-ray calls) get fewer CTAs: every CTA stages the 57 KB MLP image
+        const int grid = (int)std::min<long>(s0->head_grid, std::max<long>(1, (total_tiles * 32 + 255) / 256));
         if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[0], stream));
-        MF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_head, dim3(grid), dim3(HEAD_THREADS), args,
-                                                 sizeof(HeadSmem), stream));
+        if (s0->chunk == 2) k_head<2><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
+        else if (s0->chunk == 8) k_head<8><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
+        else k_head<4><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
         if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[1], stream));
         launches++;
     }
@@ -1449,6 +1598,7 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
         tp.g = pf[i].g; tp.tl = s->tl; tp.table = s->torso_table; tp.density = s->torso_density; tp.mlp_image = s->torso_mlp;
         tp.state = s->state; tp.bg_color = (const __half *)f->bg_color; tp.thresh = s->cfg.density_thresh_torso;
         tp.shrink = s->cfg.torso_shrink; tp.G = (int)s->cfg.grid_size; tp.weights_sum = s->weights_sum; tp.image = s->image;
+        tp.snap = s->snap; tp.counters = ctr[i]; tp.max_steps = (int)s->cfg.max_steps;
         tp.out_f32 = pf[i].resize ? s->final_f32 : f->out_image_f32;
         tp.out_u8 = pf[i].resize ? nullptr : outs[i];
         tp.dbg_mask = d ? d->torso_mask : nullptr;
@@ -1469,12 +1619,15 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
             if (d->weights_sum)
                 MF_CUDA(ctx, cudaMemcpyAsync(d->weights_sum, s->weights_sum, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
             if (d->round_info)
-                MF_CUDA(ctx, cudaMemcpy2DAsync(d->round_info, 4 * sizeof(int), s->counters, ER_CTR_STRIDE * sizeof(int),
-                                               4 * sizeof(int), ER_MAX_ROUNDS + 1, cudaMemcpyDeviceToDevice, stream));
+                MF_CUDA(ctx, cudaMemcpyAsync(d->round_info, ctr[i] + CT_ROUNDS, (ER_MAX_ROUNDS + 1) * 4 * sizeof(int),
+                                             cudaMemcpyDeviceToDevice, stream));
         }
     }
     MF_CUDA(ctx, cudaGetLastError());
-    for (int i = 0; i < n; i++) pf[i].s->last_launches = launches;
+    for (int i = 0; i < n; i++) {
+        pf[i].s->last_launches = launches;
+        pf[i].s->frame_no++;
+    }
     return MF_OK;
 }
 

@@ -189,10 +189,10 @@ struct Ray {
 };
 
 // body of the while-loop of kernel_march_rays (raymarching.cu:872-928): advance t until the
-// next occupied voxel; returns true and the sample (x, y, z, dt; t advanced past it), or false
-// once t >= far.
+// next occupied voxel; returns true with the sample (x, y, z, dt) and t AT the sample (not yet advanced), or false
+// once t >= far.  march_next = march_find + `t += dt`, the reference's own order of operations.
 template <bool FAST>
-__device__ __forceinline__ bool march_next_t(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
+__device__ __forceinline__ bool march_find_t(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
                                              float &y, float &z, float &dt_out, uint32_t &vox) {
     while (t < far) {
         x = clampf_(fmaf(t, r.dx, r.ox), -p.bound, p.bound);
@@ -220,7 +220,6 @@ __device__ __forceinline__ bool march_next_t(const MarchParams &p, const Ray &r,
         }
         const bool occ = __ldg(p.grid + index / 8) & (1 << (index % 8));
         if (occ) {
-            t += dt;
             dt_out = dt;
             vox = index;
             return true;
@@ -236,10 +235,23 @@ __device__ __forceinline__ bool march_next_t(const MarchParams &p, const Ray &r,
     return false;
 }
 
+template <bool FAST>
+__device__ __forceinline__ bool march_next_t(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
+                                             float &y, float &z, float &dt_out, uint32_t &vox) {
+    if (!march_find_t<FAST>(p, r, t, far, x, y, z, dt_out, vox)) return false;
+    t += dt_out;
+    return true;
+}
+
 __device__ __forceinline__ bool march_next(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
                                            float &y, float &z, float &dt_out, uint32_t &vox) {
     return p.fast ? march_next_t<true>(p, r, t, far, x, y, z, dt_out, vox)
                   : march_next_t<false>(p, r, t, far, x, y, z, dt_out, vox);
+}
+__device__ __forceinline__ bool march_find(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
+                                           float &y, float &z, float &dt_out, uint32_t &vox) {
+    return p.fast ? march_find_t<true>(p, r, t, far, x, y, z, dt_out, vox)
+                  : march_find_t<false>(p, r, t, far, x, y, z, dt_out, vox);
 }
 
 // shencoder.cu:43-68, degree 4
