@@ -1099,7 +1099,7 @@ def main():
                          "tensor_view_tflops": float(np.mean(bh_samples)) * FLOP_PER_SAMPLE / (float(np.mean(bh_ms)) * 1e-3) / 1e12}},
         "nerfasr_acoustic_model": asr,
         "gpu_launches": int(launches),
-        "kernels_per_step": ["k_setup", "k_head", "k_torso_compose"],
+        "kernels_per_step": ["k_setup (audio encoder CTA + ray pass + torso pass)", "k_head", "k_compose"],
         "clocks": sampler.result(),
         "roofline": {"kernel": "k_head", "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s",
                      "frac": ach_gbs / pk["hbm"], "traffic": traffic, "peak_source": pk["src"] + " burst",

@@ -49,6 +49,7 @@ using namespace ernerf;
 #define CT_TICKET 1   /* next unclaimed hit-list slot (k_head refill) */
 #define CT_SAMPLES 2  /* samples shaded by k_head */
 #define CT_NSURV 3    /* rays alive after max_steps samples = snapshot slots in use */
+#define CT_TTICKET 4  /* next unclaimed torso tile (k_head's tail filler) */
 #define CT_HIST 8     /* [ER_MAX_STEPS + 1] rays by life; bin max_steps = alive after max_steps samples */
 #define CT_ROUNDS 48  /* [ER_MAX_ROUNDS + 1][4] derived by k_torso_compose: n_alive, 0, samples emitted (round 0; -1 = not tracked), n_step */
 #define CT_INTS 128
@@ -98,7 +99,7 @@ struct ErnerfState {
     float *rays_t = nullptr, *fars = nullptr, *weights_sum = nullptr, *image = nullptr;
     float *final_f32 = nullptr;  // [N,3] when a resize follows
     int head_grid = 0;
-    int chunk = 4;           // CH: samples of a ray shaded side by side (MF_HEAD_CHUNK = 2 | 4 | 8)
+    int chunk = 2;           // CH: samples of a ray shaded side by side (MF_HEAD_CHUNK = 1 | 2 | 4 | 8; 2 measured best)
     int last_launches = 0;
     float misc_host[24] = {0};
     bool profile = false;  // CUDA events around k_head on the launching stream (bench roofline)
@@ -142,15 +143,12 @@ struct SetupParams {
     const float *auds;        // [8, A, 16] or null
     const float *enc_a_in;    // [32] or null
     const __half *audio;      // weights image
-    const __half *torso_const;
-    const float *misc;
     float *state;
     int *counters_next;       // the counter copy of this context's NEXT frame: zeroed here
     int A;
     int N;
     int smooth;
     int audio_halfs;          // size of the audio weight image (fp16 elements)
-    float wa[6];              // wrapped anchor (fp16-rounded), network.py:175-176
     float *dbg_enc_a;
 };
 
@@ -237,10 +235,7 @@ __device__ __forceinline__ void ray_pass(const SetupBatch &b, int cta, int n_cta
     }
 }
 
-__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ SetupBatch b) {
-    if ((int)blockIdx.x < b.n) setup_body(b.f[blockIdx.x]);
-    else ray_pass(b, (int)blockIdx.x - b.n, (int)gridDim.x - b.n);
-}
+// (the k_setup kernel itself is defined after the torso pass below)
 __device__ __forceinline__ void setup_body(const SetupParams &p) {
     // the whole audio-net weight image (66 KB fp16) is staged in shared memory with coalesced 16-byte loads first: read straight
     // from global inside the dot-product loops, the 2-byte weight loads formed ~1000-long dependent latency chains per thread
@@ -250,7 +245,6 @@ __device__ __forceinline__ void setup_body(const SetupParams &p) {
     float *bufB = bufA + 8 * 64 * 16;
     float *enc = bufB + 8 * 32 * 8;
     float *att = enc + 8 * 32;
-    float *anchor = att + 8;
     __half *w_sm = reinterpret_cast<__half *>(bufA + SETUP_FLOATS);
     const int tid = threadIdx.x;
     if (!p.enc_a_in) {
@@ -261,19 +255,6 @@ __device__ __forceinline__ void setup_body(const SetupParams &p) {
 
     // the counters of this context's next frame (this frame's copy is being written by the ray-pass CTAs right now)
     for (int i = tid; i < CT_INTS; i += blockDim.x) p.counters_next[i] = 0;
-
-    // per-frame torso constants: enc_anchor = freq(wrapped_anchor, deg 3) (network.py:177), then the
-    // contribution of [enc_anchor(42) | ind_code_torso(8)] to the first layer of both torso MLPs
-    if (tid < 42) anchor[tid] = freq_elem(p.wa, 6, tid);
-    __syncthreads();
-    if (tid < 64) {
-        const int which = tid / 32, n = tid % 32;
-        const __half *Wc = p.torso_const + (which * 32 + n) * 50;
-        float acc = 0.f;
-        for (int k = 0; k < 42; k++) acc = fmaf(__half2float(Wc[k]), round_half(anchor[k]), acc);
-        for (int k = 0; k < 8; k++) acc = fmaf(__half2float(Wc[42 + k]), round_half(p.misc[16 + k]), acc);
-        p.state[64 + which * 32 + n] = acc;
-    }
 
     if (p.enc_a_in) {  // pre-encoded feature: no EMA, no state update
         if (tid < 32) {
@@ -395,9 +376,199 @@ __device__ __forceinline__ void load_a(uint32_t (&a)[4], const __half *tile, int
 }
 
 // =========================================================================================
+// torso tiles (run by k_head's warps once they are out of rays) and k_compose
+// =========================================================================================
+#define TX_STRIDE 88 /* torso_net input tile: [feat 32 | freq 34 | pad] = 80 + 8 */
+
+struct TorsoModel {   // shared by the frames of a batch
+    TorsoLevels tl;
+    const __half2 *table;
+    const float *density;    // [G*G]
+    const __half *mlp_image, *torso_const;
+    const float *misc;
+    float thresh, shrink;
+    int G;
+};
+struct TorsoFrame {
+    const __half *bg_color;  // [N,3] or null (white)
+    uint8_t *dbg_mask;
+    float wa[6];             // wrapped anchor (fp16-rounded), network.py:175-176
+};
+
+// F.grid_sample(bilinear, zeros padding, align_corners=True) on a [G, G] image (renderer.py:326)
+__device__ __forceinline__ float grid_sample_ac(const float *img, int G, float x, float y) {
+    const float ix = ((x + 1.f) / 2) * (G - 1), iy = ((y + 1.f) / 2) * (G - 1);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    const float nw = ((fx + 1) - ix) * ((fy + 1) - iy), ne = (ix - fx) * ((fy + 1) - iy);
+    const float sw = ((fx + 1) - ix) * (iy - fy), se = (ix - fx) * (iy - fy);
+    auto at = [&](int yy, int xx) { return (xx >= 0 && xx < G && yy >= 0 && yy < G) ? __ldg(img + yy * G + xx) : 0.f; };
+    float out = 0.f;
+    out = fmaf(at(y0, x0), nw, out);
+    out = fmaf(at(y0, x1), ne, out);
+    out = fmaf(at(y1, x0), sw, out);
+    out = fmaf(at(y1, x1), se, out);
+    return out;
+}
+
+// torso occupancy + deformation + tiled grid + MLPs (network.py:166-201, renderer.py:294-344) for one tile of 32 pixels;
+// returns this lane's pixel's bgc = torso_color * torso_alpha + bg * (1 - torso_alpha).  mlp / bias: shared-memory torso MLP
+// image and the frame's first-layer constants; xt: the warp's [32][TX_STRIDE] activation tile.
+__device__ __forceinline__ void torso_tile(const TorsoModel &tm, const FrameGeom &g, const TorsoFrame &tf, int tile, int lane,
+                                           __half *xt, const __half *mlp, const float *bias, float (&bgc)[3]) {
+    const int N = g.N;
+    const int t = lane & 3;
+const int pix = tile * 32 + lane;
+const bool valid = pix < N;
+float c0 = 0.f, c1 = 0.f;  // bg_coords: c0 runs over image rows (utils.py:246-251)
+if (valid) {
+    if (g.bg_coords) {
+        c0 = g.bg_coords[pix * 2];
+        c1 = g.bg_coords[pix * 2 + 1];
+    } else {
+        const int row = pix / g.W, col = pix - row * g.W;
+        c0 = ((float)row * g.inv_Hm1) * 2 - 1;
+        c1 = ((float)col * g.inv_Wm1) * 2 - 1;
+    }
+}
+const bool masked = valid && (grid_sample_ac(tm.density, tm.G, c0, c1) > tm.thresh);
+const uint32_t mmask = __ballot_sync(0xffffffffu, masked);
+float alpha = 0.f, tc0 = 0.f, tc1 = 0.f, tc2 = 0.f;
+
+if (mmask) {
+    // x * torso_shrink -> freq(deg 8) 34 values -> cols 32..65 of the tile (cols 66..79 zero)
+    const float xin[2] = {c0 * tm.shrink, c1 * tm.shrink};
+    __half *row = xt + lane * TX_STRIDE;
+#pragma unroll
+    for (int c = 0; c < 34; c += 2)
+        *reinterpret_cast<uint32_t *>(row + 32 + c) =
+            masked ? pack_half2(freq_elem(xin, 2, c), freq_elem(xin, 2, c + 1)) : 0u;
+#pragma unroll
+    for (int c = 66; c < 80; c += 2) *reinterpret_cast<uint32_t *>(row + c) = 0u;
+    __syncwarp();
+
+    float dxy[2] = {0.f, 0.f};
+#pragma unroll 1
+    for (int m = 0; m < 2; m++) {
+        if (((mmask >> (16 * m)) & 0xffffu) == 0u) continue;
+        // torso_deform_net: [freq 34 (+ constants as bias)] -> 32 -> 32 -> 2
+        uint32_t a3[3][4];
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++) load_a(a3[kk], xt + m * 16 * TX_STRIDE + 32, TX_STRIDE, kk, lane);
+        float c[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            c[nt][0] = c[nt][2] = bias[nt * 8 + 2 * t];
+            c[nt][1] = c[nt][3] = bias[nt * 8 + 2 * t + 1];
+        }
+        mlp_layer<3, 4, 56>(c, a3, mlp + ER_T_DEF1, lane);
+        uint32_t ah[2][4];
+        acc_to_a<4, true>(c, ah);
+        zero_acc(c);
+        mlp_layer<2, 4, 40>(c, ah, mlp + ER_T_DEF2, lane);
+        acc_to_a<4, true>(c, ah);
+        float cd[1][4];
+        zero_acc(cd);
+        mlp_layer<2, 1, 40>(cd, ah, mlp + ER_T_DEF3, lane);
+        // dx (cols 0, 1) lives in lanes t == 0
+        const int src0 = 4 * (lane & 7);
+        const float d0lo = __shfl_sync(0xffffffffu, cd[0][0], src0), d1lo = __shfl_sync(0xffffffffu, cd[0][1], src0);
+        const float d0hi = __shfl_sync(0xffffffffu, cd[0][2], src0), d1hi = __shfl_sync(0xffffffffu, cd[0][3], src0);
+        if ((lane >> 4) == m) {
+            dxy[0] = round_half((lane & 8) ? d0hi : d0lo);
+            dxy[1] = round_half((lane & 8) ? d1hi : d1lo);
+        }
+    }
+    // x = clamp(x + dx, -1, 1); tiled grid on (x + 1) / 2 (network.py:188-190), fp16 table
+    if (masked) {
+        const float u = (clampf_(xin[0] + dxy[0], -1.f, 1.f) + 1.f) * 0.5f;
+        const float v = (clampf_(xin[1] + dxy[1], -1.f, 1.f) + 1.f) * 0.5f;
+#pragma unroll
+        for (int l = 0; l < MF_ERNERF_TORSO_LEVELS; l++) {
+            float o0, o1;
+            if (tm.tl.n_dense < 0) grid_level_f16x2<IDX_ANY>(tm.table, tm.tl.lv[l], u, v, o0, o1);
+            else if (l < tm.tl.n_dense) grid_level_f16x2<IDX_DENSE>(tm.table, tm.tl.lv[l], u, v, o0, o1);
+            else grid_level_f16x2<IDX_TILE2>(tm.table, tm.tl.lv[l], u, v, o0, o1);
+            *reinterpret_cast<uint32_t *>(row + 2 * l) = pack_half2(o0, o1);
+        }
+    } else {
+#pragma unroll
+        for (int l = 0; l < 16; l++) *reinterpret_cast<uint32_t *>(row + 2 * l) = 0u;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int m = 0; m < 2; m++) {
+        if (((mmask >> (16 * m)) & 0xffffu) == 0u) continue;
+        // torso_net: [feat 32 | freq 34 (+ constants as bias)] -> 32 -> 32 -> 4
+        uint32_t a5[5][4];
+#pragma unroll
+        for (int kk = 0; kk < 5; kk++) load_a(a5[kk], xt + m * 16 * TX_STRIDE, TX_STRIDE, kk, lane);
+        float c[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            c[nt][0] = c[nt][2] = bias[32 + nt * 8 + 2 * t];
+            c[nt][1] = c[nt][3] = bias[32 + nt * 8 + 2 * t + 1];
+        }
+        mlp_layer<5, 4, 88>(c, a5, mlp + ER_T_TOR1, lane);
+        uint32_t ah[2][4];
+        acc_to_a<4, true>(c, ah);
+        zero_acc(c);
+        mlp_layer<2, 4, 40>(c, ah, mlp + ER_T_TOR2, lane);
+        acc_to_a<4, true>(c, ah);
+        float co[1][4];
+        zero_acc(co);
+        mlp_layer<2, 1, 40>(co, ah, mlp + ER_T_TOR3, lane);
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = affine16(sigmoid16(round_half(co[0][i])));
+        // cols: 0 alpha, 1..3 color -> lanes t == 0 hold (alpha, r), t == 1 hold (g, b)
+        const int src0 = 4 * (lane & 7), src1 = src0 + 1;
+        const float a_lo = __shfl_sync(0xffffffffu, o[0], src0), a_hi = __shfl_sync(0xffffffffu, o[2], src0);
+        const float r_lo = __shfl_sync(0xffffffffu, o[1], src0), r_hi = __shfl_sync(0xffffffffu, o[3], src0);
+        const float g_lo = __shfl_sync(0xffffffffu, o[0], src1), g_hi = __shfl_sync(0xffffffffu, o[2], src1);
+        const float b_lo = __shfl_sync(0xffffffffu, o[1], src1), b_hi = __shfl_sync(0xffffffffu, o[3], src1);
+        if ((lane >> 4) == m && masked) {
+            const bool hi = lane & 8;
+            alpha = hi ? a_hi : a_lo;
+            tc0 = hi ? r_hi : r_lo;
+            tc1 = hi ? g_hi : g_lo;
+            tc2 = hi ? b_hi : b_lo;
+        }
+    }
+    __syncwarp();
+}
+
+    if (valid) {
+        // renderer.py:344 bg = torso_color * torso_alpha + bg * (1 - torso_alpha)
+        float bg[3] = {1.f, 1.f, 1.f};
+        if (tf.bg_color) {
+            bg[0] = __half2float(tf.bg_color[pix * 3]);
+            bg[1] = __half2float(tf.bg_color[pix * 3 + 1]);
+            bg[2] = __half2float(tf.bg_color[pix * 3 + 2]);
+        }
+        const float tc[3] = {tc0, tc1, tc2};
+#pragma unroll
+        for (int k = 0; k < 3; k++) bgc[k] = tc[k] * alpha + bg[k] * (1 - alpha);
+        if (tf.dbg_mask) tf.dbg_mask[pix] = masked ? 1 : 0;
+    }
+}
+
+// per-frame torso constants: enc_anchor = freq(wrapped_anchor, deg 3) (network.py:177), then the contribution of
+// [enc_anchor(42) | ind_code_torso(8)] to the first layer of both torso MLPs; called by threads 0..63 after `anchor` is filled
+__device__ __forceinline__ float torso_bias_elem(const __half *tconst_sm, const float *anchor_sm, const float *misc, int n) {
+    const __half *Wc = tconst_sm + n * 50;
+    float acc = 0.f;
+    for (int k = 0; k < 42; k++) acc = fmaf(__half2float(Wc[k]), round_half(anchor_sm[k]), acc);
+    for (int k = 0; k < 8; k++) acc = fmaf(__half2float(Wc[42 + k]), round_half(__ldg(misc + 16 + k)), acc);
+    return acc;
+}
+
+// =========================================================================================
 // k_head
 // =========================================================================================
+#ifndef HEAD_THREADS
 #define HEAD_THREADS 512
+#endif
 #define HEAD_WARPS (HEAD_THREADS / 32)
 #define XS_STRIDE 56 /* enc_x tile row stride in halfs (48 + 8) */
 #define SH_STRIDE 24 /* SH tile row stride in halfs (16 + 8) */
@@ -428,11 +599,15 @@ struct HeadParams {
     HeadFrame f[HEAD_MAX_FRAMES];
 };
 
+struct HeadWarpSmem {   // one per warp
+    alignas(16) __half xs[32 * XS_STRIDE];
+    alignas(16) __half sh[32 * SH_STRIDE];
+    float ray[9][32];                  // per lane: origin, direction, 1 / direction (kept across the passes of a ray)
+};
+
 struct HeadSmem {
     alignas(16) unsigned char mlp[ER_H_BYTES];
-    alignas(16) __half xs[HEAD_WARPS][32 * XS_STRIDE];
-    alignas(16) __half sh[HEAD_WARPS][32 * SH_STRIDE];
-    float ray[HEAD_WARPS][9][32];      // per lane: origin, direction, 1 / direction (kept across the passes of a ray)
+    alignas(16) HeadWarpSmem w[HEAD_WARPS];
     float enc_a[HEAD_MAX_FRAMES][32];
     float eye[HEAD_MAX_FRAMES];
     int end[HEAD_MAX_FRAMES];          // cumulative hit-list lengths
@@ -595,14 +770,16 @@ __device__ __forceinline__ void grid_level_prep(const GridLevel &lv, float u, fl
 #define ER_GATHER_LEVELS 3   /* levels gathered together: 3 measured; must divide 12 */
 #endif
 template <int ND>
-__device__ __forceinline__ void gather_planes(const HeadParams &p, float x, float y, float z, __half *row) {
+__device__ __forceinline__ void gather_planes_t(const HeadParams &p, float x, float y, float z, __half *row) {
     constexpr int GL = ER_GATHER_LEVELS;
     const float rb = 1.0f / (2.0f * p.bound);
-    const float u[3] = {(x + p.bound) * rb, (y + p.bound) * rb, (z + p.bound) * rb};
-#pragma unroll
+    const float u0 = (x + p.bound) * rb, u1 = (y + p.bound) * rb, u2 = (z + p.bound) * rb;
+    // the plane loop is NOT unrolled: fully unrolled, k_head was 168 KB of SASS and its top stall was instruction fetch
+    // ("no_instruction" 2.0 per issue, profiles/r02_k_head_v5_ncu_summary.md)
+#pragma unroll 1
     for (int pl = 0; pl < 3; pl++) {
-        const float a = (pl == 1) ? u[1] : u[0];
-        const float b = (pl == 0) ? u[1] : u[2];
+        const float a = (pl == 1) ? u1 : u0;
+        const float b = (pl == 0) ? u1 : u2;
         const float *tab = p.planes + (size_t)pl * p.plane_rows;
         float f[12];
         if (ND < 0) {
@@ -644,6 +821,11 @@ __device__ __forceinline__ void gather_planes(const HeadParams &p, float x, floa
     for (int i = 18; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
 }
 
+// any other level structure than the shipped one (4 dense + 8 hashed levels): kept out of line, off the hot code path
+__device__ __noinline__ void gather_planes_generic(const HeadParams &p, float x, float y, float z, __half *row) {
+    gather_planes_t<-1>(p, x, y, z, row);
+}
+
 // CH = samples of a ray shaded side by side in one pass: lane = q * CH + k holds sample k of the warp's ray slot q (32 / CH slots).
 // The CH samples of a ray are independent until the compositor (the march never looks at sigma), exactly like the n_step samples
 // of a reference round (renderer.py:258-264); samples shaded beyond a ray's exit are discarded by the compositing recurrence.
@@ -676,9 +858,9 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
     __syncthreads();
 
     const MarchParams mp = make_march_params(p.bound, p.dt_gamma, p.max_steps, p.cascade, p.grid_size, p.bitfield);
-    __half *xs = sm.xs[warp];
-    __half *sh = sm.sh[warp];
-    float (*rs)[32] = sm.ray[warp];
+    __half *xs = sm.w[warp].xs;
+    __half *sh = sm.w[warp].sh;
+    float (*rs)[32] = sm.w[warp].ray;
     const int total = sm.end[HEAD_MAX_FRAMES - 1];
     int *ticket = &p.f[0].counters[CT_TICKET];   // the batch draws its rays from ONE queue (frame 0's ticket)
     const int max_steps = (int)p.max_steps, cap = max_steps + (ER_SNAPS - 1);
@@ -745,8 +927,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
             // ---- tri-plane gather: 3 planes x 12 levels x 4 corners, fp32 (gridencoder.cu:75-175)
             __half *row = xs + lane * XS_STRIDE;
             if (has) {
-                if (p.hl.n_dense == 4) gather_planes<4>(p, x, y, z, row);
-                else gather_planes<-1>(p, x, y, z, row);
+                if (p.hl.n_dense == 4) gather_planes_t<4>(p, x, y, z, row);
+                else gather_planes_generic(p, x, y, z, row);
             } else {
 #pragma unroll
                 for (int i = 0; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
@@ -849,56 +1031,36 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
     if (threadIdx.x < F && sm.samples[threadIdx.x]) atomicAdd(&p.f[threadIdx.x].counters[CT_SAMPLES], sm.samples[threadIdx.x]);
 }
 
-// =========================================================================================
-// k_torso_compose
-// =========================================================================================
-#define TORSO_THREADS 256
-#define TORSO_WARPS (TORSO_THREADS / 32)
-#define TX_STRIDE 88 /* torso_net input tile: [feat 32 | freq 34 | pad] = 80 + 8 */
-
-struct TorsoParams {
-    FrameGeom g;
-    TorsoLevels tl;
-    const __half2 *table;
-    const float *density;   // [G*G]
-    const __half *mlp_image;
-    const float *state;     // bias_def at [64..95], bias_tor at [96..127]
-    const __half *bg_color; // [N,3] or null (white)
-    float thresh, shrink;
-    int G;
-    float *weights_sum, *image;   // head result per ray; rays alive after max_steps samples hold -(snapshot slot + 1) in weights_sum
-    const float4 *snap;
-    int *counters;          // this frame's counters: life histogram in, derived rounds out
-    int max_steps;
-    float *out_f32;         // [N,3] or null
-    uint8_t *out_u8;        // [N,3] or null
-    uint8_t *dbg_mask;
-    float *dbg_image_head;
-};
-
-struct TorsoSmem {
-    alignas(16) __half mlp[ER_T_HALFS];
-    alignas(16) __half xt[TORSO_WARPS][32 * TX_STRIDE];
-    float bias[64];
-};
-
-// F.grid_sample(bilinear, zeros padding, align_corners=True) on a [G, G] image (renderer.py:326)
-__device__ __forceinline__ float grid_sample_ac(const float *img, int G, float x, float y) {
-    const float ix = ((x + 1.f) / 2) * (G - 1), iy = ((y + 1.f) / 2) * (G - 1);
-    const float fx = floorf(ix), fy = floorf(iy);
-    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
-    const float nw = ((fx + 1) - ix) * ((fy + 1) - iy), ne = (ix - fx) * ((fy + 1) - iy);
-    const float sw = ((fx + 1) - ix) * (iy - fy), se = (ix - fx) * (iy - fy);
-    auto at = [&](int yy, int xx) { return (xx >= 0 && xx < G && yy >= 0 && yy < G) ? __ldg(img + yy * G + xx) : 0.f; };
-    float out = 0.f;
-    out = fmaf(at(y0, x0), nw, out);
-    out = fmaf(at(y0, x1), ne, out);
-    out = fmaf(at(y1, x0), sw, out);
-    out = fmaf(at(y1, x1), se, out);
-    return out;
+__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ SetupBatch b) {
+    if ((int)blockIdx.x < b.n) setup_body(b.f[blockIdx.x]);
+    else ray_pass(b, (int)blockIdx.x - b.n, (int)gridDim.x - b.n);
 }
 
-__global__ void __launch_bounds__(TORSO_THREADS) k_torso_compose(const __grid_constant__ TorsoParams p) {
+// torso + final compose (renderer.py:275-277,294-352): resolve the loop control, torso over background,
+// image + (1 - weights_sum) * bg, clamp, fp32 / u8
+#define TORSO_THREADS 256
+#define TORSO_WARPS (TORSO_THREADS / 32)
+struct ComposeParams {
+    FrameGeom g;
+    TorsoModel tm;
+    TorsoFrame tf;
+    float *weights_sum, *image;   // head result per ray; rays alive after max_steps samples hold -(snapshot slot + 1) in weights_sum
+    const float4 *snap;
+    int *counters;                // this frame's counters: life histogram in, derived rounds out
+    int max_steps;
+    float *out_f32;               // [N,3] or null
+    uint8_t *out_u8;              // [N,3] or null
+    float *dbg_image_head;
+};
+struct TorsoSmem {
+    alignas(16) __half mlp[ER_T_HALFS];
+    alignas(16) __half tconst[2 * 32 * 50];
+    alignas(16) __half xt[TORSO_WARPS][32 * TX_STRIDE];
+    float bias[64];
+    float anchor[48];
+};
+
+__global__ void __launch_bounds__(TORSO_THREADS) k_torso_compose(const __grid_constant__ ComposeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TorsoSmem &sm = *reinterpret_cast<TorsoSmem *>(smem_raw);
     // ---- the reference's loop control (renderer.py:246-256) replayed on the life histogram k_head filled:
@@ -924,169 +1086,43 @@ __global__ void __launch_bounds__(TORSO_THREADS) k_torso_compose(const __grid_co
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < ER_T_HALFS / 8; i += blockDim.x)
-        reinterpret_cast<uint4 *>(sm.mlp)[i] = __ldg(reinterpret_cast<const uint4 *>(p.mlp_image) + i);
-    if (threadIdx.x < 64) sm.bias[threadIdx.x] = p.state[64 + threadIdx.x];
+        reinterpret_cast<uint4 *>(sm.mlp)[i] = __ldg(reinterpret_cast<const uint4 *>(p.tm.mlp_image) + i);
+    for (int i = threadIdx.x; i < 2 * 32 * 50 / 8; i += blockDim.x)
+        reinterpret_cast<uint4 *>(sm.tconst)[i] = __ldg(reinterpret_cast<const uint4 *>(p.tm.torso_const) + i);
+    if (threadIdx.x < 42) sm.anchor[threadIdx.x] = freq_elem(p.tf.wa, 6, threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x < 64) sm.bias[threadIdx.x] = torso_bias_elem(sm.tconst, sm.anchor, p.tm.misc, threadIdx.x);
     __syncthreads();
 
     const int N = p.g.N;
     const int n_tiles = (N + 31) / 32;
-    __half *xt = sm.xt[warp];
-    const int g = lane >> 2, t = lane & 3;
-
     for (int tile = blockIdx.x * TORSO_WARPS + warp; tile < n_tiles; tile += gridDim.x * TORSO_WARPS) {
+        float b[3] = {0.f, 0.f, 0.f};
+        torso_tile(p.tm, p.g, p.tf, tile, lane, sm.xt[warp], sm.mlp, sm.bias, b);
+        __syncwarp();
         const int pix = tile * 32 + lane;
-        const bool valid = pix < N;
-        float c0 = 0.f, c1 = 0.f;  // bg_coords: c0 runs over image rows (utils.py:246-251)
-        if (valid) {
-            if (p.g.bg_coords) {
-                c0 = p.g.bg_coords[pix * 2];
-                c1 = p.g.bg_coords[pix * 2 + 1];
-            } else {
-                const int row = pix / p.g.W, col = pix - row * p.g.W;
-                c0 = ((float)row * p.g.inv_Hm1) * 2 - 1;
-                c1 = ((float)col * p.g.inv_Wm1) * 2 - 1;
-            }
+        if (pix >= N) continue;
+        float ws = p.weights_sum[pix];
+        float hd[3];
+        if (ws < 0.f) {   // alive after max_steps samples: the state after C samples
+            const float4 v = p.snap[(size_t)((int)(-ws) - 1) * ER_SNAPS + s_snap];
+            ws = v.x; hd[0] = v.y; hd[1] = v.z; hd[2] = v.w;
+            p.weights_sum[pix] = ws;
+            p.image[pix * 3] = hd[0]; p.image[pix * 3 + 1] = hd[1]; p.image[pix * 3 + 2] = hd[2];
+        } else {
+            hd[0] = p.image[pix * 3]; hd[1] = p.image[pix * 3 + 1]; hd[2] = p.image[pix * 3 + 2];
         }
-        const bool masked = valid && (grid_sample_ac(p.density, p.G, c0, c1) > p.thresh);
-        const uint32_t mmask = __ballot_sync(0xffffffffu, masked);
-        float alpha = 0.f, tc0 = 0.f, tc1 = 0.f, tc2 = 0.f;
-
-        if (mmask) {
-            // x * torso_shrink -> freq(deg 8) 34 values -> cols 32..65 of the tile (cols 66..79 zero)
-            const float xin[2] = {c0 * p.shrink, c1 * p.shrink};
-            __half *row = xt + lane * TX_STRIDE;
+        float out[3];
 #pragma unroll
-            for (int c = 0; c < 34; c += 2)
-                *reinterpret_cast<uint32_t *>(row + 32 + c) =
-                    masked ? pack_half2(freq_elem(xin, 2, c), freq_elem(xin, 2, c + 1)) : 0u;
-#pragma unroll
-            for (int c = 66; c < 80; c += 2) *reinterpret_cast<uint32_t *>(row + c) = 0u;
-            __syncwarp();
-
-            float dxy[2] = {0.f, 0.f};
-#pragma unroll 1
-            for (int m = 0; m < 2; m++) {
-                if (((mmask >> (16 * m)) & 0xffffu) == 0u) continue;
-                // torso_deform_net: [freq 34 (+ constants as bias)] -> 32 -> 32 -> 2
-                uint32_t a3[3][4];
-#pragma unroll
-                for (int kk = 0; kk < 3; kk++) load_a(a3[kk], xt + m * 16 * TX_STRIDE + 32, TX_STRIDE, kk, lane);
-                float c[4][4];
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) {
-                    c[nt][0] = c[nt][2] = sm.bias[nt * 8 + 2 * t];
-                    c[nt][1] = c[nt][3] = sm.bias[nt * 8 + 2 * t + 1];
-                }
-                mlp_layer<3, 4, 56>(c, a3, sm.mlp + ER_T_DEF1, lane);
-                uint32_t ah[2][4];
-                acc_to_a<4, true>(c, ah);
-                zero_acc(c);
-                mlp_layer<2, 4, 40>(c, ah, sm.mlp + ER_T_DEF2, lane);
-                acc_to_a<4, true>(c, ah);
-                float cd[1][4];
-                zero_acc(cd);
-                mlp_layer<2, 1, 40>(cd, ah, sm.mlp + ER_T_DEF3, lane);
-                // dx (cols 0, 1) lives in lanes t == 0
-                const int src0 = 4 * (lane & 7);
-                const float d0lo = __shfl_sync(0xffffffffu, cd[0][0], src0), d1lo = __shfl_sync(0xffffffffu, cd[0][1], src0);
-                const float d0hi = __shfl_sync(0xffffffffu, cd[0][2], src0), d1hi = __shfl_sync(0xffffffffu, cd[0][3], src0);
-                if ((lane >> 4) == m) {
-                    dxy[0] = round_half((lane & 8) ? d0hi : d0lo);
-                    dxy[1] = round_half((lane & 8) ? d1hi : d1lo);
-                }
-            }
-            // x = clamp(x + dx, -1, 1); tiled grid on (x + 1) / 2 (network.py:188-190), fp16 table
-            if (masked) {
-                const float u = (clampf_(xin[0] + dxy[0], -1.f, 1.f) + 1.f) * 0.5f;
-                const float v = (clampf_(xin[1] + dxy[1], -1.f, 1.f) + 1.f) * 0.5f;
-#pragma unroll
-                for (int l = 0; l < MF_ERNERF_TORSO_LEVELS; l++) {
-                    float o0, o1;
-                    if (p.tl.n_dense < 0) grid_level_f16x2<IDX_ANY>(p.table, p.tl.lv[l], u, v, o0, o1);
-                    else if (l < p.tl.n_dense) grid_level_f16x2<IDX_DENSE>(p.table, p.tl.lv[l], u, v, o0, o1);
-                    else grid_level_f16x2<IDX_TILE2>(p.table, p.tl.lv[l], u, v, o0, o1);
-                    *reinterpret_cast<uint32_t *>(row + 2 * l) = pack_half2(o0, o1);
-                }
-            } else {
-#pragma unroll
-                for (int l = 0; l < 16; l++) *reinterpret_cast<uint32_t *>(row + 2 * l) = 0u;
-            }
-            __syncwarp();
-#pragma unroll 1
-            for (int m = 0; m < 2; m++) {
-                if (((mmask >> (16 * m)) & 0xffffu) == 0u) continue;
-                // torso_net: [feat 32 | freq 34 (+ constants as bias)] -> 32 -> 32 -> 4
-                uint32_t a5[5][4];
-#pragma unroll
-                for (int kk = 0; kk < 5; kk++) load_a(a5[kk], xt + m * 16 * TX_STRIDE, TX_STRIDE, kk, lane);
-                float c[4][4];
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) {
-                    c[nt][0] = c[nt][2] = sm.bias[32 + nt * 8 + 2 * t];
-                    c[nt][1] = c[nt][3] = sm.bias[32 + nt * 8 + 2 * t + 1];
-                }
-                mlp_layer<5, 4, 88>(c, a5, sm.mlp + ER_T_TOR1, lane);
-                uint32_t ah[2][4];
-                acc_to_a<4, true>(c, ah);
-                zero_acc(c);
-                mlp_layer<2, 4, 40>(c, ah, sm.mlp + ER_T_TOR2, lane);
-                acc_to_a<4, true>(c, ah);
-                float co[1][4];
-                zero_acc(co);
-                mlp_layer<2, 1, 40>(co, ah, sm.mlp + ER_T_TOR3, lane);
-                float o[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) o[i] = affine16(sigmoid16(round_half(co[0][i])));
-                // cols: 0 alpha, 1..3 color -> lanes t == 0 hold (alpha, r), t == 1 hold (g, b)
-                const int src0 = 4 * (lane & 7), src1 = src0 + 1;
-                const float a_lo = __shfl_sync(0xffffffffu, o[0], src0), a_hi = __shfl_sync(0xffffffffu, o[2], src0);
-                const float r_lo = __shfl_sync(0xffffffffu, o[1], src0), r_hi = __shfl_sync(0xffffffffu, o[3], src0);
-                const float g_lo = __shfl_sync(0xffffffffu, o[0], src1), g_hi = __shfl_sync(0xffffffffu, o[2], src1);
-                const float b_lo = __shfl_sync(0xffffffffu, o[1], src1), b_hi = __shfl_sync(0xffffffffu, o[3], src1);
-                if ((lane >> 4) == m && masked) {
-                    const bool hi = lane & 8;
-                    alpha = hi ? a_hi : a_lo;
-                    tc0 = hi ? r_hi : r_lo;
-                    tc1 = hi ? g_hi : g_lo;
-                    tc2 = hi ? b_hi : b_lo;
-                }
-            }
-            __syncwarp();
+        for (int k = 0; k < 3; k++) {
+            out[k] = fminf(fmaxf(hd[k] + (1 - ws) * b[k], 0.f), 1.f);
+            if (p.dbg_image_head) p.dbg_image_head[pix * 3 + k] = hd[k];
         }
-
-        if (valid) {
-            // renderer.py:344 bg = torso_color * torso_alpha + bg * (1 - torso_alpha); :275-277 compose + clamp
-            float bg[3] = {1.f, 1.f, 1.f};
-            if (p.bg_color) {
-                bg[0] = __half2float(p.bg_color[pix * 3]);
-                bg[1] = __half2float(p.bg_color[pix * 3 + 1]);
-                bg[2] = __half2float(p.bg_color[pix * 3 + 2]);
-            }
-            const float tc[3] = {tc0, tc1, tc2};
-            float ws = p.weights_sum[pix];
-            float hd[3];
-            if (ws < 0.f) {   // alive after max_steps samples: the state after C samples
-                const float4 v = p.snap[(size_t)((int)(-ws) - 1) * ER_SNAPS + s_snap];
-                ws = v.x; hd[0] = v.y; hd[1] = v.z; hd[2] = v.w;
-                p.weights_sum[pix] = ws;
-                p.image[pix * 3] = hd[0]; p.image[pix * 3 + 1] = hd[1]; p.image[pix * 3 + 2] = hd[2];
-            } else {
-                hd[0] = p.image[pix * 3]; hd[1] = p.image[pix * 3 + 1]; hd[2] = p.image[pix * 3 + 2];
-            }
-            float out[3];
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float b = tc[k] * alpha + bg[k] * (1 - alpha);
-                out[k] = fminf(fmaxf(hd[k] + (1 - ws) * b, 0.f), 1.f);
-                if (p.dbg_image_head) p.dbg_image_head[pix * 3 + k] = hd[k];
-            }
-            if (p.out_f32) { p.out_f32[pix * 3] = out[0]; p.out_f32[pix * 3 + 1] = out[1]; p.out_f32[pix * 3 + 2] = out[2]; }
-            if (p.out_u8) {
-                p.out_u8[pix * 3] = (uint8_t)(out[0] * 255.f);
-                p.out_u8[pix * 3 + 1] = (uint8_t)(out[1] * 255.f);
-                p.out_u8[pix * 3 + 2] = (uint8_t)(out[2] * 255.f);
-            }
-            if (p.dbg_mask) p.dbg_mask[pix] = masked ? 1 : 0;
+        if (p.out_f32) { p.out_f32[pix * 3] = out[0]; p.out_f32[pix * 3 + 1] = out[1]; p.out_f32[pix * 3 + 2] = out[2]; }
+        if (p.out_u8) {
+            p.out_u8[pix * 3] = (uint8_t)(out[0] * 255.f);
+            p.out_u8[pix * 3 + 1] = (uint8_t)(out[1] * 255.f);
+            p.out_u8[pix * 3 + 2] = (uint8_t)(out[2] * 255.f);
         }
     }
 }
@@ -1363,17 +1399,17 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
     MF_CUDA(ctx, cudaMalloc(&s->counters, 2 * CT_INTS * sizeof(int)));
     MF_CUDA(ctx, cudaMemset(s->counters, 0, 2 * CT_INTS * sizeof(int)));
 
+    MF_CUDA(ctx, cudaFuncSetAttribute(k_torso_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TorsoSmem)));
+    MF_CUDA(ctx, cudaFuncSetAttribute(k_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     MF_CUDA(ctx, cudaFuncSetAttribute(k_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     MF_CUDA(ctx, cudaFuncSetAttribute(k_head<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     MF_CUDA(ctx, cudaFuncSetAttribute(k_head<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
-    MF_CUDA(ctx, cudaFuncSetAttribute(k_torso_compose, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(TorsoSmem)));
     int per_sm = 0;
-    MF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_head<4>, HEAD_THREADS, sizeof(HeadSmem)));
+    MF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_head<2>, HEAD_THREADS, sizeof(HeadSmem)));
     MF_REQUIRE(ctx, per_sm >= 1, "k_head does not fit on an SM");
     {   // experiment hook: MF_HEAD_CHUNK = samples of a ray shaded side by side per pass (2, 4 or 8)
         const char *e = getenv("MF_HEAD_CHUNK");
-        if (e && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8)) s->chunk = atoi(e);
+        if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8)) s->chunk = atoi(e);
     }
     s->head_grid = ctx->sm_count;
     MF_CUDA(ctx, cudaDeviceSynchronize());
@@ -1457,6 +1493,7 @@ struct PreparedFrame {
     ErnerfState *s;
     FrameGeom g;
     SetupParams sp;
+    float wa[6];   // wrapped anchor (fp16-rounded), network.py:175-176
     int N, outH, outW;
     bool resize;
 };
@@ -1505,12 +1542,12 @@ static int prepare_frame(mf_ctx *ctx, const mf_ernerf_frame *f, const mf_ernerf_
                 for (int k = 0; k < 4; k++) acc += h16(ap[a * 4 + k]) * h16((float)inv[k * 4 + j]);
                 w[j] = h16(acc);
             }
-            sp.wa[a * 2 + 0] = h16(h16(w[0] / w[3]) / w[2]);
-            sp.wa[a * 2 + 1] = h16(h16(w[1] / w[3]) / w[2]);
+            pf.wa[a * 2 + 0] = h16(h16(w[0] / w[3]) / w[2]);
+            pf.wa[a * 2 + 1] = h16(h16(w[1] / w[3]) / w[2]);
         }
     }
-    sp.auds = f->auds; sp.enc_a_in = f->enc_a; sp.audio = s->audio; sp.torso_const = s->torso_const;
-    sp.misc = s->misc; sp.state = s->state; sp.counters_next = s->counters + ((s->frame_no + 1) & 1u) * CT_INTS;
+    sp.auds = f->auds; sp.enc_a_in = f->enc_a; sp.audio = s->audio;
+    sp.state = s->state; sp.counters_next = s->counters + ((s->frame_no + 1) & 1u) * CT_INTS;
     sp.A = (int)s->cfg.audio_in_dim;
     sp.N = N; sp.smooth = (int)s->cfg.smooth_lips; sp.dbg_enc_a = dbg ? dbg->enc_a : nullptr;
     sp.audio_halfs = (int)s->audio_halfs;
@@ -1556,9 +1593,9 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
     for (int i = 0; i < 6; i++) sb.aabb[i] = aabb[i];
     static mf_per_device_flag setup_attr;
     if (!setup_attr.test_and_set(ctx->device)) {
-        MF_CUDA(ctx, cudaFuncSetAttribute(k_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MF_CUDA(ctx, cudaFuncSetAttribute(k_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     }
-    MF_REQUIRE(ctx, setup_smem <= 200 * 1024, "audio weight image too large for k_setup");
+    MF_REQUIRE(ctx, setup_smem <= 220 * 1024, "audio weight image too large for k_setup");
     {   // audio CTAs first, then the ray pass: one CTA (32 warps, one ray per lane) per SM that the audio CTAs leave free
         const int ray_ctas = (int)std::max<long>(1, std::min<long>(ctx->sm_count - n, (total_tiles + SETUP_THREADS / 32 - 1) / (SETUP_THREADS / 32)));
         k_setup<<<n + ray_ctas, SETUP_THREADS, setup_smem, stream>>>(sb);
@@ -1582,9 +1619,10 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
         // one CTA per SM; small ray counts (explicit-ray calls) get fewer CTAs: every CTA stages the 57 KB MLP image
         const int grid = (int)std::min<long>(s0->head_grid, std::max<long>(1, (total_tiles * 32 + 255) / 256));
         if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[0], stream));
-        if (s0->chunk == 2) k_head<2><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
+        if (s0->chunk == 1) k_head<1><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
+        else if (s0->chunk == 4) k_head<4><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
         else if (s0->chunk == 8) k_head<8><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
-        else k_head<4><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
+        else k_head<2><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
         if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[1], stream));
         launches++;
     }
@@ -1594,19 +1632,22 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
         const mf_ernerf_frame *f = &frames[i];
         const mf_ernerf_debug *d = i == 0 ? dbg : nullptr;
         const int N = pf[i].N;
-        TorsoParams tp;
-        tp.g = pf[i].g; tp.tl = s->tl; tp.table = s->torso_table; tp.density = s->torso_density; tp.mlp_image = s->torso_mlp;
-        tp.state = s->state; tp.bg_color = (const __half *)f->bg_color; tp.thresh = s->cfg.density_thresh_torso;
-        tp.shrink = s->cfg.torso_shrink; tp.G = (int)s->cfg.grid_size; tp.weights_sum = s->weights_sum; tp.image = s->image;
-        tp.snap = s->snap; tp.counters = ctr[i]; tp.max_steps = (int)s->cfg.max_steps;
-        tp.out_f32 = pf[i].resize ? s->final_f32 : f->out_image_f32;
-        tp.out_u8 = pf[i].resize ? nullptr : outs[i];
-        tp.dbg_mask = d ? d->torso_mask : nullptr;
-        tp.dbg_image_head = d ? d->image_head : nullptr;
+        ComposeParams cp;
+        cp.g = pf[i].g;
+        cp.tm.tl = s->tl; cp.tm.table = s->torso_table; cp.tm.density = s->torso_density; cp.tm.mlp_image = s->torso_mlp;
+        cp.tm.torso_const = s->torso_const; cp.tm.misc = s->misc; cp.tm.thresh = s->cfg.density_thresh_torso;
+        cp.tm.shrink = s->cfg.torso_shrink; cp.tm.G = (int)s->cfg.grid_size;
+        cp.tf.bg_color = (const __half *)f->bg_color; cp.tf.dbg_mask = d ? d->torso_mask : nullptr;
+        for (int k = 0; k < 6; k++) cp.tf.wa[k] = pf[i].wa[k];
+        cp.weights_sum = s->weights_sum; cp.image = s->image; cp.snap = s->snap; cp.counters = ctr[i];
+        cp.max_steps = (int)s->cfg.max_steps;
+        cp.out_f32 = pf[i].resize ? s->final_f32 : f->out_image_f32;
+        cp.out_u8 = pf[i].resize ? nullptr : outs[i];
+        cp.dbg_image_head = d ? d->image_head : nullptr;
         {
             const int n_tiles = (N + 31) / 32;
             const int grid = std::max(1, std::min((n_tiles + TORSO_WARPS - 1) / TORSO_WARPS, ctx->sm_count * 4));
-            k_torso_compose<<<grid, TORSO_THREADS, sizeof(TorsoSmem), stream>>>(tp);
+            k_torso_compose<<<grid, TORSO_THREADS, sizeof(TorsoSmem), stream>>>(cp);
             launches++;
         }
         if (pf[i].resize) {

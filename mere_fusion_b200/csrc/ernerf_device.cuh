@@ -243,15 +243,21 @@ __device__ __forceinline__ bool march_next_t(const MarchParams &p, const Ray &r,
     return true;
 }
 
-__device__ __forceinline__ bool march_next(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
-                                           float &y, float &z, float &dt_out, uint32_t &vox) {
-    return p.fast ? march_next_t<true>(p, r, t, far, x, y, z, dt_out, vox)
-                  : march_next_t<false>(p, r, t, far, x, y, z, dt_out, vox);
+// the general form (cascades, non power-of-two grids) stays out of line: it is not on the shipped model's path and would only
+// dilute the instruction cache of the fused kernels
+__device__ __noinline__ bool march_find_general(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
+                                                float &y, float &z, float &dt_out, uint32_t &vox) {
+    return march_find_t<false>(p, r, t, far, x, y, z, dt_out, vox);
 }
 __device__ __forceinline__ bool march_find(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
                                            float &y, float &z, float &dt_out, uint32_t &vox) {
-    return p.fast ? march_find_t<true>(p, r, t, far, x, y, z, dt_out, vox)
-                  : march_find_t<false>(p, r, t, far, x, y, z, dt_out, vox);
+    return p.fast ? march_find_t<true>(p, r, t, far, x, y, z, dt_out, vox) : march_find_general(p, r, t, far, x, y, z, dt_out, vox);
+}
+__device__ __forceinline__ bool march_next(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
+                                           float &y, float &z, float &dt_out, uint32_t &vox) {
+    if (!march_find(p, r, t, far, x, y, z, dt_out, vox)) return false;
+    t += dt_out;
+    return true;
 }
 
 // shencoder.cu:43-68, degree 4
