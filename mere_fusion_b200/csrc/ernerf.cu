@@ -89,7 +89,7 @@ struct ErnerfState {
     HeadLevels hl;
     TorsoLevels tl;
     // persistent device state
-    float *state = nullptr;  // [0..31] enc_a (smoothed), [32] has_prev flag, [64..95] bias_def, [96..127] bias_tor
+    float *state = nullptr;  // [ST_FLOATS]: [0..31] enc_a (smoothed), [32] has_prev flag, [33] audio CTAs done, [128..383] encoded windows
     int *counters = nullptr; // [2][CT_INTS]
     unsigned frame_no = 0;   // parity selects the counter copy
     // per-N workspace
@@ -154,27 +154,7 @@ struct SetupParams {
 
 __device__ __forceinline__ float lrelu16(float v16) { return v16 > 0.f ? v16 : round_half(v16 * 0.02f); }
 
-// nn.Conv1d(k=3) under autocast on a [B, Cin, T] activation held in shared memory as fp16 values
-__device__ void conv1d_k3(const float *x, float *y, const __half *W, const __half *b, int B, int Cin, int T, int Cout,
-                          int stride) {
-    const int To = (T + 2 - 3) / stride + 1;
-    for (int o = threadIdx.x; o < B * Cout * To; o += blockDim.x) {
-        const int t = o % To, co = (o / To) % Cout, bb = o / (To * Cout);
-        float acc = 0.f;
-        for (int c = 0; c < Cin; c++) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int ti = t * stride + k - 1;
-                if (ti >= 0 && ti < T) acc = fmaf(__half2float(W[(co * Cin + c) * 3 + k]), x[(bb * Cin + c) * T + ti], acc);
-            }
-        }
-        y[(bb * Cout + co) * To + t] = lrelu16(round_half(acc + __half2float(b[co])));
-    }
-    __syncthreads();
-}
-
 #define SETUP_THREADS 1024
-#define SETUP_FLOATS (8 * 64 * 16 + 8 * 32 * 8 + 8 * 32 + 8 + 48)
 // ray pass (the CTAs of k_setup beyond the first n): one lane per ray
 struct RayPassFrame {
     FrameGeom g;
@@ -190,7 +170,7 @@ struct SetupBatch {   // one audio CTA per frame of a batched render (HEAD_MAX_F
     const uint8_t *bitfield;
     float aabb[6];
 };
-__device__ __forceinline__ void setup_body(const SetupParams &p);
+__device__ __forceinline__ void audio_cta(const SetupParams &p, int b);
 __device__ __forceinline__ void gen_ray(const FrameGeom &g, int idx, Ray &r);
 
 // The reference's round 0 (n_alive = N, n_step = 1) without its shading: which rays have a first sample, and where.
@@ -235,82 +215,131 @@ __device__ __forceinline__ void ray_pass(const SetupBatch &b, int cta, int n_cta
     }
 }
 
-// (the k_setup kernel itself is defined after the torso pass below)
-__device__ __forceinline__ void setup_body(const SetupParams &p) {
-    // the whole audio-net weight image (66 KB fp16) is staged in shared memory with coalesced 16-byte loads first: read straight
-    // from global inside the dot-product loops, the 2-byte weight loads formed ~1000-long dependent latency chains per thread
-    // (125 us for 0.1 MFLOP: 18 % of the frame)
-    extern __shared__ __align__(16) unsigned char setup_smem[];
-    float *bufA = reinterpret_cast<float *>(setup_smem);  // activations (values already rounded to fp16)
-    float *bufB = bufA + 8 * 64 * 16;
-    float *enc = bufB + 8 * 32 * 8;
-    float *att = enc + 8 * 32;
-    __half *w_sm = reinterpret_cast<__half *>(bufA + SETUP_FLOATS);
-    const int tid = threadIdx.x;
-    if (!p.enc_a_in) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.audio);   // blob entries are 256-byte aligned and padded
-        uint4 *dst = reinterpret_cast<uint4 *>(w_sm);
-        for (int i = tid; i < (p.audio_halfs * 2 + 15) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+// ---- audio encoder (network.py:9-66,222-237; smoothing renderer.py:190-194) -----------------------------------------------
+// Round 1 ran it in ONE CTA (35-59 us of dependent layers, the 66 KB weight image staged in shared memory -- which also took
+// the L1 away from the ray-pass CTAs of the same launch).  Now: one CTA per attention window (8 per frame), every output's dot
+// product split over G lanes + a shuffle reduction, weights read straight from L2 with coalesced loads, and the CTA that
+// finishes last runs the attention net + EMA on the 8 encoded windows.
+// y[o] = act(fp16(bias[o] + sum_j W[o][j] * x[idx(o, j)])), o < O: G (power of two <= 32) lanes per output
+template <class IdxF>
+__device__ __forceinline__ void dense_split(const __half *__restrict__ W, const __half *__restrict__ bias, int O, int K, int G,
+                                            const float *x, float *y, IdxF idx, bool lrelu) {
+    for (int base = 0; base < O * G; base += blockDim.x) {   // uniform trip count: the shuffles below need whole warps
+        const int gi = base + threadIdx.x;
+        const int o = gi / G, sub = gi - o * G;
+        const bool ok = o < O;
+        float acc = 0.f;
+        if (ok)
+            for (int j = sub; j < K; j += G) {
+                const int xi = idx(o, j);
+                if (xi >= 0) acc = fmaf(__half2float(__ldg(W + (size_t)o * K + j)), x[xi], acc);
+            }
+        for (int m = G >> 1; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (ok && sub == 0) {
+            const float v = round_half(acc + __half2float(__ldg(bias + o)));
+            y[o] = lrelu ? lrelu16(v) : v;
+        }
     }
+    __syncthreads();
+}
 
-    // the counters of this context's next frame (this frame's copy is being written by the ray-pass CTAs right now)
-    for (int i = tid; i < CT_INTS; i += blockDim.x) p.counters_next[i] = 0;
+// nn.Conv1d(k = 3, padding 1) on x[Cin][T] -> y[Cout][To] (values held as fp16-rounded floats): the weight row of output
+// o = (co, t) is W[co]
+template <class IdxF>
+__device__ __forceinline__ void dense_rows(const __half *__restrict__ W, const __half *__restrict__ bias, int O, int K, int G, int To,
+                                           const float *x, float *y, IdxF idx, bool lrelu) {
+    for (int base = 0; base < O * G; base += blockDim.x) {
+        const int gi = base + threadIdx.x;
+        const int o = gi / G, sub = gi - o * G;
+        const bool ok = o < O;
+        const int co = o / To;
+        float acc = 0.f;
+        if (ok)
+            for (int j = sub; j < K; j += G) {
+                const int xi = idx(o, j);
+                if (xi >= 0) acc = fmaf(__half2float(__ldg(W + (size_t)co * K + j)), x[xi], acc);
+            }
+        for (int m = G >> 1; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (ok && sub == 0) {
+            const float v = round_half(acc + __half2float(__ldg(bias + co)));
+            y[o] = lrelu ? lrelu16(v) : v;
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void conv1d_rows(const __half *W, const __half *b, int Cin, int T, int Cout, int stride, int G,
+                                            const float *x, float *y) {
+    const int To = (T + 2 - 3) / stride + 1;
+    dense_rows(W, b, Cout * To, Cin * 3, G, To, x, y,
+               [=](int o, int j) {
+                   const int t = o % To, c = j / 3, k = j - 3 * c, ti = t * stride + k - 1;
+                   return (ti >= 0 && ti < T) ? c * T + ti : -1;
+               }, true);
+}
 
+// state layout (floats): [0..31] smoothed enc_a, [32] has-previous flag, [33] (int) audio CTAs done, [128..383] the 8 encoded windows
+#define ST_DONE 33
+#define ST_ENC8 128
+#define ST_FLOATS 512
+
+__device__ __forceinline__ void audio_cta(const SetupParams &p, int b) {
+    __shared__ float bufA[64 * 16], bufB[64 * 16], att[8];
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    if (b == 0)   // the counters of this context's next frame (this frame's copy is being written by the ray-pass CTAs right now)
+        for (int i = tid; i < CT_INTS; i += blockDim.x) p.counters_next[i] = 0;
     if (p.enc_a_in) {  // pre-encoded feature: no EMA, no state update
-        if (tid < 32) {
+        if (b == 0 && tid < 32) {
             p.state[tid] = p.enc_a_in[tid];
             if (p.dbg_enc_a) p.dbg_enc_a[tid] = p.enc_a_in[tid];
         }
         return;
     }
-
-    // ---- AudioNet (network.py:40-66): x[:, :, 0:16] -> 4x conv(k3,s2,p1)+LeakyReLU -> fc
+    // ---- AudioNet (network.py:40-66) on window b: x[:, 0:16] -> 4x conv(k3,s2,p1)+LeakyReLU -> fc
     const int A = p.A;
-    const __half *w = w_sm;
-    for (int i = tid; i < 8 * A * 16; i += blockDim.x) bufA[i] = round_half(p.auds[i]);
+    const __half *w = p.audio;
+    for (int i = tid; i < A * 16; i += blockDim.x) bufA[i] = round_half(p.auds[(size_t)b * A * 16 + i]);
     __syncthreads();
-    conv1d_k3(bufA, bufB, w, w + 32 * A * 3, 8, A, 16, 32, 2);  w += 32 * A * 3 + 32;
-    conv1d_k3(bufB, bufA, w, w + 32 * 32 * 3, 8, 32, 8, 32, 2);  w += 32 * 32 * 3 + 32;
-    conv1d_k3(bufA, bufB, w, w + 64 * 32 * 3, 8, 32, 4, 64, 2);  w += 64 * 32 * 3 + 64;
-    conv1d_k3(bufB, bufA, w, w + 64 * 64 * 3, 8, 64, 2, 64, 2);  w += 64 * 64 * 3 + 64;
-    // bufA: [8][64] ; fc1.0 64->64 + LeakyReLU
-    for (int o = tid; o < 8 * 64; o += blockDim.x) {
-        const int n = o % 64, bb = o / 64;
-        float acc = 0.f;
-        for (int k = 0; k < 64; k++) acc = fmaf(__half2float(w[n * 64 + k]), bufA[bb * 64 + k], acc);
-        bufB[o] = lrelu16(round_half(acc + __half2float(w[64 * 64 + n])));
+    conv1d_rows(w, w + 32 * A * 3, A, 16, 32, 2, 4, bufA, bufB);    w += 32 * A * 3 + 32;     // -> [32][8]
+    conv1d_rows(w, w + 32 * 32 * 3, 32, 8, 32, 2, 8, bufB, bufA);   w += 32 * 32 * 3 + 32;    // -> [32][4]
+    conv1d_rows(w, w + 64 * 32 * 3, 32, 4, 64, 2, 8, bufA, bufB);   w += 64 * 32 * 3 + 64;    // -> [64][2]
+    conv1d_rows(w, w + 64 * 64 * 3, 64, 2, 64, 2, 16, bufB, bufA);  w += 64 * 64 * 3 + 64;    // -> [64][1]
+    dense_split(w, w + 64 * 64, 64, 64, 16, bufA, bufB, [](int, int j) { return j; }, true);   w += 64 * 64 + 64;   // fc1.0 + LeakyReLU
+    dense_split(w, w + 32 * 64, 32, 64, 32, bufB, bufA, [](int, int j) { return j; }, false);  w += 32 * 64 + 32;   // fc1.2
+    if (tid < 32) p.state[ST_ENC8 + b * 32 + tid] = bufA[tid];
+    // ---- the CTA that arrives last has all 8 windows: attention net + smoothing
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(reinterpret_cast<int *>(p.state) + ST_DONE, 1) == 7;
     }
     __syncthreads();
-    w += 64 * 64 + 64;
-    for (int o = tid; o < 8 * 32; o += blockDim.x) {  // fc1.2 64->32
-        const int n = o % 32, bb = o / 32;
-        float acc = 0.f;
-        for (int k = 0; k < 64; k++) acc = fmaf(__half2float(w[n * 64 + k]), bufB[bb * 64 + k], acc);
-        enc[o] = round_half(acc + __half2float(w[32 * 64 + n]));
-    }
+    if (!s_last) return;
+    __threadfence();
+    float *enc = bufB + 512;   // [8][32]
+    for (int i = tid; i < 8 * 32; i += blockDim.x) enc[i] = __ldcg(p.state + ST_ENC8 + i);
     __syncthreads();
-    w += 32 * 64 + 32;
-    // ---- AudioAttNet (network.py:9-36): y = enc^T [1, 32, 8] -> 5x conv(k3,s1,p1)+LeakyReLU -> Linear(8,8) -> softmax
+    // AudioAttNet (network.py:9-36): y = enc^T [32][8] -> 5x conv(k3,s1,p1)+LeakyReLU -> Linear(8,8) -> softmax
     for (int i = tid; i < 32 * 8; i += blockDim.x) bufA[i] = enc[(i % 8) * 32 + i / 8];
     __syncthreads();
-    conv1d_k3(bufA, bufB, w, w + 16 * 32 * 3, 1, 32, 8, 16, 1);  w += 16 * 32 * 3 + 16;
-    conv1d_k3(bufB, bufA, w, w + 8 * 16 * 3, 1, 16, 8, 8, 1);    w += 8 * 16 * 3 + 8;
-    conv1d_k3(bufA, bufB, w, w + 4 * 8 * 3, 1, 8, 8, 4, 1);      w += 4 * 8 * 3 + 4;
-    conv1d_k3(bufB, bufA, w, w + 2 * 4 * 3, 1, 4, 8, 2, 1);      w += 2 * 4 * 3 + 2;
-    conv1d_k3(bufA, bufB, w, w + 1 * 2 * 3, 1, 2, 8, 1, 1);      w += 1 * 2 * 3 + 1;
+    conv1d_rows(w, w + 16 * 32 * 3, 32, 8, 16, 1, 8, bufA, bufB);  w += 16 * 32 * 3 + 16;
+    conv1d_rows(w, w + 8 * 16 * 3, 16, 8, 8, 1, 16, bufB, bufA);   w += 8 * 16 * 3 + 8;
+    conv1d_rows(w, w + 4 * 8 * 3, 8, 8, 4, 1, 8, bufA, bufB);      w += 4 * 8 * 3 + 4;
+    conv1d_rows(w, w + 2 * 4 * 3, 4, 8, 2, 1, 4, bufB, bufA);      w += 2 * 4 * 3 + 2;
+    conv1d_rows(w, w + 1 * 2 * 3, 2, 8, 1, 1, 2, bufA, bufB);      w += 1 * 2 * 3 + 1;
     if (tid < 8) {
         float acc = 0.f;
-        for (int k = 0; k < 8; k++) acc = fmaf(__half2float(w[tid * 8 + k]), bufB[k], acc);
-        att[tid] = round_half(acc + __half2float(w[64 + tid]));
+        for (int k = 0; k < 8; k++) acc = fmaf(__half2float(__ldg(w + tid * 8 + k)), bufB[k], acc);
+        att[tid] = round_half(acc + __half2float(__ldg(w + 64 + tid)));
     }
     __syncthreads();
     if (tid < 32) {
         float mx = att[0];
         for (int k = 1; k < 8; k++) mx = fmaxf(mx, att[k]);
-        float e[8], s = 0.f;
-        for (int k = 0; k < 8; k++) { e[k] = expf(att[k] - mx); s += e[k]; }
+        float e[8], sum = 0.f;
+        for (int k = 0; k < 8; k++) { e[k] = expf(att[k] - mx); sum += e[k]; }
         float out = 0.f;
-        for (int k = 0; k < 8; k++) out += (e[k] / s) * enc[k * 32 + tid];
+        for (int k = 0; k < 8; k++) out += (e[k] / sum) * enc[k * 32 + tid];
         // renderer.py:190-194
         if (p.smooth) {
             if (p.state[32] != 0.f) out = 0.35f * p.state[tid] + (1 - 0.35f) * out;
@@ -318,6 +347,7 @@ __device__ __forceinline__ void setup_body(const SetupParams &p) {
         __syncwarp();
         p.state[tid] = out;
         if (tid == 0 && p.smooth) p.state[32] = 1.f;
+        if (tid == 0) reinterpret_cast<int *>(p.state)[ST_DONE] = 0;
         if (p.dbg_enc_a) p.dbg_enc_a[tid] = out;
     }
 }
@@ -1032,8 +1062,9 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
 }
 
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ SetupBatch b) {
-    if ((int)blockIdx.x < b.n) setup_body(b.f[blockIdx.x]);
-    else ray_pass(b, (int)blockIdx.x - b.n, (int)gridDim.x - b.n);
+    const int n_audio = 8 * b.n;   // one CTA per attention window
+    if ((int)blockIdx.x < n_audio) audio_cta(b.f[blockIdx.x >> 3], blockIdx.x & 7);
+    else ray_pass(b, (int)blockIdx.x - n_audio, (int)gridDim.x - n_audio);
 }
 
 // torso + final compose (renderer.py:275-277,294-352): resolve the loop control, torso over background,
@@ -1394,8 +1425,8 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
     fill_levels(s->tl.lv, MF_ERNERF_TORSO_LEVELS, sc, cfg->torso_offsets, 1);
     s->tl.n_dense = classify_levels(s->tl.lv, MF_ERNERF_TORSO_LEVELS, IDX_TILE2);
 
-    MF_CUDA(ctx, cudaMalloc(&s->state, 128 * sizeof(float)));
-    MF_CUDA(ctx, cudaMemset(s->state, 0, 128 * sizeof(float)));
+    MF_CUDA(ctx, cudaMalloc(&s->state, ST_FLOATS * sizeof(float)));
+    MF_CUDA(ctx, cudaMemset(s->state, 0, ST_FLOATS * sizeof(float)));
     MF_CUDA(ctx, cudaMalloc(&s->counters, 2 * CT_INTS * sizeof(int)));
     MF_CUDA(ctx, cudaMemset(s->counters, 0, 2 * CT_INTS * sizeof(int)));
 
@@ -1573,14 +1604,12 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
     const float aabb[6] = {-bnd, -bnd / 2, -bnd, bnd, bnd / 2, bnd};
     int *ctr[HEAD_MAX_FRAMES];   // this frame's counter copy per context (zeroed by the context's previous frame)
     for (int i = 0; i < n; i++) ctr[i] = pf[i].s->counters + (pf[i].s->frame_no & 1u) * CT_INTS;
-    size_t setup_smem = 0;
     SetupBatch sb;
     sb.n = n;
     long total_tiles = 0;
     for (int i = 0; i < n; i++) {
         ErnerfState *s = pf[i].s;
         sb.f[i] = pf[i].sp;
-        setup_smem = std::max(setup_smem, SETUP_FLOATS * sizeof(float) + (s->audio_halfs * 2 + 15) / 16 * 16);
         RayPassFrame &rp = sb.r[i];
         rp.g = pf[i].g; rp.hits = s->hits; rp.counters = ctr[i]; rp.rays_t = s->rays_t; rp.fars = s->fars;
         rp.nears = (i == 0 && dbg && dbg->nears) ? dbg->nears : nullptr;
@@ -1591,14 +1620,10 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
     sb.max_steps = s0->cfg.max_steps; sb.cascade = s0->cfg.cascade; sb.grid_size = s0->cfg.grid_size;
     sb.bitfield = s0->bitfield;
     for (int i = 0; i < 6; i++) sb.aabb[i] = aabb[i];
-    static mf_per_device_flag setup_attr;
-    if (!setup_attr.test_and_set(ctx->device)) {
-        MF_CUDA(ctx, cudaFuncSetAttribute(k_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    }
-    MF_REQUIRE(ctx, setup_smem <= 220 * 1024, "audio weight image too large for k_setup");
-    {   // audio CTAs first, then the ray pass: one CTA (32 warps, one ray per lane) per SM that the audio CTAs leave free
-        const int ray_ctas = (int)std::max<long>(1, std::min<long>(ctx->sm_count - n, (total_tiles + SETUP_THREADS / 32 - 1) / (SETUP_THREADS / 32)));
-        k_setup<<<n + ray_ctas, SETUP_THREADS, setup_smem, stream>>>(sb);
+    {   // 8 audio CTAs per frame first, then the ray pass: one CTA (32 warps, one ray per lane) per SM that is left
+        const int n_audio = 8 * n;
+        const int ray_ctas = (int)std::max<long>(1, std::min<long>(ctx->sm_count - n_audio, (total_tiles + SETUP_THREADS / 32 - 1) / (SETUP_THREADS / 32)));
+        k_setup<<<n_audio + ray_ctas, SETUP_THREADS, 0, stream>>>(sb);
     }
     int launches = 1;
 
