@@ -81,6 +81,7 @@ struct ErnerfState {
     const float *planes = nullptr;
     uint32_t plane_rows = 0;
     const uint8_t *bitfield = nullptr;
+    uint8_t *bitfield_linear = nullptr;   // owned: (z * H + y) * H + x copy for the fused kernels (cascade 1, H a multiple of 32)
     const __half2 *torso_table = nullptr;
     const float *torso_density = nullptr;
     const __half *head_mlp = nullptr, *torso_mlp = nullptr, *audio = nullptr, *torso_const = nullptr;
@@ -112,6 +113,19 @@ struct ErnerfState {
 __global__ void k_level_scales(float S, uint32_t H, int L, float *out) {
     const uint32_t level = threadIdx.x;
     if ((int)level < L) out[level] = exp2f(level * S) * H - 1.0f;
+}
+
+// load-time: the density bitfield (Morton order, raymarching.cu:56-71,894-895) re-indexed as (z * H + y) * H + x, same bits
+__global__ void k_linear_bitfield(const uint8_t *__restrict__ morton, uint32_t H, uint32_t *linear_words) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;   // one 32-voxel word along x
+    if (w >= H * H * H / 32) return;
+    const uint32_t x0 = (w * 32) % H, y = (w * 32 / H) % H, z = w * 32 / (H * H);
+    uint32_t bits = 0;
+    for (uint32_t i = 0; i < 32; i++) {
+        const uint32_t m = morton3D(x0 + i, y, z);
+        if (morton[m / 8] & (1u << (m % 8))) bits |= 1u << i;
+    }
+    linear_words[w] = bits;
 }
 
 static void fill_levels(GridLevel *lv, int L, const float *scales, const int32_t *offsets, uint32_t gridtype) {
@@ -168,6 +182,7 @@ struct SetupBatch {   // one audio CTA per frame of a batched render (HEAD_MAX_F
     float bound, min_near, dt_gamma;
     uint32_t max_steps, cascade, grid_size;
     const uint8_t *bitfield;
+    const uint8_t *bitfield_linear;   // nullable
     float aabb[6];
 };
 __device__ __forceinline__ void audio_cta(const SetupParams &p, int b);
@@ -178,7 +193,8 @@ __device__ __forceinline__ void gen_ray(const FrameGeom &g, int idx, Ray &r);
 // their final head result here (weights_sum = 0, image = 0).
 __device__ __forceinline__ void ray_pass(const SetupBatch &b, int cta, int n_ctas) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    const MarchParams mp = make_march_params(b.bound, b.dt_gamma, b.max_steps, b.cascade, b.grid_size, b.bitfield);
+    MarchParams mp = make_march_params(b.bound, b.dt_gamma, b.max_steps, b.cascade, b.grid_size, b.bitfield);
+    if (b.bitfield_linear) { mp.grid = b.bitfield_linear; mp.linear = true; }
     for (int f = 0; f < b.n; f++) {
         const RayPassFrame &fr = b.r[f];
         const int n_tiles = (fr.g.N + 31) / 32;
@@ -409,6 +425,12 @@ __device__ __forceinline__ void load_a(uint32_t (&a)[4], const __half *tile, int
 // torso tiles (run by k_head's warps once they are out of rays) and k_compose
 // =========================================================================================
 #define TX_STRIDE 88 /* torso_net input tile: [feat 32 | freq 34 | pad] = 80 + 8 */
+#ifndef TORSO_GL
+#define TORSO_GL 4   /* torso grid levels gathered together */
+#endif
+#ifndef TORSO_MINB
+#define TORSO_MINB 3 /* k_torso_compose CTAs per SM the register allocation aims at */
+#endif
 
 struct TorsoModel {   // shared by the frames of a batch
     TorsoLevels tl;
@@ -440,6 +462,56 @@ __device__ __forceinline__ float grid_sample_ac(const float *img, int G, float x
     out = fmaf(at(y1, x1), se, out);
     return out;
 }
+
+// the 16 levels of the torso grid (fp16 table, C = 2), four levels at a time: corner indices first, then their 16 loads back to
+// back, then the per-level sums -- same arithmetic per level as grid_level_f16x2 (bit-identical features), but 4 exposed L2
+// latencies per pixel instead of 16.  ND = number of leading dense levels (9 for the shipped 16 -> 2048 grid); ND < 0 = generic.
+template <int ND>
+__device__ __forceinline__ void torso_gather_t(const TorsoModel &tm, float u, float v, __half *row) {
+    if (ND < 0) {
+#pragma unroll
+        for (int l = 0; l < MF_ERNERF_TORSO_LEVELS; l++) {
+            float o0, o1;
+            grid_level_f16x2<IDX_ANY>(tm.table, tm.tl.lv[l], u, v, o0, o1);
+            *reinterpret_cast<uint32_t *>(row + 2 * l) = pack_half2(o0, o1);
+        }
+        return;
+    }
+    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f) {   // grid_level_f16x2's bounds test
+#pragma unroll
+        for (int l = 0; l < MF_ERNERF_TORSO_LEVELS; l++) *reinterpret_cast<uint32_t *>(row + 2 * l) = 0u;
+        return;
+    }
+    constexpr int GL = TORSO_GL;
+#pragma unroll
+    for (int l0 = 0; l0 < MF_ERNERF_TORSO_LEVELS; l0 += GL) {
+        uint32_t idx[GL][4];
+        float pu[GL], pv[GL];
+        __half2 val[GL][4];
+#pragma unroll
+        for (int j = 0; j < GL; j++) {
+            if (l0 + j < ND) grid_level_prep<IDX_DENSE>(tm.tl.lv[l0 + j], u, v, idx[j], pu[j], pv[j]);
+            else grid_level_prep<IDX_TILE2>(tm.tl.lv[l0 + j], u, v, idx[j], pu[j], pv[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < GL; j++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) val[j][c] = __ldg(tm.table + idx[j][c]);
+#pragma unroll
+        for (int j = 0; j < GL; j++) {
+            const float w[4] = {(1 - pu[j]) * (1 - pv[j]), pu[j] * (1 - pv[j]), (1 - pu[j]) * pv[j], pu[j] * pv[j]};
+            float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float2 f = __half22float2(val[j][c]);
+                o0 = round_half(o0 + round_half(w[c] * f.x));
+                o1 = round_half(o1 + round_half(w[c] * f.y));
+            }
+            *reinterpret_cast<uint32_t *>(row + 2 * (l0 + j)) = pack_half2(o0, o1);
+        }
+    }
+}
+__device__ __noinline__ void torso_gather_generic(const TorsoModel &tm, float u, float v, __half *row) { torso_gather_t<-1>(tm, u, v, row); }
 
 // torso occupancy + deformation + tiled grid + MLPs (network.py:166-201, renderer.py:294-344) for one tile of 32 pixels;
 // returns this lane's pixel's bgc = torso_color * torso_alpha + bg * (1 - torso_alpha).  mlp / bias: shared-memory torso MLP
@@ -513,14 +585,8 @@ if (mmask) {
     if (masked) {
         const float u = (clampf_(xin[0] + dxy[0], -1.f, 1.f) + 1.f) * 0.5f;
         const float v = (clampf_(xin[1] + dxy[1], -1.f, 1.f) + 1.f) * 0.5f;
-#pragma unroll
-        for (int l = 0; l < MF_ERNERF_TORSO_LEVELS; l++) {
-            float o0, o1;
-            if (tm.tl.n_dense < 0) grid_level_f16x2<IDX_ANY>(tm.table, tm.tl.lv[l], u, v, o0, o1);
-            else if (l < tm.tl.n_dense) grid_level_f16x2<IDX_DENSE>(tm.table, tm.tl.lv[l], u, v, o0, o1);
-            else grid_level_f16x2<IDX_TILE2>(tm.table, tm.tl.lv[l], u, v, o0, o1);
-            *reinterpret_cast<uint32_t *>(row + 2 * l) = pack_half2(o0, o1);
-        }
+        if (tm.tl.n_dense == 9) torso_gather_t<9>(tm, u, v, row);
+        else torso_gather_generic(tm, u, v, row);
     } else {
 #pragma unroll
         for (int l = 0; l < 16; l++) *reinterpret_cast<uint32_t *>(row + 2 * l) = 0u;
@@ -622,6 +688,7 @@ struct HeadParams {
     const float *planes;
     uint32_t plane_rows;
     const uint8_t *bitfield;
+    const uint8_t *bitfield_linear;   // nullable
     const __half *mlp_image;
     float bound, min_near, dt_gamma, T_thresh;
     uint32_t max_steps, cascade, grid_size;
@@ -776,19 +843,6 @@ __device__ __forceinline__ void head_mlp_tile(const HeadSmem &sm, const float *e
 
 // enc_x of one sample -> fp16 row of the warp's tile.  ND = number of leading dense levels (the shipped
 // architecture has 4: base 64, 512 desired, 2^14 hash rows); ND < 0 = generic indexing.
-// corner indices and fractions of one level (the first half of grid_level_f32, ernerf_device.cuh)
-template <int CLS>
-__device__ __forceinline__ void grid_level_prep(const GridLevel &lv, float u, float v, uint32_t (&idx)[4], float &pu, float &pv) {
-    pu = fmaf(u, lv.scale, 0.5f); pv = fmaf(v, lv.scale, 0.5f);
-    const float flu = floorf(pu), flv = floorf(pv);
-    const uint32_t gx = (uint32_t)flu, gy = (uint32_t)flv;
-    pu -= (float)gx;
-    pv -= (float)gy;
-    idx[0] = lv.offset + grid_index2c<CLS>(lv, gx, gy);
-    idx[1] = lv.offset + grid_index2c<CLS>(lv, gx + 1, gy);
-    idx[2] = lv.offset + grid_index2c<CLS>(lv, gx, gy + 1);
-    idx[3] = lv.offset + grid_index2c<CLS>(lv, gx + 1, gy + 1);
-}
 
 // enc_x of one sample -> fp16 row of the warp's tile.  ND = number of leading dense levels (the shipped
 // architecture has 4: base 64, 512 desired, 2^14 hash rows); ND < 0 = generic indexing.
@@ -887,7 +941,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
     mbar_wait(&sm.bar, 0);
     __syncthreads();
 
-    const MarchParams mp = make_march_params(p.bound, p.dt_gamma, p.max_steps, p.cascade, p.grid_size, p.bitfield);
+    MarchParams mp = make_march_params(p.bound, p.dt_gamma, p.max_steps, p.cascade, p.grid_size, p.bitfield);
+    if (p.bitfield_linear) { mp.grid = p.bitfield_linear; mp.linear = true; }
     __half *xs = sm.w[warp].xs;
     __half *sh = sm.w[warp].sh;
     float (*rs)[32] = sm.w[warp].ray;
@@ -1091,7 +1146,7 @@ struct TorsoSmem {
     float anchor[48];
 };
 
-__global__ void __launch_bounds__(TORSO_THREADS) k_torso_compose(const __grid_constant__ ComposeParams p) {
+__global__ void __launch_bounds__(TORSO_THREADS, TORSO_MINB) k_torso_compose(const __grid_constant__ ComposeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TorsoSmem &sm = *reinterpret_cast<TorsoSmem *>(smem_raw);
     // ---- the reference's loop control (renderer.py:246-256) replayed on the life histogram k_head filled:
@@ -1347,6 +1402,7 @@ void ernerf_destroy(mf_ctx *ctx) {
     ernerf_free_ws(s);
     cudaFree(s->state);
     cudaFree(s->counters);
+    cudaFree(s->bitfield_linear);
     if (s->ev_head[0]) { cudaEventDestroy(s->ev_head[0]); cudaEventDestroy(s->ev_head[1]); }
     delete s;
     ctx->ernerf = nullptr;
@@ -1427,6 +1483,10 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
 
     MF_CUDA(ctx, cudaMalloc(&s->state, ST_FLOATS * sizeof(float)));
     MF_CUDA(ctx, cudaMemset(s->state, 0, ST_FLOATS * sizeof(float)));
+    if (cfg->cascade == 1 && (G & (G - 1)) == 0 && G >= 32) {
+        MF_CUDA(ctx, cudaMalloc(&s->bitfield_linear, G * G * G / 8));
+        k_linear_bitfield<<<(unsigned)((G * G * G / 32 + 255) / 256), 256>>>(s->bitfield, (uint32_t)G, reinterpret_cast<uint32_t *>(s->bitfield_linear));
+    }
     MF_CUDA(ctx, cudaMalloc(&s->counters, 2 * CT_INTS * sizeof(int)));
     MF_CUDA(ctx, cudaMemset(s->counters, 0, 2 * CT_INTS * sizeof(int)));
 
@@ -1618,7 +1678,7 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
     }
     sb.bound = s0->cfg.bound; sb.min_near = s0->cfg.min_near; sb.dt_gamma = s0->cfg.dt_gamma;
     sb.max_steps = s0->cfg.max_steps; sb.cascade = s0->cfg.cascade; sb.grid_size = s0->cfg.grid_size;
-    sb.bitfield = s0->bitfield;
+    sb.bitfield = s0->bitfield; sb.bitfield_linear = s0->bitfield_linear;
     for (int i = 0; i < 6; i++) sb.aabb[i] = aabb[i];
     {   // 8 audio CTAs per frame first, then the ray pass: one CTA (32 warps, one ray per lane) per SM that is left
         const int n_audio = 8 * n;
@@ -1629,6 +1689,7 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
 
     HeadParams hp;
     hp.hl = s0->hl; hp.planes = s0->planes; hp.plane_rows = s0->plane_rows; hp.bitfield = s0->bitfield;
+    hp.bitfield_linear = s0->bitfield_linear;
     hp.mlp_image = s0->head_mlp;
     hp.bound = s0->cfg.bound; hp.min_near = s0->cfg.min_near; hp.dt_gamma = s0->cfg.dt_gamma; hp.T_thresh = s0->cfg.T_thresh;
     hp.max_steps = s0->cfg.max_steps; hp.cascade = s0->cfg.cascade; hp.grid_size = s0->cfg.grid_size;

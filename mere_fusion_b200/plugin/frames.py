@@ -34,7 +34,9 @@ except ImportError:
 
         @classmethod
         def from_ndarray(cls, arr, format="bgr24"):
-            return cls(arr, format)
+            # av.VideoFrame.from_ndarray COPIES the pixels into the frame's planes; the plugin relies on that (it hands over
+            # views into a pinned ring that is overwritten a few batches later), so the stand-in copies too
+            return cls(np.array(arr, copy=True), format)
 
         def to_ndarray(self, format=None):
             return self._arr
