@@ -149,6 +149,11 @@ def config1_cpu_plumbing(seconds=10.0):
 
 
 def run_reference(args):
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    return _run_reference(args)
+
+
+def _run_reference(args):
     """--impl reference: the reference has NO CPU renderer for ErNeRF (renderer.py:664 always
     dispatches to run_cuda), so the CPU arm is the oracle port (kind "port") on all host cores,
     each step a bounded sub-grid sample of the 512x512 workload."""
@@ -159,13 +164,10 @@ def run_reference(args):
     from oracle.ernerf_oracle import ErnerfOracle
     sd, md = load_ernerf_fixture()
     orc = ErnerfOracle(sd, md)
-    budget = 150.0
-    pose, intr, auds, eye = ernerf_inputs(0, 48, 48)
-    t0 = time.perf_counter()
-    orc.render_frame(pose, intr, 48, 48, auds, eye)
-    rate = 48 * 48 / (time.perf_counter() - t0)            # rays/s, first estimate
-    per_step = budget / max(1, args.steps + args.warmup)
-    n_side = int(max(32, min(256, np.sqrt(rate * per_step))))
+    # a CONSTANT sample (the same 96x96 sub-grid of the 512x512 ray grid every run, all host cores): the sample used to be sized
+    # from a first-estimate rate, which made this arm drift 2x between boxes
+    n_side = 96
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
     for w in range(args.warmup):
         orc.render_frame(*ernerf_inputs(w, n_side, n_side)[:2], n_side, n_side, *ernerf_inputs(w, n_side, n_side)[2:])
     t0 = time.perf_counter()
@@ -383,6 +385,120 @@ def torch_gpu_whisper(dev, flush):
     return {"ms_per_window": float(np.median(ts)) * 1e3, "feature_shape": list(feat.shape),
             "what": "vendored reference Whisper-tiny (unmodified, oracle/_ref/py) Audio2Feature.audio2feat on one 52-chunk window, host audio in / "
                     "numpy out, on the same GPU (the reference pads every window to 30 s before the encoder, transcribe.py:108)"}
+
+
+class _TimedQueue:
+    """the aiortc track queue of the fake tracks: every put is time-stamped; never reports a backlog"""
+
+    def __init__(self):
+        self.t = []
+
+    async def put(self, x):
+        self.t.append(time.perf_counter())
+
+    def qsize(self):
+        return 0
+
+
+class _TimedTrack:
+    def __init__(self):
+        self._queue = _TimedQueue()
+
+
+def plugin_drive(real, B, wav, n_tp, n_lat):
+    """What the DROP-IN delivers (reference loops lipreal.py:232-250, musereal.py:267-290, nerfreal.py:129-156):
+    the plugin object itself -- put_audio_frame -> asr.run_step -> inference -> process_frames -> VideoFrame + 2 AudioFrame on the
+    (fake) tracks, its own threads and queues -- driven (1) at full speed, all audio queued up front: frames/s out of
+    video_track._queue; (2) closed loop, one engine step in flight: p50 of [put_audio_frame of the last chunk of a step ->
+    the last video frame of that step on the track] (SURVEY 8(d) latency definition; excludes the reference's fixed look-ahead).
+    B = video frames per engine step (16 Lip / Muse, 1 ErNeRF)."""
+    vt, at = _TimedTrack(), _TimedTrack()
+    quit_event = threading.Event()
+    real.asr.poll_timeout = 30.0                 # wait for audio instead of substituting silence: every frame below is a speech frame
+    cps = 2 * B                                  # chunks per step
+    pos = [0]
+
+    def feed(n):
+        for _ in range(n):
+            i = pos[0] % (len(wav) // 320)
+            real.put_audio_frame(wav[i * 320:(i + 1) * 320])
+            pos[0] += 1
+
+    feed(cps * (n_tp + 3))
+    th = threading.Thread(target=real.render, args=(quit_event, None, at, vt), daemon=True)
+    t_start = time.perf_counter()
+    th.start()
+    want = B * (n_tp + 2)
+    while len(vt._queue.t) < want and time.perf_counter() - t_start < 120:
+        time.sleep(0.002)
+    tv = list(vt._queue.t)
+    fps = (want - 2 * B) / (tv[want - 1] - tv[2 * B - 1]) if len(tv) >= want else None
+    # drain what is left of the throughput phase
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 10:
+        n0 = len(vt._queue.t)
+        time.sleep(0.1)
+        if len(vt._queue.t) == n0:
+            break
+    lats = []
+    for _ in range(n_lat):
+        base = len(vt._queue.t)
+        feed(cps)
+        t_put = time.perf_counter()
+        while len(vt._queue.t) < base + B and time.perf_counter() - t_put < 20:
+            time.sleep(0.0002)
+        if len(vt._queue.t) >= base + B:
+            lats.append((vt._queue.t[base + B - 1] - t_put) * 1e3)
+    quit_event.set()
+    feed(cps * 2)                                # unblock a run_step that waits for audio
+    th.join(timeout=20)
+    nv, na = len(vt._queue.t), len(at._queue.t)
+    return {"frames_per_s": fps, "p50_last_chunk_to_last_frame_of_step_ms": float(np.median(lats)) if lats else None,
+            "frames_per_step": B, "steps_full_speed": n_tp, "steps_closed_loop": len(lats), "video_frames": nv, "audio_frames": na,
+            "audio_per_video": na / max(nv, 1)}
+
+
+def plugin_legs(args, dev, local, shared, ernerf_blob, ernerf_cfg, w2v):
+    """heads.<head>.plugin: LipReal / MuseReal / NeRFReal constructed as app.py does (fake avatar / tracks), see plugin_drive"""
+    import torch
+    from helpers import load_pose_fixture, synthetic_speech
+    from test_plugin_cpu import _fake_avatar, _fake_muse_avatar, make_opt
+    out = {}
+    wav = synthetic_speech(160000, 0)
+    try:
+        if "wav2lip_blob" in shared:
+            from mere_fusion_b200.plugin.lipreal import LipReal
+            from mere_fusion_b200.wav2lip import Wav2LipEngine
+            real = LipReal(make_opt(), engine=Wav2LipEngine(blob=shared["wav2lip_blob"], max_batch=16, device=local), avatar=_fake_avatar(), paste="gpu")
+            out["wav2lip"] = plugin_drive(real, 16, wav, 40, 15)
+    except Exception as e:                                   # noqa: BLE001
+        out["wav2lip"] = {"error": repr(e)[:300]}
+    try:
+        if "musetalk_engine" in shared:
+            from mere_fusion_b200.plugin.musereal import MuseReal
+            real = MuseReal(make_opt(), engine=shared["musetalk_engine"], audio_processor=shared["a2f"], avatar=_fake_muse_avatar(), paste="gpu")
+            out["musetalk"] = plugin_drive(real, 16, wav, 12, 8)
+    except Exception as e:                                   # noqa: BLE001
+        out["musetalk"] = {"error": repr(e)[:300]}
+    try:
+        from mere_fusion_b200.ernerf import ErnerfRenderer
+        from mere_fusion_b200.ernerf_data import ErnerfPoseProvider
+        from mere_fusion_b200.plugin.nerfreal import NeRFReal
+        pf = load_pose_fixture()
+        tr = dict(cx=W / 2.0, cy=H / 2.0, focal_len=float(pf["focal_len"]) * H / (2 * float(pf["cy"])),
+                  frames=[dict(transform_matrix=pf["raw"][i].tolist(), img_id=int(pf["img_id"][i])) for i in range(290)])
+        au = np.zeros(int(pf["img_id"][:290].max()) + 1)
+        au[:min(len(au), len(pf["au"]))] = pf["au"][:len(au)]
+        for name, fn in (("ernerf_synthetic_logits", lambda fr: torch.zeros(((len(fr) - 400) // 320 + 1, 44))),
+                         ("ernerf_with_wav2vec2", w2v.feature_fn if w2v is not None else None)):
+            if fn is None:
+                continue
+            ren = ErnerfRenderer(blob=ernerf_blob, cfg=ernerf_cfg, device=local)
+            real = NeRFReal(make_opt(W=W, H=H), ren, ErnerfPoseProvider(tr, au), feature_fn=fn, device=local)
+            out[name] = plugin_drive(real, 1, wav, 300, 60)
+    except Exception as e:                                   # noqa: BLE001
+        out["ernerf"] = {"error": repr(e)[:300]}
+    return out
 
 
 def p50_latency_ms(step_host, n=30):
@@ -669,6 +785,40 @@ def musetalk_leg(args, dev, local, rank, world, flush, timed_fn, pk, shared=None
                          "ms_per_launch": m * 1e3, "traffic": None, "peak_source": pk["src"] + " burst"}}
 
 
+def musetalk_streams_leg(args, dev, local, rank, world, timed_fn, shared, n_streams=8):
+    """BASELINE configs[2] as written: 8 concurrent MuseTalk streams on one GPU.  Every stream is a session (own avatar latents,
+    own audio window) served by the GPU's shared engine (scheduler.SharedEngine: the sessions' 16-frame requests of a step are
+    coalesced into passes of the one resident UNet + VAE); one step = every stream advances 16 frames."""
+    import torch
+    from helpers import synthetic_speech
+    from mere_fusion_b200.scheduler import SharedEngine
+    B = 16
+    eng, a2f = shared["musetalk_engine"], shared["a2f"]
+    sh = SharedEngine(eng, threaded=False)
+    rng = np.random.default_rng(77 + rank)
+    lat = [torch.from_numpy((rng.standard_normal((B, 8, 32, 32)) * 0.18215 * 5).astype(np.float16)).to(dev) for _ in range(n_streams)]
+    audio = [torch.from_numpy(synthetic_speech(52 * 320, 400 + rank * 8 + i)).to(dev) for i in range(n_streams)]
+    preds = [torch.empty((B, 256, 256, 3), dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+
+    def step(k):
+        reqs = []
+        for i in range(n_streams):
+            chunks = a2f.audio2chunks_device(None, fps=25.0, batch_size=B, start=5.0, audio_dev=audio[(i + k) % n_streams])
+            reqs.append(sh.submit(lat[i], chunks, out=preds[i]))
+        sh.flush()
+        for rq in reqs:
+            sh.wait(rq)
+
+    K = max(3, args.steps // 30)
+    tot, _, _ = timed_fn(step, K, 3)
+    sh.shutdown()
+    fps = world * K * n_streams * B / (tot / 1e3)
+    return {"workload": f"{n_streams} concurrent MuseTalk streams per GPU on {world} GPU(s) (BASELINE configs[2]), 16 frames per stream and step, "
+                        "Whisper window + UNet + VAE per stream through the shared engine (no paste)",
+            "value": fps, "unit": "frames/s (aggregate)", "ms_per_step": tot / K, "frames_per_step_per_gpu": n_streams * B,
+            "fps_per_stream": fps / (world * n_streams), "realtime_streams_capacity_25fps": fps / 25.0}
+
+
 def mixed_leg(args, dev, local, rank, world, flush, timed_fn, shared, ernerf_blob, ernerf_cfg):
     """BASELINE configs[4] / SURVEY 8(d) config 5: 64 concurrent mixed sessions on 8 GPUs = 8 sessions per GPU, heads round-robin by
     session id (22 ErNeRF + 21 MuseTalk + 21 Wav2Lip in total, every GPU hosts all three heads).  This rank runs ITS 8 sessions
@@ -842,6 +992,7 @@ def main():
     ap.add_argument("--no-asr", action="store_true")
     ap.add_argument("--no-mixed", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-plugin", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -1019,6 +1170,7 @@ def main():
     # (= every 4 video frames, nerfasr.py:105-124); reported beside the render, not inside its step (SURVEY 8(d) config 4 feeds
     # synthetic logit windows)
     asr = None
+    w2v = None
     if not args.no_asr:
         from helpers import W2V_XLSR53, seeded_w2v_state, synthetic_speech
         from mere_fusion_b200.wav2vec2 import Wav2Vec2Engine
@@ -1045,7 +1197,25 @@ def main():
                "gpu_launches_per_window": w2v.last_launches, "gflop_per_window": meta_a["flops"] / 1e9,
                "batched_4_sessions": {"ms_per_pass": asr_b_ms / max(20, args.steps // 4), "ms_per_window": asr_b_ms / max(20, args.steps // 4) / 4,
                                       "ms_per_video_frame_amortised": asr_b_ms / max(20, args.steps // 4) / 16}}
-        del w2v, blob_a
+
+    # ---- SURVEY 8(e) single-stream scaling: ONE session's frames sharded round-robin over the ranks; every rank follows the
+    # session's audio state (mf_ernerf_encode_audio on every frame) and renders only its own frames with the feature passed
+    # explicitly (bit-identical to the in-order stream: tests/test_ernerf_gpu.py).  K frames per rank and pass.
+    ren_s = ErnerfRenderer(blob=blob, cfg=cfg, device=local)
+    ins_s = [ernerf_inputs(f % 290, H, W) for f in range(16 * world)]
+    auds_s = [torch.from_numpy(i[2]).to(dev) for i in ins_s]
+    enc_s = torch.empty(32, dtype=torch.float32, device=dev)
+
+    def step_sharded(k):
+        for j in range(world):                      # frames k*world .. k*world + world - 1 of the session; this rank owns one
+            i = (k * world + j) % len(ins_s)
+            ren_s.encode_audio(auds_s[i], out=enc_s)
+            if j == rank:
+                p_, intr_, _, eye_ = ins_s[i]
+                ren_s.render(p_, intr_, H, W, None, eye_, out=out, enc_a=enc_s)
+
+    shard_ms, _, _ = timed(step_sharded, args.steps, args.warmup)
+    del ren_s
 
     value = world * args.steps / (total_ms / 1e3)
     e2e_value = world * args.steps / (e2e_ms / 1e3)
@@ -1056,8 +1226,16 @@ def main():
         heads["wav2lip_256"] = wav2lip_leg(args, dev, local, rank, world, flush, timed, peaks(), S=256)
     if not args.no_musetalk:
         heads["musetalk"] = musetalk_leg(args, dev, local, rank, world, flush, timed, peaks(), shared=shared)
+    if not args.no_musetalk and "musetalk_engine" in shared:
+        try:
+            heads["musetalk_8streams"] = musetalk_streams_leg(args, dev, local, rank, world, timed, shared)
+        except Exception as e:                           # noqa: BLE001
+            heads["musetalk_8streams"] = {"error": repr(e)[:300]}
     if not args.no_mixed and "wav2lip_blob" in shared and "musetalk_engine" in shared:
         heads["mixed_sessions"] = mixed_leg(args, dev, local, rank, world, flush, timed, shared, blob, cfg)
+    plugin = None
+    if not args.no_plugin and rank == 0:
+        plugin = plugin_legs(args, dev, local, shared, blob, cfg, w2v)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -1067,10 +1245,23 @@ def main():
     hs = float(np.mean(head_samples))
     ach_gbs = hs * BYTES_PER_SAMPLE / (hm * 1e-3) / 1e9
     ach_tf = hs * FLOP_PER_SAMPLE / (hm * 1e-3) / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_k_head_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    # DRAM traffic + L1 sector rate of k_head from the newest `ncu --set full` capture of this kernel (scripts/gpu/ncu_head.sh writes
+    # the json; copied to profiles/ with the summary of the same capture)
+    import glob
+    traffic, l1_view = None, None
+    caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_head_traffic.json")))
+    if caps:
+        cap = json.load(open(caps[-1]))
+        traffic = cap.get("dram_bytes_per_launch")
+        sec, us = cap.get("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"), cap.get("gpu__time_duration.sum")
+        if sec and us:
+            clk = us * 1e-6 * 1.965e9                     # ncu runs with --clock-control none: boost clock
+            l1_view = {"l1_global_load_sectors_per_launch": sec, "sectors_per_clk_per_sm": sec / clk / 148, "peak_sectors_per_clk_per_sm": 4.0,
+                       "frac": sec / clk / 148 / 4.0, "l1_hit_pct": cap.get("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": cap.get("lts__t_sector_hit_rate.pct"),
+                       "shared_load_wavefronts_pct_of_peak": cap.get("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed"),
+                       "capture": os.path.basename(caps[-1]),
+                       "note": "the tables are L2/L1-resident (DRAM traffic ~2.7 MB per launch): this is the ceiling the gathers actually face; "
+                               "the HBM figure above is the conservative stand-in SURVEY 8(d) prescribes"}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -1097,12 +1288,16 @@ def main():
                          "frac": float(np.mean(bh_samples)) * BYTES_PER_SAMPLE / (float(np.mean(bh_ms)) * 1e-3) / 1e9 / peaks()["hbm"],
                          "ms_per_launch": float(np.mean(bh_ms)), "samples_per_launch": float(np.mean(bh_samples)),
                          "tensor_view_tflops": float(np.mean(bh_samples)) * FLOP_PER_SAMPLE / (float(np.mean(bh_ms)) * 1e-3) / 1e12}},
+        "ernerf_single_stream_sharded": {
+            "workload": f"ONE ErNeRF session, frames round-robin over {world} rank(s), audio state followed on every rank (SURVEY 8e)",
+            "value": world * args.steps / (shard_ms / 1e3), "unit": "frames/s", "ms_per_pass": shard_ms / args.steps},
+        "plugin_level": plugin,
         "nerfasr_acoustic_model": asr,
         "gpu_launches": int(launches),
         "kernels_per_step": ["k_setup (audio encoder CTA + ray pass + torso pass)", "k_head", "k_compose"],
         "clocks": sampler.result(),
         "roofline": {"kernel": "k_head", "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                     "frac": ach_gbs / pk["hbm"], "traffic": traffic, "peak_source": pk["src"] + " burst",
+                     "frac": ach_gbs / pk["hbm"], "traffic": traffic, "l1_view": l1_view, "peak_source": pk["src"] + " burst",
                      "ms_per_launch": hm, "samples_per_launch": hs, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE,
                      "share_of_step": hm / (total_ms / args.steps),
                      "tensor_view": {"achieved": ach_tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf"],

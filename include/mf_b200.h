@@ -166,6 +166,12 @@ int mf_ernerf_render(mf_ctx *ctx, const mf_ernerf_frame *frame /*host*/, uint8_t
  * device blob with the same configuration (one avatar model, many sessions).  Errors are reported on ctxs[0]. */
 int mf_ernerf_render_batch(mf_ctx *const *ctxs /*host*/, const mf_ernerf_frame *frames /*host, [n]*/,
                            uint8_t *const *outs /*host array of device pointers*/, int n, void *stream);
+/* The audio half of a frame on its own: encode_audio (network.py:222-237) + the EMA of renderer.py:190-194 on one attention window,
+ * advancing the session's audio state exactly as mf_ernerf_render would, and writing the smoothed feature to enc_a_out (device fp32
+ * [32]).  SURVEY 8(e): when ONE session's frames are sharded round-robin over several GPUs, every rank follows the session's audio
+ * state with this call (8 small CTAs) and renders only its own frames with mf_ernerf_frame.enc_a set -- frames can then be rendered
+ * out of order and are bit-identical to the in-order stream. */
+int mf_ernerf_encode_audio(mf_ctx *ctx, const float *auds /*device [8, audio_in_dim, 16]*/, float *enc_a_out, void *stream);
 /* forget the audio-feature EMA (a new session on a reused context) */
 int mf_ernerf_reset_state(mf_ctx *ctx);
 /* offsets of the packed-blob MLP images (csrc/ernerf_layout.h) for the Python packer; returns the

@@ -62,6 +62,7 @@ def lib():
                                        ctypes.POINTER(MfErnerfDebug), c_vp]
         L.mf_ernerf_render_batch.argtypes = [ctypes.POINTER(c_vp), ctypes.POINTER(MfErnerfFrame), ctypes.POINTER(c_vp), ctypes.c_int, c_vp]
         L.mf_ernerf_reset_state.argtypes = [c_vp]
+        L.mf_ernerf_encode_audio.argtypes = [c_vp, c_vp, c_vp, c_vp]
         L.mf_ernerf_last_launches.argtypes = [c_vp]
         L.mf_ernerf_profile.argtypes = [c_vp, ctypes.c_int]
         L.mf_ernerf_last_head_ms.argtypes = [c_vp, ctypes.POINTER(c_f), ctypes.POINTER(ctypes.c_int64)]

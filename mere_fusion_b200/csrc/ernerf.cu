@@ -34,6 +34,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -302,13 +303,10 @@ __device__ __forceinline__ void audio_cta(const SetupParams &p, int b) {
     __shared__ float bufA[64 * 16], bufB[64 * 16], att[8];
     __shared__ int s_last;
     const int tid = threadIdx.x;
-    if (b == 0)   // the counters of this context's next frame (this frame's copy is being written by the ray-pass CTAs right now)
+    if (b == 0 && p.counters_next)   // the counters of this context's next frame (this frame's copy is being written by the ray-pass CTAs right now)
         for (int i = tid; i < CT_INTS; i += blockDim.x) p.counters_next[i] = 0;
-    if (p.enc_a_in) {  // pre-encoded feature: no EMA, no state update
-        if (b == 0 && tid < 32) {
-            p.state[tid] = p.enc_a_in[tid];
-            if (p.dbg_enc_a) p.dbg_enc_a[tid] = p.enc_a_in[tid];
-        }
+    if (p.enc_a_in) {  // pre-encoded feature: k_head reads it where the caller put it; no EMA, the session's audio state is untouched
+        if (b == 0 && tid < 32 && p.dbg_enc_a) p.dbg_enc_a[tid] = p.enc_a_in[tid];
         return;
     }
     // ---- AudioNet (network.py:40-66) on window b: x[:, 0:16] -> 4x conv(k3,s2,p1)+LeakyReLU -> fc
@@ -1697,7 +1695,7 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
     for (int i = 0; i < n; i++) {
         ErnerfState *s = pf[i].s;
         HeadFrame &hf = hp.f[i];
-        hf.g = pf[i].g; hf.state = s->state; hf.eye = frames[i].eye;
+        hf.g = pf[i].g; hf.state = frames[i].enc_a ? frames[i].enc_a : s->state; hf.eye = frames[i].eye;
         hf.hits = s->hits; hf.counters = ctr[i];
         hf.rays_t = s->rays_t; hf.fars = s->fars; hf.weights_sum = s->weights_sum; hf.image = s->image; hf.snap = s->snap;
     }
@@ -1755,6 +1753,25 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
         pf[i].s->last_launches = launches;
         pf[i].s->frame_no++;
     }
+    return MF_OK;
+}
+
+// encode_audio + EMA of one attention window, exactly the audio CTAs of a render (same kernel, same state update), without a frame
+extern "C" int mf_ernerf_encode_audio(mf_ctx *ctx, const float *auds, float *enc_a_out, void *stream_) {
+    if (!ctx) return MF_E_INVALID;
+    ErnerfState *s = ctx->ernerf;
+    if (!s) return mf_fail(ctx, MF_E_STATE, "mf_ernerf_encode_audio: ErNeRF weights not loaded");
+    MF_REQUIRE(ctx, auds && enc_a_out, "mf_ernerf_encode_audio: null pointer");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    SetupBatch sb;
+    memset(&sb, 0, sizeof(sb));
+    sb.n = 1;
+    SetupParams &sp = sb.f[0];
+    sp.auds = auds; sp.enc_a_in = nullptr; sp.audio = s->audio; sp.state = s->state; sp.counters_next = nullptr;
+    sp.A = (int)s->cfg.audio_in_dim; sp.N = 0; sp.smooth = (int)s->cfg.smooth_lips; sp.audio_halfs = (int)s->audio_halfs;
+    sp.dbg_enc_a = enc_a_out;
+    k_setup<<<8, SETUP_THREADS, 0, (cudaStream_t)stream_>>>(sb);
+    MF_CUDA(ctx, cudaGetLastError());
     return MF_OK;
 }
 

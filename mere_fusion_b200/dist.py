@@ -52,3 +52,24 @@ def mixed_sessions(n=64):
             if pools[h]:
                 order.append((h, pools[h].pop(0)))
     return order[:n]
+
+
+def stream_shard_plan(n_frames, world, rank):
+    """SURVEY 8(e), single-stream scaling: frame i of ONE session is rendered by rank i % world (frame batches round-robin, the
+    audio window replicated); returns this rank's frame indices"""
+    return [i for i in range(n_frames) if i % world == rank]
+
+
+def render_stream_shard(renderer, frames, world, rank, render_kw=None):
+    """One session's frames [(pose, intrinsics, H, W, auds cuda tensor, eye), ...] sharded over `world` ranks: EVERY rank follows
+    the session's audio state (renderer.encode_audio on every frame: 8 small CTAs), and renders only the frames of
+    stream_shard_plan with the smoothed feature passed explicitly -- so the EMA, the one per-session recurrence
+    (renderer.py:190-194), is carried as an input and the frames are bit-identical to the in-order stream.  Returns {frame index:
+    u8 cuda image}; nothing is exchanged between the ranks."""
+    mine = set(stream_shard_plan(len(frames), world, rank))
+    out = {}
+    for i, (pose, intr, H, W, auds, eye) in enumerate(frames):
+        enc_a = renderer.encode_audio(auds)
+        if i in mine:
+            out[i] = renderer.render(pose, intr, H, W, None, eye, enc_a=enc_a, **(render_kw or {}))
+    return out

@@ -35,6 +35,17 @@ class ErnerfRenderer:
     def reset(self):
         check(self.ctx.handle, lib().mf_ernerf_reset_state(self.ctx.handle), "mf_ernerf_reset_state")
 
+    def encode_audio(self, auds, out=None, stream=None):
+        """the audio half of a frame (encode_audio + EMA, advances the session's audio state): cuda fp32 [8, A, 16] -> cuda fp32 [32].
+        With render(..., enc_a=that) a rank can render any subset of a session's frames bit-identically to the in-order stream
+        (mere_fusion_b200.dist.render_stream_shard)."""
+        if out is None:
+            out = torch.empty(32, dtype=torch.float32, device=self.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        check(self.ctx.handle, lib().mf_ernerf_encode_audio(self.ctx.handle, _ptr(auds), _ptr(out), ctypes.c_void_p(s.cuda_stream)),
+              "mf_ernerf_encode_audio")
+        return out
+
     def profile(self, enable=True):
         check(self.ctx.handle, lib().mf_ernerf_profile(self.ctx.handle, int(enable)), "mf_ernerf_profile")
 

@@ -22,7 +22,8 @@ out = {"kernel": "k_head", "tag": tag, "dram_bytes_read": get("dram__bytes_read.
 out["dram_bytes_per_launch"] = out["dram_bytes_read"] + out["dram_bytes_write"]
 for k in ("gpu__time_duration.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
           "launch__registers_per_thread", "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
-          "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"):
+          "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+          "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum"):
     try:
         out[k] = get(k)
     except ValueError:

@@ -69,3 +69,56 @@ def test_shard_is_a_partition():
     assert len(s) == 64 and sorted(x[0] for x in s).count("ernerf") == 22
     parts = [shard(s, 8, r) for r in range(8)]
     assert sorted(sum(parts, [])) == sorted(s) and all(len(p) == 8 for p in parts)
+
+
+def _shard_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mere_fusion_b200.dist import render_stream_shard, stream_shard_plan
+
+    class HostRenderer:
+        """stands in for ErnerfRenderer on the CPU: the same two calls, the EMA of renderer.py:190-194 as the only state"""
+        def __init__(self):
+            self.prev = None
+
+        def encode_audio(self, auds):
+            raw = auds.mean(dim=(0, 2))[:32]
+            self.prev = raw if self.prev is None else 0.35 * self.prev + 0.65 * raw
+            return self.prev.clone()
+
+        def render(self, pose, intr, H, W, auds, eye, enc_a=None):
+            assert auds is None and enc_a is not None                   # sharded frames carry the feature explicitly
+            return (enc_a.sum() * 1000 + float(pose) + eye).reshape(1)
+
+    g = torch.Generator().manual_seed(5)
+    frames = [(float(i), None, 4, 4, torch.randn(8, 44, 16, generator=g), 0.25) for i in range(11)]
+    part = render_stream_shard(HostRenderer(), frames, world, rank)
+    assert sorted(part) == stream_shard_plan(len(frames), world, rank)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {k: float(v) for k, v in part.items()})      # test-only: the product exchanges nothing
+    if rank == 0:
+        merged = {}
+        for d in gathered:
+            merged.update(d)
+        inorder = render_stream_shard(HostRenderer(), frames, 1, 0)
+        q.put((sorted(merged) == list(range(len(frames))), all(abs(merged[i] - float(inorder[i])) == 0.0 for i in merged)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_single_stream_frame_sharding_world2():
+    """one session's frames round-robin over 2 ranks with the audio state followed on every rank: the union of the
+    ranks' frames is the in-order stream (host logic on gloo; the GPU version is tests/test_ernerf_gpu.py)"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    complete, equal = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert complete and equal

@@ -388,3 +388,47 @@ def test_render_batch_equals_single_renders(env):
         ErnerfRenderer.render_batch([rens[0], other], frames(0)[:2])
     with pytest.raises(MfError):
         ErnerfRenderer.render_batch(rens + [other], frames(0) + frames(0)[:1])        # more than 4
+
+
+def test_single_stream_sharded_over_ranks_is_bit_identical(env):
+    """ONE session's frames sharded round-robin over W ranks, every rank following the audio state with
+    mf_ernerf_encode_audio and rendering only its own frames with the smoothed feature passed explicitly
+    (mf_ernerf_frame.enc_a): each frame equals the in-order stream's frame bit for bit, and so does the audio feature"""
+    from mere_fusion_b200.dist import render_stream_shard, stream_shard_plan
+    from mere_fusion_b200.ernerf import ErnerfRenderer
+    H = 128
+    n = 9
+    frames = []
+    for f in range(n):
+        pose, intr, auds, eye = ernerf_inputs(f, H, H)
+        frames.append((pose, intr, H, H, cu(auds), eye))
+    stream = ErnerfRenderer(env["sd"], env["md"], device=0)           # the in-order session
+    ref, ref_enc = [], []
+    for pose, intr, _, _, auds, eye in frames:
+        img, dbg = stream.render(pose, intr, H, H, auds, eye, debug=True)
+        ref.append(img.clone())
+        ref_enc.append(dbg["enc_a"].clone())
+    for world in (2, 3):
+        got = {}
+        for rank in range(world):                                      # one renderer per simulated rank (own context, own audio state)
+            r = ErnerfRenderer(env["sd"], env["md"], device=0)
+            part = render_stream_shard(r, frames, world, rank)
+            assert sorted(part) == stream_shard_plan(n, world, rank)
+            got.update(part)
+        torch.cuda.synchronize()
+        assert sorted(got) == list(range(n))
+        for i in range(n):
+            assert torch.equal(got[i], ref[i]), f"world {world}: frame {i} differs from the in-order stream"
+    # the audio half on its own reproduces the render's smoothed feature, frame after frame
+    r = ErnerfRenderer(env["sd"], env["md"], device=0)
+    for i, fr in enumerate(frames):
+        assert torch.equal(r.encode_audio(fr[4]), ref_enc[i]), f"enc_a of frame {i}"
+    # an explicit enc_a leaves the session's audio state alone
+    before = r.encode_audio(frames[0][4]).clone()
+    r2 = ErnerfRenderer(env["sd"], env["md"], device=0)
+    a0 = r2.encode_audio(frames[0][4]).clone()
+    r2.render(frames[1][0], frames[1][1], H, H, None, frames[1][5], enc_a=cu(np.zeros(32, np.float32)))
+    a1 = r2.encode_audio(frames[1][4])
+    r3 = ErnerfRenderer(env["sd"], env["md"], device=0)
+    r3.encode_audio(frames[0][4])
+    assert torch.equal(a1, r3.encode_audio(frames[1][4])) and before is not None and a0 is not None
