@@ -101,7 +101,6 @@ struct ErnerfState {
     float *rays_t = nullptr, *fars = nullptr, *weights_sum = nullptr, *image = nullptr;
     float *final_f32 = nullptr;  // [N,3] when a resize follows
     int head_grid = 0;
-    bool warp_specialised = false;  // MF_HEAD_WS=1: k_head_ws (producer / consumer warps) instead of k_head -- measured slower, kept as the experiment
     int chunk = 2;           // CH: samples of a ray shaded side by side (MF_HEAD_CHUNK = 1 | 2 | 4 | 8; 2 measured best)
     int last_launches = 0;
     float misc_host[24] = {0};
@@ -1122,317 +1121,6 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 }
 
 // =========================================================================================
-// k_head_ws (EXPERIMENT, off by default: MF_HEAD_WS=1): the same algorithm, warp-specialised (profiles/r02_k_head_v8_ncu_summary.md:
-// nothing is saturated in k_head, it is bound by per-warp latency at 16 warps per SM, and the registers are held by the MLP
-// accumulators).  Measured: 375 us against k_head's 243 us per 512x512 frame (profiles/r02_k_head_ws_experiment.md) -- the MLP
-// chain of a tile is itself latency-bound per warp, so 8 consumer warps cannot keep up with what 16 interleaved warps did, and
-// the register pool of the CTA (threads x launch registers) does not allow more warps on either side.
-//   producer warps (WS_PRODUCERS, setmaxnreg 64): refill, march, tri-plane gather -> fp16 tile in shared memory, compositing
-//   consumer warps (WS_CONSUMERS, setmaxnreg 128): the 9 MLP layers of a producer's 32-sample tile on mma.sync, results back
-// A producer hands its tile over with one mbarrier arrival and waits on a second one; consumer c serves the producers p with
-// p % WS_CONSUMERS == c.  Per-sample arithmetic is head_mlp_tile / the compositor above, untouched: bit-identical images.
-// =========================================================================================
-#ifndef WS_PRODUCERS
-#define WS_PRODUCERS 16
-#endif
-#ifndef WS_CONSUMERS
-#define WS_CONSUMERS 8
-#endif
-#define WS_THREADS ((WS_PRODUCERS + WS_CONSUMERS) * 32)
-#ifndef WS_PROD_REGS
-#define WS_PROD_REGS 64
-#endif
-#ifndef WS_CONS_REGS
-#define WS_CONS_REGS 112
-#endif
-// setmaxnreg moves registers inside the pool the CTA was launched with (threads x launch registers = 768 x 80), not the SM's
-// whole file: the two budgets must fit that pool or the consumers' setmaxnreg.inc waits forever
-static_assert(WS_PRODUCERS * WS_PROD_REGS + WS_CONSUMERS * WS_CONS_REGS <= (WS_PRODUCERS + WS_CONSUMERS) * 80, "register pool");
-#define WS_STR2(x) #x
-#define WS_STR(x) WS_STR2(x)
-
-struct WsWarpSmem {   // one per producer warp
-    alignas(16) __half xs[32 * XS_STRIDE];
-    alignas(16) __half sh[32 * SH_STRIDE];
-    float ray[9][32];
-    float4 res[32];      // per sample: sigma logit, r, g, b
-    int fi[32];          // per sample: frame of the batch
-    uint32_t hasmask;
-    int fin;
-    alignas(8) uint64_t full, done;
-};
-struct WsSmem {
-    alignas(16) unsigned char mlp[ER_H_BYTES];
-    alignas(16) WsWarpSmem w[WS_PRODUCERS];
-    float enc_a[HEAD_MAX_FRAMES][32];
-    float eye[HEAD_MAX_FRAMES];
-    int end[HEAD_MAX_FRAMES];
-    int hist[HEAD_MAX_FRAMES][ER_MAX_STEPS + 1];
-    int samples[HEAD_MAX_FRAMES];
-    alignas(8) uint64_t bar;
-};
-
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t phase) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_arrive1(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <int CH>
-__device__ __forceinline__ void ws_producer(const HeadParams &p, WsSmem &sm, int warp, int lane) {
-    WsWarpSmem &w = sm.w[warp];
-    const int F = p.n_frames;
-    MarchParams mp = make_march_params(p.bound, p.dt_gamma, p.max_steps, p.cascade, p.grid_size, p.bitfield);
-    if (p.bitfield_linear) { mp.grid = p.bitfield_linear; mp.linear = true; }
-    __half *xs = w.xs;
-    __half *sh = w.sh;
-    float (*rs)[32] = w.ray;
-    const int total = sm.end[HEAD_MAX_FRAMES - 1];
-    int *ticket = &p.f[0].counters[CT_TICKET];
-    const int max_steps = (int)p.max_steps, cap = max_steps + (ER_SNAPS - 1);
-    const int k = lane % CH, lead = lane - k;
-    int ray = -1, fi = 0, cnt = 0, sidx = -1;
-    float t = 0.f, far = 0.f, ws = 0.f, cr = 0.f, cg_ = 0.f, cb = 0.f;
-    bool exhausted = total == 0;
-    uint32_t phase = 0;
-
-    while (true) {
-        const uint32_t empty = __ballot_sync(0xffffffffu, ray < 0 && k == 0);
-        if (empty && !exhausted) {
-            const int need = __popc(empty);
-            int base = 0;
-            if (lane == 0) base = atomicAdd(ticket, need);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if ((empty >> lead) & 1u) {
-                const int idx = base + __popc(empty & ((1u << lead) - 1u));
-                if (idx < total) {
-                    int f = 0;
-                    while (idx >= sm.end[f]) f++;
-                    const HeadFrame &fr = p.f[f];
-                    ray = fr.hits[idx - (f ? sm.end[f - 1] : 0)];
-                    fi = f;
-                    t = fr.rays_t[ray];
-                    far = fr.fars[ray];
-                    ws = cr = cg_ = cb = 0.f;
-                    cnt = 0;
-                    sidx = -1;
-                    Ray ry;
-                    gen_ray(fr.g, ray, ry);
-                    rs[0][lane] = ry.ox; rs[1][lane] = ry.oy; rs[2][lane] = ry.oz;
-                    rs[3][lane] = ry.dx; rs[4][lane] = ry.dy; rs[5][lane] = ry.dz;
-                    rs[6][lane] = ry.rdx; rs[7][lane] = ry.rdy; rs[8][lane] = ry.rdz;
-                    float shv[16];
-                    sh4(ry.dx, ry.dy, ry.dz, shv);
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        *reinterpret_cast<uint32_t *>(sh + lane * SH_STRIDE + 2 * i) = pack_half2(shv[2 * i], shv[2 * i + 1]);
-                    w.fi[lane] = f;
-                }
-            }
-            if (base + need >= total) exhausted = true;
-        }
-        const bool valid = ray >= 0;
-        if (!__any_sync(0xffffffffu, valid)) break;
-        const HeadFrame &fr = p.f[fi];
-
-        float x = 0.f, y = 0.f, z = 0.f, dt = 0.f, tt = t;
-        bool has = valid && cnt + k < cap;
-        if (has) {
-            Ray ry;
-            ry.ox = rs[0][lane]; ry.oy = rs[1][lane]; ry.oz = rs[2][lane];
-            ry.dx = rs[3][lane]; ry.dy = rs[4][lane]; ry.dz = rs[5][lane];
-            ry.rdx = rs[6][lane]; ry.rdy = rs[7][lane]; ry.rdz = rs[8][lane];
-            uint32_t vox;
-            for (int j = 0; j <= k && has; j++) has = march_next(mp, ry, tt, far, x, y, z, dt, vox);
-        }
-        const uint32_t hasmask = __ballot_sync(0xffffffffu, has);
-        float sigma_logit = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        if (hasmask != 0u) {
-            __half *row = xs + lane * XS_STRIDE;
-            if (has) {
-                if (p.hl.n_dense == 4) gather_planes_t<4>(p, x, y, z, row);
-                else gather_planes_generic(p, x, y, z, row);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 24; i++) *reinterpret_cast<uint32_t *>(row + 2 * i) = 0u;
-            }
-            if (lane == 0) w.hasmask = hasmask;
-            __syncwarp();
-            if (lane == 0) mbar_arrive1(&w.full);        // hand the tile to the consumer warp ...
-            for (int f = 0; f < F; f++) {
-                const int c = __popc(__ballot_sync(0xffffffffu, has && fi == f));
-                if (lane == 0 && c) atomicAdd(&sm.samples[f], c);
-            }
-            mbar_wait(&w.done, phase);                   // ... and wait for sigma / rgb of the 32 samples
-            phase ^= 1u;
-            const float4 r = w.res[lane];
-            sigma_logit = r.x; c0 = r.y; c1 = r.z; c2 = r.w;
-        }
-
-        const float my_alpha = has ? 1.0f - __expf(-expf(sigma_logit) * dt) : 0.f;
-        bool done = !valid;
-        int life = max_steps;
-#pragma unroll
-        for (int j = 0; j < CH; j++) {
-            const int src = lead + j;
-            const bool h_j = (hasmask >> src) & 1u;
-            const float a_j = __shfl_sync(0xffffffffu, my_alpha, src);
-            const float r_j = __shfl_sync(0xffffffffu, c0, src), g_j = __shfl_sync(0xffffffffu, c1, src);
-            const float b_j = __shfl_sync(0xffffffffu, c2, src);
-            if (!done) {
-                if (cnt >= cap) {
-                    done = true;
-                } else if (!h_j) {
-                    done = true;
-                    life = min(cnt, max_steps);
-                } else {
-                    const float T = 1 - ws;
-                    const float weight = a_j * T;
-                    ws += weight;
-                    cr = fmaf(weight, r_j, cr);
-                    cg_ = fmaf(weight, g_j, cg_);
-                    cb = fmaf(weight, b_j, cb);
-                    cnt++;
-                    if (T < p.T_thresh) {
-                        done = true;
-                        life = min(cnt - 1, max_steps);
-                    }
-                    if (cnt >= max_steps && k == 0) {
-                        if (cnt == max_steps && !done) sidx = atomicAdd(&fr.counters[CT_NSURV], 1);
-                        if (sidx >= 0) fr.snap[(size_t)sidx * ER_SNAPS + (cnt - max_steps)] = make_float4(ws, cr, cg_, cb);
-                    }
-                }
-            }
-        }
-        if (!done && cnt >= cap) done = true;
-        const float t_end = __shfl_sync(0xffffffffu, tt, lead + CH - 1);
-        if (valid) {
-            if (done) {
-                if (k == 0) {
-                    if (sidx >= 0) {
-                        for (int j = cnt - max_steps + 1; j < ER_SNAPS; j++)
-                            fr.snap[(size_t)sidx * ER_SNAPS + j] = make_float4(ws, cr, cg_, cb);
-                        fr.weights_sum[ray] = -(float)(sidx + 1);
-                    } else {
-                        fr.weights_sum[ray] = ws;
-                        fr.image[ray * 3] = cr; fr.image[ray * 3 + 1] = cg_; fr.image[ray * 3 + 2] = cb;
-                    }
-                    atomicAdd(&sm.hist[fi][life], 1);
-                }
-                ray = -1;
-            } else {
-                t = t_end;
-            }
-        }
-        __syncwarp();
-    }
-    if (lane == 0) *reinterpret_cast<volatile int *>(&w.fin) = 1;
-}
-
-__device__ __forceinline__ void ws_consumer(WsSmem &sm, int c, int lane) {
-    constexpr int PER = WS_PRODUCERS / WS_CONSUMERS;
-    uint32_t phase[PER];
-    bool fin[PER];
-#pragma unroll
-    for (int i = 0; i < PER; i++) { phase[i] = 0; fin[i] = false; }
-    const int g = lane >> 2, t4 = lane & 3;
-    while (true) {
-        bool all_fin = true, worked = false;
-#pragma unroll
-        for (int i = 0; i < PER; i++) {
-            if (fin[i]) continue;
-            WsWarpSmem &w = sm.w[c + i * WS_CONSUMERS];
-            int st = 0;   // one lane looks, the warp follows: 1 = a tile is waiting, 2 = the producer has finished
-            if (lane == 0) st = mbar_test(&w.full, phase[i]) ? 1 : (*reinterpret_cast<volatile int *>(&w.fin) ? 2 : 0);
-            st = __shfl_sync(0xffffffffu, st, 0);
-            if (st == 1) {
-                phase[i] ^= 1u;
-                worked = true;
-                const uint32_t hasmask = w.hasmask;
-#pragma unroll 1
-                for (int m = 0; m < 2; m++) {
-                    if (((hasmask >> (16 * m)) & 0xffffu) == 0u) continue;
-                    const int f_lo = w.fi[m * 16 + g], f_hi = w.fi[m * 16 + g + 8];
-                    float slo, shi, rgb[4];
-                    head_mlp_tile(sm.mlp, sm.enc_a[f_lo], sm.enc_a[f_hi], w.xs, w.sh, m, lane, sm.eye[f_lo], sm.eye[f_hi], slo, shi, rgb);
-                    float *r_lo = reinterpret_cast<float *>(&w.res[m * 16 + g]), *r_hi = reinterpret_cast<float *>(&w.res[m * 16 + g + 8]);
-                    if (t4 == 0) {
-                        r_lo[0] = slo; r_lo[1] = rgb[0]; r_lo[2] = rgb[1];
-                        r_hi[0] = shi; r_hi[1] = rgb[2]; r_hi[2] = rgb[3];
-                    } else if (t4 == 1) {
-                        r_lo[3] = rgb[0];
-                        r_hi[3] = rgb[2];
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive1(&w.done);
-                all_fin = false;
-            } else if (st == 2) {
-                fin[i] = true;
-            } else {
-                all_fin = false;
-            }
-        }
-        if (all_fin) break;
-        if (!worked) __nanosleep(100);
-    }
-}
-
-template <int CH>
-__global__ void __launch_bounds__(WS_THREADS, 1) k_head_ws(const __grid_constant__ HeadParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    WsSmem &sm = *reinterpret_cast<WsSmem *>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int F = p.n_frames;
-    if (threadIdx.x == 0) {
-        mbar_init(&sm.bar, 1);
-        for (int i = 0; i < WS_PRODUCERS; i++) {
-            mbar_init(&sm.w[i].full, 1);
-            mbar_init(&sm.w[i].done, 1);
-            sm.w[i].fin = 0;
-        }
-        fence_barrier_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(&sm.bar, ER_H_BYTES);
-        bulk_g2s(sm.mlp, p.mlp_image, ER_H_BYTES, &sm.bar);
-        int end = 0;
-        for (int f = 0; f < HEAD_MAX_FRAMES; f++) {
-            if (f < F) { end += p.f[f].counters[CT_NHIT]; sm.eye[f] = p.f[f].eye; }
-            sm.end[f] = end;
-            sm.samples[f] = 0;
-        }
-    }
-    if (threadIdx.x < 32 * F) sm.enc_a[threadIdx.x >> 5][threadIdx.x & 31] = p.f[threadIdx.x >> 5].state[threadIdx.x & 31];
-    for (int i = threadIdx.x; i < HEAD_MAX_FRAMES * (ER_MAX_STEPS + 1); i += WS_THREADS) (&sm.hist[0][0])[i] = 0;
-    mbar_wait(&sm.bar, 0);
-    __syncthreads();
-
-    if (warp < WS_PRODUCERS) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 " WS_STR(WS_PROD_REGS) ";\n");
-        ws_producer<CH>(p, sm, warp, lane);
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 " WS_STR(WS_CONS_REGS) ";\n");
-        ws_consumer(sm, warp - WS_PRODUCERS, lane);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < F * (ER_MAX_STEPS + 1); i += WS_THREADS) {
-        const int f = i / (ER_MAX_STEPS + 1), b = i % (ER_MAX_STEPS + 1);
-        if (sm.hist[f][b]) atomicAdd(&p.f[f].counters[CT_HIST + b], sm.hist[f][b]);
-    }
-    if (threadIdx.x < F && sm.samples[threadIdx.x]) atomicAdd(&p.f[threadIdx.x].counters[CT_SAMPLES], sm.samples[threadIdx.x]);
-}
-
 // torso + final compose (renderer.py:275-277,294-352): resolve the loop control, torso over background,
 // image + (1 - weights_sum) * bg, clamp, fp32 / u8
 #define TORSO_THREADS 256
@@ -1802,12 +1490,6 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
     MF_CUDA(ctx, cudaMemset(s->counters, 0, 2 * CT_INTS * sizeof(int)));
 
     MF_CUDA(ctx, cudaFuncSetAttribute(k_torso_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TorsoSmem)));
-    MF_CUDA(ctx, cudaFuncSetAttribute(k_head_ws<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem)));
-    MF_CUDA(ctx, cudaFuncSetAttribute(k_head_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem)));
-    {   // MF_HEAD_WS=1: the warp-specialised experiment instead of the one-role kernel
-        const char *e = getenv("MF_HEAD_WS");
-        if (e) s->warp_specialised = atoi(e) != 0;
-    }
     MF_CUDA(ctx, cudaFuncSetAttribute(k_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     MF_CUDA(ctx, cudaFuncSetAttribute(k_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
     MF_CUDA(ctx, cudaFuncSetAttribute(k_head<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeadSmem)));
@@ -2022,9 +1704,7 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
         // one CTA per SM; small ray counts (explicit-ray calls) get fewer CTAs: every CTA stages the 57 KB MLP image
         const int grid = (int)std::min<long>(s0->head_grid, std::max<long>(1, (total_tiles * 32 + 255) / 256));
         if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[0], stream));
-        if (s0->warp_specialised && s0->chunk == 4) k_head_ws<4><<<grid, WS_THREADS, sizeof(WsSmem), stream>>>(hp);
-        else if (s0->warp_specialised) k_head_ws<2><<<grid, WS_THREADS, sizeof(WsSmem), stream>>>(hp);
-        else if (s0->chunk == 1) k_head<1><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
+        if (s0->chunk == 1) k_head<1><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
         else if (s0->chunk == 4) k_head<4><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
         else if (s0->chunk == 8) k_head<8><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
         else k_head<2><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
