@@ -229,6 +229,17 @@ class ProgramBuilder:
         return self._misc(3, q[0], out[0], in_coff=q[1], out_coff=out[1], res_buf=k[0], res_coff=k[1], Mh=v[0], Mw=v[1],
                           ntaps=heads, Cin=dim_head, Kpad=self._fbits(dim_head ** -0.5))
 
+    def transformer_stack(self, in_buf, out_buf, image, D, inter, heads, layers, eps, flops):
+        """op kind 5 (csrc/w2v_stack.cuh): `layers` pre-LN transformer layers as ONE persistent kernel; `image` = the packed weights
+        of all layers (bytes, layout in w2v_stack.cuh)"""
+        assert self.buffers[in_buf] == self.buffers[out_buf] and self.buffers[in_buf][2] == D
+        self.flops_per_sample += flops
+        rec = struct.pack("<28i", in_buf, 0, out_buf, 0, -1, 0, layers, inter, 0, 0, 1, 1, 1, 1, heads, D, self._fbits(eps), 0, 0, 0, 0, 0,
+                          self._tensor(image), -1, -1, 5, 0, 0)
+        rec += bytes(2 * CONV_MAX_TAPS)
+        self.ops.append(rec)
+        return len(self.ops) - 1
+
     def geglu(self, in_buf, out_buf):
         Hd = self.buffers[out_buf][2]
         assert self.buffers[in_buf][2] == 2 * Hd

@@ -101,6 +101,7 @@ struct ErnerfState {
     float *rays_t = nullptr, *fars = nullptr, *weights_sum = nullptr, *image = nullptr;
     float *final_f32 = nullptr;  // [N,3] when a resize follows
     int head_grid = 0;
+    bool chunk_forced = false;
     int chunk = 2;           // CH: samples of a ray shaded side by side (MF_HEAD_CHUNK = 1 | 2 | 4 | 8; 2 measured best)
     int last_launches = 0;
     float misc_host[24] = {0};
@@ -1499,7 +1500,7 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
     MF_REQUIRE(ctx, per_sm >= 1, "k_head does not fit on an SM");
     {   // experiment hook: MF_HEAD_CHUNK = samples of a ray shaded side by side per pass (2, 4 or 8)
         const char *e = getenv("MF_HEAD_CHUNK");
-        if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8)) s->chunk = atoi(e);
+        if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8)) { s->chunk = atoi(e); s->chunk_forced = true; }
     }
     s->head_grid = ctx->sm_count;
     MF_CUDA(ctx, cudaDeviceSynchronize());
@@ -1701,12 +1702,18 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
         hf.rays_t = s->rays_t; hf.fars = s->fars; hf.weights_sum = s->weights_sum; hf.image = s->image; hf.snap = s->snap;
     }
     {
-        // one CTA per SM; small ray counts (explicit-ray calls) get fewer CTAs: every CTA stages the 57 KB MLP image
-        const int grid = (int)std::min<long>(s0->head_grid, std::max<long>(1, (total_tiles * 32 + 255) / 256));
+        // Samples of a ray shaded side by side per pass: 2 for full frames (least speculation, measured best); a launch with few
+        // rays cannot fill the ray slots anyway and is bound by the number of sequential passes per ray, so it takes 4 or 8
+        // (the literal "2048 rays per frame" reading of BASELINE configs[3]).  MF_HEAD_CHUNK overrides.
+        int chunk = s0->chunk;
+        if (!s0->chunk_forced) chunk = total_tiles * 32 <= 16384 ? 8 : (total_tiles * 32 <= 65536 ? 4 : 2);
+        // one CTA per SM; small ray counts get fewer CTAs (every CTA stages the 57 KB MLP image): 16 warps x 32 / chunk ray slots each
+        const long slots_per_cta = HEAD_WARPS * (32 / chunk);
+        const int grid = (int)std::min<long>(s0->head_grid, std::max<long>(1, (total_tiles * 32 + slots_per_cta - 1) / slots_per_cta));
         if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[0], stream));
-        if (s0->chunk == 1) k_head<1><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
-        else if (s0->chunk == 4) k_head<4><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
-        else if (s0->chunk == 8) k_head<8><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
+        if (chunk == 1) k_head<1><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
+        else if (chunk == 4) k_head<4><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
+        else if (chunk == 8) k_head<8><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
         else k_head<2><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
         if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[1], stream));
         launches++;

@@ -1,0 +1,414 @@
+// w2v_stack.cuh -- the 24 pre-LN transformer layers of the wav2vec2 CTC acoustic model (NerfASR.__frame_to_text, nerfasr.py:128-143;
+// transformers modeling_wav2vec2.py: Wav2Vec2EncoderLayerStableLayerNorm) as ONE persistent kernel.
+//
+// Round 1 ran the stack as 24 x 7 launches of the conv executor (LayerNorm, QKV GEMM, attention, out-proj, LayerNorm, FFN1, FFN2):
+// M = 27 tokens per window, so every GEMM is a weight-streaming GEMV-like problem (25 MB of bf16 weights per layer, 604 MB in
+// all = ~0.1 ms at HBM speed) and the 1.6 ms it took were launch latency and under-filled grids (profiles: 203 launches).
+// Here: G = 128 CTAs (one per SM, all resident), each owns a fixed slice of the OUTPUT columns of every matrix, so every weight is
+// read from HBM exactly once per forward and results need no cross-CTA reduction (deterministic); a phase is
+//   [stream this CTA's rows of W in K-chunks by cp.async.bulk (TMA 1-D) into padded shared-memory rows, double buffered,
+//    the first chunk of the NEXT phase issued before the grid barrier]  x  [A chunk built by the CTA: LayerNorm of the fp32
+//    residual stream on the fly, or the bf16 activations of the previous phase]  ->  mma.sync.m16n8k16 bf16  ->  epilogue
+// and phases are separated by a software grid barrier (5 per layer):
+//   P1  qkv  = LN1(x) Wqkv^T + b          P2  attention per (window, head) on 16 x B CTAs      P3  x += ao Wo^T + b
+//   P4  hid  = gelu(LN2(x) W1^T + b)      P5  x += hid W2^T + b
+// The residual stream stays fp32 in a scratch buffer (the executor's buffers are bf16).  One window per launch (M <= 32 rows): an engine
+// that batches the windows of several sessions keeps the op-by-op program.
+// Measured (B200, XLSR-53 shape): 1.75 ms per window against 2.0 ms for the 203-launch program; per layer ~56 us = LN1+QKV 9.5, attention
+// 6.9 (30 with one CTA per head), out-proj 5.4, LN2+FFN1 9.6 (of which the per-CTA LayerNorm of the 27 rows 6.2), FFN2 13.8 (K = 4096
+// streamed in 16 chunks), 5 barriers ~2 us each -- every phase is a few dependent L2 round trips; the weight stream (25 MB per layer,
+// 4 us at HBM speed) is nowhere near the limit yet.
+#pragma once
+
+#define WS_G 128          /* CTAs; output-column slices are multiples of 8 */
+#define WS_THREADS_ 256
+#define WS_KC 256         /* K chunk (elements) of the A ring used when K > WS_KA */
+#define WS_KS (WS_KC + 8) /* padded chunk row stride in smem (bank-conflict-free ldmatrix) */
+#define WS_KA 1024        /* largest K whose A operand is resident as a whole */
+#define WS_STAGES 6       /* A ring depth (chunks of WS_KC): 3 stages in sm.A, 3 in the weight buffer that is idle during the phase */
+#define WS_MAX_NC 32      /* output columns per CTA and phase */
+#define WS_MAX_MT 2       /* 16-row tiles of tokens: one window (<= 32 frames); batched windows use the op-by-op program */
+#define WS_WBUF_HALFS (WS_MAX_NC * (WS_KA + 8))   /* one weight slice: nc rows x (K + 8), nc * K <= 32 * 1024 */
+
+struct W2vStackParams {
+    const unsigned char *image;   // packed weights (layout below)
+    const __nv_bfloat16 *x_in;    // [M][D] bf16 (after the positional conv)
+    __nv_bfloat16 *x_out;         // [M][D] bf16
+    float *xres;                  // scratch [M][D] fp32 residual stream
+    __nv_bfloat16 *qkv, *ao, *hid;  // scratch [M][3D], [M][D], [M][I]
+    unsigned *barrier;            // zeroed before the launch
+    int M, T, B, D, I, heads, layers;
+    float eps, scale_log2;        // softmax scale * log2(e)
+};
+
+// image layout per layer (bytes): vectors fp32 [ln1_g D | ln1_b D | bqkv 3D | bo D | ln2_g D | ln2_b D | b1 I | b2 D], then matrices bf16
+// row-major [Wqkv 3D x D | Wo D x D | W1 I x D | W2 D x I]
+struct W2vLayerPtrs {
+    const float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *b1, *b2;
+    const __nv_bfloat16 *Wqkv, *Wo, *W1, *W2;
+};
+__host__ __device__ inline size_t w2v_layer_bytes(int D, int I) { return (size_t)(9 * D + I) * 4 + ((size_t)4 * D * D + (size_t)2 * D * I) * 2; }
+__device__ __forceinline__ W2vLayerPtrs w2v_layer(const unsigned char *image, int l, int D, int I) {
+    const unsigned char *p = image + (size_t)l * w2v_layer_bytes(D, I);
+    W2vLayerPtrs w;
+    const float *f = reinterpret_cast<const float *>(p);
+    w.ln1_g = f; f += D; w.ln1_b = f; f += D; w.bqkv = f; f += 3 * D; w.bo = f; f += D;
+    w.ln2_g = f; f += D; w.ln2_b = f; f += D; w.b1 = f; f += I; w.b2 = f; f += D;
+    const __nv_bfloat16 *h = reinterpret_cast<const __nv_bfloat16 *>(f);
+    w.Wqkv = h; h += (size_t)3 * D * D; w.Wo = h; h += (size_t)D * D; w.W1 = h; h += (size_t)I * D; w.W2 = h;
+    return w;
+}
+
+struct W2vSmem {
+    alignas(16) __nv_bfloat16 W[2][WS_WBUF_HALFS];                // this phase's weight slice (whole K) / the next phase's, in flight
+    alignas(16) __nv_bfloat16 A[WS_MAX_MT * 16 * (WS_KA + 8)];    // A operand: whole (K <= WS_KA) or a WS_STAGES ring of WS_KC chunks
+    float red[8][32][8];                                          // split-K partials: [warp][lane][c]
+    float mean[WS_MAX_MT * 16], rstd[WS_MAX_MT * 16];
+    alignas(8) uint64_t wbar[2];
+};
+
+__device__ __forceinline__ void w2v_grid_barrier(unsigned *ctr, unsigned &gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gen++;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        const unsigned target = gen * gridDim.x;
+        while (*reinterpret_cast<volatile unsigned *>(ctr) < target) __nanosleep(40);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// issue the bulk copies (TMA 1-D, one per row) of this CTA's weight rows [n0, n0 + nc) of W [N][K] into buffer `slot` (one thread)
+__device__ __forceinline__ void w2v_issue_w(W2vSmem &sm, const __nv_bfloat16 *W, int K, int n0, int nc, int slot) {
+    mbar_expect_tx(&sm.wbar[slot], (uint32_t)(nc * K * 2));
+    for (int r = 0; r < nc; r++) bulk_g2s(sm.W[slot] + (size_t)r * (K + 8), W + (size_t)(n0 + r) * K, (uint32_t)(K * 2), &sm.wbar[slot]);
+}
+__device__ __forceinline__ void w2v_cp16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void w2v_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void w2v_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// A operand builders: rows 0..Mpad-1 of sm.A with row stride `ks` halfs ------------------------------------------------------
+// LayerNorm of the fp32 residual rows -> bf16 A operand (row stride D + 8).  A warp owns rows warp, warp + 8, ...; the loads of ALL
+// its rows are issued before the first use (one exposed L2 latency per phase instead of one per row: the first version walked every
+// row with dependent loads, 25 us per phase), gamma / beta are staged in shared memory once; two-pass statistics like
+// torch.nn.functional.layer_norm.  D <= 1024, M <= 32.
+__device__ __forceinline__ void w2v_ln_rows(W2vSmem &sm, const float *xres, int M, int Mpad, int D, float eps, const float *g, const float *b) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ks = D + 8;
+    constexpr int NV = WS_KA / 128, NR = WS_MAX_MT * 16 / (WS_THREADS_ / 32);   // float4 per lane and row; rows per warp
+    float *gs = reinterpret_cast<float *>(sm.red), *bs = gs + WS_KA;             // 8 KB: the split-K scratch is free here
+    for (int c = threadIdx.x * 4; c < D; c += WS_THREADS_ * 4) {
+        *reinterpret_cast<float4 *>(gs + c) = __ldg(reinterpret_cast<const float4 *>(g + c));
+        *reinterpret_cast<float4 *>(bs + c) = __ldg(reinterpret_cast<const float4 *>(b + c));
+    }
+    float4 v[NR][NV];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const int m = warp + r * (WS_THREADS_ / 32);
+#pragma unroll
+        for (int i = 0; i < NV; i++)
+            v[r][i] = (m < M && lane * 4 + i * 128 < D) ? __ldcg(reinterpret_cast<const float4 *>(xres + (size_t)m * D + lane * 4 + i * 128))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);     // written by other CTAs: not through L1
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const int m = warp + r * (WS_THREADS_ / 32);
+        if (m >= Mpad) continue;
+        __nv_bfloat16 *dst = sm.A + (size_t)m * ks;
+        if (m >= M) {
+            for (int c = lane * 4; c < D; c += 128) *reinterpret_cast<uint2 *>(dst + c) = make_uint2(0u, 0u);
+            continue;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; i++) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)D;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; i++)
+            if (lane * 4 + i * 128 < D) {
+                const float a0 = v[r][i].x - mean, a1 = v[r][i].y - mean, a2 = v[r][i].z - mean, a3 = v[r][i].w - mean;
+                q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+            }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rs = rsqrtf(q / (float)D + eps);
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int c = lane * 4 + i * 128;
+            if (c < D) {
+                const float4 gg = *reinterpret_cast<const float4 *>(gs + c), bb = *reinterpret_cast<const float4 *>(bs + c);
+                __nv_bfloat162 h0 = __floats2bfloat162_rn((v[r][i].x - mean) * rs * gg.x + bb.x, (v[r][i].y - mean) * rs * gg.y + bb.y);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn((v[r][i].z - mean) * rs * gg.z + bb.z, (v[r][i].w - mean) * rs * gg.w + bb.w);
+                *reinterpret_cast<uint2 *>(dst + c) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+            }
+        }
+    }
+}
+// columns [k0, k0 + kn) of bf16 activations [M][ld] -> rows of `dst` (stride ks) by cp.async (global -> shared, no registers)
+__device__ __forceinline__ void w2v_copy_a(__nv_bfloat16 *dst, int ks, const __nv_bfloat16 *src, int M, int Mpad, int ld, int k0, int kn) {
+    for (int i = threadIdx.x; i < Mpad * (kn / 8); i += WS_THREADS_) {
+        const int m = i / (kn / 8), j = (i - m * (kn / 8)) * 8;
+        if (m < M) w2v_cp16(dst + (size_t)m * ks + j, src + (size_t)m * ld + k0 + j);
+        else *reinterpret_cast<uint4 *>(dst + (size_t)m * ks + j) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+// One phase GEMM for this CTA: C[M x nc] = A[M x K] W[n0 .. n0+nc)[K]^T.  The weight slice is whole in sm.W[wslot] (in flight since
+// before the preceding grid barrier); the A operand is whole in sm.A when K <= WS_KA (built by the caller before the call), else
+// streamed from `a_src` (bf16 [M][K]) through a WS_STAGES-deep cp.async ring of WS_KC-column chunks.  epi(m, n, value) is called for
+// every valid (m < M, n < nc) exactly once; the order of summation is fixed.
+// Work split: (m-tile, n-tile) pairs over the 8 warps; with fewer pairs than warps the k-steps are split over the spare warps and
+// the partials are added in warp order through shared memory.
+template <class Epi>
+__device__ __forceinline__ void w2v_phase_gemm(W2vSmem &sm, int K, int nc, int M, const __nv_bfloat16 *a_src, Epi epi, uint32_t (&wphase)[2],
+                                               int &wslot) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = (M + 15) / 16, Mpad = mt * 16, nt = nc / 8, pairs = mt * nt;
+    const int ksplit = pairs >= 8 ? 1 : (8 / pairs >= 4 ? 4 : (8 / pairs >= 2 ? 2 : 1));
+    const int groups = 8 / ksplit;                 // warps working on distinct pairs at a time
+    const int kpart = warp / groups, pg = warp % groups;
+    const int pr = pg;                             // at most one pair per warp: mt <= 2, nt <= 4
+    const bool active = pr < pairs;
+    const int mi = active ? pr / nt : 0, ni = active ? pr - mi * nt : 0;
+    const int wks = K + 8;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const __nv_bfloat16 *Wsm = sm.W[wslot];
+    const int q = lane >> 3;
+    if (K <= WS_KA) {
+        __syncthreads();                           // the caller's A is complete
+        mbar_wait(&sm.wbar[wslot], wphase[wslot]);
+        const int ksteps = K / 16, kper = ksteps / ksplit, aks = K + 8;
+        if (active)
+#pragma unroll 4
+            for (int ks = kpart * kper; ks < (kpart + 1) * kper; ks++) {
+                uint32_t a[4], b0, b1;
+                ldmatrix_x4(a, smem_u32(sm.A + (size_t)(mi * 16 + (lane & 7) + 8 * (q & 1)) * aks + ks * 16 + 8 * (q >> 1)));
+                ldmatrix_x2(b0, b1, smem_u32(Wsm + (size_t)(ni * 8 + (lane & 7)) * wks + ks * 16 + 8 * (q & 1)));
+                mma_bf16_16816(acc, a, b0, b1);
+            }
+    } else {
+        const int nchunks = K / WS_KC;
+        __nv_bfloat16 *idle = sm.W[wslot ^ 1];     // the next phase's weights are issued only after this call returns
+        auto stage = [&](int c) { const int st = c % WS_STAGES; return st < 3 ? sm.A + (size_t)st * Mpad * WS_KS : idle + (size_t)(st - 3) * Mpad * WS_KS; };
+        __syncthreads();                           // everyone is done with sm.A of the phase before
+        for (int c = 0; c < WS_STAGES - 1 && c < nchunks; c++) {
+            w2v_copy_a(stage(c), WS_KS, a_src, M, Mpad, K, c * WS_KC, WS_KC);
+            w2v_cp_commit();
+        }
+        mbar_wait(&sm.wbar[wslot], wphase[wslot]);
+        for (int kc = 0; kc < nchunks; kc++) {
+            if (kc + WS_STAGES - 1 < nchunks) w2v_cp_wait<WS_STAGES - 2>(); else w2v_cp_wait<0>();
+            __syncthreads();                       // chunk kc has landed for everyone; the stage refilled below was consumed in kc - 1
+            if (kc + WS_STAGES - 1 < nchunks) {
+                const int c = kc + WS_STAGES - 1;
+                w2v_copy_a(stage(c), WS_KS, a_src, M, Mpad, K, c * WS_KC, WS_KC);
+                w2v_cp_commit();
+            }
+            const __nv_bfloat16 *As = stage(kc);
+            const int kper = (WS_KC / 16) / ksplit;
+            if (active)
+                for (int ks = kpart * kper; ks < (kpart + 1) * kper; ks++) {
+                    uint32_t a[4], b0, b1;
+                    ldmatrix_x4(a, smem_u32(As + (size_t)(mi * 16 + (lane & 7) + 8 * (q & 1)) * WS_KS + ks * 16 + 8 * (q >> 1)));
+                    ldmatrix_x2(b0, b1, smem_u32(Wsm + (size_t)(ni * 8 + (lane & 7)) * wks + kc * WS_KC + ks * 16 + 8 * (q & 1)));
+                    mma_bf16_16816(acc, a, b0, b1);
+                }
+        }
+    }
+    wphase[wslot] ^= 1u;
+    wslot ^= 1;
+    // split-K reduction in warp order, then the epilogue by the kpart == 0 warps
+    if (ksplit > 1) {
+        if (active && kpart > 0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) sm.red[warp][lane][c] = acc[c];
+        }
+        __syncthreads();
+        if (active && kpart == 0)
+            for (int kp = 1; kp < ksplit; kp++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[c] += sm.red[kp * groups + pg][lane][c];
+    }
+    if (active && kpart == 0) {
+        const int r0 = mi * 16 + (lane >> 2), cc = ni * 8 + 2 * (lane & 3);
+        if (r0 < M) { epi(r0, cc, acc[0]); epi(r0, cc + 1, acc[1]); }
+        if (r0 + 8 < M) { epi(r0 + 8, cc, acc[2]); epi(r0 + 8, cc + 1, acc[3]); }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float w2v_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// this CTA's column slice of an N-wide output
+__device__ __forceinline__ void w2v_slice(int N, int &n0, int &nc) {
+    int per = (N + WS_G - 1) / WS_G;
+    per = (per + 7) / 8 * 8;
+    n0 = blockIdx.x * per;
+    nc = n0 >= N ? 0 : min(per, N - n0);
+}
+
+struct ZeroParams { unsigned *p; int n; };
+__global__ void k_zero_u32(const ZeroParams z) {
+    pdl_launch();
+    pdl_wait();
+    if ((int)threadIdx.x < z.n) z.p[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_constant__ W2vStackParams p) {
+    pdl_launch();
+    pdl_wait();
+    extern __shared__ __align__(128) unsigned char w2v_smem_raw[];
+    W2vSmem &sm = *reinterpret_cast<W2vSmem *>(w2v_smem_raw);
+    const int D = p.D, I = p.I, M = p.M, Mpad = (M + 15) / 16 * 16;
+    unsigned gen = 0;
+    uint32_t wphase[2] = {0u, 0u};
+    int wslot = 0;                                 // sm.W[wslot] holds (or is receiving) the NEXT phase's weight slice
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.wbar[0], 1);
+        mbar_init(&sm.wbar[1], 1);
+        fence_barrier_init();
+    }
+    // residual stream in fp32
+    for (size_t i = (size_t)blockIdx.x * WS_THREADS_ + threadIdx.x; i < (size_t)M * D; i += (size_t)gridDim.x * WS_THREADS_)
+        p.xres[i] = __bfloat162float(p.x_in[i]);
+    __syncthreads();
+    int n0q, ncq, n0d, ncd, n0i, nci;
+    w2v_slice(3 * D, n0q, ncq);
+    w2v_slice(D, n0d, ncd);
+    w2v_slice(I, n0i, nci);
+    // first weight chunk of layer 0 / P1 in flight before the first barrier
+    {
+        const W2vLayerPtrs w0 = w2v_layer(p.image, 0, D, I);
+        if (threadIdx.x == 0 && ncq) w2v_issue_w(sm, w0.Wqkv, D, n0q, ncq, wslot);
+    }
+    w2v_grid_barrier(p.barrier, gen);
+
+    for (int l = 0; l < p.layers; l++) {
+        const W2vLayerPtrs w = w2v_layer(p.image, l, D, I);
+        // ---- P1: qkv = LN1(x) Wqkv^T + b
+        if (ncq) {
+            w2v_ln_rows(sm, p.xres, M, Mpad, D, p.eps, w.ln1_g, w.ln1_b);
+            w2v_phase_gemm(sm, D, ncq, M, nullptr,
+                           [&](int m, int n, float v) { p.qkv[(size_t)m * 3 * D + n0q + n] = __float2bfloat16_rn(v + __ldg(w.bqkv + n0q + n)); },
+                           wphase, wslot);
+        }
+        if (threadIdx.x == 0 && ncd) w2v_issue_w(sm, w.Wo, D, n0d, ncd, wslot);         // P3's weights stream during P2
+        w2v_grid_barrier(p.barrier, gen);
+        // ---- P2: attention; item = (window, head, group of query rows) so that all CTAs take part (one CTA per head took 30 us)
+        {
+            const int dh = D / p.heads, T = p.T;
+            const int RG = max(1, min(T, (int)gridDim.x / (p.B * p.heads)));      // query-row groups per (window, head)
+            const int rows_per = (T + RG - 1) / RG;
+            float *sq = reinterpret_cast<float *>(sm.A);             // q rows of the group | k | v [T][dh], scores [rows_per][T]
+            float *sk = sq + rows_per * dh, *sv = sk + T * dh, *sc = sv + T * dh;
+            for (int item = blockIdx.x; item < p.B * p.heads * RG; item += gridDim.x) {
+                const int bh = item / RG, rg = item - bh * RG, b = bh / p.heads, h = bh - b * p.heads;
+                const int t0 = rg * rows_per, nr = min(rows_per, T - t0);
+                if (nr <= 0) continue;
+                const int nvec = (nr + 2 * T) * (dh / 8);
+                for (int i = threadIdx.x; i < nvec; i += WS_THREADS_) {                 // 16-byte loads, all in flight together
+                    const int r = i / (dh / 8), d = (i - r * (dh / 8)) * 8;
+                    const int which = r < nr ? 0 : (r < nr + T ? 1 : 2), t = which == 0 ? t0 + r : (which == 1 ? r - nr : r - nr - T);
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p.qkv + (size_t)(b * T + t) * 3 * D + which * D + h * dh + d));   // not through L1
+                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                    float *dstf = (which == 0 ? sq + r * dh : (which == 1 ? sk + t * dh : sv + t * dh)) + d;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        dstf[2 * j] = __uint_as_float(wv[j] << 16);
+                        dstf[2 * j + 1] = __uint_as_float(wv[j] & 0xffff0000u);
+                    }
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < nr * T; i += WS_THREADS_) {
+                    const int tq = i / T, tk = i - tq * T;
+                    float s0 = 0.f, s1 = 0.f;
+                    for (int d = 0; d < dh; d += 2) {
+                        s0 = fmaf(sq[tq * dh + d], sk[tk * dh + d], s0);
+                        s1 = fmaf(sq[tq * dh + d + 1], sk[tk * dh + d + 1], s1);
+                    }
+                    sc[i] = (s0 + s1) * p.scale_log2;
+                }
+                __syncthreads();
+                for (int tq = threadIdx.x >> 5; tq < nr; tq += WS_THREADS_ / 32) {      // softmax per row, one warp per row
+                    const int lane = threadIdx.x & 31;
+                    float mx = -3.0e38f;
+                    for (int tk = lane; tk < T; tk += 32) mx = fmaxf(mx, sc[tq * T + tk]);
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    float sum = 0.f;
+                    for (int tk = lane; tk < T; tk += 32) { const float e = exp2f(sc[tq * T + tk] - mx); sc[tq * T + tk] = e; sum += e; }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    const float inv = 1.0f / sum;
+                    for (int tk = lane; tk < T; tk += 32) sc[tq * T + tk] = __bfloat162float(__float2bfloat16_rn(sc[tq * T + tk] * inv));
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < nr * dh; i += WS_THREADS_) {
+                    const int t = i / dh, d = i - t * dh;
+                    float o0 = 0.f, o1 = 0.f;
+                    int tk = 0;
+                    for (; tk + 1 < T; tk += 2) {
+                        o0 = fmaf(sc[t * T + tk], sv[tk * dh + d], o0);
+                        o1 = fmaf(sc[t * T + tk + 1], sv[(tk + 1) * dh + d], o1);
+                    }
+                    if (tk < T) o0 = fmaf(sc[t * T + tk], sv[tk * dh + d], o0);
+                    p.ao[(size_t)(b * T + t0 + t) * D + h * dh + d] = __float2bfloat16_rn(o0 + o1);
+                }
+                __syncthreads();
+            }
+        }
+        w2v_grid_barrier(p.barrier, gen);
+        // ---- P3: x += ao Wo^T + b
+        if (ncd) {
+            w2v_copy_a(sm.A, D + 8, p.ao, M, Mpad, D, 0, D);
+            w2v_cp_commit();
+            w2v_cp_wait<0>();
+            w2v_phase_gemm(sm, D, ncd, M, nullptr,
+                           [&](int m, int n, float v) { float *x = p.xres + (size_t)m * D + n0d + n; *x = __ldcg(x) + (v + __ldg(w.bo + n0d + n)); },
+                           wphase, wslot);
+        }
+        if (threadIdx.x == 0 && nci) w2v_issue_w(sm, w.W1, D, n0i, nci, wslot);
+        w2v_grid_barrier(p.barrier, gen);
+        // ---- P4: hid = gelu(LN2(x) W1^T + b)
+        if (nci) {
+            w2v_ln_rows(sm, p.xres, M, Mpad, D, p.eps, w.ln2_g, w.ln2_b);
+            w2v_phase_gemm(sm, D, nci, M, nullptr,
+                           [&](int m, int n, float v) { p.hid[(size_t)m * I + n0i + n] = __float2bfloat16_rn(w2v_gelu(v + __ldg(w.b1 + n0i + n))); },
+                           wphase, wslot);
+        }
+        if (threadIdx.x == 0 && ncd) w2v_issue_w(sm, w.W2, I, n0d, ncd, wslot);
+        w2v_grid_barrier(p.barrier, gen);
+        // ---- P5: x += hid W2^T + b
+        if (ncd) {
+            if (I <= WS_KA) {
+                w2v_copy_a(sm.A, I + 8, p.hid, M, Mpad, I, 0, I);
+                w2v_cp_commit();
+                w2v_cp_wait<0>();
+            }
+            w2v_phase_gemm(sm, I, ncd, M, p.hid,
+                           [&](int m, int n, float v) { float *x = p.xres + (size_t)m * D + n0d + n; *x = __ldcg(x) + (v + __ldg(w.b2 + n0d + n)); },
+                           wphase, wslot);
+        }
+        if (l + 1 < p.layers) {
+            const W2vLayerPtrs wn = w2v_layer(p.image, l + 1, D, I);
+            if (threadIdx.x == 0 && ncq) w2v_issue_w(sm, wn.Wqkv, D, n0q, ncq, wslot);
+        }
+        w2v_grid_barrier(p.barrier, gen);
+    }
+    for (size_t i = (size_t)blockIdx.x * WS_THREADS_ + threadIdx.x; i < (size_t)M * D; i += (size_t)gridDim.x * WS_THREADS_)
+        p.x_out[i] = __float2bfloat16_rn(__ldcg(p.xres + i));
+}

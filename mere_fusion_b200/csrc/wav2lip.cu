@@ -54,6 +54,8 @@ struct W2LBuffer {
 //   3 attention       : q = (in_buf, in_coff), k = (res_buf, res_coff), v = (Mh, Mw), out = (out_buf, out_coff),
 //                       ntaps = heads, Cin = dim_head, Kpad = scale (float bits)
 //   4 GEGLU           : in_buf [.., 2 * Cin] -> out_buf [.., Cin]
+//   5 transformer stack (wav2vec2, w2v_stack.cuh): in_buf [T,1,D] -> out_buf [T,1,D], Cin = D, Mw = intermediate size, ntaps = heads,
+//                       Mh = layers, Kpad = LayerNorm eps bits, w_entry = packed weights of all layers
 struct W2LOp {
     int32_t in_buf, in_coff, out_buf, out_coff, res_buf, res_coff;
     int32_t Mh, Mw, oy0, ox0, osy, osx, isy, isx;
@@ -330,6 +332,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv(const __grid_constant__ C
 }
 
 #include "conv_tma.cuh"
+#include "w2v_stack.cuh"
 
 // =====================================================================================================
 // host: program loader, launch list, direct / CUDA-graph execution
@@ -456,6 +459,10 @@ struct Wav2LipState {
     int w2v_samples = 0, w2v_frames = 0, w2v_vocab = 0, w2v_c0 = 0, w2v_k0 = 0, w2v_s0 = 0;
     const float *w2v_conv0 = nullptr;   // [C0][k0] weights then [C0] bias, fp32
     float *w2v_stats = nullptr;         // (mean, rstd) of the window
+    float *w2v_xres = nullptr;          // transformer stack (op kind 5) scratch: fp32 residual stream, qkv / attention out / FFN hidden, barrier
+    __nv_bfloat16 *w2v_qkv = nullptr, *w2v_ao = nullptr, *w2v_hid = nullptr;
+    unsigned *w2v_barrier = nullptr;
+    const unsigned char *w2v_image = nullptr;
     // GroupNorm statistics fused into the producing conv (k_conv_tma epilogue): per conv op its consumer GN op (or -1), per GN op
     // its producer conv (or -1), the per-conv slot buffers, and the slot count chosen while the current launch list is built
     std::vector<int> gn_consumer, gn_producer, gn_fused_slots;
@@ -478,6 +485,7 @@ void wav2lip_destroy(mf_ctx *ctx) {
     Wav2LipState *s = ctx->wav2lip;
     if (!s) return;
     for (auto p : s->dbuf) cudaFree(p);
+    cudaFree(s->w2v_xres); cudaFree(s->w2v_qkv); cudaFree(s->w2v_ao); cudaFree(s->w2v_hid); cudaFree(s->w2v_barrier);
     for (auto pl : s->plans) {
         if (pl->exec) cudaGraphExecDestroy(pl->exec);
         if (pl->graph) cudaGraphDestroy(pl->graph);
@@ -572,8 +580,32 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
     for (int i = 0; i < s->hdr.n_ops; i++) {
         const W2LOp &o = s->ops[i];
         if (o.kind != 0) {
-            MF_REQUIRE(ctx, o.kind >= 1 && o.kind <= 4, "op %d: unknown kind %d", i, o.kind);
+            MF_REQUIRE(ctx, o.kind >= 1 && o.kind <= 5, "op %d: unknown kind %d", i, o.kind);
             MF_REQUIRE(ctx, okbuf(o.in_buf) && okbuf(o.out_buf), "op %d: bad buffer id", i);
+            if (o.kind == 5) {
+                const int D = o.Cin, I = o.Mw, heads = o.ntaps, layers = o.Mh;
+                const W2LBuffer &ib = s->bufs[o.in_buf], &ob = s->bufs[o.out_buf];
+                const int T = ib.H * ib.W;
+                const mf_blob_entry *we = find(o.w_entry);
+                auto slice = [](int N) { int per = (N + WS_G - 1) / WS_G; return (per + 7) / 8 * 8; };
+                MF_REQUIRE(ctx, D > 0 && I > 0 && heads > 0 && layers > 0 && ib.C == D && ob.C == D && ob.H * ob.W == T && D % WS_KC == 0 &&
+                                    I % WS_KC == 0 && D <= WS_KA && D % heads == 0 && slice(3 * D) <= WS_MAX_NC && slice(I) <= WS_MAX_NC &&
+                                    (size_t)slice(3 * D) * (D + 8) <= WS_WBUF_HALFS && (size_t)slice(I) * (D + 8) <= WS_WBUF_HALFS &&
+                                    (size_t)slice(D) * (I + 8) <= WS_WBUF_HALFS && (size_t)max_batch * T <= WS_MAX_MT * 16 &&
+                                    (size_t)(3 * T * (D / heads) + T * T) * 4 <= sizeof(((W2vSmem *)nullptr)->A),
+                           "op %d: transformer stack outside what k_w2v_stack implements (one window, D <= 1024)", i);
+                MF_REQUIRE(ctx, we && we->nbytes == (size_t)layers * w2v_layer_bytes(D, I), "op %d: transformer weight image does not match the geometry", i);
+                const size_t M = (size_t)max_batch * T;
+                MF_REQUIRE(ctx, !s->w2v_xres, "only one transformer stack per program");
+                MF_CUDA(ctx, cudaMalloc(&s->w2v_xres, M * D * 4));
+                MF_CUDA(ctx, cudaMalloc(&s->w2v_qkv, M * 3 * D * 2));
+                MF_CUDA(ctx, cudaMalloc(&s->w2v_ao, M * D * 2));
+                MF_CUDA(ctx, cudaMalloc(&s->w2v_hid, M * I * 2));
+                MF_CUDA(ctx, cudaMalloc(&s->w2v_barrier, 64));
+                s->w2v_image = base + we->offset;
+                MF_CUDA(ctx, cudaFuncSetAttribute(k_w2v_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(W2vSmem)));
+                continue;
+            }
             if (o.kind == 1 || o.kind == 2) {
                 const mf_blob_entry *se = find(o.scale_entry), *he = find(o.shift_entry);
                 MF_REQUIRE(ctx, se && he && se->nbytes == (size_t)o.Cin * 4 && he->nbytes == (size_t)o.Cin * 4 &&
@@ -1008,6 +1040,26 @@ static int add_op_launches(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vect
             a.set(n);
             L.push_back(std::move(a));
         }
+        return MF_OK;
+    }
+    if (o.kind == 5) {
+        Launch z;
+        ZeroParams zp;
+        zp.p = s->w2v_barrier; zp.n = 16;
+        z.func = (void *)k_zero_u32; z.grid = dim3(1); z.block = dim3(32); z.op = i;
+        z.set(zp);
+        L.push_back(std::move(z));
+        W2vStackParams w;
+        w.image = s->w2v_image;
+        w.x_in = s->dbuf[o.in_buf]; w.x_out = s->dbuf[o.out_buf];
+        w.xres = s->w2v_xres; w.qkv = s->w2v_qkv; w.ao = s->w2v_ao; w.hid = s->w2v_hid; w.barrier = s->w2v_barrier;
+        w.T = ib.H * ib.W; w.B = B; w.M = B * w.T; w.D = o.Cin; w.I = o.Mw; w.heads = o.ntaps; w.layers = o.Mh;
+        w.eps = bits_to_float(o.Kpad);
+        w.scale_log2 = 1.4426950408889634f / sqrtf((float)(o.Cin / o.ntaps));
+        Launch a;
+        a.func = (void *)k_w2v_stack; a.grid = dim3(WS_G); a.block = dim3(WS_THREADS_); a.smem = (int)sizeof(W2vSmem); a.op = i;
+        a.set(w);
+        L.push_back(std::move(a));
         return MF_OK;
     }
     if (o.kind == 4) {

@@ -16,7 +16,9 @@ class Wav2Vec2Engine(ConvNet):
         """max_batch > 1: `logits_batch` runs the windows of several sessions in one pass (one engine per GPU)"""
         self.n_samples, self.vocab = n_samples, cfg["vocab"]
         if blob is None:
-            blob, pb = pack_wav2vec2(state_dict, cfg, n_samples)
+            # one window per pass: the transformer layers run as ONE persistent kernel (csrc/w2v_stack.cuh); an engine that batches the
+            # windows of several sessions (max_batch > 1) keeps the op-by-op program, whose GEMMs take any number of rows
+            blob, pb = pack_wav2vec2(state_dict, cfg, n_samples, fused_stack=max_batch == 1)
             self.flops_per_call = pb.flops_per_sample
             n_frames = pb.n_frames
         self.n_frames = n_frames

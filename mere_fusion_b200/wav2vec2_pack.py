@@ -12,7 +12,7 @@ The program is built for ONE window length (n_samples = (l + m + r) * 320 = 8960
 """
 import numpy as np
 
-from .convnet_pack import ACT_GELU, ProgramBuilder
+from .convnet_pack import ACT_GELU, ProgramBuilder, f32_to_bf16_bits
 
 XLSR53_CFG = dict(vocab=44, hidden=1024, layers=24, heads=16, inter=4096, conv_dim=(512,) * 7, conv_stride=(5, 2, 2, 2, 2, 2, 2),
                   conv_kernel=(10, 3, 3, 3, 3, 2, 2), pos_k=128, pos_groups=16, eps=1e-5)
@@ -30,7 +30,7 @@ def frame_counts(n_samples, cfg=XLSR53_CFG):
     return out
 
 
-def pack_wav2vec2(sd, cfg=XLSR53_CFG, n_samples=8960):
+def pack_wav2vec2(sd, cfg=XLSR53_CFG, n_samples=8960, fused_stack=True):
     sd = {k: _np(v) for k, v in sd.items()}
     D, L, H, I, V = cfg["hidden"], cfg["layers"], cfg["heads"], cfg["inter"], cfg["vocab"]
     cd, ck, cs = cfg["conv_dim"], cfg["conv_kernel"], cfg["conv_stride"]
@@ -82,23 +82,47 @@ def pack_wav2vec2(sd, cfg=XLSR53_CFG, n_samples=8960):
     for g in range(G):   # x = h + gelu(conv(h)): the residual is added after the activation
         pb.conv1d_same(h, g * cg, x, g * cg, wpos[g * cg:(g + 1) * cg], bpos[g * cg:(g + 1) * cg], left_pad=K // 2, act=ACT_GELU,
                        res=(h, g * cg), res_after_act=True)
-    ln, qkv, ao, hid = pb.buffer(T, 1, D), pb.buffer(T, 1, 3 * D), pb.buffer(T, 1, D), pb.buffer(T, 1, I)
-    for i in range(L):
-        p = f"wav2vec2.encoder.layers.{i}."
-        pb.layer_norm(x, ln, need(p + "layer_norm.weight", (D,)), need(p + "layer_norm.bias", (D,)), eps)
-        wq = np.concatenate([need(p + f"attention.{n}_proj.weight", (D, D)) for n in ("q", "k", "v")])
-        bq = np.concatenate([need(p + f"attention.{n}_proj.bias", (D,)) for n in ("q", "k", "v")])
-        pb.linear(ln, 0, qkv, 0, wq, bq)
-        pb.attention((qkv, 0), (qkv, D), (qkv, 2 * D), (ao, 0), H, D // H)
-        x1 = pb.buffer(T, 1, D)
-        pb.linear(ao, 0, x1, 0, need(p + "attention.out_proj.weight", (D, D)), need(p + "attention.out_proj.bias", (D,)), res=(x, 0))
-        pb.layer_norm(x1, ln, need(p + "final_layer_norm.weight", (D,)), need(p + "final_layer_norm.bias", (D,)), eps)
-        pb.linear(ln, 0, hid, 0, need(p + "feed_forward.intermediate_dense.weight", (I, D)), need(p + "feed_forward.intermediate_dense.bias", (I,)),
-                  act=ACT_GELU)
+    import os
+    fused = fused_stack and os.environ.get("MF_W2V_FUSED", "1") != "0" and D % 256 == 0 and I % 256 == 0 and max(3 * D, I) <= 4096 and T <= 32 and (D // H) <= 128
+    ln = pb.buffer(T, 1, D)
+    if fused:
+        # the L transformer layers as ONE persistent kernel (csrc/w2v_stack.cuh): per layer fp32 vectors, then bf16 row-major matrices
+        parts = []
+        for i in range(L):
+            p = f"wav2vec2.encoder.layers.{i}."
+            wq = np.concatenate([need(p + f"attention.{n}_proj.weight", (D, D)) for n in ("q", "k", "v")])
+            bq = np.concatenate([need(p + f"attention.{n}_proj.bias", (D,)) for n in ("q", "k", "v")])
+            vec = np.concatenate([need(p + "layer_norm.weight", (D,)), need(p + "layer_norm.bias", (D,)), bq,
+                                  need(p + "attention.out_proj.bias", (D,)), need(p + "final_layer_norm.weight", (D,)),
+                                  need(p + "final_layer_norm.bias", (D,)), need(p + "feed_forward.intermediate_dense.bias", (I,)),
+                                  need(p + "feed_forward.output_dense.bias", (D,))]).astype(np.float32)
+            assert vec.size == 9 * D + I
+            parts.append(vec.tobytes())
+            for wm in (wq, need(p + "attention.out_proj.weight", (D, D)), need(p + "feed_forward.intermediate_dense.weight", (I, D)),
+                       need(p + "feed_forward.output_dense.weight", (D, I))):
+                parts.append(f32_to_bf16_bits(np.ascontiguousarray(wm, np.float32)).tobytes())
         x2 = pb.buffer(T, 1, D)
-        pb.linear(hid, 0, x2, 0, need(p + "feed_forward.output_dense.weight", (D, I)), need(p + "feed_forward.output_dense.bias", (D,)),
-                  res=(x1, 0))
+        flops = L * (2 * T * (4 * D * D + 2 * D * I) + 2 * 2 * H * T * T * (D // H))
+        pb.transformer_stack(x, x2, b"".join(parts), D, I, H, L, eps, flops)
         x = x2
+    else:
+        qkv, ao, hid = pb.buffer(T, 1, 3 * D), pb.buffer(T, 1, D), pb.buffer(T, 1, I)
+        for i in range(L):
+            p = f"wav2vec2.encoder.layers.{i}."
+            pb.layer_norm(x, ln, need(p + "layer_norm.weight", (D,)), need(p + "layer_norm.bias", (D,)), eps)
+            wq = np.concatenate([need(p + f"attention.{n}_proj.weight", (D, D)) for n in ("q", "k", "v")])
+            bq = np.concatenate([need(p + f"attention.{n}_proj.bias", (D,)) for n in ("q", "k", "v")])
+            pb.linear(ln, 0, qkv, 0, wq, bq)
+            pb.attention((qkv, 0), (qkv, D), (qkv, 2 * D), (ao, 0), H, D // H)
+            x1 = pb.buffer(T, 1, D)
+            pb.linear(ao, 0, x1, 0, need(p + "attention.out_proj.weight", (D, D)), need(p + "attention.out_proj.bias", (D,)), res=(x, 0))
+            pb.layer_norm(x1, ln, need(p + "final_layer_norm.weight", (D,)), need(p + "final_layer_norm.bias", (D,)), eps)
+            pb.linear(ln, 0, hid, 0, need(p + "feed_forward.intermediate_dense.weight", (I, D)),
+                      need(p + "feed_forward.intermediate_dense.bias", (I,)), act=ACT_GELU)
+            x2 = pb.buffer(T, 1, D)
+            pb.linear(hid, 0, x2, 0, need(p + "feed_forward.output_dense.weight", (D, I)), need(p + "feed_forward.output_dense.bias", (D,)),
+                      res=(x1, 0))
+            x = x2
     pb.layer_norm(x, ln, need("wav2vec2.encoder.layer_norm.weight", (D,)), need("wav2vec2.encoder.layer_norm.bias", (D,)), eps)
     pb.linear(ln, 0, -1, 0, need("lm_head.weight", (V, D)), need("lm_head.bias", (V,)), mode=3)
     pb.aux = [n_samples, T, V, conv0_id, cd[0], ck[0], cs[0]]
