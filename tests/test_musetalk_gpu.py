@@ -135,8 +135,9 @@ def test_musetalk_small_config_vs_oracle():
     torch.cuda.synchronize()
     got = f32.cpu().numpy()
     p = psnr(got, img)
-    # bf16 activations through ~60 residual blocks with GroupNorm: stated tolerance
-    assert p >= 30.0, f"PSNR {p:.2f} dB"
+    # bf16 activations through ~60 residual blocks with GroupNorm: stated tolerance 40 dB (measured 48 dB; the gate used to be a
+    # loose 30 dB, under which an 18 dB regression would have passed -- VERDICT r1)
+    assert p >= 40.0, f"PSNR {p:.2f} dB"
     d = np.abs(out.cpu().numpy().astype(int) - u8.astype(int))
     assert d.mean() < 3.0
     assert out.shape == (B, 256, 256, 3) and eng.last_launches > 400
@@ -192,7 +193,7 @@ def test_musetalk_full_config_vs_oracle():
     p = psnr(f32.cpu().numpy(), img)
     d = np.abs(out.cpu().numpy().astype(int) - u8.astype(int))
     print(f"musetalk full config: PSNR vs oracle {p:.2f} dB, mean |du8| {d.mean():.3f}, launches {eng.last_launches}")
-    assert p >= 30.0, f"PSNR {p:.2f} dB"                       # same stated tolerance as the reduced-width config
+    assert p >= 40.0, f"PSNR {p:.2f} dB"                       # same stated tolerance as the reduced-width config
     assert d.mean() < 3.0 and img.std() > 0.05                 # and the case is not a flat image
     # frame 1 alone == frame 1 of the batch (per-item GroupNorm / attention), to the split-K summation order
     f1 = torch.empty(1, 256, 256, 3, device="cuda")
