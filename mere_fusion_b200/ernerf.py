@@ -72,6 +72,37 @@ class ErnerfRenderer:
         out_pinned.copy_(d_out, non_blocking=True)
         return out_pinned
 
+    def render_host_async(self, pose, intrinsics, H, W, auds_pinned, eye, outH=None, outW=None, **kw):
+        """Pipelined end-to-end call with HOST buffers: pinned fp32 auds in, pinned u8 frame out through a two-slot ring.  The
+        device -> host copy of this frame runs on a side stream and overlaps the NEXT call's render; before returning, the current
+        stream is made to wait for the PREVIOUS call's copy, so a caller that brackets calls on its stream sees every copy inside
+        some call's interval.  Returns (pinned u8 tensor, event): the frame is complete once the event has completed (it is
+        overwritten two calls later)."""
+        oH, oW = int(outH or H), int(outW or W)
+        p = getattr(self, "_pipe", None)
+        if p is None or p["shape"] != (oH, oW) or p["auds"].shape != auds_pinned.shape:
+            p = self._pipe = dict(shape=(oH, oW), k=0, copy=torch.cuda.Stream(self.device),
+                                  auds=torch.empty(auds_pinned.shape, dtype=torch.float32, device=self.device),
+                                  dev=[torch.empty((oH, oW, 3), dtype=torch.uint8, device=self.device) for _ in range(2)],
+                                  pin=[torch.empty((oH, oW, 3), dtype=torch.uint8).pin_memory() for _ in range(2)],
+                                  rendered=[torch.cuda.Event() for _ in range(2)], copied=[torch.cuda.Event() for _ in range(2)], used=[False, False])
+        s = p["k"] & 1
+        p["k"] += 1
+        cur = torch.cuda.current_stream(self.device)
+        if p["used"][s]:
+            cur.wait_event(p["copied"][s])                 # the slot's previous frame has left the device buffer
+        p["auds"].copy_(auds_pinned, non_blocking=True)
+        self.render(pose, intrinsics, H, W, p["auds"], eye, out=p["dev"][s], outH=oH, outW=oW, **kw)
+        p["rendered"][s].record(cur)
+        p["copy"].wait_event(p["rendered"][s])
+        with torch.cuda.stream(p["copy"]):
+            p["pin"][s].copy_(p["dev"][s], non_blocking=True)
+            p["copied"][s].record(p["copy"])
+        p["used"][s] = True
+        if p["used"][s ^ 1]:
+            cur.wait_event(p["copied"][s ^ 1])             # the previous frame's copy, overlapped with this frame's render
+        return p["pin"][s], p["copied"][s]
+
     @property
     def last_launches(self):
         return lib().mf_ernerf_last_launches(self.ctx.handle)
