@@ -918,6 +918,9 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
     HeadSmem &sm = *reinterpret_cast<HeadSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int F = p.n_frames;
+    // programmatic dependent launch: k_torso_compose may be scheduled onto the SMs that CTAs of this grid leave (its torso pass does not
+    // depend on the head; it waits for this grid before compositing), and this grid itself may have started while k_setup drains
+    pdl_launch();
 
     // stage the MLP image with one bulk TMA copy
     if (threadIdx.x == 0) {
@@ -928,6 +931,10 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
     if (threadIdx.x == 0) {
         mbar_expect_tx(&sm.bar, ER_H_BYTES);
         bulk_g2s(sm.mlp, p.mlp_image, ER_H_BYTES, &sm.bar);
+    }
+    for (int i = threadIdx.x; i < HEAD_MAX_FRAMES * (ER_MAX_STEPS + 1); i += HEAD_THREADS) (&sm.hist[0][0])[i] = 0;
+    pdl_wait();                    // k_setup has completed: hit lists, counters and the audio feature are visible
+    if (threadIdx.x == 0) {
         int end = 0;
         for (int f = 0; f < HEAD_MAX_FRAMES; f++) {
             if (f < F) { end += p.f[f].counters[CT_NHIT]; sm.eye[f] = p.f[f].eye; }
@@ -936,7 +943,6 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
         }
     }
     if (threadIdx.x < 32 * F) sm.enc_a[threadIdx.x >> 5][threadIdx.x & 31] = p.f[threadIdx.x >> 5].state[threadIdx.x & 31];
-    for (int i = threadIdx.x; i < HEAD_MAX_FRAMES * (ER_MAX_STEPS + 1); i += HEAD_THREADS) (&sm.hist[0][0])[i] = 0;
     mbar_wait(&sm.bar, 0);
     __syncthreads();
 
@@ -1116,6 +1122,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
 }
 
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ SetupBatch b) {
+    pdl_launch();                  // k_head's CTAs may take the SMs this grid's CTAs leave (they wait for the grid's completion themselves)
     const int n_audio = 8 * b.n;   // one CTA per attention window
     if ((int)blockIdx.x < n_audio) audio_cta(b.f[blockIdx.x >> 3], blockIdx.x & 7);
     else ray_pass(b, (int)blockIdx.x - n_audio, (int)gridDim.x - n_audio);
@@ -1142,34 +1149,16 @@ struct TorsoSmem {
     alignas(16) __half mlp[ER_T_HALFS];
     alignas(16) __half tconst[2 * 32 * 50];
     alignas(16) __half xt[TORSO_WARPS][32 * TX_STRIDE];
+    float bsave[TORSO_WARPS][4][3][32];   // torso-over-background colour of the warp's tiles, kept across the wait for k_head
     float bias[64];
     float anchor[48];
 };
 
+#define TORSO_TPW 4   /* tiles whose torso colour a warp keeps (shared memory) across the wait for k_head */
 __global__ void __launch_bounds__(TORSO_THREADS, TORSO_MINB) k_torso_compose(const __grid_constant__ ComposeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TorsoSmem &sm = *reinterpret_cast<TorsoSmem *>(smem_raw);
-    // ---- the reference's loop control (renderer.py:246-256) replayed on the life histogram k_head filled:
-    // A(0) = N, A(c) = hits - #{rays with life < c}; round r starts at c_r with n_alive = A(c_r), n_step = clamp(N / n_alive, 1, 8);
-    // the summed n_step C selects the snapshot of the rays that were still alive after max_steps samples
     __shared__ int s_snap;
-    if (threadIdx.x == 0) {
-        const int N = p.g.N, nhit = p.counters[CT_NHIT];
-        int c = 0, r = 0, gone = 0, upto = 1;
-        while (c < p.max_steps && r < ER_MAX_ROUNDS) {
-            for (; upto < c; upto++) gone += p.counters[CT_HIST + upto];
-            const int n_alive = c == 0 ? N : nhit - gone;
-            if (n_alive <= 0) break;
-            const int n_step = max(min(N / n_alive, 8), 1);
-            if (blockIdx.x == 0) {
-                int *row = p.counters + CT_ROUNDS + 4 * r;
-                row[0] = n_alive; row[1] = 0; row[2] = r == 0 ? nhit : -1; row[3] = n_step;
-            }
-            c += n_step;
-            r++;
-        }
-        s_snap = min(max(c - p.max_steps, 0), ER_SNAPS - 1);
-    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < ER_T_HALFS / 8; i += blockDim.x)
         reinterpret_cast<uint4 *>(sm.mlp)[i] = __ldg(reinterpret_cast<const uint4 *>(p.tm.mlp_image) + i);
@@ -1182,33 +1171,75 @@ __global__ void __launch_bounds__(TORSO_THREADS, TORSO_MINB) k_torso_compose(con
 
     const int N = p.g.N;
     const int n_tiles = (N + 31) / 32;
-    for (int tile = blockIdx.x * TORSO_WARPS + warp; tile < n_tiles; tile += gridDim.x * TORSO_WARPS) {
-        float b[3] = {0.f, 0.f, 0.f};
-        torso_tile(p.tm, p.g, p.tf, tile, lane, sm.xt[warp], sm.mlp, sm.bias, b);
-        __syncwarp();
-        const int pix = tile * 32 + lane;
-        if (pix >= N) continue;
-        float ws = p.weights_sum[pix];
-        float hd[3];
-        if (ws < 0.f) {   // alive after max_steps samples: the state after C samples
-            const float4 v = p.snap[(size_t)((int)(-ws) - 1) * ER_SNAPS + s_snap];
-            ws = v.x; hd[0] = v.y; hd[1] = v.z; hd[2] = v.w;
-            p.weights_sum[pix] = ws;
-            p.image[pix * 3] = hd[0]; p.image[pix * 3 + 1] = hd[1]; p.image[pix * 3 + 2] = hd[2];
-        } else {
-            hd[0] = p.image[pix * 3]; hd[1] = p.image[pix * 3 + 1]; hd[2] = p.image[pix * 3 + 2];
+    const int stride = gridDim.x * TORSO_WARPS;
+    // round 0 is executed by every warp (its wait contains a __syncthreads); later rounds only by the warps that still have tiles
+    for (int round = 0; ; round++) {
+        const int base = blockIdx.x * TORSO_WARPS + warp + round * stride * TORSO_TPW;
+        if (round > 0 && base >= n_tiles) break;
+        // ---- torso pass: independent of the head -- under programmatic dependent launch it runs on the SMs that k_head's CTAs have
+        // already left, while the last rays of the frame are still being shaded
+#pragma unroll 1
+        for (int i = 0; i < TORSO_TPW; i++) {
+            const int tile = base + i * stride;
+            if (tile < n_tiles) {
+                float b[3] = {0.f, 0.f, 0.f};
+                torso_tile(p.tm, p.g, p.tf, tile, lane, sm.xt[warp], sm.mlp, sm.bias, b);
+                sm.bsave[warp][i][0][lane] = b[0]; sm.bsave[warp][i][1][lane] = b[1]; sm.bsave[warp][i][2][lane] = b[2];
+                __syncwarp();
+            }
         }
-        float out[3];
+        if (round == 0) {
+            // ---- k_head has completed.  The reference's loop control (renderer.py:246-256) replayed on the life histogram it filled:
+            // A(0) = N, A(c) = hits - #{rays with life < c}; round r starts at c_r with n_alive = A(c_r), n_step = clamp(N / n_alive, 1, 8);
+            // the summed n_step C selects the snapshot of the rays that were still alive after max_steps samples
+            pdl_wait();
+            if (threadIdx.x == 0) {
+                const int nhit = p.counters[CT_NHIT];
+                int c = 0, r = 0, gone = 0, upto = 1;
+                while (c < p.max_steps && r < ER_MAX_ROUNDS) {
+                    for (; upto < c; upto++) gone += p.counters[CT_HIST + upto];
+                    const int n_alive = c == 0 ? N : nhit - gone;
+                    if (n_alive <= 0) break;
+                    const int n_step = max(min(N / n_alive, 8), 1);
+                    if (blockIdx.x == 0) {
+                        int *row = p.counters + CT_ROUNDS + 4 * r;
+                        row[0] = n_alive; row[1] = 0; row[2] = r == 0 ? nhit : -1; row[3] = n_step;
+                    }
+                    c += n_step;
+                    r++;
+                }
+                s_snap = min(max(c - p.max_steps, 0), ER_SNAPS - 1);
+            }
+            __syncthreads();
+        }
+        // ---- resolve + compose (renderer.py:275-277)
+#pragma unroll 1
+        for (int i = 0; i < TORSO_TPW; i++) {
+            const int tile = base + i * stride;
+            const int pix = tile * 32 + lane;
+            if (tile >= n_tiles || pix >= N) continue;
+            float ws = p.weights_sum[pix];
+            float hd[3];
+            if (ws < 0.f) {   // alive after max_steps samples: the state after C samples
+                const float4 v = p.snap[(size_t)((int)(-ws) - 1) * ER_SNAPS + s_snap];
+                ws = v.x; hd[0] = v.y; hd[1] = v.z; hd[2] = v.w;
+                p.weights_sum[pix] = ws;
+                p.image[pix * 3] = hd[0]; p.image[pix * 3 + 1] = hd[1]; p.image[pix * 3 + 2] = hd[2];
+            } else {
+                hd[0] = p.image[pix * 3]; hd[1] = p.image[pix * 3 + 1]; hd[2] = p.image[pix * 3 + 2];
+            }
+            float out[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            out[k] = fminf(fmaxf(hd[k] + (1 - ws) * b[k], 0.f), 1.f);
-            if (p.dbg_image_head) p.dbg_image_head[pix * 3 + k] = hd[k];
-        }
-        if (p.out_f32) { p.out_f32[pix * 3] = out[0]; p.out_f32[pix * 3 + 1] = out[1]; p.out_f32[pix * 3 + 2] = out[2]; }
-        if (p.out_u8) {
-            p.out_u8[pix * 3] = (uint8_t)(out[0] * 255.f);
-            p.out_u8[pix * 3 + 1] = (uint8_t)(out[1] * 255.f);
-            p.out_u8[pix * 3 + 2] = (uint8_t)(out[2] * 255.f);
+            for (int k = 0; k < 3; k++) {
+                out[k] = fminf(fmaxf(hd[k] + (1 - ws) * sm.bsave[warp][i][k][lane], 0.f), 1.f);
+                if (p.dbg_image_head) p.dbg_image_head[pix * 3 + k] = hd[k];
+            }
+            if (p.out_f32) { p.out_f32[pix * 3] = out[0]; p.out_f32[pix * 3 + 1] = out[1]; p.out_f32[pix * 3 + 2] = out[2]; }
+            if (p.out_u8) {
+                p.out_u8[pix * 3] = (uint8_t)(out[0] * 255.f);
+                p.out_u8[pix * 3 + 1] = (uint8_t)(out[1] * 255.f);
+                p.out_u8[pix * 3 + 2] = (uint8_t)(out[2] * 255.f);
+            }
         }
     }
 }
@@ -1579,6 +1610,18 @@ static bool inv4(const double *m, double *out) {
 
 static inline float h16(float v) { return __half2float(__float2half_rn(v)); }
 
+// launch configuration with programmatic stream serialization (MF_ERNERF_PDL=0 turns it off): the kernel may start while its
+// predecessor in the stream drains; it calls griddepcontrol.wait before touching anything the predecessor writes
+static void pdl_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *at, dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("MF_ERNERF_PDL"); on = e ? atoi(e) != 0 : 1; }
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = on ? 1 : 0;
+}
+
 // one frame of a (possibly batched) render: argument checks, workspace, geometry and the k_setup arguments
 struct PreparedFrame {
     ErnerfState *s;
@@ -1711,10 +1754,13 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
         const long slots_per_cta = HEAD_WARPS * (32 / chunk);
         const int grid = (int)std::min<long>(s0->head_grid, std::max<long>(1, (total_tiles * 32 + slots_per_cta - 1) / slots_per_cta));
         if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[0], stream));
-        if (chunk == 1) k_head<1><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
-        else if (chunk == 4) k_head<4><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
-        else if (chunk == 8) k_head<8><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
-        else k_head<2><<<grid, HEAD_THREADS, sizeof(HeadSmem), stream>>>(hp);
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute at[1];
+        pdl_config(cfg, at, dim3(grid), dim3(HEAD_THREADS), sizeof(HeadSmem), stream);
+        if (chunk == 1) MF_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_head<1>, hp));
+        else if (chunk == 4) MF_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_head<4>, hp));
+        else if (chunk == 8) MF_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_head<8>, hp));
+        else MF_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_head<2>, hp));
         if (s0->profile) MF_CUDA(ctx, cudaEventRecord(s0->ev_head[1], stream));
         launches++;
     }
@@ -1739,7 +1785,12 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
         {
             const int n_tiles = (N + 31) / 32;
             const int grid = std::max(1, std::min((n_tiles + TORSO_WARPS - 1) / TORSO_WARPS, ctx->sm_count * 4));
-            k_torso_compose<<<grid, TORSO_THREADS, sizeof(TorsoSmem), stream>>>(cp);
+            cudaLaunchConfig_t cfg;
+            cudaLaunchAttribute at[1];
+            pdl_config(cfg, at, dim3(grid), dim3(TORSO_THREADS), sizeof(TorsoSmem), stream);
+            // n > 1 (batched sessions): the second frame's kernel must not pass the first one's -- only the first is a programmatic dependent
+            if (i > 0) cfg.numAttrs = 0;
+            MF_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_torso_compose, cp));
             launches++;
         }
         if (pf[i].resize) {
