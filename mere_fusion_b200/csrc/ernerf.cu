@@ -50,9 +50,10 @@ using namespace ernerf;
 #define CT_TICKET 1   /* next unclaimed hit-list slot (k_head refill) */
 #define CT_SAMPLES 2  /* samples shaded by k_head */
 #define CT_NSURV 3    /* rays alive after max_steps samples = snapshot slots in use */
-#define CT_TTICKET 4  /* next unclaimed torso tile (k_head's tail filler) */
+#define CT_PASSES 5   /* k_head telemetry: warp passes (32 sample lanes each) of the launch (frame 0's counters) */
+#define CT_TILES 6    /* k_head telemetry: 16-row MLP tiles evaluated */
 #define CT_HIST 8     /* [ER_MAX_STEPS + 1] rays by life; bin max_steps = alive after max_steps samples */
-#define CT_ROUNDS 48  /* [ER_MAX_ROUNDS + 1][4] derived by k_torso_compose: n_alive, 0, samples emitted (round 0; -1 = not tracked), n_step */
+#define CT_ROUNDS 48  /* [ER_MAX_ROUNDS + 1][4] derived by k_torso_compose: n_alive, k_head telemetry (row 0: warp passes, row 1: MLP tiles), samples emitted (round 0; -1 = not tracked), n_step */
 #define CT_INTS 128
 #define ER_SNAPS 8    /* states recorded per surviving ray: after sample max_steps + j, j = 0..7 */
 
@@ -398,6 +399,10 @@ __device__ __forceinline__ void zero_acc(float (&c)[NT][4]) {
     for (int i = 0; i < NT; i++) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
 }
 
+__device__ __forceinline__ uint32_t relu_half2(uint32_t v) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2 *>(&v), __float2half2_rn(0.f));
+    return *reinterpret_cast<const uint32_t *>(&r);
+}
 // accumulators of NT n-tiles -> A fragments of NT/2 k-steps for the next layer (ReLU optional)
 template <int NT, bool RELU>
 __device__ __forceinline__ void acc_to_a(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
@@ -405,10 +410,11 @@ __device__ __forceinline__ void acc_to_a(const float (&c)[NT][4], uint32_t (&a)[
     for (int j = 0; j < NT / 2; j++) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            float v0 = c[2 * j + h][0], v1 = c[2 * j + h][1], v2 = c[2 * j + h][2], v3 = c[2 * j + h][3];
-            if (RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-            a[j][2 * h + 0] = pack_half2(v0, v1);
-            a[j][2 * h + 1] = pack_half2(v2, v3);
+            // ReLU on the packed pair (one HMNMX2 for two values): rounding to fp16 is monotone and keeps the sign, so
+            // max(rn(x), 0) == rn(max(x, 0)) up to the sign of a zero, which a dot product cannot see
+            const uint32_t lo = pack_half2(c[2 * j + h][0], c[2 * j + h][1]), hi = pack_half2(c[2 * j + h][2], c[2 * j + h][3]);
+            a[j][2 * h + 0] = RELU ? relu_half2(lo) : lo;
+            a[j][2 * h + 1] = RELU ? relu_half2(hi) : hi;
         }
     }
 }
@@ -489,8 +495,8 @@ __device__ __forceinline__ void torso_gather_t(const TorsoModel &tm, float u, fl
         __half2 val[GL][4];
 #pragma unroll
         for (int j = 0; j < GL; j++) {
-            if (l0 + j < ND) grid_level_prep<IDX_DENSE>(tm.tl.lv[l0 + j], u, v, idx[j], pu[j], pv[j]);
-            else grid_level_prep<IDX_TILE2>(tm.tl.lv[l0 + j], u, v, idx[j], pu[j], pv[j]);
+            if (l0 + j < ND) grid_level_prep<IDX_DENSE>(tm.tl.lv[l0 + j], tm.tl.lv[l0 + j].offset, u, v, idx[j], pu[j], pv[j]);
+            else grid_level_prep<IDX_TILE2>(tm.tl.lv[l0 + j], tm.tl.lv[l0 + j].offset, u, v, idx[j], pu[j], pv[j]);
         }
 #pragma unroll
         for (int j = 0; j < GL; j++)
@@ -709,6 +715,7 @@ struct HeadSmem {
     int end[HEAD_MAX_FRAMES];          // cumulative hit-list lengths
     int hist[HEAD_MAX_FRAMES][ER_MAX_STEPS + 1];
     int samples[HEAD_MAX_FRAMES];
+    int passes, tiles;                 // telemetry: warp passes / MLP tiles of this CTA
     alignas(8) uint64_t bar;
 };
 
@@ -736,7 +743,7 @@ __device__ __forceinline__ void gen_ray(const FrameGeom &g, int idx, Ray &r) {
 }
 
 // density + color for one 16-row tile (rows m*16..m*16+15 of the warp's 32-sample tile).
-// Returns in lane (t == 0): sigma logit of rows g / g+8; rgb in lanes t == 0 (r, g) and t == 1 (b).
+// Returns in lane (t == 0): sigma logit of rows g / g+8; rgb LOGITS (fp16-rounded) in lanes t == 0 (r, g) and t == 1 (b).
 // ea_lo / eye_lo belong to the frame of row g, ea_hi / eye_hi to that of row g + 8 (a tile may mix sessions).
 __device__ __forceinline__ void head_mlp_tile(const unsigned char *mlp, const float *ea_lo, const float *ea_hi, __half *xs, const __half *sh,
                                               int m, int lane, float eye_lo, float eye_hi, float &sig_lo, float &sig_hi, float (&rgb)[4]) {
@@ -835,8 +842,10 @@ __device__ __forceinline__ void head_mlp_tile(const unsigned char *mlp, const fl
         float cc[1][4];
         zero_acc(cc);
         mlp_layer<4, 1, 72>(cc, ah, W + ER_H_COL2, lane);
+        // the colour LOGITS: sigmoid + the affine map are applied by the caller once each value sits in its sample's lane (3 per lane
+        // and pass instead of 4 per lane and tile here, most of them on padding columns)
 #pragma unroll
-        for (int i = 0; i < 4; i++) rgb[i] = affine16(sigmoid16(round_half(cc[0][i])));
+        for (int i = 0; i < 4; i++) rgb[i] = round_half(cc[0][i]);
     }
 }
 
@@ -863,7 +872,8 @@ __device__ __forceinline__ void gather_planes_t(const HeadParams &p, float x, fl
     for (int pl = 0; pl < 3; pl++) {
         const float a = (pl == 1) ? u1 : u0;
         const float b = (pl == 0) ? u1 : u2;
-        const float *tab = p.planes + (size_t)pl * p.plane_rows;
+        const float *tab = p.planes + (size_t)pl * p.plane_rows;   // generic path
+        const uint32_t pbase = (uint32_t)pl * p.plane_rows;         // 32-bit element offset of the plane (3 * plane_rows < 2^32: checked at load)
         float f[12];
         if (ND < 0) {
 #pragma unroll
@@ -878,13 +888,13 @@ __device__ __forceinline__ void gather_planes_t(const HeadParams &p, float x, fl
                 float pu[GL], pv[GL], v[GL][4];
 #pragma unroll
                 for (int j = 0; j < GL; j++) {
-                    if (l0 + j < ND) grid_level_prep<IDX_DENSE>(p.hl.lv[l0 + j], a, b, idx[j], pu[j], pv[j]);
-                    else grid_level_prep<IDX_HASH2>(p.hl.lv[l0 + j], a, b, idx[j], pu[j], pv[j]);
+                    if (l0 + j < ND) grid_level_prep<IDX_DENSE>(p.hl.lv[l0 + j], pbase + p.hl.lv[l0 + j].offset, a, b, idx[j], pu[j], pv[j]);
+                    else grid_level_prep<IDX_HASH2>(p.hl.lv[l0 + j], pbase + p.hl.lv[l0 + j].offset, a, b, idx[j], pu[j], pv[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < GL; j++)
 #pragma unroll
-                    for (int c = 0; c < 4; c++) v[j][c] = __ldg(tab + idx[j][c]);
+                    for (int c = 0; c < 4; c++) v[j][c] = __ldg(p.planes + idx[j][c]);
 #pragma unroll
                 for (int j = 0; j < GL; j++) {
                     float r = 0.f;
@@ -941,6 +951,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
             sm.end[f] = end;
             sm.samples[f] = 0;
         }
+        sm.passes = sm.tiles = 0;
     }
     if (threadIdx.x < 32 * F) sm.enc_a[threadIdx.x >> 5][threadIdx.x & 31] = p.f[threadIdx.x >> 5].state[threadIdx.x & 31];
     mbar_wait(&sm.bar, 0);
@@ -1046,10 +1057,15 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
                     c2 = hi ? b_hi : b_lo;
                 }
             }
+            c0 = affine16(sigmoid16(c0)); c1 = affine16(sigmoid16(c1)); c2 = affine16(sigmoid16(c2));   // network.py:296-297 (fp16 ops)
             __syncwarp();
             for (int f = 0; f < F; f++) {
                 const int c = __popc(__ballot_sync(0xffffffffu, has && fi == f));
                 if (lane == 0 && c) atomicAdd(&sm.samples[f], c);
+            }
+            if (lane == 0) {
+                atomicAdd(&sm.passes, 1);
+                atomicAdd(&sm.tiles, ((hasmask & 0xffffu) != 0u) + ((hasmask >> 16) != 0u));
             }
         }
 
@@ -1119,6 +1135,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
         if (sm.hist[f][b]) atomicAdd(&p.f[f].counters[CT_HIST + b], sm.hist[f][b]);
     }
     if (threadIdx.x < F && sm.samples[threadIdx.x]) atomicAdd(&p.f[threadIdx.x].counters[CT_SAMPLES], sm.samples[threadIdx.x]);
+    if (threadIdx.x == 32 && sm.passes) { atomicAdd(&p.f[0].counters[CT_PASSES], sm.passes); atomicAdd(&p.f[0].counters[CT_TILES], sm.tiles); }
 }
 
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ SetupBatch b) {
@@ -1203,7 +1220,9 @@ __global__ void __launch_bounds__(TORSO_THREADS, TORSO_MINB) k_torso_compose(con
                     const int n_step = max(min(N / n_alive, 8), 1);
                     if (blockIdx.x == 0) {
                         int *row = p.counters + CT_ROUNDS + 4 * r;
-                        row[0] = n_alive; row[1] = 0; row[2] = r == 0 ? nhit : -1; row[3] = n_step;
+                        // column 1 carries k_head's telemetry: warp passes (row 0), 16-row MLP tiles (row 1)
+                        row[0] = n_alive; row[1] = r == 0 ? p.counters[CT_PASSES] : (r == 1 ? p.counters[CT_TILES] : 0);
+                        row[2] = r == 0 ? nhit : -1; row[3] = n_step;
                     }
                     c += n_step;
                     r++;
@@ -1480,7 +1499,8 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
     const size_t audio_halfs = (size_t)32 * cfg->audio_in_dim * 3 + 32 + 32 * 32 * 3 + 32 + 64 * 32 * 3 + 64 +
                                64 * 64 * 3 + 64 + 64 * 64 + 64 + 32 * 64 + 32 + 16 * 32 * 3 + 16 + 8 * 16 * 3 + 8 +
                                4 * 8 * 3 + 4 + 2 * 4 * 3 + 2 + 1 * 2 * 3 + 1 + 64 + 8;
-    bool ok = sz[ER_ID_HEAD_PLANES] == (size_t)3 * head_rows * 4 && sz[ER_ID_BITFIELD] == G * G * G / 8 &&
+    bool ok = (uint64_t)3 * head_rows < (1ull << 32) &&   // k_head indexes the three planes with 32-bit element offsets
+              sz[ER_ID_HEAD_PLANES] == (size_t)3 * head_rows * 4 && sz[ER_ID_BITFIELD] == G * G * G / 8 &&
               sz[ER_ID_TORSO_TABLE] == (size_t)torso_rows * 4 && sz[ER_ID_TORSO_DENSITY] == G * G * 4 &&
               sz[ER_ID_HEAD_MLP] == ER_H_BYTES && sz[ER_ID_TORSO_MLP] == ER_T_BYTES &&
               sz[ER_ID_AUDIO] == audio_halfs * 2 && sz[ER_ID_MISC] == 24 * 4 && sz[ER_ID_TORSO_CONST] == 2 * 32 * 50 * 2;

@@ -78,18 +78,33 @@ __device__ __forceinline__ float grid_level_f32(const float *__restrict__ table,
 }
 
 // corner indices and fractions of one level (the first half of grid_level_f32 / grid_level_f16x2): lets a caller
-// issue the loads of several levels back to back
+// issue the loads of several levels back to back.  `base` (32-bit element offset of the level's table inside the caller's
+// allocation, lv.offset + whatever precedes it) is folded into the indices HERE, in 32-bit arithmetic: added to the pointer
+// by the caller it became a 64-bit multiply-add per corner (5 instructions per load instead of 2, ~10 % of k_head's
+// instruction count, profiles/r02_k_head_v8 source page).  Same indices as grid_index2c corner by corner:
+// (gx + 1) + gy * s == (gx + gy * s) + 1 and (gy + 1) * P == gy * P + P in uint32 arithmetic.
 template <int CLS>
-__device__ __forceinline__ void grid_level_prep(const GridLevel &lv, float u, float v, uint32_t (&idx)[4], float &pu, float &pv) {
+__device__ __forceinline__ void grid_level_prep(const GridLevel &lv, uint32_t base, float u, float v, uint32_t (&idx)[4], float &pu, float &pv) {
     pu = fmaf(u, lv.scale, 0.5f); pv = fmaf(v, lv.scale, 0.5f);
     const float flu = floorf(pu), flv = floorf(pv);
     const uint32_t gx = (uint32_t)flu, gy = (uint32_t)flv;
     pu -= (float)gx;
     pv -= (float)gy;
-    idx[0] = lv.offset + grid_index2c<CLS>(lv, gx, gy);
-    idx[1] = lv.offset + grid_index2c<CLS>(lv, gx + 1, gy);
-    idx[2] = lv.offset + grid_index2c<CLS>(lv, gx, gy + 1);
-    idx[3] = lv.offset + grid_index2c<CLS>(lv, gx + 1, gy + 1);
+    if (CLS == IDX_DENSE) {
+        const uint32_t i0 = base + gx + gy * lv.stride1, i2 = i0 + lv.stride1;
+        idx[0] = i0; idx[1] = i0 + 1u; idx[2] = i2; idx[3] = i2 + 1u;
+    } else if (CLS == IDX_HASH2) {
+        const uint32_t m = lv.size - 1u, h0 = gy * 2654435761u, h1 = h0 + 2654435761u;
+        idx[0] = base + ((gx ^ h0) & m);
+        idx[1] = base + (((gx + 1u) ^ h0) & m);
+        idx[2] = base + ((gx ^ h1) & m);
+        idx[3] = base + (((gx + 1u) ^ h1) & m);
+    } else {
+        idx[0] = base + grid_index2c<CLS>(lv, gx, gy);
+        idx[1] = base + grid_index2c<CLS>(lv, gx + 1, gy);
+        idx[2] = base + grid_index2c<CLS>(lv, gx, gy + 1);
+        idx[3] = base + grid_index2c<CLS>(lv, gx + 1, gy + 1);
+    }
 }
 
 // same kernel instantiated for scalar_t = at::Half, C = 2 (torso encoder under autocast):
