@@ -101,6 +101,7 @@ struct ErnerfState {
     float4 *snap = nullptr;  // [N][ER_SNAPS] (ws, r, g, b) of rays alive after max_steps samples
     float *rays_t = nullptr, *fars = nullptr, *weights_sum = nullptr, *image = nullptr;
     float *final_f32 = nullptr;  // [N,3] when a resize follows
+    float *torso_rgb = nullptr;  // [3][N] torso over background, written and read back by k_torso_compose (across its wait for k_head)
     int head_grid = 0;
     bool chunk_forced = false;
     int chunk = 2;           // CH: samples of a ray shaded side by side (MF_HEAD_CHUNK = 1 | 2 | 4 | 8; 2 measured best)
@@ -186,6 +187,7 @@ struct SetupBatch {   // one audio CTA per frame of a batched render (HEAD_MAX_F
     uint32_t max_steps, cascade, grid_size;
     const uint8_t *bitfield;
     const uint8_t *bitfield_linear;   // nullable
+    MarchParams mp;                   // make_march_params of the fields above (host), grid = the linear bitfield when there is one
     float aabb[6];
 };
 __device__ __forceinline__ void audio_cta(const SetupParams &p, int b);
@@ -196,8 +198,7 @@ __device__ __forceinline__ void gen_ray(const FrameGeom &g, int idx, Ray &r);
 // their final head result here (weights_sum = 0, image = 0).
 __device__ __forceinline__ void ray_pass(const SetupBatch &b, int cta, int n_ctas) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    MarchParams mp = make_march_params(b.bound, b.dt_gamma, b.max_steps, b.cascade, b.grid_size, b.bitfield);
-    if (b.bitfield_linear) { mp.grid = b.bitfield_linear; mp.linear = true; }
+    const MarchParams &mp = b.mp;
     for (int f = 0; f < b.n; f++) {
         const RayPassFrame &fr = b.r[f];
         const int n_tiles = (fr.g.N + 31) / 32;
@@ -434,7 +435,7 @@ __device__ __forceinline__ void load_a(uint32_t (&a)[4], const __half *tile, int
 #define TORSO_GL 4   /* torso grid levels gathered together */
 #endif
 #ifndef TORSO_MINB
-#define TORSO_MINB 3 /* k_torso_compose CTAs per SM the register allocation aims at */
+#define TORSO_MINB 2 /* k_torso_compose CTAs per SM: 2 (105 registers, no spills) measured 4 % faster per frame than 3 (80 registers, 100 B of spills) */
 #endif
 
 struct TorsoModel {   // shared by the frames of a batch
@@ -698,6 +699,7 @@ struct HeadParams {
     float bound, min_near, dt_gamma, T_thresh;
     uint32_t max_steps, cascade, grid_size;
     int n_frames;
+    MarchParams mp;
     HeadFrame f[HEAD_MAX_FRAMES];
 };
 
@@ -859,7 +861,7 @@ __device__ __forceinline__ void head_mlp_tile(const unsigned char *mlp, const fl
 // (36 of them per sample; long scoreboard is the kernel's top stall once the barrier wait is gone).  Same arithmetic per level as
 // grid_level_f32 (gridencoder.cu:75-175): bit-identical features.
 #ifndef ER_GATHER_LEVELS
-#define ER_GATHER_LEVELS 3   /* levels gathered together: 3 measured; must divide 12 */
+#define ER_GATHER_LEVELS 6   /* levels whose loads are written back to back in the source (2, 3, 4, 6 measured within 1 %: ptxas schedules the loads itself); must divide 12 */
 #endif
 template <int ND>
 __device__ __forceinline__ void gather_planes_t(const HeadParams &p, float x, float y, float z, __half *row) {
@@ -957,8 +959,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) k_head(const __grid_constant_
     mbar_wait(&sm.bar, 0);
     __syncthreads();
 
-    MarchParams mp = make_march_params(p.bound, p.dt_gamma, p.max_steps, p.cascade, p.grid_size, p.bitfield);
-    if (p.bitfield_linear) { mp.grid = p.bitfield_linear; mp.linear = true; }
+    const MarchParams &mp = p.mp;                // built on the host: read from the constant bank, not carried in registers
     __half *xs = sm.w[warp].xs;
     __half *sh = sm.w[warp].sh;
     float (*rs)[32] = sm.w[warp].ray;
@@ -1158,6 +1159,7 @@ struct ComposeParams {
     const float4 *snap;
     int *counters;                // this frame's counters: life histogram in, derived rounds out
     int max_steps;
+    float *torso_rgb;             // scratch [3][N]
     float *out_f32;               // [N,3] or null
     uint8_t *out_u8;              // [N,3] or null
     float *dbg_image_head;
@@ -1166,16 +1168,19 @@ struct TorsoSmem {
     alignas(16) __half mlp[ER_T_HALFS];
     alignas(16) __half tconst[2 * 32 * 50];
     alignas(16) __half xt[TORSO_WARPS][32 * TX_STRIDE];
-    float bsave[TORSO_WARPS][4][3][32];   // torso-over-background colour of the warp's tiles, kept across the wait for k_head
     float bias[64];
     float anchor[48];
+    int hist[ER_MAX_STEPS + 2];   // the frame's life histogram + the hit count, staged for the loop-control replay
+    int snap;
 };
 
-#define TORSO_TPW 4   /* tiles whose torso colour a warp keeps (shared memory) across the wait for k_head */
+// The grid is ONE wave (TORSO_MINB CTAs per SM): under programmatic dependent launch its CTAs take the SMs that k_head's CTAs have
+// already left and run the torso pass of ALL their tiles -- independent of the head -- while the last rays of the frame are still being
+// shaded; the torso-over-background colour waits in an L2-resident scratch (each thread reads back what it wrote).  Then the grid
+// waits for k_head, replays the loop control and composes.
 __global__ void __launch_bounds__(TORSO_THREADS, TORSO_MINB) k_torso_compose(const __grid_constant__ ComposeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TorsoSmem &sm = *reinterpret_cast<TorsoSmem *>(smem_raw);
-    __shared__ int s_snap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < ER_T_HALFS / 8; i += blockDim.x)
         reinterpret_cast<uint4 *>(sm.mlp)[i] = __ldg(reinterpret_cast<const uint4 *>(p.tm.mlp_image) + i);
@@ -1189,76 +1194,70 @@ __global__ void __launch_bounds__(TORSO_THREADS, TORSO_MINB) k_torso_compose(con
     const int N = p.g.N;
     const int n_tiles = (N + 31) / 32;
     const int stride = gridDim.x * TORSO_WARPS;
-    // round 0 is executed by every warp (its wait contains a __syncthreads); later rounds only by the warps that still have tiles
-    for (int round = 0; ; round++) {
-        const int base = blockIdx.x * TORSO_WARPS + warp + round * stride * TORSO_TPW;
-        if (round > 0 && base >= n_tiles) break;
-        // ---- torso pass: independent of the head -- under programmatic dependent launch it runs on the SMs that k_head's CTAs have
-        // already left, while the last rays of the frame are still being shaded
+    // ---- torso pass
 #pragma unroll 1
-        for (int i = 0; i < TORSO_TPW; i++) {
-            const int tile = base + i * stride;
-            if (tile < n_tiles) {
-                float b[3] = {0.f, 0.f, 0.f};
-                torso_tile(p.tm, p.g, p.tf, tile, lane, sm.xt[warp], sm.mlp, sm.bias, b);
-                sm.bsave[warp][i][0][lane] = b[0]; sm.bsave[warp][i][1][lane] = b[1]; sm.bsave[warp][i][2][lane] = b[2];
-                __syncwarp();
+    for (int tile = blockIdx.x * TORSO_WARPS + warp; tile < n_tiles; tile += stride) {
+        float b[3] = {0.f, 0.f, 0.f};
+        torso_tile(p.tm, p.g, p.tf, tile, lane, sm.xt[warp], sm.mlp, sm.bias, b);
+        const int pix = tile * 32 + lane;
+        if (pix < N) { p.torso_rgb[pix] = b[0]; p.torso_rgb[N + pix] = b[1]; p.torso_rgb[2 * N + pix] = b[2]; }
+        __syncwarp();
+    }
+    // ---- k_head has completed.  The reference's loop control (renderer.py:246-256) replayed on the life histogram it filled:
+    // A(0) = N, A(c) = hits - #{rays with life < c}; round r starts at c_r with n_alive = A(c_r), n_step = clamp(N / n_alive, 1, 8);
+    // the summed n_step C selects the snapshot of the rays that were still alive after max_steps samples
+    pdl_wait();
+    if (threadIdx.x <= ER_MAX_STEPS) sm.hist[threadIdx.x] = p.counters[CT_HIST + threadIdx.x];     // one round trip for the histogram
+    if (threadIdx.x == ER_MAX_STEPS + 1) sm.hist[ER_MAX_STEPS + 1] = p.counters[CT_NHIT];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nhit = sm.hist[ER_MAX_STEPS + 1];
+        int c = 0, r = 0, gone = 0, upto = 1;
+        while (c < p.max_steps && r < ER_MAX_ROUNDS) {
+            for (; upto < c; upto++) gone += sm.hist[upto];
+            const int n_alive = c == 0 ? N : nhit - gone;
+            if (n_alive <= 0) break;
+            const int n_step = max(min(N / n_alive, 8), 1);
+            if (blockIdx.x == 0) {
+                int *row = p.counters + CT_ROUNDS + 4 * r;
+                // column 1 carries k_head's telemetry: warp passes (row 0), 16-row MLP tiles (row 1)
+                row[0] = n_alive; row[1] = r == 0 ? p.counters[CT_PASSES] : (r == 1 ? p.counters[CT_TILES] : 0);
+                row[2] = r == 0 ? nhit : -1; row[3] = n_step;
             }
+            c += n_step;
+            r++;
         }
-        if (round == 0) {
-            // ---- k_head has completed.  The reference's loop control (renderer.py:246-256) replayed on the life histogram it filled:
-            // A(0) = N, A(c) = hits - #{rays with life < c}; round r starts at c_r with n_alive = A(c_r), n_step = clamp(N / n_alive, 1, 8);
-            // the summed n_step C selects the snapshot of the rays that were still alive after max_steps samples
-            pdl_wait();
-            if (threadIdx.x == 0) {
-                const int nhit = p.counters[CT_NHIT];
-                int c = 0, r = 0, gone = 0, upto = 1;
-                while (c < p.max_steps && r < ER_MAX_ROUNDS) {
-                    for (; upto < c; upto++) gone += p.counters[CT_HIST + upto];
-                    const int n_alive = c == 0 ? N : nhit - gone;
-                    if (n_alive <= 0) break;
-                    const int n_step = max(min(N / n_alive, 8), 1);
-                    if (blockIdx.x == 0) {
-                        int *row = p.counters + CT_ROUNDS + 4 * r;
-                        // column 1 carries k_head's telemetry: warp passes (row 0), 16-row MLP tiles (row 1)
-                        row[0] = n_alive; row[1] = r == 0 ? p.counters[CT_PASSES] : (r == 1 ? p.counters[CT_TILES] : 0);
-                        row[2] = r == 0 ? nhit : -1; row[3] = n_step;
-                    }
-                    c += n_step;
-                    r++;
-                }
-                s_snap = min(max(c - p.max_steps, 0), ER_SNAPS - 1);
-            }
-            __syncthreads();
-        }
-        // ---- resolve + compose (renderer.py:275-277)
+        sm.snap = min(max(c - p.max_steps, 0), ER_SNAPS - 1);
+    }
+    __syncthreads();
+    const int s_snap = sm.snap;
+    // ---- resolve + compose (renderer.py:275-277)
 #pragma unroll 1
-        for (int i = 0; i < TORSO_TPW; i++) {
-            const int tile = base + i * stride;
-            const int pix = tile * 32 + lane;
-            if (tile >= n_tiles || pix >= N) continue;
-            float ws = p.weights_sum[pix];
-            float hd[3];
-            if (ws < 0.f) {   // alive after max_steps samples: the state after C samples
-                const float4 v = p.snap[(size_t)((int)(-ws) - 1) * ER_SNAPS + s_snap];
-                ws = v.x; hd[0] = v.y; hd[1] = v.z; hd[2] = v.w;
-                p.weights_sum[pix] = ws;
-                p.image[pix * 3] = hd[0]; p.image[pix * 3 + 1] = hd[1]; p.image[pix * 3 + 2] = hd[2];
-            } else {
-                hd[0] = p.image[pix * 3]; hd[1] = p.image[pix * 3 + 1]; hd[2] = p.image[pix * 3 + 2];
-            }
-            float out[3];
+    for (int tile = blockIdx.x * TORSO_WARPS + warp; tile < n_tiles; tile += stride) {
+        const int pix = tile * 32 + lane;
+        if (pix >= N) continue;
+        float ws = p.weights_sum[pix];
+        const float b[3] = {p.torso_rgb[pix], p.torso_rgb[N + pix], p.torso_rgb[2 * N + pix]};
+        float hd[3];
+        if (ws < 0.f) {   // alive after max_steps samples: the state after C samples
+            const float4 v = p.snap[(size_t)((int)(-ws) - 1) * ER_SNAPS + s_snap];
+            ws = v.x; hd[0] = v.y; hd[1] = v.z; hd[2] = v.w;
+            p.weights_sum[pix] = ws;
+            p.image[pix * 3] = hd[0]; p.image[pix * 3 + 1] = hd[1]; p.image[pix * 3 + 2] = hd[2];
+        } else {
+            hd[0] = p.image[pix * 3]; hd[1] = p.image[pix * 3 + 1]; hd[2] = p.image[pix * 3 + 2];
+        }
+        float out[3];
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                out[k] = fminf(fmaxf(hd[k] + (1 - ws) * sm.bsave[warp][i][k][lane], 0.f), 1.f);
-                if (p.dbg_image_head) p.dbg_image_head[pix * 3 + k] = hd[k];
-            }
-            if (p.out_f32) { p.out_f32[pix * 3] = out[0]; p.out_f32[pix * 3 + 1] = out[1]; p.out_f32[pix * 3 + 2] = out[2]; }
-            if (p.out_u8) {
-                p.out_u8[pix * 3] = (uint8_t)(out[0] * 255.f);
-                p.out_u8[pix * 3 + 1] = (uint8_t)(out[1] * 255.f);
-                p.out_u8[pix * 3 + 2] = (uint8_t)(out[2] * 255.f);
-            }
+        for (int k = 0; k < 3; k++) {
+            out[k] = fminf(fmaxf(hd[k] + (1 - ws) * b[k], 0.f), 1.f);
+            if (p.dbg_image_head) p.dbg_image_head[pix * 3 + k] = hd[k];
+        }
+        if (p.out_f32) { p.out_f32[pix * 3] = out[0]; p.out_f32[pix * 3 + 1] = out[1]; p.out_f32[pix * 3 + 2] = out[2]; }
+        if (p.out_u8) {
+            p.out_u8[pix * 3] = (uint8_t)(out[0] * 255.f);
+            p.out_u8[pix * 3 + 1] = (uint8_t)(out[1] * 255.f);
+            p.out_u8[pix * 3 + 2] = (uint8_t)(out[2] * 255.f);
         }
     }
 }
@@ -1439,10 +1438,10 @@ extern "C" int mf_ernerf_blob_layout(int32_t *out, int n) {
 
 static void ernerf_free_ws(ErnerfState *s) {
     cudaFree(s->hits); cudaFree(s->snap); cudaFree(s->rays_t); cudaFree(s->fars);
-    cudaFree(s->weights_sum); cudaFree(s->image); cudaFree(s->final_f32);
+    cudaFree(s->weights_sum); cudaFree(s->image); cudaFree(s->final_f32); cudaFree(s->torso_rgb);
     s->hits = nullptr;
     s->snap = nullptr;
-    s->rays_t = s->fars = s->weights_sum = s->image = s->final_f32 = nullptr;
+    s->rays_t = s->fars = s->weights_sum = s->image = s->final_f32 = s->torso_rgb = nullptr;
     s->capN = 0;
 }
 
@@ -1603,6 +1602,7 @@ static int ensure_ws(mf_ctx *ctx, ErnerfState *s, int N) {
     MF_CUDA(ctx, cudaMalloc(&s->weights_sum, (size_t)N * 4));
     MF_CUDA(ctx, cudaMalloc(&s->image, (size_t)N * 12));
     MF_CUDA(ctx, cudaMalloc(&s->final_f32, (size_t)N * 12));
+    MF_CUDA(ctx, cudaMalloc(&s->torso_rgb, (size_t)N * 12));
     s->capN = N;
     return MF_OK;
 }
@@ -1742,6 +1742,8 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
     sb.bound = s0->cfg.bound; sb.min_near = s0->cfg.min_near; sb.dt_gamma = s0->cfg.dt_gamma;
     sb.max_steps = s0->cfg.max_steps; sb.cascade = s0->cfg.cascade; sb.grid_size = s0->cfg.grid_size;
     sb.bitfield = s0->bitfield; sb.bitfield_linear = s0->bitfield_linear;
+    sb.mp = make_march_params(sb.bound, sb.dt_gamma, sb.max_steps, sb.cascade, sb.grid_size, sb.bitfield);
+    if (sb.bitfield_linear) { sb.mp.grid = sb.bitfield_linear; sb.mp.linear = true; }
     for (int i = 0; i < 6; i++) sb.aabb[i] = aabb[i];
     {   // 8 audio CTAs per frame first, then the ray pass: one CTA (32 warps, one ray per lane) per SM that is left
         const int n_audio = 8 * n;
@@ -1757,6 +1759,7 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
     hp.bound = s0->cfg.bound; hp.min_near = s0->cfg.min_near; hp.dt_gamma = s0->cfg.dt_gamma; hp.T_thresh = s0->cfg.T_thresh;
     hp.max_steps = s0->cfg.max_steps; hp.cascade = s0->cfg.cascade; hp.grid_size = s0->cfg.grid_size;
     hp.n_frames = n;
+    hp.mp = sb.mp;
     for (int i = 0; i < n; i++) {
         ErnerfState *s = pf[i].s;
         HeadFrame &hf = hp.f[i];
@@ -1797,14 +1800,14 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
         cp.tm.shrink = s->cfg.torso_shrink; cp.tm.G = (int)s->cfg.grid_size;
         cp.tf.bg_color = (const __half *)f->bg_color; cp.tf.dbg_mask = d ? d->torso_mask : nullptr;
         for (int k = 0; k < 6; k++) cp.tf.wa[k] = pf[i].wa[k];
-        cp.weights_sum = s->weights_sum; cp.image = s->image; cp.snap = s->snap; cp.counters = ctr[i];
+        cp.weights_sum = s->weights_sum; cp.image = s->image; cp.snap = s->snap; cp.counters = ctr[i]; cp.torso_rgb = s->torso_rgb;
         cp.max_steps = (int)s->cfg.max_steps;
         cp.out_f32 = pf[i].resize ? s->final_f32 : f->out_image_f32;
         cp.out_u8 = pf[i].resize ? nullptr : outs[i];
         cp.dbg_image_head = d ? d->image_head : nullptr;
         {
             const int n_tiles = (N + 31) / 32;
-            const int grid = std::max(1, std::min((n_tiles + TORSO_WARPS - 1) / TORSO_WARPS, ctx->sm_count * 4));
+            const int grid = std::max(1, std::min((n_tiles + TORSO_WARPS - 1) / TORSO_WARPS, ctx->sm_count * TORSO_MINB));   // one wave
             cudaLaunchConfig_t cfg;
             cudaLaunchAttribute at[1];
             pdl_config(cfg, at, dim3(grid), dim3(TORSO_THREADS), sizeof(TorsoSmem), stream);

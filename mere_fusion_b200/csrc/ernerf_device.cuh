@@ -187,16 +187,19 @@ __device__ __forceinline__ void near_far_aabb(float ox, float oy, float oz, floa
 
 struct MarchParams {
     float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Cf;
-    float mip_bound0, mip_rbound0, halfH;  // level-0 constants of the fast path
+    float mip_bound0, mip_rbound0, halfH, rH2;  // level-0 constants of the fast path
     uint32_t H;
-    bool fast;  // cascade == 1 and H a power of two: level is always 0 and the double sub-expression
-                // 0.5 * (x * rbound + 1) * H is an exact power-of-two scaling, so fp32 gives the same bits
+    bool fast;  // cascade == 1, H a power of two and dt_min == dt_max: level is always 0, the double sub-expression
+                // 0.5 * (x * rbound + 1) * H is an exact power-of-two scaling (fp32 gives the same bits), and the step
+                // clamp(t * dt_gamma, dt_min, dt_max) is the constant dt_max (max_steps <= H, every shipped configuration)
     bool linear;  // `grid` is a copy of the bitfield re-indexed as (z * H + y) * H + x (same bits, made at load time): the fused
                   // frame kernels test ~10^7 voxels per frame and the Morton expansion was a quarter of that loop's instructions
     const uint8_t *grid;
 };
 
-__device__ __forceinline__ MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+// __host__ too: the fused frame kernels take the finished struct as a kernel argument (constant bank, no registers); every field is a
+// correctly rounded IEEE fp32 operation on both sides
+__host__ __device__ __forceinline__ MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
                                                          uint32_t H, const uint8_t *grid) {
     MarchParams p;
     p.bound = bound;
@@ -212,7 +215,8 @@ __device__ __forceinline__ MarchParams make_march_params(float bound, float dt_g
     p.mip_bound0 = fminf(1.0f, bound);
     p.mip_rbound0 = 1 / p.mip_bound0;
     p.halfH = 0.5f * (float)H;
-    p.fast = (C == 1) && ((H & (H - 1)) == 0);
+    p.rH2 = 2.0f * p.rH;
+    p.fast = (C == 1) && ((H & (H - 1)) == 0) && p.dt_min == p.dt_max;
     p.linear = false;
     return p;
 }
@@ -227,30 +231,50 @@ struct Ray {
 template <bool FAST>
 __device__ __forceinline__ bool march_find_t(const MarchParams &p, const Ray &r, float &t, const float far, float &x,
                                              float &y, float &z, float &dt_out, uint32_t &vox) {
+    if (FAST) {
+        // Same values as the general loop below, fewer instructions per voxel (the ray pass of k_setup tests ~10^7 voxels per frame,
+        // profiles/r02_k_setup_torso_v10.md):  dt is the constant dt_max;  (int)clamp(v, 0, hi) == (int)min(v, hi) for v > -1
+        // (conversion truncates toward zero; v >= -H * 2^-24 because x is clamped to the bound);  nx + 0.5 + 0.5 * sign(d) and
+        // (..) * rH * 2 - 1 are exact in fp32 (small integers, power-of-two scale), so they may be regrouped.
+        const float dt = p.dt_max, hi = (float)(p.H - 1);
+        // 0.5 + 0.5 * copysign(1, d) is 1 or 0 by the sign BIT of d: added to the voxel coordinate as an integer
+        auto pos = [](float d) { return (int)((~__float_as_uint(d)) >> 31); };
+        while (t < far) {
+            x = clampf_(fmaf(t, r.dx, r.ox), -p.bound, p.bound);
+            y = clampf_(fmaf(t, r.dy, r.oy), -p.bound, p.bound);
+            z = clampf_(fmaf(t, r.dz, r.oz), -p.bound, p.bound);
+            const int nx = fminf(fmaf(x, p.mip_rbound0, 1.0f) * p.halfH, hi);
+            const int ny = fminf(fmaf(y, p.mip_rbound0, 1.0f) * p.halfH, hi);
+            const int nz = fminf(fmaf(z, p.mip_rbound0, 1.0f) * p.halfH, hi);
+            const uint32_t index = p.linear ? ((uint32_t)nz * p.H + (uint32_t)ny) * p.H + (uint32_t)nx : morton3D(nx, ny, nz);
+            const bool occ = __ldg(p.grid + index / 8) & (1 << (index % 8));
+            if (occ) {
+                dt_out = dt;
+                vox = index;
+                return true;
+            }
+            const float tx = (fmaf((float)(nx + pos(r.dx)), p.rH2, -1.0f) * p.mip_bound0 - x) * r.rdx;
+            const float ty = (fmaf((float)(ny + pos(r.dy)), p.rH2, -1.0f) * p.mip_bound0 - y) * r.rdy;
+            const float tz = (fmaf((float)(nz + pos(r.dz)), p.rH2, -1.0f) * p.mip_bound0 - z) * r.rdz;
+            const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+            do {
+                t += dt;
+            } while (t < tt);
+        }
+        return false;
+    }
     while (t < far) {
         x = clampf_(fmaf(t, r.dx, r.ox), -p.bound, p.bound);
         y = clampf_(fmaf(t, r.dy, r.oy), -p.bound, p.bound);
         z = clampf_(fmaf(t, r.dz, r.oz), -p.bound, p.bound);
         const float dt = clampf_(t * p.dt_gamma, p.dt_min, p.dt_max);
-        float mip_bound;
-        int nx, ny, nz;
-        uint32_t index;
-        if (FAST) {
-            mip_bound = p.mip_bound0;
-            const float hi = (float)(p.H - 1);
-            nx = clampf_(fmaf(x, p.mip_rbound0, 1.0f) * p.halfH, 0.0f, hi);
-            ny = clampf_(fmaf(y, p.mip_rbound0, 1.0f) * p.halfH, 0.0f, hi);
-            nz = clampf_(fmaf(z, p.mip_rbound0, 1.0f) * p.halfH, 0.0f, hi);
-            index = p.linear ? ((uint32_t)nz * p.H + (uint32_t)ny) * p.H + (uint32_t)nx : morton3D(nx, ny, nz);
-        } else {
-            const int level = max(mip_from_pos(x, y, z, p.Cf), mip_from_dt(dt, p.Hf, p.Cf));
-            mip_bound = fminf(scalbnf(1, level), p.bound);
-            const float mip_rbound = 1 / mip_bound;
-            nx = clampf_(0.5 * fmaf(x, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
-            ny = clampf_(0.5 * fmaf(y, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
-            nz = clampf_(0.5 * fmaf(z, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
-            index = level * p.H3 + morton3D(nx, ny, nz);
-        }
+        const int level = max(mip_from_pos(x, y, z, p.Cf), mip_from_dt(dt, p.Hf, p.Cf));
+        const float mip_bound = fminf(scalbnf(1, level), p.bound);
+        const float mip_rbound = 1 / mip_bound;
+        const int nx = clampf_(0.5 * fmaf(x, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
+        const int ny = clampf_(0.5 * fmaf(y, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
+        const int nz = clampf_(0.5 * fmaf(z, mip_rbound, 1.0f) * p.H, 0.0f, (float)(p.H - 1));
+        const uint32_t index = level * p.H3 + morton3D(nx, ny, nz);
         const bool occ = __ldg(p.grid + index / 8) & (1 << (index % 8));
         if (occ) {
             dt_out = dt;
@@ -319,7 +343,7 @@ __device__ __forceinline__ float freq_elem(const float *in, uint32_t D, uint32_t
     if (c < D) return in[c];
     const uint32_t col = c / D - 1, d = c % D, freq = col / 2;
     const float phase_shift = (col % 2) * (3.141592653589793f / 2);
-    return __sinf(scalbnf(in[d], freq) + phase_shift);
+    return __sinf(in[d] * (float)(1u << freq) + phase_shift);   // scalbnf(in[d], freq): the same exact power-of-two scaling
 }
 
 // autocast(fp16) elementwise helpers
