@@ -506,14 +506,16 @@ __device__ __forceinline__ void torso_gather_t(const TorsoModel &tm, float u, fl
 #pragma unroll
         for (int j = 0; j < GL; j++) {
             const float w[4] = {(1 - pu[j]) * (1 - pv[j]), pu[j] * (1 - pv[j]), (1 - pu[j]) * pv[j], pu[j] * pv[j]};
-            float o0 = 0.f, o1 = 0.f;
+            // Half += float (grid_level_f16x2): the product rounded to half, then a half + half sum rounded to half.  __hadd2 IS that sum:
+            // the fp32 sum of two halves is either exact or (exponents > 13 bits apart) strictly inside the larger one's rounding
+            // interval, so rounding it to half equals rounding the exact sum once.  4 instead of 12 instructions per corner.
+            __half2 o = __float2half2_rn(0.f);
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const float2 f = __half22float2(val[j][c]);
-                o0 = round_half(o0 + round_half(w[c] * f.x));
-                o1 = round_half(o1 + round_half(w[c] * f.y));
+                o = __hadd2(o, __floats2half2_rn(w[c] * f.x, w[c] * f.y));
             }
-            *reinterpret_cast<uint32_t *>(row + 2 * (l0 + j)) = pack_half2(o0, o1);
+            *reinterpret_cast<__half2 *>(row + 2 * (l0 + j)) = o;
         }
     }
 }
