@@ -183,7 +183,7 @@ def _run_reference(args):
             "config": {"workload": "ernerf_512x512_fullframe", "note": "reference has no CPU renderer; oracle port"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=sys.__stdout__, flush=True)
 
 
 def reference_cuda_leg(dev, n_frames=24, warmup=4):
@@ -1028,6 +1028,7 @@ def mixed_leg(args, dev, local, rank, world, flush, timed_fn, shared, ernerf_blo
 
 
 def main():
+    sys.stdout = sys.stderr   # ONE JSON line on stdout: everything else (the plugins' own fps prints, library chatter) goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -1439,7 +1440,7 @@ def main():
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": f"128x128 sub-grid of the 512x512 ray grid (16384 of {RAYS} rays), full pipeline, "
                                           f"median of 3 ({t:.2f} s each), scaled to full frames; the reference has no CPU renderer"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=sys.__stdout__, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
