@@ -105,6 +105,8 @@ struct ErnerfState {
     float *torso_rgb = nullptr;  // [3][N] torso over background, written and read back by k_torso_compose (across its wait for k_head)
     int head_grid = 0;
     bool chunk_forced = false;
+    int setup_per_sm = 1;    // k_setup CTAs per SM for a BATCHED pass (2 measured 1.5 % faster per frame at 4 sessions; for one frame the more
+                             // interleaved hit list costs k_head 2 %, so a single frame keeps one CTA per SM)
     int chunk = 2;           // CH: samples of a ray shaded side by side (MF_HEAD_CHUNK = 1 | 2 | 4 | 8; 2 measured best)
     int last_launches = 0;
     float misc_host[24] = {0};
@@ -1559,6 +1561,9 @@ extern "C" int mf_ernerf_load(mf_ctx *ctx, const void *blob, size_t nbytes, cons
     int per_sm = 0;
     MF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_head<2>, HEAD_THREADS, sizeof(HeadSmem)));
     MF_REQUIRE(ctx, per_sm >= 1, "k_head does not fit on an SM");
+    MF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_setup, SETUP_THREADS, 0));
+    s->setup_per_sm = std::max(1, std::min(per_sm, 2));
+    if (const char *e = getenv("MF_SETUP_PER_SM")) s->setup_per_sm = std::max(1, std::min(atoi(e), 2));
     {   // experiment hook: MF_HEAD_CHUNK = samples of a ray shaded side by side per pass (2, 4 or 8)
         const char *e = getenv("MF_HEAD_CHUNK");
         if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8)) { s->chunk = atoi(e); s->chunk_forced = true; }
@@ -1758,7 +1763,7 @@ static int render_frames(mf_ctx *const *ctxs, const mf_ernerf_frame *frames, uin
     for (int i = 0; i < 6; i++) sb.aabb[i] = aabb[i];
     {   // 8 audio CTAs per frame first, then the ray pass: one CTA (32 warps, one ray per lane) per SM that is left
         const int n_audio = 8 * n;
-        const int ray_ctas = (int)std::max<long>(1, std::min<long>(ctx->sm_count - n_audio, (total_tiles + SETUP_THREADS / 32 - 1) / (SETUP_THREADS / 32)));
+        const int ray_ctas = (int)std::max<long>(1, std::min<long>((n > 1 ? s0->setup_per_sm : 1) * ctx->sm_count - n_audio, (total_tiles + SETUP_THREADS / 32 - 1) / (SETUP_THREADS / 32)));
         k_setup<<<n_audio + ray_ctas, SETUP_THREADS, 0, stream>>>(sb);
     }
     int launches = 1;
