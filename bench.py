@@ -1344,7 +1344,7 @@ def main():
                                 "note": "SURVEY 8(d) config 4 (i): 2048 explicit rays (every 128th pixel of the 512x512 grid) per frame"},
         "ernerf_batched_sessions": {
             "workload": f"{FB} ErNeRF sessions of one avatar model per GPU, one 512x512 frame each per pass (mf_ernerf_render_batch: ONE k_head "
-                        "launch per pass, shared round barriers); bit-identical to single renders",
+                        "launch per pass, the sessions' hit lists form one queue); bit-identical to single renders",
             "value": world * Kb * FB / (batch_ms / 1e3), "unit": "frames/s", "ms_per_pass": batch_ms / Kb, "ms_per_frame": batch_ms / Kb / FB,
             "e2e": {"value": world * Kb * FB / (batch_e2e_ms / 1e3), "unit": "frames/s",
                     "h2d_bytes_per_step": int(FB * (auds_pin[0].numel() * 4 + 84)), "d2h_bytes_per_step": int(outs_b_pin.numel())},
@@ -1360,7 +1360,7 @@ def main():
         "plugin_level": plugin,
         "nerfasr_acoustic_model": asr,
         "gpu_launches": int(launches),
-        "kernels_per_step": ["k_setup (audio encoder CTA + ray pass + torso pass)", "k_head", "k_compose"],
+        "kernels_per_step": ["k_setup (8 audio-window CTAs + the ray pass)", "k_head", "k_torso_compose"],
         "clocks": sampler.result(),
         "roofline": {"kernel": "k_head", "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s",
                      "frac": ach_gbs / pk["hbm"], "traffic": traffic, "l1_view": l1_view, "peak_source": pk["src"] + " burst",

@@ -72,7 +72,7 @@ class NeRFReal(BaseReal):
             self.fullbody_list_cycle = [cv2.imread(p) for p in lst[:len(self.provider)]]
         self.asr = NerfASR(opt, self, feature_fn=feature_fn, device=f"cuda:{device}" if self._has_cuda() else "cpu")
         self.asr.warm_up()
-        self._out = None
+        self._out = None                                # two-slot ring of device / pinned frames (_render_async)
         self._pin = None
         self._bg = None
 
@@ -100,27 +100,46 @@ class NeRFReal(BaseReal):
             except StopIteration:
                 pass
 
-    def render_image(self, pose, eye, auds):
-        """Trainer.test_gui_with_data (utils.py:1191-1223) + nerfreal.py:110 in one call"""
+    def _render_async(self, pose, eye, auds):
+        """Trainer.test_gui_with_data (utils.py:1191-1223) + nerfreal.py:110, enqueued only: the frame is rendered into one of two device
+        buffers and copied to its pinned twin on a copy stream; returns (pinned u8 tensor, event that completes with the copy)."""
         import torch
+        dev = self.renderer.device
         if self._out is None:
-            self._out = torch.empty((self.H, self.W, 3), dtype=torch.uint8, device=self.renderer.device)
-            self._pin = torch.empty((self.H, self.W, 3), dtype=torch.uint8).pin_memory()
+            self._out = [torch.empty((self.H, self.W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+            self._pin = [torch.empty((self.H, self.W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._done = [torch.cuda.Event() for _ in range(2)]
+            self._drawn = [torch.cuda.Event() for _ in range(2)]
+            self._copy = torch.cuda.Stream(dev)
+            self._slot = 0
         p = self.provider
         fix_eye = getattr(self.opt, "fix_eye", -1)
         eye = fix_eye if (self.opt.exp_eye and fix_eye >= 0) else eye            # utils.py:937-940
-        dev = self.renderer.device
         if self._bg is None and getattr(p, "bg_img", None) is not None:        # data['bg_color'] (provider.py:330-332), uploaded once
             self._bg = torch.from_numpy(np.ascontiguousarray(p.bg_img, np.float32).reshape(-1, 3)).to(dev, torch.float16)
+        k = self._slot
+        self._slot ^= 1
         with torch.cuda.device(dev):                     # this thread may never have selected the session's GPU
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(self._done[k])                # the slot's previous frame has left the device buffer (no-op the first time)
             self.renderer.render(pose, p.intrinsics, p.H, p.W, auds.contiguous(), eye if eye is not None else 0.0,
-                                 out=self._out, outH=self.H, outW=self.W, bg_color=self._bg)
-            self._pin.copy_(self._out, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
-        return self._pin.numpy().copy()
+                                 out=self._out[k], outH=self.H, outW=self.W, bg_color=self._bg)
+            self._drawn[k].record(cur)
+            self._copy.wait_event(self._drawn[k])
+            with torch.cuda.stream(self._copy):
+                self._pin[k].copy_(self._out[k], non_blocking=True)
+                self._done[k].record(self._copy)
+        return self._pin[k], self._done[k]
 
-    def test_step(self, loop=None, audio_track=None, video_track=None):
-        """nerfreal.py:70-127"""
+    def render_image(self, pose, eye, auds):
+        """one frame, synchronously: [H, W, 3] u8 RGB ndarray (a view of a pinned buffer that is reused two frames later)"""
+        pin, done = self._render_async(pose, eye, auds)
+        done.synchronize()
+        return pin.numpy()
+
+    def _step(self, loop, audio_track):
+        """nerfreal.py:70-108: one step up to the image -- the two audio frames are emitted, the video frame is returned as a handle
+        (kind, payload, provider index): ("image", ndarray) or ("pending", (pinned tensor, event))."""
         index, pose, eye = next(self.provider)
         auds = self.asr.get_next_feat()
         audiotype1 = audiotype2 = 0
@@ -140,27 +159,50 @@ class NeRFReal(BaseReal):
             mirindex = self.mirror_index(len(self.custom_img_cycle[audiotype1]), self.custom_index[audiotype1])
             image = cv2.cvtColor(self.custom_img_cycle[audiotype1][mirindex], cv2.COLOR_BGR2RGB)
             self.custom_index[audiotype1] += 1
-        else:
-            image = self.render_image(pose, eye, auds)
+            return ("image", image, index)
+        return ("pending", self._render_async(pose, eye, auds), index)
+
+    def _finish(self, handle, loop, video_track):
+        """nerfreal.py:108-127: wait for the frame if it is still in flight, full-body composite, VideoFrame, video queue"""
+        kind, payload, index = handle
+        if kind == "pending":
+            pin, done = payload
+            done.synchronize()
+            image = pin.numpy()                          # VideoFrame.from_ndarray copies (PyAV semantics): the pinned slot is free again
             if getattr(self.opt, "fullbody", False):
                 import cv2
                 image_fullbody = cv2.cvtColor(self.fullbody_list_cycle[index], cv2.COLOR_BGR2RGB)
                 sx, sy = self.opt.fullbody_offset_x, self.opt.fullbody_offset_y
                 image_fullbody[sy:sy + image.shape[0], sx:sx + image.shape[1]] = image
                 image = image_fullbody
+        else:
+            image = payload
         new_frame = VideoFrame.from_ndarray(image, format="rgb24")
         self._emit(video_track._queue.put(new_frame), loop)
 
+    def test_step(self, loop=None, audio_track=None, video_track=None):
+        """nerfreal.py:70-127, one step start to finish (the reference's own granularity)"""
+        self._finish(self._step(loop, audio_track), loop, video_track)
+
     def render(self, quit_event, loop=None, audio_track=None, video_track=None):
-        """nerfreal.py:129-156 (webrtc transport)"""
+        """nerfreal.py:129-156 (webrtc transport).  Same steps in the same order; the video frame of step k is handed to the track while
+        step k + 1 is already on the GPU -- but only while more audio is waiting: with an empty input queue (a live 25 fps session, a
+        closed-loop client) the frame is finished at once, so nothing is ever held back behind the queue's 10 ms time-out."""
         self.init_customindex()
         count, totaltime = 0, 0.0
         self.tts.render(quit_event)
+        pending = None
         while not quit_event.is_set():
             t = time.perf_counter()
             for _ in range(2):
                 self.asr.run_step()
-            self.test_step(loop, audio_track, video_track)
+            handle = self._step(loop, audio_track)
+            if pending is not None:
+                self._finish(pending, loop, video_track)
+            pending = handle
+            if self.asr.queue.empty():
+                self._finish(pending, loop, video_track)
+                pending = None
             totaltime += time.perf_counter() - t
             count += 1
             if count == 100:
@@ -168,3 +210,5 @@ class NeRFReal(BaseReal):
                 count, totaltime = 0, 0.0
             if video_track._queue.qsize() >= 5:
                 time.sleep(0.04 * video_track._queue.qsize() * 0.8)
+        if pending is not None:
+            self._finish(pending, loop, video_track)
