@@ -251,6 +251,9 @@ int mf_wav2vec2_logits(mf_ctx *ctx, const float *audio, int n_samples, float *ou
  * pass over the 630 MB of weights (the model is weight-streaming / launch-latency bound at one window).
  *   audio   : device fp32 [B, n_samples]          out_f32 : device fp32 [B, n_frames, vocab] */
 int mf_wav2vec2_logits_batch(mf_ctx *ctx, const float *audio, int n_samples, int B, float *out_f32, void *stream);
+/* debug tap (no reference counterpart): %globaltimer stamps in ns of one CTA at the 11 phase boundaries of the second transformer layer of
+ * the last fused-stack launch (csrc/w2v_stack.cuh); synchronises the device.  scripts/time_w2v.py prints them. */
+int mf_debug_w2v_phase_ns(mf_ctx *ctx, unsigned long long *out, int n);
 
 /* ------------------------------------------------------------------------------------------
  * Paste-back (lipreal.py:207-214): out[i] = frames[idx_i] with faces[i] resized (cv2.resize, u8,

@@ -88,6 +88,7 @@ def lib():
                                          ctypes.c_int, ctypes.POINTER(c_i32), c_vp, c_vp]
         L.mf_wav2vec2_logits.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp, c_vp]
         L.mf_wav2vec2_logits_batch.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp]
+        L.mf_debug_w2v_phase_ns.argtypes = [c_vp, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
         L.mf_whisper_features.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp]
         L.mf_wav2lip_mel_chunks.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp, ctypes.POINTER(c_i32), ctypes.c_int, c_vp, c_vp]
         L.mf_paste_blend_u8.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int,

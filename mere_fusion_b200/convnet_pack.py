@@ -174,10 +174,11 @@ class ProgramBuilder:
         w = np.asarray(weight, np.float32)
         return self.conv(in_buf, in_coff, out_buf, out_coff, w[:, :, None, None], bias, None, res=res, relu=act, mode=mode)
 
-    def conv1d_same(self, in_buf, in_coff, out_buf, out_coff, weight, bias, left_pad, act=False, res=None, res_after_act=False):
+    def conv1d_same(self, in_buf, in_coff, out_buf, out_coff, weight, bias, left_pad, act=False, res=None, res_after_act=False, par=0):
         """nn.Conv1d over the token axis of [T, 1, C] buffers with `left_pad` zeros in front and as many behind as needed to
         keep T outputs (an even kernel with padding k/2 followed by dropping the last output: HF Wav2Vec2SamePadLayer).
-        weight [Cout, Cin, k]"""
+        weight [Cout, Cin, k].  par (1..255): consecutive ops carrying the same id promise not to touch each other's outputs (the groups
+        of a grouped conv) -- the executor may run them side by side (flags bits 8..15; checked at load)"""
         w = np.asarray(weight, np.float32)
         cout, cin, k = w.shape
         T = self.buffers[in_buf][0]
@@ -187,7 +188,7 @@ class ProgramBuilder:
         scale, shift = bn_fold(bias, None, cout)
         self.flops_per_sample += 2 * cout * cin * k * T
         return self._emit(in_buf, in_coff, cin, out_buf, out_coff, Wm, taps, scale, shift, T, 1, 0, 0, 1, 1, 1, 1, res, act, 0, cout,
-                          flags=int(bool(res_after_act)))
+                          flags=int(bool(res_after_act)) | ((int(par) & 0xff) << 8))
 
     def _misc(self, kind, in_buf, out_buf, **f):
         v = dict(in_coff=0, out_coff=0, res_buf=-1, res_coff=0, Mh=0, Mw=0, ntaps=0, Cin=0, Kpad=0, relu=0, s_id=-1, h_id=-1)

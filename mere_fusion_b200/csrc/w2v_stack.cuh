@@ -36,7 +36,7 @@ struct W2vStackParams {
     __nv_bfloat16 *x_out;         // [M][D] bf16
     float *xres;                  // scratch [M][D] fp32 residual stream
     __nv_bfloat16 *qkv, *ao, *hid;  // scratch [M][3D], [M][D], [M][I]
-    unsigned *barrier;            // zeroed before the launch
+    unsigned *barrier;            // zeroed before the launch; 16 counters, then 16 x u64 phase time stamps of CTA 0 in layer 1 (debug tap)
     int M, T, B, D, I, heads, layers;
     float eps, scale_log2;        // softmax scale * log2(e)
 };
@@ -80,6 +80,13 @@ __device__ __forceinline__ void w2v_grid_barrier(unsigned *ctr, unsigned &gen) {
     __syncthreads();
 }
 
+__device__ __forceinline__ void w2v_stamp(const W2vStackParams &p, int l, int i) {   // %globaltimer at a phase boundary (mf_debug_w2v_phase_ns)
+    if (l == 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long *>(p.barrier + 16)[i] = t;
+    }
+}
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -299,6 +306,7 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
 
     for (int l = 0; l < p.layers; l++) {
         const W2vLayerPtrs w = w2v_layer(p.image, l, D, I);
+        w2v_stamp(p, l, 0);
         // ---- P1: qkv = LN1(x) Wqkv^T + b
         if (ncq) {
             w2v_ln_rows(sm, p.xres, M, Mpad, D, p.eps, w.ln1_g, w.ln1_b);
@@ -307,7 +315,9 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
                            wphase, wslot);
         }
         if (threadIdx.x == 0 && ncd) w2v_issue_w(sm, w.Wo, D, n0d, ncd, wslot);         // P3's weights stream during P2
+        w2v_stamp(p, l, 1);
         w2v_grid_barrier(p.barrier, gen);
+        w2v_stamp(p, l, 2);
         // ---- P2: attention; item = (window, head, group of query rows) so that all CTAs take part (one CTA per head took 30 us)
         {
             const int dh = D / p.heads, T = p.T;
@@ -371,7 +381,9 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
                 __syncthreads();
             }
         }
+        w2v_stamp(p, l, 3);
         w2v_grid_barrier(p.barrier, gen);
+        w2v_stamp(p, l, 4);
         // ---- P3: x += ao Wo^T + b
         if (ncd) {
             w2v_copy_a(sm.A, D + 8, p.ao, M, Mpad, D, 0, D);
@@ -382,7 +394,9 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
                            wphase, wslot);
         }
         if (threadIdx.x == 0 && nci) w2v_issue_w(sm, w.W1, D, n0i, nci, wslot);
+        w2v_stamp(p, l, 5);
         w2v_grid_barrier(p.barrier, gen);
+        w2v_stamp(p, l, 6);
         // ---- P4: hid = gelu(LN2(x) W1^T + b)
         if (nci) {
             w2v_ln_rows(sm, p.xres, M, Mpad, D, p.eps, w.ln2_g, w.ln2_b);
@@ -391,7 +405,9 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
                            wphase, wslot);
         }
         if (threadIdx.x == 0 && ncd) w2v_issue_w(sm, w.W2, I, n0d, ncd, wslot);
+        w2v_stamp(p, l, 7);
         w2v_grid_barrier(p.barrier, gen);
+        w2v_stamp(p, l, 8);
         // ---- P5: x += hid W2^T + b
         if (ncd) {
             if (I <= WS_KA) {
@@ -407,7 +423,9 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
             const W2vLayerPtrs wn = w2v_layer(p.image, l + 1, D, I);
             if (threadIdx.x == 0 && ncq) w2v_issue_w(sm, wn.Wqkv, D, n0q, ncq, wslot);
         }
+        w2v_stamp(p, l, 9);
         w2v_grid_barrier(p.barrier, gen);
+        w2v_stamp(p, l, 10);
     }
     for (size_t i = (size_t)blockIdx.x * WS_THREADS_ + threadIdx.x; i < (size_t)M * D; i += (size_t)gridDim.x * WS_THREADS_)
         p.x_out[i] = __float2bfloat16_rn(__ldcg(p.xres + i));

@@ -387,6 +387,7 @@ struct Launch {
     int op = -1;  // program op index (conv ops: profiling hook), -1 for helper kernels
     size_t ws_bytes = 0;  // k_conv_tma split-K: workspace / counter requirement (patched in by finish_launch_list)
     int ws_counters = 0;
+    int par = 0;          // != 0: consecutive launches with the same id are independent (W2LOp.flags bits 8..15) and may run side by side
     std::vector<unsigned char> params;
     template <class T>
     void set(const T &p) { params.assign((const unsigned char *)&p, (const unsigned char *)&p + sizeof(T)); }
@@ -450,6 +451,8 @@ struct Wav2LipState {
     bool use_graph = true;
     bool use_pdl = true;
     cudaStream_t capture_stream = nullptr;
+    std::vector<cudaStream_t> par_streams;   // fork-join branches of independent launches inside the captured graph
+    std::vector<cudaEvent_t> par_events;     // [0] fork, [1 + j] end of branch j
     // Whisper program (hdr.mel_w == -2): log-mel scratch, embedding buffers to gather, filterbank
     float *wh_logspec = nullptr;
     int *wh_maxslot = nullptr;
@@ -495,6 +498,8 @@ void wav2lip_destroy(mf_ctx *ctx) {
     }
     delete s->entry_table;
     if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
+    for (auto st : s->par_streams) cudaStreamDestroy(st);
+    for (auto ev : s->par_events) cudaEventDestroy(ev);
     for (auto b : s->gn_fused_buf) cudaFree(b);
     cudaFree(s->dbg_ws);
     cudaFree(s->dbg_counters);
@@ -601,7 +606,8 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
                 MF_CUDA(ctx, cudaMalloc(&s->w2v_qkv, M * 3 * D * 2));
                 MF_CUDA(ctx, cudaMalloc(&s->w2v_ao, M * D * 2));
                 MF_CUDA(ctx, cudaMalloc(&s->w2v_hid, M * I * 2));
-                MF_CUDA(ctx, cudaMalloc(&s->w2v_barrier, 64));
+                MF_CUDA(ctx, cudaMalloc(&s->w2v_barrier, 64 + 16 * 8));
+                MF_CUDA(ctx, cudaMemset(s->w2v_barrier, 0, 64 + 16 * 8));
                 s->w2v_image = base + we->offset;
                 MF_CUDA(ctx, cudaFuncSetAttribute(k_w2v_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(W2vSmem)));
                 continue;
@@ -636,6 +642,20 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
         MF_REQUIRE(ctx, o.ntaps >= 1 && o.ntaps <= CONV_MAX_TAPS && o.Cin % 8 == 0 && o.Kpad % CONV_BK == 0 &&
                             o.Kpad >= o.ntaps * o.Cin && o.Cout_pad % o.BN == 0 && o.Cout <= o.Cout_pad && o.ups >= 0 && o.ups <= 2,
                    "op %d: bad geometry", i);
+        if (const int par = (o.flags >> 8) & 0xff) {
+            // the packer's promise for a run of independent ops, checked: this op's output channels are touched by no other op of the run
+            MF_REQUIRE(ctx, o.mode == 0, "op %d: an output-head op cannot be part of an independent run", i);
+            for (int j = i - 1; j >= 0 && s->ops[j].kind == 0 && ((s->ops[j].flags >> 8) & 0xff) == par; j--) {
+                const W2LOp &q = s->ops[j];
+                auto overlap = [](int b0, int c0, int n0, int b1, int c1, int n1) { return b0 == b1 && b0 >= 0 && c0 < c1 + n1 && c1 < c0 + n0; };
+                const bool bad = overlap(o.out_buf, o.out_coff, o.Cout, q.out_buf, q.out_coff, q.Cout) ||
+                                 overlap(o.out_buf, o.out_coff, o.Cout, q.in_buf, q.in_coff, q.Cin) ||
+                                 overlap(o.out_buf, o.out_coff, o.Cout, q.res_buf, q.res_coff, q.Cout) ||
+                                 overlap(q.out_buf, q.out_coff, q.Cout, o.in_buf, o.in_coff, o.Cin) ||
+                                 overlap(q.out_buf, q.out_coff, q.Cout, o.res_buf, o.res_coff, o.Cout);
+                MF_REQUIRE(ctx, !bad, "ops %d and %d are tagged independent (par %d) but touch each other's output channels", j, i, par);
+            }
+        }
         const mf_blob_entry *we = find(o.w_entry), *se = find(o.scale_entry), *he = find(o.shift_entry);
         MF_REQUIRE(ctx, we && se && he && we->nbytes == (size_t)o.Cout_pad * o.Kpad * 2 &&
                             se->nbytes == (size_t)o.Cout_pad * 4 && he->nbytes == (size_t)o.Cout_pad * 4,
@@ -944,9 +964,24 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
 
 // allocate (or grow) the split-K workspace for a finished launch list and patch it into the k_conv_tma launches
 static int finish_launch_list(mf_ctx *ctx, std::vector<Launch> &L, float **ws, unsigned **counters, size_t *ws_bytes, int *n_counters) {
+    // launches run one after the other and share the workspace from offset 0 -- except inside a run of independent launches (par),
+    // which may execute concurrently: there every launch gets its own region
     size_t need = 0;
     int nc = 0;
-    for (auto &l : L) { need = std::max(need, l.ws_bytes); nc = std::max(nc, l.ws_counters); }
+    std::vector<size_t> ws_off(L.size(), 0);
+    std::vector<int> c_off(L.size(), 0);
+    for (size_t a = 0; a < L.size();) {
+        size_t b = a + 1;
+        while (L[a].par != 0 && b < L.size() && L[b].par == L[a].par) b++;
+        size_t w = 0;
+        int c = 0;
+        for (size_t j = a; j < b; j++) {
+            ws_off[j] = w; c_off[j] = c;
+            w += (L[j].ws_bytes + 255) / 256 * 256; c += L[j].ws_counters;
+        }
+        need = std::max(need, w); nc = std::max(nc, c);
+        a = b;
+    }
     if (need > *ws_bytes) {
         MF_CUDA(ctx, cudaDeviceSynchronize());
         cudaFree(*ws);
@@ -962,13 +997,25 @@ static int finish_launch_list(mf_ctx *ctx, std::vector<Launch> &L, float **ws, u
         MF_CUDA(ctx, cudaMemset(*counters, 0, (size_t)nc * sizeof(unsigned)));
         *n_counters = nc;
     }
-    for (auto &l : L)
-        if (is_conv_tma(l.func)) { l.as<ConvTmaParams>().ws = *ws; l.as<ConvTmaParams>().counters = *counters; }
+    for (size_t j = 0; j < L.size(); j++)
+        if (is_conv_tma(L[j].func)) {
+            L[j].as<ConvTmaParams>().ws = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(*ws) + ws_off[j]);
+            L[j].as<ConvTmaParams>().counters = *counters + c_off[j];
+        }
     return MF_OK;
 }
 
 // ---- launch list -----------------------------------------------------------------------------------
+static int add_op_launches_(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<Launch> &L);
 static int add_op_launches(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<Launch> &L) {
+    const size_t n0 = L.size();
+    const int rc = add_op_launches_(ctx, s, i, B, L);
+    const int par = (s->ops[i].flags >> 8) & 0xff;
+    // an op that expands to ONE launch keeps its independence tag; multi-launch ops run in order
+    if (rc == MF_OK && par && L.size() == n0 + 1) L[n0].par = par;
+    return rc;
+}
+static int add_op_launches_(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<Launch> &L) {
     const W2LOp &o = s->ops[i];
     if (conv_tma_eligible(o)) return add_conv_tma(ctx, s, i, B, L);
     if (o.kind == 0) {
@@ -1215,39 +1262,72 @@ static void patch_io(Wav2LipState::Plan *pl, const void *in0, const void *in1, v
     pl->in0 = in0; pl->in1 = in1; pl->out_u8 = out_u8; pl->out_f32 = out_f32;
 }
 
-static int launch_direct(mf_ctx *ctx, Wav2LipState *s, std::vector<Launch> &L, cudaStream_t st, bool pdl = false) {
-    bool started = false, first = true;
-    for (auto &l : L) {
-        // profiling: events around ALL launches of the profiled op (an op may expand to several kernels)
-        const bool prof = s->profile && l.op >= 0 && l.op == s->profile_op;
-        if (prof && !started) { cudaEventRecord(s->ev[0], st); started = true; }
-        void *args[] = {l.params.data()};
-        if ((pdl && !first) || l.cluster > 1) {
-            // programmatic dependent launch: this kernel's CTA-local prologue may overlap the predecessor's tail; every executor
-            // kernel calls griddepcontrol.wait before its first global access.  CTA pairs are launched as clusters of 2.
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof(cfg));
-            cfg.gridDim = l.grid; cfg.blockDim = l.block; cfg.dynamicSmemBytes = (size_t)l.smem; cfg.stream = st;
-            cudaLaunchAttribute at[2];
-            memset(at, 0, sizeof(at));
-            int na = 0;
-            if (pdl && !first) {
-                at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                at[na].val.programmaticStreamSerializationAllowed = 1;
-                na++;
-            }
-            if (l.cluster > 1) {
-                at[na].id = cudaLaunchAttributeClusterDimension;
-                at[na].val.clusterDim.x = (unsigned)l.cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
-                na++;
-            }
-            cfg.attrs = at; cfg.numAttrs = (unsigned)na;
-            MF_CUDA(ctx, cudaLaunchKernelExC(&cfg, l.func, args));
-        } else {
-            MF_CUDA(ctx, cudaLaunchKernel(l.func, l.grid, l.block, args, l.smem, st));
+#define MF_PAR_BRANCHES 16
+static int launch_one(mf_ctx *ctx, Launch &l, cudaStream_t st, bool pdl_attr) {
+    void *args[] = {l.params.data()};
+    if (pdl_attr || l.cluster > 1) {
+        // programmatic dependent launch: this kernel's CTA-local prologue may overlap the predecessor's tail; every executor
+        // kernel calls griddepcontrol.wait before its first global access.  CTA pairs are launched as clusters of 2.
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = l.grid; cfg.blockDim = l.block; cfg.dynamicSmemBytes = (size_t)l.smem; cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        memset(at, 0, sizeof(at));
+        int na = 0;
+        if (pdl_attr) {
+            at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[na].val.programmaticStreamSerializationAllowed = 1;
+            na++;
         }
-        first = false;
-        if (prof) cudaEventRecord(s->ev[1], st);
+        if (l.cluster > 1) {
+            at[na].id = cudaLaunchAttributeClusterDimension;
+            at[na].val.clusterDim.x = (unsigned)l.cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+            na++;
+        }
+        cfg.attrs = at; cfg.numAttrs = (unsigned)na;
+        MF_CUDA(ctx, cudaLaunchKernelExC(&cfg, l.func, args));
+    } else {
+        MF_CUDA(ctx, cudaLaunchKernel(l.func, l.grid, l.block, args, l.smem, st));
+    }
+    return MF_OK;
+}
+
+// `capturing`: st is a capturing stream (the graph path).  Runs of independent launches (Launch::par) then become a fork-join of up to
+// MF_PAR_BRANCHES branches (the 16 groups of wav2vec2's positional conv: 16 launches of 16 CTAs each, 22 us apiece one after the other);
+// launched directly they simply run in order.
+static int launch_direct(mf_ctx *ctx, Wav2LipState *s, std::vector<Launch> &L, cudaStream_t st, bool pdl = false, bool capturing = false) {
+    bool started = false, first = true;
+    for (size_t a = 0; a < L.size();) {
+        size_t b = a + 1;
+        while (L[a].par != 0 && b < L.size() && L[b].par == L[a].par) b++;
+        if (capturing && b - a >= 2) {
+            MF_REQUIRE(ctx, !s->par_streams.empty(), "fork-join streams were not created before the capture");
+            const int nb = (int)std::min<size_t>(MF_PAR_BRANCHES, b - a);
+            MF_CUDA(ctx, cudaEventRecord(s->par_events[0], st));
+            for (int j = 0; j < nb; j++) MF_CUDA(ctx, cudaStreamWaitEvent(s->par_streams[j], s->par_events[0], 0));
+            for (size_t j = a; j < b; j++) {
+                const int rc = launch_one(ctx, L[j], s->par_streams[(j - a) % nb], false);
+                if (rc) return rc;
+            }
+            for (int j = 0; j < nb; j++) {
+                MF_CUDA(ctx, cudaEventRecord(s->par_events[1 + j], s->par_streams[j]));
+                MF_CUDA(ctx, cudaStreamWaitEvent(st, s->par_events[1 + j], 0));
+            }
+            first = true;   // the launch after the join has several predecessors: a plain (fully serialised) launch
+            a = b;
+            continue;
+        }
+        for (size_t j = a; j < b; j++) {
+            Launch &l = L[j];
+            // profiling: events around ALL launches of the profiled op (an op may expand to several kernels)
+            const bool prof = s->profile && l.op >= 0 && l.op == s->profile_op;
+            if (prof && !started) { cudaEventRecord(s->ev[0], st); started = true; }
+            const int rc = launch_one(ctx, l, st, pdl && !first);
+            if (rc) return rc;
+            first = false;
+            if (prof) cudaEventRecord(s->ev[1], st);
+        }
+        a = b;
     }
     return MF_OK;
 }
@@ -1278,8 +1358,18 @@ static int forward_common(mf_ctx *ctx, Wav2LipState *s, const void *in0, const v
         if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
         if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
         if (!s->capture_stream) MF_CUDA(ctx, cudaStreamCreateWithFlags(&s->capture_stream, cudaStreamNonBlocking));
+        if (s->par_streams.empty()) {   // created outside the capture
+            bool any = false;
+            for (auto &l : pl->launches) any = any || l.par != 0;
+            if (any) {
+                s->par_streams.resize(MF_PAR_BRANCHES);
+                s->par_events.resize(MF_PAR_BRANCHES + 1);
+                for (auto &x : s->par_streams) MF_CUDA(ctx, cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+                for (auto &e : s->par_events) MF_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
+        }
         MF_CUDA(ctx, cudaStreamBeginCapture(s->capture_stream, cudaStreamCaptureModeThreadLocal));
-        int rc = launch_direct(ctx, s, pl->launches, s->capture_stream, s->use_pdl);
+        int rc = launch_direct(ctx, s, pl->launches, s->capture_stream, s->use_pdl, true);
         cudaError_t ce = cudaStreamEndCapture(s->capture_stream, &pl->graph);
         if (rc) { if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; } return rc; }
         MF_CUDA(ctx, ce);
@@ -1340,6 +1430,19 @@ extern "C" int mf_wav2vec2_logits_batch(mf_ctx *ctx, const float *audio, int n_s
                n_samples);
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     return forward_common(ctx, s, audio, nullptr, nullptr, out_f32, B, (cudaStream_t)stream);
+}
+
+// debug tap: %globaltimer stamps (ns) of CTA 0 at the phase boundaries of layer 1 of the last k_w2v_stack launch
+// [P1 start, P1 end, P2 start, P2 end, P3 start, P3 end, P4 start, P4 end, P5 start, P5 end, next layer's start]; synchronises the device
+extern "C" int mf_debug_w2v_phase_ns(mf_ctx *ctx, unsigned long long *out, int n) {
+    if (!ctx) return MF_E_INVALID;
+    Wav2LipState *s = ctx->wav2lip;
+    if (!s || !s->w2v_barrier) return mf_fail(ctx, MF_E_STATE, "mf_debug_w2v_phase_ns: no fused transformer stack loaded");
+    MF_REQUIRE(ctx, out && n >= 1 && n <= 16, "mf_debug_w2v_phase_ns: bad arguments");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    MF_CUDA(ctx, cudaDeviceSynchronize());
+    MF_CUDA(ctx, cudaMemcpy(out, s->w2v_barrier + 16, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return MF_OK;
 }
 
 extern "C" int mf_wav2vec2_logits(mf_ctx *ctx, const float *audio, int n_samples, float *out_f32, void *stream) {

@@ -26,27 +26,34 @@ class Wav2Vec2Engine(ConvNet):
         self._pin = torch.empty(n_samples, dtype=torch.float32).pin_memory()
         self._dev = torch.empty(n_samples, dtype=torch.float32, device=self.device)
         self._h2d_done = None
+        # the executor replays a CUDA graph that is re-captured whenever the caller's pointers change: without an `out` the program
+        # writes into this fixed buffer and the caller gets a copy (one tiny D2D kernel instead of a capture + instantiate per window)
+        self._out = torch.empty((max_batch, self.n_frames, self.vocab), dtype=torch.float32, device=self.device)
 
     def logits(self, audio, out=None, stream=None):
         """audio: cuda fp32 [n_samples] -> cuda fp32 [n_frames, vocab]"""
         assert audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous() and audio.numel() == self.n_samples
-        if out is None:
-            out = torch.empty((self.n_frames, self.vocab), dtype=torch.float32, device=self.device)
+        dst = out if out is not None else self._out[0]
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
-        check(self.ctx.handle, lib().mf_wav2vec2_logits(self.ctx.handle, _ptr(audio), self.n_samples, _ptr(out), ctypes.c_void_p(s.cuda_stream)),
+        check(self.ctx.handle, lib().mf_wav2vec2_logits(self.ctx.handle, _ptr(audio), self.n_samples, _ptr(dst), ctypes.c_void_p(s.cuda_stream)),
               "mf_wav2vec2_logits")
-        return out
+        if out is not None:
+            return out
+        with torch.cuda.stream(s):
+            return dst.clone()
 
     def logits_batch(self, audio, out=None, stream=None):
         """audio: cuda fp32 [B, n_samples] (B <= max_batch) -> cuda fp32 [B, n_frames, vocab]"""
         assert audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous() and audio.dim() == 2 and audio.shape[1] == self.n_samples
         B = int(audio.shape[0])
-        if out is None:
-            out = torch.empty((B, self.n_frames, self.vocab), dtype=torch.float32, device=self.device)
+        dst = out if out is not None else self._out[:B]
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
-        check(self.ctx.handle, lib().mf_wav2vec2_logits_batch(self.ctx.handle, _ptr(audio), self.n_samples, B, _ptr(out),
+        check(self.ctx.handle, lib().mf_wav2vec2_logits_batch(self.ctx.handle, _ptr(audio), self.n_samples, B, _ptr(dst),
                                                               ctypes.c_void_p(s.cuda_stream)), "mf_wav2vec2_logits_batch")
-        return out
+        if out is not None:
+            return out
+        with torch.cuda.stream(s):
+            return dst.clone()
 
     def feature_fn(self, frame):
         """NerfASR's `feature_fn(float32[n_samples]) -> [T, audio_dim]` (device tensor)"""
