@@ -22,13 +22,14 @@
 
 #define WS_G 128          /* CTAs; output-column slices are multiples of 8 */
 #define WS_THREADS_ 256
-#define WS_KC 256         /* K chunk (elements) of the A ring used when K > WS_KA */
+#define WS_KC 512         /* K chunk (elements) of the A ring used when K > WS_KA (256: 16 sync points per FFN2 phase, 13.7 us) */
 #define WS_KS (WS_KC + 8) /* padded chunk row stride in smem (bank-conflict-free ldmatrix) */
 #define WS_KA 1024        /* largest K whose A operand is resident as a whole */
-#define WS_STAGES 6       /* A ring depth (chunks of WS_KC): 3 stages in sm.A, 3 in the weight buffer that is idle during the phase */
+#define WS_STAGES 4       /* A ring depth (chunks of WS_KC): 2 stages in sm.A, 2 in the weight buffer that is idle during the phase */
+#define WS_RING_PAD 256   /* halfs added to sm.A and each weight buffer so that two ring stages (32 x (WS_KC + 8)) fit */
 #define WS_MAX_NC 32      /* output columns per CTA and phase */
 #define WS_MAX_MT 2       /* 16-row tiles of tokens: one window (<= 32 frames); batched windows use the op-by-op program */
-#define WS_WBUF_HALFS (WS_MAX_NC * (WS_KA + 8))   /* one weight slice: nc rows x (K + 8), nc * K <= 32 * 1024 */
+#define WS_WBUF_HALFS (WS_MAX_NC * (WS_KA + 8) + WS_RING_PAD)   /* one weight slice: nc rows x (K + 8), nc * K <= 32 * 1024 */
 
 struct W2vStackParams {
     const unsigned char *image;   // packed weights (layout below)
@@ -36,12 +37,13 @@ struct W2vStackParams {
     __nv_bfloat16 *x_out;         // [M][D] bf16
     float *xres;                  // scratch [M][D] fp32 residual stream
     __nv_bfloat16 *qkv, *ao, *hid;  // scratch [M][3D], [M][D], [M][I]
-    unsigned *barrier;            // zeroed before the launch; 16 counters, then 16 x u64 phase time stamps of CTA 0 in layer 1 (debug tap)
+    unsigned *barrier;            // zeroed before the launch; 16 counters, then 24 x u64 phase time stamps of CTA 0 in layer 1 (debug tap)
     int M, T, B, D, I, heads, layers;
     float eps, scale_log2;        // softmax scale * log2(e)
 };
 
-// image layout per layer (bytes): vectors fp32 [ln1_g D | ln1_b D | bqkv 3D | bo D | ln2_g D | ln2_b D | b1 I | b2 D], then matrices bf16
+// image layout per layer (bytes): vectors fp32 [ln1_g D | ln1_b D | bqkv 3D | bo D | ln2_g D | ln2_b D | b1 I | b2 D] (the LayerNorm
+// affines are folded into Wqkv / bqkv and W1 / b1 by the packer; their slots hold 1 / 0 and are not read), then matrices bf16
 // row-major [Wqkv 3D x D | Wo D x D | W1 I x D | W2 D x I]
 struct W2vLayerPtrs {
     const float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *b1, *b2;
@@ -61,20 +63,31 @@ __device__ __forceinline__ W2vLayerPtrs w2v_layer(const unsigned char *image, in
 
 struct W2vSmem {
     alignas(16) __nv_bfloat16 W[2][WS_WBUF_HALFS];                // this phase's weight slice (whole K) / the next phase's, in flight
-    alignas(16) __nv_bfloat16 A[WS_MAX_MT * 16 * (WS_KA + 8)];    // A operand: whole (K <= WS_KA) or a WS_STAGES ring of WS_KC chunks
+    alignas(16) __nv_bfloat16 A[WS_MAX_MT * 16 * (WS_KA + 8) + WS_RING_PAD];    // A operand: whole (K <= WS_KA) or a WS_STAGES ring of WS_KC chunks
     float red[8][32][8];                                          // split-K partials: [warp][lane][c]
     float mean[WS_MAX_MT * 16], rstd[WS_MAX_MT * 16];
     alignas(8) uint64_t wbar[2];
 };
 
+// Software grid barrier.  Arrivals are spread over 16 counters (CTA b -> counter b & 15): atomics on ONE address serialise in L2 at ~27
+// cycles each, i.e. ~1.8 us for 128 CTAs -- most of what a barrier cost; 8 per counter take 0.1 us.  Warp 0 polls: lane i watches counter i.
+#define WS_BAR_CTRS 16
 __device__ __forceinline__ void w2v_grid_barrier(unsigned *ctr, unsigned &gen) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        gen++;
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        const unsigned target = gen * gridDim.x;
-        while (*reinterpret_cast<volatile unsigned *>(ctr) < target) __nanosleep(40);
+    gen++;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        if (lane == 0) {
+            __threadfence();
+            atomicAdd(ctr + (blockIdx.x & (WS_BAR_CTRS - 1)), 1u);
+        }
+        // CTAs that share counter i: b = i, i + 16, ... < gridDim.x
+        const unsigned per = lane < WS_BAR_CTRS ? (gridDim.x - lane + WS_BAR_CTRS - 1) / WS_BAR_CTRS : 0u;
+        const unsigned target = gen * per;
+        bool ok;
+        do {
+            ok = lane >= WS_BAR_CTRS || per == 0u || *reinterpret_cast<volatile unsigned *>(ctr + lane) >= target;
+        } while (!__all_sync(0xffffffffu, ok));
         __threadfence();
     }
     __syncthreads();
@@ -107,64 +120,77 @@ template <int N>
 __device__ __forceinline__ void w2v_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // A operand builders: rows 0..Mpad-1 of sm.A with row stride `ks` halfs ------------------------------------------------------
-// LayerNorm of the fp32 residual rows -> bf16 A operand (row stride D + 8).  A warp owns rows warp, warp + 8, ...; the loads of ALL
-// its rows are issued before the first use (one exposed L2 latency per phase instead of one per row: the first version walked every
-// row with dependent loads, 25 us per phase), gamma / beta are staged in shared memory once; two-pass statistics like
-// torch.nn.functional.layer_norm.  D <= 1024, M <= 32.
-__device__ __forceinline__ void w2v_ln_rows(W2vSmem &sm, const float *xres, int M, int Mpad, int D, float eps, const float *g, const float *b) {
+// LayerNorm of the fp32 residual rows -> bf16 A operand (row stride D + 8).  Every CTA needs ALL rows; computing them in every CTA was
+// 6.0 us of the 9.3 us LN1+QKV phase (128-fold redundant: 110 KB of fp32 rows through each SM's L1, ~270 instructions per row and lane).
+// The CTAs of a thread-block cluster share the work instead: CTA rank r normalises rows r, r + csize, ... (one warp per row, the row in
+// registers, two-pass statistics like torch.nn.functional.layer_norm) and stores the bf16 row into the shared memory of EVERY CTA of the
+// cluster (st.shared::cluster through mapa), then the cluster synchronises.  csize = 1 degenerates to every CTA doing every row.
+// Safe against the neighbours' use of sm.A: every CTA of the grid has passed the grid barrier that precedes an LN phase, i.e. has finished
+// the previous phase's reads of its sm.A, before any CTA gets here; nobody writes sm.A remotely outside an LN phase.  D <= 1024, M <= 32.
+__device__ __forceinline__ uint32_t w2v_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t w2v_cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void w2v_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void w2v_st_cluster_v4(uint32_t local_saddr, uint32_t rank, const uint32_t (&w)[4]) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_saddr), "r"(rank));
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+// The affine part (gamma, beta) is folded into the following linear layer at pack time (wav2vec2_pack.py): the phase starts with the
+// loads of x instead of a round trip to HBM for two vectors.
+__device__ __forceinline__ void w2v_ln_rows(W2vSmem &sm, const float *xres, int M, int Mpad, int D, float eps, const W2vStackParams &dbg_p, int dbg_l = -1) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ks = D + 8;
-    constexpr int NV = WS_KA / 128, NR = WS_MAX_MT * 16 / (WS_THREADS_ / 32);   // float4 per lane and row; rows per warp
-    float *gs = reinterpret_cast<float *>(sm.red), *bs = gs + WS_KA;             // 8 KB: the split-K scratch is free here
-    for (int c = threadIdx.x * 4; c < D; c += WS_THREADS_ * 4) {
-        *reinterpret_cast<float4 *>(gs + c) = __ldg(reinterpret_cast<const float4 *>(g + c));
-        *reinterpret_cast<float4 *>(bs + c) = __ldg(reinterpret_cast<const float4 *>(b + c));
+    constexpr int NV = WS_KA / 128;                                              // float4 per lane and row
+    const int crank = (int)w2v_cluster_rank(), csize = (int)w2v_cluster_size();
+    // the zero rows M .. Mpad-1 of this CTA's own operand
+    for (int i = threadIdx.x; i < (Mpad - M) * (D / 4); i += WS_THREADS_) {
+        const int m = M + i / (D / 4), c = (i - (i / (D / 4)) * (D / 4)) * 4;
+        *reinterpret_cast<uint2 *>(sm.A + (size_t)m * ks + c) = make_uint2(0u, 0u);
     }
-    float4 v[NR][NV];
+    // a lane owns 8 consecutive columns per 256-column group: two float4 loads, one 16-byte remote store per destination CTA
+    for (int m = crank + csize * warp; m < M; m += csize * (WS_THREADS_ / 32)) {
+        float4 v[NV];
 #pragma unroll
-    for (int r = 0; r < NR; r++) {
-        const int m = warp + r * (WS_THREADS_ / 32);
-#pragma unroll
-        for (int i = 0; i < NV; i++)
-            v[r][i] = (m < M && lane * 4 + i * 128 < D) ? __ldcg(reinterpret_cast<const float4 *>(xres + (size_t)m * D + lane * 4 + i * 128))
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);     // written by other CTAs: not through L1
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < NR; r++) {
-        const int m = warp + r * (WS_THREADS_ / 32);
-        if (m >= Mpad) continue;
-        __nv_bfloat16 *dst = sm.A + (size_t)m * ks;
-        if (m >= M) {
-            for (int c = lane * 4; c < D; c += 128) *reinterpret_cast<uint2 *>(dst + c) = make_uint2(0u, 0u);
-            continue;
+        for (int i = 0; i < NV; i++) {
+            const int c = lane * 8 + (i >> 1) * 256 + (i & 1) * 4;
+            v[i] = c < D ? __ldcg(reinterpret_cast<const float4 *>(xres + (size_t)m * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);   // written by other CTAs: not through L1
         }
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < NV; i++) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+        for (int i = 0; i < NV; i++) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (dbg_l >= 0) w2v_stamp(dbg_p, dbg_l, 16);
         const float mean = s / (float)D;
         float q = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; i++)
-            if (lane * 4 + i * 128 < D) {
-                const float a0 = v[r][i].x - mean, a1 = v[r][i].y - mean, a2 = v[r][i].z - mean, a3 = v[r][i].w - mean;
+            if (lane * 8 + (i >> 1) * 256 + (i & 1) * 4 < D) {
+                const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
                 q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
             }
 #pragma unroll
         for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         const float rs = rsqrtf(q / (float)D + eps);
+        const uint32_t row_saddr = smem_u32(sm.A + (size_t)m * ks);
 #pragma unroll
-        for (int i = 0; i < NV; i++) {
-            const int c = lane * 4 + i * 128;
+        for (int i = 0; i < NV; i += 2) {
+            const int c = lane * 8 + (i >> 1) * 256;
             if (c < D) {
-                const float4 gg = *reinterpret_cast<const float4 *>(gs + c), bb = *reinterpret_cast<const float4 *>(bs + c);
-                __nv_bfloat162 h0 = __floats2bfloat162_rn((v[r][i].x - mean) * rs * gg.x + bb.x, (v[r][i].y - mean) * rs * gg.y + bb.y);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn((v[r][i].z - mean) * rs * gg.z + bb.z, (v[r][i].w - mean) * rs * gg.w + bb.w);
-                *reinterpret_cast<uint2 *>(dst + c) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                uint32_t w[4];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn((v[i + h].x - mean) * rs, (v[i + h].y - mean) * rs);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn((v[i + h].z - mean) * rs, (v[i + h].w - mean) * rs);
+                    w[2 * h] = *reinterpret_cast<uint32_t *>(&h0); w[2 * h + 1] = *reinterpret_cast<uint32_t *>(&h1);
+                }
+                for (int d = 0; d < csize; d++) w2v_st_cluster_v4(row_saddr + (uint32_t)c * 2u, (uint32_t)d, w);
             }
         }
     }
+    if (dbg_l >= 0) w2v_stamp(dbg_p, dbg_l, 17);
+    w2v_cluster_sync();                                    // every CTA's rows have landed in every CTA's operand
 }
 // columns [k0, k0 + kn) of bf16 activations [M][ld] -> rows of `dst` (stride ks) by cp.async (global -> shared, no registers)
 __device__ __forceinline__ void w2v_copy_a(__nv_bfloat16 *dst, int ks, const __nv_bfloat16 *src, int M, int Mpad, int ld, int k0, int kn) {
@@ -182,7 +208,7 @@ __device__ __forceinline__ void w2v_copy_a(__nv_bfloat16 *dst, int ks, const __n
 // the partials are added in warp order through shared memory.
 template <class Epi>
 __device__ __forceinline__ void w2v_phase_gemm(W2vSmem &sm, int K, int nc, int M, const __nv_bfloat16 *a_src, Epi epi, uint32_t (&wphase)[2],
-                                               int &wslot) {
+                                               int &wslot, const W2vStackParams &dbg_p, int dbg_l = -1, int dbg_i = 0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = (M + 15) / 16, Mpad = mt * 16, nt = nc / 8, pairs = mt * nt;
     const int ksplit = pairs >= 8 ? 1 : (8 / pairs >= 4 ? 4 : (8 / pairs >= 2 ? 2 : 1));
@@ -198,6 +224,7 @@ __device__ __forceinline__ void w2v_phase_gemm(W2vSmem &sm, int K, int nc, int M
     if (K <= WS_KA) {
         __syncthreads();                           // the caller's A is complete
         mbar_wait(&sm.wbar[wslot], wphase[wslot]);
+        if (dbg_l >= 0) w2v_stamp(dbg_p, dbg_l, dbg_i);
         const int ksteps = K / 16, kper = ksteps / ksplit, aks = K + 8;
         if (active)
 #pragma unroll 4
@@ -210,13 +237,15 @@ __device__ __forceinline__ void w2v_phase_gemm(W2vSmem &sm, int K, int nc, int M
     } else {
         const int nchunks = K / WS_KC;
         __nv_bfloat16 *idle = sm.W[wslot ^ 1];     // the next phase's weights are issued only after this call returns
-        auto stage = [&](int c) { const int st = c % WS_STAGES; return st < 3 ? sm.A + (size_t)st * Mpad * WS_KS : idle + (size_t)(st - 3) * Mpad * WS_KS; };
+        auto stage = [&](int c) { const int st = c % WS_STAGES; return st < WS_STAGES / 2 ? sm.A + (size_t)st * Mpad * WS_KS : idle + (size_t)(st - WS_STAGES / 2) * Mpad * WS_KS; };
+        static_assert((WS_STAGES / 2) * WS_MAX_MT * 16 * WS_KS <= WS_MAX_MT * 16 * (WS_KA + 8) + WS_RING_PAD && (WS_STAGES / 2) * WS_MAX_MT * 16 * WS_KS <= WS_WBUF_HALFS, "ring stages do not fit");
         __syncthreads();                           // everyone is done with sm.A of the phase before
         for (int c = 0; c < WS_STAGES - 1 && c < nchunks; c++) {
             w2v_copy_a(stage(c), WS_KS, a_src, M, Mpad, K, c * WS_KC, WS_KC);
             w2v_cp_commit();
         }
         mbar_wait(&sm.wbar[wslot], wphase[wslot]);
+        if (dbg_l >= 0) w2v_stamp(dbg_p, dbg_l, dbg_i);
         for (int kc = 0; kc < nchunks; kc++) {
             if (kc + WS_STAGES - 1 < nchunks) w2v_cp_wait<WS_STAGES - 2>(); else w2v_cp_wait<0>();
             __syncthreads();                       // chunk kc has landed for everyone; the stage refilled below was consumed in kc - 1
@@ -238,6 +267,7 @@ __device__ __forceinline__ void w2v_phase_gemm(W2vSmem &sm, int K, int nc, int M
     }
     wphase[wslot] ^= 1u;
     wslot ^= 1;
+    if (dbg_l >= 0) { __syncthreads(); w2v_stamp(dbg_p, dbg_l, dbg_i + 1); }
     // split-K reduction in warp order, then the epilogue by the kpart == 0 warps
     if (ksplit > 1) {
         if (active && kpart > 0) {
@@ -308,11 +338,12 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
         const W2vLayerPtrs w = w2v_layer(p.image, l, D, I);
         w2v_stamp(p, l, 0);
         // ---- P1: qkv = LN1(x) Wqkv^T + b
+        w2v_ln_rows(sm, p.xres, M, Mpad, D, p.eps, p, l);   // every CTA: the rows are shared inside the cluster
+        w2v_stamp(p, l, 15);
         if (ncq) {
-            w2v_ln_rows(sm, p.xres, M, Mpad, D, p.eps, w.ln1_g, w.ln1_b);
             w2v_phase_gemm(sm, D, ncq, M, nullptr,
                            [&](int m, int n, float v) { p.qkv[(size_t)m * 3 * D + n0q + n] = __float2bfloat16_rn(v + __ldg(w.bqkv + n0q + n)); },
-                           wphase, wslot);
+                           wphase, wslot, p, l, 11);
         }
         if (threadIdx.x == 0 && ncd) w2v_issue_w(sm, w.Wo, D, n0d, ncd, wslot);         // P3's weights stream during P2
         w2v_stamp(p, l, 1);
@@ -391,18 +422,18 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
             w2v_cp_wait<0>();
             w2v_phase_gemm(sm, D, ncd, M, nullptr,
                            [&](int m, int n, float v) { float *x = p.xres + (size_t)m * D + n0d + n; *x = __ldcg(x) + (v + __ldg(w.bo + n0d + n)); },
-                           wphase, wslot);
+                           wphase, wslot, p);
         }
         if (threadIdx.x == 0 && nci) w2v_issue_w(sm, w.W1, D, n0i, nci, wslot);
         w2v_stamp(p, l, 5);
         w2v_grid_barrier(p.barrier, gen);
         w2v_stamp(p, l, 6);
         // ---- P4: hid = gelu(LN2(x) W1^T + b)
+        w2v_ln_rows(sm, p.xres, M, Mpad, D, p.eps, p);
         if (nci) {
-            w2v_ln_rows(sm, p.xres, M, Mpad, D, p.eps, w.ln2_g, w.ln2_b);
             w2v_phase_gemm(sm, D, nci, M, nullptr,
                            [&](int m, int n, float v) { p.hid[(size_t)m * I + n0i + n] = __float2bfloat16_rn(w2v_gelu(v + __ldg(w.b1 + n0i + n))); },
-                           wphase, wslot);
+                           wphase, wslot, p);
         }
         if (threadIdx.x == 0 && ncd) w2v_issue_w(sm, w.W2, I, n0d, ncd, wslot);
         w2v_stamp(p, l, 7);
@@ -417,7 +448,7 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
             }
             w2v_phase_gemm(sm, I, ncd, M, p.hid,
                            [&](int m, int n, float v) { float *x = p.xres + (size_t)m * D + n0d + n; *x = __ldcg(x) + (v + __ldg(w.b2 + n0d + n)); },
-                           wphase, wslot);
+                           wphase, wslot, p, l, 13);
         }
         if (l + 1 < p.layers) {
             const W2vLayerPtrs wn = w2v_layer(p.image, l + 1, D, I);

@@ -465,6 +465,7 @@ struct Wav2LipState {
     float *w2v_xres = nullptr;          // transformer stack (op kind 5) scratch: fp32 residual stream, qkv / attention out / FFN hidden, barrier
     __nv_bfloat16 *w2v_qkv = nullptr, *w2v_ao = nullptr, *w2v_hid = nullptr;
     unsigned *w2v_barrier = nullptr;
+    int w2v_cluster = 1;                // cluster size of k_w2v_stack: the largest of 8 / 4 / 2 / 1 with all WS_G CTAs co-resident
     const unsigned char *w2v_image = nullptr;
     // GroupNorm statistics fused into the producing conv (k_conv_tma epilogue): per conv op its consumer GN op (or -1), per GN op
     // its producer conv (or -1), the per-conv slot buffers, and the slot count chosen while the current launch list is built
@@ -593,8 +594,8 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
                 const int T = ib.H * ib.W;
                 const mf_blob_entry *we = find(o.w_entry);
                 auto slice = [](int N) { int per = (N + WS_G - 1) / WS_G; return (per + 7) / 8 * 8; };
-                MF_REQUIRE(ctx, D > 0 && I > 0 && heads > 0 && layers > 0 && ib.C == D && ob.C == D && ob.H * ob.W == T && D % WS_KC == 0 &&
-                                    I % WS_KC == 0 && D <= WS_KA && D % heads == 0 && slice(3 * D) <= WS_MAX_NC && slice(I) <= WS_MAX_NC &&
+                MF_REQUIRE(ctx, D > 0 && I > 0 && heads > 0 && layers > 0 && ib.C == D && ob.C == D && ob.H * ob.W == T && D % 64 == 0 &&
+                                    (I <= WS_KA ? I % 64 == 0 : I % WS_KC == 0) && D <= WS_KA && D % heads == 0 && slice(3 * D) <= WS_MAX_NC && slice(I) <= WS_MAX_NC &&
                                     (size_t)slice(3 * D) * (D + 8) <= WS_WBUF_HALFS && (size_t)slice(I) * (D + 8) <= WS_WBUF_HALFS &&
                                     (size_t)slice(D) * (I + 8) <= WS_WBUF_HALFS && (size_t)max_batch * T <= WS_MAX_MT * 16 &&
                                     (size_t)(3 * T * (D / heads) + T * T) * 4 <= sizeof(((W2vSmem *)nullptr)->A),
@@ -606,10 +607,28 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
                 MF_CUDA(ctx, cudaMalloc(&s->w2v_qkv, M * 3 * D * 2));
                 MF_CUDA(ctx, cudaMalloc(&s->w2v_ao, M * D * 2));
                 MF_CUDA(ctx, cudaMalloc(&s->w2v_hid, M * I * 2));
-                MF_CUDA(ctx, cudaMalloc(&s->w2v_barrier, 64 + 16 * 8));
-                MF_CUDA(ctx, cudaMemset(s->w2v_barrier, 0, 64 + 16 * 8));
+                MF_CUDA(ctx, cudaMalloc(&s->w2v_barrier, 64 + 24 * 8));
+                MF_CUDA(ctx, cudaMemset(s->w2v_barrier, 0, 64 + 24 * 8));
                 s->w2v_image = base + we->offset;
                 MF_CUDA(ctx, cudaFuncSetAttribute(k_w2v_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(W2vSmem)));
+                {   // the software grid barrier needs every CTA resident: pick the largest cluster size the device can co-schedule WS_G / size times
+                    s->w2v_cluster = 1;
+                    const char *force = getenv("MF_W2V_CLUSTER");
+                    for (int cs = 8; cs >= 2; cs >>= 1) {
+                        if (force && atoi(force) != cs) continue;
+                        cudaLaunchConfig_t cfg;
+                        memset(&cfg, 0, sizeof(cfg));
+                        cfg.gridDim = dim3(WS_G); cfg.blockDim = dim3(WS_THREADS_); cfg.dynamicSmemBytes = sizeof(W2vSmem);
+                        cudaLaunchAttribute at[1];
+                        memset(at, 0, sizeof(at));
+                        at[0].id = cudaLaunchAttributeClusterDimension;
+                        at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                        cfg.attrs = at; cfg.numAttrs = 1;
+                        int n_clusters = 0;
+                        if (cudaOccupancyMaxActiveClusters(&n_clusters, k_w2v_stack, &cfg) == cudaSuccess && n_clusters * cs >= WS_G) { s->w2v_cluster = cs; break; }
+                        cudaGetLastError();
+                    }
+                }
                 continue;
             }
             if (o.kind == 1 || o.kind == 2) {
@@ -1105,6 +1124,7 @@ static int add_op_launches_(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vec
         w.scale_log2 = 1.4426950408889634f / sqrtf((float)(o.Cin / o.ntaps));
         Launch a;
         a.func = (void *)k_w2v_stack; a.grid = dim3(WS_G); a.block = dim3(WS_THREADS_); a.smem = (int)sizeof(W2vSmem); a.op = i;
+        a.cluster = s->w2v_cluster;   // LayerNorm rows are shared inside a cluster (w2v_ln_rows)
         a.set(w);
         L.push_back(std::move(a));
         return MF_OK;
@@ -1438,7 +1458,7 @@ extern "C" int mf_debug_w2v_phase_ns(mf_ctx *ctx, unsigned long long *out, int n
     if (!ctx) return MF_E_INVALID;
     Wav2LipState *s = ctx->wav2lip;
     if (!s || !s->w2v_barrier) return mf_fail(ctx, MF_E_STATE, "mf_debug_w2v_phase_ns: no fused transformer stack loaded");
-    MF_REQUIRE(ctx, out && n >= 1 && n <= 16, "mf_debug_w2v_phase_ns: bad arguments");
+    MF_REQUIRE(ctx, out && n >= 1 && n <= 24, "mf_debug_w2v_phase_ns: bad arguments");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     MF_CUDA(ctx, cudaDeviceSynchronize());
     MF_CUDA(ctx, cudaMemcpy(out, s->w2v_barrier + 16, (size_t)n * 8, cudaMemcpyDeviceToHost));

@@ -83,7 +83,7 @@ def pack_wav2vec2(sd, cfg=XLSR53_CFG, n_samples=8960, fused_stack=True):
         pb.conv1d_same(h, g * cg, x, g * cg, wpos[g * cg:(g + 1) * cg], bpos[g * cg:(g + 1) * cg], left_pad=K // 2, act=ACT_GELU,
                        res=(h, g * cg), res_after_act=True, par=1)   # the G groups are independent: one fork-join in the graph
     import os
-    fused = fused_stack and os.environ.get("MF_W2V_FUSED", "1") != "0" and D % 256 == 0 and I % 256 == 0 and max(3 * D, I) <= 4096 and T <= 32 and (D // H) <= 128
+    fused = fused_stack and os.environ.get("MF_W2V_FUSED", "1") != "0" and D % 64 == 0 and (I % 512 == 0 or (I <= 1024 and I % 64 == 0)) and max(3 * D, I) <= 4096 and T <= 32 and (D // H) <= 128
     ln = pb.buffer(T, 1, D)
     if fused:
         # the L transformer layers as ONE persistent kernel (csrc/w2v_stack.cuh): per layer fp32 vectors, then bf16 row-major matrices
@@ -92,13 +92,22 @@ def pack_wav2vec2(sd, cfg=XLSR53_CFG, n_samples=8960, fused_stack=True):
             p = f"wav2vec2.encoder.layers.{i}."
             wq = np.concatenate([need(p + f"attention.{n}_proj.weight", (D, D)) for n in ("q", "k", "v")])
             bq = np.concatenate([need(p + f"attention.{n}_proj.bias", (D,)) for n in ("q", "k", "v")])
-            vec = np.concatenate([need(p + "layer_norm.weight", (D,)), need(p + "layer_norm.bias", (D,)), bq,
-                                  need(p + "attention.out_proj.bias", (D,)), need(p + "final_layer_norm.weight", (D,)),
-                                  need(p + "final_layer_norm.bias", (D,)), need(p + "feed_forward.intermediate_dense.bias", (I,)),
+            # the LayerNorm affine is folded into the linear layer it feeds (fp64 at pack time): LN(x) W^T + b =
+            # ((x - mean) rstd) (W diag(g))^T + (b + W beta); the kernel normalises only.  The image keeps the g / beta slots (unit / zero).
+            g1, be1 = need(p + "layer_norm.weight", (D,)).astype(np.float64), need(p + "layer_norm.bias", (D,)).astype(np.float64)
+            g2, be2 = need(p + "final_layer_norm.weight", (D,)).astype(np.float64), need(p + "final_layer_norm.bias", (D,)).astype(np.float64)
+            w1 = need(p + "feed_forward.intermediate_dense.weight", (I, D))
+            bq = (bq.astype(np.float64) + wq.astype(np.float64) @ be1).astype(np.float32)
+            b1 = (need(p + "feed_forward.intermediate_dense.bias", (I,)).astype(np.float64) + w1.astype(np.float64) @ be2).astype(np.float32)
+            wq = (wq.astype(np.float64) * g1[None, :]).astype(np.float32)
+            w1 = (w1.astype(np.float64) * g2[None, :]).astype(np.float32)
+            vec = np.concatenate([np.ones(D, np.float32), np.zeros(D, np.float32), bq,
+                                  need(p + "attention.out_proj.bias", (D,)), np.ones(D, np.float32),
+                                  np.zeros(D, np.float32), b1,
                                   need(p + "feed_forward.output_dense.bias", (D,))]).astype(np.float32)
             assert vec.size == 9 * D + I
             parts.append(vec.tobytes())
-            for wm in (wq, need(p + "attention.out_proj.weight", (D, D)), need(p + "feed_forward.intermediate_dense.weight", (I, D)),
+            for wm in (wq, need(p + "attention.out_proj.weight", (D, D)), w1,
                        need(p + "feed_forward.output_dense.weight", (D, I))):
                 parts.append(f32_to_bf16_bits(np.ascontiguousarray(wm, np.float32)).tobytes())
         x2 = pb.buffer(T, 1, D)
