@@ -112,6 +112,18 @@ __device__ __forceinline__ void w2v_issue_w(W2vSmem &sm, const __nv_bfloat16 *W,
     mbar_expect_tx(&sm.wbar[slot], (uint32_t)(nc * K * 2));
     for (int r = 0; r < nc; r++) bulk_g2s(sm.W[slot] + (size_t)r * (K + 8), W + (size_t)(n0 + r) * K, (uint32_t)(K * 2), &sm.wbar[slot]);
 }
+// ... columns [k0, k0 + Ks) of those rows only (row stride ldK in HBM, Ks + 8 in shared memory): the K-split form of FFN2
+__device__ __forceinline__ void w2v_issue_w_sub(W2vSmem &sm, const __nv_bfloat16 *W, int ldK, int k0, int Ks, int n0, int nc, int slot) {
+    mbar_expect_tx(&sm.wbar[slot], (uint32_t)(nc * Ks * 2));
+    for (int r = 0; r < nc; r++) bulk_g2s(sm.W[slot] + (size_t)r * (Ks + 8), W + (size_t)(n0 + r) * ldK + k0, (uint32_t)(Ks * 2), &sm.wbar[slot]);
+}
+__device__ __forceinline__ float w2v_ld_cluster_f32(uint32_t local_saddr, uint32_t rank) {
+    uint32_t remote;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_saddr), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
 __device__ __forceinline__ void w2v_cp16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -327,6 +339,14 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
     w2v_slice(3 * D, n0q, ncq);
     w2v_slice(D, n0d, ncd);
     w2v_slice(I, n0i, nci);
+    // FFN2 (K = I = 4096) split over the K dimension inside the cluster: rank j multiplies columns [j * I / csize, ..) of hid with the
+    // matching weight columns for ALL the cluster's output columns (A and W slices whole in shared memory: no ring, a quarter of the A
+    // traffic), the partial sums meet through distributed shared memory in rank order (deterministic)
+    const int crank = (int)w2v_cluster_rank(), csize = (int)w2v_cluster_size();
+    const int Ks = I / csize;
+    const bool p5_split = csize > 1 && I > WS_KA && I % csize == 0 && Ks <= WS_KA && Ks % 64 == 0 && ncd * csize <= WS_MAX_NC &&
+                          D % ((int)gridDim.x * 8) == 0 && D / (int)gridDim.x == ncd;
+    const int n0c = ((int)blockIdx.x - crank) * ncd;   // first output column of the cluster
     // first weight chunk of layer 0 / P1 in flight before the first barrier
     {
         const W2vLayerPtrs w0 = w2v_layer(p.image, 0, D, I);
@@ -435,12 +455,31 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
                            [&](int m, int n, float v) { p.hid[(size_t)m * I + n0i + n] = __float2bfloat16_rn(w2v_gelu(v + __ldg(w.b1 + n0i + n))); },
                            wphase, wslot, p);
         }
-        if (threadIdx.x == 0 && ncd) w2v_issue_w(sm, w.W2, I, n0d, ncd, wslot);
+        if (threadIdx.x == 0 && ncd) {
+            if (p5_split) w2v_issue_w_sub(sm, w.W2, I, crank * Ks, Ks, n0c, ncd * csize, wslot);
+            else w2v_issue_w(sm, w.W2, I, n0d, ncd, wslot);
+        }
         w2v_stamp(p, l, 7);
         w2v_grid_barrier(p.barrier, gen);
         w2v_stamp(p, l, 8);
         // ---- P5: x += hid W2^T + b
-        if (ncd) {
+        if (p5_split) {
+            float *part = reinterpret_cast<float *>(sm.red);            // [M][ncd * csize] partial sums of this rank's K slice
+            const int ncc = ncd * csize;
+            w2v_copy_a(sm.A, Ks + 8, p.hid, M, Mpad, I, crank * Ks, Ks);
+            w2v_cp_commit();
+            w2v_cp_wait<0>();
+            w2v_phase_gemm(sm, Ks, ncc, M, nullptr, [&](int m, int n, float v) { part[m * ncc + n] = v; }, wphase, wslot, p, l, 13);
+            w2v_cluster_sync();
+            for (int i = threadIdx.x; i < M * ncd; i += WS_THREADS_) {
+                const int m = i / ncd, n = i - m * ncd;
+                const uint32_t a = smem_u32(part + m * ncc + crank * ncd + n);
+                float v = 0.f;
+                for (int r = 0; r < csize; r++) v += w2v_ld_cluster_f32(a, (uint32_t)r);
+                float *x = p.xres + (size_t)m * D + n0d + n;
+                *x = __ldcg(x) + (v + __ldg(w.b2 + n0d + n));
+            }
+        } else if (ncd) {
             if (I <= WS_KA) {
                 w2v_copy_a(sm.A, I + 8, p.hid, M, Mpad, I, 0, I);
                 w2v_cp_commit();
