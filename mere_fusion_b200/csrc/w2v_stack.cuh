@@ -4,20 +4,25 @@
 // Round 1 ran the stack as 24 x 7 launches of the conv executor (LayerNorm, QKV GEMM, attention, out-proj, LayerNorm, FFN1, FFN2):
 // M = 27 tokens per window, so every GEMM is a weight-streaming GEMV-like problem (25 MB of bf16 weights per layer, 604 MB in
 // all = ~0.1 ms at HBM speed) and the 1.6 ms it took were launch latency and under-filled grids (profiles: 203 launches).
-// Here: G = 128 CTAs (one per SM, all resident), each owns a fixed slice of the OUTPUT columns of every matrix, so every weight is
-// read from HBM exactly once per forward and results need no cross-CTA reduction (deterministic); a phase is
-//   [stream this CTA's rows of W in K-chunks by cp.async.bulk (TMA 1-D) into padded shared-memory rows, double buffered,
-//    the first chunk of the NEXT phase issued before the grid barrier]  x  [A chunk built by the CTA: LayerNorm of the fp32
-//    residual stream on the fly, or the bf16 activations of the previous phase]  ->  mma.sync.m16n8k16 bf16  ->  epilogue
+// Here: G = 128 CTAs (one per SM, all resident, clusters of 4), each owns a fixed slice of the OUTPUT columns of every matrix, so every
+// weight is read from HBM exactly once per forward and results need no cross-CTA reduction (deterministic); a phase is
+//   [stream this CTA's rows of W by cp.async.bulk (TMA 1-D, one copy per row) into padded shared-memory rows, double buffered,
+//    the NEXT phase's slice issued before the grid barrier]  x  [A operand: LayerNorm of the fp32 residual stream -- each CTA of a
+//    cluster normalises a quarter of the rows and stores them into all four operands through distributed shared memory -- or the
+//    bf16 activations of the previous phase by cp.async]  ->  mma.sync.m16n8k16 bf16  ->  epilogue
 // and phases are separated by a software grid barrier (5 per layer):
-//   P1  qkv  = LN1(x) Wqkv^T + b          P2  attention per (window, head) on 16 x B CTAs      P3  x += ao Wo^T + b
-//   P4  hid  = gelu(LN2(x) W1^T + b)      P5  x += hid W2^T + b
-// The residual stream stays fp32 in a scratch buffer (the executor's buffers are bf16).  One window per launch (M <= 32 rows): an engine
-// that batches the windows of several sessions keeps the op-by-op program.
-// Measured (B200, XLSR-53 shape): 1.75 ms per window against 2.0 ms for the 203-launch program; per layer ~56 us = LN1+QKV 9.5, attention
-// 6.9 (30 with one CTA per head), out-proj 5.4, LN2+FFN1 9.6 (of which the per-CTA LayerNorm of the 27 rows 6.2), FFN2 13.8 (K = 4096
-// streamed in 16 chunks), 5 barriers ~2 us each -- every phase is a few dependent L2 round trips; the weight stream (25 MB per layer,
-// 4 us at HBM speed) is nowhere near the limit yet.
+//   P1  qkv  = LN1(x) Wqkv^T + b          P2  attention per (window, head, row group) item      P3  x += ao Wo^T + b
+//   P4  hid  = gelu(LN2(x) W1^T + b)      P5  x += hid W2^T + b  (K = 4096 split over the cluster's ranks, partial sums through DSMEM)
+// The LayerNorm affines are folded into Wqkv / W1 and their biases at pack time.  The residual stream stays fp32 in a scratch buffer
+// (the executor's buffers are bf16).  One window per launch (M <= 32 rows): an engine that batches the windows of several sessions keeps
+// the op-by-op program.
+// Measured (B200, XLSR-53 shape, scripts/time_w2v.py: %globaltimer stamps of CTA 0 in layer 1): 1.32 ms per window against 1.97 ms for
+// the 203-launch program of round 1; per layer 45 us = LN1+QKV 6.7 (LN 3.5: x loaded + first reduction 1.3, normalise + remote stores
+// 1.5, cluster sync 0.6; MMA 1.5; epilogue 1.1), attention 7.0, out-proj 5.8, LN2+FFN1 6.9-8.3, FFN2 7.8 (11.4 as a 4-stage ring over
+// the full K, 13.7 with 256-column chunks), five barriers ~2 each (arrival skew + fence, not atomics: spreading the arrivals over 16
+// counters changed nothing).  Every phase is a few dependent L2 round trips at ~32 B/clk of L1 ingest per SM; the weight stream (25 MB
+// per layer, 4 us at HBM speed) is nowhere near the limit.  Tried and dropped: the FFN2 ring fed by cp.async.bulk row copies (216
+// copies of 1 KB per phase: 17.6 us), clusters of 8 (16 of them are not co-resident on this part).
 #pragma once
 
 #define WS_G 128          /* CTAs; output-column slices are multiples of 8 */
