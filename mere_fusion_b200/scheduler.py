@@ -177,7 +177,11 @@ class SharedEngine:
         if req.error is not None:
             raise req.error
         if self._cuda:
-            self._torch.cuda.current_stream(self.device).wait_event(req.done_event)
+            cur = self._torch.cuda.current_stream(self.device)
+            cur.wait_event(req.done_event)
+            for t in (req.out, req.out_f32):     # allocated under the dispatcher's stream, consumed on the caller's: keep the allocator from
+                if t is not None and hasattr(t, "record_stream"):   # recycling the block for the next batch while the caller still reads it
+                    t.record_stream(cur)
         return req.out if req.out is not None else req.out_f32
 
     def flush(self):
@@ -352,16 +356,28 @@ class ErnerfBatcher:
         if req.error is not None:
             raise req.error
         if self._cuda:
-            self._torch.cuda.current_stream(self.device).wait_event(req.done_event)
+            cur = self._torch.cuda.current_stream(self.device)
+            cur.wait_event(req.done_event)
+            if req.out is not None and hasattr(req.out, "record_stream"):
+                req.out.record_stream(cur)
         return req.out
 
+    @staticmethod
+    def _model_key(renderer):
+        """mf_ernerf_render_batch requires contexts loaded from the SAME device blob (pointer-identical tables): sessions whose
+        renderers hold different copies of a model are never put into one pass"""
+        blob = getattr(renderer, "blob", None)
+        return blob.data_ptr() if hasattr(blob, "data_ptr") else 0
+
     def _take(self):
-        """next batch: arrival order, one frame per session, at most MAX_FRAMES"""
-        take, rest, seen = [], [], set()
+        """next batch: arrival order, one frame per session, at most MAX_FRAMES, all of the first request's model"""
+        take, rest, seen, key = [], [], set(), None
         for r in self._pending:
-            if len(take) < self.MAX_FRAMES and id(r.a) not in seen:
+            k = self._model_key(r.a)
+            if len(take) < self.MAX_FRAMES and id(r.a) not in seen and (key is None or k == key):
                 take.append(r)
                 seen.add(id(r.a))
+                key = k
             else:
                 rest.append(r)
         self._pending = rest
