@@ -115,6 +115,7 @@ class ProgramBuilder:
         rb, rc = res if res is not None else (-1, 0)
         if np.all(sc[:cout] == 1.0):
             flags |= 2                                  # unit scale: the epilogue adds the bias only
+        flags |= (int(getattr(self, "par", 0)) & 0xff) << 8   # branch of a parallel region (see `par` below)
         rec = struct.pack("<28i", in_buf, in_coff, out_buf, out_coff, rb, rc, Mh, Mw, oy0, ox0, osy, osx, isy, isx,
                           ntaps, cin_pad, kpad, cout, cout_pad, bn, int(relu), mode, w_id, s_id, h_id, 0, ups, flags)
         rec += struct.pack(f"<{CONV_MAX_TAPS}b", *dy) + struct.pack(f"<{CONV_MAX_TAPS}b", *dx)
@@ -174,11 +175,16 @@ class ProgramBuilder:
         w = np.asarray(weight, np.float32)
         return self.conv(in_buf, in_coff, out_buf, out_coff, w[:, :, None, None], bias, None, res=res, relu=act, mode=mode)
 
-    def conv1d_same(self, in_buf, in_coff, out_buf, out_coff, weight, bias, left_pad, act=False, res=None, res_after_act=False, par=0):
+    # Parallel regions.  While `self.par` is non-zero every conv op that is emitted carries it in flags bits 8..15: a maximal run of
+    # tagged ops is a REGION, the ops of one tag are a BRANCH (executed in order), and the packer promises that no op touches the
+    # output channels of an op of another branch of its region (checked at load).  The executor's captured graph runs the branches of
+    # a region side by side (fork-join): the groups of a grouped conv, or two sub-networks that only meet later.
+    par = 0
+
+    def conv1d_same(self, in_buf, in_coff, out_buf, out_coff, weight, bias, left_pad, act=False, res=None, res_after_act=False):
         """nn.Conv1d over the token axis of [T, 1, C] buffers with `left_pad` zeros in front and as many behind as needed to
         keep T outputs (an even kernel with padding k/2 followed by dropping the last output: HF Wav2Vec2SamePadLayer).
-        weight [Cout, Cin, k].  par (1..255): consecutive ops carrying the same id promise not to touch each other's outputs (the groups
-        of a grouped conv) -- the executor may run them side by side (flags bits 8..15; checked at load)"""
+        weight [Cout, Cin, k]"""
         w = np.asarray(weight, np.float32)
         cout, cin, k = w.shape
         T = self.buffers[in_buf][0]
@@ -188,7 +194,7 @@ class ProgramBuilder:
         scale, shift = bn_fold(bias, None, cout)
         self.flops_per_sample += 2 * cout * cin * k * T
         return self._emit(in_buf, in_coff, cin, out_buf, out_coff, Wm, taps, scale, shift, T, 1, 0, 0, 1, 1, 1, 1, res, act, 0, cout,
-                          flags=int(bool(res_after_act)) | ((int(par) & 0xff) << 8))
+                          flags=int(bool(res_after_act)))
 
     def _misc(self, kind, in_buf, out_buf, **f):
         v = dict(in_coff=0, out_coff=0, res_buf=-1, res_coff=0, Mh=0, Mw=0, ntaps=0, Cin=0, Kpad=0, relu=0, s_id=-1, h_id=-1)

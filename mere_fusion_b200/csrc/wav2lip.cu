@@ -387,7 +387,8 @@ struct Launch {
     int op = -1;  // program op index (conv ops: profiling hook), -1 for helper kernels
     size_t ws_bytes = 0;  // k_conv_tma split-K: workspace / counter requirement (patched in by finish_launch_list)
     int ws_counters = 0;
-    int par = 0;          // != 0: consecutive launches with the same id are independent (W2LOp.flags bits 8..15) and may run side by side
+    int par = 0;          // != 0: branch id inside a parallel region (W2LOp.flags bits 8..15): a maximal run of tagged launches is a region,
+                          // equal ids run in order, different ids may run side by side
     std::vector<unsigned char> params;
     template <class T>
     void set(const T &p) { params.assign((const unsigned char *)&p, (const unsigned char *)&p + sizeof(T)); }
@@ -587,6 +588,7 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
         const W2LOp &o = s->ops[i];
         if (o.kind != 0) {
             MF_REQUIRE(ctx, o.kind >= 1 && o.kind <= 5, "op %d: unknown kind %d", i, o.kind);
+            MF_REQUIRE(ctx, ((o.flags >> 8) & 0xff) == 0, "op %d: only conv ops can be part of a parallel region", i);
             MF_REQUIRE(ctx, okbuf(o.in_buf) && okbuf(o.out_buf), "op %d: bad buffer id", i);
             if (o.kind == 5) {
                 const int D = o.Cin, I = o.Mw, heads = o.ntaps, layers = o.Mh;
@@ -662,17 +664,19 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
                             o.Kpad >= o.ntaps * o.Cin && o.Cout_pad % o.BN == 0 && o.Cout <= o.Cout_pad && o.ups >= 0 && o.ups <= 2,
                    "op %d: bad geometry", i);
         if (const int par = (o.flags >> 8) & 0xff) {
-            // the packer's promise for a run of independent ops, checked: this op's output channels are touched by no other op of the run
-            MF_REQUIRE(ctx, o.mode == 0, "op %d: an output-head op cannot be part of an independent run", i);
-            for (int j = i - 1; j >= 0 && s->ops[j].kind == 0 && ((s->ops[j].flags >> 8) & 0xff) == par; j--) {
+            // the packer's promise for a parallel region, checked: this op's output channels are touched by no op of ANOTHER branch of
+            // the region, and it touches no output of theirs
+            MF_REQUIRE(ctx, o.mode == 0, "op %d: an output-head op cannot be part of a parallel region", i);
+            for (int j = i - 1; j >= 0 && s->ops[j].kind == 0 && ((s->ops[j].flags >> 8) & 0xff) != 0; j--) {
                 const W2LOp &q = s->ops[j];
+                if (((q.flags >> 8) & 0xff) == par) continue;
                 auto overlap = [](int b0, int c0, int n0, int b1, int c1, int n1) { return b0 == b1 && b0 >= 0 && c0 < c1 + n1 && c1 < c0 + n0; };
                 const bool bad = overlap(o.out_buf, o.out_coff, o.Cout, q.out_buf, q.out_coff, q.Cout) ||
                                  overlap(o.out_buf, o.out_coff, o.Cout, q.in_buf, q.in_coff, q.Cin) ||
                                  overlap(o.out_buf, o.out_coff, o.Cout, q.res_buf, q.res_coff, q.Cout) ||
                                  overlap(q.out_buf, q.out_coff, q.Cout, o.in_buf, o.in_coff, o.Cin) ||
                                  overlap(q.out_buf, q.out_coff, q.Cout, o.res_buf, o.res_coff, o.Cout);
-                MF_REQUIRE(ctx, !bad, "ops %d and %d are tagged independent (par %d) but touch each other's output channels", j, i, par);
+                MF_REQUIRE(ctx, !bad, "ops %d and %d are in different branches of a parallel region but touch each other's output channels", j, i);
             }
         }
         const mf_blob_entry *we = find(o.w_entry), *se = find(o.scale_entry), *he = find(o.shift_entry);
@@ -983,20 +987,29 @@ static int add_conv_tma(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<
 
 // allocate (or grow) the split-K workspace for a finished launch list and patch it into the k_conv_tma launches
 static int finish_launch_list(mf_ctx *ctx, std::vector<Launch> &L, float **ws, unsigned **counters, size_t *ws_bytes, int *n_counters) {
-    // launches run one after the other and share the workspace from offset 0 -- except inside a run of independent launches (par),
-    // which may execute concurrently: there every launch gets its own region
+    // launches run one after the other and share the workspace from offset 0 -- except inside a parallel region (Launch::par), whose
+    // branches may execute concurrently: there every BRANCH gets its own region (its launches run in order and share it)
     size_t need = 0;
     int nc = 0;
     std::vector<size_t> ws_off(L.size(), 0);
     std::vector<int> c_off(L.size(), 0);
     for (size_t a = 0; a < L.size();) {
         size_t b = a + 1;
-        while (L[a].par != 0 && b < L.size() && L[b].par == L[a].par) b++;
+        if (L[a].par != 0) while (b < L.size() && L[b].par != 0) b++;
         size_t w = 0;
         int c = 0;
-        for (size_t j = a; j < b; j++) {
-            ws_off[j] = w; c_off[j] = c;
-            w += (L[j].ws_bytes + 255) / 256 * 256; c += L[j].ws_counters;
+        if (L[a].par == 0) {
+            w = L[a].ws_bytes; c = L[a].ws_counters;
+        } else {
+            std::vector<int> tags;
+            for (size_t j = a; j < b; j++) if (std::find(tags.begin(), tags.end(), L[j].par) == tags.end()) tags.push_back(L[j].par);
+            for (int t : tags) {
+                size_t bw = 0;
+                int bc = 0;
+                for (size_t j = a; j < b; j++) if (L[j].par == t) { bw = std::max(bw, L[j].ws_bytes); bc = std::max(bc, L[j].ws_counters); }
+                for (size_t j = a; j < b; j++) if (L[j].par == t) { ws_off[j] = w; c_off[j] = c; }
+                w += (bw + 255) / 256 * 256; c += bc;
+            }
         }
         need = std::max(need, w); nc = std::max(nc, c);
         a = b;
@@ -1030,8 +1043,7 @@ static int add_op_launches(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vect
     const size_t n0 = L.size();
     const int rc = add_op_launches_(ctx, s, i, B, L);
     const int par = (s->ops[i].flags >> 8) & 0xff;
-    // an op that expands to ONE launch keeps its independence tag; multi-launch ops run in order
-    if (rc == MF_OK && par && L.size() == n0 + 1) L[n0].par = par;
+    if (rc == MF_OK && par) for (size_t j = n0; j < L.size(); j++) L[j].par = par;
     return rc;
 }
 static int add_op_launches_(mf_ctx *ctx, Wav2LipState *s, int i, int B, std::vector<Launch> &L) {
@@ -1312,22 +1324,28 @@ static int launch_one(mf_ctx *ctx, Launch &l, cudaStream_t st, bool pdl_attr) {
     return MF_OK;
 }
 
-// `capturing`: st is a capturing stream (the graph path).  Runs of independent launches (Launch::par) then become a fork-join of up to
-// MF_PAR_BRANCHES branches (the 16 groups of wav2vec2's positional conv: 16 launches of 16 CTAs each, 22 us apiece one after the other);
-// launched directly they simply run in order.
+// `capturing`: st is a capturing stream (the graph path).  A parallel region (maximal run of launches with Launch::par != 0) then becomes a
+// fork-join with one branch per tag: the 16 groups of wav2vec2's positional conv (16 launches of 16 CTAs, 22 us apiece one after the
+// other), Wav2Lip's audio encoder beside its face encoder.  Launched directly (profiling, MF_NO_GRAPH) the region simply runs in order.
 static int launch_direct(mf_ctx *ctx, Wav2LipState *s, std::vector<Launch> &L, cudaStream_t st, bool pdl = false, bool capturing = false) {
     bool started = false, first = true;
     for (size_t a = 0; a < L.size();) {
         size_t b = a + 1;
-        while (L[a].par != 0 && b < L.size() && L[b].par == L[a].par) b++;
-        if (capturing && b - a >= 2) {
+        if (L[a].par != 0) while (b < L.size() && L[b].par != 0) b++;
+        std::vector<int> tags;
+        if (L[a].par != 0)
+            for (size_t j = a; j < b; j++) if (std::find(tags.begin(), tags.end(), L[j].par) == tags.end()) tags.push_back(L[j].par);
+        if (capturing && tags.size() >= 2 && tags.size() <= MF_PAR_BRANCHES) {
             MF_REQUIRE(ctx, !s->par_streams.empty(), "fork-join streams were not created before the capture");
-            const int nb = (int)std::min<size_t>(MF_PAR_BRANCHES, b - a);
+            const int nb = (int)tags.size();
             MF_CUDA(ctx, cudaEventRecord(s->par_events[0], st));
             for (int j = 0; j < nb; j++) MF_CUDA(ctx, cudaStreamWaitEvent(s->par_streams[j], s->par_events[0], 0));
+            std::vector<char> first_in_branch(nb, 1);
             for (size_t j = a; j < b; j++) {
-                const int rc = launch_one(ctx, L[j], s->par_streams[(j - a) % nb], false);
+                const int br = (int)(std::find(tags.begin(), tags.end(), L[j].par) - tags.begin());
+                const int rc = launch_one(ctx, L[j], s->par_streams[br], pdl && !first_in_branch[br]);
                 if (rc) return rc;
+                first_in_branch[br] = 0;
             }
             for (int j = 0; j < nb; j++) {
                 MF_CUDA(ctx, cudaEventRecord(s->par_events[1 + j], s->par_streams[j]));

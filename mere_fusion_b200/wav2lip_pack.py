@@ -133,7 +133,9 @@ def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
     in_mel = pb.buffer(80, 16, 8)
     pb.hdr.update(in_face_buf=in_face, in_mel_buf=in_mel, face_hw=S, mel_h=80, mel_w=16, out_hw=S)
 
-    # ---- audio encoder (wav2lip.py:38-55)
+    # ---- audio encoder (wav2lip.py:38-55).  It meets the face encoder only in the decoder: the two are the branches of one parallel
+    # region (convnet_pack.ProgramBuilder.par), 13 small layers that used to run in front of the face encoder now run beside it
+    pb.par = 1
     cur, coff, H, W = in_mel, 0, 80, 16
     for j, (cout, k, st, p, resid) in enumerate(AUDIO_ENC):
         w, b, bn = block(f"audio_encoder.{j}")
@@ -144,6 +146,7 @@ def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
     audio_emb = cur                                               # [B, 1, 1, 512]
 
     # ---- face encoder (wav2lip.py:13-36); the last conv of block i lands in cat[i][..., cat_off[i]:]
+    pb.par = 2
     cur, coff = in_face, 0
     for i, blk in enumerate(FACE_ENC):
         for j, (cout, k, s, p, resid) in enumerate(blk):
@@ -163,6 +166,7 @@ def pack_wav2lip(sd, nominal_batch=16, face_hw=96):
             cur, coff = out, ooff
 
     # ---- face decoder (wav2lip.py:57-81,102-112)
+    pb.par = 0
     cur, coff = audio_emb, 0
     for i, blk in enumerate(FACE_DEC):
         tgt = cat[n - 1 - i]

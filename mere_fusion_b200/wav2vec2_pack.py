@@ -80,8 +80,10 @@ def pack_wav2vec2(sd, cfg=XLSR53_CFG, n_samples=8960, fused_stack=True):
     bpos = need(pc + "bias", (D,))
     x = pb.buffer(T, 1, D)
     for g in range(G):   # x = h + gelu(conv(h)): the residual is added after the activation
+        pb.par = 1 + g % 16                                    # the G groups are independent: branches of one parallel region
         pb.conv1d_same(h, g * cg, x, g * cg, wpos[g * cg:(g + 1) * cg], bpos[g * cg:(g + 1) * cg], left_pad=K // 2, act=ACT_GELU,
-                       res=(h, g * cg), res_after_act=True, par=1)   # the G groups are independent: one fork-join in the graph
+                       res=(h, g * cg), res_after_act=True)
+    pb.par = 0
     import os
     fused = fused_stack and os.environ.get("MF_W2V_FUSED", "1") != "0" and D % 64 == 0 and (I % 512 == 0 or (I <= 1024 and I % 64 == 0)) and max(3 * D, I) <= 4096 and T <= 32 and (D // H) <= 128
     ln = pb.buffer(T, 1, D)
