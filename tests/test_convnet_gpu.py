@@ -133,3 +133,37 @@ def test_conv3x3_row_halo_tiles():
     # twice -- the planner must take a narrower BN (MuseTalk VAE 256 -> 256 @128x128 at B = 1 failed to plan before)
     run_case(1, 100, 128, 256, 256, 3, 1, 1, residual=True, seed=17)
     run_case(1, 64, 128, 512, 256, 3, 1, 1, seed=18)
+
+
+def test_parallel_region_branches_are_checked_and_equal_the_serial_program():
+    """ProgramBuilder.par: two branches of one region (here: the two halves of a 128-channel 3x3 conv as independent 64-channel convs,
+    each followed by a second conv of its own branch) give the result of the untagged program bit for bit; branches that write the
+    same output channels are refused at load (MfError), not raced."""
+    from mere_fusion_b200._lib import MfError
+    from mere_fusion_b200.convnet_pack import ProgramBuilder
+    from mere_fusion_b200.wav2lip import ConvNet
+    g = torch.Generator().manual_seed(5)
+    B, H, C = 2, 12, 64
+    x = torch.randn(B, H, H, 2 * C, generator=g)
+    ws = [(torch.randn(C, C, 3, 3, generator=g) / 24).numpy() for _ in range(4)]
+    bs = [(torch.randn(C, generator=g) * 0.1).numpy() for _ in range(4)]
+
+    def build(tagged, clash=False):
+        pb = ProgramBuilder(nominal_batch=B)
+        ib, mid, ob = pb.buffer(H, H, 2 * C), pb.buffer(H, H, 2 * C), pb.buffer(H, H, 2 * C)
+        for br in range(2):
+            pb.par = (br + 1) if tagged else 0
+            pb.conv(ib, br * C, mid, br * C, ws[2 * br], bs[2 * br], None, stride=1, padding=1)
+            pb.conv(mid, br * C, ob, 0 if clash else br * C, ws[2 * br + 1], bs[2 * br + 1], None, stride=1, padding=1)
+        pb.par = 0
+        return pb, ib, ob
+    outs = []
+    for tagged in (False, True):
+        pb, ib, ob = build(tagged)
+        net = ConvNet(pb.finish(), max_batch=B)
+        outs.append(net.debug_run(ib, x, ob, (B, H, H, 2 * C)).cpu())
+        torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and float(outs[0].abs().max()) > 0
+    pb, ib, ob = build(True, clash=True)
+    with pytest.raises(MfError, match="different branches of a parallel region"):
+        ConvNet(pb.finish(), max_batch=B)
