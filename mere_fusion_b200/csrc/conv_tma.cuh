@@ -278,6 +278,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 5 && lane == 0) {   // the descriptors are kernel arguments: fetched while the predecessor drains
+        tma_prefetch_desc(&p.amap);
+        tma_prefetch_desc(&p.wmap);
+    }
     pdl_launch();
     pdl_wait();   // barrier init, TMEM allocation and descriptor fetch above overlap the predecessor's tail
     const int total = p.total_items;            // work items of a CTA (CG 1) or of a CTA pair (CG 2)
@@ -287,8 +291,6 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tma(const __grid_constan
     if (warp == 5) {
         // =========================== TMA producer ==============================================
         if (lane == 0) {
-            tma_prefetch_desc(&p.amap);
-            tma_prefetch_desc(&p.wmap);
             int s = 0;
             uint32_t ph = 1;   // parity to wait for on empty[s]: a fresh barrier passes a wait on parity 1 (first lap = free)
             for (int item = item0; item < total; item += item_step) {

@@ -35,8 +35,14 @@ class WhisperEngine(ConvNet):
         n = int(audio.shape[0])
         if T is None:
             T = int((n // 160) / 2)
-        if out is None:
-            out = torch.empty((T, self.n_embeds, self.n_state), dtype=torch.float32, device=self.device)
+        fixed = out is None
+        if fixed:
+            # the executor re-captures its CUDA graph whenever the caller's pointers change: without an `out` the program writes into a
+            # per-T buffer that stays put and the caller gets a copy (one small D2D kernel instead of a possible capture per window)
+            outs = self.__dict__.setdefault("_outs", {})
+            out = outs.get(T)
+            if out is None:
+                out = outs[T] = torch.empty((T, self.n_embeds, self.n_state), dtype=torch.float32, device=self.device)
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         # one audio processor may serve several MuseReal sessions (threads, each on its own stream): the context and its
         # activation workspace are single-user, so calls are serialised on the host (lock) AND on the device (event chain)
@@ -45,6 +51,9 @@ class WhisperEngine(ConvNet):
                 s.wait_event(self._last_done)
             check(self.ctx.handle, lib().mf_whisper_features(self.ctx.handle, _ptr(audio), n, _ptr(out), T, ctypes.c_void_p(s.cuda_stream)),
                   "mf_whisper_features")
+            if fixed:
+                with torch.cuda.stream(s):
+                    out = out.clone()
             ev = torch.cuda.Event()
             ev.record(s)
             self._last_done = ev
