@@ -214,7 +214,13 @@ __device__ __forceinline__ void ray_pass(const SetupBatch &b, int cta, int n_cta
             if (lane == 0) tile = atomicAdd(&fr.counters[CT_RTICKET], 1);
             tile = __shfl_sync(0xffffffffu, tile, 0);
             if (tile >= n_tiles) break;
-            const int ray = tile * 32 + lane;
+            // a tile is an 8 x 4 pixel block when the image allows it (a warp's rays then stay together in k_head: nearer samples, more
+            // shared table texels, more alike lives than a 32 x 1 row segment), else 32 consecutive rays
+            int ray = tile * 32 + lane;
+            if (!fr.g.rays_o && (fr.g.W & 7) == 0 && (fr.g.H & 3) == 0 && fr.g.N == fr.g.H * fr.g.W) {
+                const int bw = fr.g.W >> 3, ty = tile / bw, tx = tile - ty * bw;
+                ray = (ty * 4 + (lane >> 3)) * fr.g.W + tx * 8 + (lane & 7);
+            }
             const bool valid = ray < fr.g.N;
             bool has = false;
             float t = 0.f;
