@@ -379,8 +379,9 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
             const int dh = D / p.heads, T = p.T;
             const int RG = max(1, min(T, (int)gridDim.x / (p.B * p.heads)));      // query-row groups per (window, head)
             const int rows_per = (T + RG - 1) / RG;
-            float *sq = reinterpret_cast<float *>(sm.A);             // q rows of the group | k | v [T][dh], scores [rows_per][T]
-            float *sk = sq + rows_per * dh, *sv = sk + T * dh, *sc = sv + T * dh;
+            float *sq = reinterpret_cast<float *>(sm.A);             // q rows of the group | k [T][dh + 1] | v [T][dh], scores [rows_per][T]
+            const int dk = dh + 1;                                   // k rows padded: the score loop reads k[tk][d] with tk across the lanes
+            float *sk = sq + rows_per * dh, *sv = sk + T * dk, *sc = sv + T * dh;
             for (int item = blockIdx.x; item < p.B * p.heads * RG; item += gridDim.x) {
                 const int bh = item / RG, rg = item - bh * RG, b = bh / p.heads, h = bh - b * p.heads;
                 const int t0 = rg * rows_per, nr = min(rows_per, T - t0);
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
                     const int which = r < nr ? 0 : (r < nr + T ? 1 : 2), t = which == 0 ? t0 + r : (which == 1 ? r - nr : r - nr - T);
                     const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p.qkv + (size_t)(b * T + t) * 3 * D + which * D + h * dh + d));   // not through L1
                     const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-                    float *dstf = (which == 0 ? sq + r * dh : (which == 1 ? sk + t * dh : sv + t * dh)) + d;
+                    float *dstf = (which == 0 ? sq + r * dh : (which == 1 ? sk + t * dk : sv + t * dh)) + d;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         dstf[2 * j] = __uint_as_float(wv[j] << 16);
@@ -403,8 +404,8 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
                     const int tq = i / T, tk = i - tq * T;
                     float s0 = 0.f, s1 = 0.f;
                     for (int d = 0; d < dh; d += 2) {
-                        s0 = fmaf(sq[tq * dh + d], sk[tk * dh + d], s0);
-                        s1 = fmaf(sq[tq * dh + d + 1], sk[tk * dh + d + 1], s1);
+                        s0 = fmaf(sq[tq * dh + d], sk[tk * dk + d], s0);
+                        s1 = fmaf(sq[tq * dh + d + 1], sk[tk * dk + d + 1], s1);
                     }
                     sc[i] = (s0 + s1) * p.scale_log2;
                 }

@@ -600,7 +600,7 @@ extern "C" int mf_wav2lip_load(mf_ctx *ctx, const void *blob, size_t nbytes, int
                                     (I <= WS_KA ? I % 64 == 0 : I % WS_KC == 0) && D <= WS_KA && D % heads == 0 && slice(3 * D) <= WS_MAX_NC && slice(I) <= WS_MAX_NC &&
                                     (size_t)slice(3 * D) * (D + 8) <= WS_WBUF_HALFS && (size_t)slice(I) * (D + 8) <= WS_WBUF_HALFS &&
                                     (size_t)slice(D) * (I + 8) <= WS_WBUF_HALFS && (size_t)max_batch * T <= WS_MAX_MT * 16 &&
-                                    (size_t)(3 * T * (D / heads) + T * T) * 4 <= sizeof(((W2vSmem *)nullptr)->A),
+                                    (size_t)(3 * T * (D / heads + 1) + T * T) * 4 <= sizeof(((W2vSmem *)nullptr)->A),
                            "op %d: transformer stack outside what k_w2v_stack implements (one window, D <= 1024)", i);
                 MF_REQUIRE(ctx, we && we->nbytes == (size_t)layers * w2v_layer_bytes(D, I), "op %d: transformer weight image does not match the geometry", i);
                 const size_t M = (size_t)max_batch * T;
