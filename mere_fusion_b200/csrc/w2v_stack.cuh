@@ -223,8 +223,11 @@ __device__ __forceinline__ void w2v_copy_a(__nv_bfloat16 *dst, int ks, const __n
 // every valid (m < M, n < nc) exactly once; the order of summation is fixed.
 // Work split: (m-tile, n-tile) pairs over the 8 warps; with fewer pairs than warps the k-steps are split over the spare warps and
 // the partials are added in warp order through shared memory.
-template <class Epi>
-__device__ __forceinline__ void w2v_phase_gemm(W2vSmem &sm, int K, int nc, int M, const __nv_bfloat16 *a_src, Epi epi, uint32_t (&wphase)[2],
+// pre(m, n) -> float2 is called for the thread's (up to four) outputs BEFORE the MMA loop and handed to epi(m, n, value, pre): the bias
+// (cold in HBM: part of the weight image) and the residual element are loaded while the GEMM runs instead of one L2 / HBM round trip
+// after it (~1 us per phase).
+template <class Pre, class Epi>
+__device__ __forceinline__ void w2v_phase_gemm(W2vSmem &sm, int K, int nc, int M, const __nv_bfloat16 *a_src, Pre pre, Epi epi, uint32_t (&wphase)[2],
                                                int &wslot, const W2vStackParams &dbg_p, int dbg_l = -1, int dbg_i = 0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = (M + 15) / 16, Mpad = mt * 16, nt = nc / 8, pairs = mt * nt;
@@ -236,6 +239,12 @@ __device__ __forceinline__ void w2v_phase_gemm(W2vSmem &sm, int K, int nc, int M
     const int mi = active ? pr / nt : 0, ni = active ? pr - mi * nt : 0;
     const int wks = K + 8;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 pv[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    if (active && kpart == 0) {
+        const int r0 = mi * 16 + (lane >> 2), cc = ni * 8 + 2 * (lane & 3);
+        if (r0 < M) { pv[0] = pre(r0, cc); pv[1] = pre(r0, cc + 1); }
+        if (r0 + 8 < M) { pv[2] = pre(r0 + 8, cc); pv[3] = pre(r0 + 8, cc + 1); }
+    }
     const __nv_bfloat16 *Wsm = sm.W[wslot];
     const int q = lane >> 3;
     if (K <= WS_KA) {
@@ -299,8 +308,8 @@ __device__ __forceinline__ void w2v_phase_gemm(W2vSmem &sm, int K, int nc, int M
     }
     if (active && kpart == 0) {
         const int r0 = mi * 16 + (lane >> 2), cc = ni * 8 + 2 * (lane & 3);
-        if (r0 < M) { epi(r0, cc, acc[0]); epi(r0, cc + 1, acc[1]); }
-        if (r0 + 8 < M) { epi(r0 + 8, cc, acc[2]); epi(r0 + 8, cc + 1, acc[3]); }
+        if (r0 < M) { epi(r0, cc, acc[0], pv[0]); epi(r0, cc + 1, acc[1], pv[1]); }
+        if (r0 + 8 < M) { epi(r0 + 8, cc, acc[2], pv[2]); epi(r0 + 8, cc + 1, acc[3], pv[3]); }
     }
     __syncthreads();
 }
@@ -367,7 +376,8 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
         w2v_stamp(p, l, 15);
         if (ncq) {
             w2v_phase_gemm(sm, D, ncq, M, nullptr,
-                           [&](int m, int n, float v) { p.qkv[(size_t)m * 3 * D + n0q + n] = __float2bfloat16_rn(v + __ldg(w.bqkv + n0q + n)); },
+                           [&](int, int n) { return make_float2(__ldg(w.bqkv + n0q + n), 0.f); },
+                           [&](int m, int n, float v, float2 pr) { p.qkv[(size_t)m * 3 * D + n0q + n] = __float2bfloat16_rn(v + pr.x); },
                            wphase, wslot, p, l, 11);
         }
         if (threadIdx.x == 0 && ncd) w2v_issue_w(sm, w.Wo, D, n0d, ncd, wslot);         // P3's weights stream during P2
@@ -447,7 +457,8 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
             w2v_cp_commit();
             w2v_cp_wait<0>();
             w2v_phase_gemm(sm, D, ncd, M, nullptr,
-                           [&](int m, int n, float v) { float *x = p.xres + (size_t)m * D + n0d + n; *x = __ldcg(x) + (v + __ldg(w.bo + n0d + n)); },
+                           [&](int m, int n) { return make_float2(__ldg(w.bo + n0d + n), __ldcg(p.xres + (size_t)m * D + n0d + n)); },
+                           [&](int m, int n, float v, float2 pr) { p.xres[(size_t)m * D + n0d + n] = pr.y + (v + pr.x); },
                            wphase, wslot, p);
         }
         if (threadIdx.x == 0 && nci) w2v_issue_w(sm, w.W1, D, n0i, nci, wslot);
@@ -458,7 +469,8 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
         w2v_ln_rows(sm, p.xres, M, Mpad, D, p.eps, p);
         if (nci) {
             w2v_phase_gemm(sm, D, nci, M, nullptr,
-                           [&](int m, int n, float v) { p.hid[(size_t)m * I + n0i + n] = __float2bfloat16_rn(w2v_gelu(v + __ldg(w.b1 + n0i + n))); },
+                           [&](int, int n) { return make_float2(__ldg(w.b1 + n0i + n), 0.f); },
+                           [&](int m, int n, float v, float2 pr) { p.hid[(size_t)m * I + n0i + n] = __float2bfloat16_rn(w2v_gelu(v + pr.x)); },
                            wphase, wslot, p);
         }
         if (threadIdx.x == 0 && ncd) {
@@ -475,9 +487,21 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
             w2v_copy_a(sm.A, Ks + 8, p.hid, M, Mpad, I, crank * Ks, Ks);
             w2v_cp_commit();
             w2v_cp_wait<0>();
-            w2v_phase_gemm(sm, Ks, ncc, M, nullptr, [&](int m, int n, float v) { part[m * ncc + n] = v; }, wphase, wslot, p, l, 13);
+            // this thread's output element of the final reduction (M * ncd <= 256): residual and bias are loaded before the GEMM
+            const int om = (int)threadIdx.x / ncd, on = (int)threadIdx.x - om * ncd;
+            const bool mine = (int)threadIdx.x < M * ncd;
+            float xr = 0.f, br = 0.f;
+            if (mine) { xr = __ldcg(p.xres + (size_t)om * D + n0d + on); br = __ldg(w.b2 + n0d + on); }
+            w2v_phase_gemm(sm, Ks, ncc, M, nullptr, [](int, int) { return make_float2(0.f, 0.f); },
+                           [&](int m, int n, float v, float2) { part[m * ncc + n] = v; }, wphase, wslot, p, l, 13);
             w2v_cluster_sync();
-            for (int i = threadIdx.x; i < M * ncd; i += WS_THREADS_) {
+            if (mine) {
+                const uint32_t a = smem_u32(part + om * ncc + crank * ncd + on);
+                float v = 0.f;
+                for (int r = 0; r < csize; r++) v += w2v_ld_cluster_f32(a, (uint32_t)r);
+                p.xres[(size_t)om * D + n0d + on] = xr + (v + br);
+            }
+            for (int i = threadIdx.x + WS_THREADS_; i < M * ncd; i += WS_THREADS_) {   // (not reached for M <= 32, ncd = 8)
                 const int m = i / ncd, n = i - m * ncd;
                 const uint32_t a = smem_u32(part + m * ncc + crank * ncd + n);
                 float v = 0.f;
@@ -492,7 +516,8 @@ __global__ void __launch_bounds__(WS_THREADS_, 1) k_w2v_stack(const __grid_const
                 w2v_cp_wait<0>();
             }
             w2v_phase_gemm(sm, I, ncd, M, p.hid,
-                           [&](int m, int n, float v) { float *x = p.xres + (size_t)m * D + n0d + n; *x = __ldcg(x) + (v + __ldg(w.b2 + n0d + n)); },
+                           [&](int m, int n) { return make_float2(__ldg(w.b2 + n0d + n), __ldcg(p.xres + (size_t)m * D + n0d + n)); },
+                           [&](int m, int n, float v, float2 pr) { p.xres[(size_t)m * D + n0d + n] = pr.y + (v + pr.x); },
                            wphase, wslot, p, l, 13);
         }
         if (l + 1 < p.layers) {
