@@ -16,13 +16,14 @@
 // The LayerNorm affines are folded into Wqkv / W1 and their biases at pack time.  The residual stream stays fp32 in a scratch buffer
 // (the executor's buffers are bf16).  One window per launch (M <= 32 rows): an engine that batches the windows of several sessions keeps
 // the op-by-op program.
-// Measured (B200, XLSR-53 shape, scripts/time_w2v.py: %globaltimer stamps of CTA 0 in layer 1): 1.32 ms per window against 1.97 ms for
-// the 203-launch program of round 1; per layer 45 us = LN1+QKV 6.7 (LN 3.5: x loaded + first reduction 1.3, normalise + remote stores
-// 1.5, cluster sync 0.6; MMA 1.5; epilogue 1.1), attention 7.0, out-proj 5.8, LN2+FFN1 6.9-8.3, FFN2 7.8 (11.4 as a 4-stage ring over
-// the full K, 13.7 with 256-column chunks), five barriers ~2 each (arrival skew + fence, not atomics: spreading the arrivals over 16
-// counters changed nothing).  Every phase is a few dependent L2 round trips at ~32 B/clk of L1 ingest per SM; the weight stream (25 MB
-// per layer, 4 us at HBM speed) is nowhere near the limit.  Tried and dropped: the FFN2 ring fed by cp.async.bulk row copies (216
-// copies of 1 KB per phase: 17.6 us), clusters of 8 (16 of them are not co-resident on this part).
+// Measured (B200, XLSR-53 shape, scripts/time_w2v.py: %globaltimer stamps of CTA 0 in layer 1): 1.20 ms per window against 1.97 ms for
+// the 203-launch program of round 1; per layer 41 us = LN1+QKV 6.6 (LN 3.5: x loaded + first reduction 1.3, normalise + remote stores
+// 1.5, cluster sync 0.6; MMA 1.4; epilogue 0.7 with the bias loaded before the GEMM), attention 4.0 (7.0 before the K rows were padded:
+// 32-way bank conflict in the score loop), out-proj 4.9, LN2+FFN1 8.4, FFN2 7.5 (11.4 as a 4-stage ring over the full K, 13.7 with
+// 256-column chunks), five barriers ~2 each (arrival skew + fence, not atomics: spreading the arrivals over 16 counters changed nothing).
+// Every phase is a few dependent L2 round trips at ~32 B/clk of L1 ingest per SM; the weight stream (25 MB per layer, 4 us at HBM speed)
+// is nowhere near the limit.  Tried and dropped: the FFN2 ring fed by cp.async.bulk row copies (216 copies of 1 KB per phase: 17.6 us),
+// bulk row copies for the whole-A operands of out-proj / FFN2 (no change), clusters of 8 (16 of them are not co-resident on this part).
 #pragma once
 
 #define WS_G 128          /* CTAs; output-column slices are multiples of 8 */
