@@ -2,19 +2,22 @@
 //
 // Replaces, per frame, the ~400 launches + <=16 host syncs of the reference's
 // NeRFRenderer.run_cuda / run_torso (ernerf/nerf_triplane/renderer.py:158-352) by
-//   k_setup         CTA f < n_frames : AudioNet + AudioAttNet + EMA (network.py:9-66,222-237) and the per-frame torso
-//                                      constants of frame f
-//                   the other CTAs   : the RAY PASS -- ray generation (utils.py:255-341) -> near/far
-//                                      (raymarching.cu:91-145) -> march to the first sample (raymarching.cu:827-929);
-//                                      rays that have one are appended to the frame's hit list (this is the reference's
-//                                      round 0 minus its shading: n_step = N / N = 1)
+//   k_setup         CTAs < 8 n_frames: AudioNet on one attention window each, the last one to finish adds AudioAttNet +
+//                                      EMA (network.py:9-66,222-237) of its frame
+//                   the other CTAs   : the RAY PASS -- 32-ray tiles (8 x 4 pixel blocks) drawn by ticket: ray generation
+//                                      (utils.py:255-341) -> near/far (raymarching.cu:91-145) -> march to the first sample
+//                                      (raymarching.cu:827-929); rays that have one are appended to the frame's hit list
+//                                      (this is the reference's round 0 minus its shading: n_step = N / N = 1)
 //   k_head          persistent, NO grid barrier: each warp owns 32 / CH rays at a time, marches CH samples of each
 //                   side by side -> tri-plane hash-grid gather (gridencoder.cu:75-175) -> SH (shencoder.cu:27-68) ->
 //                   aud_ch_att / eye_att / sigma / color MLPs (network.py:249-308) on warp-level tensor-core tiles ->
 //                   composite (raymarching.cu:2141-2249) in sample order, and refills finished rays from the hit list
-//   k_torso_compose resolves the loop control from the life histogram, then torso occupancy + deformation + tiled grid
-//                   + MLPs (network.py:166-201, renderer.py:294-352), background blend, clamp, fp32 / u8 output
+//   k_torso_compose torso occupancy + deformation + tiled grid + MLPs (network.py:166-201, renderer.py:294-352) over the
+//                   background for all its tiles first, THEN it waits for k_head, resolves the loop control from the life
+//                   histogram and composes: head + (1 - weights_sum) * that, clamp, fp32 / u8 output
 //   k_resize_u8     bilinear resize (utils.py:1212) + u8 (nerfreal.py:110) when sizes differ
+// The three kernels of a frame are chained by programmatic dependent launch (griddepcontrol): k_head stages its MLP image
+// while k_setup drains, k_torso_compose's torso pass runs on the SMs k_head's CTAs have already left.
 //
 // Round semantics WITHOUT rounds.  The reference marches every alive ray n_step = clamp(N / n_alive, 1, 8) samples per
 // round and stops when the summed n_step reaches max_steps (renderer.py:246-270); n_alive is a global quantity, which is
