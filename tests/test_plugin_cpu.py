@@ -432,3 +432,82 @@ def test_ernerf_background_image_is_carried_over(tmp_path):
     assert ErnerfPoseProvider(tr, None, bg_img="black").bg_img.shape == (8, 8, 3)
     with pytest.raises(NotImplementedError):
         ErnerfPoseProvider(tr, None, torso_imgs="data/torso")
+
+
+def test_nerfreal_render_hands_frames_over_in_order_and_never_holds_one_back():
+    """NeRFReal.render (nerfreal.py:129-156): the video frame of step k is finished while step k + 1 is in flight -- but only while more
+    audio is waiting; with an empty input queue it is finished at once.  Every step yields exactly one video frame and two audio frames,
+    in order, and the frame that is still pending when the loop is told to quit is flushed.  The GPU part is replaced by a stand-in."""
+    from mere_fusion_b200.ernerf_data import ErnerfPoseProvider
+    from mere_fusion_b200.plugin.nerfreal import NeRFReal
+
+    class Ev:
+        def __init__(self, log, k):
+            self.log, self.k = log, k
+
+        def synchronize(self):
+            self.log.append(("sync", self.k))
+
+    class Pin:
+        def __init__(self, k):
+            self.k = k
+
+        def numpy(self):
+            return np.full((8, 8, 3), self.k % 256, np.uint8)
+
+    tr = dict(cx=4.0, cy=4.0, focal_len=10.0, frames=[dict(transform_matrix=np.eye(4).tolist(), img_id=0)] * 4)
+    real = NeRFReal.__new__(NeRFReal)
+    from mere_fusion_b200.plugin.basereal import BaseReal
+    opt = make_opt(W=8, H=8)
+    BaseReal.__init__(real, opt)
+    real.W = real.H = 8
+    real.provider = ErnerfPoseProvider(tr, None)
+    log = []
+    state = dict(k=0, waiting=6)      # audio chunks "waiting" in the input queue: 6, then none
+
+    class Asr:
+        class Q:
+            def empty(self_q):
+                return state["waiting"] <= 0
+        queue = Q()
+
+        def run_step(self):
+            state["waiting"] -= 1
+
+        def get_next_feat(self):
+            return None
+
+        def get_audio_out(self):
+            return np.zeros(320, np.float32), 0
+
+    real.asr = Asr()
+
+    def fake_render_async(pose, eye, auds):
+        k = state["k"]
+        state["k"] += 1
+        log.append(("issue", k))
+        return Pin(k), Ev(log, k)
+    real._render_async = fake_render_async
+    quit_event = threading.Event()
+    audio_track, video_track = FakeTrack(), FakeTrack()
+    orig_put = video_track._queue.put
+
+    async def put_and_count(x):
+        await orig_put(x)
+        log.append(("video", len(video_track._queue.items) - 1))
+        if len(video_track._queue.items) == 5:
+            quit_event.set()
+    video_track._queue.put = put_and_count
+    real.render(quit_event, None, audio_track, video_track)
+    vids = video_track._queue.items
+    assert len(vids) == state["k"] and len(audio_track._queue.items) == 2 * state["k"]            # one video + two audio frames per step, none lost
+    assert [int(v.to_ndarray()[0, 0, 0]) for v in vids] == list(range(len(vids)))                   # in order
+    ev = [e for e in log if e[0] != "sync"]
+    # while audio was waiting (steps 0..2: two chunks per step) frame k went out only after step k + 1 had been issued ...
+    assert ev[:5] == [("issue", 0), ("issue", 1), ("video", 0), ("issue", 2), ("video", 1)]
+    # ... and once the queue was empty every frame was finished inside its own step
+    tail = ev[5:]
+    assert tail[:2] == [("video", 2), ("issue", 3)] or tail[:1] == [("video", 2)]
+    for a, b in zip(tail, tail[1:]):
+        if a[0] == "issue" and a[1] >= 3:
+            assert b == ("video", a[1])
