@@ -16,11 +16,11 @@
 // The LayerNorm affines are folded into Wqkv / W1 and their biases at pack time.  The residual stream stays fp32 in a scratch buffer
 // (the executor's buffers are bf16).  One window per launch (M <= 32 rows): an engine that batches the windows of several sessions keeps
 // the op-by-op program.
-// Measured (B200, XLSR-53 shape, scripts/time_w2v.py: %globaltimer stamps of CTA 0 in layer 1): 1.20 ms per window against 1.97 ms for
-// the 203-launch program of round 1; per layer 41 us = LN1+QKV 6.6 (LN 3.5: x loaded + first reduction 1.3, normalise + remote stores
+// Measured (B200, XLSR-53 shape, scripts/time_w2v.py: %globaltimer stamps of CTA 0 in layer 1): 1.16 ms per window against 1.97 ms for
+// the 203-launch program of round 1; per layer 38.5 us = LN1+QKV 6.6 (LN 3.5: x loaded + first reduction 1.3, normalise + remote stores
 // 1.5, cluster sync 0.6; MMA 1.4; epilogue 0.7 with the bias loaded before the GEMM), attention 4.0 (7.0 before the K rows were padded:
 // 32-way bank conflict in the score loop), out-proj 4.9, LN2+FFN1 8.4, FFN2 7.5 (11.4 as a 4-stage ring over the full K, 13.7 with
-// 256-column chunks), five barriers ~2 each (arrival skew + fence, not atomics: spreading the arrivals over 16 counters changed nothing).
+// 256-column chunks), five barriers ~1.5 each (release / acquire instead of full fences: 2.0 -> 1.5; the rest is arrival skew).
 // Every phase is a few dependent L2 round trips at ~32 B/clk of L1 ingest per SM; the weight stream (25 MB per layer, 4 us at HBM speed)
 // is nowhere near the limit.  Tried and dropped: the FFN2 ring fed by cp.async.bulk row copies (216 copies of 1 KB per phase: 17.6 us),
 // bulk row copies for the whole-A operands of out-proj / FFN2 (no change), clusters of 8 (16 of them are not co-resident on this part).
@@ -75,26 +75,26 @@ struct W2vSmem {
     alignas(8) uint64_t wbar[2];
 };
 
-// Software grid barrier.  Arrivals are spread over 16 counters (CTA b -> counter b & 15): atomics on ONE address serialise in L2 at ~27
-// cycles each, i.e. ~1.8 us for 128 CTAs -- most of what a barrier cost; 8 per counter take 0.1 us.  Warp 0 polls: lane i watches counter i.
+// Software grid barrier.  Arrivals are spread over 16 counters (CTA b -> counter b & 15), warp 0 polls: lane i watches counter i.  The
+// arrival is a red.release.gpu, the poll an ld.acquire.gpu: with __threadfence() on both sides a barrier cost ~2.0 us, so ~1.5 (the
+// full fences drained every outstanding access of the thread; the multi-counter split alone changed nothing: the rest is arrival skew).
 #define WS_BAR_CTRS 16
 __device__ __forceinline__ void w2v_grid_barrier(unsigned *ctr, unsigned &gen) {
     __syncthreads();
     gen++;
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
-        if (lane == 0) {
-            __threadfence();
-            atomicAdd(ctr + (blockIdx.x & (WS_BAR_CTRS - 1)), 1u);
-        }
+        if (lane == 0)   // release: the CTA's writes (ordered before this by the __syncthreads above) are visible to whoever acquires the counter
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(ctr + (blockIdx.x & (WS_BAR_CTRS - 1))) : "memory");
         // CTAs that share counter i: b = i, i + 16, ... < gridDim.x
         const unsigned per = lane < WS_BAR_CTRS ? (gridDim.x - lane + WS_BAR_CTRS - 1) / WS_BAR_CTRS : 0u;
         const unsigned target = gen * per;
         bool ok;
         do {
-            ok = lane >= WS_BAR_CTRS || per == 0u || *reinterpret_cast<volatile unsigned *>(ctr + lane) >= target;
+            unsigned v = target;
+            if (lane < WS_BAR_CTRS && per != 0u) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(ctr + lane) : "memory");
+            ok = v >= target;
         } while (!__all_sync(0xffffffffu, ok));
-        __threadfence();
     }
     __syncthreads();
 }
