@@ -99,9 +99,12 @@ class MelFrontEnd:
 
     def __init__(self, engine):
         from .audio_mel import mel_filterbank
-        self.ctx = engine.ctx
+        # a context of its own (mf_wav2lip_mel_chunks needs no loaded program): the front-end runs on the ASR thread while the engine's
+        # context is used by the inference thread, and a context is single-user (include/mf_b200.h)
+        from ._lib import Context
         self.device = engine.device
-        self._lock = getattr(engine, "lock", None) or contextlib.nullcontext()   # scheduler.SharedEngine: one caller at a time per context
+        self.ctx = Context(self.device.index if self.device.index is not None else 0)
+        self._lock = contextlib.nullcontext()
         self.filters = torch.from_numpy(np.ascontiguousarray(mel_filterbank(), np.float32)).to(self.device)
         self._pin = None
         self._h2d_done = None
